@@ -1,0 +1,2 @@
+/* esl_stats.h -- Easel compat shim: everything lives in easel.h (see that file). */
+#include "easel.h"

@@ -1,0 +1,2 @@
+/* esl_vectorops.h -- Easel compat shim: everything lives in easel.h (see that file). */
+#include "easel.h"

@@ -1,0 +1,95 @@
+/* mi_glue.c -- tiny C helpers so that Python tests can drive an implementation of the
+ * reference's covariation API (corr_Create / corr_Probs / corr_Calculate* /
+ * corr_CalculateCOVCorrected over struct mutual_s and struct data_s) through ctypes without
+ * knowing struct layouts.  TEST INFRASTRUCTURE.  Compiled twice:
+ *   -DGLUE_REFERENCE : against the reference's own src/correlators.h -> oracle/_ref/librscape_ref.so
+ *   (default)        : against include/rscape_compat.h               -> r-scape_b200/librscape_b200_host.so
+ * so each library is handled with the header it was built with.
+ */
+#ifdef GLUE_REFERENCE
+#include "rscape_config.h"
+#include "easel.h"
+#include "correlators.h"
+#define MI_CLASS(mi) ((mi)->class)
+#else
+#include "rscape_compat.h"
+#include "rscape_b200_host.h"
+#define MI_CLASS(mi) ((mi)->class)
+#endif
+
+ESL_ALPHABET *glue_abc_rna(void) { static ESL_ALPHABET *abc = NULL; if (!abc) abc = esl_alphabet_Create(eslRNA); return abc; }
+
+/* residues [nseq][L] (no sentinels) -> digital ESL_MSA with ax[s][1..L] */
+ESL_MSA *
+glue_msa_create(int nseq, int L, const uint8_t *res, const double *wgt)
+{
+  ESL_MSA *msa = esl_msa_CreateDigital(glue_abc_rna(), nseq, L);
+  int      s;
+  if (!msa) return NULL;
+  for (s = 0; s < nseq; s++) {
+    memcpy(msa->ax[s] + 1, res + (size_t) s * L, (size_t) L);
+    msa->wgt[s] = wgt ? wgt[s] : 1.0;
+  }
+  return msa;
+}
+void glue_msa_destroy(ESL_MSA *msa) { esl_msa_Destroy(msa); }
+
+/* WC + GU, src/R-scape.c:883-887 */
+ESL_DMATRIX *
+glue_allowpair_default(void)
+{
+  ESL_DMATRIX *ap = esl_dmatrix_Create(4, 4);
+  esl_dmatrix_Set(ap, 0.0);
+  ap->mx[0][3] = ap->mx[3][0] = 1.0;
+  ap->mx[1][2] = ap->mx[2][1] = 1.0;
+  ap->mx[2][3] = ap->mx[3][2] = 1.0;
+  return ap;
+}
+ESL_DMATRIX *
+glue_allowpair_from(const double *v16)
+{
+  ESL_DMATRIX *ap = esl_dmatrix_Create(4, 4);
+  int i;
+  for (i = 0; i < 16; i++) ap->mx[0][i] = v16[i];
+  return ap;
+}
+
+struct data_s *
+glue_data_create(struct mutual_s *mi, ESL_DMATRIX *allowpair, int covtype, double tol)
+{
+  struct data_s *d = calloc(1, sizeof(struct data_s));
+  if (!d) return NULL;
+  d->mi        = mi;
+  d->allowpair = allowpair;
+  d->covtype   = (COVTYPE) covtype;
+  d->covmethod = NONPARAM;
+  d->mode      = RANSS;
+  d->tol       = tol;
+  d->verbose   = 0;
+  d->errbuf    = calloc(1, eslERRBUFSIZE);
+  d->bmin      = -10.0;
+  d->w         = 0.05;
+  return d;
+}
+void        glue_data_destroy(struct data_s *d) { if (d) { free(d->errbuf); free(d); } }
+const char *glue_data_errbuf(struct data_s *d)  { return d->errbuf; }
+size_t      glue_sizeof_data(void)              { return sizeof(struct data_s); }
+size_t      glue_sizeof_mutual(void)            { return sizeof(struct mutual_s); }
+
+/* flatten the state block; any pointer may be NULL */
+void
+glue_mi_export(struct mutual_s *mi, double *pp, double *pm, double *ps, double *nseff, double *ngap,
+               double *cov, double *minmax, int *type_class)
+{
+  int L = (int) mi->alen, i, j;
+  for (i = 0; i < L; i++) {
+    if (pm) memcpy(pm + (size_t) i * 4, mi->pm[i], sizeof(double) * 4);
+    if (ps) memcpy(ps + (size_t) i * 5, mi->ps[i], sizeof(double) * 5);
+    if (nseff) memcpy(nseff + (size_t) i * L, mi->nseff[i], sizeof(double) * (size_t) L);
+    if (ngap)  memcpy(ngap  + (size_t) i * L, mi->ngap[i],  sizeof(double) * (size_t) L);
+    if (cov)   memcpy(cov   + (size_t) i * L, mi->COV->mx[i], sizeof(double) * (size_t) L);
+    if (pp) for (j = 0; j < L; j++) memcpy(pp + ((size_t) i * L + j) * 16, mi->pp[i][j], sizeof(double) * 16);
+  }
+  if (minmax) { minmax[0] = mi->minCOV; minmax[1] = mi->maxCOV; }
+  if (type_class) { type_class[0] = (int) mi->type; type_class[1] = (int) MI_CLASS(mi); }
+}
