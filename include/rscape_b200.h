@@ -1,0 +1,130 @@
+/* rscape_b200.h -- C-ABI of the B200-native covariation scan (librscape_b200.so).
+ *
+ * Plain C: pointers and sizes only, no CUDA or torch types in any signature (a CUDA stream crosses
+ * as void*).  This is the layer the reference's covariation API would bind to; the functions a
+ * maintainer actually calls keep the reference's own names and signatures and live one level up in
+ * include/rscape_b200_host.h (corr_Create / corr_Probs / corr_Calculate* / corr_CalculateCOVCorrected
+ * over struct mutual_s, src/correlators.h:445-482), implemented in r-scape_b200/host/ on top of this.
+ *
+ * Each entry point names the reference code it replaces.  All return 0 on success; on failure a
+ * message is available from rsb_error() (the host layer copies it into the caller's errbuf and
+ * returns eslFAIL, the reference's error convention, src/correlators.c:72-88).
+ *
+ * There is no CPU fallback: every call needs a CUDA device of compute capability 10.x.
+ *
+ * Matrix layouts on the host side follow the reference: residues uint8 [nseq][row_stride] with the
+ * digital RNA codes A0 C1 G2 U3 gap4 N15 (ESL_MSA ax[s]+1); cov/nseff/ngap double [L][L];
+ * pp double [L][L][16]; pm double [L][4]; ps double [L][5].
+ */
+#ifndef RSCAPE_B200_INCLUDED
+#define RSCAPE_B200_INCLUDED
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rsb_ctx rsb_ctx;
+
+/* statistic = base COVTYPE (src/correlators.h:43-87), class = COVCLASS (:36-41), correction = ACTYPE (:89-92) */
+enum { RSB_STAT_CHI = 0, RSB_STAT_GT = 3, RSB_STAT_MI = 6, RSB_STAT_MIr = 9, RSB_STAT_MIg = 12, RSB_STAT_OMES = 15,
+       RSB_STAT_RAF = 18, RSB_STAT_RAFS = 21, RSB_STAT_CCF = 24 };
+enum { RSB_CLASS_C16 = 0, RSB_CLASS_C2 = 1, RSB_CLASS_CWC = 2, RSB_CLASS_CSELECT = 3 };
+enum { RSB_CORR_APC = 0, RSB_CORR_ASC = 1, RSB_CORR_NONE = 2 };
+
+/* ---- lifetime ------------------------------------------------------------------------------- */
+/* device: CUDA ordinal.  stream: a cudaStream_t to enqueue on (e.g. torch's current stream), or NULL
+ * for a stream owned by the context. */
+int         rsb_create(int device, void *stream, rsb_ctx **out);
+void        rsb_destroy(rsb_ctx *ctx);
+const char *rsb_error(const rsb_ctx *ctx);
+/* last error of a failed rsb_create (no context exists yet) */
+const char *rsb_create_error(void);
+
+/* Shape of the alignments to be scanned and how many of them are in flight at once (replicate slots).
+ * nslices: number of 8-bit weight slices S (1..6), 0 = choose from the weights (1 if they are all
+ * small integers, else 5).  Replaces corr_Create's allocations, src/correlators.c:1161-1219. */
+int rsb_configure(rsb_ctx *ctx, int nseq, int alen, int max_replicates, int nslices);
+
+/* Sequence weights (host, double[nseq]); NULL = all 1.  Quantised to fixed point wq = round(w 2^q).
+ * The same weights serve the input alignment and every null (src/R-scape.c:1668). */
+int rsb_set_weights(rsb_ctx *ctx, const double *wgt);
+/* the quantisation actually used: wq[s] (may be NULL), q, S */
+int rsb_get_quantisation(rsb_ctx *ctx, int64_t *wq, int *q, int *nslices);
+
+/* ---- one alignment: the corr_* sequence of cov_Calculate (src/covariation.c:78-258) ----------- */
+/* corr_Probs (src/correlators.c:1424): counts -> pp, nseff, ngap, ps, pm.  Host outputs may be NULL.
+ * on_device != 0: msa is a device pointer. */
+int rsb_probs(rsb_ctx *ctx, const uint8_t *msa, int64_t row_stride, int on_device, double tol,
+              double *pp, double *pm, double *ps, double *nseff, double *ngap);
+/* host copies of the state left by the last rsb_probs, without recomputing it (corr_NaivePS / corr_Marginals
+ * called on their own, src/correlators.c:1320-1375) */
+int rsb_fetch_probs(rsb_ctx *ctx, double *pp, double *pm, double *ps, double *nseff, double *ngap);
+/* corr_Calculate{CHI,OMES,GT,MI,MIr,MIg,CCF} (:50-1061) on the state left by rsb_probs, or
+ * corr_Calculate{RAF,RAFS} (:877-982) on msa (which is then required; unweighted).
+ * covclass must already be resolved (no CSELECT).  allowpair: double[16], > 0 = allowed. */
+int rsb_statistic(rsb_ctx *ctx, int stat, int covclass, const double *allowpair,
+                  const uint8_t *msa, int64_t row_stride, int on_device,
+                  double *cov, double *mincov, double *maxcov);
+/* corr_CalculateCOVCorrected (:1064-1157) on the state left by rsb_statistic */
+int rsb_correct(rsb_ctx *ctx, int actype, double *cov, double *mincov, double *maxcov);
+/* the same correction applied to a raw matrix held by the host (cov is read and overwritten): the reference
+ * corrects whatever mi->COV contains, e.g. Potts scores written on the host (src/covariation.c:100-106) */
+int rsb_correct_host(rsb_ctx *ctx, int actype, double *cov, double *mincov, double *maxcov);
+/* the three above back to back with no host round trip in between */
+int rsb_scan(rsb_ctx *ctx, const uint8_t *msa, int64_t row_stride, int on_device,
+             int stat, int covclass, int actype, const double *allowpair, double tol,
+             double *cov, double *mincov, double *maxcov,
+             double *pp, double *pm, double *ps, double *nseff, double *ngap);
+/* fixed-point counts of the last rsb_probs/rsb_scan: int64 [16][L][L], upper triangle (parity tests) */
+int rsb_get_counts(rsb_ctx *ctx, int64_t *counts);
+/* the same counts recomputed by the direct verification kernel (no tensor cores); tests only */
+int rsb_get_counts_direct(rsb_ctx *ctx, const uint8_t *msa, int64_t row_stride, int64_t *counts);
+
+/* ---- null alignments: the loop body of null_rscape (src/R-scape.c:1650-1697) ------------------- */
+/* calculate_width_histo (src/R-scape.c:1281-1371): scan one null, w = min(w_old, (max - max(bmin,min))/hpts). */
+int rsb_null_width(rsb_ctx *ctx, const uint8_t *null0, int64_t row_stride, int on_device,
+                   int stat, int covclass, int actype, const double *allowpair, double tol,
+                   double w_old, double bmin, int hpts, double *w_out, double *mincov, double *maxcov);
+/* run_rscape(RANSS) + null_add2cumranklist for nrep nulls [nrep][nseq][row_stride]: scores are added to the
+ * context's cumulative histogram (bin b = ceil((max(x,bmin+w) - bmin)/w - 1)).  minmax: double[nrep][2] or NULL. */
+int rsb_null_hist(rsb_ctx *ctx, const uint8_t *nulls, int nrep, int64_t row_stride, int64_t rep_stride, int on_device,
+                  int stat, int covclass, int actype, const double *allowpair, double tol,
+                  double w, double bmin, double *minmax);
+int rsb_hist_reset(rsb_ctx *ctx);
+/* bins[0..nb_cap), number of scores added, highest non-empty bin (-1 if none) */
+int rsb_hist_read(rsb_ctx *ctx, uint64_t *bins, int nb_cap, uint64_t *n_out, int *imax_out);
+/* nseff / ngap of the last replicate scanned (quirk Q3: what .cov prints as nseff(%), src/power.c:94-95) */
+int rsb_last_nseff(rsb_ctx *ctx, double *nseff, double *ngap);
+
+/* ---- null generators on the device --------------------------------------------------------------- */
+/* tree in Easel convention: nseq leaves, internal nodes 0..nseq-2 with parents before children,
+ * child <= 0 is leaf -child.  Stays resident for the simulators. */
+int rsb_set_tree(rsb_ctx *ctx, const int *left, const int *right, const int *parent, const double *ld, const double *rd);
+/* cov_GenerateAlignment, ungapped noss path (src/cov_simulate.c:289-324,585-631,724-773): evolve every
+ * (replicate, column) independently down the tree with P(t) = exp(tQ) (src/ratematrix.c:185-233),
+ * Philox4x32-10 keyed by (seed, replicate, column).  root: uint8[alen] residues 0..3.  gapmask: optional
+ * uint8 [nseq][alen] alignment whose non-canonical cells are copied over the result.
+ * Output: nrep nulls in the context's replicate slots [first_rep, first_rep+nrep). */
+int rsb_null_simulate(rsb_ctx *ctx, const double *Q, const uint8_t *root, const uint8_t *gapmask, int64_t gap_stride,
+                      uint64_t seed, int first_rep, int nrep);
+/* default null of R-scape: Fitch ancestral reconstruction + one column permutation + per-branch
+ * substitution re-placement (src/msatree.c:173-227,1700-1931; src/msamanip.c:1164-1233,1449-1780) */
+int rsb_null_fitch_shuffle(rsb_ctx *ctx, const uint8_t *msa, int64_t row_stride, uint64_t seed, int first_rep, int nrep);
+/* score the nulls sitting in the replicate slots (output of the two generators) */
+int rsb_null_hist_slots(rsb_ctx *ctx, int first_rep, int nrep, int stat, int covclass, int actype, const double *allowpair,
+                        double tol, double w, double bmin, double *minmax);
+/* copy replicate slots back to the host: uint8 [nrep][nseq][alen] */
+int rsb_get_slots(rsb_ctx *ctx, int first_rep, int nrep, uint8_t *out);
+
+/* ---- instrumentation ------------------------------------------------------------------------------ */
+/* kernels launched by this context so far; device milliseconds spent in the gram kernel and number of
+ * gram launches since the last call with reset != 0 (CUDA events on the context's stream). */
+int rsb_counters(rsb_ctx *ctx, int64_t *launches, double *gram_ms, int64_t *gram_launches, int reset);
+/* enable (1) / disable (0) event timing around the gram kernel */
+int rsb_profile_gram(rsb_ctx *ctx, int enable);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

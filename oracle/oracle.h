@@ -95,7 +95,7 @@ typedef struct {
   const double *ld, *rd;
 } ORC_TREE;
 
-typedef struct orc_rng_s ORC_RNG;        /* MT19937 with the shim's seeding (easel_shim.c) */
+typedef struct orc_rng_s ORC_RNG;        /* MT19937 with the shim's seeding (r-scape_b200/host/easel_shim.c) */
 ORC_RNG *orc_rng_create(uint32_t seed);
 void     orc_rng_destroy(ORC_RNG *r);
 double   orc_rng_uniform(ORC_RNG *r);

@@ -1,0 +1,247 @@
+"""rscape_b200 -- Python plumbing over the C-ABI of include/rscape_b200.h (librscape_b200.so).
+
+The product is the shared library (hand-written sm_100a kernels behind a plain C-ABI) and the C host layer
+that mirrors the reference's covariation API (librscape_b200_host.so).  This module only loads them through
+ctypes for the tests, the benchmark and multi-GPU orchestration (torch.distributed); it contains no
+arithmetic and no fallback: if the CUDA library is missing or no B200 is present, it raises.
+
+The package directory is named ``r-scape_b200`` (not importable by name); ``__graft_entry__.load_package()``
+registers it as ``rscape_b200``.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "librscape_b200.so")
+HOST_LIB_PATH = os.path.join(HERE, "librscape_b200_host.so")
+
+CHI, GT, MI, MIr, MIg, OMES, RAF, RAFS, CCF = 0, 3, 6, 9, 12, 15, 18, 21, 24
+C16, C2, CWC, CSELECT = 0, 1, 2, 3
+APC, ASC, NOCORR = 0, 1, 2
+
+_dp = C.POINTER(C.c_double)
+_u8p = C.POINTER(C.c_uint8)
+_ip = C.POINTER(C.c_int)
+_i64p = C.POINTER(C.c_int64)
+_u64p = C.POINTER(C.c_uint64)
+_vp = C.c_void_p
+
+_lib = None
+
+
+class RscapeB200Error(RuntimeError):
+    pass
+
+
+def lib():
+    """The C-ABI library.  Fails loudly when it has not been built: there is no other implementation."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RscapeB200Error(f"{LIB_PATH} is missing: run __graft_entry__.build() (make -C r-scape_b200)")
+        L = C.CDLL(LIB_PATH)
+        L.rsb_create.argtypes = [C.c_int, _vp, C.POINTER(_vp)]
+        L.rsb_destroy.argtypes = [_vp]
+        L.rsb_error.restype = C.c_char_p
+        L.rsb_error.argtypes = [_vp]
+        L.rsb_create_error.restype = C.c_char_p
+        L.rsb_configure.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.rsb_set_weights.argtypes = [_vp, _dp]
+        L.rsb_get_quantisation.argtypes = [_vp, _i64p, _ip, _ip]
+        L.rsb_probs.argtypes = [_vp, _vp, C.c_int64, C.c_int, C.c_double, _dp, _dp, _dp, _dp, _dp]
+        L.rsb_fetch_probs.argtypes = [_vp, _dp, _dp, _dp, _dp, _dp]
+        L.rsb_statistic.argtypes = [_vp, C.c_int, C.c_int, _dp, _vp, C.c_int64, C.c_int, _dp, _dp, _dp]
+        L.rsb_correct.argtypes = [_vp, C.c_int, _dp, _dp, _dp]
+        L.rsb_correct_host.argtypes = [_vp, C.c_int, _dp, _dp, _dp]
+        L.rsb_scan.argtypes = [_vp, _vp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.c_double,
+                               _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp]
+        L.rsb_get_counts.argtypes = [_vp, _i64p]
+        L.rsb_get_counts_direct.argtypes = [_vp, _vp, C.c_int64, _i64p]
+        L.rsb_null_width.argtypes = [_vp, _vp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.c_double,
+                                     C.c_double, C.c_double, C.c_int, _dp, _dp, _dp]
+        L.rsb_null_hist.argtypes = [_vp, _vp, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, _dp,
+                                    C.c_double, C.c_double, C.c_double, _dp]
+        L.rsb_null_hist_slots.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.c_double, C.c_double,
+                                          C.c_double, _dp]
+        L.rsb_hist_reset.argtypes = [_vp]
+        L.rsb_hist_read.argtypes = [_vp, _u64p, C.c_int, _u64p, _ip]
+        L.rsb_last_nseff.argtypes = [_vp, _dp, _dp]
+        L.rsb_set_tree.argtypes = [_vp, _ip, _ip, _ip, _dp, _dp]
+        L.rsb_null_simulate.argtypes = [_vp, _dp, _u8p, _u8p, C.c_int64, C.c_uint64, C.c_int, C.c_int]
+        L.rsb_null_fitch_shuffle.argtypes = [_vp, _u8p, C.c_int64, C.c_uint64, C.c_int, C.c_int]
+        L.rsb_get_slots.argtypes = [_vp, C.c_int, C.c_int, _u8p]
+        L.rsb_counters.argtypes = [_vp, _i64p, _dp, _i64p, C.c_int]
+        L.rsb_profile_gram.argtypes = [_vp, C.c_int]
+        _lib = L
+    return _lib
+
+
+def _d(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+def _ptr(x):
+    """(pointer, on_device) of a numpy array or a torch CUDA tensor."""
+    if isinstance(x, np.ndarray):
+        return x.ctypes.data_as(_vp), 0
+    return C.c_void_p(x.data_ptr()), (1 if x.is_cuda else 0)
+
+
+class Context:
+    """One device + one stream.  Mirrors the C-ABI one to one; numpy in, numpy out."""
+
+    def __init__(self, device=0, stream=None):
+        self._h = _vp()
+        self.N = self.L = 0
+        L = lib()
+        if L.rsb_create(device, _vp(stream) if stream else None, C.byref(self._h)) != 0:
+            raise RscapeB200Error(L.rsb_create_error().decode())
+
+    def close(self):
+        if self._h:
+            lib().rsb_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise RscapeB200Error(lib().rsb_error(self._h).decode())
+
+    # ---- configuration ------------------------------------------------------------------------
+    def configure(self, nseq, alen, max_replicates=1, nslices=0):
+        self._ck(lib().rsb_configure(self._h, nseq, alen, max_replicates, nslices))
+        self.N, self.L, self.R = nseq, alen, max_replicates
+
+    def set_weights(self, wgt=None):
+        w = None if wgt is None else np.ascontiguousarray(wgt, dtype=np.float64)
+        self._ck(lib().rsb_set_weights(self._h, _d(w)))
+
+    def quantisation(self):
+        wq = np.zeros(self.N, dtype=np.int64)
+        q, S = C.c_int(), C.c_int()
+        self._ck(lib().rsb_get_quantisation(self._h, wq.ctypes.data_as(_i64p), C.byref(q), C.byref(S)))
+        return wq, q.value, S.value
+
+    # ---- one alignment ------------------------------------------------------------------------
+    def _msa(self, msa):
+        if isinstance(msa, np.ndarray):
+            msa = np.ascontiguousarray(msa, dtype=np.uint8)
+            assert msa.shape == (self.N, self.L), (msa.shape, self.N, self.L)
+        return msa
+
+    def scan(self, msa, stat=GT, covclass=C16, actype=APC, allowpair=None, tol=1e-6, want_cov=True, want_probs=False):
+        msa = self._msa(msa)
+        p, dev = _ptr(msa)
+        L = self.L
+        ap = None if allowpair is None else np.ascontiguousarray(allowpair, dtype=np.float64)
+        out = dict(cov=np.empty((L, L)) if want_cov else None, pp=None, pm=None, ps=None, nseff=None, ngap=None)
+        if want_probs:
+            out.update(pp=np.empty((L, L, 16)), pm=np.empty((L, 4)), ps=np.empty((L, 5)), nseff=np.empty((L, L)), ngap=np.empty((L, L)))
+        mn, mx = C.c_double(), C.c_double()
+        self._ck(lib().rsb_scan(self._h, p, L, dev, stat, covclass, actype, _d(ap), tol, _d(out["cov"]), C.byref(mn), C.byref(mx),
+                                _d(out["pp"]), _d(out["pm"]), _d(out["ps"]), _d(out["nseff"]), _d(out["ngap"])))
+        out.update(mincov=mn.value, maxcov=mx.value)
+        return out
+
+    def counts(self):
+        out = np.empty((16, self.L, self.L), dtype=np.int64)
+        self._ck(lib().rsb_get_counts(self._h, out.ctypes.data_as(_i64p)))
+        return out
+
+    def counts_direct(self, msa):
+        msa = self._msa(msa)
+        out = np.empty((16, self.L, self.L), dtype=np.int64)
+        self._ck(lib().rsb_get_counts_direct(self._h, msa.ctypes.data_as(_vp), self.L, out.ctypes.data_as(_i64p)))
+        return out
+
+    # ---- nulls --------------------------------------------------------------------------------
+    def null_width(self, null0, stat=GT, covclass=C16, actype=APC, allowpair=None, tol=1e-6, w_old=0.05, bmin=-10.0, hpts=400):
+        ap = None if allowpair is None else np.ascontiguousarray(allowpair, dtype=np.float64)
+        if null0 is None:
+            p, dev = None, 0
+        else:
+            null0 = self._msa(null0)
+            p, dev = _ptr(null0)
+        w, mn, mx = C.c_double(), C.c_double(), C.c_double()
+        self._ck(lib().rsb_null_width(self._h, p, self.L, dev, stat, covclass, actype, _d(ap), tol, w_old, bmin, hpts,
+                                      C.byref(w), C.byref(mn), C.byref(mx)))
+        return w.value, mn.value, mx.value
+
+    def null_hist(self, nulls, w, stat=GT, covclass=C16, actype=APC, allowpair=None, tol=1e-6, bmin=-10.0, want_minmax=True):
+        """nulls: uint8 [R][N][L], numpy (host) or torch CUDA tensor (device)."""
+        ap = None if allowpair is None else np.ascontiguousarray(allowpair, dtype=np.float64)
+        if isinstance(nulls, np.ndarray):
+            nulls = np.ascontiguousarray(nulls, dtype=np.uint8)
+        R = nulls.shape[0]
+        assert tuple(nulls.shape[1:]) == (self.N, self.L)
+        p, dev = _ptr(nulls)
+        mm = np.empty((R, 2)) if want_minmax else None
+        self._ck(lib().rsb_null_hist(self._h, p, R, self.L, self.N * self.L, dev, stat, covclass, actype, _d(ap), tol, w, bmin, _d(mm)))
+        return mm
+
+    def null_hist_slots(self, nrep, w, stat=GT, covclass=C16, actype=APC, allowpair=None, tol=1e-6, bmin=-10.0):
+        ap = None if allowpair is None else np.ascontiguousarray(allowpair, dtype=np.float64)
+        mm = np.empty((nrep, 2))
+        self._ck(lib().rsb_null_hist_slots(self._h, 0, nrep, stat, covclass, actype, _d(ap), tol, w, bmin, _d(mm)))
+        return mm
+
+    def hist_reset(self):
+        self._ck(lib().rsb_hist_reset(self._h))
+
+    def hist_read(self, nb):
+        bins = np.zeros(nb, dtype=np.uint64)
+        n, imax = C.c_uint64(), C.c_int()
+        self._ck(lib().rsb_hist_read(self._h, bins.ctypes.data_as(_u64p), nb, C.byref(n), C.byref(imax)))
+        return bins, n.value, imax.value
+
+    def last_nseff(self):
+        ne, ng = np.empty((self.L, self.L)), np.empty((self.L, self.L))
+        self._ck(lib().rsb_last_nseff(self._h, _d(ne), _d(ng)))
+        return ne, ng
+
+    # ---- generators ---------------------------------------------------------------------------
+    def set_tree(self, left, right, parent, ld, rd):
+        a = [np.ascontiguousarray(x, dtype=np.int32) for x in (left, right, parent)]
+        b = [np.ascontiguousarray(x, dtype=np.float64) for x in (ld, rd)]
+        self._ck(lib().rsb_set_tree(self._h, a[0].ctypes.data_as(_ip), a[1].ctypes.data_as(_ip), a[2].ctypes.data_as(_ip), _d(b[0]), _d(b[1])))
+
+    def null_simulate(self, Q, root, seed, nrep, gapmask=None, first_rep=0):
+        Q = np.ascontiguousarray(Q, dtype=np.float64)
+        root = np.ascontiguousarray(root, dtype=np.uint8)
+        gm = None if gapmask is None else np.ascontiguousarray(gapmask, dtype=np.uint8)
+        self._ck(lib().rsb_null_simulate(self._h, _d(Q), root.ctypes.data_as(_u8p), None if gm is None else gm.ctypes.data_as(_u8p),
+                                         self.L, seed, first_rep, nrep))
+
+    def null_fitch_shuffle(self, msa, seed, nrep, first_rep=0):
+        msa = self._msa(msa)
+        self._ck(lib().rsb_null_fitch_shuffle(self._h, msa.ctypes.data_as(_u8p), self.L, seed, first_rep, nrep))
+
+    def get_slots(self, nrep, first_rep=0):
+        out = np.empty((nrep, self.N, self.L), dtype=np.uint8)
+        self._ck(lib().rsb_get_slots(self._h, first_rep, nrep, out.ctypes.data_as(_u8p)))
+        return out
+
+    # ---- instrumentation ------------------------------------------------------------------------
+    def profile_gram(self, enable=True):
+        self._ck(lib().rsb_profile_gram(self._h, 1 if enable else 0))
+
+    def counters(self, reset=False):
+        a, b, c = C.c_int64(), C.c_double(), C.c_int64()
+        self._ck(lib().rsb_counters(self._h, C.byref(a), C.byref(b), C.byref(c), 1 if reset else 0))
+        return dict(launches=a.value, gram_ms=b.value, gram_launches=c.value)
+
+
+def replicate_slots(nseq, alen, nnull, nslices=5, budget_bytes=24e9, sm_count=148):
+    """How many null replicates to keep in flight: enough tiles for every SM, bounded by HBM use."""
+    cj = {1: 64, 2: 32, 3: 20, 4: 16, 5: 12, 6: 10}[nslices]
+    tiles = (alen / 32.0) * (alen / cj) * 0.5 + 1.0
+    per_rep = (4 + 4 * nslices) * alen * nseq + 16 * 8 * alen * alen + 3 * 8 * alen * alen + nseq * alen
+    r = int(np.ceil(4.0 * sm_count / tiles))
+    return int(max(1, min(r, int(budget_bytes // per_rep), nnull, 64)))

@@ -1,0 +1,893 @@
+// capi.cu -- the C-ABI of include/rscape_b200.h: context, buffers in HBM, TMA descriptors, kernel sequencing.
+//
+// One context = one CUDA device + one stream.  All work is enqueued asynchronously on that stream;
+// the only host synchronisations are the D2H reads the caller asked for.  There is no CPU path:
+// rsb_create fails unless a compute-capability-10.x device is present.
+#include "rsb_common.cuh"
+#include "../../include/rscape_b200.h"
+#include <cstdarg>
+#include <cstring>
+#include <cmath>
+#include <vector>
+#include <string>
+#include <algorithm>
+
+// ---- kernel launchers defined in the other translation units
+cudaError_t rsb_launch_gram_i8(int S, const CUtensorMap &tmA, const CUtensorMap &tmB, const int2 *tiles, int ntiles,
+                               int nrep, int L, int Lp, int kstages, long long *cnt, int grid, cudaStream_t st);
+cudaError_t rsb_launch_pack(int S, const uint8_t *res, int nrep, int N, int L, long long rep_stride_res, const uint8_t *wdig,
+                            int Kpad, uint8_t *planeA, int MA, uint8_t *planeB, int NBrows, int Lcover, cudaStream_t st);
+cudaError_t rsb_launch_colsum(const uint8_t *res, int N, int L, const unsigned long long *wq, unsigned long long *colsum, cudaStream_t st);
+cudaError_t rsb_launch_counts_direct(const uint8_t *res, int N, int L, int Lp, const unsigned long long *wq, long long *cnt, cudaStream_t st);
+void        rsb_stat_grid(int L, int *nJT, int *nIT);
+cudaError_t rsb_launch_marginals(const long long *cnt, int nrep, int L, int Lp, double scale, long long wtot, double tol,
+                                 double *rowpart, double *colpart, double *nseff, double *pm, int *flags, cudaStream_t st);
+cudaError_t rsb_launch_statistic(int stat, int cls, const long long *cnt, const double *pm, int nrep, int L, int Lp, double scale,
+                                 long long wtot, unsigned mask, double *cov, double *rowpart, double *colpart, double *mm, cudaStream_t st);
+cudaError_t rsb_launch_raf(const long long *cnt, int nrep, int L, int Lp, int nseq, unsigned mask, int smooth, double *tmp, double *cov,
+                           double *rowpart, double *colpart, double *mm, cudaStream_t st);
+cudaError_t rsb_launch_ccf(const double *nseff, const double *pm, int nrep, int L, int Lp, double *part, double *meanp, double *cov,
+                           double *rowpart, double *colpart, double *mm, cudaStream_t st);
+cudaError_t rsb_launch_reduce_cov(const double *cov, int nrep, int L, int Lp, double *rowpart, double *colpart, double *mm, cudaStream_t st);
+cudaError_t rsb_launch_export_probs(const long long *cnt, int L, int Lp, double scale, long long wtot, double *pp, double *nseff,
+                                    double *ngap, cudaStream_t st);
+cudaError_t rsb_launch_ps(const unsigned long long *colsum, int L, double scale, double *ps, cudaStream_t st);
+cudaError_t rsb_launch_correct_final(const double *rowpart, const double *colpart, const double *mm, int nrep, int L,
+                                     double *covx, double *scal, cudaStream_t st);
+cudaError_t rsb_launch_correct_hist(double *cov, const double *covx, const double *scal, int nrep, int L, int Lp, int actype, int mode,
+                                    double bmin, const double *wptr, unsigned long long *hist, int nbins, double *mm, double *minmax_out,
+                                    int *flags, cudaStream_t st);
+cudaError_t rsb_launch_width(const double *minmax, double w_old, double bmin, int hpts, double tol, double *wout, cudaStream_t st);
+cudaError_t rsb_launch_symmetrize(double *cov, int L, int Lp, cudaStream_t st);
+cudaError_t rsb_launch_null_simulate(const int *left, const int *right, const double *pcdf, int N, int L, const uint8_t *root,
+                                     const uint8_t *gapmask, long long gap_stride, unsigned long long seed, int first_rep, int nrep,
+                                     uint8_t *res, uint8_t *scratch, cudaStream_t st);
+cudaError_t rsb_launch_fitch_shuffle(const int *left, const int *right, const int *parent, const int *order, const int *level_start,
+                                     int nlevels, int N, int L, const uint8_t *msa, unsigned long long seed, int first_rep, int nrep,
+                                     uint8_t *res, uint8_t *anc, uint8_t *shanc, int *perm, cudaStream_t st);
+
+namespace {
+constexpr int HIST_BINS = 1 << 22;
+
+// operand geometry for one slice count
+struct Geo {
+  int S = 0, CJ = 0, NT = 0, nJB = 0, NBrows = 0, ntiles = 0, q = 0;
+  CUtensorMap tmB;
+  int2 *d_tiles = nullptr;
+  uint8_t *d_wdig = nullptr;
+  unsigned long long *d_wq = nullptr;
+  std::vector<long long> wq;
+  double scale = 1.0;
+  long long wtot = 0;
+  bool ready = false;
+};
+} // namespace
+
+struct rsb_ctx {
+  int device = 0, sm_count = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  char err[512] = { 0 };
+
+  int N = 0, L = 0, Lp = 0, Kpad = 0, MA = 0, nIB = 0, Rcap = 0, Sreq = 0, Lcover = 0;
+  size_t planeB_rows_cap = 0;
+  Geo geo[2];                         // [0] weighted, [1] unit weights (RAF/RAFS)
+  int cur_geo = 0;                    // geometry of the counts currently in d_cnt
+  int last_slot = 0;                  // replicate slot scanned last (quirk Q3)
+  CUtensorMap tmA;
+  std::vector<double> wgt;
+
+  uint8_t *d_res = nullptr, *d_planeA = nullptr, *d_planeB = nullptr;
+  long long *d_cnt = nullptr;
+  double *d_nseff = nullptr, *d_pm = nullptr, *d_cov = nullptr, *d_tmp = nullptr;
+  double *d_rowpart = nullptr, *d_colpart = nullptr, *d_mm = nullptr, *d_scal = nullptr, *d_covx = nullptr, *d_minmax = nullptr;
+  double *d_meanp = nullptr, *d_w = nullptr;
+  unsigned long long *d_hist = nullptr, *d_colsum = nullptr;
+  int *d_flags = nullptr;
+  double *d_ps = nullptr, *d_pp_out = nullptr, *d_nseff_out = nullptr, *d_ngap_out = nullptr;
+  // tree + simulators
+  int *d_left = nullptr, *d_right = nullptr, *d_parent = nullptr, *d_order = nullptr, *d_level_start = nullptr, *d_perm = nullptr;
+  int nlevels = 0;
+  std::vector<int> h_left, h_right, h_parent;
+  std::vector<double> h_ld, h_rd;
+  double *d_pcdf = nullptr;
+  std::vector<int> h_level_start;
+  uint8_t *d_root = nullptr, *d_gapmask = nullptr, *d_simscratch = nullptr, *d_msa0 = nullptr, *d_anc = nullptr, *d_shanc = nullptr;
+  bool have_tree = false;
+
+  unsigned long long hist_n = 0;
+  long long launches = 0, gram_launches = 0;
+  double gram_ms = 0.0;
+  bool profile = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+};
+
+void rsb_set_error(rsb_ctx *ctx, const char *fmt, ...)
+{
+  if (!ctx) return;
+  va_list ap; va_start(ap, fmt);
+  vsnprintf(ctx->err, sizeof(ctx->err), fmt, ap);
+  va_end(ap);
+}
+
+namespace {
+char g_create_err[512] = "";
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_fn()
+{
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn) p;
+  }
+  return fn;
+}
+
+// 3-D u8 tensor map {Kpad (contiguous), rows, replicates}, box {128, box_rows, 1}, 128-byte swizzle
+int make_plane_map(rsb_ctx *ctx, CUtensorMap *tm, void *base, int Kpad, size_t rows, int reps, int box_rows)
+{
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { rsb_set_error(ctx, "cuTensorMapEncodeTiled entry point not available"); return 1; }
+  cuuint64_t dims[3]    = { (cuuint64_t) Kpad, (cuuint64_t) rows, (cuuint64_t) reps };
+  cuuint64_t strides[2] = { (cuuint64_t) Kpad, (cuuint64_t) Kpad * rows };
+  cuuint32_t box[3]     = { (cuuint32_t) RSB_KSTAGE, (cuuint32_t) box_rows, 1 };
+  cuuint32_t estr[3]    = { 1, 1, 1 };
+  CUresult rc = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) { rsb_set_error(ctx, "cuTensorMapEncodeTiled failed with CUresult %d", (int) rc); return 1; }
+  return 0;
+}
+
+template <class T> void dfree(T *&p) { if (p) { cudaFree(p); p = nullptr; } }
+
+void free_geo(Geo &g) { dfree(g.d_tiles); dfree(g.d_wdig); dfree(g.d_wq); g.ready = false; }
+
+void free_plan(rsb_ctx *c)
+{
+  free_geo(c->geo[0]); free_geo(c->geo[1]);
+  dfree(c->d_res); dfree(c->d_planeA); dfree(c->d_planeB); dfree(c->d_cnt); dfree(c->d_nseff); dfree(c->d_pm); dfree(c->d_cov);
+  dfree(c->d_tmp); dfree(c->d_rowpart); dfree(c->d_colpart); dfree(c->d_mm); dfree(c->d_scal); dfree(c->d_covx); dfree(c->d_minmax);
+  dfree(c->d_meanp); dfree(c->d_w); dfree(c->d_hist); dfree(c->d_colsum); dfree(c->d_flags); dfree(c->d_ps); dfree(c->d_pp_out);
+  dfree(c->d_nseff_out); dfree(c->d_ngap_out); dfree(c->d_left); dfree(c->d_right); dfree(c->d_parent); dfree(c->d_order);
+  dfree(c->d_level_start); dfree(c->d_perm); dfree(c->d_pcdf); dfree(c->d_root); dfree(c->d_gapmask); dfree(c->d_simscratch);
+  dfree(c->d_msa0); dfree(c->d_anc); dfree(c->d_shanc);
+  c->have_tree = false;
+}
+
+// tiles (ib, jb) of the upper triangle, jb-major so that concurrently running CTAs share planeB rows in L2
+int build_geo(rsb_ctx *ctx, Geo &g, int S)
+{
+  g.S  = S;
+  g.CJ = rsb_cj_for(S);
+  g.NT = 4 * S * g.CJ;
+  g.nJB = (ctx->L + g.CJ - 1) / g.CJ;
+  g.NBrows = g.nJB * g.NT;
+  if ((size_t) g.NBrows > ctx->planeB_rows_cap) { rsb_set_error(ctx, "internal: planeB capacity"); return 1; }
+  std::vector<int2> tiles;
+  for (int jb = 0; jb < g.nJB; jb++) {
+    const int maxj = std::min(jb * g.CJ + g.CJ - 1, ctx->L - 1);
+    for (int ib = 0; ib < ctx->nIB; ib++)
+      if (ib * RSB_ICOLS < maxj) tiles.push_back(make_int2(ib, jb));
+  }
+  g.ntiles = (int) tiles.size();
+  dfree(g.d_tiles);
+  if (g.ntiles > 0) {
+    RSB_CUDA_OK(cudaMalloc(&g.d_tiles, sizeof(int2) * tiles.size()));
+    RSB_CUDA_OK(cudaMemcpyAsync(g.d_tiles, tiles.data(), sizeof(int2) * tiles.size(), cudaMemcpyHostToDevice, ctx->stream));
+    RSB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  }
+  if (make_plane_map(ctx, &g.tmB, ctx->d_planeB, ctx->Kpad, (size_t) g.NBrows, ctx->Rcap, g.NT)) return 1;
+  dfree(g.d_wdig); dfree(g.d_wq);
+  RSB_CUDA_OK(cudaMalloc(&g.d_wdig, (size_t) S * ctx->Kpad));
+  RSB_CUDA_OK(cudaMalloc(&g.d_wq, sizeof(unsigned long long) * ctx->N));
+  return 0;
+}
+
+// fixed-point weights: wq = round(w 2^q) < 256^S, digits base 256
+int quantise(rsb_ctx *ctx, Geo &g, const std::vector<double> &w, bool unit)
+{
+  const int N = ctx->N, S = g.S;
+  g.wq.assign(N, 1);
+  g.q = 0;
+  if (!unit) {
+    double maxw = 0.0;
+    for (int s = 0; s < N; s++) {
+      if (!(w[s] >= 0.0) || !std::isfinite(w[s])) { rsb_set_error(ctx, "sequence weight %d is negative or not finite", s); return 1; }
+      maxw = std::max(maxw, w[s]);
+    }
+    bool small_int = true;
+    for (int s = 0; s < N && small_int; s++) small_int = (w[s] == std::floor(w[s]) && w[s] <= 255.0);
+    if (small_int && S == 1) g.q = 0;
+    else if (maxw > 0.0) {
+      int e; std::frexp(maxw, &e);                     // maxw < 2^e
+      g.q = 8 * S - e;
+      for (;;) {
+        bool ok = true;
+        for (int s = 0; s < N && ok; s++) ok = std::llround(std::ldexp(w[s], g.q)) < (1LL << (8 * S));
+        if (ok) break;
+        g.q--;
+      }
+    }
+    for (int s = 0; s < N; s++) g.wq[s] = std::llround(std::ldexp(w[s], g.q));
+  }
+  int nbits = 0; while ((1LL << nbits) < (long long) N + 1) nbits++;
+  if (8 * S + nbits > 63) { rsb_set_error(ctx, "%d weight slices with %d sequences overflow the 63-bit count (use fewer slices)", S, N); return 1; }
+  g.scale = std::ldexp(1.0, -g.q);
+  g.wtot = 0;
+  std::vector<uint8_t> dig((size_t) S * ctx->Kpad, 0);
+  for (int s = 0; s < N; s++) {
+    g.wtot += g.wq[s];
+    for (int k = 0; k < S; k++) dig[(size_t) k * ctx->Kpad + s] = (uint8_t) ((g.wq[s] >> (8 * k)) & 0xFF);
+  }
+  RSB_CUDA_OK(cudaMemcpyAsync(g.d_wdig, dig.data(), dig.size(), cudaMemcpyHostToDevice, ctx->stream));
+  RSB_CUDA_OK(cudaMemcpyAsync(g.d_wq, g.wq.data(), sizeof(long long) * N, cudaMemcpyHostToDevice, ctx->stream));
+  RSB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  g.ready = true;
+  return 0;
+}
+
+int ensure_geo(rsb_ctx *ctx, int which)
+{
+  Geo &g = ctx->geo[which];
+  if (g.ready) return 0;
+  if (which == 1) {
+    if (build_geo(ctx, g, 1)) return 1;
+    return quantise(ctx, g, ctx->wgt, true);
+  }
+  rsb_set_error(ctx, "rsb_set_weights has not been called");
+  return 1;
+}
+
+unsigned allow_mask(const double *allowpair)
+{
+  // default WC + GU (src/R-scape.c:883-887)
+  static const double dflt[16] = { 0, 0, 0, 1,  0, 0, 1, 0,  0, 1, 0, 1,  1, 0, 1, 0 };
+  const double *ap = allowpair ? allowpair : dflt;
+  unsigned m = 0;
+  for (int k = 0; k < 16; k++) if (ap[k] > 0.0) m |= 1u << k;
+  return m;
+}
+
+int upload_msa(rsb_ctx *ctx, const uint8_t *msa, int64_t row_stride, int64_t rep_stride, int nrep, int first_slot, int on_device)
+{
+  const size_t repbytes = (size_t) ctx->N * ctx->L;
+  if (first_slot + nrep > ctx->Rcap) { rsb_set_error(ctx, "%d replicates exceed the configured %d slots", first_slot + nrep, ctx->Rcap); return 1; }
+  for (int r = 0; r < nrep; r++) {
+    const uint8_t *src = msa + (size_t) r * rep_stride;
+    RSB_CUDA_OK(cudaMemcpy2DAsync(ctx->d_res + (size_t) (first_slot + r) * repbytes, ctx->L, src, (size_t) row_stride, ctx->L, ctx->N,
+                                  on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+  }
+  return 0;
+}
+
+// pack + gram for replicate slots [0, nrep) with geometry `which`
+int run_counts(rsb_ctx *ctx, int which, int nrep)
+{
+  if (ensure_geo(ctx, which)) return 1;
+  Geo &g = ctx->geo[which];
+  RSB_CUDA_OK(rsb_launch_pack(g.S, ctx->d_res, nrep, ctx->N, ctx->L, (long long) ctx->N * ctx->L, g.d_wdig, ctx->Kpad,
+                              ctx->d_planeA, ctx->MA, ctx->d_planeB, g.NBrows, ctx->Lcover, ctx->stream));
+  ctx->launches++;
+  if (g.ntiles > 0) {
+    const long long work = (long long) g.ntiles * nrep;
+    const int grid = (int) std::min<long long>(work, ctx->sm_count);
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (ctx->profile) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, ctx->stream); }
+    RSB_CUDA_OK(rsb_launch_gram_i8(g.S, ctx->tmA, g.tmB, g.d_tiles, g.ntiles, nrep, ctx->L, ctx->Lp, ctx->Kpad / RSB_KSTAGE,
+                                   ctx->d_cnt, grid, ctx->stream));
+    if (ctx->profile) { cudaEventRecord(e1, ctx->stream); ctx->pending.push_back({ e0, e1 }); }
+    ctx->launches++;
+    ctx->gram_launches++;
+  }
+  ctx->cur_geo = which;
+  ctx->last_slot = nrep - 1;
+  return 0;
+}
+
+int check_flags(rsb_ctx *ctx, const char *what)
+{
+  int f = 0;
+  RSB_CUDA_OK(cudaMemcpyAsync(&f, ctx->d_flags, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  RSB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  if (f) {
+    RSB_CUDA_OK(cudaMemsetAsync(ctx->d_flags, 0, sizeof(int), ctx->stream));
+    if (f & 1) { rsb_set_error(ctx, "%s: pm validation failed", what); return 1; }           // corr_Marginals / corr_ValidateProbs
+    if (f & 2) { rsb_set_error(ctx, "%s: bad covariation (NaN)", what); return 1; }          // correlators.c:1124
+    if (f & 4) { rsb_set_error(ctx, "%s: score histogram capacity (%d bins) exceeded", what, HIST_BINS); return 1; }
+  }
+  return 0;
+}
+
+int resolve_stat(rsb_ctx *ctx, int stat, int covclass)
+{
+  if (covclass == RSB_CSELECT) { rsb_set_error(ctx, "covclass must be resolved by the caller (CSELECT rule, correlators.c:336)"); return 1; }
+  switch (stat) {
+  case RSB_GT: if (covclass == RSB_C16 || covclass == RSB_C2 || covclass == RSB_CWC) return 0; break;
+  case RSB_CHI: case RSB_OMES: case RSB_MI: case RSB_MIr: case RSB_MIg:
+    if (covclass == RSB_C16 || covclass == RSB_C2) return 0;
+    rsb_set_error(ctx, "CWC not implemented for this statistic"); return 1;                   // e.g. correlators.c:72
+  case RSB_RAF: case RSB_RAFS: case RSB_CCF: return 0;
+  }
+  rsb_set_error(ctx, "wrong covariation type %d / class %d", stat, covclass);
+  return 1;
+}
+
+// statistic on the counts of slots [0,nrep); leaves raw cov + correction partials
+int run_statistic(rsb_ctx *ctx, int nrep, int stat, int covclass, unsigned mask)
+{
+  Geo &g = ctx->geo[ctx->cur_geo];
+  if (stat == RSB_RAF || stat == RSB_RAFS) {
+    if (ctx->cur_geo != 1) { rsb_set_error(ctx, "internal: RAF needs unit-weight counts"); return 1; }
+    RSB_CUDA_OK(rsb_launch_raf(ctx->d_cnt, nrep, ctx->L, ctx->Lp, ctx->N, mask, stat == RSB_RAFS, ctx->d_tmp, ctx->d_cov,
+                               ctx->d_rowpart, ctx->d_colpart, ctx->d_mm, ctx->stream));
+    ctx->launches += (stat == RSB_RAFS) ? 3 : 2;
+  } else if (stat == RSB_CCF) {
+    RSB_CUDA_OK(rsb_launch_ccf(ctx->d_nseff, ctx->d_pm, nrep, ctx->L, ctx->Lp, ctx->d_tmp, ctx->d_meanp, ctx->d_cov,
+                               ctx->d_rowpart, ctx->d_colpart, ctx->d_mm, ctx->stream));
+    ctx->launches += 4;
+  } else {
+    RSB_CUDA_OK(rsb_launch_statistic(stat, covclass, ctx->d_cnt, ctx->d_pm, nrep, ctx->L, ctx->Lp, g.scale, g.wtot, mask,
+                                     ctx->d_cov, ctx->d_rowpart, ctx->d_colpart, ctx->d_mm, ctx->stream));
+    ctx->launches++;
+  }
+  RSB_CUDA_OK(rsb_launch_correct_final(ctx->d_rowpart, ctx->d_colpart, ctx->d_mm, nrep, ctx->L, ctx->d_covx, ctx->d_scal, ctx->stream));
+  ctx->launches++;
+  return 0;
+}
+
+int run_probs(rsb_ctx *ctx, int nrep, double tol)
+{
+  Geo &g = ctx->geo[0];
+  if (run_counts(ctx, 0, nrep)) return 1;
+  RSB_CUDA_OK(rsb_launch_marginals(ctx->d_cnt, nrep, ctx->L, ctx->Lp, g.scale, g.wtot, tol, ctx->d_rowpart, ctx->d_colpart,
+                                   ctx->d_nseff, ctx->d_pm, ctx->d_flags, ctx->stream));
+  ctx->launches += 2;
+  return 0;
+}
+
+// full pipeline on slots [0,nrep): counts -> (marginals) -> statistic -> correction partials
+int run_pipeline(rsb_ctx *ctx, int nrep, int stat, int covclass, unsigned mask, double tol)
+{
+  if (stat == RSB_RAF || stat == RSB_RAFS) { if (run_counts(ctx, 1, nrep)) return 1; }
+  else if (run_probs(ctx, nrep, tol)) return 1;
+  return run_statistic(ctx, nrep, stat, covclass, mask);
+}
+
+int copy_matrix_out(rsb_ctx *ctx, const double *dsrc, double *hdst)   // [L][Lp] device -> [L][L] host
+{
+  RSB_CUDA_OK(cudaMemcpy2DAsync(hdst, sizeof(double) * ctx->L, dsrc, sizeof(double) * ctx->Lp, sizeof(double) * ctx->L, ctx->L,
+                                cudaMemcpyDeviceToHost, ctx->stream));
+  return 0;
+}
+
+} // namespace
+
+// =============================================================================================== C-ABI
+extern "C" {
+
+const char *rsb_create_error(void) { return g_create_err; }
+const char *rsb_error(const rsb_ctx *ctx) { return ctx ? ctx->err : g_create_err; }
+
+int rsb_create(int device, void *stream, rsb_ctx **out)
+{
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    snprintf(g_create_err, sizeof(g_create_err), "no CUDA device available (%s); librscape_b200 has no CPU fallback",
+             e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    return 1;
+  }
+  if (device < 0 || device >= ndev) { snprintf(g_create_err, sizeof(g_create_err), "device %d out of range (%d devices)", device, ndev); return 1; }
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { snprintf(g_create_err, sizeof(g_create_err), "%s", cudaGetErrorString(e)); return 1; }
+  if (prop.major != 10) {
+    snprintf(g_create_err, sizeof(g_create_err), "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+    return 1;
+  }
+  if ((e = cudaSetDevice(device)) != cudaSuccess) { snprintf(g_create_err, sizeof(g_create_err), "%s", cudaGetErrorString(e)); return 1; }
+  rsb_ctx *c = new rsb_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  if (stream) c->stream = (cudaStream_t) stream;
+  else { cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking); c->own_stream = true; }
+  *out = c;
+  return 0;
+}
+
+void rsb_destroy(rsb_ctx *ctx)
+{
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto &p : ctx->pending) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+  free_plan(ctx);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int rsb_configure(rsb_ctx *ctx, int nseq, int alen, int max_replicates, int nslices)
+{
+  if (nseq < 1 || alen < 1 || max_replicates < 1 || nslices < 0 || nslices > RSB_MAX_SLICES) { rsb_set_error(ctx, "bad configuration"); return 1; }
+  RSB_CUDA_OK(cudaSetDevice(ctx->device));
+  RSB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  free_plan(ctx);
+  ctx->N = nseq; ctx->L = alen; ctx->Rcap = max_replicates; ctx->Sreq = nslices;
+  ctx->Lp   = (alen + 3) & ~3;
+  ctx->Kpad = (nseq + RSB_KSTAGE - 1) / RSB_KSTAGE * RSB_KSTAGE;
+  ctx->nIB  = (alen + RSB_ICOLS - 1) / RSB_ICOLS;
+  ctx->MA   = ctx->nIB * RSB_MTILE;
+  // planeB must hold the widest geometry (any S in 1..6); rows = nJB * NT
+  size_t rows_cap = 0; int lcover = ctx->nIB * RSB_ICOLS;
+  for (int S = 1; S <= RSB_MAX_SLICES; S++) {
+    if (nslices && S != nslices && S != 1) continue;
+    const int CJ = rsb_cj_for(S), nJB = (alen + CJ - 1) / CJ;
+    rows_cap = std::max(rows_cap, (size_t) nJB * 4 * S * CJ);
+    lcover = std::max(lcover, nJB * CJ);
+  }
+  ctx->planeB_rows_cap = rows_cap;
+  ctx->Lcover = (lcover + 31) & ~31;
+
+  const size_t R = max_replicates, L = alen, Lp = ctx->Lp, N = nseq;
+  int nJT, nIT; rsb_stat_grid(alen, &nJT, &nIT);
+  RSB_CUDA_OK(cudaMalloc(&ctx->d_res, R * N * L));
+  RSB_CUDA_OK(cudaMalloc(&ctx->d_planeA, R * ctx->MA * ctx->Kpad));
+  RSB_CUDA_OK(cudaMalloc(&ctx->d_planeB, R * rows_cap * ctx->Kpad));
+  RSB_CUDA_OK(cudaMalloc(&ctx->d_cnt, R * 16 * L * Lp * sizeof(long long)));
+  RSB_CUDA_OK(cudaMalloc(&ctx->d_nseff, R * L * Lp * sizeof(double)));
+  RSB_CUDA_OK(cudaMalloc(&ctx->d_cov, R * L * Lp * sizeof(double)));
+  RSB_CUDA_OK(cudaMalloc(&ctx->d_tmp, std::max(R * L * Lp, R * (size_t) nJT * nIT * 4) * sizeof(double)));
+  RSB_CUDA_OK(cudaMalloc(&ctx->d_pm, R * L * 4 * sizeof(double)));
+  RSB_CUDA_OK(cudaMalloc(&ctx->d_rowpart, R * nJT * L * 4 * sizeof(double)));
+  RSB_CUDA_OK(cudaMalloc(&ctx->d_colpart, R * nIT * L * 4 * sizeof(double)));
+  RSB_CUDA_OK(cudaMalloc(&ctx->d_mm, R * nJT * nIT * 2 * sizeof(double)));
+  RSB_CUDA_OK(cudaMalloc(&ctx->d_scal, R * 4 * sizeof(double)));
+  RSB_CUDA_OK(cudaMalloc(&ctx->d_covx, R * L * sizeof(double)));
+  RSB_CUDA_OK(cudaMalloc(&ctx->d_minmax, R * 2 * sizeof(double)));
+  RSB_CUDA_OK(cudaMalloc(&ctx->d_meanp, R * 4 * sizeof(double)));
+  RSB_CUDA_OK(cudaMalloc(&ctx->d_w, sizeof(double)));
+  RSB_CUDA_OK(cudaMalloc(&ctx->d_hist, sizeof(unsigned long long) * HIST_BINS));
+  RSB_CUDA_OK(cudaMalloc(&ctx->d_colsum, L * 5 * sizeof(unsigned long long)));
+  RSB_CUDA_OK(cudaMalloc(&ctx->d_ps, L * 5 * sizeof(double)));
+  RSB_CUDA_OK(cudaMalloc(&ctx->d_flags, sizeof(int)));
+  RSB_CUDA_OK(cudaMemsetAsync(ctx->d_flags, 0, sizeof(int), ctx->stream));
+  RSB_CUDA_OK(cudaMemsetAsync(ctx->d_hist, 0, sizeof(unsigned long long) * HIST_BINS, ctx->stream));
+  // counts outside the computed upper-triangle tiles are never read, but keep the buffer defined
+  RSB_CUDA_OK(cudaMemsetAsync(ctx->d_cnt, 0, R * 16 * L * Lp * sizeof(long long), ctx->stream));
+  RSB_CUDA_OK(cudaMemsetAsync(ctx->d_cov, 0, R * L * Lp * sizeof(double), ctx->stream));
+  ctx->hist_n = 0;
+  if (make_plane_map(ctx, &ctx->tmA, ctx->d_planeA, ctx->Kpad, (size_t) ctx->MA, ctx->Rcap, RSB_MTILE)) return 1;
+  ctx->wgt.assign(nseq, 1.0);
+  RSB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int rsb_set_weights(rsb_ctx *ctx, const double *wgt)
+{
+  if (ctx->N == 0) { rsb_set_error(ctx, "rsb_configure first"); return 1; }
+  RSB_CUDA_OK(cudaSetDevice(ctx->device));
+  if (wgt) ctx->wgt.assign(wgt, wgt + ctx->N); else ctx->wgt.assign(ctx->N, 1.0);
+  int S = ctx->Sreq;
+  if (S == 0) {
+    bool small_int = true;
+    for (int s = 0; s < ctx->N && small_int; s++) small_int = (ctx->wgt[s] >= 0 && ctx->wgt[s] == std::floor(ctx->wgt[s]) && ctx->wgt[s] <= 255.0);
+    S = small_int ? 1 : 5;
+  }
+  Geo &g = ctx->geo[0];
+  if (g.S != S || !g.d_tiles) { if (build_geo(ctx, g, S)) return 1; }
+  return quantise(ctx, g, ctx->wgt, false);
+}
+
+int rsb_get_quantisation(rsb_ctx *ctx, int64_t *wq, int *q, int *nslices)
+{
+  Geo &g = ctx->geo[0];
+  if (!g.ready) { rsb_set_error(ctx, "rsb_set_weights has not been called"); return 1; }
+  if (wq) for (int s = 0; s < ctx->N; s++) wq[s] = g.wq[s];
+  if (q) *q = g.q;
+  if (nslices) *nslices = g.S;
+  return 0;
+}
+
+int rsb_fetch_probs(rsb_ctx *ctx, double *pp, double *pm, double *ps, double *nseff, double *ngap)
+{
+  RSB_CUDA_OK(cudaSetDevice(ctx->device));
+  Geo &g = ctx->geo[0];
+  if (!g.ready || ctx->cur_geo != 0) { rsb_set_error(ctx, "no weighted counts resident (call rsb_probs)"); return 1; }
+  const size_t L = ctx->L;
+  if (pp || nseff || ngap) {
+    if (!ctx->d_pp_out) {
+      RSB_CUDA_OK(cudaMalloc(&ctx->d_pp_out, L * L * 16 * sizeof(double)));
+      RSB_CUDA_OK(cudaMalloc(&ctx->d_nseff_out, L * L * sizeof(double)));
+      RSB_CUDA_OK(cudaMalloc(&ctx->d_ngap_out, L * L * sizeof(double)));
+    }
+    RSB_CUDA_OK(rsb_launch_export_probs(ctx->d_cnt, ctx->L, ctx->Lp, g.scale, g.wtot, ctx->d_pp_out, ctx->d_nseff_out, ctx->d_ngap_out, ctx->stream));
+    ctx->launches++;
+    if (pp)    RSB_CUDA_OK(cudaMemcpyAsync(pp, ctx->d_pp_out, L * L * 16 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (nseff) RSB_CUDA_OK(cudaMemcpyAsync(nseff, ctx->d_nseff_out, L * L * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (ngap)  RSB_CUDA_OK(cudaMemcpyAsync(ngap, ctx->d_ngap_out, L * L * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  if (ps) {
+    RSB_CUDA_OK(rsb_launch_colsum(ctx->d_res, ctx->N, ctx->L, g.d_wq, ctx->d_colsum, ctx->stream));
+    RSB_CUDA_OK(rsb_launch_ps(ctx->d_colsum, ctx->L, g.scale, ctx->d_ps, ctx->stream));
+    ctx->launches += 2;
+    RSB_CUDA_OK(cudaMemcpyAsync(ps, ctx->d_ps, L * 5 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  if (pm) RSB_CUDA_OK(cudaMemcpyAsync(pm, ctx->d_pm, L * 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  RSB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int rsb_probs(rsb_ctx *ctx, const uint8_t *msa, int64_t row_stride, int on_device, double tol,
+              double *pp, double *pm, double *ps, double *nseff, double *ngap)
+{
+  RSB_CUDA_OK(cudaSetDevice(ctx->device));
+  if (ensure_geo(ctx, 0)) return 1;
+  if (upload_msa(ctx, msa, row_stride, 0, 1, 0, on_device)) return 1;
+  if (run_probs(ctx, 1, tol)) return 1;
+  if (pp || pm || ps || nseff || ngap) { if (rsb_fetch_probs(ctx, pp, pm, ps, nseff, ngap)) return 1; }
+  return check_flags(ctx, "corr_Probs");
+}
+
+/* corr_CalculateCOVCorrected on a host-supplied raw matrix (the reference corrects whatever mi->COV holds,
+ * e.g. Potts scores filled on the host): upload, reduce, correct. */
+int rsb_correct_host(rsb_ctx *ctx, int actype, double *cov, double *mincov, double *maxcov)
+{
+  RSB_CUDA_OK(cudaSetDevice(ctx->device));
+  if (actype != RSB_APC && actype != RSB_ASC) { rsb_set_error(ctx, "wrong correction type"); return 1; }
+  RSB_CUDA_OK(cudaMemcpy2DAsync(ctx->d_cov, sizeof(double) * ctx->Lp, cov, sizeof(double) * ctx->L, sizeof(double) * ctx->L, ctx->L,
+                                cudaMemcpyHostToDevice, ctx->stream));
+  RSB_CUDA_OK(rsb_launch_reduce_cov(ctx->d_cov, 1, ctx->L, ctx->Lp, ctx->d_rowpart, ctx->d_colpart, ctx->d_mm, ctx->stream));
+  RSB_CUDA_OK(rsb_launch_correct_final(ctx->d_rowpart, ctx->d_colpart, ctx->d_mm, 1, ctx->L, ctx->d_covx, ctx->d_scal, ctx->stream));
+  ctx->launches += 2;
+  return rsb_correct(ctx, actype, cov, mincov, maxcov);
+}
+
+int rsb_statistic(rsb_ctx *ctx, int stat, int covclass, const double *allowpair, const uint8_t *msa, int64_t row_stride, int on_device,
+                  double *cov, double *mincov, double *maxcov)
+{
+  RSB_CUDA_OK(cudaSetDevice(ctx->device));
+  if (resolve_stat(ctx, stat, covclass)) return 1;
+  if (stat == RSB_RAF || stat == RSB_RAFS) {
+    if (!msa) { rsb_set_error(ctx, "RAF/RAFS need the alignment"); return 1; }
+    if (upload_msa(ctx, msa, row_stride, 0, 1, 0, on_device)) return 1;
+    if (run_counts(ctx, 1, 1)) return 1;
+  } else if (ctx->cur_geo != 0) { rsb_set_error(ctx, "rsb_probs must precede this statistic"); return 1; }
+  if (run_statistic(ctx, 1, stat, covclass, allow_mask(allowpair))) return 1;
+  double sc[4];
+  if (cov) {
+    RSB_CUDA_OK(rsb_launch_symmetrize(ctx->d_cov, ctx->L, ctx->Lp, ctx->stream));
+    ctx->launches++;
+    if (copy_matrix_out(ctx, ctx->d_cov, cov)) return 1;
+  }
+  RSB_CUDA_OK(cudaMemcpyAsync(sc, ctx->d_scal, sizeof(sc), cudaMemcpyDeviceToHost, ctx->stream));
+  RSB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  if (mincov) *mincov = sc[1];
+  if (maxcov) *maxcov = sc[2];
+  return 0;
+}
+
+int rsb_correct(rsb_ctx *ctx, int actype, double *cov, double *mincov, double *maxcov)
+{
+  RSB_CUDA_OK(cudaSetDevice(ctx->device));
+  if (actype != RSB_APC && actype != RSB_ASC) { rsb_set_error(ctx, "wrong correction type"); return 1; }
+  RSB_CUDA_OK(rsb_launch_correct_hist(ctx->d_cov, ctx->d_covx, ctx->d_scal, 1, ctx->L, ctx->Lp, actype, 1, 0.0, ctx->d_w, ctx->d_hist,
+                                      HIST_BINS, ctx->d_mm, ctx->d_minmax, ctx->d_flags, ctx->stream));
+  RSB_CUDA_OK(rsb_launch_symmetrize(ctx->d_cov, ctx->L, ctx->Lp, ctx->stream));
+  ctx->launches += 3;
+  double mmx[2];
+  if (cov && copy_matrix_out(ctx, ctx->d_cov, cov)) return 1;
+  RSB_CUDA_OK(cudaMemcpyAsync(mmx, ctx->d_minmax, sizeof(mmx), cudaMemcpyDeviceToHost, ctx->stream));
+  if (check_flags(ctx, "corr_CalculateCOVCorrected")) return 1;
+  if (mincov) *mincov = mmx[0];
+  if (maxcov) *maxcov = mmx[1];
+  return 0;
+}
+
+int rsb_scan(rsb_ctx *ctx, const uint8_t *msa, int64_t row_stride, int on_device, int stat, int covclass, int actype,
+             const double *allowpair, double tol, double *cov, double *mincov, double *maxcov,
+             double *pp, double *pm, double *ps, double *nseff, double *ngap)
+{
+  RSB_CUDA_OK(cudaSetDevice(ctx->device));
+  if (resolve_stat(ctx, stat, covclass)) return 1;
+  const bool raf = (stat == RSB_RAF || stat == RSB_RAFS);
+  if (!raf) { if (rsb_probs(ctx, msa, row_stride, on_device, tol, pp, pm, ps, nseff, ngap)) return 1; }
+  else {
+    const size_t L = ctx->L;            // corr_Probs is skipped for RAF*: the probability fields stay zero (covariation.c:82-84)
+    if (pp) memset(pp, 0, L * L * 16 * sizeof(double));
+    if (pm) memset(pm, 0, L * 4 * sizeof(double));
+    if (ps) memset(ps, 0, L * 5 * sizeof(double));
+    if (nseff) memset(nseff, 0, L * L * sizeof(double));
+    if (ngap)  memset(ngap, 0, L * L * sizeof(double));
+  }
+  const bool corr = (actype == RSB_APC || actype == RSB_ASC);
+  if (rsb_statistic(ctx, stat, covclass, allowpair, msa, row_stride, on_device, corr ? nullptr : cov, mincov, maxcov)) return 1;
+  if (corr) return rsb_correct(ctx, actype, cov, mincov, maxcov);
+  return 0;
+}
+
+int rsb_get_counts(rsb_ctx *ctx, int64_t *counts)
+{
+  RSB_CUDA_OK(cudaSetDevice(ctx->device));
+  const size_t L = ctx->L;
+  RSB_CUDA_OK(cudaMemcpy2DAsync(counts, sizeof(int64_t) * L, ctx->d_cnt, sizeof(int64_t) * ctx->Lp, sizeof(int64_t) * L, 16 * L,
+                                cudaMemcpyDeviceToHost, ctx->stream));
+  RSB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  // only the upper triangle is defined: clear the rest so that comparisons are well defined
+  for (size_t p = 0; p < 16; p++)
+    for (size_t i = 0; i < L; i++)
+      for (size_t j = 0; j <= i && j < L; j++) counts[(p * L + i) * L + j] = 0;
+  return 0;
+}
+
+int rsb_get_counts_direct(rsb_ctx *ctx, const uint8_t *msa, int64_t row_stride, int64_t *counts)
+{
+  RSB_CUDA_OK(cudaSetDevice(ctx->device));
+  Geo &g = ctx->geo[ctx->cur_geo];
+  if (!g.ready) { rsb_set_error(ctx, "no weights set"); return 1; }
+  if (upload_msa(ctx, msa, row_stride, 0, 1, 0, 0)) return 1;
+  RSB_CUDA_OK(cudaMemsetAsync(ctx->d_cnt, 0, (size_t) 16 * ctx->L * ctx->Lp * sizeof(long long), ctx->stream));
+  RSB_CUDA_OK(rsb_launch_counts_direct(ctx->d_res, ctx->N, ctx->L, ctx->Lp, g.d_wq, ctx->d_cnt, ctx->stream));
+  ctx->launches++;
+  return rsb_get_counts(ctx, counts);
+}
+
+// ---------------------------------------------------------------------------------------------- nulls
+int rsb_null_width(rsb_ctx *ctx, const uint8_t *null0, int64_t row_stride, int on_device, int stat, int covclass, int actype,
+                   const double *allowpair, double tol, double w_old, double bmin, int hpts, double *w_out, double *mincov, double *maxcov)
+{
+  RSB_CUDA_OK(cudaSetDevice(ctx->device));
+  if (resolve_stat(ctx, stat, covclass)) return 1;
+  if (null0 && upload_msa(ctx, null0, row_stride, 0, 1, 0, on_device)) return 1;
+  if (run_pipeline(ctx, 1, stat, covclass, allow_mask(allowpair), tol)) return 1;
+  RSB_CUDA_OK(rsb_launch_correct_hist(ctx->d_cov, ctx->d_covx, ctx->d_scal, 1, ctx->L, ctx->Lp, actype, 0, bmin, ctx->d_w, ctx->d_hist,
+                                      HIST_BINS, ctx->d_mm, ctx->d_minmax, ctx->d_flags, ctx->stream));
+  RSB_CUDA_OK(rsb_launch_width(ctx->d_minmax, w_old, bmin, hpts, tol, ctx->d_w, ctx->stream));
+  ctx->launches += 3;
+  double mmx[2], w;
+  RSB_CUDA_OK(cudaMemcpyAsync(mmx, ctx->d_minmax, sizeof(mmx), cudaMemcpyDeviceToHost, ctx->stream));
+  RSB_CUDA_OK(cudaMemcpyAsync(&w, ctx->d_w, sizeof(w), cudaMemcpyDeviceToHost, ctx->stream));
+  if (check_flags(ctx, "calculate_width_histo")) return 1;
+  if (!(mmx[1] > bmin)) { rsb_set_error(ctx, "bmin %f should be larger than maxCOV %f", bmin, mmx[1]); return 1; }   // R-scape.c:1355
+  if (w_out) *w_out = w;
+  if (mincov) *mincov = mmx[0];
+  if (maxcov) *maxcov = mmx[1];
+  return 0;
+}
+
+static int null_hist_chunk(rsb_ctx *ctx, int nrep, int stat, int covclass, int actype, unsigned mask, double tol, double w, double bmin, double *minmax)
+{
+  if (run_pipeline(ctx, nrep, stat, covclass, mask, tol)) return 1;
+  RSB_CUDA_OK(cudaMemcpyAsync(ctx->d_w, &w, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  RSB_CUDA_OK(rsb_launch_correct_hist(ctx->d_cov, ctx->d_covx, ctx->d_scal, nrep, ctx->L, ctx->Lp, actype, 2, bmin, ctx->d_w, ctx->d_hist,
+                                      HIST_BINS, ctx->d_mm, ctx->d_minmax, ctx->d_flags, ctx->stream));
+  ctx->launches += 2;
+  if (w > 0.0) ctx->hist_n += (unsigned long long) nrep * ((unsigned long long) ctx->L * (ctx->L - 1) / 2);
+  if (minmax) RSB_CUDA_OK(cudaMemcpyAsync(minmax, ctx->d_minmax, sizeof(double) * 2 * nrep, cudaMemcpyDeviceToHost, ctx->stream));
+  return 0;
+}
+
+int rsb_null_hist(rsb_ctx *ctx, const uint8_t *nulls, int nrep, int64_t row_stride, int64_t rep_stride, int on_device, int stat, int covclass,
+                  int actype, const double *allowpair, double tol, double w, double bmin, double *minmax)
+{
+  RSB_CUDA_OK(cudaSetDevice(ctx->device));
+  if (resolve_stat(ctx, stat, covclass)) return 1;
+  const unsigned mask = allow_mask(allowpair);
+  for (int r0 = 0; r0 < nrep; r0 += ctx->Rcap) {
+    const int n = std::min(ctx->Rcap, nrep - r0);
+    if (upload_msa(ctx, nulls + (size_t) r0 * rep_stride, row_stride, rep_stride, n, 0, on_device)) return 1;
+    if (null_hist_chunk(ctx, n, stat, covclass, actype, mask, tol, w, bmin, minmax ? minmax + 2 * r0 : nullptr)) return 1;
+    if (minmax || r0 + n < nrep) RSB_CUDA_OK(cudaStreamSynchronize(ctx->stream));   // host staging buffers of the next chunk may alias
+  }
+  return check_flags(ctx, "null_rscape");
+}
+
+int rsb_null_hist_slots(rsb_ctx *ctx, int first_rep, int nrep, int stat, int covclass, int actype, const double *allowpair,
+                        double tol, double w, double bmin, double *minmax)
+{
+  RSB_CUDA_OK(cudaSetDevice(ctx->device));
+  if (first_rep != 0) { rsb_set_error(ctx, "slots must start at 0"); return 1; }
+  if (nrep > ctx->Rcap) { rsb_set_error(ctx, "%d replicates exceed the configured %d slots", nrep, ctx->Rcap); return 1; }
+  if (resolve_stat(ctx, stat, covclass)) return 1;
+  if (null_hist_chunk(ctx, nrep, stat, covclass, actype, allow_mask(allowpair), tol, w, bmin, minmax)) return 1;
+  return check_flags(ctx, "null_rscape");
+}
+
+int rsb_hist_reset(rsb_ctx *ctx)
+{
+  RSB_CUDA_OK(cudaSetDevice(ctx->device));
+  RSB_CUDA_OK(cudaMemsetAsync(ctx->d_hist, 0, sizeof(unsigned long long) * HIST_BINS, ctx->stream));
+  ctx->hist_n = 0;
+  return 0;
+}
+
+int rsb_hist_read(rsb_ctx *ctx, uint64_t *bins, int nb_cap, uint64_t *n_out, int *imax_out)
+{
+  RSB_CUDA_OK(cudaSetDevice(ctx->device));
+  const int nb = std::min(nb_cap, HIST_BINS);
+  RSB_CUDA_OK(cudaMemcpyAsync(bins, ctx->d_hist, sizeof(uint64_t) * nb, cudaMemcpyDeviceToHost, ctx->stream));
+  RSB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  int imax = -1;
+  for (int b = 0; b < nb; b++) if (bins[b]) imax = b;
+  if (n_out) *n_out = ctx->hist_n;
+  if (imax_out) *imax_out = imax;
+  return 0;
+}
+
+int rsb_last_nseff(rsb_ctx *ctx, double *nseff, double *ngap)
+{
+  RSB_CUDA_OK(cudaSetDevice(ctx->device));
+  Geo &g = ctx->geo[0];
+  const size_t L = ctx->L;
+  if (ctx->cur_geo != 0) { rsb_set_error(ctx, "no weighted counts resident"); return 1; }
+  if (!ctx->d_pp_out) {
+    RSB_CUDA_OK(cudaMalloc(&ctx->d_pp_out, L * L * 16 * sizeof(double)));
+    RSB_CUDA_OK(cudaMalloc(&ctx->d_nseff_out, L * L * sizeof(double)));
+    RSB_CUDA_OK(cudaMalloc(&ctx->d_ngap_out, L * L * sizeof(double)));
+  }
+  RSB_CUDA_OK(rsb_launch_export_probs(ctx->d_cnt + (size_t) ctx->last_slot * 16 * L * ctx->Lp, ctx->L, ctx->Lp, g.scale, g.wtot,
+                                      ctx->d_pp_out, ctx->d_nseff_out, ctx->d_ngap_out, ctx->stream));
+  ctx->launches++;
+  if (nseff) RSB_CUDA_OK(cudaMemcpyAsync(nseff, ctx->d_nseff_out, L * L * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (ngap)  RSB_CUDA_OK(cudaMemcpyAsync(ngap, ctx->d_ngap_out, L * L * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  RSB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- generators
+int rsb_set_tree(rsb_ctx *ctx, const int *left, const int *right, const int *parent, const double *ld, const double *rd)
+{
+  RSB_CUDA_OK(cudaSetDevice(ctx->device));
+  const int N = ctx->N, nn = N - 1;
+  if (N < 2) { rsb_set_error(ctx, "a tree needs at least 2 leaves"); return 1; }
+  for (int v = 0; v < nn; v++) {
+    const int kids[2] = { left[v], right[v] };
+    for (int c : kids) if (c > 0 && (c <= v || c >= nn)) { rsb_set_error(ctx, "tree node %d: child %d must have a larger index than its parent", v, c); return 1; }
+      else if (c <= 0 && -c >= N) { rsb_set_error(ctx, "tree node %d: leaf %d out of range", v, -c); return 1; }
+  }
+  ctx->h_left.assign(left, left + nn); ctx->h_right.assign(right, right + nn); ctx->h_parent.assign(parent, parent + nn);
+  ctx->h_ld.assign(ld, ld + nn); ctx->h_rd.assign(rd, rd + nn);
+  // nodes grouped by depth (level order): every level is a set of independent branches
+  std::vector<int> depth(nn, 0), order(nn), level_start;
+  for (int v = 0; v < nn; v++) { if (left[v] > 0) depth[left[v]] = depth[v] + 1; if (right[v] > 0) depth[right[v]] = depth[v] + 1; }
+  int maxd = 0; for (int v = 0; v < nn; v++) maxd = std::max(maxd, depth[v]);
+  for (int v = 0; v < nn; v++) order[v] = v;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return depth[a] < depth[b]; });
+  level_start.assign(maxd + 2, 0);
+  for (int v = 0; v < nn; v++) level_start[depth[v] + 1]++;
+  for (int d = 0; d <= maxd; d++) level_start[d + 1] += level_start[d];
+  ctx->nlevels = maxd + 1;
+  ctx->h_level_start = level_start;
+  dfree(ctx->d_left); dfree(ctx->d_right); dfree(ctx->d_parent); dfree(ctx->d_order); dfree(ctx->d_level_start);
+  RSB_CUDA_OK(cudaMalloc(&ctx->d_left, sizeof(int) * nn));
+  RSB_CUDA_OK(cudaMalloc(&ctx->d_right, sizeof(int) * nn));
+  RSB_CUDA_OK(cudaMalloc(&ctx->d_parent, sizeof(int) * nn));
+  RSB_CUDA_OK(cudaMalloc(&ctx->d_order, sizeof(int) * nn));
+  RSB_CUDA_OK(cudaMalloc(&ctx->d_level_start, sizeof(int) * (maxd + 2)));
+  RSB_CUDA_OK(cudaMemcpyAsync(ctx->d_left, left, sizeof(int) * nn, cudaMemcpyHostToDevice, ctx->stream));
+  RSB_CUDA_OK(cudaMemcpyAsync(ctx->d_right, right, sizeof(int) * nn, cudaMemcpyHostToDevice, ctx->stream));
+  RSB_CUDA_OK(cudaMemcpyAsync(ctx->d_parent, parent, sizeof(int) * nn, cudaMemcpyHostToDevice, ctx->stream));
+  RSB_CUDA_OK(cudaMemcpyAsync(ctx->d_order, order.data(), sizeof(int) * nn, cudaMemcpyHostToDevice, ctx->stream));
+  RSB_CUDA_OK(cudaMemcpyAsync(ctx->d_level_start, level_start.data(), sizeof(int) * (maxd + 2), cudaMemcpyHostToDevice, ctx->stream));
+  RSB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  ctx->have_tree = true;
+  return 0;
+}
+
+// P(t) = exp(tQ) by scaling and squaring in double on the host (4x4, N-1 branches x 2: negligible), with the
+// reference's float-rounded floored time, negative clip and row renormalisation (e1_model.c:64-75, ratematrix.c:199-222)
+static int branch_matrix(const double *Q, double t, double *P)
+{
+  float rt = (float) t;
+  rt = (rt >= 0.0 && rt < 1e-5) ? 1e-5 : rt;
+  if (rt < 0.0) { if (rt > -1e-5) rt = 1e-5; else return 1; }
+  const double time = (rt > 10000.) ? 10000.0 : (double) rt;
+  double M[16], T[16], X[16], norm = 0.0;
+  for (int k = 0; k < 16; k++) { M[k] = time * Q[k]; norm += M[k] * M[k]; }
+  norm = std::sqrt(norm);
+  int z = 0; while (norm > 0.1) { norm *= 0.5; z++; }
+  for (int k = 0; k < 16; k++) M[k] = std::ldexp(M[k], -z);
+  for (int k = 0; k < 16; k++) { P[k] = (k % 5 == 0) ? 1.0 : 0.0; T[k] = P[k]; }
+  for (int n = 1; n < 100; n++) {
+    double delta = 0.0;
+    for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) { double s = 0; for (int k = 0; k < 4; k++) s += T[i * 4 + k] * M[k * 4 + j]; X[i * 4 + j] = s / n; }
+    for (int k = 0; k < 16; k++) { T[k] = X[k]; P[k] += T[k]; delta += std::fabs(T[k]); }
+    if (delta < 1e-18) break;
+  }
+  while (z-- > 0) {
+    for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) { double s = 0; for (int k = 0; k < 4; k++) s += P[i * 4 + k] * P[k * 4 + j]; X[i * 4 + j] = s; }
+    memcpy(P, X, sizeof(X));
+  }
+  for (int i = 0; i < 4; i++) {
+    double sum = 0.0;
+    for (int j = 0; j < 4; j++) { if (P[i * 4 + j] < 0.0) { if (std::fabs(P[i * 4 + j]) < 0.001) P[i * 4 + j] = 0.0; else return 2; } sum += P[i * 4 + j]; }
+    for (int j = 0; j < 4; j++) P[i * 4 + j] = (sum != 0.0) ? P[i * 4 + j] / sum : 0.25;
+  }
+  return 0;
+}
+
+int rsb_null_simulate(rsb_ctx *ctx, const double *Q, const uint8_t *root, const uint8_t *gapmask, int64_t gap_stride,
+                      uint64_t seed, int first_rep, int nrep)
+{
+  RSB_CUDA_OK(cudaSetDevice(ctx->device));
+  if (!ctx->have_tree) { rsb_set_error(ctx, "rsb_set_tree first"); return 1; }
+  if (first_rep < 0 || first_rep + nrep > ctx->Rcap) { rsb_set_error(ctx, "replicate slots out of range"); return 1; }
+  const int N = ctx->N, L = ctx->L, nn = N - 1;
+  // cumulative branch matrices [node][side][4][4]: row a holds the CDF over child residues
+  std::vector<double> pb((size_t) nn * 2 * 16);
+  for (int v = 0; v < nn; v++)
+    for (int side = 0; side < 2; side++) {
+      double P[16];
+      if (branch_matrix(Q, side ? ctx->h_rd[v] : ctx->h_ld[v], P)) { rsb_set_error(ctx, "failed to evolve node %d to time %f", v, side ? ctx->h_rd[v] : ctx->h_ld[v]); return 1; }
+      for (int a = 0; a < 4; a++) { double cdf = 0.0; for (int b = 0; b < 4; b++) { cdf += P[a * 4 + b]; pb[((size_t) v * 2 + side) * 16 + a * 4 + b] = cdf; } }
+    }
+  if (!ctx->d_pcdf) RSB_CUDA_OK(cudaMalloc(&ctx->d_pcdf, pb.size() * sizeof(double)));
+  if (!ctx->d_root)    RSB_CUDA_OK(cudaMalloc(&ctx->d_root, L));
+  if (!ctx->d_simscratch) RSB_CUDA_OK(cudaMalloc(&ctx->d_simscratch, (size_t) ctx->Rcap * nn * L));
+  RSB_CUDA_OK(cudaMemcpyAsync(ctx->d_pcdf, pb.data(), pb.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  RSB_CUDA_OK(cudaMemcpyAsync(ctx->d_root, root, L, cudaMemcpyHostToDevice, ctx->stream));
+  if (gapmask) {
+    if (!ctx->d_gapmask) RSB_CUDA_OK(cudaMalloc(&ctx->d_gapmask, (size_t) N * L));
+    RSB_CUDA_OK(cudaMemcpy2DAsync(ctx->d_gapmask, L, gapmask, (size_t) gap_stride, L, N, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  RSB_CUDA_OK(cudaStreamSynchronize(ctx->stream));       // pb is a host temporary
+  RSB_CUDA_OK(rsb_launch_null_simulate(ctx->d_left, ctx->d_right, ctx->d_pcdf, N, L, ctx->d_root, gapmask ? ctx->d_gapmask : nullptr, L,
+                                       seed, first_rep, nrep, ctx->d_res, ctx->d_simscratch, ctx->stream));
+  ctx->launches++;
+  return 0;
+}
+
+int rsb_null_fitch_shuffle(rsb_ctx *ctx, const uint8_t *msa, int64_t row_stride, uint64_t seed, int first_rep, int nrep)
+{
+  RSB_CUDA_OK(cudaSetDevice(ctx->device));
+  if (!ctx->have_tree) { rsb_set_error(ctx, "rsb_set_tree first"); return 1; }
+  if (first_rep < 0 || first_rep + nrep > ctx->Rcap) { rsb_set_error(ctx, "replicate slots out of range"); return 1; }
+  const int N = ctx->N, L = ctx->L, nn = N - 1;
+  if (!ctx->d_msa0)  RSB_CUDA_OK(cudaMalloc(&ctx->d_msa0, (size_t) N * L));
+  if (!ctx->d_anc)   RSB_CUDA_OK(cudaMalloc(&ctx->d_anc, (size_t) ctx->Rcap * nn * L));
+  if (!ctx->d_shanc) RSB_CUDA_OK(cudaMalloc(&ctx->d_shanc, (size_t) ctx->Rcap * nn * L));
+  if (!ctx->d_perm)  RSB_CUDA_OK(cudaMalloc(&ctx->d_perm, sizeof(int) * (size_t) ctx->Rcap * L));
+  RSB_CUDA_OK(cudaMemcpy2DAsync(ctx->d_msa0, L, msa, (size_t) row_stride, L, N, cudaMemcpyHostToDevice, ctx->stream));
+  RSB_CUDA_OK(rsb_launch_fitch_shuffle(ctx->d_left, ctx->d_right, ctx->d_parent, ctx->d_order, ctx->h_level_start.data(), ctx->nlevels, N, L,
+                                       ctx->d_msa0, seed, first_rep, nrep, ctx->d_res, ctx->d_anc, ctx->d_shanc, ctx->d_perm, ctx->stream));
+  ctx->launches += 2 + ctx->nlevels;
+  return 0;
+}
+
+int rsb_get_slots(rsb_ctx *ctx, int first_rep, int nrep, uint8_t *out)
+{
+  RSB_CUDA_OK(cudaSetDevice(ctx->device));
+  if (first_rep < 0 || first_rep + nrep > ctx->Rcap) { rsb_set_error(ctx, "replicate slots out of range"); return 1; }
+  const size_t rb = (size_t) ctx->N * ctx->L;
+  RSB_CUDA_OK(cudaMemcpyAsync(out, ctx->d_res + first_rep * rb, rb * nrep, cudaMemcpyDeviceToHost, ctx->stream));
+  RSB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- instrumentation
+int rsb_profile_gram(rsb_ctx *ctx, int enable) { ctx->profile = enable != 0; return 0; }
+
+int rsb_counters(rsb_ctx *ctx, int64_t *launches, double *gram_ms, int64_t *gram_launches, int reset)
+{
+  RSB_CUDA_OK(cudaSetDevice(ctx->device));
+  if (!ctx->pending.empty()) {
+    RSB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    for (auto &p : ctx->pending) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, p.first, p.second) == cudaSuccess) ctx->gram_ms += ms;
+      cudaEventDestroy(p.first); cudaEventDestroy(p.second);
+    }
+    ctx->pending.clear();
+  }
+  if (launches) *launches = ctx->launches;
+  if (gram_ms) *gram_ms = ctx->gram_ms;
+  if (gram_launches) *gram_launches = ctx->gram_launches;
+  if (reset) { ctx->launches = 0; ctx->gram_ms = 0.0; ctx->gram_launches = 0; }
+  return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,202 @@
+// correct_hist.cu -- background correction (APC / ASC), score range, and the score histogram.
+//
+// Reference: corr_CalculateCOVCorrected (src/correlators.c:1064-1157); histogram fill of
+// cov_SignificantPairs_Ranking (src/covariation.c:415-432) with Easel's bin rule
+// b = ceil((x - bmin)/w - 1), value clamped to max(x, bmin + w); histogram width
+// from the first null, calculate_width_histo (src/R-scape.c:1357-1360); cumulative null histogram,
+// null_add2cumranklist (src/R-scape.c:1565-1612): with a common (bmin, w) every replicate's bin b
+// is the cumulative histogram's bin b, so all replicates add into one device array.
+#include "rsb_common.cuh"
+#include <math.h>
+
+namespace {
+
+constexpr int CH_TI = 32;
+constexpr int CH_TJ = 256;
+constexpr int CH_SMEM_BINS = 4096;
+
+// COVx[i] = sum_{j != i} COV[i][j] / (L-1) from the tile partials; COVavg = 2/(L(L-1)) sum_{i<j} COV;
+// raw min/max from the per-block partials.  One block per replicate; fixed summation order.
+// scal[r][0..3] = { COVavg, raw min, raw max, unused }
+__global__ void __launch_bounds__(256)
+correct_final_kernel(const double *__restrict__ rowpart, const double *__restrict__ colpart, const double *__restrict__ mm,
+                     int L, int nJT, int nIT, double *__restrict__ covx, double *__restrict__ scal)
+{
+  __shared__ double red[256], rmin[256], rmax[256];
+  const int r = blockIdx.x;
+  double upper = 0.0;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) {
+    double rs = 0.0, cs = 0.0;
+    for (int jt = 0; jt < nJT; jt++) rs += rowpart[((size_t) r * nJT + jt) * L + i];
+    for (int it = 0; it < nIT; it++) cs += colpart[((size_t) r * nIT + it) * L + i];
+    double x = rs + cs;
+    if (L > 1) x /= (double) L - 1.;
+    covx[(size_t) r * L + i] = x;
+    upper += rs;
+  }
+  double a = INFINITY, b = -INFINITY;
+  for (int k = threadIdx.x; k < nJT * nIT; k += blockDim.x) {
+    a = fmin(a, mm[((size_t) r * nJT * nIT + k) * 2]);
+    b = fmax(b, mm[((size_t) r * nJT * nIT + k) * 2 + 1]);
+  }
+  red[threadIdx.x] = upper; rmin[threadIdx.x] = a; rmax[threadIdx.x] = b;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      red[threadIdx.x] += red[threadIdx.x + o];
+      rmin[threadIdx.x] = fmin(rmin[threadIdx.x], rmin[threadIdx.x + o]);
+      rmax[threadIdx.x] = fmax(rmax[threadIdx.x], rmax[threadIdx.x + o]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    double avg = red[0];
+    if (L > 1) avg /= (double) L * ((double) L - 1.);
+    avg *= 2.;
+    scal[r * 4 + 0] = avg; scal[r * 4 + 1] = rmin[0]; scal[r * 4 + 2] = rmax[0]; scal[r * 4 + 3] = 0.0;
+  }
+}
+
+__device__ __forceinline__ double corrected(int actype, double raw, double xi, double xj, double avg)
+{
+  if (actype == RSB_APC) return (avg != 0.0) ? raw - xi * xj / avg : 0.0;      // :1118
+  if (actype == RSB_ASC) return raw - (xi + xj - avg);                         // :1120
+  return raw;
+}
+
+// One pass over the upper triangle of the raw statistic.
+//   mode bit 0: write the corrected score back (upper triangle; symmetrize_kernel mirrors it and sets the diagonal)
+//   mode bit 1: add max(x, bmin+w) into the histogram (w read from *wptr so that it can come from the
+//               device-side width computation without a host round trip)
+// Always: per-block min/max of the corrected score, NaN flag (:1124).
+__global__ void __launch_bounds__(CH_TJ)
+correct_hist_kernel(double *__restrict__ cov, const double *__restrict__ covx, const double *__restrict__ scal, int L, int Lp,
+                    int actype, int mode, double bmin, const double *__restrict__ wptr, unsigned long long *__restrict__ hist,
+                    int nbins, double *__restrict__ mm, int *__restrict__ flags, int nJT, int nIT)
+{
+  __shared__ unsigned int sh[CH_SMEM_BINS];
+  __shared__ double smin[CH_TJ / 32], smax[CH_TJ / 32];
+  const int jt = blockIdx.x, it = blockIdx.y, r = blockIdx.z;
+  const int j  = jt * CH_TJ + threadIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool tile_live = (it * CH_TI) < (jt * CH_TJ + CH_TJ - 1);
+  const bool do_hist = (mode & 2) != 0;
+  const double avg = scal[r * 4];
+  const double w   = do_hist ? *wptr : 1.0;
+  double vmin = INFINITY, vmax = -INFINITY;
+
+  if (do_hist) { for (int k = threadIdx.x; k < CH_SMEM_BINS; k += CH_TJ) sh[k] = 0; __syncthreads(); }
+
+  if (tile_live && j < L) {
+    const double xj = covx[(size_t) r * L + j];
+    double *C = cov + (size_t) r * L * Lp;
+    for (int il = 0; il < CH_TI; il++) {
+      const int i = it * CH_TI + il;
+      if (i >= L || i >= j) continue;
+      const double v = corrected(actype, C[(size_t) i * Lp + j], covx[(size_t) r * L + i], xj, avg);
+      if (isnan(v)) atomicOr(flags, 2);
+      vmin = fmin(vmin, v);
+      vmax = fmax(vmax, v);
+      if (mode & 1) C[(size_t) i * Lp + j] = v;                     // mirrored by symmetrize_kernel
+      if (do_hist && w > 0.0) {
+        const double x = fmax(v, bmin + w);                           // ESL_MAX(cov, bmin+w), covariation.c:431
+        const double bd = ceil(((x - bmin) / w) - 1.);                // esl_histogram_Score2Bin
+        if (bd >= 0.0 && bd < (double) nbins) {
+          const int b = (int) bd;
+          if (b < CH_SMEM_BINS) atomicAdd(&sh[b], 1u);
+          else                  atomicAdd(&hist[b], 1ull);
+        } else atomicOr(flags, 4);                                    // histogram capacity exceeded
+      }
+    }
+  }
+  #pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    vmin = fmin(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+    vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+  }
+  if (lane == 0) { smin[warp] = vmin; smax[warp] = vmax; }
+  __syncthreads();
+  if (do_hist)
+    for (int k = threadIdx.x; k < CH_SMEM_BINS && k < nbins; k += CH_TJ)
+      if (sh[k]) atomicAdd(&hist[k], (unsigned long long) sh[k]);
+  if (threadIdx.x == 0) {
+    double a = smin[0], b = smax[0];
+    for (int q = 1; q < CH_TJ / 32; q++) { a = fmin(a, smin[q]); b = fmax(b, smax[q]); }
+    double *o = mm + (((size_t) r * nIT + it) * nJT + jt) * 2;
+    o[0] = a; o[1] = b;
+  }
+}
+
+// out[r][0..1] = min/max over the block partials
+__global__ void __launch_bounds__(256)
+minmax_final_kernel(const double *__restrict__ mm, int nblocks, double *__restrict__ out)
+{
+  __shared__ double rmin[256], rmax[256];
+  const int r = blockIdx.x;
+  double a = INFINITY, b = -INFINITY;
+  for (int k = threadIdx.x; k < nblocks; k += blockDim.x) {
+    a = fmin(a, mm[((size_t) r * nblocks + k) * 2]);
+    b = fmax(b, mm[((size_t) r * nblocks + k) * 2 + 1]);
+  }
+  rmin[threadIdx.x] = a; rmax[threadIdx.x] = b;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { rmin[threadIdx.x] = fmin(rmin[threadIdx.x], rmin[threadIdx.x + o]); rmax[threadIdx.x] = fmax(rmax[threadIdx.x], rmax[threadIdx.x + o]); }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { out[r * 2] = rmin[0]; out[r * 2 + 1] = rmax[0]; }
+}
+
+// w = min(w_old, (maxCOV - max(bmin, minCOV)) / hpts), zeroed below tol: src/R-scape.c:1357-1360
+__global__ void width_kernel(const double *__restrict__ minmax, double w_old, double bmin, int hpts, double tol, double *__restrict__ wout)
+{
+  if (threadIdx.x || blockIdx.x) return;
+  const double lo = fmax(bmin, minmax[0]);
+  const double w_new = (minmax[1] - lo) / (double) hpts;
+  double w = fmin(w_old, w_new);
+  if (w < tol) w = 0.0;
+  *wout = w;
+}
+
+// copy raw -> lower triangle mirror and -inf diagonal for a host-visible symmetric matrix (no correction case)
+__global__ void symmetrize_kernel(double *__restrict__ cov, int L, int Lp)
+{
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+  if (j >= L) return;
+  if (i == j) cov[(size_t) i * Lp + j] = -INFINITY;
+  else if (i < j) cov[(size_t) j * Lp + i] = cov[(size_t) i * Lp + j];
+}
+
+} // namespace
+
+void rsb_corr_grid(int L, int *nJT, int *nIT) { *nJT = (L + CH_TJ - 1) / CH_TJ; *nIT = (L + CH_TI - 1) / CH_TI; }
+
+cudaError_t rsb_launch_correct_final(const double *rowpart, const double *colpart, const double *mm, int nrep, int L,
+                                     double *covx, double *scal, cudaStream_t st)
+{
+  int nJT, nIT; rsb_corr_grid(L, &nJT, &nIT);
+  correct_final_kernel<<<nrep, 256, 0, st>>>(rowpart, colpart, mm, L, nJT, nIT, covx, scal);
+  return cudaGetLastError();
+}
+
+cudaError_t rsb_launch_correct_hist(double *cov, const double *covx, const double *scal, int nrep, int L, int Lp, int actype, int mode,
+                                    double bmin, const double *wptr, unsigned long long *hist, int nbins, double *mm, double *minmax_out,
+                                    int *flags, cudaStream_t st)
+{
+  int nJT, nIT; rsb_corr_grid(L, &nJT, &nIT);
+  correct_hist_kernel<<<dim3(nJT, nIT, nrep), CH_TJ, 0, st>>>(cov, covx, scal, L, Lp, actype, mode, bmin, wptr, hist, nbins, mm, flags, nJT, nIT);
+  minmax_final_kernel<<<nrep, 256, 0, st>>>(mm, nJT * nIT, minmax_out);
+  return cudaGetLastError();
+}
+
+cudaError_t rsb_launch_width(const double *minmax, double w_old, double bmin, int hpts, double tol, double *wout, cudaStream_t st)
+{
+  width_kernel<<<1, 32, 0, st>>>(minmax, w_old, bmin, hpts, tol, wout);
+  return cudaGetLastError();
+}
+
+cudaError_t rsb_launch_symmetrize(double *cov, int L, int Lp, cudaStream_t st)
+{
+  symmetrize_kernel<<<dim3((L + 127) / 128, L), 128, 0, st>>>(cov, L, Lp);
+  return cudaGetLastError();
+}

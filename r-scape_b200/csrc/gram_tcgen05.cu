@@ -1,0 +1,265 @@
+// gram_tcgen05.cu -- the pair-count contraction on the 5th-generation tensor cores.
+//
+// Replaces the accumulate loop of mutual_naive_ppij (reference src/correlators.c:1724-1755), run
+// over all i<j by corr_NaivePP (:1301-1317).  The reference walks every pair of columns and every
+// sequence; here the whole table set is one integer Gram product over one-hot residue planes,
+//
+//     cnt[a*4+b][i][j] = sum_s wq_s [x_si = a][x_sj = b]          wq_s = round(w_s 2^q)  (pack.cu)
+//                      = sum_k 256^k  sum_s planeA[4i+a][s] * planeB[(j S + k) 4 + b][s]
+//
+// with unsigned 8-bit operands and int32 accumulation (exact), one accumulator column block per
+// weight slice k, recombined to int64 in the epilogue.  S = 1 with wq = 1 is the unweighted count.
+//
+// Kernel shape (one CTA per SM, persistent over a host-built list of upper-triangle tiles):
+//   warp 0      TMA producer : cp.async.bulk.tensor 128B-swizzled boxes of planeA (128 rows) and
+//                              planeB (4*S*CJ rows) x 128 sequences into a 4-stage smem ring
+//   warp 1      MMA issuer   : tcgen05.mma.cta_group::1.kind::i8, M=128, N=4*S*CJ, K=32, D in TMEM
+//   warp 2      TMEM allocator (512 columns = two accumulator buffers)
+//   warps 4-7   epilogue     : tcgen05.ld 32x32b, recombine slices, store int64 count planes
+// Accumulators are double-buffered so the epilogue of tile t overlaps the MMAs of tile t+1.
+#include "rsb_common.cuh"
+
+namespace {
+
+constexpr int NSTAGE       = 4;
+constexpr int GRAM_THREADS = 256;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *tmap, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               :: "r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after()  { asm volatile("tcgen05.fence::after_thread_sync;"  ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem]^T, u8 x u8 -> s32
+__device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\t"
+               "setp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+               :: "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive on an mbarrier once every MMA issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major operand tile, 128-byte rows, SWIZZLE_128B: 8-row groups 1024 B apart (SBO), LBO unused (=1),
+// descriptor version 1 (sm_100), layout type 2.  Fields per cute/arch/mma_sm100_desc.hpp.
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
+  return  (uint64_t) ((saddr >> 4) & 0x3FFFu)
+        | ((uint64_t) 1u  << 16)
+        | ((uint64_t) 64u << 32)
+        | ((uint64_t) 1u  << 46)
+        | ((uint64_t) 2u  << 61);
+}
+
+template <int S>
+__global__ void __launch_bounds__(GRAM_THREADS, 1)
+gram_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
+               const int2 *__restrict__ tiles, int ntiles, int nrep, int L, int Lp, int kstages,
+               long long *__restrict__ cnt)
+{
+  constexpr int      CJ          = rsb_cj_for(S);
+  constexpr int      NT          = 4 * S * CJ;                 // UMMA N
+  constexpr uint32_t A_BYTES     = RSB_MTILE * RSB_KSTAGE;
+  constexpr uint32_t B_BYTES     = NT * RSB_KSTAGE;
+  constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  // instruction descriptor: D = s32 (2 << 4), A/B unsigned 8 bit, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+  constexpr uint32_t IDESC       = (2u << 4) | ((uint32_t) (NT >> 3) << 17) | ((uint32_t) (RSB_MTILE >> 4) << 24);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;      // swizzle-128B tiles need 1024 B alignment
+  const uint32_t bar_base  = smem_base + NSTAGE * STAGE_BYTES;
+  auto full_bar   = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar  = [&](int s) { return bar_base + 8u * (NSTAGE + s); };
+  auto tfull_bar  = [&](int a) { return bar_base + 8u * (2 * NSTAGE + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * NSTAGE + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * NSTAGE + 4);
+  volatile uint32_t *tmem_slot_ptr = (volatile uint32_t *) (smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < NSTAGE; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; a++)      { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const long long nwork = (long long) ntiles * nrep;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (long long w = blockIdx.x; w < nwork; w += gridDim.x) {
+        const int  r = (int) (w / ntiles);
+        const int2 t = tiles[(int) (w % ntiles)];
+        for (int ks = 0; ks < kstages; ks++) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+          const uint32_t sA = smem_base + stage * STAGE_BYTES;
+          tma_load_3d(sA,           &tmapA, full_bar(stage), ks * RSB_KSTAGE, t.x * RSB_MTILE, r);
+          tma_load_3d(sA + A_BYTES, &tmapB, full_bar(stage), ks * RSB_KSTAGE, t.y * NT,        r);
+          if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (one thread)
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0;   uint32_t acc_phase = 0;
+      for (long long w = blockIdx.x; w < nwork; w += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);               // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t) acc * 256u;
+        for (int ks = 0; ks < kstages; ks++) {
+          mbar_wait(full_bar(stage), phase);                       // TMA bytes have landed
+          tc_fence_after();
+          const uint32_t sA    = smem_base + stage * STAGE_BYTES;
+          const uint64_t adesc = smem_desc_sw128(sA);
+          const uint64_t bdesc = smem_desc_sw128(sA + A_BYTES);
+          #pragma unroll
+          for (int k = 0; k < RSB_KSTAGE / 32; k++)                // UMMA K = 32 bytes: +32 B = +2 in the address field
+            umma_i8(d_tmem, adesc + 2u * k, bdesc + 2u * k, IDESC, (uint32_t) ((ks | k) != 0));
+          umma_commit(empty_bar(stage));                           // frees the smem slot when these MMAs retire
+          if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(acc));                               // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue: TMEM -> int64 count planes
+    const int ew = warp - 4;                                       // TMEM lane quarter owned by this warp
+    const int m  = ew * 32 + lane;                                 // accumulator row = planeA row within the tile
+    const int il = m >> 2, a = m & 3;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (long long w = blockIdx.x; w < nwork; w += gridDim.x) {
+      const int  r = (int) (w / ntiles);
+      const int2 t = tiles[(int) (w % ntiles)];
+      const int  i = t.x * RSB_ICOLS + il;
+      long long *base = cnt + ((size_t) r * 16 + (size_t) a * 4) * (size_t) L * Lp + (size_t) i * Lp;
+      const size_t plane = (size_t) L * Lp;
+
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + ((uint32_t) (ew * 32) << 16) + (uint32_t) acc * 256u;
+
+      #pragma unroll 1
+      for (int jl = 0; jl < CJ; jl += 2) {
+        uint32_t d[2][S][4];
+        #pragma unroll
+        for (int u = 0; u < 2; u++)
+          #pragma unroll
+          for (int k = 0; k < S; k++)
+            tmem_ld4(trow + (uint32_t) (((jl + u) * S + k) * 4), d[u][k][0], d[u][k][1], d[u][k][2], d[u][k][3]);
+        tmem_ld_wait();
+
+        const int j0 = t.y * CJ + jl;
+        unsigned long long c[2][4];
+        #pragma unroll
+        for (int u = 0; u < 2; u++)
+          #pragma unroll
+          for (int b = 0; b < 4; b++) {
+            unsigned long long v = 0;
+            #pragma unroll
+            for (int k = S - 1; k >= 0; k--) v = (v << 8) + (unsigned long long) d[u][k][b];
+            c[u][b] = v;
+          }
+        if (i < L) {
+          const bool ok0 = (j0 < L)     && (i < j0);
+          const bool ok1 = (j0 + 1 < L) && (i < j0 + 1);
+          if (ok0 && ok1) {
+            #pragma unroll
+            for (int b = 0; b < 4; b++)
+              *reinterpret_cast<ulonglong2 *>(base + b * plane + j0) = make_ulonglong2(c[0][b], c[1][b]);
+          } else {
+            #pragma unroll
+            for (int b = 0; b < 4; b++) {
+              if (ok0) base[b * plane + j0]     = (long long) c[0][b];
+              if (ok1) base[b * plane + j0 + 1] = (long long) c[1][b];
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+template <int S> constexpr size_t gram_smem_bytes() {
+  return (size_t) NSTAGE * (RSB_MTILE * RSB_KSTAGE + 4 * S * rsb_cj_for(S) * RSB_KSTAGE) + 8 * (2 * NSTAGE + 4) + 16 + 1024;
+}
+
+template <int S>
+cudaError_t launch_gram(const CUtensorMap &tmA, const CUtensorMap &tmB, const int2 *tiles, int ntiles, int nrep,
+                        int L, int Lp, int kstages, long long *cnt, int grid, cudaStream_t st)
+{
+  constexpr size_t smem = gram_smem_bytes<S>();
+  cudaError_t e = cudaFuncSetAttribute(gram_i8_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+  if (e != cudaSuccess) return e;
+  gram_i8_kernel<S><<<grid, GRAM_THREADS, smem, st>>>(tmA, tmB, tiles, ntiles, nrep, L, Lp, kstages, cnt);
+  return cudaGetLastError();
+}
+
+} // namespace
+
+// Host entry used by capi.cu.  tmA/tmB are 3-D tensor maps {Kpad, rows, replicate} with 128B swizzle
+// and boxes {128, 128, 1} / {128, 4*S*CJ, 1}.
+cudaError_t rsb_launch_gram_i8(int S, const CUtensorMap &tmA, const CUtensorMap &tmB, const int2 *tiles, int ntiles,
+                               int nrep, int L, int Lp, int kstages, long long *cnt, int grid, cudaStream_t st)
+{
+  switch (S) {
+  case 1: return launch_gram<1>(tmA, tmB, tiles, ntiles, nrep, L, Lp, kstages, cnt, grid, st);
+  case 2: return launch_gram<2>(tmA, tmB, tiles, ntiles, nrep, L, Lp, kstages, cnt, grid, st);
+  case 3: return launch_gram<3>(tmA, tmB, tiles, ntiles, nrep, L, Lp, kstages, cnt, grid, st);
+  case 4: return launch_gram<4>(tmA, tmB, tiles, ntiles, nrep, L, Lp, kstages, cnt, grid, st);
+  case 5: return launch_gram<5>(tmA, tmB, tiles, ntiles, nrep, L, Lp, kstages, cnt, grid, st);
+  case 6: return launch_gram<6>(tmA, tmB, tiles, ntiles, nrep, L, Lp, kstages, cnt, grid, st);
+  }
+  return cudaErrorInvalidValue;
+}

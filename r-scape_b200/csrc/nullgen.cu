@@ -1,0 +1,271 @@
+// nullgen.cu -- null-alignment generators on the device.
+//
+// (B) null_simulate_kernel: cov_GenerateAlignment's ungapped, structure-free path
+//     (src/cov_simulate.c:289-324 tree walk, :585-631 emission, :724-773 inverse-CDF draw) with
+//     P(t) = exp(tQ) per branch (src/ratematrix.c:185-233; matrices are built on the host in capi.cu,
+//     4x4 per branch).  Every (replicate, column) is an independent chain down the tree, so one thread
+//     owns one (replicate, column) and walks v = 0..N-2 (parents precede children).
+//     Randomness: Philox4x32-10 keyed by (seed, replicate), counter (node, column): one 128-bit block
+//     serves both children of a node.  The reference consumes one Mersenne-Twister stream in branch-major
+//     order; the streams differ, the per-draw distribution is the same (validated distributionally).
+//
+// (A) Fitch + shuffle, R-scape's default null (src/R-scape.c:1653-1668):
+//     fitch_kernel        tree_fitch_column (src/msatree.c:1700-1831): one thread per (replicate, column);
+//                         sets as 5-bit masks, post-order = descending node index, pre-order = ascending.
+//     permute_root_kernel msamanip_ShuffleColumns (src/msamanip.c:1164-1233).  Only the root's permuted row is
+//                         ever read (every other row is overwritten by its parent's row at msamanip.c:1645).
+//     replay_level_kernel shuffle_tree_substitutions + shuffle_tree_substitute_all (src/msamanip.c:1597-1780):
+//                         one warp per (replicate, node) of one tree level; counts the 5x5 substitutions of each
+//                         child branch on the Fitch rows, copies the shuffled parent row to the child and re-places
+//                         the substitutions at positions drawn uniformly without replacement among the columns
+//                         holding the source residue (bitmask + rank-select instead of the reference's Fisher-Yates
+//                         over an index list: same distribution).
+#include "rsb_common.cuh"
+
+namespace {
+
+struct Philox {
+  uint32_t key[2];
+  __device__ __forceinline__ static void round1(uint32_t *c, const uint32_t *k) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k[0], n1 = lo1, n2 = hi0 ^ c[3] ^ k[1], n3 = lo0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+  }
+  __device__ __forceinline__ void block(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t *out) const {
+    uint32_t c[4] = { c0, c1, c2, c3 }, k[2] = { key[0], key[1] };
+    #pragma unroll
+    for (int r = 0; r < 10; r++) { round1(c, k); k[0] += 0x9E3779B9u; k[1] += 0xBB67AE85u; }
+    out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
+  }
+};
+
+__device__ __forceinline__ double u01(uint32_t x) { return (double) x * (1.0 / 4294967296.0); }   // as esl_random: x / 2^32
+
+// ------------------------------------------------------------------------------------------------ generator B
+__global__ void null_simulate_kernel(const int *__restrict__ left, const int *__restrict__ right, const double *__restrict__ pcdf,
+                                     int N, int L, const uint8_t *__restrict__ root, const uint8_t *__restrict__ gapmask,
+                                     unsigned long long seed, int first_rep, uint8_t *__restrict__ res, uint8_t *__restrict__ scratch)
+{
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = first_rep + blockIdx.y;
+  if (c >= L) return;
+  Philox rng; rng.key[0] = (uint32_t) seed ^ (0x9E3779B9u * (uint32_t) (r + 1)); rng.key[1] = (uint32_t) (seed >> 32) + (uint32_t) r;
+  uint8_t *anc  = scratch + (size_t) r * (N - 1) * L;        // internal node states [N-1][L]
+  uint8_t *leaf = res + (size_t) r * N * L;
+  anc[c] = root[c];                                           // cov_add_root
+  for (int v = 0; v < N - 1; v++) {
+    const int par = anc[(size_t) v * L + c] & 3;
+    uint32_t rnd[4];
+    rng.block((uint32_t) v, (uint32_t) c, 0x5eedu, 0u, rnd);
+    #pragma unroll
+    for (int side = 0; side < 2; side++) {
+      const int child = side ? right[v] : left[v];
+      const double *cdf = pcdf + ((size_t) v * 2 + side) * 16 + par * 4;
+      const double x = u01(rnd[side]);
+      int k = 0;                                              // cov_addres: first k with cdf_k > x, else K-1
+      while (k < 3 && !(cdf[k] > x)) k++;
+      if (child > 0) anc[(size_t) child * L + c] = (uint8_t) k;
+      else {
+        uint8_t out = (uint8_t) k;
+        if (gapmask) { const uint8_t g = gapmask[(size_t) (-child) * L + c]; if (g >= 4) out = g; }
+        leaf[(size_t) (-child) * L + c] = out;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ generator A
+__device__ __forceinline__ int pick_member(unsigned set, uint32_t rnd)      // uniform member of a non-empty 5-bit set
+{
+  const int n = __popc(set);
+  const int k = (int) (((unsigned long long) rnd * (unsigned) n) >> 32);
+  return __fns(set, 0, k + 1);
+}
+
+__global__ void fitch_kernel(const int *__restrict__ left, const int *__restrict__ right, int N, int L,
+                             const uint8_t *__restrict__ msa, unsigned long long seed, int first_rep, uint8_t *__restrict__ ancbuf)
+{
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = first_rep + blockIdx.y;
+  if (c >= L) return;
+  Philox rng; rng.key[0] = (uint32_t) seed ^ 0xF17C4u; rng.key[1] = (uint32_t) (seed >> 32) ^ (0x85EBCA6Bu * (uint32_t) (r + 1));
+  uint8_t *anc = ancbuf + (size_t) r * (N - 1) * L;
+  auto leaf_set = [&](int n) -> unsigned {
+    const int x = msa[(size_t) n * L + c];
+    if (x <= 4) return 1u << x;
+    uint32_t rnd[4]; rng.block((uint32_t) n, (uint32_t) c, 0x1eafu, 0u, rnd);          // unknown -> one of the 5 at random (:1735)
+    return 1u << (int) (((unsigned long long) rnd[0] * 5u) >> 32);
+  };
+  // upwards (:1758-1777, :1869-1905): children have larger indices than their parent
+  for (int v = N - 2; v >= 0; v--) {
+    const int l = left[v], rr = right[v];
+    const unsigned Sl = (l > 0) ? anc[(size_t) l * L + c] : leaf_set(-l);
+    const unsigned Sr = (rr > 0) ? anc[(size_t) rr * L + c] : leaf_set(-rr);
+    unsigned S = Sl & Sr;
+    if (!S) S = (Sl | Sr) & 0xFu;                                                         // union of residues; a gap never joins
+    anc[(size_t) v * L + c] = (uint8_t) S;
+  }
+  // downwards (:1779-1815): the stored set is replaced by the chosen residue
+  {
+    uint32_t rnd[4]; rng.block(0xffffffffu, (uint32_t) c, 0x600du, 0u, rnd);
+    anc[c] = (uint8_t) pick_member(anc[c], rnd[0]);
+  }
+  for (int v = 0; v < N - 1; v++) {
+    const int ax = anc[(size_t) v * L + c];
+    uint32_t rnd[4]; rng.block((uint32_t) v, (uint32_t) c, 0xd0c0u, 0u, rnd);
+    const int kids[2] = { left[v], right[v] };
+    #pragma unroll
+    for (int side = 0; side < 2; side++) {
+      const int ch = kids[side];
+      if (ch <= 0) continue;
+      const unsigned S = anc[(size_t) ch * L + c];
+      anc[(size_t) ch * L + c] = (uint8_t) (((S >> ax) & 1u) ? ax : pick_member(S, rnd[side]));
+    }
+  }
+}
+
+// one random permutation per replicate (Fisher-Yates by one thread; L is a few thousand) and the permuted root row
+__global__ void permute_root_kernel(int N, int L, unsigned long long seed, int first_rep, const uint8_t *__restrict__ ancbuf,
+                                    uint8_t *__restrict__ shancbuf, int *__restrict__ permbuf)
+{
+  const int r = first_rep + blockIdx.x;
+  int *perm = permbuf + (size_t) r * L;
+  const uint8_t *anc = ancbuf + (size_t) r * (N - 1) * L;
+  uint8_t *sh = shancbuf + (size_t) r * (N - 1) * L;
+  for (int c = threadIdx.x; c < L; c += blockDim.x) perm[c] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    Philox rng; rng.key[0] = (uint32_t) seed ^ 0x5AFF1Eu; rng.key[1] = (uint32_t) (seed >> 32) + 0x27D4EB2Fu * (uint32_t) (r + 1);
+    uint32_t rnd[4]; int have = 0;
+    for (int n = L; n > 1; n--) {                                                          // esl_vec_IShuffle
+      if (!have) { rng.block((uint32_t) n, 0u, 0x9e37u, 0u, rnd); have = 4; }
+      const int w = (int) (((unsigned long long) rnd[--have] * (unsigned) n) >> 32);
+      const int t = perm[w]; perm[w] = perm[n - 1]; perm[n - 1] = t;
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < L; c += blockDim.x) sh[c] = anc[perm[c]];
+}
+
+constexpr int RP_WARPS = 4;
+constexpr int RP_MAXWORDS = 128;       // columns / 32 supported per warp bitmask (L <= 4096)
+
+// one warp per (replicate, node of this level)
+__global__ void __launch_bounds__(RP_WARPS * 32)
+replay_level_kernel(const int *__restrict__ left, const int *__restrict__ right, const int *__restrict__ order, int lvl_begin, int lvl_count,
+                    int N, int L, const uint8_t *__restrict__ msa, unsigned long long seed, int first_rep, int nrep,
+                    const uint8_t *__restrict__ ancbuf, uint8_t *__restrict__ shancbuf, uint8_t *__restrict__ res)
+{
+  __shared__ unsigned masks[RP_WARPS][5][RP_MAXWORDS];
+  __shared__ int nsub[RP_WARPS][25];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long task = (long long) blockIdx.x * RP_WARPS + warp;
+  if (task >= (long long) lvl_count * nrep) return;
+  const int r = first_rep + (int) (task / lvl_count);
+  const int v = order[lvl_begin + (int) (task % lvl_count)];
+  const int nwords = (L + 31) >> 5;
+  const uint8_t *anc = ancbuf + (size_t) r * (N - 1) * L;
+  uint8_t *shanc = shancbuf + (size_t) r * (N - 1) * L;
+  uint8_t *leaves = res + (size_t) r * N * L;
+  const uint8_t *par_o = anc + (size_t) v * L;
+  const uint8_t *par_s = shanc + (size_t) v * L;
+  Philox rng; rng.key[0] = (uint32_t) seed ^ (0xC2B2AE35u * (uint32_t) (r + 1)); rng.key[1] = (uint32_t) (seed >> 32) ^ (uint32_t) v;
+  uint32_t ctr = 0;
+
+  // class bitmasks of the shuffled parent row (shared by both children: the parent row is read-only here)
+  for (int wd = lane; wd < nwords; wd += 32)
+    #pragma unroll
+    for (int a = 0; a < 5; a++) masks[warp][a][wd] = 0;
+  __syncwarp();
+  for (int c0 = 0; c0 < L; c0 += 32) {
+    const int c = c0 + lane;
+    const int x = (c < L) ? par_s[c] : 255;
+    #pragma unroll
+    for (int a = 0; a < 5; a++) { const unsigned b = __ballot_sync(0xffffffffu, x == a); if (lane == 0) masks[warp][a][c0 >> 5] = b; }
+  }
+  __syncwarp();
+
+  for (int side = 0; side < 2; side++) {
+    const int ch = side ? right[v] : left[v];
+    const uint8_t *kid_o = (ch > 0) ? anc + (size_t) ch * L : msa + (size_t) (-ch) * L;
+    uint8_t *kid_s = (ch > 0) ? shanc + (size_t) ch * L : leaves + (size_t) (-ch) * L;
+    if (lane < 25) nsub[warp][lane] = 0;
+    __syncwarp();
+    for (int c = lane; c < L; c += 32) {
+      const int pa = par_o[c], kd = kid_o[c];
+      if (pa != kd && pa <= 4 && kd <= 4) atomicAdd(&nsub[warp][pa * 5 + kd], 1);        // msamanip.c:1634-1643
+      kid_s[c] = par_s[c];                                                                 // :1645
+    }
+    __syncwarp();
+    for (int a = 0; a < 5; a++) {
+      // working copy of the class-a mask lives in registers: lane owns words lane, lane+32, ...
+      unsigned wv[RP_MAXWORDS / 32]; int pc = 0;
+      #pragma unroll
+      for (int q = 0; q < RP_MAXWORDS / 32; q++) { const int wd = lane + 32 * q; wv[q] = (wd < nwords) ? masks[warp][a][wd] : 0u; pc += __popc(wv[q]); }
+      int remaining = pc;
+      #pragma unroll
+      for (int o = 16; o > 0; o >>= 1) remaining += __shfl_xor_sync(0xffffffffu, remaining, o);
+      for (int d = 0; d < 5; d++) {
+        int s = nsub[warp][a * 5 + d];
+        while (s > 0 && remaining > 0) {
+          uint32_t rnd[4];
+          rng.block(ctr++, (uint32_t) side, 0xab1eu, 0u, rnd);
+          int k = (int) (((unsigned long long) rnd[0] * (unsigned) remaining) >> 32);     // k-th remaining candidate, lane-major order
+          // inclusive scan of per-lane counts to find the owning lane
+          int incl = pc;
+          #pragma unroll
+          for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+          const unsigned owner_ballot = __ballot_sync(0xffffffffu, incl > k);
+          const int owner = __ffs(owner_ballot) - 1;
+          const int before = __shfl_sync(0xffffffffu, incl - pc, owner);
+          if (lane == owner) {
+            int kk = k - before;
+            #pragma unroll
+            for (int q = 0; q < RP_MAXWORDS / 32; q++) {
+              const int n = __popc(wv[q]);
+              if (kk >= 0 && kk < n) {
+                const int bit = __fns(wv[q], 0, kk + 1);
+                wv[q] &= ~(1u << bit);
+                kid_s[(lane + 32 * q) * 32 + bit] = (uint8_t) d;
+                kk = -1;
+              } else if (kk >= 0) kk -= n;
+            }
+            pc--;
+          }
+          remaining--; s--;
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+} // namespace
+
+cudaError_t rsb_launch_null_simulate(const int *left, const int *right, const double *pcdf, int N, int L, const uint8_t *root,
+                                     const uint8_t *gapmask, long long gap_stride, unsigned long long seed, int first_rep, int nrep,
+                                     uint8_t *res, uint8_t *scratch, cudaStream_t st)
+{
+  (void) gap_stride;
+  null_simulate_kernel<<<dim3((L + 127) / 128, nrep), 128, 0, st>>>(left, right, pcdf, N, L, root, gapmask, seed,
+                                                                     first_rep, res, scratch);
+  return cudaGetLastError();
+}
+
+cudaError_t rsb_launch_fitch_shuffle(const int *left, const int *right, const int *parent, const int *order, const int *level_start_host,
+                                     int nlevels, int N, int L, const uint8_t *msa, unsigned long long seed, int first_rep, int nrep,
+                                     uint8_t *res, uint8_t *anc, uint8_t *shanc, int *perm, cudaStream_t st)
+{
+  (void) parent;
+  if (L > RP_MAXWORDS * 32) return cudaErrorInvalidValue;
+  fitch_kernel<<<dim3((L + 127) / 128, nrep), 128, 0, st>>>(left, right, N, L, msa, seed, first_rep, anc);
+  permute_root_kernel<<<nrep, 256, 0, st>>>(N, L, seed, first_rep, anc, shanc, perm);
+  for (int lv = 0; lv < nlevels; lv++) {
+    const int b = level_start_host[lv], cnt = level_start_host[lv + 1] - b;
+    const long long tasks = (long long) cnt * nrep;
+    replay_level_kernel<<<(unsigned) ((tasks + RP_WARPS - 1) / RP_WARPS), RP_WARPS * 32, 0, st>>>(left, right, order, b, cnt, N, L, msa, seed,
+                                                                                                  first_rep, nrep, anc, shanc, res);
+  }
+  return cudaGetLastError();
+}

@@ -1,0 +1,154 @@
+// pack.cu -- residues -> K-major one-hot operand planes for the tcgen05 contraction, plus the
+// small per-column sums.
+//
+// Replaces the per-pair strided column gather of the reference (src/correlators.c:1716-1721):
+// instead of copying two columns out of the row-major alignment for each of the L(L-1)/2 pairs,
+// the alignment is transposed ONCE per scan into
+//     planeA[4i+a][s]          = [x_si == a]                                  (u8 0/1)
+//     planeB[(jS+k)4+b][s]     = [x_sj == b] * digit_k(wq_s)                  (u8 0..255)
+// with s (the contraction dimension) contiguous, which is the layout TMA + UMMA consume.
+// Sequence weights enter as S base-256 digits of the fixed-point weight wq_s = round(w_s 2^q);
+// "both residues canonical" (esl_abc_XIsCanonical, x < K) is implied by the one-hot encoding:
+// gaps (4) and N (15) produce all-zero rows, which is exactly the else-branch at :1751-1753.
+#include "rsb_common.cuh"
+
+namespace {
+
+constexpr int PK_SEQ = 128;     // sequences per block tile (one 128 B line of every output row)
+constexpr int PK_COL = 32;      // alignment columns per block tile
+
+template <int S>
+__global__ void __launch_bounds__(256)
+pack_planes_kernel(const uint8_t *__restrict__ res, int N, int L, long long rep_stride_res,
+                   const uint8_t *__restrict__ wdig, int Kpad,
+                   uint8_t *__restrict__ planeA, int MA, uint8_t *__restrict__ planeB, int NBrows)
+{
+  __shared__ uint8_t tile[PK_SEQ][PK_COL + 1];
+  const int r  = blockIdx.z;
+  const int s0 = blockIdx.x * PK_SEQ;
+  const int c0 = blockIdx.y * PK_COL;
+  const uint8_t *src = res + (size_t) r * rep_stride_res;
+
+  // coalesced read along the alignment row, 32 columns x 128 sequences
+  #pragma unroll
+  for (int q = 0; q < (PK_SEQ * PK_COL) / 256; q++) {
+    const int idx = threadIdx.x + 256 * q;
+    const int sl = idx >> 5, c = idx & 31;
+    const int s = s0 + sl, col = c0 + c;
+    tile[sl][c] = (s < N && col < L) ? src[(size_t) s * L + col] : (uint8_t) 4;
+  }
+  __syncthreads();
+
+  const int chunk = threadIdx.x & 7;          // 16 consecutive sequences
+  const int col   = c0 + (threadIdx.x >> 3);
+  uint8_t x[16];
+  #pragma unroll
+  for (int q = 0; q < 16; q++) x[q] = tile[chunk * 16 + q][threadIdx.x >> 3];
+
+  const size_t koff = (size_t) s0 + chunk * 16;
+  // planeA: four one-hot rows
+  if (4 * col < MA) {
+    #pragma unroll
+    for (int a = 0; a < 4; a++) {
+      uint32_t wv[4] = { 0, 0, 0, 0 };
+      #pragma unroll
+      for (int q = 0; q < 16; q++) wv[q >> 2] |= (uint32_t) (x[q] == a) << (8 * (q & 3));
+      *reinterpret_cast<uint4 *>(planeA + ((size_t) r * MA + 4 * col + a) * Kpad + koff) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+    }
+  }
+  // planeB: S x 4 weighted rows
+  if (4 * S * col < NBrows) {
+    #pragma unroll
+    for (int k = 0; k < S; k++) {
+      const uint4 dg = *reinterpret_cast<const uint4 *>(wdig + (size_t) k * Kpad + koff);
+      const uint32_t dw[4] = { dg.x, dg.y, dg.z, dg.w };
+      #pragma unroll
+      for (int b = 0; b < 4; b++) {
+        uint32_t wv[4];
+        #pragma unroll
+        for (int g = 0; g < 4; g++) {
+          uint32_t m = 0;
+          #pragma unroll
+          for (int q = 0; q < 4; q++) m |= (x[4 * g + q] == b ? 0xFFu : 0u) << (8 * q);
+          wv[g] = dw[g] & m;
+        }
+        *reinterpret_cast<uint4 *>(planeB + ((size_t) r * NBrows + ((size_t) col * S + k) * 4 + b) * Kpad + koff) =
+            make_uint4(wv[0], wv[1], wv[2], wv[3]);
+      }
+    }
+  }
+}
+
+// per-column weighted residue sums in fixed point: colsum[i][a] = sum_s wq_s [x_si == a], a = 0..4 (gap included).
+// Feeds ps (mutual_naive_psi, src/correlators.c:1783-1817).  One thread per column, coalesced across columns.
+__global__ void colsum_kernel(const uint8_t *__restrict__ res, int N, int L, const unsigned long long *__restrict__ wq,
+                              unsigned long long *__restrict__ colsum)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= L) return;
+  unsigned long long acc[5] = { 0, 0, 0, 0, 0 };
+  for (int s = 0; s < N; s++) {
+    const int x = res[(size_t) s * L + i];
+    const unsigned long long w = wq[s];
+    #pragma unroll
+    for (int a = 0; a < 5; a++) acc[a] += (x == a) ? w : 0ull;
+  }
+  #pragma unroll
+  for (int a = 0; a < 5; a++) colsum[(size_t) i * 5 + a] = acc[a];
+}
+
+// Direct (no tensor core) evaluation of the same fixed-point pair counts, one thread per pair.
+// VERIFICATION KERNEL: used by tests to check gram_i8_kernel at sizes the CPU oracle cannot reach,
+// never on the product path.
+__global__ void counts_direct_kernel(const uint8_t *__restrict__ res, int N, int L, int Lp,
+                                     const unsigned long long *__restrict__ wq, long long *__restrict__ cnt)
+{
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.y;
+  if (j >= L || i >= j) return;
+  unsigned long long acc[16];
+  #pragma unroll
+  for (int c = 0; c < 16; c++) acc[c] = 0;
+  for (int s = 0; s < N; s++) {
+    const int xi = res[(size_t) s * L + i], xj = res[(size_t) s * L + j];
+    const unsigned long long w = wq[s];
+    if (xi < 4 && xj < 4) {
+      const int cell = xi * 4 + xj;
+      #pragma unroll
+      for (int c = 0; c < 16; c++) acc[c] += (c == cell) ? w : 0ull;
+    }
+  }
+  #pragma unroll
+  for (int c = 0; c < 16; c++) cnt[((size_t) c * L + i) * Lp + j] = (long long) acc[c];
+}
+
+} // namespace
+
+cudaError_t rsb_launch_pack(int S, const uint8_t *res, int nrep, int N, int L, long long rep_stride_res, const uint8_t *wdig,
+                            int Kpad, uint8_t *planeA, int MA, uint8_t *planeB, int NBrows, int Lcover, cudaStream_t st)
+{
+  dim3 grid(Kpad / PK_SEQ, (Lcover + PK_COL - 1) / PK_COL, nrep);
+  switch (S) {
+  case 1: pack_planes_kernel<1><<<grid, 256, 0, st>>>(res, N, L, rep_stride_res, wdig, Kpad, planeA, MA, planeB, NBrows); break;
+  case 2: pack_planes_kernel<2><<<grid, 256, 0, st>>>(res, N, L, rep_stride_res, wdig, Kpad, planeA, MA, planeB, NBrows); break;
+  case 3: pack_planes_kernel<3><<<grid, 256, 0, st>>>(res, N, L, rep_stride_res, wdig, Kpad, planeA, MA, planeB, NBrows); break;
+  case 4: pack_planes_kernel<4><<<grid, 256, 0, st>>>(res, N, L, rep_stride_res, wdig, Kpad, planeA, MA, planeB, NBrows); break;
+  case 5: pack_planes_kernel<5><<<grid, 256, 0, st>>>(res, N, L, rep_stride_res, wdig, Kpad, planeA, MA, planeB, NBrows); break;
+  case 6: pack_planes_kernel<6><<<grid, 256, 0, st>>>(res, N, L, rep_stride_res, wdig, Kpad, planeA, MA, planeB, NBrows); break;
+  default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t rsb_launch_colsum(const uint8_t *res, int N, int L, const unsigned long long *wq, unsigned long long *colsum, cudaStream_t st)
+{
+  colsum_kernel<<<(L + 127) / 128, 128, 0, st>>>(res, N, L, wq, colsum);
+  return cudaGetLastError();
+}
+
+cudaError_t rsb_launch_counts_direct(const uint8_t *res, int N, int L, int Lp, const unsigned long long *wq, long long *cnt, cudaStream_t st)
+{
+  dim3 grid((L + 127) / 128, L);
+  counts_direct_kernel<<<grid, 128, 0, st>>>(res, N, L, Lp, wq, cnt);
+  return cudaGetLastError();
+}

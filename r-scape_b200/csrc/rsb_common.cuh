@@ -1,0 +1,41 @@
+// rsb_common.cuh -- shared declarations of the sm_100a covariation kernels.
+//
+// Data layout in HBM (per context; R = replicates in flight, L = alignment length, N = sequences,
+// S = number of 8-bit weight slices, Kpad = N rounded up to 128, K = 4 residues):
+//
+//   res      u8   [R][N][L]            digital residues as ESL_MSA ax (A0 C1 G2 U3, gap 4, N 15)
+//   wdig     u8   [S][Kpad]            k-th base-256 digit of round(w_s * 2^q)   (pack.cu)
+//   planeA   u8   [R][MA][Kpad]        one-hot rows, row = 4*i + a, MA = 4*roundup(L,32)
+//   planeB   u8   [R][NB][Kpad]        weighted one-hot rows, row = (j*S + k)*4 + b, value = digit_k(w_s)[x_sj == b]
+//   cnt      i64  [R][16][L][L]        fixed-point pair counts, plane = a*4+b, upper triangle i<j only
+//   pm       f64  [R][L][4]            partner-averaged marginals (corr_Marginals)
+//   cov      f64  [R][L][L]            raw statistic, then corrected in place for the real MSA
+//   hist     u64  [NB_HIST]            cumulative score histogram of the null batch
+//
+// Reference arithmetic: src/correlators.c; each kernel cites its lines.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#define RSB_K      4
+#define RSB_K2     16
+#define RSB_MTILE  128          // UMMA M = 128 rows of planeA = 32 alignment columns i
+#define RSB_ICOLS  32
+#define RSB_KSTAGE 128          // bytes of K (sequences) per pipeline stage = one 128B swizzle atom
+#define RSB_MAX_SLICES 6
+
+#define RSB_CUDA_OK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    rsb_set_error(ctx, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); return 1; } } while (0)
+
+// columns j per gram tile for a given slice count: N tile = 4*S*CJ <= 256 and a multiple of 16
+__host__ __device__ constexpr int rsb_cj_for(int S) { return S == 1 ? 64 : S == 2 ? 32 : S == 3 ? 20 : S == 4 ? 16 : S == 5 ? 12 : 10; }
+
+// statistic / class / correction codes = the reference's enums (src/correlators.h:36-92)
+enum { RSB_CHI = 0, RSB_GT = 3, RSB_MI = 6, RSB_MIr = 9, RSB_MIg = 12, RSB_OMES = 15, RSB_RAF = 18, RSB_RAFS = 21, RSB_CCF = 24 };
+enum { RSB_C16 = 0, RSB_C2 = 1, RSB_CWC = 2, RSB_CSELECT = 3 };
+enum { RSB_APC = 0, RSB_ASC = 1, RSB_NOCORR = 2 };
+
+struct rsb_ctx;
+void rsb_set_error(rsb_ctx *ctx, const char *fmt, ...);

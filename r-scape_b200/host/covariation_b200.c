@@ -1,0 +1,272 @@
+/* covariation_b200.c -- host-side callers of the covariation API, mirrored from the reference so that the
+ * hot path can be driven end to end:
+ *
+ *   cov_CalculateCOV        the covariation-matrix part of cov_Calculate, src/covariation.c:78-258
+ *   cov_CreateRankList ...  rank-list (score histogram) bookkeeping, src/covariation.c:641-736, :2334-2362
+ *   cov_RankListFromCOV     the "ha" fill of cov_SignificantPairs_Ranking, src/covariation.c:415-432
+ *   null_add2cumranklist    src/R-scape.c:1565-1612
+ *   null_rscape_b200        batched form of null_rscape's loop body, src/R-scape.c:1650-1697: all nulls are scanned
+ *                           on the device and only the cumulative histogram comes back.
+ *
+ * E-values, hit lists, power and CaCoFold (src/covariation.c:460-530, 779-1006) stay R-scape host code; they
+ * consume the RANKLIST / mutual_s produced here unchanged.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <limits.h>
+
+#include "rscape_b200_host.h"
+
+/* ------------------------------------------------------------------ cov_Calculate dispatch */
+int
+cov_CalculateCOV(struct data_s *data, ESL_MSA *msa)
+{
+  struct mutual_s *mi = data->mi;
+  COVCLASS covclass = mi->class;
+  int      base, corr, status;
+
+  if (data->covtype >= PTFp) ESL_FAIL(eslFAIL, data->errbuf, "wrong covariation type\n");       /* Potts: out of scope */
+  base = ((int) data->covtype / 3) * 3;
+  corr = (int) data->covtype % 3;                                                                /* 0 raw, 1 APC (p), 2 ASC (a) */
+
+  if (base != RAF && base != RAFS) {                                                             /* :82-84 */
+    status = corr_Probs(data->r, msa, data->T, data->ribosum, mi, data->covmethod, data->tol, data->verbose, data->errbuf);
+    if (status != eslOK) return status;
+  }
+  switch (base) {
+  case CHI:  status = corr_CalculateCHI (covclass, data);      break;
+  case GT:   status = corr_CalculateGT  (covclass, data);      break;
+  case MI:   status = corr_CalculateMI  (covclass, data);      break;
+  case MIr:  status = corr_CalculateMIr (covclass, data);      break;
+  case MIg:  status = corr_CalculateMIg (covclass, data);      break;
+  case OMES: status = corr_CalculateOMES(covclass, data);      break;
+  case RAF:  status = corr_CalculateRAF (covclass, data, msa); break;
+  case RAFS: status = corr_CalculateRAFS(covclass, data, msa); break;
+  case CCF:  status = corr_CalculateCCF (covclass, data);      break;
+  default:   ESL_FAIL(eslFAIL, data->errbuf, "wrong covariation type\n");
+  }
+  if (status != eslOK) return status;
+  if (corr == 1) status = corr_CalculateCOVCorrected(APC, data, FALSE);
+  if (corr == 2) status = corr_CalculateCOVCorrected(ASC, data, FALSE);
+  return status;
+}
+
+/* ------------------------------------------------------------------ rank lists */
+RANKLIST *
+cov_CreateRankList(double bmax, double bmin, double w)
+{
+  RANKLIST *rl = calloc(1, sizeof(RANKLIST));
+  if (!rl) return NULL;
+  rl->ha = esl_histogram_CreateFull(bmin, bmax, w);
+  rl->ht = esl_histogram_CreateFull(bmin, bmax, w);
+  rl->hb = esl_histogram_CreateFull(bmin, bmax, w);
+  if (!rl->ha || !rl->ht || !rl->hb) { cov_FreeRankList(rl); return NULL; }
+  return rl;
+}
+
+void
+cov_FreeRankList(RANKLIST *rl)
+{
+  if (!rl) return;
+  esl_histogram_Destroy(rl->ha);
+  esl_histogram_Destroy(rl->ht);
+  esl_histogram_Destroy(rl->hb);
+  free(rl->survfit);
+  free(rl);
+}
+
+int
+cov_ranklist_Bin2Bin(int b, ESL_HISTOGRAM *h, ESL_HISTOGRAM *newh, int *ret_newb)
+{
+  double x = esl_histogram_Bin2LBound(h, b);
+  *ret_newb = -1;
+  if (!isfinite(x)) return eslERANGE;
+  x = round((x - newh->bmin) / newh->w);
+  if (x < (double) INT_MIN || x > (double) INT_MAX) return eslERANGE;
+  if ((int) x > newh->nb) return eslERANGE;
+  *ret_newb = (int) x;
+  return eslOK;
+}
+
+static void
+copy_hist_meta(const ESL_HISTOGRAM *from, ESL_HISTOGRAM *to)
+{
+  to->n = from->n; to->xmin = from->xmin; to->xmax = from->xmax; to->imin = from->imin; to->imax = from->imax;
+  to->Nc = from->Nc; to->No = from->No;
+}
+
+int
+cov_GrowRankList(RANKLIST **oranklist, double bmax, double bmin)
+{
+  RANKLIST *old = *oranklist, *grown;
+  double    new_bmin = old->ha->bmin;
+  int       b, nb2;
+
+  if (bmin < old->ha->bmin) new_bmin -= fabs(bmin) * 2. * old->ha->w;             /* bmin stays a w-multiple (:694-696) */
+  grown = cov_CreateRankList(ESL_MAX(bmax, old->ha->bmax), new_bmin, old->ha->w);
+  if (!grown) return eslFAIL;
+  copy_hist_meta(old->ha, grown->ha);
+  copy_hist_meta(old->ht, grown->ht);
+  copy_hist_meta(old->hb, grown->hb);
+  for (b = old->ha->imin; b <= old->ha->imax; b++) {
+    cov_ranklist_Bin2Bin(b, old->ha, grown->ha, &nb2);
+    if (nb2 >= 0 && nb2 < grown->ha->nb) grown->ha->obs[nb2] = old->ha->obs[b];
+  }
+  cov_FreeRankList(old);
+  *oranklist = grown;
+  return eslOK;
+}
+
+int
+cov_RankListFromCOV(struct data_s *data, RANKLIST **ret_ranklist)
+{
+  struct mutual_s *mi = data->mi;
+  RANKLIST *rl;
+  double    bmax = mi->maxCOV + 5 * data->w, add;
+  int       i, j;
+
+  while (fabs(bmax - data->bmin) < data->tol) bmax += data->w;
+  if ((rl = cov_CreateRankList(bmax, data->bmin, data->w)) == NULL) ESL_FAIL(eslFAIL, data->errbuf, "rank list allocation failed");
+  for (i = 0; i < mi->alen - 1; i++)
+    for (j = i + 1; j < mi->alen; j++) {
+      if (data->msa2pdb && data->clist == NULL) continue;                          /* PDB distance filter needs R-view's CLIST: out of scope */
+      add = ESL_MAX(mi->COV->mx[i][j], data->bmin + data->w);
+      esl_histogram_Add(rl->ha, add);
+    }
+  *ret_ranklist = rl;
+  return eslOK;
+}
+
+int
+null_add2cumranklist(RANKLIST *ranklist, RANKLIST **ocumranklist, int verbose, char *errbuf)
+{
+  RANKLIST *cum;
+  int       b, cumb;
+  (void) verbose; (void) errbuf;
+
+  if (ranklist == NULL) return eslOK;
+  if (*ocumranklist == NULL) {
+    *ocumranklist = cum = cov_CreateRankList(ranklist->ha->bmax, ranklist->ha->bmin, ranklist->ha->w);
+    if (!cum) return eslFAIL;
+    cum->ha->n = ranklist->ha->n; cum->ha->xmin = ranklist->ha->xmin; cum->ha->xmax = ranklist->ha->xmax;
+    cum->ha->imin = ranklist->ha->imin; cum->ha->imax = ranklist->ha->imax;
+  } else {
+    if (cov_GrowRankList(ocumranklist, ranklist->ha->bmax, ranklist->ha->bmin) != eslOK) return eslFAIL;
+    cum = *ocumranklist;
+    cum->ha->n   += ranklist->ha->n;
+    cum->ha->xmin = ESL_MIN(cum->ha->xmin, ranklist->ha->xmin);
+    cum->ha->xmax = ESL_MAX(cum->ha->xmax, ranklist->ha->xmax);
+    cum->ha->imin = ESL_MIN(cum->ha->imin, ranklist->ha->imin);
+    cum->ha->imax = ESL_MAX(cum->ha->imax, ranklist->ha->imax);
+  }
+  for (b = ranklist->ha->imin; b <= ranklist->ha->imax; b++) {
+    cov_ranklist_Bin2Bin(b, ranklist->ha, cum->ha, &cumb);
+    if (cumb >= 0 && cumb < cum->ha->nb) {
+      cum->ha->obs[cumb] += ranklist->ha->obs[b];
+      cum->ha->Nc        += ranklist->ha->obs[b];
+      cum->ha->No        += ranklist->ha->obs[b];
+    }
+  }
+  return eslOK;
+}
+
+/* ------------------------------------------------------------------ the null loop, batched on the device */
+static int
+slots_for(int nseq, int alen, int nnull)
+{
+  /* enough replicates in flight to give every SM a few tiles, bounded by ~24 GB of operand + count planes */
+  double tiles = ((double) alen / 32.0) * ((double) alen / 12.0) * 0.5 + 1.0;
+  double bytes = 24.0 * alen * (double) nseq + 16.0 * 8.0 * alen * (double) alen + 3.0 * 8.0 * alen * (double) alen + (double) nseq * alen;
+  int    r = (int) ceil(4.0 * 148.0 / tiles);
+  int    rmem = (int) (24e9 / bytes);
+  if (r > rmem) r = rmem;
+  if (r > nnull) r = nnull;
+  if (r > 64) r = 64;
+  if (r < 1) r = 1;
+  return r;
+}
+
+int
+null_rscape_b200(struct data_s *data, ESL_MSA **nulls, int nnull, int hpts, RANKLIST **ret_cumranklist)
+{
+  struct mutual_s *mi = data->mi;
+  rsb_ctx  *ctx = NULL;
+  RANKLIST *cum = NULL;
+  uint8_t  *stage = NULL;
+  uint64_t *bins = NULL, n_added = 0;
+  double   *minmax = NULL, ap[16], w, mn, mx, bmax = -eslINFINITY, xmin = eslINFINITY, xmax = -eslINFINITY;
+  const char *env;
+  size_t    N = (size_t) mi->nseq, L = (size_t) mi->alen;
+  int       base, corr, cls, slots, device = 0, slices = 0, r0, r, s, imax, status = eslFAIL, x, y, nb;
+
+  *ret_cumranklist = NULL;
+  if (nnull < 1) return eslOK;
+  if (data->covtype >= PTFp) ESL_FAIL(eslFAIL, data->errbuf, "wrong covariation type\n");
+  base = ((int) data->covtype / 3) * 3;
+  corr = (int) data->covtype % 3;
+  corr = (corr == 1) ? RSB_CORR_APC : (corr == 2) ? RSB_CORR_ASC : RSB_CORR_NONE;
+  cls  = (int) mi->class;
+  if (cls == CSELECT) cls = (mi->nseq <= mi->nseqthresh || mi->alen <= mi->alenthresh) ? C2 : C16;
+  if (base == CCF) cls = C16;
+  for (x = 0; x < 4; x++) for (y = 0; y < 4; y++) ap[x * 4 + y] = data->allowpair ? data->allowpair->mx[x][y] : 0.0;
+
+  if ((env = getenv("RSCAPE_B200_DEVICE")) != NULL) device = atoi(env);
+  if ((env = getenv("RSCAPE_B200_SLICES")) != NULL) slices = atoi(env);
+  slots = slots_for((int) N, (int) L, nnull);
+  if (rsb_create(device, NULL, &ctx) != 0) { snprintf(data->errbuf, eslERRBUFSIZE, "%s", rsb_create_error()); goto DONE; }
+  if (rsb_configure(ctx, (int) N, (int) L, slots, slices) != 0 ||
+      rsb_set_weights(ctx, nulls[0]->wgt) != 0)                                    /* nulls carry the input's weights (:1668) */
+    { snprintf(data->errbuf, eslERRBUFSIZE, "%s", rsb_error(ctx)); goto DONE; }
+
+  stage  = malloc((size_t) slots * N * L);
+  minmax = malloc(sizeof(double) * 2 * (size_t) nnull);
+  if (!stage || !minmax) { snprintf(data->errbuf, eslERRBUFSIZE, "allocation failed"); goto DONE; }
+
+  /* first null: width of the histogram (calculate_width_histo, :1681-1684) */
+  for (s = 0; s < (int) N; s++) memcpy(stage + (size_t) s * L, nulls[0]->ax[s] + 1, L);
+  if (rsb_null_width(ctx, stage, (int64_t) L, 0, base, cls, corr, data->allowpair ? ap : NULL, data->tol,
+                     data->w, data->bmin, hpts, &w, &mn, &mx) != 0)
+    { snprintf(data->errbuf, eslERRBUFSIZE, "%s.\nFailed to calculate the width of the histogram", rsb_error(ctx)); goto DONE; }
+  data->w = w;
+
+  if (w >= 1e-20) {                                                                /* else "covariation scores are almost constant" (covariation.c:349) */
+    for (r0 = 0; r0 < nnull; r0 += slots) {
+      int n = ESL_MIN(slots, nnull - r0);
+      for (r = 0; r < n; r++)
+        for (s = 0; s < (int) N; s++) memcpy(stage + ((size_t) r * N + (size_t) s) * L, nulls[r0 + r]->ax[s] + 1, L);
+      if (rsb_null_hist(ctx, stage, n, (int64_t) L, (int64_t) (N * L), 0, base, cls, corr, data->allowpair ? ap : NULL,
+                        data->tol, w, data->bmin, minmax + 2 * r0) != 0)
+        { snprintf(data->errbuf, eslERRBUFSIZE, "%s.\nFailed to run null R-scape", rsb_error(ctx)); goto DONE; }
+    }
+    /* cumulative rank list in the reference's form: bmax = largest per-replicate maxCOV + 5w (covariation.c:415, :699) */
+    for (r = 0; r < nnull; r++) {
+      double lo = ESL_MAX(minmax[2 * r], data->bmin + w), hi = ESL_MAX(minmax[2 * r + 1], data->bmin + w), bm = minmax[2 * r + 1] + 5 * w;
+      while (fabs(bm - data->bmin) < data->tol) bm += w;
+      bmax = ESL_MAX(bmax, bm); xmin = ESL_MIN(xmin, lo); xmax = ESL_MAX(xmax, hi);
+    }
+    if ((cum = cov_CreateRankList(bmax, data->bmin, w)) == NULL) { snprintf(data->errbuf, eslERRBUFSIZE, "rank list allocation failed"); goto DONE; }
+    nb = cum->ha->nb;
+    if ((bins = calloc((size_t) nb + 1, sizeof(uint64_t))) == NULL) goto DONE;
+    if (rsb_hist_read(ctx, bins, nb, &n_added, &imax) != 0) { snprintf(data->errbuf, eslERRBUFSIZE, "%s", rsb_error(ctx)); goto DONE; }
+    for (s = 0; s < nb; s++) { cum->ha->obs[s] = bins[s]; cum->ha->Nc += bins[s]; cum->ha->No += bins[s]; }
+    cum->ha->n    = n_added;
+    cum->ha->xmin = xmin;
+    cum->ha->xmax = xmax;
+    esl_histogram_Score2Bin(cum->ha, xmin, &cum->ha->imin);
+    esl_histogram_Score2Bin(cum->ha, xmax, &cum->ha->imax);
+  }
+  /* quirk Q3: mi keeps the last null's nseff / ngap (read by power_SPAIR_Create, src/power.c:94-95) */
+  if (w >= 1e-20 && base != RAF && base != RAFS && rsb_last_nseff(ctx, mi->nseff[0], mi->ngap[0]) != 0)
+    { snprintf(data->errbuf, eslERRBUFSIZE, "%s", rsb_error(ctx)); goto DONE; }
+
+  *ret_cumranklist = cum; cum = NULL;
+  status = eslOK;
+
+ DONE:
+  if (cum) cov_FreeRankList(cum);
+  free(stage); free(minmax); free(bins);
+  if (ctx) rsb_destroy(ctx);
+  return status;
+}

@@ -1,14 +1,15 @@
 /* easel_shim.c -- implementations behind include/easel_compat/easel.h.
  *
- * TEST / HOST INFRASTRUCTURE.  This is NOT Easel: it is a from-scratch restatement of the
+ * HOST INFRASTRUCTURE shared with the test oracle.  This is NOT Easel: it is a from-scratch restatement of the
  * few Easel routines that R-scape's covariation path calls (`nm src/correlators.o` in the
  * reference; SURVEY.md section 8c lists them), following the upstream semantics summarised in
  * SURVEY.md section 9.7.  Easel is an un-vendored submodule of the reference
  * (configure.ac:128-129, no version pin), so parity of these routines against real Easel is
  * UNPINNED except where the tutorial transcript pins the composition (tests/test_golden_tutorial.py).
  *
- * Linked into: oracle/_ref/librscape_ref.so (reference src/correlators.c compiled unchanged),
- * oracle/liboracle.so (CPU restatement) and the host-side mirror in r-scape_b200/host.
+ * Linked into: r-scape_b200/librscape_b200_host.so (the host-side mirror of the reference API; inside a
+ * real R-scape tree the real libeasel is linked instead), oracle/liboracle.so (CPU restatement) and
+ * oracle/_ref/librscape_ref.so (reference sources compiled unchanged).
  */
 #include <stdarg.h>
 #include "easel.h"

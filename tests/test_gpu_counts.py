@@ -1,0 +1,67 @@
+"""Pair counts on the tensor cores vs the CPU oracle: bit-exact (integer fixed-point arithmetic).
+
+Reference: mutual_naive_ppij accumulate loop, src/correlators.c:1724-1755.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(ctx, oracle, msa, wgt, nslices):
+    N, L = msa.shape
+    ctx.configure(N, L, 1, nslices)
+    ctx.set_weights(wgt)
+    ctx.scan(msa, want_cov=False)
+    wq, q, S = ctx.quantisation()
+    if nslices:
+        assert S == nslices
+    ref = np.triu(oracle.counts_fixed(msa, wq).transpose(2, 0, 1), 1)
+    got = ctx.counts()
+    if not np.array_equal(got, ref):
+        bad = np.argwhere(got != ref)
+        raise AssertionError(f"{len(bad)} of {ref.size} counts differ; first {bad[:5].tolist()} got {got[tuple(bad[0])]} want {ref[tuple(bad[0])]}")
+    # the direct (non tensor core) verification kernel must agree as well
+    assert np.array_equal(ctx.counts_direct(msa), ref)
+    # quantisation error bound: |w - wq 2^-q| <= 2^-(q+1)
+    if wgt is not None:
+        assert np.max(np.abs(wgt - wq * 2.0 ** (-q))) <= 2.0 ** (-q - 1) * (1 + 1e-12)
+
+
+@pytest.mark.parametrize("nslices", [1, 2, 3, 4, 5, 6])
+def test_counts_all_slice_counts(ctx, po, oracle, nslices):
+    msa, wgt, _ = po.synthetic_msa(333, 77, seed=nslices)
+    if nslices == 1:
+        wgt = np.ones(333)
+    _check(ctx, oracle, msa, wgt, nslices)
+
+
+@pytest.mark.parametrize("N,L", [(1, 2), (2, 2), (5, 3), (129, 33), (128, 32), (257, 64), (1000, 76), (640, 130)])
+def test_counts_shapes(ctx, po, oracle, N, L):
+    msa, wgt, _ = po.synthetic_msa(N, L, seed=N + L)
+    _check(ctx, oracle, msa, wgt, 0)
+
+
+def test_counts_unit_weights_auto_single_slice(ctx, po, oracle):
+    msa, _, _ = po.synthetic_msa(500, 60, seed=3)
+    _check(ctx, oracle, msa, np.ones(500), 0)
+    assert ctx.quantisation()[2] == 1 and ctx.quantisation()[1] == 0
+
+
+def test_counts_all_gaps_and_unknowns(ctx, po, oracle):
+    rng = np.random.default_rng(5)
+    msa = rng.integers(0, 4, (200, 40)).astype(np.uint8)
+    msa[:, 3] = 4            # an all-gap column
+    msa[:, 7] = 15           # an all-N column
+    msa[17, :] = 4           # an all-gap sequence
+    wgt = rng.gamma(2.0, 0.5, 200)
+    _check(ctx, oracle, msa, wgt, 0)
+
+
+def test_counts_extreme_weights(ctx, po, oracle):
+    rng = np.random.default_rng(9)
+    msa = rng.integers(0, 5, (300, 50)).astype(np.uint8)
+    wgt = np.concatenate([rng.uniform(1e-6, 1e-3, 100), rng.uniform(0.5, 2, 199), [250.0]])
+    _check(ctx, oracle, msa, wgt, 6)
+    wgt[0] = 0.0
+    _check(ctx, oracle, msa, wgt, 5)
