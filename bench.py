@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py -- R-scape covariation scan throughput on B200 (BASELINE.json metric).
+
+Workload (config.workload): BASELINE.json configs[2], the SSU-rRNA-shaped alignment L=1800, N=10000 with 100
+null replicates, statistic GTp (G-test + APC).  One *step* is the whole job of null_rscape + run_rscape
+(src/R-scape.c:1616-1724, 2548-2724) for that alignment: the width pass on the first null, 100 null scans into
+the cumulative histogram and the scan of the input alignment = 102 scans = 102 * L(L-1)/2 * N pair-cells...
+reported with the metric's own definition of a pair-cell count per scan, L^2*N/2.
+
+  value   whole-job pair-cells/s with every input already resident in HBM (CUDA events, max over ranks)
+  e2e     the same job through the C-ABI with HOST buffers: pinned host alignments in, cumulative histogram and
+          the input alignment's score matrix out, copies inside the timed region
+  N > 1   the 100 nulls are dealt round-robin to the ranks (one process per GPU, torchrun), every rank repeats
+          the width pass (no communication needed to agree on w), rank 0 also scans the input alignment; the
+          per-rank histograms are summed with one NCCL all-reduce.  Total work is fixed: "scaling": "strong".
+
+--impl reference times the reference's own CPU implementation of the path (oracle/_ref: src/correlators.c compiled
+unchanged; the oracle port if that build is absent) on the host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as ge  # noqa: E402
+
+WORKLOADS = {
+    "trna": dict(L=76, N=1000, nulls=20),
+    "rnasep": dict(L=400, N=5000, nulls=20),
+    "ssu": dict(L=1800, N=10000, nulls=100),
+    "lsu": dict(L=3500, N=20000, nulls=20),
+}
+METRIC = "pair-cells/s (L^2*N/2) GTp+APC incl. nulls"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return dict(hbm_gbs=p["hbm_gbs"], bf16=p.get("bf16_tflops_sustained", p["bf16_tflops"]), src="measured")
+    return dict(hbm_gbs=6650.0, bf16=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index, self.proc, self.rows = index, None, []
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[k] for r in self.rows if len(r) >= 7 for k in range(4) if r[3 + k].lower().startswith("active")})
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
+                    samples=len(sm))
+
+
+# ---------------------------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    wl = WORKLOADS[args.workload]
+    L, N = wl["L"], wl["N"]
+    po = ge.load_oracle()
+    msa, wgt, _ = po.synthetic_msa(N, L, seed=42)
+    cores = os.cpu_count() or 1
+    nthreads = max(1, min(cores, 64))
+    ncols = args.ref_cols                       # columns per thread task (bounded sample of the L x L pair grid)
+    use_ref = po.RefLib.available()
+    kind = "reference" if use_ref else "port"
+    lib = po.RefLib() if use_ref else None
+    ora = None if use_ref else po.Oracle()
+    rng = np.random.default_rng(1)
+
+    def task(c0):
+        sub = np.ascontiguousarray(msa[:, c0:c0 + ncols])
+        if use_ref:                               # the reference's own corr_Probs + corr_CalculateGT + COVCorrected
+            lib.scan(sub, wgt, po.GT, po.C16, po.APC)
+        else:
+            ora.scan(sub, wgt, po.GT, po.C16, po.APC)
+
+    def one_step():
+        starts = [int(rng.integers(0, L - ncols)) for _ in range(nthreads)]
+        th = [threading.Thread(target=task, args=(c0,)) for c0 in starts]
+        t0 = time.perf_counter()
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        return time.perf_counter() - t0
+
+    for _ in range(args.warmup):
+        one_step()
+    times = [one_step() for _ in range(args.steps)]
+    cells_per_step = nthreads * (ncols * ncols * N / 2.0)
+    total = sum(times)
+    value = cells_per_step * args.steps / total
+    sample = f"{nthreads} threads x one scan (corr_Probs+GT+APC) of a {ncols}-column slice of the L={L} N={N} alignment per step"
+    line = dict(impl="reference", metric=METRIC, value=value, unit="pair-cells/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=1e3 * total / args.steps, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64", data="synthetic",
+                config=dict(workload=f"{args.workload}: L={L} N={N} nulls={wl['nulls']} GTp+APC (bounded sample)", sample=sample),
+                cpu_baseline=dict(value=value, unit="pair-cells/s", cores=nthreads, kind=kind, sample=sample),
+                e2e=dict(value=value, unit="pair-cells/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+    return 0
+
+
+def cpu_baseline_sample(args, msa, wgt):
+    """The reference's CPU path on a bounded sample (about 10-30 s of CPU work), rank 0 at N=1 only."""
+    po = ge.load_oracle()
+    N, L = msa.shape
+    cores = os.cpu_count() or 1
+    nthreads = max(1, min(cores, 64))
+    ncols = args.ref_cols
+    use_ref = po.RefLib.available()
+    lib = po.RefLib() if use_ref else None
+    ora = None if use_ref else po.Oracle()
+
+    def task(c0):
+        sub = np.ascontiguousarray(msa[:, c0:c0 + ncols])
+        (lib or ora).scan(sub, wgt, po.GT, po.C16, po.APC)
+
+    reps, t_total = 0, 0.0
+    rng = np.random.default_rng(2)
+    while t_total < args.cpu_seconds and reps < 50:
+        th = [threading.Thread(target=task, args=(int(rng.integers(0, L - ncols)),)) for _ in range(nthreads)]
+        t0 = time.perf_counter()
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        t_total += time.perf_counter() - t0
+        reps += 1
+    cells = reps * nthreads * (ncols * ncols * N / 2.0)
+    return dict(value=cells / t_total, unit="pair-cells/s", cores=nthreads, kind="reference" if use_ref else "port",
+                sample=f"{reps} x {nthreads} threads, each one scan (corr_Probs+GT+APC) of a {ncols}-column slice of the L={L} N={N} alignment "
+                       f"({t_total:.1f} s)")
+
+
+# ---------------------------------------------------------------------------------------------- B200 arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="ssu", choices=sorted(WORKLOADS))
+    ap.add_argument("--slices", type=int, default=5, help="8-bit weight slices (fixed-point weight width = 8*slices bits)")
+    ap.add_argument("--ref-cols", type=int, default=160)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    pkg = ge.load_package()
+    synth = pkg.synth
+
+    wl = WORKLOADS[args.workload]
+    L, N, R = wl["L"], wl["N"], wl["nulls"]
+    peaks = load_peaks()
+
+    # ---- synthetic inputs (same on every rank: seeded) ------------------------------------------------
+    msa, wgt, _ = synth.synthetic_msa(N, L, seed=42)
+    stream = torch.cuda.current_stream()
+    slots = pkg.replicate_slots(N, L, R, args.slices)
+    ctx = pkg.Context(local, stream.cuda_stream)
+    ctx.configure(N, L, slots, args.slices)
+    ctx.set_weights(wgt)
+    # nulls: R-scape's default null model (Fitch + tree-substitution shuffle) generated on the device from a random tree
+    tree = synth.random_tree(N, np.random.default_rng(42))
+    ctx.set_tree(tree.left, tree.right, tree.parent, tree.ld, tree.rd)
+    my_nulls = list(range(rank, R, world))                           # nulls dealt round-robin to ranks
+    t_gen0 = time.perf_counter()
+    host_nulls = torch.empty((len(my_nulls), N, L), dtype=torch.uint8).pin_memory()
+    hn = host_nulls.numpy()
+    for k0 in range(0, len(my_nulls), slots):
+        n = min(slots, len(my_nulls) - k0)
+        ctx.null_fitch_shuffle(msa, seed=1000 + my_nulls[k0], nrep=n)
+        hn[k0:k0 + n] = ctx.get_slots(n)
+    null0 = hn[0].copy() if rank == 0 else None
+    if world > 1:                                                     # every rank needs replicate 0 for the width pass
+        buf = torch.from_numpy(hn[0].copy() if rank == 0 else np.empty((N, L), np.uint8)).cuda()
+        dist.broadcast(buf, 0)
+        null0 = buf.cpu().numpy()
+    t_gen = time.perf_counter() - t_gen0
+    dev_nulls = host_nulls.cuda()
+    dev_null0 = torch.from_numpy(null0).cuda()
+    dev_msa = torch.from_numpy(msa).cuda()
+    host_msa = torch.from_numpy(msa).pin_memory()
+    host_null0 = torch.from_numpy(null0).pin_memory()
+    cov_out = np.empty((L, L))
+    NB = 1 << 18
+    hist_dev = torch.zeros(NB, dtype=torch.int64, device="cuda")
+
+    def job(nulls, n0, real):
+        """null_rscape + run_rscape for this rank's share of the work."""
+        ctx.hist_reset()
+        w, _, _ = ctx.null_width(n0, pkg.GT, pkg.C16, pkg.APC)                        # calculate_width_histo
+        if len(my_nulls):
+            ctx.null_hist(nulls, w, pkg.GT, pkg.C16, pkg.APC, want_minmax=False)      # run_rscape(RANSS) + null_add2cumranklist
+        out = None
+        if rank == 0:
+            out = ctx.scan(real, pkg.GT, pkg.C16, pkg.APC, want_cov=False)            # run_rscape(GIVSS)
+        bins, n, imax = ctx.hist_read(NB)
+        if world > 1:
+            hist_dev.copy_(torch.from_numpy(bins.astype(np.int64)))
+            dist.all_reduce(hist_dev)
+        return w, bins, out
+
+    scans_total = R + 2
+    cells_per_scan = L * L * N / 2.0
+    cells_total = scans_total * cells_per_scan
+
+    def timed(fn, steps, warm):
+        for _ in range(warm):
+            fn()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- value: inputs resident in HBM -------------------------------------------------------------------
+    sampler = ClockSampler(local)
+    ctx.counters(reset=True)
+    ctx.profile_gram(True)
+    if rank == 0:
+        sampler.start()
+    ms_dev = timed(lambda: job(dev_nulls, dev_null0, dev_msa), args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    cnt = ctx.counters(reset=True)
+    ctx.profile_gram(False)
+    value = cells_total * args.steps / (ms_dev * 1e-3)
+
+    # ---- e2e: host buffers through the C-ABI, copies inside the timed region ------------------------------
+    def job_e2e():
+        ctx.hist_reset()
+        w, _, _ = ctx.null_width(host_null0.numpy(), pkg.GT, pkg.C16, pkg.APC)
+        if len(my_nulls):
+            ctx.null_hist(hn, w, pkg.GT, pkg.C16, pkg.APC, want_minmax=False)
+        if rank == 0:
+            res = ctx.scan(host_msa.numpy(), pkg.GT, pkg.C16, pkg.APC, want_cov=True)
+            cov_out[:] = res["cov"]
+        bins, n, imax = ctx.hist_read(NB)
+        if world > 1:
+            hist_dev.copy_(torch.from_numpy(bins.astype(np.int64)))
+            dist.all_reduce(hist_dev)
+
+    ms_e2e = timed(job_e2e, args.steps, 1)
+    e2e_value = cells_total * args.steps / (ms_e2e * 1e-3)
+    h2d = (len(my_nulls) + 1 + (1 if rank == 0 else 0)) * N * L
+    d2h = NB * 8 + (L * L * 8 if rank == 0 else 0)
+
+    # ---- roofline of the dominant kernel (tcgen05 gram): algorithmic ops / measured launch time -------------
+    # launches during the value run: per step, gram launches = width(1) + ceil(nulls/slots) + real(1 on rank 0)
+    pairs = L * (L - 1) / 2.0
+    gram_ms_avg = cnt["gram_ms"] / max(1, cnt["gram_launches"])
+    scans_this_rank = (len(my_nulls) + 1 + (1 if rank == 0 else 0)) * (args.steps + args.warmup)
+    ops_alg_per_launch = 32.0 * pairs * N * scans_this_rank / max(1, cnt["gram_launches"])
+    achieved = ops_alg_per_launch / (gram_ms_avg * 1e-3) / 1e12 if gram_ms_avg > 0 else 0.0
+    peak_i8 = 2.0 * peaks["bf16"]
+    roofline = dict(bound="tensor", achieved=achieved, peak=peak_i8, unit="TOP/s", frac=achieved / peak_i8,
+                    traffic=None,
+                    note=f"algorithmic int8 ops (32 per pair-cell) of one gram launch / mean launch time {gram_ms_avg:.3f} ms; "
+                         f"the kernel issues {args.slices}x that in tcgen05 kind::i8 MMAs (one pass per 8-bit weight slice): "
+                         f"implementation rate {achieved * args.slices:.1f} TOP/s = {achieved * args.slices / peak_i8:.3f} of peak; "
+                         f"peak = 2 x {peaks['src']} bf16 {peaks['bf16']} TFLOP/s (int8 runs at twice the bf16 rate)",
+                    gram_share_of_step=cnt["gram_ms"] / (ms_dev * (args.steps + args.warmup) / args.steps) if ms_dev > 0 else None)
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = cpu_baseline_sample(args, msa, wgt)
+        line = dict(metric=METRIC, value=value, unit="pair-cells/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=ms_dev / args.steps, higher_is_better=True, scaling="strong", vs_baseline=None,
+                    dtype="u8 x u8 -> s32 tensor-core counts (fixed-point weights), f64 statistics", data="synthetic",
+                    config=dict(workload=f"{args.workload}: L={L} N={N} nulls={R} GTp+APC, scans per step = {scans_total} "
+                                         f"(width pass + {R} nulls + input alignment)",
+                                weight_slices=args.slices, replicate_slots=slots, parallelism=f"nulls round-robin over {world} GPU(s)",
+                                l2="inputs larger than L2 (null alignments %.1f GB, operand planes %.1f GB per replicate)" %
+                                   (R * N * L / 1e9, (4 + 4 * args.slices) * L * N / 1e9),
+                                null_model="Fitch + tree-substitution shuffle generated on the device before the timed region "
+                                           f"({t_gen:.2f} s incl. D2H)"),
+                    e2e=dict(value=e2e_value, unit="pair-cells/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
+                             ms_per_step=ms_e2e / args.steps),
+                    gpu_launches=int(cnt["launches"] * args.steps / (args.steps + args.warmup)),
+                    clocks=clocks, roofline=roofline, cpu_baseline=cpu)
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -57,6 +57,9 @@ glue_ref_fitch_shuffle(ESL_RANDOMNESS *r, ESL_TREE *T, int L, const uint8_t *msa
   return status;
 }
 
+/* e1_rate.c itself needs Easel's file parser; e1_model_Transitions only asks it for a label (src/e1_model.c:123) */
+char *e1_rate_EvomodelType(EVOM evomodel) { (void) evomodel; return "GG"; }
+
 int
 glue_ref_ptime(const double *Q16, double t, double *P16)
 {

@@ -13,6 +13,8 @@ import os
 
 import numpy as np
 
+from . import synth  # noqa: F401  (seeded synthetic workloads, host-side utility)
+
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "librscape_b200.so")
 HOST_LIB_PATH = os.path.join(HERE, "librscape_b200_host.so")
