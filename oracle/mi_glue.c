@@ -93,3 +93,30 @@ glue_mi_export(struct mutual_s *mi, double *pp, double *pm, double *ps, double *
   if (minmax) { minmax[0] = mi->minCOV; minmax[1] = mi->maxCOV; }
   if (type_class) { type_class[0] = (int) mi->type; type_class[1] = (int) MI_CLASS(mi); }
 }
+
+#ifndef GLUE_REFERENCE
+/* drive null_rscape_b200 (batched null loop of the host mirror) from flat arrays; returns the cumulative
+ * rank list's geometry and bins.  meta: { bmin, bmax, w, xmin, xmax }, imeta: { nb, imin, imax }, counts: { n, Nc, No } */
+int
+glue_null_rscape(struct data_s *data, int nnull, int nseq, int L, const uint8_t *nulls, const double *wgt, int hpts,
+                 double *meta, int *imeta, uint64_t *counts, uint64_t *bins, int nb_cap)
+{
+  ESL_MSA **arr = malloc(sizeof(ESL_MSA *) * (size_t) nnull);
+  RANKLIST *cum = NULL;
+  int r, b, status;
+  for (r = 0; r < nnull; r++) arr[r] = glue_msa_create(nseq, L, nulls + (size_t) r * nseq * L, wgt);
+  status = null_rscape_b200(data, arr, nnull, hpts, &cum);
+  if (status == eslOK && cum) {
+    meta[0] = cum->ha->bmin; meta[1] = cum->ha->bmax; meta[2] = cum->ha->w; meta[3] = cum->ha->xmin; meta[4] = cum->ha->xmax;
+    imeta[0] = cum->ha->nb; imeta[1] = cum->ha->imin; imeta[2] = cum->ha->imax;
+    counts[0] = cum->ha->n; counts[1] = cum->ha->Nc; counts[2] = cum->ha->No;
+    for (b = 0; b < cum->ha->nb && b < nb_cap; b++) bins[b] = cum->ha->obs[b];
+    cov_FreeRankList(cum);
+  } else if (status == eslOK) { imeta[0] = 0; }
+  for (r = 0; r < nnull; r++) esl_msa_Destroy(arr[r]);
+  free(arr);
+  return status;
+}
+double glue_data_w(struct data_s *d) { return d->w; }
+int    glue_cov_calculate(struct data_s *d, ESL_MSA *msa) { return cov_CalculateCOV(d, msa); }
+#endif

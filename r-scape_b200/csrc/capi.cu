@@ -14,7 +14,7 @@
 
 // ---- kernel launchers defined in the other translation units
 cudaError_t rsb_launch_gram_i8(int S, const CUtensorMap &tmA, const CUtensorMap &tmB, const int2 *tiles, int ntiles,
-                               int nrep, int L, int Lp, int kstages, long long *cnt, int grid, cudaStream_t st);
+                               int rep0, int nrep, int L, int Lp, int kstages, long long *cnt, int grid, cudaStream_t st);
 cudaError_t rsb_launch_pack(int S, const uint8_t *res, int nrep, int N, int L, long long rep_stride_res, const uint8_t *wdig,
                             int Kpad, uint8_t *planeA, int MA, uint8_t *planeB, int NBrows, int Lcover, cudaStream_t st);
 cudaError_t rsb_launch_colsum(const uint8_t *res, int N, int L, const unsigned long long *wq, unsigned long long *colsum, cudaStream_t st);
@@ -33,7 +33,7 @@ cudaError_t rsb_launch_export_probs(const long long *cnt, int L, int Lp, double 
                                     double *ngap, cudaStream_t st);
 cudaError_t rsb_launch_ps(const unsigned long long *colsum, int L, double scale, double *ps, cudaStream_t st);
 cudaError_t rsb_launch_correct_final(const double *rowpart, const double *colpart, const double *mm, int nrep, int L,
-                                     double *covx, double *scal, cudaStream_t st);
+                                     double *covx, double *scal, double *blocksum, cudaStream_t st);
 cudaError_t rsb_launch_correct_hist(double *cov, const double *covx, const double *scal, int nrep, int L, int Lp, int actype, int mode,
                                     double bmin, const double *wptr, unsigned long long *hist, int nbins, double *mm, double *minmax_out,
                                     int *flags, cudaStream_t st);
@@ -81,7 +81,9 @@ struct rsb_ctx {
   long long *d_cnt = nullptr;
   double *d_nseff = nullptr, *d_pm = nullptr, *d_cov = nullptr, *d_tmp = nullptr;
   double *d_rowpart = nullptr, *d_colpart = nullptr, *d_mm = nullptr, *d_scal = nullptr, *d_covx = nullptr, *d_minmax = nullptr;
-  double *d_meanp = nullptr, *d_w = nullptr;
+  double *d_meanp = nullptr, *d_w = nullptr, *d_blocksum = nullptr;
+  cudaStream_t stream_aux = nullptr, stream_copy = nullptr;     // statistics / uploads of the pipelined null loop
+  cudaEvent_t ev_entry = nullptr, ev_up[2] = { nullptr, nullptr }, ev_counts[2] = { nullptr, nullptr }, ev_stats[2] = { nullptr, nullptr };
   unsigned long long *d_hist = nullptr, *d_colsum = nullptr;
   int *d_flags = nullptr;
   double *d_ps = nullptr, *d_pp_out = nullptr, *d_nseff_out = nullptr, *d_ngap_out = nullptr;
@@ -152,7 +154,7 @@ void free_plan(rsb_ctx *c)
   free_geo(c->geo[0]); free_geo(c->geo[1]);
   dfree(c->d_res); dfree(c->d_planeA); dfree(c->d_planeB); dfree(c->d_cnt); dfree(c->d_nseff); dfree(c->d_pm); dfree(c->d_cov);
   dfree(c->d_tmp); dfree(c->d_rowpart); dfree(c->d_colpart); dfree(c->d_mm); dfree(c->d_scal); dfree(c->d_covx); dfree(c->d_minmax);
-  dfree(c->d_meanp); dfree(c->d_w); dfree(c->d_hist); dfree(c->d_colsum); dfree(c->d_flags); dfree(c->d_ps); dfree(c->d_pp_out);
+  dfree(c->d_meanp); dfree(c->d_w); dfree(c->d_blocksum); dfree(c->d_hist); dfree(c->d_colsum); dfree(c->d_flags); dfree(c->d_ps); dfree(c->d_pp_out);
   dfree(c->d_nseff_out); dfree(c->d_ngap_out); dfree(c->d_left); dfree(c->d_right); dfree(c->d_parent); dfree(c->d_order);
   dfree(c->d_level_start); dfree(c->d_perm); dfree(c->d_pcdf); dfree(c->d_root); dfree(c->d_gapmask); dfree(c->d_simscratch);
   dfree(c->d_msa0); dfree(c->d_anc); dfree(c->d_shanc);
@@ -253,40 +255,56 @@ unsigned allow_mask(const double *allowpair)
   return m;
 }
 
-int upload_msa(rsb_ctx *ctx, const uint8_t *msa, int64_t row_stride, int64_t rep_stride, int nrep, int first_slot, int on_device)
+// alignments -> replicate slots [first_slot, first_slot + nrep) on stream st
+int upload_msa(rsb_ctx *ctx, const uint8_t *msa, int64_t row_stride, int64_t rep_stride, int nrep, int first_slot, int on_device, cudaStream_t st)
 {
   const size_t repbytes = (size_t) ctx->N * ctx->L;
   if (first_slot + nrep > ctx->Rcap) { rsb_set_error(ctx, "%d replicates exceed the configured %d slots", first_slot + nrep, ctx->Rcap); return 1; }
   for (int r = 0; r < nrep; r++) {
     const uint8_t *src = msa + (size_t) r * rep_stride;
     RSB_CUDA_OK(cudaMemcpy2DAsync(ctx->d_res + (size_t) (first_slot + r) * repbytes, ctx->L, src, (size_t) row_stride, ctx->L, ctx->N,
-                                  on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+                                  on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
   }
   return 0;
 }
 
-// pack + gram for replicate slots [0, nrep) with geometry `which`
-int run_counts(rsb_ctx *ctx, int which, int nrep)
+// residues -> operand planes of replicate slots [s0, s0 + nrep) with geometry `which`, on stream st.
+// src: [nrep][N][L] contiguous (the slots themselves, or a caller's device buffer read in place).
+int enqueue_pack(rsb_ctx *ctx, int which, int s0, int nrep, const uint8_t *src, cudaStream_t st)
 {
   if (ensure_geo(ctx, which)) return 1;
   Geo &g = ctx->geo[which];
-  RSB_CUDA_OK(rsb_launch_pack(g.S, ctx->d_res, nrep, ctx->N, ctx->L, (long long) ctx->N * ctx->L, g.d_wdig, ctx->Kpad,
-                              ctx->d_planeA, ctx->MA, ctx->d_planeB, g.NBrows, ctx->Lcover, ctx->stream));
+  RSB_CUDA_OK(rsb_launch_pack(g.S, src, nrep, ctx->N, ctx->L, (long long) ctx->N * ctx->L, g.d_wdig, ctx->Kpad,
+                              ctx->d_planeA + (size_t) s0 * ctx->MA * ctx->Kpad, ctx->MA,
+                              ctx->d_planeB + (size_t) s0 * g.NBrows * ctx->Kpad, g.NBrows, ctx->Lcover, st));
   ctx->launches++;
+  return 0;
+}
+
+// tcgen05 contraction of the planes of slots [s0, s0 + nrep) -> count planes, on stream st
+int enqueue_gram(rsb_ctx *ctx, int which, int s0, int nrep, cudaStream_t st)
+{
+  Geo &g = ctx->geo[which];
   if (g.ntiles > 0) {
     const long long work = (long long) g.ntiles * nrep;
     const int grid = (int) std::min<long long>(work, ctx->sm_count);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
-    if (ctx->profile) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, ctx->stream); }
-    RSB_CUDA_OK(rsb_launch_gram_i8(g.S, ctx->tmA, g.tmB, g.d_tiles, g.ntiles, nrep, ctx->L, ctx->Lp, ctx->Kpad / RSB_KSTAGE,
-                                   ctx->d_cnt, grid, ctx->stream));
-    if (ctx->profile) { cudaEventRecord(e1, ctx->stream); ctx->pending.push_back({ e0, e1 }); }
+    if (ctx->profile) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
+    RSB_CUDA_OK(rsb_launch_gram_i8(g.S, ctx->tmA, g.tmB, g.d_tiles, g.ntiles, s0, nrep, ctx->L, ctx->Lp, ctx->Kpad / RSB_KSTAGE,
+                                   ctx->d_cnt, grid, st));
+    if (ctx->profile) { cudaEventRecord(e1, st); ctx->pending.push_back({ e0, e1 }); }
     ctx->launches++;
     ctx->gram_launches++;
   }
   ctx->cur_geo = which;
-  ctx->last_slot = nrep - 1;
+  ctx->last_slot = s0 + nrep - 1;
   return 0;
+}
+
+int enqueue_counts(rsb_ctx *ctx, int which, int s0, int nrep, const uint8_t *src, cudaStream_t st)
+{
+  if (enqueue_pack(ctx, which, s0, nrep, src, st)) return 1;
+  return enqueue_gram(ctx, which, s0, nrep, st);
 }
 
 int check_flags(rsb_ctx *ctx, const char *what)
@@ -317,45 +335,81 @@ int resolve_stat(rsb_ctx *ctx, int stat, int covclass)
   return 1;
 }
 
-// statistic on the counts of slots [0,nrep); leaves raw cov + correction partials
-int run_statistic(rsb_ctx *ctx, int nrep, int stat, int covclass, unsigned mask)
+// per-slot views of the replicate-indexed buffers
+struct SlotPtrs {
+  long long *cnt; double *nseff, *pm, *cov, *tmp, *scal, *covx, *minmax, *meanp, *blocksum, *mm;
+};
+SlotPtrs slot_ptrs(rsb_ctx *c, int s0)
 {
-  Geo &g = ctx->geo[ctx->cur_geo];
-  if (stat == RSB_RAF || stat == RSB_RAFS) {
-    if (ctx->cur_geo != 1) { rsb_set_error(ctx, "internal: RAF needs unit-weight counts"); return 1; }
-    RSB_CUDA_OK(rsb_launch_raf(ctx->d_cnt, nrep, ctx->L, ctx->Lp, ctx->N, mask, stat == RSB_RAFS, ctx->d_tmp, ctx->d_cov,
-                               ctx->d_rowpart, ctx->d_colpart, ctx->d_mm, ctx->stream));
-    ctx->launches += (stat == RSB_RAFS) ? 3 : 2;
-  } else if (stat == RSB_CCF) {
-    RSB_CUDA_OK(rsb_launch_ccf(ctx->d_nseff, ctx->d_pm, nrep, ctx->L, ctx->Lp, ctx->d_tmp, ctx->d_meanp, ctx->d_cov,
-                               ctx->d_rowpart, ctx->d_colpart, ctx->d_mm, ctx->stream));
-    ctx->launches += 4;
-  } else {
-    RSB_CUDA_OK(rsb_launch_statistic(stat, covclass, ctx->d_cnt, ctx->d_pm, nrep, ctx->L, ctx->Lp, g.scale, g.wtot, mask,
-                                     ctx->d_cov, ctx->d_rowpart, ctx->d_colpart, ctx->d_mm, ctx->stream));
-    ctx->launches++;
-  }
-  RSB_CUDA_OK(rsb_launch_correct_final(ctx->d_rowpart, ctx->d_colpart, ctx->d_mm, nrep, ctx->L, ctx->d_covx, ctx->d_scal, ctx->stream));
-  ctx->launches++;
-  return 0;
+  const size_t L = c->L, Lp = c->Lp;
+  int nJT, nIT; rsb_stat_grid(c->L, &nJT, &nIT);
+  SlotPtrs p;
+  p.cnt = c->d_cnt + (size_t) s0 * 16 * L * Lp;
+  p.nseff = c->d_nseff + (size_t) s0 * L * Lp;
+  p.pm = c->d_pm + (size_t) s0 * L * 4;
+  p.cov = c->d_cov + (size_t) s0 * L * Lp;
+  p.tmp = c->d_tmp + (size_t) s0 * std::max(L * Lp, (size_t) nJT * nIT * 4);
+  p.scal = c->d_scal + (size_t) s0 * 4;
+  p.covx = c->d_covx + (size_t) s0 * L;
+  p.minmax = c->d_minmax + (size_t) s0 * 2;
+  p.meanp = c->d_meanp + (size_t) s0 * 4;
+  p.blocksum = c->d_blocksum + (size_t) s0 * ((L + 127) / 128);
+  p.mm = c->d_mm + (size_t) s0 * nJT * nIT * 2;
+  return p;
 }
 
-int run_probs(rsb_ctx *ctx, int nrep, double tol)
+// marginals (corr_Marginals) for slots [s0, s0+nrep) on stream st
+int enqueue_marginals(rsb_ctx *ctx, int s0, int nrep, double tol, cudaStream_t st)
 {
   Geo &g = ctx->geo[0];
-  if (run_counts(ctx, 0, nrep)) return 1;
-  RSB_CUDA_OK(rsb_launch_marginals(ctx->d_cnt, nrep, ctx->L, ctx->Lp, g.scale, g.wtot, tol, ctx->d_rowpart, ctx->d_colpart,
-                                   ctx->d_nseff, ctx->d_pm, ctx->d_flags, ctx->stream));
+  int nJT, nIT; rsb_stat_grid(ctx->L, &nJT, &nIT);
+  SlotPtrs p = slot_ptrs(ctx, s0);
+  RSB_CUDA_OK(rsb_launch_marginals(p.cnt, nrep, ctx->L, ctx->Lp, g.scale, g.wtot, tol, ctx->d_rowpart + (size_t) s0 * nJT * ctx->L * 4,
+                                   ctx->d_colpart + (size_t) s0 * nIT * ctx->L * 4, p.nseff, p.pm, ctx->d_flags, st));
   ctx->launches += 2;
   return 0;
 }
 
-// full pipeline on slots [0,nrep): counts -> (marginals) -> statistic -> correction partials
+// statistic on the counts of slots [s0, s0+nrep); leaves raw cov, COVx, COVavg and the raw min/max
+int enqueue_statistic(rsb_ctx *ctx, int s0, int nrep, int stat, int covclass, unsigned mask, cudaStream_t st)
+{
+  Geo &g = ctx->geo[ctx->cur_geo];
+  int nJT, nIT; rsb_stat_grid(ctx->L, &nJT, &nIT);
+  SlotPtrs p = slot_ptrs(ctx, s0);
+  double *rowpart = ctx->d_rowpart + (size_t) s0 * nJT * ctx->L, *colpart = ctx->d_colpart + (size_t) s0 * nIT * ctx->L;
+  if (stat == RSB_RAF || stat == RSB_RAFS) {
+    if (ctx->cur_geo != 1) { rsb_set_error(ctx, "internal: RAF needs unit-weight counts"); return 1; }
+    RSB_CUDA_OK(rsb_launch_raf(p.cnt, nrep, ctx->L, ctx->Lp, ctx->N, mask, stat == RSB_RAFS, p.tmp, p.cov, rowpart, colpart, p.mm, st));
+    ctx->launches += (stat == RSB_RAFS) ? 3 : 2;
+  } else if (stat == RSB_CCF) {
+    RSB_CUDA_OK(rsb_launch_ccf(p.nseff, p.pm, nrep, ctx->L, ctx->Lp, p.tmp, p.meanp, p.cov, rowpart, colpart, p.mm, st));
+    ctx->launches += 4;
+  } else {
+    RSB_CUDA_OK(rsb_launch_statistic(stat, covclass, p.cnt, p.pm, nrep, ctx->L, ctx->Lp, g.scale, g.wtot, mask, p.cov, rowpart, colpart, p.mm, st));
+    ctx->launches++;
+  }
+  RSB_CUDA_OK(rsb_launch_correct_final(rowpart, colpart, p.mm, nrep, ctx->L, p.covx, p.scal, p.blocksum, st));
+  ctx->launches += 2;
+  return 0;
+}
+
+// correction + min/max (+ optional write-back / histogram) for slots [s0, s0+nrep)
+int enqueue_correct(rsb_ctx *ctx, int s0, int nrep, int actype, int mode, double bmin, cudaStream_t st)
+{
+  SlotPtrs p = slot_ptrs(ctx, s0);
+  RSB_CUDA_OK(rsb_launch_correct_hist(p.cov, p.covx, p.scal, nrep, ctx->L, ctx->Lp, actype, mode, bmin, ctx->d_w, ctx->d_hist, HIST_BINS,
+                                      p.mm, p.minmax, ctx->d_flags, st));
+  ctx->launches += 2;
+  return 0;
+}
+
+// serial pipeline on the main stream, slots [0,nrep): counts -> (marginals) -> statistic
 int run_pipeline(rsb_ctx *ctx, int nrep, int stat, int covclass, unsigned mask, double tol)
 {
-  if (stat == RSB_RAF || stat == RSB_RAFS) { if (run_counts(ctx, 1, nrep)) return 1; }
-  else if (run_probs(ctx, nrep, tol)) return 1;
-  return run_statistic(ctx, nrep, stat, covclass, mask);
+  const bool raf = (stat == RSB_RAF || stat == RSB_RAFS);
+  if (enqueue_counts(ctx, raf ? 1 : 0, 0, nrep, ctx->d_res, ctx->stream)) return 1;
+  if (!raf && enqueue_marginals(ctx, 0, nrep, tol, ctx->stream)) return 1;
+  return enqueue_statistic(ctx, 0, nrep, stat, covclass, mask, ctx->stream);
 }
 
 int copy_matrix_out(rsb_ctx *ctx, const double *dsrc, double *hdst)   // [L][Lp] device -> [L][L] host
@@ -396,6 +450,14 @@ int rsb_create(int device, void *stream, rsb_ctx **out)
   c->sm_count = prop.multiProcessorCount;
   if (stream) c->stream = (cudaStream_t) stream;
   else { cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking); c->own_stream = true; }
+  cudaStreamCreateWithFlags(&c->stream_aux, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&c->stream_copy, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&c->ev_entry, cudaEventDisableTiming);
+  for (int g = 0; g < 2; g++) {
+    cudaEventCreateWithFlags(&c->ev_up[g], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_counts[g], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_stats[g], cudaEventDisableTiming);
+  }
   *out = c;
   return 0;
 }
@@ -407,6 +469,10 @@ void rsb_destroy(rsb_ctx *ctx)
   cudaStreamSynchronize(ctx->stream);
   for (auto &p : ctx->pending) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   free_plan(ctx);
+  cudaStreamSynchronize(ctx->stream_aux); cudaStreamSynchronize(ctx->stream_copy);
+  cudaStreamDestroy(ctx->stream_aux); cudaStreamDestroy(ctx->stream_copy);
+  cudaEventDestroy(ctx->ev_entry);
+  for (int g = 0; g < 2; g++) { cudaEventDestroy(ctx->ev_up[g]); cudaEventDestroy(ctx->ev_counts[g]); cudaEventDestroy(ctx->ev_stats[g]); }
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -450,6 +516,7 @@ int rsb_configure(rsb_ctx *ctx, int nseq, int alen, int max_replicates, int nsli
   RSB_CUDA_OK(cudaMalloc(&ctx->d_covx, R * L * sizeof(double)));
   RSB_CUDA_OK(cudaMalloc(&ctx->d_minmax, R * 2 * sizeof(double)));
   RSB_CUDA_OK(cudaMalloc(&ctx->d_meanp, R * 4 * sizeof(double)));
+  RSB_CUDA_OK(cudaMalloc(&ctx->d_blocksum, R * ((L + 127) / 128) * sizeof(double)));
   RSB_CUDA_OK(cudaMalloc(&ctx->d_w, sizeof(double)));
   RSB_CUDA_OK(cudaMalloc(&ctx->d_hist, sizeof(unsigned long long) * HIST_BINS));
   RSB_CUDA_OK(cudaMalloc(&ctx->d_colsum, L * 5 * sizeof(unsigned long long)));
@@ -527,8 +594,9 @@ int rsb_probs(rsb_ctx *ctx, const uint8_t *msa, int64_t row_stride, int on_devic
 {
   RSB_CUDA_OK(cudaSetDevice(ctx->device));
   if (ensure_geo(ctx, 0)) return 1;
-  if (upload_msa(ctx, msa, row_stride, 0, 1, 0, on_device)) return 1;
-  if (run_probs(ctx, 1, tol)) return 1;
+  if (upload_msa(ctx, msa, row_stride, 0, 1, 0, on_device, ctx->stream)) return 1;
+  if (enqueue_counts(ctx, 0, 0, 1, ctx->d_res, ctx->stream)) return 1;
+  if (enqueue_marginals(ctx, 0, 1, tol, ctx->stream)) return 1;
   if (pp || pm || ps || nseff || ngap) { if (rsb_fetch_probs(ctx, pp, pm, ps, nseff, ngap)) return 1; }
   return check_flags(ctx, "corr_Probs");
 }
@@ -542,8 +610,8 @@ int rsb_correct_host(rsb_ctx *ctx, int actype, double *cov, double *mincov, doub
   RSB_CUDA_OK(cudaMemcpy2DAsync(ctx->d_cov, sizeof(double) * ctx->Lp, cov, sizeof(double) * ctx->L, sizeof(double) * ctx->L, ctx->L,
                                 cudaMemcpyHostToDevice, ctx->stream));
   RSB_CUDA_OK(rsb_launch_reduce_cov(ctx->d_cov, 1, ctx->L, ctx->Lp, ctx->d_rowpart, ctx->d_colpart, ctx->d_mm, ctx->stream));
-  RSB_CUDA_OK(rsb_launch_correct_final(ctx->d_rowpart, ctx->d_colpart, ctx->d_mm, 1, ctx->L, ctx->d_covx, ctx->d_scal, ctx->stream));
-  ctx->launches += 2;
+  RSB_CUDA_OK(rsb_launch_correct_final(ctx->d_rowpart, ctx->d_colpart, ctx->d_mm, 1, ctx->L, ctx->d_covx, ctx->d_scal, ctx->d_blocksum, ctx->stream));
+  ctx->launches += 3;
   return rsb_correct(ctx, actype, cov, mincov, maxcov);
 }
 
@@ -554,10 +622,10 @@ int rsb_statistic(rsb_ctx *ctx, int stat, int covclass, const double *allowpair,
   if (resolve_stat(ctx, stat, covclass)) return 1;
   if (stat == RSB_RAF || stat == RSB_RAFS) {
     if (!msa) { rsb_set_error(ctx, "RAF/RAFS need the alignment"); return 1; }
-    if (upload_msa(ctx, msa, row_stride, 0, 1, 0, on_device)) return 1;
-    if (run_counts(ctx, 1, 1)) return 1;
+    if (upload_msa(ctx, msa, row_stride, 0, 1, 0, on_device, ctx->stream)) return 1;
+    if (enqueue_counts(ctx, 1, 0, 1, ctx->d_res, ctx->stream)) return 1;
   } else if (ctx->cur_geo != 0) { rsb_set_error(ctx, "rsb_probs must precede this statistic"); return 1; }
-  if (run_statistic(ctx, 1, stat, covclass, allow_mask(allowpair))) return 1;
+  if (enqueue_statistic(ctx, 0, 1, stat, covclass, allow_mask(allowpair), ctx->stream)) return 1;
   double sc[4];
   if (cov) {
     RSB_CUDA_OK(rsb_launch_symmetrize(ctx->d_cov, ctx->L, ctx->Lp, ctx->stream));
@@ -575,10 +643,9 @@ int rsb_correct(rsb_ctx *ctx, int actype, double *cov, double *mincov, double *m
 {
   RSB_CUDA_OK(cudaSetDevice(ctx->device));
   if (actype != RSB_APC && actype != RSB_ASC) { rsb_set_error(ctx, "wrong correction type"); return 1; }
-  RSB_CUDA_OK(rsb_launch_correct_hist(ctx->d_cov, ctx->d_covx, ctx->d_scal, 1, ctx->L, ctx->Lp, actype, 1, 0.0, ctx->d_w, ctx->d_hist,
-                                      HIST_BINS, ctx->d_mm, ctx->d_minmax, ctx->d_flags, ctx->stream));
+  if (enqueue_correct(ctx, 0, 1, actype, 1, 0.0, ctx->stream)) return 1;
   RSB_CUDA_OK(rsb_launch_symmetrize(ctx->d_cov, ctx->L, ctx->Lp, ctx->stream));
-  ctx->launches += 3;
+  ctx->launches++;
   double mmx[2];
   if (cov && copy_matrix_out(ctx, ctx->d_cov, cov)) return 1;
   RSB_CUDA_OK(cudaMemcpyAsync(mmx, ctx->d_minmax, sizeof(mmx), cudaMemcpyDeviceToHost, ctx->stream));
@@ -629,7 +696,7 @@ int rsb_get_counts_direct(rsb_ctx *ctx, const uint8_t *msa, int64_t row_stride, 
   RSB_CUDA_OK(cudaSetDevice(ctx->device));
   Geo &g = ctx->geo[ctx->cur_geo];
   if (!g.ready) { rsb_set_error(ctx, "no weights set"); return 1; }
-  if (upload_msa(ctx, msa, row_stride, 0, 1, 0, 0)) return 1;
+  if (upload_msa(ctx, msa, row_stride, 0, 1, 0, 0, ctx->stream)) return 1;
   RSB_CUDA_OK(cudaMemsetAsync(ctx->d_cnt, 0, (size_t) 16 * ctx->L * ctx->Lp * sizeof(long long), ctx->stream));
   RSB_CUDA_OK(rsb_launch_counts_direct(ctx->d_res, ctx->N, ctx->L, ctx->Lp, g.d_wq, ctx->d_cnt, ctx->stream));
   ctx->launches++;
@@ -642,12 +709,11 @@ int rsb_null_width(rsb_ctx *ctx, const uint8_t *null0, int64_t row_stride, int o
 {
   RSB_CUDA_OK(cudaSetDevice(ctx->device));
   if (resolve_stat(ctx, stat, covclass)) return 1;
-  if (null0 && upload_msa(ctx, null0, row_stride, 0, 1, 0, on_device)) return 1;
+  if (null0 && upload_msa(ctx, null0, row_stride, 0, 1, 0, on_device, ctx->stream)) return 1;
   if (run_pipeline(ctx, 1, stat, covclass, allow_mask(allowpair), tol)) return 1;
-  RSB_CUDA_OK(rsb_launch_correct_hist(ctx->d_cov, ctx->d_covx, ctx->d_scal, 1, ctx->L, ctx->Lp, actype, 0, bmin, ctx->d_w, ctx->d_hist,
-                                      HIST_BINS, ctx->d_mm, ctx->d_minmax, ctx->d_flags, ctx->stream));
+  if (enqueue_correct(ctx, 0, 1, actype, 0, bmin, ctx->stream)) return 1;
   RSB_CUDA_OK(rsb_launch_width(ctx->d_minmax, w_old, bmin, hpts, tol, ctx->d_w, ctx->stream));
-  ctx->launches += 3;
+  ctx->launches++;
   double mmx[2], w;
   RSB_CUDA_OK(cudaMemcpyAsync(mmx, ctx->d_minmax, sizeof(mmx), cudaMemcpyDeviceToHost, ctx->stream));
   RSB_CUDA_OK(cudaMemcpyAsync(&w, ctx->d_w, sizeof(w), cudaMemcpyDeviceToHost, ctx->stream));
@@ -659,15 +725,57 @@ int rsb_null_width(rsb_ctx *ctx, const uint8_t *null0, int64_t row_stride, int o
   return 0;
 }
 
-static int null_hist_chunk(rsb_ctx *ctx, int nrep, int stat, int covclass, int actype, unsigned mask, double tol, double w, double bmin, double *minmax)
+// The null loop, software-pipelined over two groups of replicate slots and three streams:
+//   copy stream : alignments of chunk c+1 -> slots (host buffers only), then pack into operand planes   (HBM)
+//   main stream : tcgen05 gram of chunk c                    (tensor pipe)
+//   aux stream  : marginals, statistic, correction, histogram of chunk c-1   (FP64 / HBM)
+// so the FP64 statistics of one chunk hide under the tensor-core contraction of the next.  Events order the
+// reuse of each slot group; the caller's stream (main) waits for everything before the call returns.
+// src_dev: device-resident nulls [nrep][N][L] read in place (no copy), else host/strided input that is uploaded.
+static int null_hist_pipelined(rsb_ctx *ctx, const uint8_t *nulls, int nrep, int64_t row_stride, int64_t rep_stride, int on_device,
+                               bool in_slots, int stat, int covclass, int actype, unsigned mask, double tol, double w, double bmin,
+                               double *minmax)
 {
-  if (run_pipeline(ctx, nrep, stat, covclass, mask, tol)) return 1;
+  const bool raf = (stat == RSB_RAF || stat == RSB_RAFS);
+  const bool in_place = in_slots || (on_device && row_stride == ctx->L && rep_stride == (int64_t) ctx->N * ctx->L);
+  const int  G = (ctx->Rcap >= 2 && !in_slots) ? 2 : 1;
+  const int  chunk = in_slots ? nrep : std::max(1, ctx->Rcap / G);
+  const size_t repbytes = (size_t) ctx->N * ctx->L;
+
   RSB_CUDA_OK(cudaMemcpyAsync(ctx->d_w, &w, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  RSB_CUDA_OK(rsb_launch_correct_hist(ctx->d_cov, ctx->d_covx, ctx->d_scal, nrep, ctx->L, ctx->Lp, actype, 2, bmin, ctx->d_w, ctx->d_hist,
-                                      HIST_BINS, ctx->d_mm, ctx->d_minmax, ctx->d_flags, ctx->stream));
-  ctx->launches += 2;
-  if (w > 0.0) ctx->hist_n += (unsigned long long) nrep * ((unsigned long long) ctx->L * (ctx->L - 1) / 2);
-  if (minmax) RSB_CUDA_OK(cudaMemcpyAsync(minmax, ctx->d_minmax, sizeof(double) * 2 * nrep, cudaMemcpyDeviceToHost, ctx->stream));
+  RSB_CUDA_OK(cudaEventRecord(ctx->ev_entry, ctx->stream));
+  RSB_CUDA_OK(cudaStreamWaitEvent(ctx->stream_aux, ctx->ev_entry, 0));
+  RSB_CUDA_OK(cudaStreamWaitEvent(ctx->stream_copy, ctx->ev_entry, 0));
+  bool used[2] = { false, false };
+
+  int c = 0;
+  for (int r0 = 0; r0 < nrep; r0 += chunk, c++) {
+    const int g = c % G, s0 = g * chunk, n = std::min(chunk, nrep - r0);
+    const uint8_t *src;
+    if (used[g]) RSB_CUDA_OK(cudaStreamWaitEvent(ctx->stream_copy, ctx->ev_counts[g], 0));       // the group's slots and planes have been consumed
+    if (in_place) src = in_slots ? ctx->d_res : nulls + (size_t) r0 * repbytes;
+    else {
+      if (upload_msa(ctx, nulls + (size_t) r0 * rep_stride, row_stride, rep_stride, n, s0, on_device, ctx->stream_copy)) return 1;
+      src = ctx->d_res + (size_t) s0 * repbytes;
+    }
+    if (enqueue_pack(ctx, raf ? 1 : 0, s0, n, src, ctx->stream_copy)) return 1;                   // HBM-bound transpose: hides under the previous gram
+    RSB_CUDA_OK(cudaEventRecord(ctx->ev_up[g], ctx->stream_copy));
+    RSB_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->ev_up[g], 0));
+    if (used[g]) RSB_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->ev_stats[g], 0));               // counts of this group have been consumed
+    if (enqueue_gram(ctx, raf ? 1 : 0, s0, n, ctx->stream)) return 1;
+    RSB_CUDA_OK(cudaEventRecord(ctx->ev_counts[g], ctx->stream));
+
+    RSB_CUDA_OK(cudaStreamWaitEvent(ctx->stream_aux, ctx->ev_counts[g], 0));
+    if (!raf && enqueue_marginals(ctx, s0, n, tol, ctx->stream_aux)) return 1;
+    if (enqueue_statistic(ctx, s0, n, stat, covclass, mask, ctx->stream_aux)) return 1;
+    if (enqueue_correct(ctx, s0, n, actype, 2, bmin, ctx->stream_aux)) return 1;
+    if (minmax) RSB_CUDA_OK(cudaMemcpyAsync(minmax + 2 * (size_t) r0, ctx->d_minmax + 2 * (size_t) s0, sizeof(double) * 2 * n,
+                                            cudaMemcpyDeviceToHost, ctx->stream_aux));
+    RSB_CUDA_OK(cudaEventRecord(ctx->ev_stats[g], ctx->stream_aux));
+    used[g] = true;
+    if (w > 0.0) ctx->hist_n += (unsigned long long) n * ((unsigned long long) ctx->L * (ctx->L - 1) / 2);
+  }
+  for (int g = 0; g < G; g++) if (used[g]) RSB_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->ev_stats[g], 0));
   return 0;
 }
 
@@ -676,13 +784,8 @@ int rsb_null_hist(rsb_ctx *ctx, const uint8_t *nulls, int nrep, int64_t row_stri
 {
   RSB_CUDA_OK(cudaSetDevice(ctx->device));
   if (resolve_stat(ctx, stat, covclass)) return 1;
-  const unsigned mask = allow_mask(allowpair);
-  for (int r0 = 0; r0 < nrep; r0 += ctx->Rcap) {
-    const int n = std::min(ctx->Rcap, nrep - r0);
-    if (upload_msa(ctx, nulls + (size_t) r0 * rep_stride, row_stride, rep_stride, n, 0, on_device)) return 1;
-    if (null_hist_chunk(ctx, n, stat, covclass, actype, mask, tol, w, bmin, minmax ? minmax + 2 * r0 : nullptr)) return 1;
-    if (minmax || r0 + n < nrep) RSB_CUDA_OK(cudaStreamSynchronize(ctx->stream));   // host staging buffers of the next chunk may alias
-  }
+  if (null_hist_pipelined(ctx, nulls, nrep, row_stride, rep_stride, on_device, false, stat, covclass, actype, allow_mask(allowpair),
+                          tol, w, bmin, minmax)) return 1;
   return check_flags(ctx, "null_rscape");
 }
 
@@ -693,7 +796,8 @@ int rsb_null_hist_slots(rsb_ctx *ctx, int first_rep, int nrep, int stat, int cov
   if (first_rep != 0) { rsb_set_error(ctx, "slots must start at 0"); return 1; }
   if (nrep > ctx->Rcap) { rsb_set_error(ctx, "%d replicates exceed the configured %d slots", nrep, ctx->Rcap); return 1; }
   if (resolve_stat(ctx, stat, covclass)) return 1;
-  if (null_hist_chunk(ctx, nrep, stat, covclass, actype, allow_mask(allowpair), tol, w, bmin, minmax)) return 1;
+  if (null_hist_pipelined(ctx, nullptr, nrep, ctx->L, (int64_t) ctx->N * ctx->L, 1, true, stat, covclass, actype, allow_mask(allowpair),
+                          tol, w, bmin, minmax)) return 1;
   return check_flags(ctx, "null_rscape");
 }
 

@@ -11,46 +11,56 @@
 
 namespace {
 
-constexpr int CH_TI = 32;
-constexpr int CH_TJ = 256;
+constexpr int CH_TI = RSB_TI;
+constexpr int CH_TJ = RSB_TJ;
 constexpr int CH_SMEM_BINS = 4096;
 
-// COVx[i] = sum_{j != i} COV[i][j] / (L-1) from the tile partials; COVavg = 2/(L(L-1)) sum_{i<j} COV;
-// raw min/max from the per-block partials.  One block per replicate; fixed summation order.
-// scal[r][0..3] = { COVavg, raw min, raw max, unused }
-__global__ void __launch_bounds__(256)
-correct_final_kernel(const double *__restrict__ rowpart, const double *__restrict__ colpart, const double *__restrict__ mm,
-                     int L, int nJT, int nIT, double *__restrict__ covx, double *__restrict__ scal)
+// COVx[i] = sum_{j != i} COV[i][j] / (L-1) from the tile partials (one thread per column, fixed summation order);
+// each block also leaves the sum of its row partials (= its share of sum_{i<j} COV) in blocksum[r][block].
+__global__ void __launch_bounds__(128)
+covx_kernel(const double *__restrict__ rowpart, const double *__restrict__ colpart, int L, int nJT, int nIT,
+            double *__restrict__ covx, double *__restrict__ blocksum)
 {
-  __shared__ double red[256], rmin[256], rmax[256];
-  const int r = blockIdx.x;
-  double upper = 0.0;
-  for (int i = threadIdx.x; i < L; i += blockDim.x) {
-    double rs = 0.0, cs = 0.0;
+  __shared__ double red[128];
+  const int r = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  double rs = 0.0, cs = 0.0;
+  if (i < L) {
     for (int jt = 0; jt < nJT; jt++) rs += rowpart[((size_t) r * nJT + jt) * L + i];
     for (int it = 0; it < nIT; it++) cs += colpart[((size_t) r * nIT + it) * L + i];
     double x = rs + cs;
     if (L > 1) x /= (double) L - 1.;
     covx[(size_t) r * L + i] = x;
-    upper += rs;
   }
+  red[threadIdx.x] = rs;
+  __syncthreads();
+  for (int o = 64; o > 0; o >>= 1) { if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o]; __syncthreads(); }
+  if (threadIdx.x == 0) blocksum[(size_t) r * gridDim.x + blockIdx.x] = red[0];
+}
+
+// COVavg = 2/(L(L-1)) sum_{i<j} COV; raw min/max from the per-tile partials.  scal[r][0..3] = { COVavg, raw min, raw max, unused }
+__global__ void __launch_bounds__(256)
+correct_final_kernel(const double *__restrict__ blocksum, int nblk, const double *__restrict__ mm, int L, int ntiles,
+                     double *__restrict__ scal)
+{
+  __shared__ double rmin[256], rmax[256];
+  const int r = blockIdx.x;
   double a = INFINITY, b = -INFINITY;
-  for (int k = threadIdx.x; k < nJT * nIT; k += blockDim.x) {
-    a = fmin(a, mm[((size_t) r * nJT * nIT + k) * 2]);
-    b = fmax(b, mm[((size_t) r * nJT * nIT + k) * 2 + 1]);
+  for (int k = threadIdx.x; k < ntiles; k += blockDim.x) {
+    a = fmin(a, mm[((size_t) r * ntiles + k) * 2]);
+    b = fmax(b, mm[((size_t) r * ntiles + k) * 2 + 1]);
   }
-  red[threadIdx.x] = upper; rmin[threadIdx.x] = a; rmax[threadIdx.x] = b;
+  rmin[threadIdx.x] = a; rmax[threadIdx.x] = b;
   __syncthreads();
   for (int o = 128; o > 0; o >>= 1) {
     if (threadIdx.x < o) {
-      red[threadIdx.x] += red[threadIdx.x + o];
       rmin[threadIdx.x] = fmin(rmin[threadIdx.x], rmin[threadIdx.x + o]);
       rmax[threadIdx.x] = fmax(rmax[threadIdx.x], rmax[threadIdx.x + o]);
     }
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    double avg = red[0];
+    double avg = 0.0;
+    for (int k = 0; k < nblk; k++) avg += blocksum[(size_t) r * nblk + k];        // fixed order
     if (L > 1) avg /= (double) L * ((double) L - 1.);
     avg *= 2.;
     scal[r * 4 + 0] = avg; scal[r * 4 + 1] = rmin[0]; scal[r * 4 + 2] = rmax[0]; scal[r * 4 + 3] = 0.0;
@@ -172,10 +182,12 @@ __global__ void symmetrize_kernel(double *__restrict__ cov, int L, int Lp)
 void rsb_corr_grid(int L, int *nJT, int *nIT) { *nJT = (L + CH_TJ - 1) / CH_TJ; *nIT = (L + CH_TI - 1) / CH_TI; }
 
 cudaError_t rsb_launch_correct_final(const double *rowpart, const double *colpart, const double *mm, int nrep, int L,
-                                     double *covx, double *scal, cudaStream_t st)
+                                     double *covx, double *scal, double *blocksum, cudaStream_t st)
 {
   int nJT, nIT; rsb_corr_grid(L, &nJT, &nIT);
-  correct_final_kernel<<<nrep, 256, 0, st>>>(rowpart, colpart, mm, L, nJT, nIT, covx, scal);
+  const int nblk = (L + 127) / 128;
+  covx_kernel<<<dim3(nblk, nrep), 128, 0, st>>>(rowpart, colpart, L, nJT, nIT, covx, blocksum);
+  correct_final_kernel<<<nrep, 256, 0, st>>>(blocksum, nblk, mm, L, nJT * nIT, scal);
   return cudaGetLastError();
 }
 

@@ -81,7 +81,7 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
 template <int S>
 __global__ void __launch_bounds__(GRAM_THREADS, 1)
 gram_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
-               const int2 *__restrict__ tiles, int ntiles, int nrep, int L, int Lp, int kstages,
+               const int2 *__restrict__ tiles, int ntiles, int rep0, int nrep, int L, int Lp, int kstages,
                long long *__restrict__ cnt)
 {
   constexpr int      CJ          = rsb_cj_for(S);
@@ -126,7 +126,7 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (long long w = blockIdx.x; w < nwork; w += gridDim.x) {
-        const int  r = (int) (w / ntiles);
+        const int  r = rep0 + (int) (w / ntiles);
         const int2 t = tiles[(int) (w % ntiles)];
         for (int ks = 0; ks < kstages; ks++) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
@@ -170,7 +170,7 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
     const int il = m >> 2, a = m & 3;
     int acc = 0; uint32_t acc_phase = 0;
     for (long long w = blockIdx.x; w < nwork; w += gridDim.x) {
-      const int  r = (int) (w / ntiles);
+      const int  r = rep0 + (int) (w / ntiles);
       const int2 t = tiles[(int) (w % ntiles)];
       const int  i = t.x * RSB_ICOLS + il;
       long long *base = cnt + ((size_t) r * 16 + (size_t) a * 4) * (size_t) L * Lp + (size_t) i * Lp;
@@ -236,13 +236,13 @@ template <int S> constexpr size_t gram_smem_bytes() {
 }
 
 template <int S>
-cudaError_t launch_gram(const CUtensorMap &tmA, const CUtensorMap &tmB, const int2 *tiles, int ntiles, int nrep,
+cudaError_t launch_gram(const CUtensorMap &tmA, const CUtensorMap &tmB, const int2 *tiles, int ntiles, int rep0, int nrep,
                         int L, int Lp, int kstages, long long *cnt, int grid, cudaStream_t st)
 {
   constexpr size_t smem = gram_smem_bytes<S>();
   cudaError_t e = cudaFuncSetAttribute(gram_i8_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
   if (e != cudaSuccess) return e;
-  gram_i8_kernel<S><<<grid, GRAM_THREADS, smem, st>>>(tmA, tmB, tiles, ntiles, nrep, L, Lp, kstages, cnt);
+  gram_i8_kernel<S><<<grid, GRAM_THREADS, smem, st>>>(tmA, tmB, tiles, ntiles, rep0, nrep, L, Lp, kstages, cnt);
   return cudaGetLastError();
 }
 
@@ -251,15 +251,15 @@ cudaError_t launch_gram(const CUtensorMap &tmA, const CUtensorMap &tmB, const in
 // Host entry used by capi.cu.  tmA/tmB are 3-D tensor maps {Kpad, rows, replicate} with 128B swizzle
 // and boxes {128, 128, 1} / {128, 4*S*CJ, 1}.
 cudaError_t rsb_launch_gram_i8(int S, const CUtensorMap &tmA, const CUtensorMap &tmB, const int2 *tiles, int ntiles,
-                               int nrep, int L, int Lp, int kstages, long long *cnt, int grid, cudaStream_t st)
+                               int rep0, int nrep, int L, int Lp, int kstages, long long *cnt, int grid, cudaStream_t st)
 {
   switch (S) {
-  case 1: return launch_gram<1>(tmA, tmB, tiles, ntiles, nrep, L, Lp, kstages, cnt, grid, st);
-  case 2: return launch_gram<2>(tmA, tmB, tiles, ntiles, nrep, L, Lp, kstages, cnt, grid, st);
-  case 3: return launch_gram<3>(tmA, tmB, tiles, ntiles, nrep, L, Lp, kstages, cnt, grid, st);
-  case 4: return launch_gram<4>(tmA, tmB, tiles, ntiles, nrep, L, Lp, kstages, cnt, grid, st);
-  case 5: return launch_gram<5>(tmA, tmB, tiles, ntiles, nrep, L, Lp, kstages, cnt, grid, st);
-  case 6: return launch_gram<6>(tmA, tmB, tiles, ntiles, nrep, L, Lp, kstages, cnt, grid, st);
+  case 1: return launch_gram<1>(tmA, tmB, tiles, ntiles, rep0, nrep, L, Lp, kstages, cnt, grid, st);
+  case 2: return launch_gram<2>(tmA, tmB, tiles, ntiles, rep0, nrep, L, Lp, kstages, cnt, grid, st);
+  case 3: return launch_gram<3>(tmA, tmB, tiles, ntiles, rep0, nrep, L, Lp, kstages, cnt, grid, st);
+  case 4: return launch_gram<4>(tmA, tmB, tiles, ntiles, rep0, nrep, L, Lp, kstages, cnt, grid, st);
+  case 5: return launch_gram<5>(tmA, tmB, tiles, ntiles, rep0, nrep, L, Lp, kstages, cnt, grid, st);
+  case 6: return launch_gram<6>(tmA, tmB, tiles, ntiles, rep0, nrep, L, Lp, kstages, cnt, grid, st);
   }
   return cudaErrorInvalidValue;
 }

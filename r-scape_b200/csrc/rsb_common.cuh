@@ -25,6 +25,10 @@
 #define RSB_ICOLS  32
 #define RSB_KSTAGE 128          // bytes of K (sequences) per pipeline stage = one 128B swizzle atom
 #define RSB_MAX_SLICES 6
+// pair-tile of the HBM-bound passes (marginals, statistic, correction, histogram): a block owns
+// RSB_TI rows x RSB_TJ columns of the upper triangle, one thread per column j
+#define RSB_TI     16
+#define RSB_TJ     128
 
 #define RSB_CUDA_OK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
     rsb_set_error(ctx, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); return 1; } } while (0)

@@ -17,8 +17,8 @@
 
 namespace {
 
-constexpr int ST_TI = 32;
-constexpr int ST_TJ = 256;
+constexpr int ST_TI = RSB_TI;
+constexpr int ST_TJ = RSB_TJ;
 
 struct PairProbs { double pp[16]; double ne; double ng; };
 

@@ -181,8 +181,9 @@ slots_for(int nseq, int alen, int nnull)
   double bytes = 24.0 * alen * (double) nseq + 16.0 * 8.0 * alen * (double) alen + 3.0 * 8.0 * alen * (double) alen + (double) nseq * alen;
   int    r = (int) ceil(4.0 * 148.0 / tiles);
   int    rmem = (int) (24e9 / bytes);
+  if (r < 2) r = 2;                     /* two slot groups: statistics of one chunk overlap the contraction of the next */
   if (r > rmem) r = rmem;
-  if (r > nnull) r = nnull;
+  if (r > nnull && nnull >= 2) r = nnull;
   if (r > 64) r = 64;
   if (r < 1) r = 1;
   return r;

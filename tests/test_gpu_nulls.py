@@ -1,0 +1,100 @@
+"""Null loop on the device vs the oracle: the cumulative score histogram must have identical integer bins.
+
+Reference: null_rscape's loop body (src/R-scape.c:1650-1697): calculate_width_histo on the first null, then
+run_rscape(RANSS) + null_add2cumranklist for every null (histogram fill src/covariation.c:415-432).
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def oracle_null_loop(po, oracle, nulls, wgt, stat, cls, ac, w_old=0.05, bmin=-10.0, hpts=400, tol=1e-6):
+    first = oracle.scan(nulls[0], wgt, stat, cls, ac)
+    w = oracle.null_width(w_old, first["mincov"], first["maxcov"], bmin, hpts, tol)
+    cum = None
+    mm = []
+    for msa in nulls:
+        res = oracle.scan(msa, wgt, stat, cls, ac)
+        h = oracle.hist_from_cov(res["cov"], res["maxcov"], bmin, w, tol)
+        cum = oracle.accumulate(cum, h)
+        oracle.free(h)
+        mm.append((res["mincov"], res["maxcov"]))
+    view = oracle.view(cum)
+    oracle.free(cum)
+    return w, view, np.array(mm)
+
+
+def _nulls(po, R, N, L, seed):
+    return np.stack([po.synthetic_msa(N, L, seed=seed + r)[0] for r in range(R)])
+
+
+@pytest.mark.parametrize("R,slots", [(1, 1), (5, 2), (7, 4), (6, 6)])
+def test_null_histogram_matches_oracle(ctx, pkg, po, oracle, R, slots):
+    N, L = 250, 70
+    nulls = _nulls(po, R, N, L, 100)
+    wgt = po.synthetic_msa(N, L, seed=1)[1]
+    w_ref, view, mm_ref = oracle_null_loop(po, oracle, nulls, wgt, po.GT, po.C16, po.APC)
+    ctx.configure(N, L, slots, 0)
+    ctx.set_weights(wgt)
+    w, mn, mx = ctx.null_width(nulls[0])
+    assert abs(w - w_ref) <= 1e-12 * max(1.0, w_ref)
+    mm = ctx.null_hist(nulls, w_ref)
+    bins, n, imax = ctx.hist_read(view.nb + 8)
+    assert n == R * L * (L - 1) // 2 == view.n
+    assert np.array_equal(bins[:view.nb], view.obs), np.argwhere(bins[:view.nb] != view.obs)[:5]
+    assert not bins[view.nb:].any()
+    assert imax == view.imax
+    assert np.max(np.abs(mm - mm_ref)) <= 1e-9 * max(1.0, np.max(np.abs(mm_ref)))
+
+
+def test_null_histogram_device_resident_input(ctx, pkg, po, oracle):
+    import torch
+    N, L, R = 200, 64, 5
+    nulls = _nulls(po, R, N, L, 300)
+    wgt = po.synthetic_msa(N, L, seed=2)[1]
+    w_ref, view, _ = oracle_null_loop(po, oracle, nulls, wgt, po.GT, po.C16, po.APC)
+    ctx.configure(N, L, 2, 0)
+    ctx.set_weights(wgt)
+    dev = torch.from_numpy(nulls).cuda()
+    ctx.null_hist(dev, w_ref, want_minmax=False)
+    bins, n, imax = ctx.hist_read(view.nb)
+    assert np.array_equal(bins, view.obs)
+    # a second batch accumulates on top (cumulative histogram), reset clears
+    ctx.null_hist(dev, w_ref, want_minmax=False)
+    bins2, n2, _ = ctx.hist_read(view.nb)
+    assert np.array_equal(bins2, 2 * view.obs) and n2 == 2 * n
+    ctx.hist_reset()
+    assert not ctx.hist_read(view.nb)[0].any()
+
+
+@pytest.mark.parametrize("stat,cls,ac", [("MI", "C2", "ASC"), ("RAFS", "C2", "APC"), ("CHI", "C16", "NOCORR")])
+def test_null_histogram_other_statistics(ctx, pkg, po, oracle, stat, cls, ac):
+    N, L, R = 120, 40, 3
+    nulls = _nulls(po, R, N, L, 500)
+    wgt = po.synthetic_msa(N, L, seed=3)[1]
+    a = (getattr(po, stat), getattr(po, cls), getattr(po, ac))
+    w_ref, view, _ = oracle_null_loop(po, oracle, nulls, wgt, *a)
+    ctx.configure(N, L, 2, 0)
+    ctx.set_weights(wgt)
+    ctx.null_hist(nulls, w_ref, getattr(pkg, stat), getattr(pkg, cls), getattr(pkg, ac), want_minmax=False)
+    bins, n, imax = ctx.hist_read(view.nb)
+    # scores within 1e-12 of a bin edge may legitimately land in the neighbouring bin: allow a handful, none expected
+    diff = np.abs(bins.astype(np.int64) - view.obs.astype(np.int64)).sum()
+    assert diff <= 2, diff
+
+
+def test_last_null_nseff_quirk_q3(ctx, pkg, po, oracle):
+    N, L, R = 150, 50, 3
+    nulls = _nulls(po, R, N, L, 700)
+    wgt = po.synthetic_msa(N, L, seed=4)[1]
+    ctx.configure(N, L, 2, 0)
+    ctx.set_weights(wgt)
+    w, _, _ = ctx.null_width(nulls[0])
+    ctx.null_hist(nulls, w, want_minmax=False)
+    ne, ng = ctx.last_nseff()
+    ref = oracle.scan(nulls[-1], wgt, po.GT, po.C16, po.APC, want_probs=True)
+    assert np.max(np.abs(ne - ref["nseff"])) <= 1e-9 * N
+    assert np.max(np.abs(np.triu(ng, 1) - np.triu(ref["ngap"], 1))) <= 1e-9 * N
