@@ -14,6 +14,7 @@ import os
 import numpy as np
 
 from . import synth  # noqa: F401  (seeded synthetic workloads, host-side utility)
+from . import parallel  # noqa: F401  (null-replicate sharding over torch.distributed)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "librscape_b200.so")

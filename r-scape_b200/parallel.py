@@ -1,0 +1,40 @@
+"""parallel.py -- sharding of the null loop across the GPUs of one box (one process per GPU, torch.distributed).
+
+The path shards along the null replicates (src/R-scape.c:1650-1697: every iteration only adds into the cumulative
+histogram).  There is no data-path collective: each rank scans its own replicates; the only exchange is the sum of
+the small integer histograms (and min/max of the score range) at the end -- one all-reduce over NCCL on the GPU box,
+gloo in the CPU tests.  The histogram width w is defined by replicate 0 (src/R-scape.c:1681-1684); every rank repeats
+that width pass on the same replicate 0, so no broadcast is needed to agree on w.
+"""
+import numpy as np
+
+
+def null_shard(nnull, world, rank):
+    """Replicate indices scanned by `rank`: dealt round-robin so that every rank gets floor or ceil of nnull/world."""
+    return list(range(rank, nnull, world))
+
+
+def reduce_histogram(bins, device=None, group=None):
+    """Sum uint64 histogram bins over all ranks (no-op without an initialised process group)."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return bins
+    t = torch.from_numpy(bins.astype(np.int64))
+    if device is not None:
+        t = t.to(device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t.cpu().numpy().astype(np.uint64)
+
+
+def reduce_range(lo, hi, device=None, group=None):
+    """Global (min, max) of the per-rank score ranges."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return lo, hi
+    t = torch.tensor([-lo, hi], dtype=torch.float64)
+    if device is not None:
+        t = t.to(device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return -float(t[0]), float(t[1])
