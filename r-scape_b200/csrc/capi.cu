@@ -7,6 +7,7 @@
 #include "../../include/rscape_b200.h"
 #include <cstdarg>
 #include <cstring>
+#include <cstdlib>
 #include <cmath>
 #include <vector>
 #include <string>
@@ -102,6 +103,8 @@ struct rsb_ctx {
   double gram_ms = 0.0;
   bool profile = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending_aux;   // statistics chain of the pipelined null loop
+  double aux_ms = 0.0; long long aux_chains = 0;
 };
 
 void rsb_set_error(rsb_ctx *ctx, const char *fmt, ...)
@@ -468,6 +471,7 @@ void rsb_destroy(rsb_ctx *ctx)
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   for (auto &p : ctx->pending) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+  for (auto &p : ctx->pending_aux) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   free_plan(ctx);
   cudaStreamSynchronize(ctx->stream_aux); cudaStreamSynchronize(ctx->stream_copy);
   cudaStreamDestroy(ctx->stream_aux); cudaStreamDestroy(ctx->stream_copy);
@@ -766,11 +770,14 @@ static int null_hist_pipelined(rsb_ctx *ctx, const uint8_t *nulls, int nrep, int
     RSB_CUDA_OK(cudaEventRecord(ctx->ev_counts[g], ctx->stream));
 
     RSB_CUDA_OK(cudaStreamWaitEvent(ctx->stream_aux, ctx->ev_counts[g], 0));
+    cudaEvent_t a0 = nullptr, a1 = nullptr;
+    if (ctx->profile) { cudaEventCreate(&a0); cudaEventCreate(&a1); cudaEventRecord(a0, ctx->stream_aux); }
     if (!raf && enqueue_marginals(ctx, s0, n, tol, ctx->stream_aux)) return 1;
     if (enqueue_statistic(ctx, s0, n, stat, covclass, mask, ctx->stream_aux)) return 1;
     if (enqueue_correct(ctx, s0, n, actype, 2, bmin, ctx->stream_aux)) return 1;
     if (minmax) RSB_CUDA_OK(cudaMemcpyAsync(minmax + 2 * (size_t) r0, ctx->d_minmax + 2 * (size_t) s0, sizeof(double) * 2 * n,
                                             cudaMemcpyDeviceToHost, ctx->stream_aux));
+    if (ctx->profile) { cudaEventRecord(a1, ctx->stream_aux); ctx->pending_aux.push_back({ a0, a1 }); ctx->aux_chains++; }
     RSB_CUDA_OK(cudaEventRecord(ctx->ev_stats[g], ctx->stream_aux));
     used[g] = true;
     if (w > 0.0) ctx->hist_n += (unsigned long long) n * ((unsigned long long) ctx->L * (ctx->L - 1) / 2);
@@ -987,10 +994,21 @@ int rsb_counters(rsb_ctx *ctx, int64_t *launches, double *gram_ms, int64_t *gram
     }
     ctx->pending.clear();
   }
+  if (!ctx->pending_aux.empty()) {
+    RSB_CUDA_OK(cudaStreamSynchronize(ctx->stream_aux));
+    for (auto &p : ctx->pending_aux) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, p.first, p.second) == cudaSuccess) ctx->aux_ms += ms;
+      cudaEventDestroy(p.first); cudaEventDestroy(p.second);
+    }
+    ctx->pending_aux.clear();
+  }
   if (launches) *launches = ctx->launches;
   if (gram_ms) *gram_ms = ctx->gram_ms;
   if (gram_launches) *gram_launches = ctx->gram_launches;
-  if (reset) { ctx->launches = 0; ctx->gram_ms = 0.0; ctx->gram_launches = 0; }
+  if (getenv("RSCAPE_B200_TRACE")) fprintf(stderr, "[rsb] gram %.3f ms x %lld, statistics chain %.3f ms x %lld\n", ctx->gram_launches ? ctx->gram_ms / ctx->gram_launches : 0.0,
+                                        ctx->gram_launches, ctx->aux_chains ? ctx->aux_ms / ctx->aux_chains : 0.0, ctx->aux_chains);
+  if (reset) { ctx->launches = 0; ctx->gram_ms = 0.0; ctx->gram_launches = 0; ctx->aux_ms = 0.0; ctx->aux_chains = 0; }
   return 0;
 }
 

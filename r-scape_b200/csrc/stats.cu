@@ -14,6 +14,7 @@
 // result is deterministic run to run; no floating-point atomics anywhere.
 #include "rsb_common.cuh"
 #include <math.h>
+#pragma nv_diag_suppress 128      // template branches that return early leave the generic loop unreachable in some instantiations
 
 namespace {
 
@@ -22,28 +23,46 @@ constexpr int ST_TJ = RSB_TJ;
 
 struct PairProbs { double pp[16]; double ne; double ng; };
 
-// fixed-point counts of one pair -> nseff, ngap, pp (prior 1e-10 per cell, Kahan-summed normaliser)
+// exact uint64 -> double without the slow 64-bit I2F path: both 32-bit halves are planted in the mantissa of a
+// power of two and the offsets subtracted (each half exact, one rounding in the final add = the I2F result)
+__device__ __forceinline__ double u64_to_f64(unsigned long long v)
+{
+  const double lo = __longlong_as_double(0x4330000000000000ULL | (v & 0xffffffffULL)) - 4503599627370496.0;              // 2^52
+  const double hi = __longlong_as_double(0x4530000000000000ULL | (v >> 32))           - 19342813113834066795298816.0;   // 2^84
+  return hi + lo;
+}
+
+// fixed-point counts of one pair -> nseff, ngap, pp (prior 1e-10 per cell, Kahan-summed normaliser).
+// EXACT_DIV: divide every cell by the sum as esl_vec_DNorm does (values handed back to the host); otherwise multiply by
+// the reciprocal (1 ulp, inside the 1e-9 score tolerance) -- the statistic kernels are FP64-issue bound.
+template <bool EXACT_DIV>
 __device__ __forceinline__ void load_pair(const long long *__restrict__ cnt, size_t plane, size_t off,
                                           double scale, long long wtot, PairProbs &P)
 {
-  long long c[16];
+  unsigned long long c[16];
   #pragma unroll
-  for (int k = 0; k < 16; k++) c[k] = cnt[k * plane + off];
-  long long ne = 0;
+  for (int k = 0; k < 16; k++) c[k] = (unsigned long long) cnt[k * plane + off];
+  unsigned long long ne = 0;
   #pragma unroll
   for (int k = 0; k < 16; k++) ne += c[k];
-  P.ne = (double) ne * scale;
-  P.ng = (double) (wtot - ne) * scale;
+  P.ne = u64_to_f64(ne) * scale;
+  P.ng = u64_to_f64((unsigned long long) wtot - ne) * scale;
   double sum = 0.0, comp = 0.0;
   #pragma unroll
   for (int k = 0; k < 16; k++) {
-    P.pp[k] = 1e-10 + (double) c[k] * scale;
+    P.pp[k] = 1e-10 + u64_to_f64(c[k]) * scale;
     const double y = P.pp[k] - comp, t = sum + y;      // esl_vec_DSum is Kahan-compensated
     comp = (t - sum) - y;
     sum  = t;
   }
-  #pragma unroll
-  for (int k = 0; k < 16; k++) P.pp[k] = P.pp[k] / sum;
+  if (EXACT_DIV) {
+    #pragma unroll
+    for (int k = 0; k < 16; k++) P.pp[k] = P.pp[k] / sum;
+  } else {
+    const double inv = 1.0 / sum;
+    #pragma unroll
+    for (int k = 0; k < 16; k++) P.pp[k] = P.pp[k] * inv;
+  }
 }
 
 __device__ __forceinline__ double warp_sum(double v)
@@ -75,7 +94,7 @@ marg_partial_kernel(const long long *__restrict__ cnt, int L, int Lp, double sca
     double rs[4] = { 0, 0, 0, 0 };
     if (tile_live && i < L && j < L && i < j) {
       PairProbs P;
-      load_pair(c, plane, (size_t) i * Lp + j, scale, wtot, P);
+      load_pair<false>(c, plane, (size_t) i * Lp + j, scale, wtot, P);
       nseff[((size_t) r * L + i) * Lp + j] = P.ne;
       if (P.ne > 0) {                                                    // :1354
         #pragma unroll
@@ -132,7 +151,8 @@ __global__ void marg_final_kernel(const double *__restrict__ rowpart, const doub
 __device__ __forceinline__ bool cell_allowed(unsigned mask, int x, int y) { return (mask >> (x * 4 + y)) & 1u; }
 
 template <int STAT, int CLS>
-__device__ __forceinline__ double pair_statistic(const PairProbs &P, const double *mi, const double *mj, unsigned mask)
+__device__ __forceinline__ double pair_statistic(const PairProbs &P, const double *mi, const double *mj,
+                                                 const double *lmi, const double *lmj, unsigned mask)
 {
   double v = 0.0, H = 0.0;
   if (CLS == RSB_C2) {
@@ -168,10 +188,20 @@ __device__ __forceinline__ double pair_statistic(const PairProbs &P, const doubl
     }
     return v;
   }
-  double lmi[4], lmj[4];
-  if (STAT == RSB_MI || STAT == RSB_MIg || STAT == RSB_MIr) {
+  // lmi / lmj: log of the marginals, taken once per column by the caller.
+  if (STAT == RSB_GT && CLS == RSB_C16) {
+    // G = 2 sum obs log(obs/exp) with obs = ne pp, exp = ne pm_i pm_j (:383-387): ne cancels inside the log, so
+    // G = 2 ne sum pp (log pp - log pm_i - log pm_j), one log per cell and no division.  The terms kept are the
+    // same (exp > 0 and obs > 0 <=> ne > 0, pm_i > 0, pm_j > 0, pp > 0); the rounding differs at the 1e-15 level.
+    if (!(P.ne > 0.)) return 0.0;
     #pragma unroll
-    for (int x = 0; x < 4; x++) { lmi[x] = log(mi[x]); lmj[x] = log(mj[x]); }
+    for (int x = 0; x < 4; x++)
+      #pragma unroll
+      for (int y = 0; y < 4; y++) {
+        const double pxy = P.pp[x * 4 + y];
+        v += (pxy > 0.0 && mi[x] > 0.0 && mj[y] > 0.0) ? pxy * (log(pxy) - lmi[x] - lmj[y]) : 0.0;
+      }
+    return 2.0 * P.ne * v;
   }
   #pragma unroll
   for (int x = 0; x < 4; x++)
@@ -205,7 +235,7 @@ stat_kernel(const long long *__restrict__ cnt, const double *__restrict__ pm, in
             double *__restrict__ mm, int nJT, int nIT)
 {
   __shared__ double rowacc[ST_TJ / 32][ST_TI];
-  __shared__ double pmi[ST_TI][4];
+  __shared__ double pmi[ST_TI][4], lpmi[ST_TI][4];
   __shared__ double smin[ST_TJ / 32], smax[ST_TJ / 32];
   const int jt = blockIdx.x, it = blockIdx.y, r = blockIdx.z;
   const int j  = jt * ST_TJ + threadIdx.x;
@@ -214,16 +244,19 @@ stat_kernel(const long long *__restrict__ cnt, const double *__restrict__ pm, in
   const long long *c = cnt + (size_t) r * 16 * plane;
   const bool tile_live = (it * ST_TI) < (jt * ST_TJ + ST_TJ - 1);
   double col = 0.0, vmin = INFINITY, vmax = -INFINITY;
-  double mj[4] = { 0.25, 0.25, 0.25, 0.25 };
+  double mj[4] = { 0.25, 0.25, 0.25, 0.25 }, lmj[4];
 
   if (threadIdx.x < ST_TI * 4) {
     const int il = threadIdx.x >> 2, a = threadIdx.x & 3, i = it * ST_TI + il;
-    pmi[il][a] = (i < L) ? pm[((size_t) r * L + i) * 4 + a] : 0.25;
+    pmi[il][a]  = (i < L) ? pm[((size_t) r * L + i) * 4 + a] : 0.25;
+    lpmi[il][a] = log(pmi[il][a]);
   }
   if (j < L) {
     #pragma unroll
     for (int b = 0; b < 4; b++) mj[b] = pm[((size_t) r * L + j) * 4 + b];
   }
+  #pragma unroll
+  for (int b = 0; b < 4; b++) lmj[b] = log(mj[b]);
   __syncthreads();
 
   for (int il = 0; il < ST_TI; il++) {
@@ -231,8 +264,8 @@ stat_kernel(const long long *__restrict__ cnt, const double *__restrict__ pm, in
     double v = 0.0;
     if (tile_live && i < L && j < L && i < j) {
       PairProbs P;
-      load_pair(c, plane, (size_t) i * Lp + j, scale, wtot, P);
-      v = pair_statistic<STAT, CLS>(P, pmi[il], mj, mask);
+      load_pair<false>(c, plane, (size_t) i * Lp + j, scale, wtot, P);
+      v = pair_statistic<STAT, CLS>(P, pmi[il], mj, lpmi[il], lmj, mask);
       cov[((size_t) r * L + i) * Lp + j] = v;
       col += v;
       vmin = fmin(vmin, v);
@@ -430,7 +463,7 @@ __global__ void export_probs_kernel(const long long *__restrict__ cnt, int L, in
   }
   if (i > j) { ngap[(size_t) i * L + j] = 0.0; return; }
   PairProbs P;
-  load_pair(cnt, (size_t) L * Lp, (size_t) i * Lp + j, scale, wtot, P);
+  load_pair<true>(cnt, (size_t) L * Lp, (size_t) i * Lp + j, scale, wtot, P);
   #pragma unroll
   for (int a = 0; a < 4; a++)
     #pragma unroll

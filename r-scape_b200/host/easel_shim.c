@@ -8,7 +8,7 @@
  * UNPINNED except where the tutorial transcript pins the composition (tests/test_golden_tutorial.py).
  *
  * Linked into: r-scape_b200/librscape_b200_host.so (the host-side mirror of the reference API; inside a
- * real R-scape tree the real libeasel is linked instead), oracle/liboracle.so (CPU restatement) and
+ * real R-scape tree the real libeasel is linked instead), the CPU checker built under oracle/ and
  * oracle/_ref/librscape_ref.so (reference sources compiled unchanged).
  */
 #include <stdarg.h>

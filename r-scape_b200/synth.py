@@ -125,5 +125,5 @@ def synthetic_msa(N, L, seed=42, gap_mean=0.11, frac_paired=0.6, n_frac=0.001, m
     elif weights == "ones":
         w = np.ones(N)
     else:
-        raise ValueError("weights must be 'gamma' or 'ones' (PB / GSC weights live in oracle/pyoracle.py)")
+        raise ValueError("weights must be 'gamma' or 'ones' (PB / GSC weights are test-side preprocessing)")
     return ax, w, partner
