@@ -8,11 +8,12 @@ the cumulative histogram and the scan of the input alignment = 102 scans = 102 *
 reported with the metric's own definition of a pair-cell count per scan, L^2*N/2.
 
   value   whole-job pair-cells/s with every input already resident in HBM (CUDA events, max over ranks)
-  e2e     the same job through the C-ABI with HOST buffers: pinned host alignments in, cumulative histogram and
-          the input alignment's score matrix out, copies inside the timed region
-  N > 1   the 100 nulls are dealt round-robin to the ranks (one process per GPU, torchrun), every rank repeats
-          the width pass (no communication needed to agree on w), rank 0 also scans the input alignment; the
-          per-rank histograms are summed with one NCCL all-reduce.  Total work is fixed: "scaling": "strong".
+  e2e     the same job through the C-ABI with HOST buffers: the input alignment (pinned), tree and weights in, null
+          alignments generated on the device (Fitch + shuffle), cumulative histogram and the input alignment's score
+          matrix out, all copies inside the timed region
+  N > 1   the 100 nulls are split into one contiguous block per rank (one process per GPU, torchrun), every rank
+          repeats the width pass on replicate 0 (no communication needed to agree on w), rank 0 also scans the input
+          alignment; the per-rank histograms are summed with one NCCL all-reduce.  Total work is fixed: "scaling": "strong".
 
 --impl reference times the reference's own CPU implementation of the path (oracle/_ref: src/correlators.c compiled
 unchanged; the oracle port if that build is absent) on the host cores, on a bounded sample of the same workload.
@@ -207,51 +208,49 @@ def main():
 
     # ---- synthetic inputs (same on every rank: seeded) ------------------------------------------------
     msa, wgt, _ = synth.synthetic_msa(N, L, seed=42)
+    tree = synth.random_tree(N, np.random.default_rng(42))
     stream = torch.cuda.current_stream()
     slots = pkg.replicate_slots(N, L, R, args.slices)
     ctx = pkg.Context(local, stream.cuda_stream)
     ctx.configure(N, L, slots, args.slices)
     ctx.set_weights(wgt)
-    # nulls: R-scape's default null model (Fitch + tree-substitution shuffle) generated on the device from a random tree
-    tree = synth.random_tree(N, np.random.default_rng(42))
-    ctx.set_tree(tree.left, tree.right, tree.parent, tree.ld, tree.rd)
-    my_nulls = list(range(rank, R, world))                           # nulls dealt round-robin to ranks
-    t_gen0 = time.perf_counter()
-    host_nulls = torch.empty((len(my_nulls), N, L), dtype=torch.uint8).pin_memory()
-    hn = host_nulls.numpy()
-    for k0 in range(0, len(my_nulls), slots):
-        n = min(slots, len(my_nulls) - k0)
-        ctx.null_fitch_shuffle(msa, seed=1000 + my_nulls[k0], nrep=n)
-        hn[k0:k0 + n] = ctx.get_slots(n)
-    null0 = hn[0].copy() if rank == 0 else None
-    if world > 1:                                                     # every rank needs replicate 0 for the width pass
-        buf = torch.from_numpy(hn[0].copy() if rank == 0 else np.empty((N, L), np.uint8)).cuda()
-        dist.broadcast(buf, 0)
-        null0 = buf.cpu().numpy()
-    t_gen = time.perf_counter() - t_gen0
-    dev_nulls = host_nulls.cuda()
-    dev_null0 = torch.from_numpy(null0).cuda()
-    dev_msa = torch.from_numpy(msa).cuda()
+    my_ids = pkg.parallel.null_shard(R, world, rank)                 # contiguous block of replicate ids per rank
+    n_mine = len(my_ids)
+    own0 = (n_mine > 0 and my_ids[0] == 0)
+    ctx.pool_reserve(n_mine + (0 if own0 else 1))
+    w0_entry = 0 if own0 else n_mine                                  # pool entry holding replicate 0 (width pass)
+    SEED = 20261017
     host_msa = torch.from_numpy(msa).pin_memory()
-    host_null0 = torch.from_numpy(null0).pin_memory()
+    dev_msa = torch.from_numpy(msa).cuda()
     cov_out = np.empty((L, L))
     NB = 1 << 18
-    hist_dev = torch.zeros(NB, dtype=torch.int64, device="cuda")
 
-    def job(nulls, n0, real):
-        """null_rscape + run_rscape for this rank's share of the work."""
+    def generate():
+        """R-scape's default null model on the device: Fitch + tree-substitution shuffle (null_rscape, R-scape.c:1653-1661).
+        Replicates are keyed by their global id, so every rank that needs replicate 0 generates the same alignment."""
+        ctx.set_tree(tree.left, tree.right, tree.parent, tree.ld, tree.rd)
+        if n_mine:
+            ctx.null_fitch_shuffle(host_msa.numpy(), SEED, n_mine, first_rep=0, first_id=my_ids[0])
+        if not own0:
+            ctx.null_fitch_shuffle(host_msa.numpy(), SEED, 1, first_rep=w0_entry, first_id=0)
+
+    def job(real):
+        """null_rscape + run_rscape for this rank's share of the work, nulls already in the device pool."""
         ctx.hist_reset()
-        w, _, _ = ctx.null_width(n0, pkg.GT, pkg.C16, pkg.APC)                        # calculate_width_histo
-        if len(my_nulls):
-            ctx.null_hist(nulls, w, pkg.GT, pkg.C16, pkg.APC, want_minmax=False)      # run_rscape(RANSS) + null_add2cumranklist
+        w, _, _ = ctx.null_width_pool(w0_entry, pkg.GT, pkg.C16, pkg.APC)             # calculate_width_histo
+        if n_mine:
+            ctx.null_hist_pool(0, n_mine, w, pkg.GT, pkg.C16, pkg.APC, want_minmax=False)   # run_rscape(RANSS) + null_add2cumranklist
         out = None
         if rank == 0:
-            out = ctx.scan(real, pkg.GT, pkg.C16, pkg.APC, want_cov=False)            # run_rscape(GIVSS)
+            out = ctx.scan(real, pkg.GT, pkg.C16, pkg.APC, want_cov=isinstance(real, np.ndarray))   # run_rscape(GIVSS)
         bins, n, imax = ctx.hist_read(NB)
-        if world > 1:
-            hist_dev.copy_(torch.from_numpy(bins.astype(np.int64)))
-            dist.all_reduce(hist_dev)
+        bins = pkg.parallel.reduce_histogram(bins, device="cuda")
         return w, bins, out
+
+    t_gen0 = time.perf_counter()
+    generate()
+    torch.cuda.synchronize()
+    t_gen = time.perf_counter() - t_gen0
 
     scans_total = R + 2
     cells_per_scan = L * L * N / 2.0
@@ -282,36 +281,32 @@ def main():
     ctx.profile_gram(True)
     if rank == 0:
         sampler.start()
-    ms_dev = timed(lambda: job(dev_nulls, dev_null0, dev_msa), args.steps, args.warmup)
+    ms_dev = timed(lambda: job(dev_msa), args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
     cnt = ctx.counters(reset=True)
     ctx.profile_gram(False)
     value = cells_total * args.steps / (ms_dev * 1e-3)
 
     # ---- e2e: host buffers through the C-ABI, copies inside the timed region ------------------------------
+    # in : the input alignment (pinned host memory, uploaded twice: generators + scan), the tree, the weights
+    # out: cumulative null histogram and the input alignment's corrected score matrix
     def job_e2e():
-        ctx.hist_reset()
-        w, _, _ = ctx.null_width(host_null0.numpy(), pkg.GT, pkg.C16, pkg.APC)
-        if len(my_nulls):
-            ctx.null_hist(hn, w, pkg.GT, pkg.C16, pkg.APC, want_minmax=False)
+        ctx.set_weights(wgt)
+        generate()
+        w, bins, out = job(host_msa.numpy())
         if rank == 0:
-            res = ctx.scan(host_msa.numpy(), pkg.GT, pkg.C16, pkg.APC, want_cov=True)
-            cov_out[:] = res["cov"]
-        bins, n, imax = ctx.hist_read(NB)
-        if world > 1:
-            hist_dev.copy_(torch.from_numpy(bins.astype(np.int64)))
-            dist.all_reduce(hist_dev)
+            cov_out[:] = out["cov"]
 
     ms_e2e = timed(job_e2e, args.steps, 1)
     e2e_value = cells_total * args.steps / (ms_e2e * 1e-3)
-    h2d = (len(my_nulls) + 1 + (1 if rank == 0 else 0)) * N * L
+    h2d = (2 if rank == 0 else 1) * N * L + (N - 1) * (3 * 4 + 2 * 8) + N * 8 + (N - 1) * 2 * 16 * 8
     d2h = NB * 8 + (L * L * 8 if rank == 0 else 0)
 
     # ---- roofline of the dominant kernel (tcgen05 gram): algorithmic ops / measured launch time -------------
     # launches during the value run: per step, gram launches = width(1) + ceil(nulls/slots) + real(1 on rank 0)
     pairs = L * (L - 1) / 2.0
     gram_ms_avg = cnt["gram_ms"] / max(1, cnt["gram_launches"])
-    scans_this_rank = (len(my_nulls) + 1 + (1 if rank == 0 else 0)) * (args.steps + args.warmup)
+    scans_this_rank = (n_mine + 1 + (1 if rank == 0 else 0)) * (args.steps + args.warmup)
     ops_alg_per_launch = 32.0 * pairs * N * scans_this_rank / max(1, cnt["gram_launches"])
     achieved = ops_alg_per_launch / (gram_ms_avg * 1e-3) / 1e12 if gram_ms_avg > 0 else 0.0
     peak_i8 = 2.0 * peaks["bf16"]
@@ -332,11 +327,11 @@ def main():
                     dtype="u8 x u8 -> s32 tensor-core counts (fixed-point weights), f64 statistics", data="synthetic",
                     config=dict(workload=f"{args.workload}: L={L} N={N} nulls={R} GTp+APC, scans per step = {scans_total} "
                                          f"(width pass + {R} nulls + input alignment)",
-                                weight_slices=args.slices, replicate_slots=slots, parallelism=f"nulls round-robin over {world} GPU(s)",
+                                weight_slices=args.slices, replicate_slots=slots, parallelism=f"nulls in contiguous blocks over {world} GPU(s)",
                                 l2="inputs larger than L2 (null alignments %.1f GB, operand planes %.1f GB per replicate)" %
                                    (R * N * L / 1e9, (4 + 4 * args.slices) * L * N / 1e9),
-                                null_model="Fitch + tree-substitution shuffle generated on the device before the timed region "
-                                           f"({t_gen:.2f} s incl. D2H)"),
+                                null_model="Fitch + tree-substitution shuffle generated on the device: resident before the timed region "
+                                           f"for `value`, generated inside it for `e2e` (first generation incl. allocations {t_gen * 1e3:.0f} ms)"),
                     e2e=dict(value=e2e_value, unit="pair-cells/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
                              ms_per_step=ms_e2e / args.steps),
                     gpu_launches=int(cnt["launches"] * args.steps / (args.steps + args.warmup)),

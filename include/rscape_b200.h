@@ -101,21 +101,28 @@ int rsb_last_nseff(rsb_ctx *ctx, double *nseff, double *ngap);
 /* tree in Easel convention: nseq leaves, internal nodes 0..nseq-2 with parents before children,
  * child <= 0 is leaf -child.  Stays resident for the simulators. */
 int rsb_set_tree(rsb_ctx *ctx, const int *left, const int *right, const int *parent, const double *ld, const double *rd);
+/* The generators write into a device-resident pool of null alignments uint8 [nrep][nseq][alen] that the scan reads in
+ * place, so a null alignment never has to exist on the host. */
+int rsb_pool_reserve(rsb_ctx *ctx, int nrep);
 /* cov_GenerateAlignment, ungapped noss path (src/cov_simulate.c:289-324,585-631,724-773): evolve every
  * (replicate, column) independently down the tree with P(t) = exp(tQ) (src/ratematrix.c:185-233),
- * Philox4x32-10 keyed by (seed, replicate, column).  root: uint8[alen] residues 0..3.  gapmask: optional
+ * Philox4x32-10 keyed by (seed, replicate id, column).  root: uint8[alen] residues 0..3.  gapmask: optional
  * uint8 [nseq][alen] alignment whose non-canonical cells are copied over the result.
- * Output: nrep nulls in the context's replicate slots [first_rep, first_rep+nrep). */
+ * Replicates with global ids [first_id, first_id+nrep) land in pool entries [first_rep, first_rep+nrep); the
+ * residues depend on (seed, id) only, so ranks that generate the same id get the same alignment. */
 int rsb_null_simulate(rsb_ctx *ctx, const double *Q, const uint8_t *root, const uint8_t *gapmask, int64_t gap_stride,
-                      uint64_t seed, int first_rep, int nrep);
+                      uint64_t seed, uint64_t first_id, int first_rep, int nrep);
 /* default null of R-scape: Fitch ancestral reconstruction + one column permutation + per-branch
  * substitution re-placement (src/msatree.c:173-227,1700-1931; src/msamanip.c:1164-1233,1449-1780) */
-int rsb_null_fitch_shuffle(rsb_ctx *ctx, const uint8_t *msa, int64_t row_stride, uint64_t seed, int first_rep, int nrep);
-/* score the nulls sitting in the replicate slots (output of the two generators) */
-int rsb_null_hist_slots(rsb_ctx *ctx, int first_rep, int nrep, int stat, int covclass, int actype, const double *allowpair,
-                        double tol, double w, double bmin, double *minmax);
-/* copy replicate slots back to the host: uint8 [nrep][nseq][alen] */
-int rsb_get_slots(rsb_ctx *ctx, int first_rep, int nrep, uint8_t *out);
+int rsb_null_fitch_shuffle(rsb_ctx *ctx, const uint8_t *msa, int64_t row_stride, uint64_t seed, uint64_t first_id, int first_rep, int nrep);
+/* calculate_width_histo / the null loop on pool entries */
+int rsb_null_width_pool(rsb_ctx *ctx, int rep, int stat, int covclass, int actype, const double *allowpair, double tol,
+                        double w_old, double bmin, int hpts, double *w_out, double *mincov, double *maxcov);
+int rsb_null_hist_pool(rsb_ctx *ctx, int first_rep, int nrep, int stat, int covclass, int actype, const double *allowpair,
+                       double tol, double w, double bmin, double *minmax);
+/* copy pool entries to / from the host: uint8 [nrep][nseq][alen] (e.g. for --outnull, or host-made nulls scanned repeatedly) */
+int rsb_pool_get(rsb_ctx *ctx, int first_rep, int nrep, uint8_t *out);
+int rsb_pool_put(rsb_ctx *ctx, int first_rep, int nrep, const uint8_t *in);
 
 /* ---- instrumentation ------------------------------------------------------------------------------ */
 /* kernels launched by this context so far; device milliseconds spent in the gram kernel and number of

@@ -66,15 +66,19 @@ def lib():
                                      C.c_double, C.c_double, C.c_int, _dp, _dp, _dp]
         L.rsb_null_hist.argtypes = [_vp, _vp, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, _dp,
                                     C.c_double, C.c_double, C.c_double, _dp]
-        L.rsb_null_hist_slots.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.c_double, C.c_double,
-                                          C.c_double, _dp]
+        L.rsb_null_hist_pool.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.c_double, C.c_double,
+                                         C.c_double, _dp]
+        L.rsb_null_width_pool.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.c_double, C.c_double, C.c_double, C.c_int,
+                                          _dp, _dp, _dp]
+        L.rsb_pool_reserve.argtypes = [_vp, C.c_int]
+        L.rsb_pool_get.argtypes = [_vp, C.c_int, C.c_int, _u8p]
+        L.rsb_pool_put.argtypes = [_vp, C.c_int, C.c_int, _u8p]
         L.rsb_hist_reset.argtypes = [_vp]
         L.rsb_hist_read.argtypes = [_vp, _u64p, C.c_int, _u64p, _ip]
         L.rsb_last_nseff.argtypes = [_vp, _dp, _dp]
         L.rsb_set_tree.argtypes = [_vp, _ip, _ip, _ip, _dp, _dp]
-        L.rsb_null_simulate.argtypes = [_vp, _dp, _u8p, _u8p, C.c_int64, C.c_uint64, C.c_int, C.c_int]
-        L.rsb_null_fitch_shuffle.argtypes = [_vp, _u8p, C.c_int64, C.c_uint64, C.c_int, C.c_int]
-        L.rsb_get_slots.argtypes = [_vp, C.c_int, C.c_int, _u8p]
+        L.rsb_null_simulate.argtypes = [_vp, _dp, _u8p, _u8p, C.c_int64, C.c_uint64, C.c_uint64, C.c_int, C.c_int]
+        L.rsb_null_fitch_shuffle.argtypes = [_vp, _u8p, C.c_int64, C.c_uint64, C.c_uint64, C.c_int, C.c_int]
         L.rsb_counters.argtypes = [_vp, _i64p, _dp, _i64p, C.c_int]
         L.rsb_profile_gram.argtypes = [_vp, C.c_int]
         _lib = L
@@ -189,10 +193,17 @@ class Context:
         self._ck(lib().rsb_null_hist(self._h, p, R, self.L, self.N * self.L, dev, stat, covclass, actype, _d(ap), tol, w, bmin, _d(mm)))
         return mm
 
-    def null_hist_slots(self, nrep, w, stat=GT, covclass=C16, actype=APC, allowpair=None, tol=1e-6, bmin=-10.0):
+    def null_width_pool(self, rep=0, stat=GT, covclass=C16, actype=APC, allowpair=None, tol=1e-6, w_old=0.05, bmin=-10.0, hpts=400):
         ap = None if allowpair is None else np.ascontiguousarray(allowpair, dtype=np.float64)
-        mm = np.empty((nrep, 2))
-        self._ck(lib().rsb_null_hist_slots(self._h, 0, nrep, stat, covclass, actype, _d(ap), tol, w, bmin, _d(mm)))
+        w, mn, mx = C.c_double(), C.c_double(), C.c_double()
+        self._ck(lib().rsb_null_width_pool(self._h, rep, stat, covclass, actype, _d(ap), tol, w_old, bmin, hpts,
+                                           C.byref(w), C.byref(mn), C.byref(mx)))
+        return w.value, mn.value, mx.value
+
+    def null_hist_pool(self, first_rep, nrep, w, stat=GT, covclass=C16, actype=APC, allowpair=None, tol=1e-6, bmin=-10.0, want_minmax=True):
+        ap = None if allowpair is None else np.ascontiguousarray(allowpair, dtype=np.float64)
+        mm = np.empty((nrep, 2)) if want_minmax else None
+        self._ck(lib().rsb_null_hist_pool(self._h, first_rep, nrep, stat, covclass, actype, _d(ap), tol, w, bmin, _d(mm)))
         return mm
 
     def hist_reset(self):
@@ -215,21 +226,29 @@ class Context:
         b = [np.ascontiguousarray(x, dtype=np.float64) for x in (ld, rd)]
         self._ck(lib().rsb_set_tree(self._h, a[0].ctypes.data_as(_ip), a[1].ctypes.data_as(_ip), a[2].ctypes.data_as(_ip), _d(b[0]), _d(b[1])))
 
-    def null_simulate(self, Q, root, seed, nrep, gapmask=None, first_rep=0):
+    def pool_reserve(self, nrep):
+        self._ck(lib().rsb_pool_reserve(self._h, nrep))
+
+    def null_simulate(self, Q, root, seed, nrep, gapmask=None, first_rep=0, first_id=None):
         Q = np.ascontiguousarray(Q, dtype=np.float64)
         root = np.ascontiguousarray(root, dtype=np.uint8)
         gm = None if gapmask is None else np.ascontiguousarray(gapmask, dtype=np.uint8)
         self._ck(lib().rsb_null_simulate(self._h, _d(Q), root.ctypes.data_as(_u8p), None if gm is None else gm.ctypes.data_as(_u8p),
-                                         self.L, seed, first_rep, nrep))
+                                         self.L, seed, first_rep if first_id is None else first_id, first_rep, nrep))
 
-    def null_fitch_shuffle(self, msa, seed, nrep, first_rep=0):
+    def null_fitch_shuffle(self, msa, seed, nrep, first_rep=0, first_id=None):
         msa = self._msa(msa)
-        self._ck(lib().rsb_null_fitch_shuffle(self._h, msa.ctypes.data_as(_u8p), self.L, seed, first_rep, nrep))
+        self._ck(lib().rsb_null_fitch_shuffle(self._h, msa.ctypes.data_as(_u8p), self.L, seed,
+                                              first_rep if first_id is None else first_id, first_rep, nrep))
 
-    def get_slots(self, nrep, first_rep=0):
+    def pool_get(self, nrep, first_rep=0):
         out = np.empty((nrep, self.N, self.L), dtype=np.uint8)
-        self._ck(lib().rsb_get_slots(self._h, first_rep, nrep, out.ctypes.data_as(_u8p)))
+        self._ck(lib().rsb_pool_get(self._h, first_rep, nrep, out.ctypes.data_as(_u8p)))
         return out
+
+    def pool_put(self, nulls, first_rep=0):
+        nulls = np.ascontiguousarray(nulls, dtype=np.uint8)
+        self._ck(lib().rsb_pool_put(self._h, first_rep, nulls.shape[0], nulls.ctypes.data_as(_u8p)))
 
     # ---- instrumentation ------------------------------------------------------------------------
     def profile_gram(self, enable=True):

@@ -41,10 +41,10 @@ cudaError_t rsb_launch_correct_hist(double *cov, const double *covx, const doubl
 cudaError_t rsb_launch_width(const double *minmax, double w_old, double bmin, int hpts, double tol, double *wout, cudaStream_t st);
 cudaError_t rsb_launch_symmetrize(double *cov, int L, int Lp, cudaStream_t st);
 cudaError_t rsb_launch_null_simulate(const int *left, const int *right, const double *pcdf, int N, int L, const uint8_t *root,
-                                     const uint8_t *gapmask, long long gap_stride, unsigned long long seed, int first_rep, int nrep,
+                                     const uint8_t *gapmask, long long gap_stride, unsigned long long seed, unsigned long long id0, int first_rep, int nrep,
                                      uint8_t *res, uint8_t *scratch, cudaStream_t st);
 cudaError_t rsb_launch_fitch_shuffle(const int *left, const int *right, const int *parent, const int *order, const int *level_start,
-                                     int nlevels, int N, int L, const uint8_t *msa, unsigned long long seed, int first_rep, int nrep,
+                                     int nlevels, int N, int L, const uint8_t *msa, unsigned long long seed, unsigned long long id0, int first_rep, int nrep,
                                      uint8_t *res, uint8_t *anc, uint8_t *shanc, int *perm, cudaStream_t st);
 
 namespace {
@@ -97,6 +97,8 @@ struct rsb_ctx {
   std::vector<int> h_level_start;
   uint8_t *d_root = nullptr, *d_gapmask = nullptr, *d_simscratch = nullptr, *d_msa0 = nullptr, *d_anc = nullptr, *d_shanc = nullptr;
   bool have_tree = false;
+  uint8_t *d_pool = nullptr;          // device-resident null alignments [Rpool][N][L] (output of the generators)
+  int Rpool = 0;
 
   unsigned long long hist_n = 0;
   long long launches = 0, gram_launches = 0;
@@ -160,7 +162,8 @@ void free_plan(rsb_ctx *c)
   dfree(c->d_meanp); dfree(c->d_w); dfree(c->d_blocksum); dfree(c->d_hist); dfree(c->d_colsum); dfree(c->d_flags); dfree(c->d_ps); dfree(c->d_pp_out);
   dfree(c->d_nseff_out); dfree(c->d_ngap_out); dfree(c->d_left); dfree(c->d_right); dfree(c->d_parent); dfree(c->d_order);
   dfree(c->d_level_start); dfree(c->d_perm); dfree(c->d_pcdf); dfree(c->d_root); dfree(c->d_gapmask); dfree(c->d_simscratch);
-  dfree(c->d_msa0); dfree(c->d_anc); dfree(c->d_shanc);
+  dfree(c->d_msa0); dfree(c->d_anc); dfree(c->d_shanc); dfree(c->d_pool);
+  c->Rpool = 0;
   c->have_tree = false;
 }
 
@@ -425,6 +428,12 @@ int copy_matrix_out(rsb_ctx *ctx, const double *dsrc, double *hdst)   // [L][Lp]
 } // namespace
 
 // =============================================================================================== C-ABI
+static int pool_range_ok(rsb_ctx *ctx, int first_rep, int nrep)
+{
+  if (first_rep < 0 || nrep < 1 || first_rep + nrep > ctx->Rpool) { rsb_set_error(ctx, "pool replicates [%d,%d) out of range (reserved %d)", first_rep, first_rep + nrep, ctx->Rpool); return 1; }
+  return 0;
+}
+
 extern "C" {
 
 const char *rsb_create_error(void) { return g_create_err; }
@@ -737,13 +746,13 @@ int rsb_null_width(rsb_ctx *ctx, const uint8_t *null0, int64_t row_stride, int o
 // reuse of each slot group; the caller's stream (main) waits for everything before the call returns.
 // src_dev: device-resident nulls [nrep][N][L] read in place (no copy), else host/strided input that is uploaded.
 static int null_hist_pipelined(rsb_ctx *ctx, const uint8_t *nulls, int nrep, int64_t row_stride, int64_t rep_stride, int on_device,
-                               bool in_slots, int stat, int covclass, int actype, unsigned mask, double tol, double w, double bmin,
+                               int stat, int covclass, int actype, unsigned mask, double tol, double w, double bmin,
                                double *minmax)
 {
   const bool raf = (stat == RSB_RAF || stat == RSB_RAFS);
-  const bool in_place = in_slots || (on_device && row_stride == ctx->L && rep_stride == (int64_t) ctx->N * ctx->L);
-  const int  G = (ctx->Rcap >= 2 && !in_slots) ? 2 : 1;
-  const int  chunk = in_slots ? nrep : std::max(1, ctx->Rcap / G);
+  const bool in_place = (on_device && row_stride == ctx->L && rep_stride == (int64_t) ctx->N * ctx->L);
+  const int  G = (ctx->Rcap >= 2) ? 2 : 1;
+  const int  chunk = std::max(1, ctx->Rcap / G);
   const size_t repbytes = (size_t) ctx->N * ctx->L;
 
   RSB_CUDA_OK(cudaMemcpyAsync(ctx->d_w, &w, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
@@ -757,7 +766,7 @@ static int null_hist_pipelined(rsb_ctx *ctx, const uint8_t *nulls, int nrep, int
     const int g = c % G, s0 = g * chunk, n = std::min(chunk, nrep - r0);
     const uint8_t *src;
     if (used[g]) RSB_CUDA_OK(cudaStreamWaitEvent(ctx->stream_copy, ctx->ev_counts[g], 0));       // the group's slots and planes have been consumed
-    if (in_place) src = in_slots ? ctx->d_res : nulls + (size_t) r0 * repbytes;
+    if (in_place) src = nulls + (size_t) r0 * repbytes;
     else {
       if (upload_msa(ctx, nulls + (size_t) r0 * rep_stride, row_stride, rep_stride, n, s0, on_device, ctx->stream_copy)) return 1;
       src = ctx->d_res + (size_t) s0 * repbytes;
@@ -791,21 +800,29 @@ int rsb_null_hist(rsb_ctx *ctx, const uint8_t *nulls, int nrep, int64_t row_stri
 {
   RSB_CUDA_OK(cudaSetDevice(ctx->device));
   if (resolve_stat(ctx, stat, covclass)) return 1;
-  if (null_hist_pipelined(ctx, nulls, nrep, row_stride, rep_stride, on_device, false, stat, covclass, actype, allow_mask(allowpair),
+  if (null_hist_pipelined(ctx, nulls, nrep, row_stride, rep_stride, on_device, stat, covclass, actype, allow_mask(allowpair),
                           tol, w, bmin, minmax)) return 1;
   return check_flags(ctx, "null_rscape");
 }
 
-int rsb_null_hist_slots(rsb_ctx *ctx, int first_rep, int nrep, int stat, int covclass, int actype, const double *allowpair,
-                        double tol, double w, double bmin, double *minmax)
+int rsb_null_hist_pool(rsb_ctx *ctx, int first_rep, int nrep, int stat, int covclass, int actype, const double *allowpair,
+                       double tol, double w, double bmin, double *minmax)
 {
   RSB_CUDA_OK(cudaSetDevice(ctx->device));
-  if (first_rep != 0) { rsb_set_error(ctx, "slots must start at 0"); return 1; }
-  if (nrep > ctx->Rcap) { rsb_set_error(ctx, "%d replicates exceed the configured %d slots", nrep, ctx->Rcap); return 1; }
+  if (pool_range_ok(ctx, first_rep, nrep)) return 1;
   if (resolve_stat(ctx, stat, covclass)) return 1;
-  if (null_hist_pipelined(ctx, nullptr, nrep, ctx->L, (int64_t) ctx->N * ctx->L, 1, true, stat, covclass, actype, allow_mask(allowpair),
-                          tol, w, bmin, minmax)) return 1;
+  const size_t rb = (size_t) ctx->N * ctx->L;
+  if (null_hist_pipelined(ctx, ctx->d_pool + (size_t) first_rep * rb, nrep, ctx->L, (int64_t) rb, 1, stat, covclass, actype,
+                          allow_mask(allowpair), tol, w, bmin, minmax)) return 1;
   return check_flags(ctx, "null_rscape");
+}
+
+int rsb_null_width_pool(rsb_ctx *ctx, int rep, int stat, int covclass, int actype, const double *allowpair, double tol,
+                        double w_old, double bmin, int hpts, double *w_out, double *mincov, double *maxcov)
+{
+  if (pool_range_ok(ctx, rep, 1)) return 1;
+  return rsb_null_width(ctx, ctx->d_pool + (size_t) rep * ctx->N * ctx->L, ctx->L, 1, stat, covclass, actype, allowpair, tol,
+                        w_old, bmin, hpts, w_out, mincov, maxcov);
 }
 
 int rsb_hist_reset(rsb_ctx *ctx)
@@ -921,12 +938,25 @@ static int branch_matrix(const double *Q, double t, double *P)
   return 0;
 }
 
+int rsb_pool_reserve(rsb_ctx *ctx, int nrep)
+{
+  RSB_CUDA_OK(cudaSetDevice(ctx->device));
+  if (ctx->N == 0) { rsb_set_error(ctx, "rsb_configure first"); return 1; }
+  if (nrep < 1) { rsb_set_error(ctx, "bad pool size"); return 1; }
+  if (nrep <= ctx->Rpool) return 0;
+  RSB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  dfree(ctx->d_pool); dfree(ctx->d_simscratch); dfree(ctx->d_anc); dfree(ctx->d_shanc); dfree(ctx->d_perm);
+  RSB_CUDA_OK(cudaMalloc(&ctx->d_pool, (size_t) nrep * ctx->N * ctx->L));
+  ctx->Rpool = nrep;
+  return 0;
+}
+
 int rsb_null_simulate(rsb_ctx *ctx, const double *Q, const uint8_t *root, const uint8_t *gapmask, int64_t gap_stride,
-                      uint64_t seed, int first_rep, int nrep)
+                      uint64_t seed, uint64_t first_id, int first_rep, int nrep)
 {
   RSB_CUDA_OK(cudaSetDevice(ctx->device));
   if (!ctx->have_tree) { rsb_set_error(ctx, "rsb_set_tree first"); return 1; }
-  if (first_rep < 0 || first_rep + nrep > ctx->Rcap) { rsb_set_error(ctx, "replicate slots out of range"); return 1; }
+  if (pool_range_ok(ctx, first_rep, nrep)) return 1;
   const int N = ctx->N, L = ctx->L, nn = N - 1;
   // cumulative branch matrices [node][side][4][4]: row a holds the CDF over child residues
   std::vector<double> pb((size_t) nn * 2 * 16);
@@ -937,8 +967,8 @@ int rsb_null_simulate(rsb_ctx *ctx, const double *Q, const uint8_t *root, const 
       for (int a = 0; a < 4; a++) { double cdf = 0.0; for (int b = 0; b < 4; b++) { cdf += P[a * 4 + b]; pb[((size_t) v * 2 + side) * 16 + a * 4 + b] = cdf; } }
     }
   if (!ctx->d_pcdf) RSB_CUDA_OK(cudaMalloc(&ctx->d_pcdf, pb.size() * sizeof(double)));
-  if (!ctx->d_root)    RSB_CUDA_OK(cudaMalloc(&ctx->d_root, L));
-  if (!ctx->d_simscratch) RSB_CUDA_OK(cudaMalloc(&ctx->d_simscratch, (size_t) ctx->Rcap * nn * L));
+  if (!ctx->d_root) RSB_CUDA_OK(cudaMalloc(&ctx->d_root, L));
+  if (!ctx->d_simscratch) RSB_CUDA_OK(cudaMalloc(&ctx->d_simscratch, (size_t) ctx->Rpool * nn * L));
   RSB_CUDA_OK(cudaMemcpyAsync(ctx->d_pcdf, pb.data(), pb.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   RSB_CUDA_OK(cudaMemcpyAsync(ctx->d_root, root, L, cudaMemcpyHostToDevice, ctx->stream));
   if (gapmask) {
@@ -947,34 +977,44 @@ int rsb_null_simulate(rsb_ctx *ctx, const double *Q, const uint8_t *root, const 
   }
   RSB_CUDA_OK(cudaStreamSynchronize(ctx->stream));       // pb is a host temporary
   RSB_CUDA_OK(rsb_launch_null_simulate(ctx->d_left, ctx->d_right, ctx->d_pcdf, N, L, ctx->d_root, gapmask ? ctx->d_gapmask : nullptr, L,
-                                       seed, first_rep, nrep, ctx->d_res, ctx->d_simscratch, ctx->stream));
+                                       seed, first_id, first_rep, nrep, ctx->d_pool, ctx->d_simscratch, ctx->stream));
   ctx->launches++;
   return 0;
 }
 
-int rsb_null_fitch_shuffle(rsb_ctx *ctx, const uint8_t *msa, int64_t row_stride, uint64_t seed, int first_rep, int nrep)
+int rsb_null_fitch_shuffle(rsb_ctx *ctx, const uint8_t *msa, int64_t row_stride, uint64_t seed, uint64_t first_id, int first_rep, int nrep)
 {
   RSB_CUDA_OK(cudaSetDevice(ctx->device));
   if (!ctx->have_tree) { rsb_set_error(ctx, "rsb_set_tree first"); return 1; }
-  if (first_rep < 0 || first_rep + nrep > ctx->Rcap) { rsb_set_error(ctx, "replicate slots out of range"); return 1; }
+  if (pool_range_ok(ctx, first_rep, nrep)) return 1;
   const int N = ctx->N, L = ctx->L, nn = N - 1;
   if (!ctx->d_msa0)  RSB_CUDA_OK(cudaMalloc(&ctx->d_msa0, (size_t) N * L));
-  if (!ctx->d_anc)   RSB_CUDA_OK(cudaMalloc(&ctx->d_anc, (size_t) ctx->Rcap * nn * L));
-  if (!ctx->d_shanc) RSB_CUDA_OK(cudaMalloc(&ctx->d_shanc, (size_t) ctx->Rcap * nn * L));
-  if (!ctx->d_perm)  RSB_CUDA_OK(cudaMalloc(&ctx->d_perm, sizeof(int) * (size_t) ctx->Rcap * L));
+  if (!ctx->d_anc)   RSB_CUDA_OK(cudaMalloc(&ctx->d_anc, (size_t) ctx->Rpool * nn * L));
+  if (!ctx->d_shanc) RSB_CUDA_OK(cudaMalloc(&ctx->d_shanc, (size_t) ctx->Rpool * nn * L));
+  if (!ctx->d_perm)  RSB_CUDA_OK(cudaMalloc(&ctx->d_perm, sizeof(int) * (size_t) ctx->Rpool * L));
   RSB_CUDA_OK(cudaMemcpy2DAsync(ctx->d_msa0, L, msa, (size_t) row_stride, L, N, cudaMemcpyHostToDevice, ctx->stream));
   RSB_CUDA_OK(rsb_launch_fitch_shuffle(ctx->d_left, ctx->d_right, ctx->d_parent, ctx->d_order, ctx->h_level_start.data(), ctx->nlevels, N, L,
-                                       ctx->d_msa0, seed, first_rep, nrep, ctx->d_res, ctx->d_anc, ctx->d_shanc, ctx->d_perm, ctx->stream));
+                                       ctx->d_msa0, seed, first_id, first_rep, nrep, ctx->d_pool, ctx->d_anc, ctx->d_shanc, ctx->d_perm, ctx->stream));
   ctx->launches += 2 + ctx->nlevels;
   return 0;
 }
 
-int rsb_get_slots(rsb_ctx *ctx, int first_rep, int nrep, uint8_t *out)
+int rsb_pool_get(rsb_ctx *ctx, int first_rep, int nrep, uint8_t *out)
 {
   RSB_CUDA_OK(cudaSetDevice(ctx->device));
-  if (first_rep < 0 || first_rep + nrep > ctx->Rcap) { rsb_set_error(ctx, "replicate slots out of range"); return 1; }
+  if (pool_range_ok(ctx, first_rep, nrep)) return 1;
   const size_t rb = (size_t) ctx->N * ctx->L;
-  RSB_CUDA_OK(cudaMemcpyAsync(out, ctx->d_res + first_rep * rb, rb * nrep, cudaMemcpyDeviceToHost, ctx->stream));
+  RSB_CUDA_OK(cudaMemcpyAsync(out, ctx->d_pool + first_rep * rb, rb * nrep, cudaMemcpyDeviceToHost, ctx->stream));
+  RSB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int rsb_pool_put(rsb_ctx *ctx, int first_rep, int nrep, const uint8_t *in)
+{
+  RSB_CUDA_OK(cudaSetDevice(ctx->device));
+  if (pool_range_ok(ctx, first_rep, nrep)) return 1;
+  const size_t rb = (size_t) ctx->N * ctx->L;
+  RSB_CUDA_OK(cudaMemcpyAsync(ctx->d_pool + first_rep * rb, in, rb * nrep, cudaMemcpyHostToDevice, ctx->stream));
   RSB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
   return 0;
 }

@@ -45,12 +45,13 @@ __device__ __forceinline__ double u01(uint32_t x) { return (double) x * (1.0 / 4
 // ------------------------------------------------------------------------------------------------ generator B
 __global__ void null_simulate_kernel(const int *__restrict__ left, const int *__restrict__ right, const double *__restrict__ pcdf,
                                      int N, int L, const uint8_t *__restrict__ root, const uint8_t *__restrict__ gapmask,
-                                     unsigned long long seed, int first_rep, uint8_t *__restrict__ res, uint8_t *__restrict__ scratch)
+                                     unsigned long long seed, unsigned long long id0, int first_rep, uint8_t *__restrict__ res, uint8_t *__restrict__ scratch)
 {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   const int r = first_rep + blockIdx.y;
+  const uint32_t rid = (uint32_t) (id0 + blockIdx.y);            // global replicate id: the stream does not depend on where the replicate is stored
   if (c >= L) return;
-  Philox rng; rng.key[0] = (uint32_t) seed ^ (0x9E3779B9u * (uint32_t) (r + 1)); rng.key[1] = (uint32_t) (seed >> 32) + (uint32_t) r;
+  Philox rng; rng.key[0] = (uint32_t) seed ^ (0x9E3779B9u * (rid + 1u)); rng.key[1] = (uint32_t) (seed >> 32) + rid;
   uint8_t *anc  = scratch + (size_t) r * (N - 1) * L;        // internal node states [N-1][L]
   uint8_t *leaf = res + (size_t) r * N * L;
   anc[c] = root[c];                                           // cov_add_root
@@ -84,12 +85,13 @@ __device__ __forceinline__ int pick_member(unsigned set, uint32_t rnd)      // u
 }
 
 __global__ void fitch_kernel(const int *__restrict__ left, const int *__restrict__ right, int N, int L,
-                             const uint8_t *__restrict__ msa, unsigned long long seed, int first_rep, uint8_t *__restrict__ ancbuf)
+                             const uint8_t *__restrict__ msa, unsigned long long seed, unsigned long long id0, int first_rep, uint8_t *__restrict__ ancbuf)
 {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   const int r = first_rep + blockIdx.y;
+  const uint32_t rid = (uint32_t) (id0 + blockIdx.y);
   if (c >= L) return;
-  Philox rng; rng.key[0] = (uint32_t) seed ^ 0xF17C4u; rng.key[1] = (uint32_t) (seed >> 32) ^ (0x85EBCA6Bu * (uint32_t) (r + 1));
+  Philox rng; rng.key[0] = (uint32_t) seed ^ 0xF17C4u; rng.key[1] = (uint32_t) (seed >> 32) ^ (0x85EBCA6Bu * (rid + 1u));
   uint8_t *anc = ancbuf + (size_t) r * (N - 1) * L;
   auto leaf_set = [&](int n) -> unsigned {
     const int x = msa[(size_t) n * L + c];
@@ -126,17 +128,18 @@ __global__ void fitch_kernel(const int *__restrict__ left, const int *__restrict
 }
 
 // one random permutation per replicate (Fisher-Yates by one thread; L is a few thousand) and the permuted root row
-__global__ void permute_root_kernel(int N, int L, unsigned long long seed, int first_rep, const uint8_t *__restrict__ ancbuf,
+__global__ void permute_root_kernel(int N, int L, unsigned long long seed, unsigned long long id0, int first_rep, const uint8_t *__restrict__ ancbuf,
                                     uint8_t *__restrict__ shancbuf, int *__restrict__ permbuf)
 {
   const int r = first_rep + blockIdx.x;
+  const uint32_t rid = (uint32_t) (id0 + blockIdx.x);
   int *perm = permbuf + (size_t) r * L;
   const uint8_t *anc = ancbuf + (size_t) r * (N - 1) * L;
   uint8_t *sh = shancbuf + (size_t) r * (N - 1) * L;
   for (int c = threadIdx.x; c < L; c += blockDim.x) perm[c] = c;
   __syncthreads();
   if (threadIdx.x == 0) {
-    Philox rng; rng.key[0] = (uint32_t) seed ^ 0x5AFF1Eu; rng.key[1] = (uint32_t) (seed >> 32) + 0x27D4EB2Fu * (uint32_t) (r + 1);
+    Philox rng; rng.key[0] = (uint32_t) seed ^ 0x5AFF1Eu; rng.key[1] = (uint32_t) (seed >> 32) + 0x27D4EB2Fu * (rid + 1u);
     uint32_t rnd[4]; int have = 0;
     for (int n = L; n > 1; n--) {                                                          // esl_vec_IShuffle
       if (!have) { rng.block((uint32_t) n, 0u, 0x9e37u, 0u, rnd); have = 4; }
@@ -154,7 +157,7 @@ constexpr int RP_MAXWORDS = 128;       // columns / 32 supported per warp bitmas
 // one warp per (replicate, node of this level)
 __global__ void __launch_bounds__(RP_WARPS * 32)
 replay_level_kernel(const int *__restrict__ left, const int *__restrict__ right, const int *__restrict__ order, int lvl_begin, int lvl_count,
-                    int N, int L, const uint8_t *__restrict__ msa, unsigned long long seed, int first_rep, int nrep,
+                    int N, int L, const uint8_t *__restrict__ msa, unsigned long long seed, unsigned long long id0, int first_rep, int nrep,
                     const uint8_t *__restrict__ ancbuf, uint8_t *__restrict__ shancbuf, uint8_t *__restrict__ res)
 {
   __shared__ unsigned masks[RP_WARPS][5][RP_MAXWORDS];
@@ -163,6 +166,7 @@ replay_level_kernel(const int *__restrict__ left, const int *__restrict__ right,
   const long long task = (long long) blockIdx.x * RP_WARPS + warp;
   if (task >= (long long) lvl_count * nrep) return;
   const int r = first_rep + (int) (task / lvl_count);
+  const uint32_t rid = (uint32_t) (id0 + (unsigned long long) (task / lvl_count));
   const int v = order[lvl_begin + (int) (task % lvl_count)];
   const int nwords = (L + 31) >> 5;
   const uint8_t *anc = ancbuf + (size_t) r * (N - 1) * L;
@@ -170,7 +174,7 @@ replay_level_kernel(const int *__restrict__ left, const int *__restrict__ right,
   uint8_t *leaves = res + (size_t) r * N * L;
   const uint8_t *par_o = anc + (size_t) v * L;
   const uint8_t *par_s = shanc + (size_t) v * L;
-  Philox rng; rng.key[0] = (uint32_t) seed ^ (0xC2B2AE35u * (uint32_t) (r + 1)); rng.key[1] = (uint32_t) (seed >> 32) ^ (uint32_t) v;
+  Philox rng; rng.key[0] = (uint32_t) seed ^ (0xC2B2AE35u * (rid + 1u)); rng.key[1] = (uint32_t) (seed >> 32) ^ (uint32_t) v;
   uint32_t ctr = 0;
 
   // class bitmasks of the shuffled parent row (shared by both children: the parent row is read-only here)
@@ -244,27 +248,27 @@ replay_level_kernel(const int *__restrict__ left, const int *__restrict__ right,
 } // namespace
 
 cudaError_t rsb_launch_null_simulate(const int *left, const int *right, const double *pcdf, int N, int L, const uint8_t *root,
-                                     const uint8_t *gapmask, long long gap_stride, unsigned long long seed, int first_rep, int nrep,
+                                     const uint8_t *gapmask, long long gap_stride, unsigned long long seed, unsigned long long id0, int first_rep, int nrep,
                                      uint8_t *res, uint8_t *scratch, cudaStream_t st)
 {
   (void) gap_stride;
-  null_simulate_kernel<<<dim3((L + 127) / 128, nrep), 128, 0, st>>>(left, right, pcdf, N, L, root, gapmask, seed,
+  null_simulate_kernel<<<dim3((L + 127) / 128, nrep), 128, 0, st>>>(left, right, pcdf, N, L, root, gapmask, seed, id0,
                                                                      first_rep, res, scratch);
   return cudaGetLastError();
 }
 
 cudaError_t rsb_launch_fitch_shuffle(const int *left, const int *right, const int *parent, const int *order, const int *level_start_host,
-                                     int nlevels, int N, int L, const uint8_t *msa, unsigned long long seed, int first_rep, int nrep,
+                                     int nlevels, int N, int L, const uint8_t *msa, unsigned long long seed, unsigned long long id0, int first_rep, int nrep,
                                      uint8_t *res, uint8_t *anc, uint8_t *shanc, int *perm, cudaStream_t st)
 {
   (void) parent;
   if (L > RP_MAXWORDS * 32) return cudaErrorInvalidValue;
-  fitch_kernel<<<dim3((L + 127) / 128, nrep), 128, 0, st>>>(left, right, N, L, msa, seed, first_rep, anc);
-  permute_root_kernel<<<nrep, 256, 0, st>>>(N, L, seed, first_rep, anc, shanc, perm);
+  fitch_kernel<<<dim3((L + 127) / 128, nrep), 128, 0, st>>>(left, right, N, L, msa, seed, id0, first_rep, anc);
+  permute_root_kernel<<<nrep, 256, 0, st>>>(N, L, seed, id0, first_rep, anc, shanc, perm);
   for (int lv = 0; lv < nlevels; lv++) {
     const int b = level_start_host[lv], cnt = level_start_host[lv + 1] - b;
     const long long tasks = (long long) cnt * nrep;
-    replay_level_kernel<<<(unsigned) ((tasks + RP_WARPS - 1) / RP_WARPS), RP_WARPS * 32, 0, st>>>(left, right, order, b, cnt, N, L, msa, seed,
+    replay_level_kernel<<<(unsigned) ((tasks + RP_WARPS - 1) / RP_WARPS), RP_WARPS * 32, 0, st>>>(left, right, order, b, cnt, N, L, msa, seed, id0,
                                                                                                   first_rep, nrep, anc, shanc, res);
   }
   return cudaGetLastError();

@@ -10,8 +10,11 @@ import numpy as np
 
 
 def null_shard(nnull, world, rank):
-    """Replicate indices scanned by `rank`: dealt round-robin so that every rank gets floor or ceil of nnull/world."""
-    return list(range(rank, nnull, world))
+    """Replicate ids scanned by `rank`: one contiguous block per rank (so that a generator call covers it), sizes
+    floor or ceil of nnull/world."""
+    base, extra = divmod(nnull, world)
+    first = rank * base + min(rank, extra)
+    return list(range(first, first + base + (1 if rank < extra else 0)))
 
 
 def reduce_histogram(bins, device=None, group=None):

@@ -1,0 +1,178 @@
+"""Device null generators vs the oracle's restatement of the reference generators (which is itself pinned residue for
+residue against the reference code, tests/test_nullgen_oracle.py).  The device uses Philox streams, the reference one
+Mersenne-Twister stream, so agreement is distributional (north_star: two-sample KS on null score histograms and on
+substitution counts) plus exact checks on inputs where the generators are deterministic.
+
+A: Fitch + shuffle (src/msatree.c:173-227,1700-1931; src/msamanip.c:1164-1233,1449-1780)
+B: cov_GenerateAlignment, noss + noindels (src/cov_simulate.c:289-324,585-631,724-773; src/ratematrix.c:185-233)
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+Q_TEST = np.array([[-1.00, 0.30, 0.50, 0.20], [0.25, -0.90, 0.15, 0.50], [0.60, 0.10, -0.95, 0.25], [0.20, 0.45, 0.30, -0.95]])
+
+
+def ks_stat(a, b):
+    a, b = np.sort(a), np.sort(b)
+    allv = np.concatenate([a, b])
+    ca = np.searchsorted(a, allv, side="right") / a.size
+    cb = np.searchsorted(b, allv, side="right") / b.size
+    return float(np.max(np.abs(ca - cb)))
+
+
+def _setup(ctx, po, N, L, seed, R):
+    msa, wgt, _ = po.synthetic_msa(N, L, seed=seed)
+    tree = po.random_tree(N, np.random.default_rng(seed))
+    ctx.configure(N, L, 2, 0)
+    ctx.set_weights(wgt)
+    ctx.set_tree(tree.left, tree.right, tree.parent, tree.ld, tree.rd)
+    ctx.pool_reserve(R)
+    return msa, wgt, tree
+
+
+def _branch_subs(tree, allrows, N):
+    """number of differing positions per branch given rows [leaves | internal nodes]"""
+    out = []
+    for v in range(N - 1):
+        for ch in (tree.left[v], tree.right[v]):
+            row = allrows[N + ch] if ch > 0 else allrows[-ch]
+            out.append(int((allrows[N + v] != row).sum()))
+    return np.array(out)
+
+
+# ------------------------------------------------------------------------------------------------ generator A
+def test_fitch_shuffle_identical_sequences_is_a_column_permutation(ctx, po):
+    N, L = 12, 50
+    row = np.random.default_rng(1).integers(0, 5, L).astype(np.uint8)
+    msa = np.tile(row, (N, 1))
+    tree = po.random_tree(N, np.random.default_rng(2))
+    ctx.configure(N, L, 2, 0)
+    ctx.set_weights(None)
+    ctx.set_tree(tree.left, tree.right, tree.parent, tree.ld, tree.rd)
+    ctx.pool_reserve(3)
+    ctx.null_fitch_shuffle(msa, seed=5, nrep=3)
+    out = ctx.pool_get(3)
+    for r in range(3):
+        assert (out[r] == out[r][0]).all()                                  # no substitutions on any branch
+        assert np.array_equal(np.sort(out[r][0]), np.sort(row))             # a permutation of the columns
+    assert not np.array_equal(out[0][0], out[1][0])                         # replicates use different permutations
+
+
+def test_fitch_shuffle_is_keyed_by_replicate_id(ctx, po):
+    msa, wgt, tree = _setup(ctx, po, 40, 64, 3, 6)
+    ctx.null_fitch_shuffle(msa, seed=9, nrep=4, first_rep=0, first_id=10)
+    a = ctx.pool_get(4)
+    ctx.null_fitch_shuffle(msa, seed=9, nrep=2, first_rep=4, first_id=12)   # ids 12,13 again, other pool entries, other batch
+    b = ctx.pool_get(2, first_rep=4)
+    assert np.array_equal(a[2:], b)
+    assert not np.array_equal(a[0], a[1])
+    assert a.max() <= 4                                                      # only residues and gaps, never N (msamanip.c:1634-1645)
+
+
+def test_fitch_shuffle_distribution_matches_oracle(ctx, pkg, po, oracle):
+    N, L, R = 48, 90, 24
+    msa, wgt, tree = _setup(ctx, po, N, L, 7, R)
+    ctx.null_fitch_shuffle(msa, seed=11, nrep=R)
+    gpu = ctx.pool_get(R)
+    rng = oracle.rng(11)
+    cpu = np.stack([oracle.null_fitch_shuffle(rng, tree, msa) for _ in range(R)])
+    oracle.rng_free(rng)
+    # residue composition of every null equals (statistically) that of the oracle's nulls
+    comp_g = np.stack([(gpu == a).mean(axis=(1, 2)) for a in range(5)])       # [5][R]
+    comp_c = np.stack([(cpu == a).mean(axis=(1, 2)) for a in range(5)])
+    assert np.max(np.abs(comp_g.mean(1) - comp_c.mean(1))) < 0.01
+    # per-sequence composition is (approximately) kept, the author's intent at src/R-scape.c:1664-1667
+    seqcomp_g = np.stack([(gpu == a).mean(axis=2).mean(axis=0) for a in range(5)])   # [5][N]
+    seqcomp_c = np.stack([(cpu == a).mean(axis=2).mean(axis=0) for a in range(5)])
+    assert np.max(np.abs(seqcomp_g - seqcomp_c)) < 0.03
+    # pairwise differences between leaves (substitution counts along the tree) have the same distribution
+    def pairdiff(x):
+        i, j = np.triu_indices(N, 1)
+        return np.concatenate([(x[r][i] != x[r][j]).sum(1) for r in range(R)])
+    assert ks_stat(pairdiff(gpu), pairdiff(cpu)) < 0.05
+    # null GTp score distributions (what the E-values are made of)
+    def scores(x):
+        iu = np.triu_indices(L, 1)
+        return np.concatenate([oracle.scan(x[r], wgt, po.GT, po.C16, po.APC)["cov"][iu] for r in range(R)])
+    sg, sc = scores(gpu), scores(cpu)
+    assert ks_stat(sg, sc) < 0.03
+    for qt in (0.5, 0.9, 0.99, 0.999):
+        a, b = np.quantile(sg, qt), np.quantile(sc, qt)
+        assert abs(a - b) <= 0.08 * max(1.0, abs(b)) + 0.5, (qt, a, b)
+
+
+# ------------------------------------------------------------------------------------------------ generator B
+def test_simulate_identity_and_stationary_limits(ctx, po):
+    N, L = 30, 200
+    tree = po.random_tree(N, np.random.default_rng(4))
+    ctx.configure(N, L, 2, 0)
+    ctx.set_weights(None)
+    root = np.random.default_rng(5).integers(0, 4, L).astype(np.uint8)
+    # zero rate: P = I on every branch, every leaf equals the root
+    ctx.set_tree(tree.left, tree.right, tree.parent, tree.ld, tree.rd)
+    ctx.pool_reserve(2)
+    ctx.null_simulate(np.zeros((4, 4)), root, seed=1, nrep=2)
+    out = ctx.pool_get(2)
+    assert (out == root[None, None, :]).all()
+    # very long branches: leaves are draws from the stationary distribution of Q, whatever the root
+    long_tree = po.Tree(tree.left, tree.right, tree.parent, np.full(N - 1, 200.0), np.full(N - 1, 200.0))
+    ctx.set_tree(long_tree.left, long_tree.right, long_tree.parent, long_tree.ld, long_tree.rd)
+    ctx.null_simulate(Q_TEST, root, seed=2, nrep=2)
+    out = ctx.pool_get(2)
+    w, v = np.linalg.eig(Q_TEST.T)
+    pi = np.real(v[:, np.argmin(np.abs(w))]); pi /= pi.sum()
+    freq = np.array([(out == a).mean() for a in range(4)])
+    assert np.max(np.abs(freq - pi)) < 0.02
+
+
+def test_simulate_gap_mask_and_replicate_ids(ctx, po):
+    msa, wgt, tree = _setup(ctx, po, 35, 70, 8, 5)
+    root = np.random.default_rng(1).integers(0, 4, 70).astype(np.uint8)
+    ctx.null_simulate(Q_TEST, root, seed=3, nrep=3, gapmask=msa, first_id=100)
+    a = ctx.pool_get(3)
+    noncanon = msa >= 4
+    assert (a[:, noncanon] == msa[noncanon][None, :]).all() and (a[:, ~noncanon] < 4).all()
+    ctx.null_simulate(Q_TEST, root, seed=3, nrep=1, gapmask=msa, first_rep=4, first_id=101)
+    assert np.array_equal(ctx.pool_get(1, first_rep=4)[0], a[1])
+
+
+def test_simulate_distribution_matches_oracle(ctx, pkg, po, oracle):
+    N, L, R = 40, 120, 24
+    msa, wgt, tree = _setup(ctx, po, N, L, 12, R)
+    root = np.random.default_rng(2).integers(0, 4, L).astype(np.uint8)
+    ctx.null_simulate(Q_TEST, root, seed=21, nrep=R)
+    gpu = ctx.pool_get(R)
+    rng = oracle.rng(21)
+    cpu = np.stack([oracle.null_simulate(rng, tree, Q_TEST, root) for _ in range(R)])
+    oracle.rng_free(rng)
+    # per-column substitution counts relative to the root (north_star's second KS)
+    sub_g = (gpu != root[None, None, :]).sum(axis=1).ravel()
+    sub_c = (cpu != root[None, None, :]).sum(axis=1).ravel()
+    assert ks_stat(sub_g, sub_c) < 0.04
+    # per-leaf distance to the root follows the branch lengths: leaf by leaf means agree
+    dg = (gpu != root[None, None, :]).mean(axis=(0, 2))
+    dc = (cpu != root[None, None, :]).mean(axis=(0, 2))
+    assert np.max(np.abs(dg - dc)) < 0.04
+    iu = np.triu_indices(L, 1)
+    sg = np.concatenate([oracle.scan(gpu[r], wgt, po.GT, po.C16, po.APC)["cov"][iu] for r in range(R)])
+    sc = np.concatenate([oracle.scan(cpu[r], wgt, po.GT, po.C16, po.APC)["cov"][iu] for r in range(R)])
+    assert ks_stat(sg, sc) < 0.03
+
+
+def test_pool_scan_equals_host_scan(ctx, pkg, po, oracle):
+    """Nulls scanned in place from the device pool give the same histogram as the same alignments passed from the host."""
+    N, L, R = 60, 50, 5
+    msa, wgt, tree = _setup(ctx, po, N, L, 15, R)
+    ctx.null_fitch_shuffle(msa, seed=4, nrep=R)
+    nulls = ctx.pool_get(R)
+    w, mn, mx = ctx.null_width_pool(0)
+    w2, mn2, mx2 = ctx.null_width(nulls[0])
+    assert (w, mn, mx) == (w2, mn2, mx2)
+    ctx.null_hist_pool(0, R, w)
+    a = ctx.hist_read(4096)
+    ctx.hist_reset()
+    ctx.null_hist(nulls, w)
+    b = ctx.hist_read(4096)
+    assert np.array_equal(a[0], b[0]) and a[1] == b[1] == R * L * (L - 1) // 2
