@@ -15,11 +15,11 @@
 //     permute_root_kernel msamanip_ShuffleColumns (src/msamanip.c:1164-1233).  Only the root's permuted row is
 //                         ever read (every other row is overwritten by its parent's row at msamanip.c:1645).
 //     replay_level_kernel shuffle_tree_substitutions + shuffle_tree_substitute_all (src/msamanip.c:1597-1780):
-//                         one warp per (replicate, node) of one tree level; counts the 5x5 substitutions of each
+//                         one thread per (replicate, node) of one tree level; counts the 5x5 substitutions of each
 //                         child branch on the Fitch rows, copies the shuffled parent row to the child and re-places
 //                         the substitutions at positions drawn uniformly without replacement among the columns
-//                         holding the source residue (bitmask + rank-select instead of the reference's Fisher-Yates
-//                         over an index list: same distribution).
+//                         holding the source residue (one-pass selection sampling instead of the reference's
+//                         Fisher-Yates over an index list: same distribution, exact counts).
 #include "rsb_common.cuh"
 
 namespace {
@@ -151,97 +151,134 @@ __global__ void permute_root_kernel(int N, int L, unsigned long long seed, unsig
   for (int c = threadIdx.x; c < L; c += blockDim.x) sh[c] = anc[perm[c]];
 }
 
-constexpr int RP_WARPS = 4;
-constexpr int RP_MAXWORDS = 128;       // columns / 32 supported per warp bitmask (L <= 4096)
+constexpr int RP_THREADS = 128;
 
-// one warp per (replicate, node of this level)
-__global__ void __launch_bounds__(RP_WARPS * 32)
+// PCG32 (XSH-RR): the cheap sequential stream of one (replicate, branch), seeded from a Philox block
+struct Pcg32 {
+  unsigned long long state, inc;
+  __device__ __forceinline__ uint32_t next() {
+    const unsigned long long old = state;
+    state = old * 6364136223846793005ULL + inc;
+    const uint32_t xs = (uint32_t) (((old >> 18u) ^ old) >> 27u), rot = (uint32_t) (old >> 59u);
+    return (xs >> rot) | (xs << ((32u - rot) & 31u));
+  }
+};
+
+// One thread per (replicate, node of this tree level): both child branches of the node are replayed by that thread.
+// Pass 1 counts the branch's 5x5 substitutions on the Fitch rows and the residue classes of the shuffled parent row;
+// pass 2 walks the shuffled parent row once and re-places the substitutions by sequential selection sampling
+// (Knuth's Algorithm S): a position currently holding class a is picked with probability k_a / m_a (substitutions out of
+// a still to place / a-positions still to come), a picked position takes target d with probability n_{a->d} / k_a.
+// Every subset of positions and every assignment of targets is equally likely, exactly as after the reference's
+// Fisher-Yates shuffle of the position list (src/msamanip.c:1718-1757), and the substitution counts are reproduced exactly.
+// WORD: rows are read and written as 32-bit words (L % 4 == 0), otherwise byte by byte.
+template <bool WORD>
+__global__ void __launch_bounds__(RP_THREADS)
 replay_level_kernel(const int *__restrict__ left, const int *__restrict__ right, const int *__restrict__ order, int lvl_begin, int lvl_count,
                     int N, int L, const uint8_t *__restrict__ msa, unsigned long long seed, unsigned long long id0, int first_rep, int nrep,
                     const uint8_t *__restrict__ ancbuf, uint8_t *__restrict__ shancbuf, uint8_t *__restrict__ res)
 {
-  __shared__ unsigned masks[RP_WARPS][5][RP_MAXWORDS];
-  __shared__ int nsub[RP_WARPS][25];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long task = (long long) blockIdx.x * RP_WARPS + warp;
+  __shared__ unsigned short nsub[25][RP_THREADS];     // substitutions a -> d still to place
+  __shared__ unsigned short mcls[5][RP_THREADS];      // class counts of the shuffled parent row
+  __shared__ unsigned short mrem[5][RP_THREADS];      // a-positions still to come
+  __shared__ unsigned short krem[5][RP_THREADS];      // substitutions out of a still to place
+  const int t = threadIdx.x;
+  const long long task = (long long) blockIdx.x * RP_THREADS + t;
   if (task >= (long long) lvl_count * nrep) return;
-  const int r = first_rep + (int) (task / lvl_count);
-  const uint32_t rid = (uint32_t) (id0 + (unsigned long long) (task / lvl_count));
+  const int rr = (int) (task / lvl_count);
+  const int r = first_rep + rr;
+  const uint32_t rid = (uint32_t) (id0 + (unsigned long long) rr);
   const int v = order[lvl_begin + (int) (task % lvl_count)];
-  const int nwords = (L + 31) >> 5;
   const uint8_t *anc = ancbuf + (size_t) r * (N - 1) * L;
   uint8_t *shanc = shancbuf + (size_t) r * (N - 1) * L;
   uint8_t *leaves = res + (size_t) r * N * L;
   const uint8_t *par_o = anc + (size_t) v * L;
   const uint8_t *par_s = shanc + (size_t) v * L;
-  Philox rng; rng.key[0] = (uint32_t) seed ^ (0xC2B2AE35u * (rid + 1u)); rng.key[1] = (uint32_t) (seed >> 32) ^ (uint32_t) v;
-  uint32_t ctr = 0;
 
-  // class bitmasks of the shuffled parent row (shared by both children: the parent row is read-only here)
-  for (int wd = lane; wd < nwords; wd += 32)
-    #pragma unroll
-    for (int a = 0; a < 5; a++) masks[warp][a][wd] = 0;
-  __syncwarp();
-  for (int c0 = 0; c0 < L; c0 += 32) {
-    const int c = c0 + lane;
-    const int x = (c < L) ? par_s[c] : 255;
-    #pragma unroll
-    for (int a = 0; a < 5; a++) { const unsigned b = __ballot_sync(0xffffffffu, x == a); if (lane == 0) masks[warp][a][c0 >> 5] = b; }
+  Philox ph; ph.key[0] = (uint32_t) seed ^ (0xC2B2AE35u * (rid + 1u)); ph.key[1] = (uint32_t) (seed >> 32) ^ 0x5bd1e995u;
+  uint32_t sd[4]; ph.block((uint32_t) v, 0x7ee1u, 0u, 0u, sd);
+  Pcg32 rng; rng.state = ((unsigned long long) sd[0] << 32) | sd[1]; rng.inc = ((((unsigned long long) sd[2] << 32) | sd[3]) << 1) | 1ULL;
+  rng.next();
+
+  #pragma unroll
+  for (int a = 0; a < 5; a++) mcls[a][t] = 0;
+  if (WORD) {
+    const uint32_t *ps4 = reinterpret_cast<const uint32_t *>(par_s);
+    for (int c4 = 0; c4 < L / 4; c4++) {
+      const uint32_t w = ps4[c4];
+      #pragma unroll
+      for (int q = 0; q < 4; q++) mcls[(w >> (8 * q)) & 0xff][t]++;
+    }
+  } else {
+    for (int c = 0; c < L; c++) mcls[par_s[c]][t]++;
   }
-  __syncwarp();
 
   for (int side = 0; side < 2; side++) {
     const int ch = side ? right[v] : left[v];
     const uint8_t *kid_o = (ch > 0) ? anc + (size_t) ch * L : msa + (size_t) (-ch) * L;
     uint8_t *kid_s = (ch > 0) ? shanc + (size_t) ch * L : leaves + (size_t) (-ch) * L;
-    if (lane < 25) nsub[warp][lane] = 0;
-    __syncwarp();
-    for (int c = lane; c < L; c += 32) {
-      const int pa = par_o[c], kd = kid_o[c];
-      if (pa != kd && pa <= 4 && kd <= 4) atomicAdd(&nsub[warp][pa * 5 + kd], 1);        // msamanip.c:1634-1643
-      kid_s[c] = par_s[c];                                                                 // :1645
-    }
-    __syncwarp();
-    for (int a = 0; a < 5; a++) {
-      // working copy of the class-a mask lives in registers: lane owns words lane, lane+32, ...
-      unsigned wv[RP_MAXWORDS / 32]; int pc = 0;
-      #pragma unroll
-      for (int q = 0; q < RP_MAXWORDS / 32; q++) { const int wd = lane + 32 * q; wv[q] = (wd < nwords) ? masks[warp][a][wd] : 0u; pc += __popc(wv[q]); }
-      int remaining = pc;
-      #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) remaining += __shfl_xor_sync(0xffffffffu, remaining, o);
-      for (int d = 0; d < 5; d++) {
-        int s = nsub[warp][a * 5 + d];
-        while (s > 0 && remaining > 0) {
-          uint32_t rnd[4];
-          rng.block(ctr++, (uint32_t) side, 0xab1eu, 0u, rnd);
-          int k = (int) (((unsigned long long) rnd[0] * (unsigned) remaining) >> 32);     // k-th remaining candidate, lane-major order
-          // inclusive scan of per-lane counts to find the owning lane
-          int incl = pc;
-          #pragma unroll
-          for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-          const unsigned owner_ballot = __ballot_sync(0xffffffffu, incl > k);
-          const int owner = __ffs(owner_ballot) - 1;
-          const int before = __shfl_sync(0xffffffffu, incl - pc, owner);
-          if (lane == owner) {
-            int kk = k - before;
-            #pragma unroll
-            for (int q = 0; q < RP_MAXWORDS / 32; q++) {
-              const int n = __popc(wv[q]);
-              if (kk >= 0 && kk < n) {
-                const int bit = __fns(wv[q], 0, kk + 1);
-                wv[q] &= ~(1u << bit);
-                kid_s[(lane + 32 * q) * 32 + bit] = (uint8_t) d;
-                kk = -1;
-              } else if (kk >= 0) kk -= n;
-            }
-            pc--;
-          }
-          remaining--; s--;
+    #pragma unroll
+    for (int k = 0; k < 25; k++) nsub[k][t] = 0;
+    // pass 1: substitutions of this branch on the Fitch rows (msamanip.c:1634-1643)
+    if (WORD) {
+      const uint32_t *po4 = reinterpret_cast<const uint32_t *>(par_o), *ko4 = reinterpret_cast<const uint32_t *>(kid_o);
+      for (int c4 = 0; c4 < L / 4; c4++) {
+        const uint32_t wp = po4[c4], wk = ko4[c4];
+        if (wp == wk) continue;
+        #pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const int pa = (wp >> (8 * q)) & 0xff, kd = (wk >> (8 * q)) & 0xff;
+          if (pa != kd && pa <= 4 && kd <= 4) nsub[pa * 5 + kd][t]++;
         }
       }
+    } else {
+      for (int c = 0; c < L; c++) {
+        const int pa = par_o[c], kd = kid_o[c];
+        if (pa != kd && pa <= 4 && kd <= 4) nsub[pa * 5 + kd][t]++;
+      }
     }
-    __syncwarp();
+    int ktot = 0;
+    #pragma unroll
+    for (int a = 0; a < 5; a++) {
+      int k = 0;
+      #pragma unroll
+      for (int d = 0; d < 5; d++) k += nsub[a * 5 + d][t];
+      krem[a][t] = (unsigned short) k; mrem[a][t] = mcls[a][t]; ktot += k;
+    }
+    // pass 2: copy the shuffled parent row (:1645) and re-place the substitutions
+    auto place = [&](int cls) -> int {
+      int out = cls;
+      const int k = krem[cls][t], m = mrem[cls][t];
+      if (k > 0) {
+        if ((int) (((unsigned long long) rng.next() * (unsigned) m) >> 32) < k) {
+          int pick = (int) (((unsigned long long) rng.next() * (unsigned) k) >> 32);
+          int d = 0;
+          for (; d < 4; d++) { const int n = nsub[cls * 5 + d][t]; if (pick < n) break; pick -= n; }
+          nsub[cls * 5 + d][t]--;
+          krem[cls][t] = (unsigned short) (k - 1);
+          ktot--;
+          out = d;
+        }
+      }
+      mrem[cls][t] = (unsigned short) (m - 1);
+      return out;
+    };
+    if (WORD) {
+      const uint32_t *ps4 = reinterpret_cast<const uint32_t *>(par_s);
+      uint32_t *ks4 = reinterpret_cast<uint32_t *>(kid_s);
+      for (int c4 = 0; c4 < L / 4; c4++) {
+        uint32_t w = ps4[c4];
+        if (ktot > 0) {
+          uint32_t o = 0;
+          #pragma unroll
+          for (int q = 0; q < 4; q++) o |= (uint32_t) place((w >> (8 * q)) & 0xff) << (8 * q);
+          w = o;
+        }
+        ks4[c4] = w;
+      }
+    } else {
+      for (int c = 0; c < L; c++) { const int cls = par_s[c]; kid_s[c] = (uint8_t) (ktot > 0 ? place(cls) : cls); }
+    }
   }
 }
 
@@ -262,14 +299,15 @@ cudaError_t rsb_launch_fitch_shuffle(const int *left, const int *right, const in
                                      uint8_t *res, uint8_t *anc, uint8_t *shanc, int *perm, cudaStream_t st)
 {
   (void) parent;
-  if (L > RP_MAXWORDS * 32) return cudaErrorInvalidValue;
+  if (L > 65535) return cudaErrorInvalidValue;            // per-class counters are 16 bit
   fitch_kernel<<<dim3((L + 127) / 128, nrep), 128, 0, st>>>(left, right, N, L, msa, seed, id0, first_rep, anc);
   permute_root_kernel<<<nrep, 256, 0, st>>>(N, L, seed, id0, first_rep, anc, shanc, perm);
   for (int lv = 0; lv < nlevels; lv++) {
     const int b = level_start_host[lv], cnt = level_start_host[lv + 1] - b;
     const long long tasks = (long long) cnt * nrep;
-    replay_level_kernel<<<(unsigned) ((tasks + RP_WARPS - 1) / RP_WARPS), RP_WARPS * 32, 0, st>>>(left, right, order, b, cnt, N, L, msa, seed, id0,
-                                                                                                  first_rep, nrep, anc, shanc, res);
+    const unsigned grid = (unsigned) ((tasks + RP_THREADS - 1) / RP_THREADS);
+    if (L % 4 == 0) replay_level_kernel<true><<<grid, RP_THREADS, 0, st>>>(left, right, order, b, cnt, N, L, msa, seed, id0, first_rep, nrep, anc, shanc, res);
+    else            replay_level_kernel<false><<<grid, RP_THREADS, 0, st>>>(left, right, order, b, cnt, N, L, msa, seed, id0, first_rep, nrep, anc, shanc, res);
   }
   return cudaGetLastError();
 }
