@@ -40,7 +40,8 @@ cudaError_t rsb_launch_correct_hist(double *cov, const double *covx, const doubl
                                     int *flags, cudaStream_t st);
 cudaError_t rsb_launch_width(const double *minmax, double w_old, double bmin, int hpts, double tol, double *wout, cudaStream_t st);
 cudaError_t rsb_launch_symmetrize(double *cov, int L, int Lp, cudaStream_t st);
-cudaError_t rsb_launch_null_simulate(const int *left, const int *right, const double *pcdf, int N, int L, const uint8_t *root,
+cudaError_t rsb_launch_null_simulate(const int *left, const int *right, const int *order, const int *level_start_host, int nlevels,
+                                     const double *pcdf, int N, int L, const uint8_t *root,
                                      const uint8_t *gapmask, long long gap_stride, unsigned long long seed, unsigned long long id0, int first_rep, int nrep,
                                      uint8_t *res, uint8_t *scratch, cudaStream_t st);
 cudaError_t rsb_launch_fitch_shuffle(const int *left, const int *right, const int *parent, const int *order, const int *level_start,
@@ -976,9 +977,9 @@ int rsb_null_simulate(rsb_ctx *ctx, const double *Q, const uint8_t *root, const 
     RSB_CUDA_OK(cudaMemcpy2DAsync(ctx->d_gapmask, L, gapmask, (size_t) gap_stride, L, N, cudaMemcpyHostToDevice, ctx->stream));
   }
   RSB_CUDA_OK(cudaStreamSynchronize(ctx->stream));       // pb is a host temporary
-  RSB_CUDA_OK(rsb_launch_null_simulate(ctx->d_left, ctx->d_right, ctx->d_pcdf, N, L, ctx->d_root, gapmask ? ctx->d_gapmask : nullptr, L,
+  RSB_CUDA_OK(rsb_launch_null_simulate(ctx->d_left, ctx->d_right, ctx->d_order, ctx->h_level_start.data(), ctx->nlevels, ctx->d_pcdf, N, L, ctx->d_root, gapmask ? ctx->d_gapmask : nullptr, L,
                                        seed, first_id, first_rep, nrep, ctx->d_pool, ctx->d_simscratch, ctx->stream));
-  ctx->launches++;
+  ctx->launches += ctx->nlevels;
   return 0;
 }
 
@@ -995,7 +996,7 @@ int rsb_null_fitch_shuffle(rsb_ctx *ctx, const uint8_t *msa, int64_t row_stride,
   RSB_CUDA_OK(cudaMemcpy2DAsync(ctx->d_msa0, L, msa, (size_t) row_stride, L, N, cudaMemcpyHostToDevice, ctx->stream));
   RSB_CUDA_OK(rsb_launch_fitch_shuffle(ctx->d_left, ctx->d_right, ctx->d_parent, ctx->d_order, ctx->h_level_start.data(), ctx->nlevels, N, L,
                                        ctx->d_msa0, seed, first_id, first_rep, nrep, ctx->d_pool, ctx->d_anc, ctx->d_shanc, ctx->d_perm, ctx->stream));
-  ctx->launches += 2 + ctx->nlevels;
+  ctx->launches += 1 + 3 * ctx->nlevels;
   return 0;
 }
 

@@ -3,15 +3,15 @@
 // (B) null_simulate_kernel: cov_GenerateAlignment's ungapped, structure-free path
 //     (src/cov_simulate.c:289-324 tree walk, :585-631 emission, :724-773 inverse-CDF draw) with
 //     P(t) = exp(tQ) per branch (src/ratematrix.c:185-233; matrices are built on the host in capi.cu,
-//     4x4 per branch).  Every (replicate, column) is an independent chain down the tree, so one thread
-//     owns one (replicate, column) and walks v = 0..N-2 (parents precede children).
+//     4x4 per branch).  Every (replicate, column) is an independent chain down the tree; the tree is walked one
+//     level per launch (nodes of a level are independent given their parents), one thread per (replicate, node, column).
 //     Randomness: Philox4x32-10 keyed by (seed, replicate), counter (node, column): one 128-bit block
 //     serves both children of a node.  The reference consumes one Mersenne-Twister stream in branch-major
 //     order; the streams differ, the per-draw distribution is the same (validated distributionally).
 //
 // (A) Fitch + shuffle, R-scape's default null (src/R-scape.c:1653-1668):
-//     fitch_kernel        tree_fitch_column (src/msatree.c:1700-1831): one thread per (replicate, column);
-//                         sets as 5-bit masks, post-order = descending node index, pre-order = ascending.
+//     fitch_up/down_level tree_fitch_column (src/msatree.c:1700-1831): sets as 5-bit masks; post-order = one launch per
+//                         tree level from the deepest up, pre-order = from the root down; thread per (replicate, node, column).
 //     permute_root_kernel msamanip_ShuffleColumns (src/msamanip.c:1164-1233).  Only the root's permuted row is
 //                         ever read (every other row is overwritten by its parent's row at msamanip.c:1645).
 //     replay_level_kernel shuffle_tree_substitutions + shuffle_tree_substitute_all (src/msamanip.c:1597-1780):
@@ -43,35 +43,36 @@ struct Philox {
 __device__ __forceinline__ double u01(uint32_t x) { return (double) x * (1.0 / 4294967296.0); }   // as esl_random: x / 2^32
 
 // ------------------------------------------------------------------------------------------------ generator B
-__global__ void null_simulate_kernel(const int *__restrict__ left, const int *__restrict__ right, const double *__restrict__ pcdf,
-                                     int N, int L, const uint8_t *__restrict__ root, const uint8_t *__restrict__ gapmask,
-                                     unsigned long long seed, unsigned long long id0, int first_rep, uint8_t *__restrict__ res, uint8_t *__restrict__ scratch)
+// One launch per tree level (nodes of a level are independent given their parents); a thread owns one
+// (replicate, node, column) and emits both children of the node.  grid = (columns/128, nodes of the level, replicates).
+__global__ void null_simulate_level_kernel(const int *__restrict__ left, const int *__restrict__ right, const int *__restrict__ order,
+                                           int lvl_begin, const double *__restrict__ pcdf, int N, int L, const uint8_t *__restrict__ root,
+                                           const uint8_t *__restrict__ gapmask, unsigned long long seed, unsigned long long id0,
+                                           int first_rep, uint8_t *__restrict__ res, uint8_t *__restrict__ scratch)
 {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  const int r = first_rep + blockIdx.y;
-  const uint32_t rid = (uint32_t) (id0 + blockIdx.y);            // global replicate id: the stream does not depend on where the replicate is stored
+  const int v = order[lvl_begin + blockIdx.y];
+  const int r = first_rep + blockIdx.z;
+  const uint32_t rid = (uint32_t) (id0 + blockIdx.z);            // global replicate id: the stream does not depend on where the replicate is stored
   if (c >= L) return;
   Philox rng; rng.key[0] = (uint32_t) seed ^ (0x9E3779B9u * (rid + 1u)); rng.key[1] = (uint32_t) (seed >> 32) + rid;
   uint8_t *anc  = scratch + (size_t) r * (N - 1) * L;        // internal node states [N-1][L]
   uint8_t *leaf = res + (size_t) r * N * L;
-  anc[c] = root[c];                                           // cov_add_root
-  for (int v = 0; v < N - 1; v++) {
-    const int par = anc[(size_t) v * L + c] & 3;
-    uint32_t rnd[4];
-    rng.block((uint32_t) v, (uint32_t) c, 0x5eedu, 0u, rnd);
-    #pragma unroll
-    for (int side = 0; side < 2; side++) {
-      const int child = side ? right[v] : left[v];
-      const double *cdf = pcdf + ((size_t) v * 2 + side) * 16 + par * 4;
-      const double x = u01(rnd[side]);
-      int k = 0;                                              // cov_addres: first k with cdf_k > x, else K-1
-      while (k < 3 && !(cdf[k] > x)) k++;
-      if (child > 0) anc[(size_t) child * L + c] = (uint8_t) k;
-      else {
-        uint8_t out = (uint8_t) k;
-        if (gapmask) { const uint8_t g = gapmask[(size_t) (-child) * L + c]; if (g >= 4) out = g; }
-        leaf[(size_t) (-child) * L + c] = out;
-      }
+  const int par = (v == 0 ? root[c] : anc[(size_t) v * L + c]) & 3;       // cov_add_root for the root
+  uint32_t rnd[4];
+  rng.block((uint32_t) v, (uint32_t) c, 0x5eedu, 0u, rnd);
+  #pragma unroll
+  for (int side = 0; side < 2; side++) {
+    const int child = side ? right[v] : left[v];
+    const double *cdf = pcdf + ((size_t) v * 2 + side) * 16 + par * 4;
+    const double x = u01(rnd[side]);
+    int k = 0;                                              // cov_addres: first k with cdf_k > x, else K-1
+    while (k < 3 && !(cdf[k] > x)) k++;
+    if (child > 0) anc[(size_t) child * L + c] = (uint8_t) k;
+    else {
+      uint8_t out = (uint8_t) k;
+      if (gapmask) { const uint8_t g = gapmask[(size_t) (-child) * L + c]; if (g >= 4) out = g; }
+      leaf[(size_t) (-child) * L + c] = out;
     }
   }
 }
@@ -84,12 +85,16 @@ __device__ __forceinline__ int pick_member(unsigned set, uint32_t rnd)      // u
   return __fns(set, 0, k + 1);
 }
 
-__global__ void fitch_kernel(const int *__restrict__ left, const int *__restrict__ right, int N, int L,
-                             const uint8_t *__restrict__ msa, unsigned long long seed, unsigned long long id0, int first_rep, uint8_t *__restrict__ ancbuf)
+// Fitch sets, one launch per tree level from the deepest up (:1758-1777, :1869-1905): a thread owns one
+// (replicate, node, column).  grid = (columns/128, nodes of the level, replicates).
+__global__ void fitch_up_level_kernel(const int *__restrict__ left, const int *__restrict__ right, const int *__restrict__ order, int lvl_begin,
+                                      int N, int L, const uint8_t *__restrict__ msa, unsigned long long seed, unsigned long long id0,
+                                      int first_rep, uint8_t *__restrict__ ancbuf)
 {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  const int r = first_rep + blockIdx.y;
-  const uint32_t rid = (uint32_t) (id0 + blockIdx.y);
+  const int v = order[lvl_begin + blockIdx.y];
+  const int r = first_rep + blockIdx.z;
+  const uint32_t rid = (uint32_t) (id0 + blockIdx.z);
   if (c >= L) return;
   Philox rng; rng.key[0] = (uint32_t) seed ^ 0xF17C4u; rng.key[1] = (uint32_t) (seed >> 32) ^ (0x85EBCA6Bu * (rid + 1u));
   uint8_t *anc = ancbuf + (size_t) r * (N - 1) * L;
@@ -99,31 +104,40 @@ __global__ void fitch_kernel(const int *__restrict__ left, const int *__restrict
     uint32_t rnd[4]; rng.block((uint32_t) n, (uint32_t) c, 0x1eafu, 0u, rnd);          // unknown -> one of the 5 at random (:1735)
     return 1u << (int) (((unsigned long long) rnd[0] * 5u) >> 32);
   };
-  // upwards (:1758-1777, :1869-1905): children have larger indices than their parent
-  for (int v = N - 2; v >= 0; v--) {
-    const int l = left[v], rr = right[v];
-    const unsigned Sl = (l > 0) ? anc[(size_t) l * L + c] : leaf_set(-l);
-    const unsigned Sr = (rr > 0) ? anc[(size_t) rr * L + c] : leaf_set(-rr);
-    unsigned S = Sl & Sr;
-    if (!S) S = (Sl | Sr) & 0xFu;                                                         // union of residues; a gap never joins
-    anc[(size_t) v * L + c] = (uint8_t) S;
-  }
-  // downwards (:1779-1815): the stored set is replaced by the chosen residue
-  {
+  const int l = left[v], rr = right[v];
+  const unsigned Sl = (l > 0) ? anc[(size_t) l * L + c] : leaf_set(-l);
+  const unsigned Sr = (rr > 0) ? anc[(size_t) rr * L + c] : leaf_set(-rr);
+  unsigned S = Sl & Sr;
+  if (!S) S = (Sl | Sr) & 0xFu;                                                         // union of residues; a gap never joins
+  anc[(size_t) v * L + c] = (uint8_t) S;
+}
+
+// Traceback, one launch per level from the root down (:1779-1815): the stored set of each internal child is replaced by
+// the chosen residue (the parent's residue if it is in the child's set, else a uniform member).
+__global__ void fitch_down_level_kernel(const int *__restrict__ left, const int *__restrict__ right, const int *__restrict__ order, int lvl_begin,
+                                        int N, int L, unsigned long long seed, unsigned long long id0, int first_rep, uint8_t *__restrict__ ancbuf)
+{
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int v = order[lvl_begin + blockIdx.y];
+  const int r = first_rep + blockIdx.z;
+  const uint32_t rid = (uint32_t) (id0 + blockIdx.z);
+  if (c >= L) return;
+  Philox rng; rng.key[0] = (uint32_t) seed ^ 0xF17C4u; rng.key[1] = (uint32_t) (seed >> 32) ^ (0x85EBCA6Bu * (rid + 1u));
+  uint8_t *anc = ancbuf + (size_t) r * (N - 1) * L;
+  int ax;
+  if (v == 0) {                                                                          // root: uniform member of its set (:1779)
     uint32_t rnd[4]; rng.block(0xffffffffu, (uint32_t) c, 0x600du, 0u, rnd);
-    anc[c] = (uint8_t) pick_member(anc[c], rnd[0]);
-  }
-  for (int v = 0; v < N - 1; v++) {
-    const int ax = anc[(size_t) v * L + c];
-    uint32_t rnd[4]; rng.block((uint32_t) v, (uint32_t) c, 0xd0c0u, 0u, rnd);
-    const int kids[2] = { left[v], right[v] };
-    #pragma unroll
-    for (int side = 0; side < 2; side++) {
-      const int ch = kids[side];
-      if (ch <= 0) continue;
-      const unsigned S = anc[(size_t) ch * L + c];
-      anc[(size_t) ch * L + c] = (uint8_t) (((S >> ax) & 1u) ? ax : pick_member(S, rnd[side]));
-    }
+    ax = pick_member(anc[c], rnd[0]);
+    anc[c] = (uint8_t) ax;
+  } else ax = anc[(size_t) v * L + c];
+  uint32_t rnd[4]; rng.block((uint32_t) v, (uint32_t) c, 0xd0c0u, 0u, rnd);
+  const int kids[2] = { left[v], right[v] };
+  #pragma unroll
+  for (int side = 0; side < 2; side++) {
+    const int ch = kids[side];
+    if (ch <= 0) continue;
+    const unsigned S = anc[(size_t) ch * L + c];
+    anc[(size_t) ch * L + c] = (uint8_t) (((S >> ax) & 1u) ? ax : pick_member(S, rnd[side]));
   }
 }
 
@@ -152,6 +166,7 @@ __global__ void permute_root_kernel(int N, int L, unsigned long long seed, unsig
 }
 
 constexpr int RP_THREADS = 128;
+constexpr int RP_BATCH   = 8;        // 32-bit words (4 alignment columns each) loaded together
 
 // PCG32 (XSH-RR): the cheap sequential stream of one (replicate, branch), seeded from a Philox block
 struct Pcg32 {
@@ -183,6 +198,7 @@ replay_level_kernel(const int *__restrict__ left, const int *__restrict__ right,
   __shared__ unsigned short mrem[5][RP_THREADS];      // a-positions still to come
   __shared__ unsigned short krem[5][RP_THREADS];      // substitutions out of a still to place
   const int t = threadIdx.x;
+  const int L4 = L / 4;
   const long long task = (long long) blockIdx.x * RP_THREADS + t;
   if (task >= (long long) lvl_count * nrep) return;
   const int rr = (int) (task / lvl_count);
@@ -203,14 +219,20 @@ replay_level_kernel(const int *__restrict__ left, const int *__restrict__ right,
   #pragma unroll
   for (int a = 0; a < 5; a++) mcls[a][t] = 0;
   if (WORD) {
+    // rows are walked in batches of RP_BATCH words whose loads are issued together: the thread is alone on its rows, so
+    // memory latency can only be hidden by its own loads in flight
     const uint32_t *ps4 = reinterpret_cast<const uint32_t *>(par_s);
-    for (int c4 = 0; c4 < L / 4; c4++) {
-      const uint32_t w = ps4[c4];
+    for (int c4 = 0; c4 < L4; c4 += RP_BATCH) {
+      uint32_t wb[RP_BATCH];
       #pragma unroll
-      for (int q = 0; q < 4; q++) mcls[(w >> (8 * q)) & 0xff][t]++;
+      for (int u = 0; u < RP_BATCH; u++) wb[u] = (c4 + u < L4) ? __ldcg(ps4 + c4 + u) : 0x05050505u;
+      #pragma unroll
+      for (int u = 0; u < RP_BATCH; u++)
+        #pragma unroll
+        for (int q = 0; q < 4; q++) { const int x = (wb[u] >> (8 * q)) & 0xff; if (x < 5) mcls[x][t]++; }
     }
   } else {
-    for (int c = 0; c < L; c++) mcls[par_s[c]][t]++;
+    for (int c = 0; c < L; c++) { const int x = par_s[c]; if (x < 5) mcls[x][t]++; }
   }
 
   for (int side = 0; side < 2; side++) {
@@ -222,13 +244,18 @@ replay_level_kernel(const int *__restrict__ left, const int *__restrict__ right,
     // pass 1: substitutions of this branch on the Fitch rows (msamanip.c:1634-1643)
     if (WORD) {
       const uint32_t *po4 = reinterpret_cast<const uint32_t *>(par_o), *ko4 = reinterpret_cast<const uint32_t *>(kid_o);
-      for (int c4 = 0; c4 < L / 4; c4++) {
-        const uint32_t wp = po4[c4], wk = ko4[c4];
-        if (wp == wk) continue;
+      for (int c4 = 0; c4 < L4; c4 += RP_BATCH) {
+        uint32_t wp[RP_BATCH], wk[RP_BATCH];
         #pragma unroll
-        for (int q = 0; q < 4; q++) {
-          const int pa = (wp >> (8 * q)) & 0xff, kd = (wk >> (8 * q)) & 0xff;
-          if (pa != kd && pa <= 4 && kd <= 4) nsub[pa * 5 + kd][t]++;
+        for (int u = 0; u < RP_BATCH; u++) { const bool in = c4 + u < L4; wp[u] = in ? __ldcg(po4 + c4 + u) : 0u; wk[u] = in ? __ldcg(ko4 + c4 + u) : 0u; }
+        #pragma unroll
+        for (int u = 0; u < RP_BATCH; u++) {
+          if (wp[u] == wk[u]) continue;
+          #pragma unroll
+          for (int q = 0; q < 4; q++) {
+            const int pa = (wp[u] >> (8 * q)) & 0xff, kd = (wk[u] >> (8 * q)) & 0xff;
+            if (pa != kd && pa <= 4 && kd <= 4) nsub[pa * 5 + kd][t]++;
+          }
         }
       }
     } else {
@@ -248,6 +275,7 @@ replay_level_kernel(const int *__restrict__ left, const int *__restrict__ right,
     // pass 2: copy the shuffled parent row (:1645) and re-place the substitutions
     auto place = [&](int cls) -> int {
       int out = cls;
+      if (cls > 4) return out;
       const int k = krem[cls][t], m = mrem[cls][t];
       if (k > 0) {
         if ((int) (((unsigned long long) rng.next() * (unsigned) m) >> 32) < k) {
@@ -266,15 +294,22 @@ replay_level_kernel(const int *__restrict__ left, const int *__restrict__ right,
     if (WORD) {
       const uint32_t *ps4 = reinterpret_cast<const uint32_t *>(par_s);
       uint32_t *ks4 = reinterpret_cast<uint32_t *>(kid_s);
-      for (int c4 = 0; c4 < L / 4; c4++) {
-        uint32_t w = ps4[c4];
-        if (ktot > 0) {
-          uint32_t o = 0;
-          #pragma unroll
-          for (int q = 0; q < 4; q++) o |= (uint32_t) place((w >> (8 * q)) & 0xff) << (8 * q);
-          w = o;
+      for (int c4 = 0; c4 < L4; c4 += RP_BATCH) {
+        uint32_t wb[RP_BATCH];
+        #pragma unroll
+        for (int u = 0; u < RP_BATCH; u++) wb[u] = (c4 + u < L4) ? __ldcg(ps4 + c4 + u) : 0u;
+        #pragma unroll
+        for (int u = 0; u < RP_BATCH; u++) {
+          if (c4 + u >= L4) break;
+          uint32_t w = wb[u];
+          if (ktot > 0) {
+            uint32_t o = 0;
+            #pragma unroll
+            for (int q = 0; q < 4; q++) o |= (uint32_t) place((w >> (8 * q)) & 0xff) << (8 * q);
+            w = o;
+          }
+          ks4[c4 + u] = w;
         }
-        ks4[c4] = w;
       }
     } else {
       for (int c = 0; c < L; c++) { const int cls = par_s[c]; kid_s[c] = (uint8_t) (ktot > 0 ? place(cls) : cls); }
@@ -284,13 +319,17 @@ replay_level_kernel(const int *__restrict__ left, const int *__restrict__ right,
 
 } // namespace
 
-cudaError_t rsb_launch_null_simulate(const int *left, const int *right, const double *pcdf, int N, int L, const uint8_t *root,
+cudaError_t rsb_launch_null_simulate(const int *left, const int *right, const int *order, const int *level_start_host, int nlevels,
+                                     const double *pcdf, int N, int L, const uint8_t *root,
                                      const uint8_t *gapmask, long long gap_stride, unsigned long long seed, unsigned long long id0, int first_rep, int nrep,
                                      uint8_t *res, uint8_t *scratch, cudaStream_t st)
 {
   (void) gap_stride;
-  null_simulate_kernel<<<dim3((L + 127) / 128, nrep), 128, 0, st>>>(left, right, pcdf, N, L, root, gapmask, seed, id0,
-                                                                     first_rep, res, scratch);
+  for (int lv = 0; lv < nlevels; lv++) {
+    const int b = level_start_host[lv], cnt = level_start_host[lv + 1] - b;
+    null_simulate_level_kernel<<<dim3((L + 127) / 128, cnt, nrep), 128, 0, st>>>(left, right, order, b, pcdf, N, L, root, gapmask, seed, id0,
+                                                                                 first_rep, res, scratch);
+  }
   return cudaGetLastError();
 }
 
@@ -300,7 +339,14 @@ cudaError_t rsb_launch_fitch_shuffle(const int *left, const int *right, const in
 {
   (void) parent;
   if (L > 65535) return cudaErrorInvalidValue;            // per-class counters are 16 bit
-  fitch_kernel<<<dim3((L + 127) / 128, nrep), 128, 0, st>>>(left, right, N, L, msa, seed, id0, first_rep, anc);
+  for (int lv = nlevels - 1; lv >= 0; lv--) {
+    const int b = level_start_host[lv], cnt = level_start_host[lv + 1] - b;
+    fitch_up_level_kernel<<<dim3((L + 127) / 128, cnt, nrep), 128, 0, st>>>(left, right, order, b, N, L, msa, seed, id0, first_rep, anc);
+  }
+  for (int lv = 0; lv < nlevels; lv++) {
+    const int b = level_start_host[lv], cnt = level_start_host[lv + 1] - b;
+    fitch_down_level_kernel<<<dim3((L + 127) / 128, cnt, nrep), 128, 0, st>>>(left, right, order, b, N, L, seed, id0, first_rep, anc);
+  }
   permute_root_kernel<<<nrep, 256, 0, st>>>(N, L, seed, id0, first_rep, anc, shanc, perm);
   for (int lv = 0; lv < nlevels; lv++) {
     const int b = level_start_host[lv], cnt = level_start_host[lv + 1] - b;
