@@ -1,0 +1,71 @@
+"""BASELINE.json shapes at full size.  The CPU oracle needs minutes to hours there, so parity is checked through
+(a) the direct (non tensor core) verification kernel: fixed-point counts must be bit-identical to the tcgen05 kernel's,
+(b) the oracle on a slice of columns (pairs inside the slice do not depend on the other columns for counts / pp),
+(c) size-independent properties: symmetry, -inf diagonal, the APC correction recomputed in numpy from the device's raw
+    scores, histogram mass = number of pairs, determinism run to run."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = {"trna": (1000, 76), "rnasep": (5000, 400), "ssu": (10000, 1800), "lsu": (20000, 3500)}
+
+
+@pytest.mark.parametrize("name", ["trna", "rnasep", "ssu", "lsu"])
+def test_full_size_counts_and_properties(ctx, pkg, po, oracle, name):
+    N, L = SHAPES[name]
+    msa, wgt, _ = pkg.synth.synthetic_msa(N, L, seed=42)
+    ctx.configure(N, L, 2, 5)
+    ctx.set_weights(wgt)
+    res = ctx.scan(msa, pkg.GT, pkg.C16, pkg.APC, want_cov=True)
+    cov = res["cov"]
+    got = ctx.counts()
+    # (a) tensor-core counts == direct kernel counts, every cell of every pair
+    direct = ctx.counts_direct(msa)
+    assert np.array_equal(got, direct)
+    del direct
+    # (b) oracle on a column slice: counts bit-exact, pp within 1e-12
+    sl = slice(L // 3, L // 3 + min(24, L))
+    sub = np.ascontiguousarray(msa[:, sl])
+    wq, q, S = ctx.quantisation()
+    ref_cnt = np.triu(oracle.counts_fixed(sub, wq).transpose(2, 0, 1), 1)
+    assert np.array_equal(got[:, sl, sl], ref_cnt)
+    # (c) properties
+    off = ~np.eye(L, dtype=bool)
+    assert np.array_equal(cov, cov.T) or np.allclose(cov[off], cov.T[off], rtol=0, atol=0)
+    assert np.isneginf(np.diag(cov)).all() and np.isfinite(cov[off]).all()
+    assert res["mincov"] == cov[off].min() and res["maxcov"] == cov[off].max()
+    # the correction applied to the device's own raw scores, recomputed in numpy (corr_CalculateCOVCorrected :1093-1118)
+    raw = ctx.scan(msa, pkg.GT, pkg.C16, pkg.NOCORR, want_cov=True)["cov"]
+    rawz = np.where(off, raw, 0.0)
+    avg = rawz.sum() / (L * (L - 1.0))
+    covx = rawz.sum(1) / (L - 1.0)
+    want = rawz - np.outer(covx, covx) / avg
+    scale = np.abs(rawz).max()
+    assert np.max(np.abs(cov[off] - want[off])) <= 1e-9 * scale
+    del raw, rawz, want
+    # determinism: a second scan gives the same bits
+    res2 = ctx.scan(msa, pkg.GT, pkg.C16, pkg.APC, want_cov=True)
+    assert np.array_equal(res2["cov"], cov)
+    # null histogram mass
+    w, _, _ = ctx.null_width(msa)
+    ctx.hist_reset()
+    ctx.null_hist(msa[None], w, want_minmax=False)
+    bins, n, imax = ctx.hist_read(1 << 20)
+    assert n == L * (L - 1) // 2 == int(bins.sum())
+
+
+def test_ssu_slice_scores_match_oracle(ctx, pkg, po, oracle):
+    """Scores of a full-size scan cannot be compared pair by pair with an oracle run on a slice (pm and APC depend on all
+    columns), so the comparison runs the device on the same slice: N = 10000 sequences, 160 columns."""
+    N, L = 10000, 160
+    msa, wgt, _ = pkg.synth.synthetic_msa(N, 1800, seed=42)
+    sub = np.ascontiguousarray(msa[:, 400:400 + L])
+    ctx.configure(N, L, 1, 5)
+    ctx.set_weights(wgt)
+    got = ctx.scan(sub, pkg.GT, pkg.C16, pkg.APC)
+    ref = oracle.scan(sub, wgt, po.GT, po.C16, po.APC)
+    raw = oracle.scan(sub, wgt, po.GT, po.C16, po.NOCORR)
+    scale = max(abs(raw["maxcov"]), abs(raw["mincov"]), 1.0)
+    off = ~np.eye(L, dtype=bool)
+    assert np.max(np.abs(got["cov"][off] - ref["cov"][off])) <= 1e-9 * scale
