@@ -15,8 +15,8 @@
 //     permute_root_kernel msamanip_ShuffleColumns (src/msamanip.c:1164-1233).  Only the root's permuted row is
 //                         ever read (every other row is overwritten by its parent's row at msamanip.c:1645).
 //     replay_level_kernel shuffle_tree_substitutions + shuffle_tree_substitute_all (src/msamanip.c:1597-1780):
-//                         one thread per (replicate, node) of one tree level; counts the 5x5 substitutions of each
-//                         child branch on the Fitch rows, copies the shuffled parent row to the child and re-places
+//                         one thread per (replicate, branch) of one tree level; counts the 5x5 substitutions of the
+//                         branch on the Fitch rows, copies the shuffled parent row to the child and re-places
 //                         the substitutions at positions drawn uniformly without replacement among the columns
 //                         holding the source residue (one-pass selection sampling instead of the reference's
 //                         Fisher-Yates over an index list: same distribution, exact counts).
@@ -179,141 +179,118 @@ struct Pcg32 {
   }
 };
 
-// One thread per (replicate, node of this tree level): both child branches of the node are replayed by that thread.
-// Pass 1 counts the branch's 5x5 substitutions on the Fitch rows and the residue classes of the shuffled parent row;
-// pass 2 walks the shuffled parent row once and re-places the substitutions by sequential selection sampling
-// (Knuth's Algorithm S): a position currently holding class a is picked with probability k_a / m_a (substitutions out of
-// a still to place / a-positions still to come), a picked position takes target d with probability n_{a->d} / k_a.
-// Every subset of positions and every assignment of targets is equally likely, exactly as after the reference's
-// Fisher-Yates shuffle of the position list (src/msamanip.c:1718-1757), and the substitution counts are reproduced exactly.
+// One thread per (replicate, branch of this tree level).  Pass 1 counts the branch's 5x5 substitutions on the Fitch rows
+// and the residue classes of the parent row (the shuffled parent row has the same composition: the root row is a
+// permutation, and re-placing a branch's substitutions changes the composition exactly as the branch did); pass 2 walks
+// the shuffled parent row once and re-places the substitutions by sequential selection sampling (Knuth's Algorithm S):
+// a position currently holding class a is picked with probability k_a / m_a (substitutions out of a still to place /
+// a-positions still to come), a picked position takes target d with probability n_{a->d} / k_a.  Every subset of positions
+// and every assignment of targets is equally likely, exactly as after the reference's Fisher-Yates shuffle of the
+// position list (src/msamanip.c:1718-1757), and the substitution counts are reproduced exactly.
+// The per-class counters live in registers (selected by predication): a thread is alone on its rows, so the length of
+// the dependent instruction chain per position is what bounds a tree level's latency.
 // WORD: rows are read and written as 32-bit words (L % 4 == 0), otherwise byte by byte.
+#define RP_SEL5(c, v0, v1, v2, v3, v4) ((c) == 0 ? (v0) : (c) == 1 ? (v1) : (c) == 2 ? (v2) : (c) == 3 ? (v3) : (v4))
+
 template <bool WORD>
 __global__ void __launch_bounds__(RP_THREADS)
 replay_level_kernel(const int *__restrict__ left, const int *__restrict__ right, const int *__restrict__ order, int lvl_begin, int lvl_count,
                     int N, int L, const uint8_t *__restrict__ msa, unsigned long long seed, unsigned long long id0, int first_rep, int nrep,
                     const uint8_t *__restrict__ ancbuf, uint8_t *__restrict__ shancbuf, uint8_t *__restrict__ res)
 {
-  __shared__ unsigned short nsub[25][RP_THREADS];     // substitutions a -> d still to place
-  __shared__ unsigned short mcls[5][RP_THREADS];      // class counts of the shuffled parent row
-  __shared__ unsigned short mrem[5][RP_THREADS];      // a-positions still to come
-  __shared__ unsigned short krem[5][RP_THREADS];      // substitutions out of a still to place
+  __shared__ unsigned short nsub[25][RP_THREADS];     // substitutions a -> d still to place (touched on differences / picks only)
   const int t = threadIdx.x;
   const int L4 = L / 4;
   const long long task = (long long) blockIdx.x * RP_THREADS + t;
-  if (task >= (long long) lvl_count * nrep) return;
-  const int rr = (int) (task / lvl_count);
+  if (task >= 2LL * lvl_count * nrep) return;
+  const int side = (int) (task & 1);
+  const long long nt = task >> 1;
+  const int rr = (int) (nt / lvl_count);
   const int r = first_rep + rr;
   const uint32_t rid = (uint32_t) (id0 + (unsigned long long) rr);
-  const int v = order[lvl_begin + (int) (task % lvl_count)];
+  const int v = order[lvl_begin + (int) (nt % lvl_count)];
   const uint8_t *anc = ancbuf + (size_t) r * (N - 1) * L;
   uint8_t *shanc = shancbuf + (size_t) r * (N - 1) * L;
   uint8_t *leaves = res + (size_t) r * N * L;
   const uint8_t *par_o = anc + (size_t) v * L;
   const uint8_t *par_s = shanc + (size_t) v * L;
+  const int ch = side ? right[v] : left[v];
+  const uint8_t *kid_o = (ch > 0) ? anc + (size_t) ch * L : msa + (size_t) (-ch) * L;
+  uint8_t *kid_s = (ch > 0) ? shanc + (size_t) ch * L : leaves + (size_t) (-ch) * L;
 
   Philox ph; ph.key[0] = (uint32_t) seed ^ (0xC2B2AE35u * (rid + 1u)); ph.key[1] = (uint32_t) (seed >> 32) ^ 0x5bd1e995u;
-  uint32_t sd[4]; ph.block((uint32_t) v, 0x7ee1u, 0u, 0u, sd);
+  uint32_t sd[4]; ph.block((uint32_t) v, 0x7ee1u + (uint32_t) side, 0u, 0u, sd);
   Pcg32 rng; rng.state = ((unsigned long long) sd[0] << 32) | sd[1]; rng.inc = ((((unsigned long long) sd[2] << 32) | sd[3]) << 1) | 1ULL;
   rng.next();
 
   #pragma unroll
-  for (int a = 0; a < 5; a++) mcls[a][t] = 0;
+  for (int k = 0; k < 25; k++) nsub[k][t] = 0;
+  int m0 = 0, m1 = 0, m2 = 0, m3 = 0, m4 = 0;
+
+  // pass 1: composition of the parent row; substitutions of this branch on the Fitch rows (msamanip.c:1634-1643)
+  auto count1 = [&](int pa, int kd) {
+    m0 += (pa == 0); m1 += (pa == 1); m2 += (pa == 2); m3 += (pa == 3); m4 += (pa == 4);
+    if (pa != kd && pa <= 4 && kd <= 4) nsub[pa * 5 + kd][t]++;
+  };
   if (WORD) {
-    // rows are walked in batches of RP_BATCH words whose loads are issued together: the thread is alone on its rows, so
-    // memory latency can only be hidden by its own loads in flight
-    const uint32_t *ps4 = reinterpret_cast<const uint32_t *>(par_s);
-    for (int c4 = 0; c4 < L4; c4 += RP_BATCH) {
-      uint32_t wb[RP_BATCH];
+    const uint32_t *po4 = reinterpret_cast<const uint32_t *>(par_o), *ko4 = reinterpret_cast<const uint32_t *>(kid_o);
+    for (int c4 = 0; c4 < L4; c4 += RP_BATCH) {          // loads of a batch are issued together (latency hiding within the thread)
+      uint32_t wp[RP_BATCH], wk[RP_BATCH];
       #pragma unroll
-      for (int u = 0; u < RP_BATCH; u++) wb[u] = (c4 + u < L4) ? __ldcg(ps4 + c4 + u) : 0x05050505u;
+      for (int u = 0; u < RP_BATCH; u++) { const bool in = c4 + u < L4; wp[u] = in ? __ldcg(po4 + c4 + u) : 0x05050505u; wk[u] = in ? __ldcg(ko4 + c4 + u) : 0x05050505u; }
       #pragma unroll
       for (int u = 0; u < RP_BATCH; u++)
         #pragma unroll
-        for (int q = 0; q < 4; q++) { const int x = (wb[u] >> (8 * q)) & 0xff; if (x < 5) mcls[x][t]++; }
+        for (int q = 0; q < 4; q++) count1((wp[u] >> (8 * q)) & 0xff, (wk[u] >> (8 * q)) & 0xff);
     }
   } else {
-    for (int c = 0; c < L; c++) { const int x = par_s[c]; if (x < 5) mcls[x][t]++; }
+    for (int c = 0; c < L; c++) count1(par_o[c], kid_o[c]);
   }
+  int k0 = 0, k1 = 0, k2 = 0, k3 = 0, k4 = 0;
+  #pragma unroll
+  for (int d = 0; d < 5; d++) { k0 += nsub[d][t]; k1 += nsub[5 + d][t]; k2 += nsub[10 + d][t]; k3 += nsub[15 + d][t]; k4 += nsub[20 + d][t]; }
+  int ktot = k0 + k1 + k2 + k3 + k4;
 
-  for (int side = 0; side < 2; side++) {
-    const int ch = side ? right[v] : left[v];
-    const uint8_t *kid_o = (ch > 0) ? anc + (size_t) ch * L : msa + (size_t) (-ch) * L;
-    uint8_t *kid_s = (ch > 0) ? shanc + (size_t) ch * L : leaves + (size_t) (-ch) * L;
-    #pragma unroll
-    for (int k = 0; k < 25; k++) nsub[k][t] = 0;
-    // pass 1: substitutions of this branch on the Fitch rows (msamanip.c:1634-1643)
-    if (WORD) {
-      const uint32_t *po4 = reinterpret_cast<const uint32_t *>(par_o), *ko4 = reinterpret_cast<const uint32_t *>(kid_o);
-      for (int c4 = 0; c4 < L4; c4 += RP_BATCH) {
-        uint32_t wp[RP_BATCH], wk[RP_BATCH];
-        #pragma unroll
-        for (int u = 0; u < RP_BATCH; u++) { const bool in = c4 + u < L4; wp[u] = in ? __ldcg(po4 + c4 + u) : 0u; wk[u] = in ? __ldcg(ko4 + c4 + u) : 0u; }
-        #pragma unroll
-        for (int u = 0; u < RP_BATCH; u++) {
-          if (wp[u] == wk[u]) continue;
-          #pragma unroll
-          for (int q = 0; q < 4; q++) {
-            const int pa = (wp[u] >> (8 * q)) & 0xff, kd = (wk[u] >> (8 * q)) & 0xff;
-            if (pa != kd && pa <= 4 && kd <= 4) nsub[pa * 5 + kd][t]++;
-          }
-        }
-      }
-    } else {
-      for (int c = 0; c < L; c++) {
-        const int pa = par_o[c], kd = kid_o[c];
-        if (pa != kd && pa <= 4 && kd <= 4) nsub[pa * 5 + kd][t]++;
-      }
+  // pass 2: copy the shuffled parent row (:1645) and re-place the substitutions
+  auto place = [&](int cls) -> int {
+    if (cls > 4) return cls;
+    const int k = RP_SEL5(cls, k0, k1, k2, k3, k4);
+    const int m = RP_SEL5(cls, m0, m1, m2, m3, m4);
+    int out = cls;
+    if (k > 0 && (int) __umulhi(rng.next(), (uint32_t) (m > 0 ? m : 1)) < k) {
+      int pick = (int) __umulhi(rng.next(), (uint32_t) k);
+      int d = 0;
+      for (; d < 4; d++) { const int n = nsub[cls * 5 + d][t]; if (pick < n) break; pick -= n; }
+      nsub[cls * 5 + d][t]--;
+      k0 -= (cls == 0); k1 -= (cls == 1); k2 -= (cls == 2); k3 -= (cls == 3); k4 -= (cls == 4);
+      ktot--;
+      out = d;
     }
-    int ktot = 0;
-    #pragma unroll
-    for (int a = 0; a < 5; a++) {
-      int k = 0;
+    m0 -= (cls == 0); m1 -= (cls == 1); m2 -= (cls == 2); m3 -= (cls == 3); m4 -= (cls == 4);
+    return out;
+  };
+  if (WORD) {
+    const uint32_t *ps4 = reinterpret_cast<const uint32_t *>(par_s);
+    uint32_t *ks4 = reinterpret_cast<uint32_t *>(kid_s);
+    for (int c4 = 0; c4 < L4; c4 += RP_BATCH) {
+      uint32_t wb[RP_BATCH];
       #pragma unroll
-      for (int d = 0; d < 5; d++) k += nsub[a * 5 + d][t];
-      krem[a][t] = (unsigned short) k; mrem[a][t] = mcls[a][t]; ktot += k;
-    }
-    // pass 2: copy the shuffled parent row (:1645) and re-place the substitutions
-    auto place = [&](int cls) -> int {
-      int out = cls;
-      if (cls > 4) return out;
-      const int k = krem[cls][t], m = mrem[cls][t];
-      if (k > 0) {
-        if ((int) (((unsigned long long) rng.next() * (unsigned) m) >> 32) < k) {
-          int pick = (int) (((unsigned long long) rng.next() * (unsigned) k) >> 32);
-          int d = 0;
-          for (; d < 4; d++) { const int n = nsub[cls * 5 + d][t]; if (pick < n) break; pick -= n; }
-          nsub[cls * 5 + d][t]--;
-          krem[cls][t] = (unsigned short) (k - 1);
-          ktot--;
-          out = d;
+      for (int u = 0; u < RP_BATCH; u++) wb[u] = (c4 + u < L4) ? __ldcg(ps4 + c4 + u) : 0u;
+      #pragma unroll
+      for (int u = 0; u < RP_BATCH; u++) {
+        if (c4 + u >= L4) break;
+        uint32_t w = wb[u];
+        if (ktot > 0) {
+          uint32_t o = 0;
+          #pragma unroll
+          for (int q = 0; q < 4; q++) o |= (uint32_t) place((w >> (8 * q)) & 0xff) << (8 * q);
+          w = o;
         }
+        ks4[c4 + u] = w;
       }
-      mrem[cls][t] = (unsigned short) (m - 1);
-      return out;
-    };
-    if (WORD) {
-      const uint32_t *ps4 = reinterpret_cast<const uint32_t *>(par_s);
-      uint32_t *ks4 = reinterpret_cast<uint32_t *>(kid_s);
-      for (int c4 = 0; c4 < L4; c4 += RP_BATCH) {
-        uint32_t wb[RP_BATCH];
-        #pragma unroll
-        for (int u = 0; u < RP_BATCH; u++) wb[u] = (c4 + u < L4) ? __ldcg(ps4 + c4 + u) : 0u;
-        #pragma unroll
-        for (int u = 0; u < RP_BATCH; u++) {
-          if (c4 + u >= L4) break;
-          uint32_t w = wb[u];
-          if (ktot > 0) {
-            uint32_t o = 0;
-            #pragma unroll
-            for (int q = 0; q < 4; q++) o |= (uint32_t) place((w >> (8 * q)) & 0xff) << (8 * q);
-            w = o;
-          }
-          ks4[c4 + u] = w;
-        }
-      }
-    } else {
-      for (int c = 0; c < L; c++) { const int cls = par_s[c]; kid_s[c] = (uint8_t) (ktot > 0 ? place(cls) : cls); }
     }
+  } else {
+    for (int c = 0; c < L; c++) { const int cls = par_s[c]; kid_s[c] = (uint8_t) (ktot > 0 ? place(cls) : cls); }
   }
 }
 
@@ -350,7 +327,7 @@ cudaError_t rsb_launch_fitch_shuffle(const int *left, const int *right, const in
   permute_root_kernel<<<nrep, 256, 0, st>>>(N, L, seed, id0, first_rep, anc, shanc, perm);
   for (int lv = 0; lv < nlevels; lv++) {
     const int b = level_start_host[lv], cnt = level_start_host[lv + 1] - b;
-    const long long tasks = (long long) cnt * nrep;
+    const long long tasks = 2LL * cnt * nrep;                    // one thread per (replicate, branch)
     const unsigned grid = (unsigned) ((tasks + RP_THREADS - 1) / RP_THREADS);
     if (L % 4 == 0) replay_level_kernel<true><<<grid, RP_THREADS, 0, st>>>(left, right, order, b, cnt, N, L, msa, seed, id0, first_rep, nrep, anc, shanc, res);
     else            replay_level_kernel<false><<<grid, RP_THREADS, 0, st>>>(left, right, order, b, cnt, N, L, msa, seed, id0, first_rep, nrep, anc, shanc, res);
