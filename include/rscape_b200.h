@@ -76,10 +76,30 @@ int rsb_scan(rsb_ctx *ctx, const uint8_t *msa, int64_t row_stride, int on_device
              int stat, int covclass, int actype, const double *allowpair, double tol,
              double *cov, double *mincov, double *maxcov,
              double *pp, double *pm, double *ps, double *nseff, double *ngap);
+/* The score histograms of that scan, cov_SignificantPairs_Ranking (src/covariation.c:415-457): ha[b] counts every pair
+ * i<j in bin b = ceil((max(x, bmin+w) - bmin)/w - 1), b < nb; with pairmask (uint8 [L][L], nonzero = pair belongs to the
+ * structure set chosen by data->samplesize: contacts / base pairs / WC pairs) hb gets the flagged pairs and ht the others. */
+int rsb_scan_hist(rsb_ctx *ctx, const uint8_t *pairmask, double w, double bmin, int nb, uint64_t *ha, uint64_t *hb, uint64_t *ht);
 /* fixed-point counts of the last rsb_probs/rsb_scan: int64 [16][L][L], upper triangle (parity tests) */
 int rsb_get_counts(rsb_ctx *ctx, int64_t *counts);
 /* the same counts recomputed by the direct verification kernel (no tensor cores); tests only */
 int rsb_get_counts_direct(rsb_ctx *ctx, const uint8_t *msa, int64_t row_stride, int64_t *counts);
+
+/* ---- the pair grid of ONE scan sharded over ranks (LSU-scale L) -----------------------------------------
+ * Rank `rank` of `world` owns the 32-column row blocks ib with ib % world == rank and computes counts, statistic, correction
+ * and histogram for the pairs (i,j), i<j, whose row i it owns.  The operand planes are replicated, so the contraction needs
+ * no exchange; what all pairs feed -- the marginal sums, the APC row sums -- leaves each phase as a small host vector that
+ * the caller sums over ranks (one all-reduce each) before the next phase:
+ *     rsb_set_shard; rsb_set_weights;
+ *     rsb_sharded_counts    -> marg_sums[L][4]   (all-reduce SUM)      corr_Probs      src/correlators.c:1424
+ *     rsb_sharded_statistic -> cov_sums[L+4]     (SUM on [0..L], MIN on [L+1], MAX on [L+2])   corr_Calculate* :50-874
+ *     rsb_sharded_correct   -> corrected scores of the owned rows (0 elsewhere: SUM assembles the upper triangle), local
+ *                              min/max, histogram (rsb_hist_read + all-reduce SUM)   corr_CalculateCOVCorrected :1064
+ * mode of rsb_sharded_correct: bit 0 = write the corrected scores (needed for cov), bit 1 = add them to the histogram. */
+int rsb_set_shard(rsb_ctx *ctx, int rank, int world);
+int rsb_sharded_counts(rsb_ctx *ctx, const uint8_t *msa, int64_t row_stride, int on_device, double tol, double *marg_sums);
+int rsb_sharded_statistic(rsb_ctx *ctx, const double *marg_sums, double tol, int stat, int covclass, const double *allowpair, double *cov_sums);
+int rsb_sharded_correct(rsb_ctx *ctx, const double *cov_sums, int actype, int mode, double w, double bmin, double *cov, double *minmax);
 
 /* ---- null alignments: the loop body of null_rscape (src/R-scape.c:1650-1697) ------------------- */
 /* calculate_width_histo (src/R-scape.c:1281-1371): scan one null, w = min(w_old, (max - max(bmin,min))/hpts). */

@@ -60,6 +60,11 @@ def lib():
         L.rsb_correct_host.argtypes = [_vp, C.c_int, _dp, _dp, _dp]
         L.rsb_scan.argtypes = [_vp, _vp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.c_double,
                                _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp]
+        L.rsb_scan_hist.argtypes = [_vp, _u8p, C.c_double, C.c_double, C.c_int, _u64p, _u64p, _u64p]
+        L.rsb_set_shard.argtypes = [_vp, C.c_int, C.c_int]
+        L.rsb_sharded_counts.argtypes = [_vp, _vp, C.c_int64, C.c_int, C.c_double, _dp]
+        L.rsb_sharded_statistic.argtypes = [_vp, _dp, C.c_double, C.c_int, C.c_int, _dp, _dp]
+        L.rsb_sharded_correct.argtypes = [_vp, _dp, C.c_int, C.c_int, C.c_double, C.c_double, _dp, _dp]
         L.rsb_get_counts.argtypes = [_vp, _i64p]
         L.rsb_get_counts_direct.argtypes = [_vp, _vp, C.c_int64, _i64p]
         L.rsb_null_width.argtypes = [_vp, _vp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.c_double,
@@ -156,6 +161,42 @@ class Context:
                                 _d(out["pp"]), _d(out["pm"]), _d(out["ps"]), _d(out["nseff"]), _d(out["ngap"])))
         out.update(mincov=mn.value, maxcov=mx.value)
         return out
+
+    def scan_hist(self, w, bmin, nb, pairmask=None):
+        """ha / hb / ht of the last scan (cov_SignificantPairs_Ranking, src/covariation.c:415-457)."""
+        ha = np.zeros(nb, np.uint64)
+        hb = np.zeros(nb, np.uint64) if pairmask is not None else None
+        ht = np.zeros(nb, np.uint64) if pairmask is not None else None
+        pm = None if pairmask is None else np.ascontiguousarray(pairmask, dtype=np.uint8)
+        up = lambda a: None if a is None else a.ctypes.data_as(_u64p)
+        self._ck(lib().rsb_scan_hist(self._h, None if pm is None else pm.ctypes.data_as(_u8p), w, bmin, nb, up(ha), up(hb), up(ht)))
+        return ha, hb, ht
+
+    # ---- one scan with the pair grid sharded over ranks ------------------------------------------
+    def set_shard(self, rank, world):
+        self._ck(lib().rsb_set_shard(self._h, rank, world))
+
+    def sharded_counts(self, msa, tol=1e-6):
+        msa = self._msa(msa)
+        p, dev = _ptr(msa)
+        sums = np.empty((self.L, 4))
+        self._ck(lib().rsb_sharded_counts(self._h, p, self.L, dev, tol, _d(sums)))
+        return sums
+
+    def sharded_statistic(self, marg_sums, stat=GT, covclass=C16, allowpair=None, tol=1e-6):
+        ap = None if allowpair is None else np.ascontiguousarray(allowpair, dtype=np.float64)
+        ms = np.ascontiguousarray(marg_sums, dtype=np.float64)
+        out = np.empty(self.L + 4)
+        self._ck(lib().rsb_sharded_statistic(self._h, _d(ms), tol, stat, covclass, _d(ap), _d(out)))
+        return out
+
+    def sharded_correct(self, cov_sums, actype=APC, want_cov=True, hist_w=None, bmin=-10.0):
+        cs = np.ascontiguousarray(cov_sums, dtype=np.float64)
+        cov = np.empty((self.L, self.L)) if want_cov else None
+        mm = np.empty(2)
+        mode = (1 if want_cov else 0) | (2 if hist_w is not None else 0)
+        self._ck(lib().rsb_sharded_correct(self._h, _d(cs), actype, mode, 0.0 if hist_w is None else hist_w, bmin, _d(cov), _d(mm)))
+        return cov, mm[0], mm[1]
 
     def counts(self):
         out = np.empty((16, self.L, self.L), dtype=np.int64)

@@ -22,9 +22,10 @@ cudaError_t rsb_launch_colsum(const uint8_t *res, int N, int L, const unsigned l
 cudaError_t rsb_launch_counts_direct(const uint8_t *res, int N, int L, int Lp, const unsigned long long *wq, long long *cnt, cudaStream_t st);
 void        rsb_stat_grid(int L, int *nJT, int *nIT);
 cudaError_t rsb_launch_marginals(const long long *cnt, int nrep, int L, int Lp, double scale, long long wtot, double tol,
-                                 double *rowpart, double *colpart, double *nseff, double *pm, int *flags, cudaStream_t st);
+                                 double *rowpart, double *colpart, double *nseff, double *msum, double *pm, int *flags,
+                                 int sr, int sw, int phase, cudaStream_t st);
 cudaError_t rsb_launch_statistic(int stat, int cls, const long long *cnt, const double *pm, int nrep, int L, int Lp, double scale,
-                                 long long wtot, unsigned mask, double *cov, double *rowpart, double *colpart, double *mm, cudaStream_t st);
+                                 long long wtot, unsigned mask, double *cov, double *rowpart, double *colpart, double *mm, int sr, int sw, cudaStream_t st);
 cudaError_t rsb_launch_raf(const long long *cnt, int nrep, int L, int Lp, int nseq, unsigned mask, int smooth, double *tmp, double *cov,
                            double *rowpart, double *colpart, double *mm, cudaStream_t st);
 cudaError_t rsb_launch_ccf(const double *nseff, const double *pm, int nrep, int L, int Lp, double *part, double *meanp, double *cov,
@@ -34,12 +35,14 @@ cudaError_t rsb_launch_export_probs(const long long *cnt, int L, int Lp, double 
                                     double *ngap, cudaStream_t st);
 cudaError_t rsb_launch_ps(const unsigned long long *colsum, int L, double scale, double *ps, cudaStream_t st);
 cudaError_t rsb_launch_correct_final(const double *rowpart, const double *colpart, const double *mm, int nrep, int L,
-                                     double *covx, double *scal, double *blocksum, cudaStream_t st);
+                                     double *covx, double *scal, double *blocksum, double *covsum, int phase, cudaStream_t st);
 cudaError_t rsb_launch_correct_hist(double *cov, const double *covx, const double *scal, int nrep, int L, int Lp, int actype, int mode,
                                     double bmin, const double *wptr, unsigned long long *hist, int nbins, double *mm, double *minmax_out,
-                                    int *flags, cudaStream_t st);
+                                    int *flags, int sr, int sw, cudaStream_t st);
 cudaError_t rsb_launch_width(const double *minmax, double w_old, double bmin, int hpts, double tol, double *wout, cudaStream_t st);
 cudaError_t rsb_launch_symmetrize(double *cov, int L, int Lp, cudaStream_t st);
+cudaError_t rsb_launch_hist3(const double *cov, int L, int Lp, const uint8_t *pairmask, double bmin, double w, int nb,
+                             unsigned long long *ha, unsigned long long *hb, unsigned long long *ht, int *flags, cudaStream_t st);
 cudaError_t rsb_launch_null_simulate(const int *left, const int *right, const int *order, const int *level_start_host, int nlevels,
                                      const double *pcdf, int N, int L, const uint8_t *root,
                                      const uint8_t *gapmask, long long gap_stride, unsigned long long seed, unsigned long long id0, int first_rep, int nrep,
@@ -83,7 +86,8 @@ struct rsb_ctx {
   long long *d_cnt = nullptr;
   double *d_nseff = nullptr, *d_pm = nullptr, *d_cov = nullptr, *d_tmp = nullptr;
   double *d_rowpart = nullptr, *d_colpart = nullptr, *d_mm = nullptr, *d_scal = nullptr, *d_covx = nullptr, *d_minmax = nullptr;
-  double *d_meanp = nullptr, *d_w = nullptr, *d_blocksum = nullptr;
+  double *d_meanp = nullptr, *d_w = nullptr, *d_blocksum = nullptr, *d_msum = nullptr, *d_covsum = nullptr;
+  int shard_rank = 0, shard_world = 1;  // row-block sharding of the pair grid across ranks
   cudaStream_t stream_aux = nullptr, stream_copy = nullptr;     // statistics / uploads of the pipelined null loop
   cudaEvent_t ev_entry = nullptr, ev_up[2] = { nullptr, nullptr }, ev_counts[2] = { nullptr, nullptr }, ev_stats[2] = { nullptr, nullptr };
   unsigned long long *d_hist = nullptr, *d_colsum = nullptr;
@@ -160,7 +164,7 @@ void free_plan(rsb_ctx *c)
   free_geo(c->geo[0]); free_geo(c->geo[1]);
   dfree(c->d_res); dfree(c->d_planeA); dfree(c->d_planeB); dfree(c->d_cnt); dfree(c->d_nseff); dfree(c->d_pm); dfree(c->d_cov);
   dfree(c->d_tmp); dfree(c->d_rowpart); dfree(c->d_colpart); dfree(c->d_mm); dfree(c->d_scal); dfree(c->d_covx); dfree(c->d_minmax);
-  dfree(c->d_meanp); dfree(c->d_w); dfree(c->d_blocksum); dfree(c->d_hist); dfree(c->d_colsum); dfree(c->d_flags); dfree(c->d_ps); dfree(c->d_pp_out);
+  dfree(c->d_meanp); dfree(c->d_w); dfree(c->d_blocksum); dfree(c->d_msum); dfree(c->d_covsum); dfree(c->d_hist); dfree(c->d_colsum); dfree(c->d_flags); dfree(c->d_ps); dfree(c->d_pp_out);
   dfree(c->d_nseff_out); dfree(c->d_ngap_out); dfree(c->d_left); dfree(c->d_right); dfree(c->d_parent); dfree(c->d_order);
   dfree(c->d_level_start); dfree(c->d_perm); dfree(c->d_pcdf); dfree(c->d_root); dfree(c->d_gapmask); dfree(c->d_simscratch);
   dfree(c->d_msa0); dfree(c->d_anc); dfree(c->d_shanc); dfree(c->d_pool);
@@ -181,7 +185,7 @@ int build_geo(rsb_ctx *ctx, Geo &g, int S)
   for (int jb = 0; jb < g.nJB; jb++) {
     const int maxj = std::min(jb * g.CJ + g.CJ - 1, ctx->L - 1);
     for (int ib = 0; ib < ctx->nIB; ib++)
-      if (ib * RSB_ICOLS < maxj) tiles.push_back(make_int2(ib, jb));
+      if (ib * RSB_ICOLS < maxj && (ctx->shard_world <= 1 || ib % ctx->shard_world == ctx->shard_rank)) tiles.push_back(make_int2(ib, jb));
   }
   g.ntiles = (int) tiles.size();
   dfree(g.d_tiles);
@@ -344,7 +348,7 @@ int resolve_stat(rsb_ctx *ctx, int stat, int covclass)
 
 // per-slot views of the replicate-indexed buffers
 struct SlotPtrs {
-  long long *cnt; double *nseff, *pm, *cov, *tmp, *scal, *covx, *minmax, *meanp, *blocksum, *mm;
+  long long *cnt; double *nseff, *pm, *cov, *tmp, *scal, *covx, *minmax, *meanp, *blocksum, *mm, *msum, *covsum;
 };
 SlotPtrs slot_ptrs(rsb_ctx *c, int s0)
 {
@@ -362,41 +366,50 @@ SlotPtrs slot_ptrs(rsb_ctx *c, int s0)
   p.meanp = c->d_meanp + (size_t) s0 * 4;
   p.blocksum = c->d_blocksum + (size_t) s0 * ((L + 127) / 128);
   p.mm = c->d_mm + (size_t) s0 * nJT * nIT * 2;
+  p.msum = c->d_msum + (size_t) s0 * L * 4;
+  p.covsum = c->d_covsum + (size_t) s0 * (L + 4);
   return p;
 }
 
-// marginals (corr_Marginals) for slots [s0, s0+nrep) on stream st
-int enqueue_marginals(rsb_ctx *ctx, int s0, int nrep, double tol, cudaStream_t st)
+// marginals (corr_Marginals) for slots [s0, s0+nrep) on stream st.  phase 1 = partial sums -> msum, 2 = normalise, 3 = both
+int enqueue_marginals(rsb_ctx *ctx, int s0, int nrep, double tol, cudaStream_t st, int phase = 3)
 {
   Geo &g = ctx->geo[0];
   int nJT, nIT; rsb_stat_grid(ctx->L, &nJT, &nIT);
   SlotPtrs p = slot_ptrs(ctx, s0);
   RSB_CUDA_OK(rsb_launch_marginals(p.cnt, nrep, ctx->L, ctx->Lp, g.scale, g.wtot, tol, ctx->d_rowpart + (size_t) s0 * nJT * ctx->L * 4,
-                                   ctx->d_colpart + (size_t) s0 * nIT * ctx->L * 4, p.nseff, p.pm, ctx->d_flags, st));
-  ctx->launches += 2;
+                                   ctx->d_colpart + (size_t) s0 * nIT * ctx->L * 4, p.nseff, p.msum, p.pm, ctx->d_flags,
+                                   ctx->shard_rank, ctx->shard_world, phase, st));
+  ctx->launches += (phase == 3) ? 3 : (phase == 1 ? 2 : 1);
   return 0;
 }
 
-// statistic on the counts of slots [s0, s0+nrep); leaves raw cov, COVx, COVavg and the raw min/max
-int enqueue_statistic(rsb_ctx *ctx, int s0, int nrep, int stat, int covclass, unsigned mask, cudaStream_t st)
+// statistic on the counts of slots [s0, s0+nrep); leaves raw cov and (phase bit 1) the reduced sums covsum, (phase bit 2)
+// COVx, COVavg and the raw min/max
+int enqueue_statistic(rsb_ctx *ctx, int s0, int nrep, int stat, int covclass, unsigned mask, cudaStream_t st, int phase = 3)
 {
   Geo &g = ctx->geo[ctx->cur_geo];
   int nJT, nIT; rsb_stat_grid(ctx->L, &nJT, &nIT);
   SlotPtrs p = slot_ptrs(ctx, s0);
   double *rowpart = ctx->d_rowpart + (size_t) s0 * nJT * ctx->L, *colpart = ctx->d_colpart + (size_t) s0 * nIT * ctx->L;
-  if (stat == RSB_RAF || stat == RSB_RAFS) {
-    if (ctx->cur_geo != 1) { rsb_set_error(ctx, "internal: RAF needs unit-weight counts"); return 1; }
-    RSB_CUDA_OK(rsb_launch_raf(p.cnt, nrep, ctx->L, ctx->Lp, ctx->N, mask, stat == RSB_RAFS, p.tmp, p.cov, rowpart, colpart, p.mm, st));
-    ctx->launches += (stat == RSB_RAFS) ? 3 : 2;
-  } else if (stat == RSB_CCF) {
-    RSB_CUDA_OK(rsb_launch_ccf(p.nseff, p.pm, nrep, ctx->L, ctx->Lp, p.tmp, p.meanp, p.cov, rowpart, colpart, p.mm, st));
-    ctx->launches += 4;
-  } else {
-    RSB_CUDA_OK(rsb_launch_statistic(stat, covclass, p.cnt, p.pm, nrep, ctx->L, ctx->Lp, g.scale, g.wtot, mask, p.cov, rowpart, colpart, p.mm, st));
-    ctx->launches++;
+  if (phase & 1) {
+    if (stat == RSB_RAF || stat == RSB_RAFS) {
+      if (ctx->cur_geo != 1) { rsb_set_error(ctx, "internal: RAF needs unit-weight counts"); return 1; }
+      if (ctx->shard_world > 1) { rsb_set_error(ctx, "RAF/RAFS are not available with a sharded pair grid"); return 1; }
+      RSB_CUDA_OK(rsb_launch_raf(p.cnt, nrep, ctx->L, ctx->Lp, ctx->N, mask, stat == RSB_RAFS, p.tmp, p.cov, rowpart, colpart, p.mm, st));
+      ctx->launches += (stat == RSB_RAFS) ? 3 : 2;
+    } else if (stat == RSB_CCF) {
+      if (ctx->shard_world > 1) { rsb_set_error(ctx, "CCF is not available with a sharded pair grid"); return 1; }
+      RSB_CUDA_OK(rsb_launch_ccf(p.nseff, p.pm, nrep, ctx->L, ctx->Lp, p.tmp, p.meanp, p.cov, rowpart, colpart, p.mm, st));
+      ctx->launches += 4;
+    } else {
+      RSB_CUDA_OK(rsb_launch_statistic(stat, covclass, p.cnt, p.pm, nrep, ctx->L, ctx->Lp, g.scale, g.wtot, mask, p.cov, rowpart, colpart, p.mm,
+                                       ctx->shard_rank, ctx->shard_world, st));
+      ctx->launches++;
+    }
   }
-  RSB_CUDA_OK(rsb_launch_correct_final(rowpart, colpart, p.mm, nrep, ctx->L, p.covx, p.scal, p.blocksum, st));
-  ctx->launches += 2;
+  RSB_CUDA_OK(rsb_launch_correct_final(rowpart, colpart, p.mm, nrep, ctx->L, p.covx, p.scal, p.blocksum, p.covsum, phase, st));
+  ctx->launches += (phase == 3) ? 3 : (phase == 1 ? 2 : 1);
   return 0;
 }
 
@@ -405,7 +418,7 @@ int enqueue_correct(rsb_ctx *ctx, int s0, int nrep, int actype, int mode, double
 {
   SlotPtrs p = slot_ptrs(ctx, s0);
   RSB_CUDA_OK(rsb_launch_correct_hist(p.cov, p.covx, p.scal, nrep, ctx->L, ctx->Lp, actype, mode, bmin, ctx->d_w, ctx->d_hist, HIST_BINS,
-                                      p.mm, p.minmax, ctx->d_flags, st));
+                                      p.mm, p.minmax, ctx->d_flags, ctx->shard_rank, ctx->shard_world, st));
   ctx->launches += 2;
   return 0;
 }
@@ -531,6 +544,8 @@ int rsb_configure(rsb_ctx *ctx, int nseq, int alen, int max_replicates, int nsli
   RSB_CUDA_OK(cudaMalloc(&ctx->d_minmax, R * 2 * sizeof(double)));
   RSB_CUDA_OK(cudaMalloc(&ctx->d_meanp, R * 4 * sizeof(double)));
   RSB_CUDA_OK(cudaMalloc(&ctx->d_blocksum, R * ((L + 127) / 128) * sizeof(double)));
+  RSB_CUDA_OK(cudaMalloc(&ctx->d_msum, R * L * 4 * sizeof(double)));
+  RSB_CUDA_OK(cudaMalloc(&ctx->d_covsum, R * (L + 4) * sizeof(double)));
   RSB_CUDA_OK(cudaMalloc(&ctx->d_w, sizeof(double)));
   RSB_CUDA_OK(cudaMalloc(&ctx->d_hist, sizeof(unsigned long long) * HIST_BINS));
   RSB_CUDA_OK(cudaMalloc(&ctx->d_colsum, L * 5 * sizeof(unsigned long long)));
@@ -624,8 +639,8 @@ int rsb_correct_host(rsb_ctx *ctx, int actype, double *cov, double *mincov, doub
   RSB_CUDA_OK(cudaMemcpy2DAsync(ctx->d_cov, sizeof(double) * ctx->Lp, cov, sizeof(double) * ctx->L, sizeof(double) * ctx->L, ctx->L,
                                 cudaMemcpyHostToDevice, ctx->stream));
   RSB_CUDA_OK(rsb_launch_reduce_cov(ctx->d_cov, 1, ctx->L, ctx->Lp, ctx->d_rowpart, ctx->d_colpart, ctx->d_mm, ctx->stream));
-  RSB_CUDA_OK(rsb_launch_correct_final(ctx->d_rowpart, ctx->d_colpart, ctx->d_mm, 1, ctx->L, ctx->d_covx, ctx->d_scal, ctx->d_blocksum, ctx->stream));
-  ctx->launches += 3;
+  RSB_CUDA_OK(rsb_launch_correct_final(ctx->d_rowpart, ctx->d_colpart, ctx->d_mm, 1, ctx->L, ctx->d_covx, ctx->d_scal, ctx->d_blocksum, ctx->d_covsum, 3, ctx->stream));
+  ctx->launches += 4;
   return rsb_correct(ctx, actype, cov, mincov, maxcov);
 }
 
@@ -824,6 +839,86 @@ int rsb_null_width_pool(rsb_ctx *ctx, int rep, int stat, int covclass, int actyp
   if (pool_range_ok(ctx, rep, 1)) return 1;
   return rsb_null_width(ctx, ctx->d_pool + (size_t) rep * ctx->N * ctx->L, ctx->L, 1, stat, covclass, actype, allowpair, tol,
                         w_old, bmin, hpts, w_out, mincov, maxcov);
+}
+
+// ---------------------------------------------------------------------------------------------- sharded pair grid
+int rsb_set_shard(rsb_ctx *ctx, int rank, int world)
+{
+  if (world < 1 || rank < 0 || rank >= world) { rsb_set_error(ctx, "bad shard %d of %d", rank, world); return 1; }
+  RSB_CUDA_OK(cudaSetDevice(ctx->device));
+  RSB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  ctx->shard_rank = rank; ctx->shard_world = world;
+  free_geo(ctx->geo[0]); free_geo(ctx->geo[1]);          // tile lists depend on the shard: rsb_set_weights rebuilds them
+  ctx->geo[0].S = 0; ctx->geo[1].S = 0;
+  return 0;
+}
+
+int rsb_sharded_counts(rsb_ctx *ctx, const uint8_t *msa, int64_t row_stride, int on_device, double tol, double *marg_sums)
+{
+  RSB_CUDA_OK(cudaSetDevice(ctx->device));
+  if (ensure_geo(ctx, 0)) return 1;
+  if (upload_msa(ctx, msa, row_stride, 0, 1, 0, on_device, ctx->stream)) return 1;
+  if (enqueue_counts(ctx, 0, 0, 1, ctx->d_res, ctx->stream)) return 1;
+  if (enqueue_marginals(ctx, 0, 1, tol, ctx->stream, 1)) return 1;
+  RSB_CUDA_OK(cudaMemcpyAsync(marg_sums, ctx->d_msum, sizeof(double) * 4 * ctx->L, cudaMemcpyDeviceToHost, ctx->stream));
+  RSB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int rsb_sharded_statistic(rsb_ctx *ctx, const double *marg_sums, double tol, int stat, int covclass, const double *allowpair, double *cov_sums)
+{
+  RSB_CUDA_OK(cudaSetDevice(ctx->device));
+  if (resolve_stat(ctx, stat, covclass)) return 1;
+  if (stat == RSB_RAF || stat == RSB_RAFS || stat == RSB_CCF) { rsb_set_error(ctx, "statistic not available with a sharded pair grid"); return 1; }
+  RSB_CUDA_OK(cudaMemcpyAsync(ctx->d_msum, marg_sums, sizeof(double) * 4 * ctx->L, cudaMemcpyHostToDevice, ctx->stream));
+  if (enqueue_marginals(ctx, 0, 1, tol, ctx->stream, 2)) return 1;
+  RSB_CUDA_OK(cudaMemsetAsync(ctx->d_cov, 0, sizeof(double) * (size_t) ctx->L * ctx->Lp, ctx->stream));     // rows of other ranks stay 0
+  if (enqueue_statistic(ctx, 0, 1, stat, covclass, allow_mask(allowpair), ctx->stream, 1)) return 1;
+  RSB_CUDA_OK(cudaMemcpyAsync(cov_sums, ctx->d_covsum, sizeof(double) * (ctx->L + 4), cudaMemcpyDeviceToHost, ctx->stream));
+  return check_flags(ctx, "corr_Probs");
+}
+
+int rsb_sharded_correct(rsb_ctx *ctx, const double *cov_sums, int actype, int mode, double w, double bmin, double *cov, double *minmax)
+{
+  RSB_CUDA_OK(cudaSetDevice(ctx->device));
+  RSB_CUDA_OK(cudaMemcpyAsync(ctx->d_covsum, cov_sums, sizeof(double) * (ctx->L + 4), cudaMemcpyHostToDevice, ctx->stream));
+  RSB_CUDA_OK(cudaMemcpyAsync(ctx->d_w, &w, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  if (enqueue_statistic(ctx, 0, 1, RSB_GT, RSB_C16, 0, ctx->stream, 2)) return 1;                          // covsum -> COVx, COVavg
+  if (enqueue_correct(ctx, 0, 1, actype, mode, bmin, ctx->stream)) return 1;
+  if ((mode & 2) && w > 0.0) {                                                                            // pairs owned by this rank
+    unsigned long long mine = 0;
+    for (int i = 0; i < ctx->L; i++) if ((i / RSB_ICOLS) % ctx->shard_world == ctx->shard_rank) mine += (unsigned long long) (ctx->L - 1 - i);
+    ctx->hist_n += mine;
+  }
+  double mmx[2];
+  if (cov && copy_matrix_out(ctx, ctx->d_cov, cov)) return 1;
+  RSB_CUDA_OK(cudaMemcpyAsync(mmx, ctx->d_minmax, sizeof(mmx), cudaMemcpyDeviceToHost, ctx->stream));
+  if (check_flags(ctx, "corr_CalculateCOVCorrected")) return 1;
+  if (minmax) { minmax[0] = mmx[0]; minmax[1] = mmx[1]; }
+  return 0;
+}
+
+/* histograms of the scan left by rsb_scan / rsb_correct / rsb_statistic: ha (all pairs), and with pairmask also hb / ht */
+int rsb_scan_hist(rsb_ctx *ctx, const uint8_t *pairmask, double w, double bmin, int nb, uint64_t *ha, uint64_t *hb, uint64_t *ht)
+{
+  RSB_CUDA_OK(cudaSetDevice(ctx->device));
+  if (nb < 1 || !(w > 0.0)) { rsb_set_error(ctx, "bad histogram geometry"); return 1; }
+  const size_t L = ctx->L;
+  unsigned long long *d3 = nullptr; uint8_t *dmask = nullptr;
+  RSB_CUDA_OK(cudaMalloc(&d3, sizeof(unsigned long long) * 3 * (size_t) nb));
+  RSB_CUDA_OK(cudaMemsetAsync(d3, 0, sizeof(unsigned long long) * 3 * (size_t) nb, ctx->stream));
+  if (pairmask) {
+    RSB_CUDA_OK(cudaMalloc(&dmask, L * L));
+    RSB_CUDA_OK(cudaMemcpyAsync(dmask, pairmask, L * L, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  RSB_CUDA_OK(rsb_launch_hist3(ctx->d_cov, ctx->L, ctx->Lp, dmask, bmin, w, nb, d3, d3 + nb, d3 + 2 * (size_t) nb, ctx->d_flags, ctx->stream));
+  ctx->launches++;
+  if (ha) RSB_CUDA_OK(cudaMemcpyAsync(ha, d3, sizeof(uint64_t) * nb, cudaMemcpyDeviceToHost, ctx->stream));
+  if (hb) RSB_CUDA_OK(cudaMemcpyAsync(hb, d3 + nb, sizeof(uint64_t) * nb, cudaMemcpyDeviceToHost, ctx->stream));
+  if (ht) RSB_CUDA_OK(cudaMemcpyAsync(ht, d3 + 2 * (size_t) nb, sizeof(uint64_t) * nb, cudaMemcpyDeviceToHost, ctx->stream));
+  const int rc = check_flags(ctx, "cov_SignificantPairs_Ranking");
+  cudaFree(d3); if (dmask) cudaFree(dmask);
+  return rc;
 }
 
 int rsb_hist_reset(rsb_ctx *ctx)

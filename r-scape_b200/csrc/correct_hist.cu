@@ -15,11 +15,11 @@ constexpr int CH_TI = RSB_TI;
 constexpr int CH_TJ = RSB_TJ;
 constexpr int CH_SMEM_BINS = 4096;
 
-// COVx[i] = sum_{j != i} COV[i][j] / (L-1) from the tile partials (one thread per column, fixed summation order);
-// each block also leaves the sum of its row partials (= its share of sum_{i<j} COV) in blocksum[r][block].
+// covsum[i] = sum_{j != i} COV[i][j] from the tile partials (one thread per column, fixed summation order); each block
+// also leaves the sum of its row partials (= its share of sum_{i<j} COV) in blocksum[r][block].
 __global__ void __launch_bounds__(128)
-covx_kernel(const double *__restrict__ rowpart, const double *__restrict__ colpart, int L, int nJT, int nIT,
-            double *__restrict__ covx, double *__restrict__ blocksum)
+covsum_kernel(const double *__restrict__ rowpart, const double *__restrict__ colpart, int L, int nJT, int nIT,
+              double *__restrict__ covsum, double *__restrict__ blocksum)
 {
   __shared__ double red[128];
   const int r = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -27,9 +27,7 @@ covx_kernel(const double *__restrict__ rowpart, const double *__restrict__ colpa
   if (i < L) {
     for (int jt = 0; jt < nJT; jt++) rs += rowpart[((size_t) r * nJT + jt) * L + i];
     for (int it = 0; it < nIT; it++) cs += colpart[((size_t) r * nIT + it) * L + i];
-    double x = rs + cs;
-    if (L > 1) x /= (double) L - 1.;
-    covx[(size_t) r * L + i] = x;
+    covsum[(size_t) r * (L + 4) + i] = rs + cs;
   }
   red[threadIdx.x] = rs;
   __syncthreads();
@@ -37,10 +35,10 @@ covx_kernel(const double *__restrict__ rowpart, const double *__restrict__ colpa
   if (threadIdx.x == 0) blocksum[(size_t) r * gridDim.x + blockIdx.x] = red[0];
 }
 
-// COVavg = 2/(L(L-1)) sum_{i<j} COV; raw min/max from the per-tile partials.  scal[r][0..3] = { COVavg, raw min, raw max, unused }
+// covsum[r][L..L+2] = { sum_{i<j} COV, raw min, raw max } from the per-block / per-tile partials.  Together with covsum[0..L)
+// this is the vector that is reduced across ranks when the pair grid is sharded (sum, sum, min, max).
 __global__ void __launch_bounds__(256)
-correct_final_kernel(const double *__restrict__ blocksum, int nblk, const double *__restrict__ mm, int L, int ntiles,
-                     double *__restrict__ scal)
+covtot_kernel(const double *__restrict__ blocksum, int nblk, const double *__restrict__ mm, int L, int ntiles, double *__restrict__ covsum)
 {
   __shared__ double rmin[256], rmax[256];
   const int r = blockIdx.x;
@@ -59,11 +57,28 @@ correct_final_kernel(const double *__restrict__ blocksum, int nblk, const double
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    double avg = 0.0;
-    for (int k = 0; k < nblk; k++) avg += blocksum[(size_t) r * nblk + k];        // fixed order
+    double tot = 0.0;
+    for (int k = 0; k < nblk; k++) tot += blocksum[(size_t) r * nblk + k];        // fixed order
+    double *o = covsum + (size_t) r * (L + 4) + L;
+    o[0] = tot; o[1] = rmin[0]; o[2] = rmax[0]; o[3] = 0.0;
+  }
+}
+
+// COVx[i] = covsum[i] / (L-1) (:1101-1108); COVavg = 2/(L(L-1)) sum_{i<j} COV (:1093-1098).  scal[r] = { COVavg, raw min, raw max, - }
+__global__ void covx_kernel(const double *__restrict__ covsum, int L, double *__restrict__ covx, double *__restrict__ scal)
+{
+  const int r = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  const double *cs = covsum + (size_t) r * (L + 4);
+  if (i < L) {
+    double x = cs[i];
+    if (L > 1) x /= (double) L - 1.;
+    covx[(size_t) r * L + i] = x;
+  }
+  if (i == 0) {
+    double avg = cs[L];
     if (L > 1) avg /= (double) L * ((double) L - 1.);
     avg *= 2.;
-    scal[r * 4 + 0] = avg; scal[r * 4 + 1] = rmin[0]; scal[r * 4 + 2] = rmax[0]; scal[r * 4 + 3] = 0.0;
+    scal[r * 4 + 0] = avg; scal[r * 4 + 1] = cs[L + 1]; scal[r * 4 + 2] = cs[L + 2]; scal[r * 4 + 3] = 0.0;
   }
 }
 
@@ -82,14 +97,14 @@ __device__ __forceinline__ double corrected(int actype, double raw, double xi, d
 __global__ void __launch_bounds__(CH_TJ)
 correct_hist_kernel(double *__restrict__ cov, const double *__restrict__ covx, const double *__restrict__ scal, int L, int Lp,
                     int actype, int mode, double bmin, const double *__restrict__ wptr, unsigned long long *__restrict__ hist,
-                    int nbins, double *__restrict__ mm, int *__restrict__ flags, int nJT, int nIT)
+                    int nbins, double *__restrict__ mm, int *__restrict__ flags, int nJT, int nIT, int sr, int sw)
 {
   __shared__ unsigned int sh[CH_SMEM_BINS];
   __shared__ double smin[CH_TJ / 32], smax[CH_TJ / 32];
   const int jt = blockIdx.x, it = blockIdx.y, r = blockIdx.z;
   const int j  = jt * CH_TJ + threadIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool tile_live = (it * CH_TI) < (jt * CH_TJ + CH_TJ - 1);
+  const bool tile_live = (it * CH_TI) < (jt * CH_TJ + CH_TJ - 1) && RSB_OWNED(it, sr, sw);
   const bool do_hist = (mode & 2) != 0;
   const double avg = scal[r * 4];
   const double w   = do_hist ? *wptr : 1.0;
@@ -177,26 +192,46 @@ __global__ void symmetrize_kernel(double *__restrict__ cov, int L, int Lp)
   else if (i < j) cov[(size_t) j * Lp + i] = cov[(size_t) i * Lp + j];
 }
 
+// The three histograms of the input alignment's scan (src/covariation.c:420-457): ha gets every pair, hb the pairs
+// flagged in pairmask (the structure's contacts / base pairs, by data->samplesize), ht the others.
+__global__ void hist3_kernel(const double *__restrict__ cov, int L, int Lp, const uint8_t *__restrict__ pairmask, double bmin, double w,
+                             int nb, unsigned long long *__restrict__ ha, unsigned long long *__restrict__ hb, unsigned long long *__restrict__ ht,
+                             int *__restrict__ flags)
+{
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+  if (j >= L || i >= j) return;
+  const double x  = fmax(cov[(size_t) i * Lp + j], bmin + w);
+  const double bd = ceil(((x - bmin) / w) - 1.);
+  if (!(bd >= 0.0 && bd < (double) nb)) { atomicOr(flags, 4); return; }
+  const int b = (int) bd;
+  atomicAdd(&ha[b], 1ull);
+  if (pairmask) atomicAdd(pairmask[(size_t) i * L + j] ? &hb[b] : &ht[b], 1ull);
+}
+
 } // namespace
 
 void rsb_corr_grid(int L, int *nJT, int *nIT) { *nJT = (L + CH_TJ - 1) / CH_TJ; *nIT = (L + CH_TI - 1) / CH_TI; }
 
+// phase: 1 = reduce the tile partials -> covsum[r][L+4], 2 = covsum -> COVx, COVavg, 3 = both
 cudaError_t rsb_launch_correct_final(const double *rowpart, const double *colpart, const double *mm, int nrep, int L,
-                                     double *covx, double *scal, double *blocksum, cudaStream_t st)
+                                     double *covx, double *scal, double *blocksum, double *covsum, int phase, cudaStream_t st)
 {
   int nJT, nIT; rsb_corr_grid(L, &nJT, &nIT);
   const int nblk = (L + 127) / 128;
-  covx_kernel<<<dim3(nblk, nrep), 128, 0, st>>>(rowpart, colpart, L, nJT, nIT, covx, blocksum);
-  correct_final_kernel<<<nrep, 256, 0, st>>>(blocksum, nblk, mm, L, nJT * nIT, scal);
+  if (phase & 1) {
+    covsum_kernel<<<dim3(nblk, nrep), 128, 0, st>>>(rowpart, colpart, L, nJT, nIT, covsum, blocksum);
+    covtot_kernel<<<nrep, 256, 0, st>>>(blocksum, nblk, mm, L, nJT * nIT, covsum);
+  }
+  if (phase & 2) covx_kernel<<<dim3(nblk, nrep), 128, 0, st>>>(covsum, L, covx, scal);
   return cudaGetLastError();
 }
 
 cudaError_t rsb_launch_correct_hist(double *cov, const double *covx, const double *scal, int nrep, int L, int Lp, int actype, int mode,
                                     double bmin, const double *wptr, unsigned long long *hist, int nbins, double *mm, double *minmax_out,
-                                    int *flags, cudaStream_t st)
+                                    int *flags, int sr, int sw, cudaStream_t st)
 {
   int nJT, nIT; rsb_corr_grid(L, &nJT, &nIT);
-  correct_hist_kernel<<<dim3(nJT, nIT, nrep), CH_TJ, 0, st>>>(cov, covx, scal, L, Lp, actype, mode, bmin, wptr, hist, nbins, mm, flags, nJT, nIT);
+  correct_hist_kernel<<<dim3(nJT, nIT, nrep), CH_TJ, 0, st>>>(cov, covx, scal, L, Lp, actype, mode, bmin, wptr, hist, nbins, mm, flags, nJT, nIT, sr, sw);
   minmax_final_kernel<<<nrep, 256, 0, st>>>(mm, nJT * nIT, minmax_out);
   return cudaGetLastError();
 }
@@ -210,5 +245,12 @@ cudaError_t rsb_launch_width(const double *minmax, double w_old, double bmin, in
 cudaError_t rsb_launch_symmetrize(double *cov, int L, int Lp, cudaStream_t st)
 {
   symmetrize_kernel<<<dim3((L + 127) / 128, L), 128, 0, st>>>(cov, L, Lp);
+  return cudaGetLastError();
+}
+
+cudaError_t rsb_launch_hist3(const double *cov, int L, int Lp, const uint8_t *pairmask, double bmin, double w, int nb,
+                             unsigned long long *ha, unsigned long long *hb, unsigned long long *ht, int *flags, cudaStream_t st)
+{
+  hist3_kernel<<<dim3((L + 127) / 128, L), 128, 0, st>>>(cov, L, Lp, pairmask, bmin, w, nb, ha, hb, ht, flags);
   return cudaGetLastError();
 }

@@ -29,6 +29,9 @@
 // RSB_TI rows x RSB_TJ columns of the upper triangle, one thread per column j
 #define RSB_TI     16
 #define RSB_TJ     128
+// row-block sharding of the pair grid across ranks (LSU-scale L): rank sr of sw owns the 32-column row blocks ib with
+// ib % sw == sr (cyclic, because row i has L-1-i pairs); a tile row `it` of RSB_TI rows belongs to block it*RSB_TI/32
+#define RSB_OWNED(it, sr, sw) ((sw) <= 1 || (((it) * RSB_TI / RSB_ICOLS) % (sw)) == (sr))
 
 #define RSB_CUDA_OK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
     rsb_set_error(ctx, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); return 1; } } while (0)

@@ -78,7 +78,7 @@ __device__ __forceinline__ double warp_sum(double v)
 __global__ void __launch_bounds__(ST_TJ)
 marg_partial_kernel(const long long *__restrict__ cnt, int L, int Lp, double scale, long long wtot,
                     double *__restrict__ rowpart, double *__restrict__ colpart, double *__restrict__ nseff,
-                    int nJT, int nIT)
+                    int nJT, int nIT, int sr, int sw)
 {
   __shared__ double rowacc[ST_TJ / 32][ST_TI][4];
   const int jt = blockIdx.x, it = blockIdx.y, r = blockIdx.z;
@@ -86,7 +86,7 @@ marg_partial_kernel(const long long *__restrict__ cnt, int L, int Lp, double sca
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const size_t plane = (size_t) L * Lp;
   const long long *c = cnt + (size_t) r * 16 * plane;
-  const bool tile_live = (it * ST_TI) < (jt * ST_TJ + ST_TJ - 1);      // some i < some j
+  const bool tile_live = (it * ST_TI) < (jt * ST_TJ + ST_TJ - 1) && RSB_OWNED(it, sr, sw);      // some i < some j, rows owned by this rank
   double col[4] = { 0, 0, 0, 0 };
 
   for (int il = 0; il < ST_TI; il++) {
@@ -123,9 +123,10 @@ marg_partial_kernel(const long long *__restrict__ cnt, int L, int Lp, double sca
   }
 }
 
-// pm[i] = normalise(sum of partials); validation flag as corr_Marginals' esl_vec_DValidate (:1363)
-__global__ void marg_final_kernel(const double *__restrict__ rowpart, const double *__restrict__ colpart, int L,
-                                  int nJT, int nIT, double tol, double *__restrict__ pm, int *__restrict__ flags)
+// unnormalised marginal sums msum[i][a] = sum of the tile partials in a fixed order.  With the pair grid sharded over
+// ranks these are the vectors that are summed across ranks before normalisation.
+__global__ void marg_sum_kernel(const double *__restrict__ rowpart, const double *__restrict__ colpart, int L,
+                                int nJT, int nIT, double *__restrict__ msum)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
   if (i >= L) return;
@@ -136,6 +137,18 @@ __global__ void marg_final_kernel(const double *__restrict__ rowpart, const doub
   for (int it = 0; it < nIT; it++)
     #pragma unroll
     for (int a = 0; a < 4; a++) m[a] += colpart[(((size_t) r * nIT + it) * L + i) * 4 + a];
+  #pragma unroll
+  for (int a = 0; a < 4; a++) msum[((size_t) r * L + i) * 4 + a] = m[a];
+}
+
+// pm[i] = normalise(msum[i]); validation flag as corr_Marginals' esl_vec_DValidate (:1363)
+__global__ void marg_norm_kernel(const double *__restrict__ msum, int L, double tol, double *__restrict__ pm, int *__restrict__ flags)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+  if (i >= L) return;
+  double m[4];
+  #pragma unroll
+  for (int a = 0; a < 4; a++) m[a] = msum[((size_t) r * L + i) * 4 + a];
   double sum = 0.0, comp = 0.0;
   #pragma unroll
   for (int a = 0; a < 4; a++) { const double y = m[a] - comp, t = sum + y; comp = (t - sum) - y; sum = t; }
@@ -232,7 +245,7 @@ template <int STAT, int CLS>
 __global__ void __launch_bounds__(ST_TJ)
 stat_kernel(const long long *__restrict__ cnt, const double *__restrict__ pm, int L, int Lp, double scale, long long wtot,
             unsigned mask, double *__restrict__ cov, double *__restrict__ rowpart, double *__restrict__ colpart,
-            double *__restrict__ mm, int nJT, int nIT)
+            double *__restrict__ mm, int nJT, int nIT, int sr, int sw)
 {
   __shared__ double rowacc[ST_TJ / 32][ST_TI];
   __shared__ double pmi[ST_TI][4], lpmi[ST_TI][4];
@@ -242,7 +255,7 @@ stat_kernel(const long long *__restrict__ cnt, const double *__restrict__ pm, in
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const size_t plane = (size_t) L * Lp;
   const long long *c = cnt + (size_t) r * 16 * plane;
-  const bool tile_live = (it * ST_TI) < (jt * ST_TJ + ST_TJ - 1);
+  const bool tile_live = (it * ST_TI) < (jt * ST_TJ + ST_TJ - 1) && RSB_OWNED(it, sr, sw);
   double col = 0.0, vmin = INFINITY, vmax = -INFINITY;
   double mj[4] = { 0.25, 0.25, 0.25, 0.25 }, lmj[4];
 
@@ -494,20 +507,25 @@ __global__ void ps_kernel(const unsigned long long *__restrict__ colsum, int L, 
 // ---------------------------------------------------------------------------------------------- launchers
 void rsb_stat_grid(int L, int *nJT, int *nIT) { *nJT = (L + ST_TJ - 1) / ST_TJ; *nIT = (L + ST_TI - 1) / ST_TI; }
 
+// phase: 1 = partial sums only (-> msum), 2 = normalise msum -> pm, 3 = both
 cudaError_t rsb_launch_marginals(const long long *cnt, int nrep, int L, int Lp, double scale, long long wtot, double tol,
-                                 double *rowpart, double *colpart, double *nseff, double *pm, int *flags, cudaStream_t st)
+                                 double *rowpart, double *colpart, double *nseff, double *msum, double *pm, int *flags,
+                                 int sr, int sw, int phase, cudaStream_t st)
 {
   int nJT, nIT; rsb_stat_grid(L, &nJT, &nIT);
-  marg_partial_kernel<<<dim3(nJT, nIT, nrep), ST_TJ, 0, st>>>(cnt, L, Lp, scale, wtot, rowpart, colpart, nseff, nJT, nIT);
-  marg_final_kernel<<<dim3((L + 127) / 128, nrep), 128, 0, st>>>(rowpart, colpart, L, nJT, nIT, tol, pm, flags);
+  if (phase & 1) {
+    marg_partial_kernel<<<dim3(nJT, nIT, nrep), ST_TJ, 0, st>>>(cnt, L, Lp, scale, wtot, rowpart, colpart, nseff, nJT, nIT, sr, sw);
+    marg_sum_kernel<<<dim3((L + 127) / 128, nrep), 128, 0, st>>>(rowpart, colpart, L, nJT, nIT, msum);
+  }
+  if (phase & 2) marg_norm_kernel<<<dim3((L + 127) / 128, nrep), 128, 0, st>>>(msum, L, tol, pm, flags);
   return cudaGetLastError();
 }
 
 #define RSB_STAT_CASE(STAT, CLS) \
-  stat_kernel<STAT, CLS><<<grid, ST_TJ, 0, st>>>(cnt, pm, L, Lp, scale, wtot, mask, cov, rowpart, colpart, mm, nJT, nIT); break;
+  stat_kernel<STAT, CLS><<<grid, ST_TJ, 0, st>>>(cnt, pm, L, Lp, scale, wtot, mask, cov, rowpart, colpart, mm, nJT, nIT, sr, sw); break;
 
 cudaError_t rsb_launch_statistic(int stat, int cls, const long long *cnt, const double *pm, int nrep, int L, int Lp, double scale,
-                                 long long wtot, unsigned mask, double *cov, double *rowpart, double *colpart, double *mm, cudaStream_t st)
+                                 long long wtot, unsigned mask, double *cov, double *rowpart, double *colpart, double *mm, int sr, int sw, cudaStream_t st)
 {
   int nJT, nIT; rsb_stat_grid(L, &nJT, &nIT);
   dim3 grid(nJT, nIT, nrep);

@@ -41,3 +41,28 @@ def reduce_range(lo, hi, device=None, group=None):
         t = t.to(device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     return -float(t[0]), float(t[1])
+
+
+def reduce_sum(vec, device=None, group=None):
+    """Sum a float64 vector over all ranks (marginal sums of a sharded pair grid)."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return vec
+    t = torch.from_numpy(np.ascontiguousarray(vec, dtype=np.float64))
+    if device is not None:
+        t = t.to(device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t.cpu().numpy()
+
+
+def reduce_cov_sums(cov_sums, L, device=None, group=None):
+    """cov_sums of rsb_sharded_statistic: [0..L] are sums, [L+1] a minimum, [L+2] a maximum."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return cov_sums
+    out = np.array(cov_sums, dtype=np.float64)
+    out[:L + 1] = reduce_sum(out[:L + 1], device, group)
+    lo, hi = reduce_range(out[L + 1], out[L + 2], device, group)
+    out[L + 1], out[L + 2] = lo, hi
+    return out

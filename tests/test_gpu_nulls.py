@@ -98,3 +98,29 @@ def test_last_null_nseff_quirk_q3(ctx, pkg, po, oracle):
     ref = oracle.scan(nulls[-1], wgt, po.GT, po.C16, po.APC, want_probs=True)
     assert np.max(np.abs(ne - ref["nseff"])) <= 1e-9 * N
     assert np.max(np.abs(np.triu(ng, 1) - np.triu(ref["ngap"], 1))) <= 1e-9 * N
+
+
+def test_scan_histograms_ha_hb_ht(ctx, pkg, po, oracle):
+    """The three histograms of the input alignment's scan (src/covariation.c:420-457) with a structure pair mask."""
+    N, L = 200, 60
+    msa, wgt, partner = po.synthetic_msa(N, L, seed=77)
+    ctx.configure(N, L, 1, 0)
+    ctx.set_weights(wgt)
+    res = ctx.scan(msa, pkg.GT, pkg.C16, pkg.APC)
+    ref = oracle.scan(msa, wgt, po.GT, po.C16, po.APC)
+    w, bmin = 0.05, -10.0
+    h = oracle.hist_from_cov(ref["cov"], ref["maxcov"], bmin, w)
+    v = oracle.view(h)
+    oracle.free(h)
+    mask = np.zeros((L, L), np.uint8)
+    for i, j in enumerate(partner):
+        if j > i:
+            mask[i, j] = 1
+    ha, hb, ht = ctx.scan_hist(w, bmin, v.nb, mask)
+    assert np.array_equal(ha, v.obs)
+    assert np.array_equal(hb + ht, ha) and int(hb.sum()) == int(mask.sum())
+    iu = np.triu_indices(L, 1)
+    x = np.maximum(ref["cov"][iu], bmin + w)
+    b = np.ceil((x - bmin) / w - 1).astype(int)
+    want_hb = np.bincount(b[mask[iu] > 0], minlength=v.nb)
+    assert np.array_equal(hb, want_hb.astype(np.uint64))
