@@ -182,6 +182,8 @@ def main():
     ap.add_argument("--ref-cols", type=int, default=160)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--grid-shard", action="store_true",
+                    help="shard the L x L pair grid of every scan over the GPUs (BASELINE config 4) instead of the null replicates")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -214,7 +216,10 @@ def main():
     ctx = pkg.Context(local, stream.cuda_stream)
     ctx.configure(N, L, slots, args.slices)
     ctx.set_weights(wgt)
-    my_ids = pkg.parallel.null_shard(R, world, rank)                 # contiguous block of replicate ids per rank
+    if args.grid_shard:
+        ctx.set_shard(rank, world)                                    # row blocks of the pair grid of EVERY scan dealt to the ranks
+        ctx.set_weights(wgt)
+    my_ids = list(range(R)) if args.grid_shard else pkg.parallel.null_shard(R, world, rank)   # replicate ids held by this rank
     n_mine = len(my_ids)
     own0 = (n_mine > 0 and my_ids[0] == 0)
     ctx.pool_reserve(n_mine + (0 if own0 else 1))
@@ -234,8 +239,31 @@ def main():
         if not own0:
             ctx.null_fitch_shuffle(host_msa.numpy(), SEED, 1, first_rep=w0_entry, first_id=0)
 
+    def sharded_scan(src, hist_w=None, want_cov=False):
+        """One scan with the pair grid sharded over the ranks: three phases, one small all-reduce between them."""
+        ms = ctx.sharded_counts_pool(src) if isinstance(src, int) else ctx.sharded_counts(src)
+        ms = pkg.parallel.reduce_sum(ms, device="cuda")
+        cs = pkg.parallel.reduce_cov_sums(ctx.sharded_statistic(ms, pkg.GT, pkg.C16), L, device="cuda")
+        cov, lo, hi = ctx.sharded_correct(cs, pkg.APC, want_cov=want_cov, hist_w=hist_w)
+        lo, hi = pkg.parallel.reduce_range(lo, hi, device="cuda")
+        return cov, lo, hi
+
+    def job_grid(real):
+        """the same job with every scan sharded over all ranks (config 4: L x L tile grid over the GPUs)"""
+        ctx.hist_reset()
+        _, lo, hi = sharded_scan(w0_entry)                                            # calculate_width_histo
+        w = min(0.05, (hi - max(-10.0, lo)) / 400.0)
+        for k in range(n_mine):
+            sharded_scan(k, hist_w=w)
+        cov, _, _ = sharded_scan(real, want_cov=isinstance(real, np.ndarray))
+        bins, n, imax = ctx.hist_read(NB)
+        bins = pkg.parallel.reduce_histogram(bins, device="cuda")
+        return w, bins, dict(cov=cov)
+
     def job(real):
         """null_rscape + run_rscape for this rank's share of the work, nulls already in the device pool."""
+        if args.grid_shard:
+            return job_grid(real)
         ctx.hist_reset()
         w, _, _ = ctx.null_width_pool(w0_entry, pkg.GT, pkg.C16, pkg.APC)             # calculate_width_histo
         if n_mine:
@@ -294,7 +322,7 @@ def main():
         ctx.set_weights(wgt)
         generate()
         w, bins, out = job(host_msa.numpy())
-        if rank == 0:
+        if rank == 0 and out is not None and out.get("cov") is not None:
             cov_out[:] = out["cov"]
 
     ms_e2e = timed(job_e2e, args.steps, 1)
@@ -306,7 +334,9 @@ def main():
     # launches during the value run: per step, gram launches = width(1) + ceil(nulls/slots) + real(1 on rank 0)
     pairs = L * (L - 1) / 2.0
     gram_ms_avg = cnt["gram_ms"] / max(1, cnt["gram_launches"])
-    scans_this_rank = (n_mine + 1 + (1 if rank == 0 else 0)) * (args.steps + args.warmup)
+    scans_this_rank = (n_mine + 1 + (1 if (rank == 0 or args.grid_shard) else 0)) * (args.steps + args.warmup)
+    if args.grid_shard:
+        scans_this_rank /= world                                     # every rank contracts 1/world of each scan's tiles
     ops_alg_per_launch = 32.0 * pairs * N * scans_this_rank / max(1, cnt["gram_launches"])
     achieved = ops_alg_per_launch / (gram_ms_avg * 1e-3) / 1e12 if gram_ms_avg > 0 else 0.0
     peak_i8 = 2.0 * peaks["bf16"]
@@ -327,7 +357,8 @@ def main():
                     dtype="u8 x u8 -> s32 tensor-core counts (fixed-point weights), f64 statistics", data="synthetic",
                     config=dict(workload=f"{args.workload}: L={L} N={N} nulls={R} GTp+APC, scans per step = {scans_total} "
                                          f"(width pass + {R} nulls + input alignment)",
-                                weight_slices=args.slices, replicate_slots=slots, parallelism=f"nulls in contiguous blocks over {world} GPU(s)",
+                                weight_slices=args.slices, replicate_slots=slots, parallelism=(f"L x L pair grid of every scan sharded over {world} GPU(s) by 32-column row blocks" if args.grid_shard
+                                             else f"nulls in contiguous blocks over {world} GPU(s)"),
                                 l2="inputs larger than L2 (null alignments %.1f GB, operand planes %.1f GB per replicate)" %
                                    (R * N * L / 1e9, (4 + 4 * args.slices) * L * N / 1e9),
                                 null_model="Fitch + tree-substitution shuffle generated on the device: resident before the timed region "

@@ -98,6 +98,8 @@ int rsb_get_counts_direct(rsb_ctx *ctx, const uint8_t *msa, int64_t row_stride, 
  * mode of rsb_sharded_correct: bit 0 = write the corrected scores (needed for cov), bit 1 = add them to the histogram. */
 int rsb_set_shard(rsb_ctx *ctx, int rank, int world);
 int rsb_sharded_counts(rsb_ctx *ctx, const uint8_t *msa, int64_t row_stride, int on_device, double tol, double *marg_sums);
+/* the same on pool entry `rep` (a null generated on the device; every rank generates the same replicate ids) */
+int rsb_sharded_counts_pool(rsb_ctx *ctx, int rep, double tol, double *marg_sums);
 int rsb_sharded_statistic(rsb_ctx *ctx, const double *marg_sums, double tol, int stat, int covclass, const double *allowpair, double *cov_sums);
 int rsb_sharded_correct(rsb_ctx *ctx, const double *cov_sums, int actype, int mode, double w, double bmin, double *cov, double *minmax);
 

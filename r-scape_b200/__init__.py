@@ -63,6 +63,7 @@ def lib():
         L.rsb_scan_hist.argtypes = [_vp, _u8p, C.c_double, C.c_double, C.c_int, _u64p, _u64p, _u64p]
         L.rsb_set_shard.argtypes = [_vp, C.c_int, C.c_int]
         L.rsb_sharded_counts.argtypes = [_vp, _vp, C.c_int64, C.c_int, C.c_double, _dp]
+        L.rsb_sharded_counts_pool.argtypes = [_vp, C.c_int, C.c_double, _dp]
         L.rsb_sharded_statistic.argtypes = [_vp, _dp, C.c_double, C.c_int, C.c_int, _dp, _dp]
         L.rsb_sharded_correct.argtypes = [_vp, _dp, C.c_int, C.c_int, C.c_double, C.c_double, _dp, _dp]
         L.rsb_get_counts.argtypes = [_vp, _i64p]
@@ -181,6 +182,11 @@ class Context:
         p, dev = _ptr(msa)
         sums = np.empty((self.L, 4))
         self._ck(lib().rsb_sharded_counts(self._h, p, self.L, dev, tol, _d(sums)))
+        return sums
+
+    def sharded_counts_pool(self, rep, tol=1e-6):
+        sums = np.empty((self.L, 4))
+        self._ck(lib().rsb_sharded_counts_pool(self._h, rep, tol, _d(sums)))
         return sums
 
     def sharded_statistic(self, marg_sums, stat=GT, covclass=C16, allowpair=None, tol=1e-6):

@@ -865,6 +865,12 @@ int rsb_sharded_counts(rsb_ctx *ctx, const uint8_t *msa, int64_t row_stride, int
   return 0;
 }
 
+int rsb_sharded_counts_pool(rsb_ctx *ctx, int rep, double tol, double *marg_sums)
+{
+  if (pool_range_ok(ctx, rep, 1)) return 1;
+  return rsb_sharded_counts(ctx, ctx->d_pool + (size_t) rep * ctx->N * ctx->L, ctx->L, 1, tol, marg_sums);
+}
+
 int rsb_sharded_statistic(rsb_ctx *ctx, const double *marg_sums, double tol, int stat, int covclass, const double *allowpair, double *cov_sums)
 {
   RSB_CUDA_OK(cudaSetDevice(ctx->device));
