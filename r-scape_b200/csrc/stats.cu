@@ -123,22 +123,32 @@ marg_partial_kernel(const long long *__restrict__ cnt, int L, int Lp, double sca
   }
 }
 
-// unnormalised marginal sums msum[i][a] = sum of the tile partials in a fixed order.  With the pair grid sharded over
-// ranks these are the vectors that are summed across ranks before normalisation.
-__global__ void marg_sum_kernel(const double *__restrict__ rowpart, const double *__restrict__ colpart, int L,
-                                int nJT, int nIT, double *__restrict__ msum)
+// unnormalised marginal sums msum[i][a] = sum of the tile partials in a fixed order: one warp per column, lanes stride
+// over the partial blocks, fixed xor-tree over the lanes (deterministic).  With the pair grid sharded over ranks these are
+// the vectors that are summed across ranks before normalisation.
+__global__ void __launch_bounds__(256)
+marg_sum_kernel(const double *__restrict__ rowpart, const double *__restrict__ colpart, int L,
+                int nJT, int nIT, double *__restrict__ msum)
 {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), r = blockIdx.y;
   if (i >= L) return;
   double m[4] = { 0, 0, 0, 0 };
-  for (int jt = 0; jt < nJT; jt++)
-    #pragma unroll
-    for (int a = 0; a < 4; a++) m[a] += rowpart[(((size_t) r * nJT + jt) * L + i) * 4 + a];
-  for (int it = 0; it < nIT; it++)
-    #pragma unroll
-    for (int a = 0; a < 4; a++) m[a] += colpart[(((size_t) r * nIT + it) * L + i) * 4 + a];
+  for (int k = lane; k < nJT + nIT; k += 32) {
+    const double *src = (k < nJT) ? rowpart + (((size_t) r * nJT + k) * L + i) * 4
+                                  : colpart + (((size_t) r * nIT + (k - nJT)) * L + i) * 4;
+    const double2 lo = *reinterpret_cast<const double2 *>(src), hi = *reinterpret_cast<const double2 *>(src + 2);
+    m[0] += lo.x; m[1] += lo.y; m[2] += hi.x; m[3] += hi.y;
+  }
   #pragma unroll
-  for (int a = 0; a < 4; a++) msum[((size_t) r * L + i) * 4 + a] = m[a];
+  for (int a = 0; a < 4; a++) {
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m[a] += __shfl_xor_sync(0xffffffffu, m[a], o);
+  }
+  if (lane == 0) {
+    #pragma unroll
+    for (int a = 0; a < 4; a++) msum[((size_t) r * L + i) * 4 + a] = m[a];
+  }
 }
 
 // pm[i] = normalise(msum[i]); validation flag as corr_Marginals' esl_vec_DValidate (:1363)
@@ -515,7 +525,7 @@ cudaError_t rsb_launch_marginals(const long long *cnt, int nrep, int L, int Lp, 
   int nJT, nIT; rsb_stat_grid(L, &nJT, &nIT);
   if (phase & 1) {
     marg_partial_kernel<<<dim3(nJT, nIT, nrep), ST_TJ, 0, st>>>(cnt, L, Lp, scale, wtot, rowpart, colpart, nseff, nJT, nIT, sr, sw);
-    marg_sum_kernel<<<dim3((L + 127) / 128, nrep), 128, 0, st>>>(rowpart, colpart, L, nJT, nIT, msum);
+    marg_sum_kernel<<<dim3((L + 7) / 8, nrep), 256, 0, st>>>(rowpart, colpart, L, nJT, nIT, msum);
   }
   if (phase & 2) marg_norm_kernel<<<dim3((L + 127) / 128, nrep), 128, 0, st>>>(msum, L, tol, pm, flags);
   return cudaGetLastError();
