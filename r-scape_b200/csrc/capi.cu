@@ -86,6 +86,7 @@ struct rsb_ctx {
   long long *d_cnt = nullptr;
   double *d_nseff = nullptr, *d_pm = nullptr, *d_cov = nullptr, *d_tmp = nullptr;
   double *d_rowpart = nullptr, *d_colpart = nullptr, *d_mm = nullptr, *d_scal = nullptr, *d_covx = nullptr, *d_minmax = nullptr;
+  double *h_mm = nullptr; size_t h_mm_cap = 0;      // pinned staging of the per-replicate min/max: a pageable target would block the enqueuing thread
   double *d_meanp = nullptr, *d_w = nullptr, *d_blocksum = nullptr, *d_msum = nullptr, *d_covsum = nullptr;
   int shard_rank = 0, shard_world = 1;  // row-block sharding of the pair grid across ranks
   cudaStream_t stream_aux = nullptr, stream_copy = nullptr;     // statistics / uploads of the pipelined null loop
@@ -111,6 +112,8 @@ struct rsb_ctx {
   bool profile = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending_aux;   // statistics chain of the pipelined null loop
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending_stage; // its stage boundaries (after marginals, after statistic)
+  double stage_ms[3] = { 0.0, 0.0, 0.0 };
   double aux_ms = 0.0; long long aux_chains = 0;
 };
 
@@ -164,6 +167,7 @@ void free_plan(rsb_ctx *c)
   free_geo(c->geo[0]); free_geo(c->geo[1]);
   dfree(c->d_res); dfree(c->d_planeA); dfree(c->d_planeB); dfree(c->d_cnt); dfree(c->d_nseff); dfree(c->d_pm); dfree(c->d_cov);
   dfree(c->d_tmp); dfree(c->d_rowpart); dfree(c->d_colpart); dfree(c->d_mm); dfree(c->d_scal); dfree(c->d_covx); dfree(c->d_minmax);
+  if (c->h_mm) { cudaFreeHost(c->h_mm); c->h_mm = nullptr; c->h_mm_cap = 0; }
   dfree(c->d_meanp); dfree(c->d_w); dfree(c->d_blocksum); dfree(c->d_msum); dfree(c->d_covsum); dfree(c->d_hist); dfree(c->d_colsum); dfree(c->d_flags); dfree(c->d_ps); dfree(c->d_pp_out);
   dfree(c->d_nseff_out); dfree(c->d_ngap_out); dfree(c->d_left); dfree(c->d_right); dfree(c->d_parent); dfree(c->d_order);
   dfree(c->d_level_start); dfree(c->d_perm); dfree(c->d_pcdf); dfree(c->d_root); dfree(c->d_gapmask); dfree(c->d_simscratch);
@@ -495,6 +499,7 @@ void rsb_destroy(rsb_ctx *ctx)
   cudaStreamSynchronize(ctx->stream);
   for (auto &p : ctx->pending) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   for (auto &p : ctx->pending_aux) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+  for (auto &p : ctx->pending_stage) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   free_plan(ctx);
   cudaStreamSynchronize(ctx->stream_aux); cudaStreamSynchronize(ctx->stream_copy);
   cudaStreamDestroy(ctx->stream_aux); cudaStreamDestroy(ctx->stream_copy);
@@ -770,40 +775,50 @@ static int null_hist_pipelined(rsb_ctx *ctx, const uint8_t *nulls, int nrep, int
   const int  G = (ctx->Rcap >= 2) ? 2 : 1;
   const int  chunk = std::max(1, ctx->Rcap / G);
   const size_t repbytes = (size_t) ctx->N * ctx->L;
+  static const int serial = getenv("RSCAPE_B200_SERIAL") ? atoi(getenv("RSCAPE_B200_SERIAL")) : 0;      // experiments: 1 = statistics on the main stream, 2 = pack too
+  cudaStream_t st_aux = (serial & 1) ? ctx->stream : ctx->stream_aux, st_copy = (serial & 2) ? ctx->stream : ctx->stream_copy;
 
+  if (minmax && ctx->h_mm_cap < (size_t) nrep) {
+    if (ctx->h_mm) cudaFreeHost(ctx->h_mm);
+    ctx->h_mm = nullptr; ctx->h_mm_cap = 0;
+    RSB_CUDA_OK(cudaMallocHost(&ctx->h_mm, sizeof(double) * 2 * (size_t) nrep));
+    ctx->h_mm_cap = (size_t) nrep;
+  }
   RSB_CUDA_OK(cudaMemcpyAsync(ctx->d_w, &w, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   RSB_CUDA_OK(cudaEventRecord(ctx->ev_entry, ctx->stream));
-  RSB_CUDA_OK(cudaStreamWaitEvent(ctx->stream_aux, ctx->ev_entry, 0));
-  RSB_CUDA_OK(cudaStreamWaitEvent(ctx->stream_copy, ctx->ev_entry, 0));
+  RSB_CUDA_OK(cudaStreamWaitEvent(st_aux, ctx->ev_entry, 0));
+  RSB_CUDA_OK(cudaStreamWaitEvent(st_copy, ctx->ev_entry, 0));
   bool used[2] = { false, false };
 
   int c = 0;
   for (int r0 = 0; r0 < nrep; r0 += chunk, c++) {
     const int g = c % G, s0 = g * chunk, n = std::min(chunk, nrep - r0);
     const uint8_t *src;
-    if (used[g]) RSB_CUDA_OK(cudaStreamWaitEvent(ctx->stream_copy, ctx->ev_counts[g], 0));       // the group's slots and planes have been consumed
+    if (used[g]) RSB_CUDA_OK(cudaStreamWaitEvent(st_copy, ctx->ev_counts[g], 0));       // the group's slots and planes have been consumed
     if (in_place) src = nulls + (size_t) r0 * repbytes;
     else {
-      if (upload_msa(ctx, nulls + (size_t) r0 * rep_stride, row_stride, rep_stride, n, s0, on_device, ctx->stream_copy)) return 1;
+      if (upload_msa(ctx, nulls + (size_t) r0 * rep_stride, row_stride, rep_stride, n, s0, on_device, st_copy)) return 1;
       src = ctx->d_res + (size_t) s0 * repbytes;
     }
-    if (enqueue_pack(ctx, raf ? 1 : 0, s0, n, src, ctx->stream_copy)) return 1;                   // HBM-bound transpose: hides under the previous gram
-    RSB_CUDA_OK(cudaEventRecord(ctx->ev_up[g], ctx->stream_copy));
+    if (enqueue_pack(ctx, raf ? 1 : 0, s0, n, src, st_copy)) return 1;                   // HBM-bound transpose: hides under the previous gram
+    RSB_CUDA_OK(cudaEventRecord(ctx->ev_up[g], st_copy));
     RSB_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->ev_up[g], 0));
     if (used[g]) RSB_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->ev_stats[g], 0));               // counts of this group have been consumed
     if (enqueue_gram(ctx, raf ? 1 : 0, s0, n, ctx->stream)) return 1;
     RSB_CUDA_OK(cudaEventRecord(ctx->ev_counts[g], ctx->stream));
 
-    RSB_CUDA_OK(cudaStreamWaitEvent(ctx->stream_aux, ctx->ev_counts[g], 0));
-    cudaEvent_t a0 = nullptr, a1 = nullptr;
-    if (ctx->profile) { cudaEventCreate(&a0); cudaEventCreate(&a1); cudaEventRecord(a0, ctx->stream_aux); }
-    if (!raf && enqueue_marginals(ctx, s0, n, tol, ctx->stream_aux)) return 1;
-    if (enqueue_statistic(ctx, s0, n, stat, covclass, mask, ctx->stream_aux)) return 1;
-    if (enqueue_correct(ctx, s0, n, actype, 2, bmin, ctx->stream_aux)) return 1;
-    if (minmax) RSB_CUDA_OK(cudaMemcpyAsync(minmax + 2 * (size_t) r0, ctx->d_minmax + 2 * (size_t) s0, sizeof(double) * 2 * n,
-                                            cudaMemcpyDeviceToHost, ctx->stream_aux));
-    if (ctx->profile) { cudaEventRecord(a1, ctx->stream_aux); ctx->pending_aux.push_back({ a0, a1 }); ctx->aux_chains++; }
-    RSB_CUDA_OK(cudaEventRecord(ctx->ev_stats[g], ctx->stream_aux));
+    RSB_CUDA_OK(cudaStreamWaitEvent(st_aux, ctx->ev_counts[g], 0));
+    cudaEvent_t a0 = nullptr, a1 = nullptr, am = nullptr, as = nullptr;
+    if (ctx->profile) { cudaEventCreate(&a0); cudaEventCreate(&a1); cudaEventCreate(&am); cudaEventCreate(&as); cudaEventRecord(a0, st_aux); }
+    if (!raf && enqueue_marginals(ctx, s0, n, tol, st_aux)) return 1;
+    if (ctx->profile) cudaEventRecord(am, st_aux);
+    if (enqueue_statistic(ctx, s0, n, stat, covclass, mask, st_aux)) return 1;
+    if (ctx->profile) cudaEventRecord(as, st_aux);
+    if (enqueue_correct(ctx, s0, n, actype, 2, bmin, st_aux)) return 1;
+    if (minmax) RSB_CUDA_OK(cudaMemcpyAsync(ctx->h_mm + 2 * (size_t) r0, ctx->d_minmax + 2 * (size_t) s0, sizeof(double) * 2 * n,
+                                            cudaMemcpyDeviceToHost, st_aux));
+    if (ctx->profile) { cudaEventRecord(a1, st_aux); ctx->pending_aux.push_back({ a0, a1 }); ctx->pending_stage.push_back({ am, as }); ctx->aux_chains++; }
+    RSB_CUDA_OK(cudaEventRecord(ctx->ev_stats[g], st_aux));
     used[g] = true;
     if (w > 0.0) ctx->hist_n += (unsigned long long) n * ((unsigned long long) ctx->L * (ctx->L - 1) / 2);
   }
@@ -818,7 +833,9 @@ int rsb_null_hist(rsb_ctx *ctx, const uint8_t *nulls, int nrep, int64_t row_stri
   if (resolve_stat(ctx, stat, covclass)) return 1;
   if (null_hist_pipelined(ctx, nulls, nrep, row_stride, rep_stride, on_device, stat, covclass, actype, allow_mask(allowpair),
                           tol, w, bmin, minmax)) return 1;
-  return check_flags(ctx, "null_rscape");
+  if (check_flags(ctx, "null_rscape")) return 1;
+  if (minmax) memcpy(minmax, ctx->h_mm, sizeof(double) * 2 * (size_t) nrep);
+  return 0;
 }
 
 int rsb_null_hist_pool(rsb_ctx *ctx, int first_rep, int nrep, int stat, int covclass, int actype, const double *allowpair,
@@ -830,7 +847,9 @@ int rsb_null_hist_pool(rsb_ctx *ctx, int first_rep, int nrep, int stat, int covc
   const size_t rb = (size_t) ctx->N * ctx->L;
   if (null_hist_pipelined(ctx, ctx->d_pool + (size_t) first_rep * rb, nrep, ctx->L, (int64_t) rb, 1, stat, covclass, actype,
                           allow_mask(allowpair), tol, w, bmin, minmax)) return 1;
-  return check_flags(ctx, "null_rscape");
+  if (check_flags(ctx, "null_rscape")) return 1;
+  if (minmax) memcpy(minmax, ctx->h_mm, sizeof(double) * 2 * (size_t) nrep);
+  return 0;
 }
 
 int rsb_null_width_pool(rsb_ctx *ctx, int rep, int stat, int covclass, int actype, const double *allowpair, double tol,
@@ -1124,6 +1143,30 @@ int rsb_pool_put(rsb_ctx *ctx, int first_rep, int nrep, const uint8_t *in)
 // ---------------------------------------------------------------------------------------------- instrumentation
 int rsb_profile_gram(rsb_ctx *ctx, int enable) { ctx->profile = enable != 0; return 0; }
 
+#ifdef RSB_BLOCKTRACE
+extern "C" void rsb_trace_set_stats(unsigned long long *buf);
+extern "C" void rsb_trace_set_gram(unsigned long long *buf);
+static unsigned long long *g_trace = nullptr;
+extern "C" int rsb_blocktrace(int on, const char *path)
+{
+  const size_t bytes = 8 * (1 + 3 * (1ULL << 20));
+  if (on) {
+    if (!g_trace) cudaMalloc(&g_trace, bytes);
+    cudaMemset(g_trace, 0, bytes);
+    rsb_trace_set_stats(g_trace); rsb_trace_set_gram(g_trace);
+  } else {
+    cudaDeviceSynchronize();
+    rsb_trace_set_stats(nullptr); rsb_trace_set_gram(nullptr);
+    std::vector<unsigned long long> h(bytes / 8);
+    cudaMemcpy(h.data(), g_trace, bytes, cudaMemcpyDeviceToHost);
+    FILE *f = fopen(path, "wb"); if (!f) return 1;
+    const size_t n = std::min<unsigned long long>(h[0], 1ULL << 20);
+    fwrite(h.data(), 8, 1 + 3 * n, f); fclose(f);
+  }
+  return 0;
+}
+#endif
+
 int rsb_counters(rsb_ctx *ctx, int64_t *launches, double *gram_ms, int64_t *gram_launches, int reset)
 {
   RSB_CUDA_OK(cudaSetDevice(ctx->device));
@@ -1138,19 +1181,27 @@ int rsb_counters(rsb_ctx *ctx, int64_t *launches, double *gram_ms, int64_t *gram
   }
   if (!ctx->pending_aux.empty()) {
     RSB_CUDA_OK(cudaStreamSynchronize(ctx->stream_aux));
-    for (auto &p : ctx->pending_aux) {
+    for (size_t k = 0; k < ctx->pending_aux.size(); k++) {
+      auto &p = ctx->pending_aux[k]; auto &q = ctx->pending_stage[k];
       float ms = 0.f;
       if (cudaEventElapsedTime(&ms, p.first, p.second) == cudaSuccess) ctx->aux_ms += ms;
-      cudaEventDestroy(p.first); cudaEventDestroy(p.second);
+      if (cudaEventElapsedTime(&ms, p.first, q.first) == cudaSuccess) ctx->stage_ms[0] += ms;
+      if (cudaEventElapsedTime(&ms, q.first, q.second) == cudaSuccess) ctx->stage_ms[1] += ms;
+      if (cudaEventElapsedTime(&ms, q.second, p.second) == cudaSuccess) ctx->stage_ms[2] += ms;
+      cudaEventDestroy(p.first); cudaEventDestroy(p.second); cudaEventDestroy(q.first); cudaEventDestroy(q.second);
     }
-    ctx->pending_aux.clear();
+    ctx->pending_aux.clear(); ctx->pending_stage.clear();
   }
   if (launches) *launches = ctx->launches;
   if (gram_ms) *gram_ms = ctx->gram_ms;
   if (gram_launches) *gram_launches = ctx->gram_launches;
-  if (getenv("RSCAPE_B200_TRACE")) fprintf(stderr, "[rsb] gram %.3f ms x %lld, statistics chain %.3f ms x %lld\n", ctx->gram_launches ? ctx->gram_ms / ctx->gram_launches : 0.0,
-                                        ctx->gram_launches, ctx->aux_chains ? ctx->aux_ms / ctx->aux_chains : 0.0, ctx->aux_chains);
-  if (reset) { ctx->launches = 0; ctx->gram_ms = 0.0; ctx->gram_launches = 0; ctx->aux_ms = 0.0; ctx->aux_chains = 0; }
+  if (getenv("RSCAPE_B200_TRACE")) {
+    const double na = ctx->aux_chains ? (double) ctx->aux_chains : 1.0;
+    fprintf(stderr, "[rsb] gram %.3f ms x %lld, statistics chain %.3f ms x %lld (marginals %.3f, statistic %.3f, correct+hist %.3f)\n",
+            ctx->gram_launches ? ctx->gram_ms / ctx->gram_launches : 0.0, ctx->gram_launches, ctx->aux_ms / na, ctx->aux_chains,
+            ctx->stage_ms[0] / na, ctx->stage_ms[1] / na, ctx->stage_ms[2] / na);
+  }
+  if (reset) { ctx->launches = 0; ctx->gram_ms = 0.0; ctx->gram_launches = 0; ctx->aux_ms = 0.0; ctx->aux_chains = 0; ctx->stage_ms[0] = ctx->stage_ms[1] = ctx->stage_ms[2] = 0.0; }
   return 0;
 }
 

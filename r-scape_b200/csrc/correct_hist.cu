@@ -219,9 +219,10 @@ cudaError_t rsb_launch_correct_final(const double *rowpart, const double *colpar
   int nJT, nIT; rsb_corr_grid(L, &nJT, &nIT);
   const int nblk = (L + 127) / 128;
   if (phase & 1) {
-    covsum_kernel<<<dim3(nblk, nrep), 128, 0, st>>>(rowpart, colpart, L, nJT, nIT, covsum, blocksum);
-    covtot_kernel<<<nrep, 256, 0, st>>>(blocksum, nblk, mm, L, nJT * nIT, covsum);
+    rsb_coreside(covsum_kernel); covsum_kernel<<<dim3(nblk, nrep), 128, 0, st>>>(rowpart, colpart, L, nJT, nIT, covsum, blocksum);
+    rsb_coreside(covtot_kernel); covtot_kernel<<<nrep, 256, 0, st>>>(blocksum, nblk, mm, L, nJT * nIT, covsum);
   }
+  rsb_coreside(covx_kernel);
   if (phase & 2) covx_kernel<<<dim3(nblk, nrep), 128, 0, st>>>(covsum, L, covx, scal);
   return cudaGetLastError();
 }
@@ -231,8 +232,8 @@ cudaError_t rsb_launch_correct_hist(double *cov, const double *covx, const doubl
                                     int *flags, int sr, int sw, cudaStream_t st)
 {
   int nJT, nIT; rsb_corr_grid(L, &nJT, &nIT);
-  correct_hist_kernel<<<dim3(nJT, nIT, nrep), CH_TJ, 0, st>>>(cov, covx, scal, L, Lp, actype, mode, bmin, wptr, hist, nbins, mm, flags, nJT, nIT, sr, sw);
-  minmax_final_kernel<<<nrep, 256, 0, st>>>(mm, nJT * nIT, minmax_out);
+  rsb_coreside(correct_hist_kernel); correct_hist_kernel<<<dim3(nJT, nIT, nrep), CH_TJ, 0, st>>>(cov, covx, scal, L, Lp, actype, mode, bmin, wptr, hist, nbins, mm, flags, nJT, nIT, sr, sw);
+  rsb_coreside(minmax_final_kernel); minmax_final_kernel<<<nrep, 256, 0, st>>>(mm, nJT * nIT, minmax_out);
   return cudaGetLastError();
 }
 

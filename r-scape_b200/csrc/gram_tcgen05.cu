@@ -78,6 +78,10 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
         | ((uint64_t) 2u  << 61);
 }
 
+#ifdef RSB_BLOCKTRACE
+__device__ unsigned long long *gram_trace_buf;
+#endif
+
 template <int S>
 __global__ void __launch_bounds__(GRAM_THREADS, 1)
 gram_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
@@ -93,6 +97,9 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
   constexpr uint32_t IDESC       = (2u << 4) | ((uint32_t) (NT >> 3) << 17) | ((uint32_t) (RSB_MTILE >> 4) << 24);
 
   extern __shared__ uint8_t smem_raw[];
+#ifdef RSB_BLOCKTRACE
+  const unsigned long long t0 = rsb_gtime();
+#endif
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;      // swizzle-128B tiles need 1024 B alignment
   const uint32_t bar_base  = smem_base + NSTAGE * STAGE_BYTES;
   auto full_bar   = [&](int s) { return bar_base + 8u * s; };
@@ -228,6 +235,9 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(512u) : "memory");
+#ifdef RSB_BLOCKTRACE
+    if ((threadIdx.x & 31) == 0) rsb_trace_put(gram_trace_buf, 1, t0);
+#endif
   }
 }
 
@@ -242,6 +252,9 @@ cudaError_t launch_gram(const CUtensorMap &tmA, const CUtensorMap &tmB, const in
   constexpr size_t smem = gram_smem_bytes<S>();
   cudaError_t e = cudaFuncSetAttribute(gram_i8_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
   if (e != cudaSuccess) return e;
+  // the ring takes ~190 KB; with the SM's carve-out at its maximum (228 KB) the rest is left for the blocks of the
+  // statistics chain, which run beside this kernel (a 196 KB carve-out would leave them no shared memory at all)
+  rsb_coreside(gram_i8_kernel<S>);
   gram_i8_kernel<S><<<grid, GRAM_THREADS, smem, st>>>(tmA, tmB, tiles, ntiles, rep0, nrep, L, Lp, kstages, cnt);
   return cudaGetLastError();
 }
@@ -263,3 +276,7 @@ cudaError_t rsb_launch_gram_i8(int S, const CUtensorMap &tmA, const CUtensorMap 
   }
   return cudaErrorInvalidValue;
 }
+
+#ifdef RSB_BLOCKTRACE
+extern "C" void rsb_trace_set_gram(unsigned long long *buf) { cudaMemcpyToSymbol(gram_trace_buf, &buf, sizeof(buf)); }
+#endif

@@ -129,12 +129,12 @@ cudaError_t rsb_launch_pack(int S, const uint8_t *res, int nrep, int N, int L, l
 {
   dim3 grid(Kpad / PK_SEQ, (Lcover + PK_COL - 1) / PK_COL, nrep);
   switch (S) {
-  case 1: pack_planes_kernel<1><<<grid, 256, 0, st>>>(res, N, L, rep_stride_res, wdig, Kpad, planeA, MA, planeB, NBrows); break;
-  case 2: pack_planes_kernel<2><<<grid, 256, 0, st>>>(res, N, L, rep_stride_res, wdig, Kpad, planeA, MA, planeB, NBrows); break;
-  case 3: pack_planes_kernel<3><<<grid, 256, 0, st>>>(res, N, L, rep_stride_res, wdig, Kpad, planeA, MA, planeB, NBrows); break;
-  case 4: pack_planes_kernel<4><<<grid, 256, 0, st>>>(res, N, L, rep_stride_res, wdig, Kpad, planeA, MA, planeB, NBrows); break;
-  case 5: pack_planes_kernel<5><<<grid, 256, 0, st>>>(res, N, L, rep_stride_res, wdig, Kpad, planeA, MA, planeB, NBrows); break;
-  case 6: pack_planes_kernel<6><<<grid, 256, 0, st>>>(res, N, L, rep_stride_res, wdig, Kpad, planeA, MA, planeB, NBrows); break;
+  case 1: rsb_coreside(pack_planes_kernel<1>); pack_planes_kernel<1><<<grid, 256, 0, st>>>(res, N, L, rep_stride_res, wdig, Kpad, planeA, MA, planeB, NBrows); break;
+  case 2: rsb_coreside(pack_planes_kernel<2>); pack_planes_kernel<2><<<grid, 256, 0, st>>>(res, N, L, rep_stride_res, wdig, Kpad, planeA, MA, planeB, NBrows); break;
+  case 3: rsb_coreside(pack_planes_kernel<3>); pack_planes_kernel<3><<<grid, 256, 0, st>>>(res, N, L, rep_stride_res, wdig, Kpad, planeA, MA, planeB, NBrows); break;
+  case 4: rsb_coreside(pack_planes_kernel<4>); pack_planes_kernel<4><<<grid, 256, 0, st>>>(res, N, L, rep_stride_res, wdig, Kpad, planeA, MA, planeB, NBrows); break;
+  case 5: rsb_coreside(pack_planes_kernel<5>); pack_planes_kernel<5><<<grid, 256, 0, st>>>(res, N, L, rep_stride_res, wdig, Kpad, planeA, MA, planeB, NBrows); break;
+  case 6: rsb_coreside(pack_planes_kernel<6>); pack_planes_kernel<6><<<grid, 256, 0, st>>>(res, N, L, rep_stride_res, wdig, Kpad, planeA, MA, planeB, NBrows); break;
   default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();

@@ -44,5 +44,25 @@ enum { RSB_CHI = 0, RSB_GT = 3, RSB_MI = 6, RSB_MIr = 9, RSB_MIg = 12, RSB_OMES 
 enum { RSB_C16 = 0, RSB_C2 = 1, RSB_CWC = 2, RSB_CSELECT = 3 };
 enum { RSB_APC = 0, RSB_ASC = 1, RSB_NOCORR = 2 };
 
+// The kernels of the statistics chain run beside the persistent tcgen05 kernel, which holds every SM's shared memory at
+// the maximum carve-out: they ask for the same carve-out so that an SM never has to drain to switch configuration.
+template <typename K> static inline void rsb_coreside(K kernel)
+{
+  cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int) cudaSharedmemCarveoutMaxShared);
+}
+
+#ifdef RSB_BLOCKTRACE
+// experiment: per-block (kernel id, SM, start, end) records, to see which kernels really share an SM
+__device__ __forceinline__ unsigned long long rsb_gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ unsigned rsb_smid() { unsigned s; asm volatile("mov.u32 %0, %%smid;" : "=r"(s)); return s; }
+__device__ __forceinline__ void rsb_trace_put(unsigned long long *buf, unsigned kid, unsigned long long t0)
+{
+  if (!buf) return;
+  const unsigned long long t1 = rsb_gtime();
+  const unsigned long long k = atomicAdd(buf, 1ULL);
+  if (k < (1ULL << 20)) { buf[1 + 3 * k] = ((unsigned long long) kid << 32) | rsb_smid(); buf[2 + 3 * k] = t0; buf[3 + 3 * k] = t1; }
+}
+#endif
+
 struct rsb_ctx;
 void rsb_set_error(rsb_ctx *ctx, const char *fmt, ...);

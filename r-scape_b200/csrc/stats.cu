@@ -18,6 +18,9 @@
 
 namespace {
 
+#ifdef RSB_BLOCKTRACE
+__device__ unsigned long long *stats_trace_buf;
+#endif
 constexpr int ST_TI = RSB_TI;
 constexpr int ST_TJ = RSB_TJ;
 
@@ -32,9 +35,16 @@ __device__ __forceinline__ double u64_to_f64(unsigned long long v)
   return hi + lo;
 }
 
-// fixed-point counts of one pair -> nseff, ngap, pp (prior 1e-10 per cell, Kahan-summed normaliser).
-// EXACT_DIV: divide every cell by the sum as esl_vec_DNorm does (values handed back to the host); otherwise multiply by
-// the reciprocal (1 ulp, inside the 1e-9 score tolerance) -- the statistic kernels are FP64-issue bound.
+// counts below 2^52 (the whole alignment's weight is: wtot < 2^52, checked by the caller) convert with one subtraction
+__device__ __forceinline__ double u52_to_f64(unsigned long long v)
+{
+  return __longlong_as_double(0x4330000000000000ULL | v) - 4503599627370496.0;
+}
+
+// fixed-point counts of one pair -> nseff, ngap, pp (prior 1e-10 per cell).
+// EXACT_DIV (values handed back to the host): Kahan-summed normaliser and a division per cell, as esl_vec_DNorm does
+// (SURVEY 9.7).  Otherwise (statistic kernels, FP64-issue bound): pairwise-tree normaliser and a multiplication by the
+// reciprocal; both differ from the exact form by a few ulp, far inside the 1e-9 score tolerance.
 template <bool EXACT_DIV>
 __device__ __forceinline__ void load_pair(const long long *__restrict__ cnt, size_t plane, size_t off,
                                           double scale, long long wtot, PairProbs &P)
@@ -45,24 +55,67 @@ __device__ __forceinline__ void load_pair(const long long *__restrict__ cnt, siz
   unsigned long long ne = 0;
   #pragma unroll
   for (int k = 0; k < 16; k++) ne += c[k];
-  P.ne = u64_to_f64(ne) * scale;
-  P.ng = u64_to_f64((unsigned long long) wtot - ne) * scale;
-  double sum = 0.0, comp = 0.0;
-  #pragma unroll
-  for (int k = 0; k < 16; k++) {
-    P.pp[k] = 1e-10 + u64_to_f64(c[k]) * scale;
-    const double y = P.pp[k] - comp, t = sum + y;      // esl_vec_DSum is Kahan-compensated
-    comp = (t - sum) - y;
-    sum  = t;
-  }
   if (EXACT_DIV) {
+    P.ne = u64_to_f64(ne) * scale;
+    P.ng = u64_to_f64((unsigned long long) wtot - ne) * scale;
+    double sum = 0.0, comp = 0.0;
+    #pragma unroll
+    for (int k = 0; k < 16; k++) {
+      P.pp[k] = 1e-10 + u64_to_f64(c[k]) * scale;
+      const double y = P.pp[k] - comp, t = sum + y;      // esl_vec_DSum is Kahan-compensated
+      comp = (t - sum) - y;
+      sum  = t;
+    }
     #pragma unroll
     for (int k = 0; k < 16; k++) P.pp[k] = P.pp[k] / sum;
   } else {
+    const bool small = ((unsigned long long) wtot >> 52) == 0;       // uniform over the grid
+    if (small) {
+      P.ne = u52_to_f64(ne) * scale;
+      P.ng = u52_to_f64((unsigned long long) wtot - ne) * scale;
+      #pragma unroll
+      for (int k = 0; k < 16; k++) P.pp[k] = fma(u52_to_f64(c[k]), scale, 1e-10);
+    } else {
+      P.ne = u64_to_f64(ne) * scale;
+      P.ng = u64_to_f64((unsigned long long) wtot - ne) * scale;
+      #pragma unroll
+      for (int k = 0; k < 16; k++) P.pp[k] = fma(u64_to_f64(c[k]), scale, 1e-10);
+    }
+    double t[8];
+    #pragma unroll
+    for (int k = 0; k < 8; k++) t[k] = P.pp[2 * k] + P.pp[2 * k + 1];
+    const double sum = ((t[0] + t[1]) + (t[2] + t[3])) + ((t[4] + t[5]) + (t[6] + t[7]));
     const double inv = 1.0 / sum;
     #pragma unroll
     for (int k = 0; k < 16; k++) P.pp[k] = P.pp[k] * inv;
   }
+}
+
+// natural log of a positive normal double from a 128-entry table in shared memory: x = 2^e m, m = c (1 + r) with c the
+// centre of m's 1/128 bin, so |r| <= 2^-8 and log1p(r) needs six terms (truncation 2^-58).  About 10 FP64 operations
+// against ~40 for the library log; absolute error <= 4e-16 + 1 ulp(e ln 2).  tab[k] = { 1/c_k rounded, -log of that }.
+constexpr int LOGTAB_N = 128;
+__device__ __forceinline__ void logtab_init(double2 *tab)
+{
+  for (int k = threadIdx.x; k < LOGTAB_N; k += blockDim.x) {
+    const double ic = 1.0 / (1.0 + (k + 0.5) * (1.0 / LOGTAB_N));
+    tab[k] = make_double2(ic, -log(ic));
+  }
+}
+
+__device__ __forceinline__ double fast_log(double x, const double2 *__restrict__ tab)
+{
+  const int hi = __double2hiint(x), lo = __double2loint(x);
+  if ((unsigned) (hi - 0x00100000) >= 0x7fe00000u) return log(x);        // zero, subnormal, negative, inf, nan
+  const double m  = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
+  const double2 t = tab[(hi >> 13) & (LOGTAB_N - 1)];
+  const double r  = fma(m, t.x, -1.0);
+  const double e  = __hiloint2double(0x43300000, ((hi >> 20) - 1023) ^ 0x80000000) - 4503601774854144.0;   // 2^52 + 2^31
+  double p = fma(r, -1.0 / 6.0, 0.2);
+  p = fma(p, r, -0.25);
+  p = fma(p, r, 1.0 / 3.0);
+  p = fma(p, r, -0.5);
+  return fma(e, 0.6931471805599453094, t.y) + fma(p, r * r, r);
 }
 
 __device__ __forceinline__ double warp_sum(double v)
@@ -81,6 +134,9 @@ marg_partial_kernel(const long long *__restrict__ cnt, int L, int Lp, double sca
                     int nJT, int nIT, int sr, int sw)
 {
   __shared__ double rowacc[ST_TJ / 32][ST_TI][4];
+#ifdef RSB_BLOCKTRACE
+  const unsigned long long t0 = rsb_gtime();
+#endif
   const int jt = blockIdx.x, it = blockIdx.y, r = blockIdx.z;
   const int j  = jt * ST_TJ + threadIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -121,6 +177,9 @@ marg_partial_kernel(const long long *__restrict__ cnt, int L, int Lp, double sca
       rowpart[(((size_t) r * nJT + jt) * L + i) * 4 + a] = v;
     }
   }
+#ifdef RSB_BLOCKTRACE
+  if (threadIdx.x == 0) rsb_trace_put(stats_trace_buf, 2, t0);
+#endif
 }
 
 // unnormalised marginal sums msum[i][a] = sum of the tile partials in a fixed order: one warp per column, lanes stride
@@ -175,7 +234,8 @@ __device__ __forceinline__ bool cell_allowed(unsigned mask, int x, int y) { retu
 
 template <int STAT, int CLS>
 __device__ __forceinline__ double pair_statistic(const PairProbs &P, const double *mi, const double *mj,
-                                                 const double *lmi, const double *lmj, unsigned mask)
+                                                 const double *lmi, const double *lmj, unsigned mask,
+                                                 const double2 *__restrict__ tab)
 {
   double v = 0.0, H = 0.0;
   if (CLS == RSB_C2) {
@@ -195,25 +255,25 @@ __device__ __forceinline__ double pair_statistic(const PairProbs &P, const doubl
       v += (exp_in  > 0.) ? (obs_in  - exp_in)  * (obs_in  - exp_in)  / P.ne : 0.0;
       v += (exp_out > 0.) ? (obs_out - exp_out) * (obs_out - exp_out) / P.ne : 0.0;
     } else if (STAT == RSB_GT) {
-      v += (exp_in  > 0. && obs_in  > 0.) ? obs_in  * log(obs_in  / exp_in)  : 0.0;
-      v += (exp_out > 0. && obs_out > 0.) ? obs_out * log(obs_out / exp_out) : 0.0;
+      v += (exp_in  > 0. && obs_in  > 0.) ? obs_in  * fast_log(obs_in  / exp_in, tab)  : 0.0;
+      v += (exp_out > 0. && obs_out > 0.) ? obs_out * fast_log(obs_out / exp_out, tab) : 0.0;
       v *= 2.0;
     } else if (STAT == RSB_MI || STAT == RSB_MIg) {
-      v += (p_in  > 0.) ? p_in  * (log(p_in)  - log(q_in))  : 0.0;
-      v += (p_out > 0.) ? p_out * (log(p_out) - log(q_out)) : 0.0;
+      v += (p_in  > 0.) ? p_in  * (fast_log(p_in, tab)  - fast_log(q_in, tab))  : 0.0;
+      v += (p_out > 0.) ? p_out * (fast_log(p_out, tab) - fast_log(q_out, tab)) : 0.0;
       if (STAT == RSB_MIg) v -= (P.ne > 0) ? P.ng / P.ne : 0.0;
     } else if (STAT == RSB_MIr) {
-      H -= (p_in  > 0.) ? p_in  * log(p_in)  : 0.0;
-      H -= (p_out > 0.) ? p_out * log(p_out) : 0.0;
-      v += (p_in  > 0. && q_in  > 0.) ? p_in  * (log(p_in)  - log(q_in))  : 0.0;
-      v += (p_out > 0. && q_out > 0.) ? p_out * (log(p_out) - log(q_out)) : 0.0;
+      H -= (p_in  > 0.) ? p_in  * fast_log(p_in, tab)  : 0.0;
+      H -= (p_out > 0.) ? p_out * fast_log(p_out, tab) : 0.0;
+      v += (p_in  > 0. && q_in  > 0.) ? p_in  * (fast_log(p_in, tab)  - fast_log(q_in, tab))  : 0.0;
+      v += (p_out > 0. && q_out > 0.) ? p_out * (fast_log(p_out, tab) - fast_log(q_out, tab)) : 0.0;
       v = (H > 1e-2) ? v / H : 0.0;
     }
     return v;
   }
   // lmi / lmj: log of the marginals, taken once per column by the caller.
   if (STAT == RSB_GT && CLS == RSB_C16) {
-    // G = 2 sum obs log(obs/exp) with obs = ne pp, exp = ne pm_i pm_j (:383-387): ne cancels inside the log, so
+    // G = 2 sum obs fast_log(obs/exp, tab) with obs = ne pp, exp = ne pm_i pm_j (:383-387): ne cancels inside the log, so
     // G = 2 ne sum pp (log pp - log pm_i - log pm_j), one log per cell and no division.  The terms kept are the
     // same (exp > 0 and obs > 0 <=> ne > 0, pm_i > 0, pm_j > 0, pp > 0); the rounding differs at the 1e-15 level.
     if (!(P.ne > 0.)) return 0.0;
@@ -222,7 +282,7 @@ __device__ __forceinline__ double pair_statistic(const PairProbs &P, const doubl
       #pragma unroll
       for (int y = 0; y < 4; y++) {
         const double pxy = P.pp[x * 4 + y];
-        v += (pxy > 0.0 && mi[x] > 0.0 && mj[y] > 0.0) ? pxy * (log(pxy) - lmi[x] - lmj[y]) : 0.0;
+        v += (pxy > 0.0 && mi[x] > 0.0 && mj[y] > 0.0) ? pxy * (fast_log(pxy, tab) - lmi[x] - lmj[y]) : 0.0;
       }
     return 2.0 * P.ne * v;
   }
@@ -236,9 +296,9 @@ __device__ __forceinline__ double pair_statistic(const PairProbs &P, const doubl
       const double ob  = P.ne * pxy;
       if      (STAT == RSB_CHI)  v += (ex > 0.) ? (ob - ex) * (ob - ex) / ex   : 0.0;
       else if (STAT == RSB_OMES) v += (ex > 0.) ? (ob - ex) * (ob - ex) / P.ne : 0.0;
-      else if (STAT == RSB_GT)   v += (ex > 0. && ob > 0.) ? ob * log(ob / ex) : 0.0;
+      else if (STAT == RSB_GT)   v += (ex > 0. && ob > 0.) ? ob * fast_log(ob / ex, tab) : 0.0;
       else {
-        const double lp = (pxy > 0.0) ? log(pxy) : 0.0;
+        const double lp = (pxy > 0.0) ? fast_log(pxy, tab) : 0.0;
         if (STAT == RSB_MIr) H -= (pxy > 0.0) ? pxy * lp : 0.0;
         v += (pxy > 0.0 && mi[x] > 0.0 && mj[y] > 0.0) ? pxy * (lp - lmi[x] - lmj[y]) : 0.0;
       }
@@ -260,6 +320,10 @@ stat_kernel(const long long *__restrict__ cnt, const double *__restrict__ pm, in
   __shared__ double rowacc[ST_TJ / 32][ST_TI];
   __shared__ double pmi[ST_TI][4], lpmi[ST_TI][4];
   __shared__ double smin[ST_TJ / 32], smax[ST_TJ / 32];
+  __shared__ double2 tab[LOGTAB_N];
+#ifdef RSB_BLOCKTRACE
+  const unsigned long long t0 = rsb_gtime();
+#endif
   const int jt = blockIdx.x, it = blockIdx.y, r = blockIdx.z;
   const int j  = jt * ST_TJ + threadIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -267,6 +331,7 @@ stat_kernel(const long long *__restrict__ cnt, const double *__restrict__ pm, in
   const long long *c = cnt + (size_t) r * 16 * plane;
   const bool tile_live = (it * ST_TI) < (jt * ST_TJ + ST_TJ - 1) && RSB_OWNED(it, sr, sw);
   double col = 0.0, vmin = INFINITY, vmax = -INFINITY;
+  if (tile_live) logtab_init(tab);
   double mj[4] = { 0.25, 0.25, 0.25, 0.25 }, lmj[4];
 
   if (threadIdx.x < ST_TI * 4) {
@@ -288,7 +353,7 @@ stat_kernel(const long long *__restrict__ cnt, const double *__restrict__ pm, in
     if (tile_live && i < L && j < L && i < j) {
       PairProbs P;
       load_pair<false>(c, plane, (size_t) i * Lp + j, scale, wtot, P);
-      v = pair_statistic<STAT, CLS>(P, pmi[il], mj, lpmi[il], lmj, mask);
+      v = pair_statistic<STAT, CLS>(P, pmi[il], mj, lpmi[il], lmj, mask, tab);
       cov[((size_t) r * L + i) * Lp + j] = v;
       col += v;
       vmin = fmin(vmin, v);
@@ -321,6 +386,9 @@ stat_kernel(const long long *__restrict__ cnt, const double *__restrict__ pm, in
     double *o = mm + (((size_t) r * nIT + it) * nJT + jt) * 2;
     o[0] = a; o[1] = b;
   }
+#ifdef RSB_BLOCKTRACE
+  if (threadIdx.x == 0) rsb_trace_put(stats_trace_buf, 3, t0);
+#endif
 }
 
 // RAF from the UNWEIGHTED count table (planes built with wq = 1, S = 1): integer arithmetic up to the
@@ -524,15 +592,16 @@ cudaError_t rsb_launch_marginals(const long long *cnt, int nrep, int L, int Lp, 
 {
   int nJT, nIT; rsb_stat_grid(L, &nJT, &nIT);
   if (phase & 1) {
-    marg_partial_kernel<<<dim3(nJT, nIT, nrep), ST_TJ, 0, st>>>(cnt, L, Lp, scale, wtot, rowpart, colpart, nseff, nJT, nIT, sr, sw);
-    marg_sum_kernel<<<dim3((L + 7) / 8, nrep), 256, 0, st>>>(rowpart, colpart, L, nJT, nIT, msum);
+    rsb_coreside(marg_partial_kernel); marg_partial_kernel<<<dim3(nJT, nIT, nrep), ST_TJ, 0, st>>>(cnt, L, Lp, scale, wtot, rowpart, colpart, nseff, nJT, nIT, sr, sw);
+    rsb_coreside(marg_sum_kernel); marg_sum_kernel<<<dim3((L + 7) / 8, nrep), 256, 0, st>>>(rowpart, colpart, L, nJT, nIT, msum);
   }
+  rsb_coreside(marg_norm_kernel);
   if (phase & 2) marg_norm_kernel<<<dim3((L + 127) / 128, nrep), 128, 0, st>>>(msum, L, tol, pm, flags);
   return cudaGetLastError();
 }
 
 #define RSB_STAT_CASE(STAT, CLS) \
-  stat_kernel<STAT, CLS><<<grid, ST_TJ, 0, st>>>(cnt, pm, L, Lp, scale, wtot, mask, cov, rowpart, colpart, mm, nJT, nIT, sr, sw); break;
+  rsb_coreside(stat_kernel<STAT, CLS>); stat_kernel<STAT, CLS><<<grid, ST_TJ, 0, st>>>(cnt, pm, L, Lp, scale, wtot, mask, cov, rowpart, colpart, mm, nJT, nIT, sr, sw); break;
 
 cudaError_t rsb_launch_statistic(int stat, int cls, const long long *cnt, const double *pm, int nrep, int L, int Lp, double scale,
                                  long long wtot, unsigned mask, double *cov, double *rowpart, double *colpart, double *mm, int sr, int sw, cudaStream_t st)
@@ -599,3 +668,7 @@ cudaError_t rsb_launch_ps(const unsigned long long *colsum, int L, double scale,
   ps_kernel<<<(L + 127) / 128, 128, 0, st>>>(colsum, L, scale, ps);
   return cudaGetLastError();
 }
+
+#ifdef RSB_BLOCKTRACE
+extern "C" void rsb_trace_set_stats(unsigned long long *buf) { cudaMemcpyToSymbol(stats_trace_buf, &buf, sizeof(buf)); }
+#endif
