@@ -178,7 +178,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="ssu", choices=sorted(WORKLOADS))
-    ap.add_argument("--slices", type=int, default=5, help="8-bit weight slices (fixed-point weight width = 8*slices bits)")
+    ap.add_argument("--slices", type=int, default=4,
+                    help="8-bit digit slices S of the fixed-point weights wq = u V (8-bit multiplier u, V < 256^S): ~8(S+1)-bit weights")
     ap.add_argument("--ref-cols", type=int, default=160)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -216,6 +217,7 @@ def main():
     ctx = pkg.Context(local, stream.cuda_stream)
     ctx.configure(N, L, slots, args.slices)
     ctx.set_weights(wgt)
+    q_abs, q_bits = ctx.quantisation_error()
     if args.grid_shard:
         ctx.set_shard(rank, world)                                    # row blocks of the pair grid of EVERY scan dealt to the ranks
         ctx.set_weights(wgt)
@@ -343,7 +345,7 @@ def main():
     roofline = dict(bound="tensor", achieved=achieved, peak=peak_i8, unit="TOP/s", frac=achieved / peak_i8,
                     traffic=None,
                     note=f"algorithmic int8 ops (32 per pair-cell) of one gram launch / mean launch time {gram_ms_avg:.3f} ms; "
-                         f"the kernel issues {args.slices}x that in tcgen05 kind::i8 MMAs (one pass per 8-bit weight slice): "
+                         f"the kernel issues {args.slices}x that in tcgen05 kind::i8 MMAs (one pass per 8-bit digit slice of the weights): "
                          f"implementation rate {achieved * args.slices:.1f} TOP/s = {achieved * args.slices / peak_i8:.3f} of peak; "
                          f"peak = 2 x {peaks['src']} bf16 {peaks['bf16']} TFLOP/s (int8 runs at twice the bf16 rate)",
                     gram_share_of_step=cnt["gram_ms"] / (ms_dev * (args.steps + args.warmup) / args.steps) if ms_dev > 0 else None)
@@ -357,7 +359,10 @@ def main():
                     dtype="u8 x u8 -> s32 tensor-core counts (fixed-point weights), f64 statistics", data="synthetic",
                     config=dict(workload=f"{args.workload}: L={L} N={N} nulls={R} GTp+APC, scans per step = {scans_total} "
                                          f"(width pass + {R} nulls + input alignment)",
-                                weight_slices=args.slices, replicate_slots=slots, parallelism=(f"L x L pair grid of every scan sharded over {world} GPU(s) by 32-column row blocks" if args.grid_shard
+                                weight_slices=args.slices,
+                                weights=f"fixed point wq = u V, u < 256, V < 256^{args.slices}: largest |wq 2^-q - w| = {q_abs:.3g} "
+                                        f"({q_bits:.1f} bits below the largest weight); counts are exact integer arithmetic on wq",
+                                replicate_slots=slots, parallelism=(f"L x L pair grid of every scan sharded over {world} GPU(s) by 32-column row blocks" if args.grid_shard
                                              else f"nulls in contiguous blocks over {world} GPU(s)"),
                                 l2="inputs larger than L2 (null alignments %.1f GB, operand planes %.1f GB per replicate)" %
                                    (R * N * L / 1e9, (4 + 4 * args.slices) * L * N / 1e9),

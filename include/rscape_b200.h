@@ -42,15 +42,20 @@ const char *rsb_error(const rsb_ctx *ctx);
 const char *rsb_create_error(void);
 
 /* Shape of the alignments to be scanned and how many of them are in flight at once (replicate slots).
- * nslices: number of 8-bit weight slices S (1..6), 0 = choose from the weights (1 if they are all
- * small integers, else 5).  Replaces corr_Create's allocations, src/correlators.c:1161-1219. */
+ * nslices: number of 8-bit digit slices S (1..6) of the fixed-point weights, 0 = choose from the weights (1 if they
+ * are all small integers, else 4: ~40-bit weights, see rsb_set_weights).  Replaces corr_Create's allocations, src/correlators.c:1161-1219. */
 int rsb_configure(rsb_ctx *ctx, int nseq, int alen, int max_replicates, int nslices);
 
-/* Sequence weights (host, double[nseq]); NULL = all 1.  Quantised to fixed point wq = round(w 2^q).
+/* Sequence weights (host, double[nseq]); NULL = all 1.  Quantised to fixed point wq = u V ~ w 2^q with an 8-bit
+ * multiplier u (carried by the one-hot operand) and S base-256 digits of V (the weighted operand), so S slices give
+ * ~8(S+1)-bit weights; every count is then exact integer arithmetic on wq.
  * The same weights serve the input alignment and every null (src/R-scape.c:1668). */
 int rsb_set_weights(rsb_ctx *ctx, const double *wgt);
 /* the quantisation actually used: wq[s] (may be NULL), q, S */
 int rsb_get_quantisation(rsb_ctx *ctx, int64_t *wq, int *q, int *nslices);
+/* Largest |wq_s 2^-q - w_s| over the sequences (weight units) and log2(max weight / that error): how faithfully the
+ * fixed-point weights follow the double weights of msa->wgt (src/correlators.c:1716 reads them as double). */
+int rsb_get_quantisation_error(rsb_ctx *ctx, double *max_abs_err, double *effective_bits);
 
 /* ---- one alignment: the corr_* sequence of cov_Calculate (src/covariation.c:78-258) ----------- */
 /* corr_Probs (src/correlators.c:1424): counts -> pp, nseff, ngap, ps, pm.  Host outputs may be NULL.

@@ -53,6 +53,7 @@ def lib():
         L.rsb_configure.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_int]
         L.rsb_set_weights.argtypes = [_vp, _dp]
         L.rsb_get_quantisation.argtypes = [_vp, _i64p, _ip, _ip]
+        L.rsb_get_quantisation_error.argtypes = [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.rsb_probs.argtypes = [_vp, _vp, C.c_int64, C.c_int, C.c_double, _dp, _dp, _dp, _dp, _dp]
         L.rsb_fetch_probs.argtypes = [_vp, _dp, _dp, _dp, _dp, _dp]
         L.rsb_statistic.argtypes = [_vp, C.c_int, C.c_int, _dp, _vp, C.c_int64, C.c_int, _dp, _dp, _dp]
@@ -141,6 +142,12 @@ class Context:
         q, S = C.c_int(), C.c_int()
         self._ck(lib().rsb_get_quantisation(self._h, wq.ctypes.data_as(_i64p), C.byref(q), C.byref(S)))
         return wq, q.value, S.value
+
+    def quantisation_error(self):
+        """(largest |wq 2^-q - w| in weight units, log2(max weight / that error))."""
+        a, b = C.c_double(), C.c_double()
+        self._ck(lib().rsb_get_quantisation_error(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     # ---- one alignment ------------------------------------------------------------------------
     def _msa(self, msa):
@@ -307,7 +314,7 @@ class Context:
         return dict(launches=a.value, gram_ms=b.value, gram_launches=c.value)
 
 
-def replicate_slots(nseq, alen, nnull, nslices=5, budget_bytes=24e9, sm_count=148):
+def replicate_slots(nseq, alen, nnull, nslices=4, budget_bytes=24e9, sm_count=148):
     """How many null replicates to keep in flight: enough tiles for every SM, bounded by HBM use."""
     cj = {1: 64, 2: 32, 3: 20, 4: 16, 5: 12, 6: 10}[nslices]
     tiles = (alen / 32.0) * (alen / cj) * 0.5 + 1.0

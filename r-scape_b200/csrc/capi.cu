@@ -15,16 +15,19 @@
 
 // ---- kernel launchers defined in the other translation units
 cudaError_t rsb_launch_gram_i8(int S, const CUtensorMap &tmA, const CUtensorMap &tmB, const int2 *tiles, int ntiles,
-                               int rep0, int nrep, int L, int Lp, int kstages, long long *cnt, int grid, cudaStream_t st);
+                               int rep0, int nrep, int L, int Lp, int kstages, long long *cnt, double scale, double *mrow,
+                               double *mcol, int nJB, int nIB, int grid, cudaStream_t st);
 cudaError_t rsb_launch_pack(int S, const uint8_t *res, int nrep, int N, int L, long long rep_stride_res, const uint8_t *wdig,
                             int Kpad, uint8_t *planeA, int MA, uint8_t *planeB, int NBrows, int Lcover, cudaStream_t st);
 cudaError_t rsb_launch_colsum(const uint8_t *res, int N, int L, const unsigned long long *wq, unsigned long long *colsum, cudaStream_t st);
 cudaError_t rsb_launch_counts_direct(const uint8_t *res, int N, int L, int Lp, const unsigned long long *wq, long long *cnt, cudaStream_t st);
 void        rsb_stat_grid(int L, int *nJT, int *nIT);
-cudaError_t rsb_launch_marginals(const long long *cnt, int nrep, int L, int Lp, double scale, long long wtot, double tol,
-                                 double *rowpart, double *colpart, double *nseff, double *msum, double *pm, int *flags,
-                                 int sr, int sw, int phase, cudaStream_t st);
-cudaError_t rsb_launch_statistic(int stat, int cls, const long long *cnt, const double *pm, int nrep, int L, int Lp, double scale,
+cudaError_t rsb_launch_marginals(const double *mrow, const double *mcol, int nrep, int L, int CJ, int nJB, int nIB, double tol,
+                                 double *msum, double *pm, int *flags, int sr, int sw, int phase, cudaStream_t st);
+cudaError_t rsb_launch_nseff(const long long *cnt, int nrep, int L, int Lp, double scale, double *nseff, cudaStream_t st);
+cudaError_t rsb_launch_logtab(void *tab, cudaStream_t st);
+size_t rsb_logtab_bytes();
+cudaError_t rsb_launch_statistic(int stat, int cls, const long long *cnt, const double *pm, const void *logtab, int nrep, int L, int Lp, double scale,
                                  long long wtot, unsigned mask, double *cov, double *rowpart, double *colpart, double *mm, int sr, int sw, cudaStream_t st);
 cudaError_t rsb_launch_raf(const long long *cnt, int nrep, int L, int Lp, int nseq, unsigned mask, int smooth, double *tmp, double *cov,
                            double *rowpart, double *colpart, double *mm, cudaStream_t st);
@@ -63,6 +66,7 @@ struct Geo {
   unsigned long long *d_wq = nullptr;
   std::vector<long long> wq;
   double scale = 1.0;
+  double qerr_abs = 0.0, maxw = 1.0;      // largest |wq 2^-q - w| over the sequences, largest weight
   long long wtot = 0;
   bool ready = false;
 };
@@ -85,12 +89,15 @@ struct rsb_ctx {
   uint8_t *d_res = nullptr, *d_planeA = nullptr, *d_planeB = nullptr;
   long long *d_cnt = nullptr;
   double *d_nseff = nullptr, *d_pm = nullptr, *d_cov = nullptr, *d_tmp = nullptr;
+  double *d_mrow = nullptr, *d_mcol = nullptr; size_t mrow_stride = 0, mcol_stride = 0;   // marginal partials of the gram tiles, per slot
   double *d_rowpart = nullptr, *d_colpart = nullptr, *d_mm = nullptr, *d_scal = nullptr, *d_covx = nullptr, *d_minmax = nullptr;
+  void *d_logtab = nullptr;                          // table of the statistic kernels' log (stats.cu), built once
   double *h_mm = nullptr; size_t h_mm_cap = 0;      // pinned staging of the per-replicate min/max: a pageable target would block the enqueuing thread
   double *d_meanp = nullptr, *d_w = nullptr, *d_blocksum = nullptr, *d_msum = nullptr, *d_covsum = nullptr;
   int shard_rank = 0, shard_world = 1;  // row-block sharding of the pair grid across ranks
   cudaStream_t stream_aux = nullptr, stream_copy = nullptr;     // statistics / uploads of the pipelined null loop
-  cudaEvent_t ev_entry = nullptr, ev_up[2] = { nullptr, nullptr }, ev_counts[2] = { nullptr, nullptr }, ev_stats[2] = { nullptr, nullptr };
+  cudaEvent_t ev_entry = nullptr, ev_up[2] = { nullptr, nullptr }, ev_counts[2] = { nullptr, nullptr }, ev_stats[2] = { nullptr, nullptr },
+              ev_marg[2] = { nullptr, nullptr }, ev_statk[2] = { nullptr, nullptr };
   unsigned long long *d_hist = nullptr, *d_colsum = nullptr;
   int *d_flags = nullptr;
   double *d_ps = nullptr, *d_pp_out = nullptr, *d_nseff_out = nullptr, *d_ngap_out = nullptr;
@@ -166,7 +173,7 @@ void free_plan(rsb_ctx *c)
 {
   free_geo(c->geo[0]); free_geo(c->geo[1]);
   dfree(c->d_res); dfree(c->d_planeA); dfree(c->d_planeB); dfree(c->d_cnt); dfree(c->d_nseff); dfree(c->d_pm); dfree(c->d_cov);
-  dfree(c->d_tmp); dfree(c->d_rowpart); dfree(c->d_colpart); dfree(c->d_mm); dfree(c->d_scal); dfree(c->d_covx); dfree(c->d_minmax);
+  dfree(c->d_mrow); dfree(c->d_mcol); dfree(c->d_tmp); dfree(c->d_rowpart); dfree(c->d_colpart); dfree(c->d_mm); dfree(c->d_scal); dfree(c->d_covx); dfree(c->d_minmax);
   if (c->h_mm) { cudaFreeHost(c->h_mm); c->h_mm = nullptr; c->h_mm_cap = 0; }
   dfree(c->d_meanp); dfree(c->d_w); dfree(c->d_blocksum); dfree(c->d_msum); dfree(c->d_covsum); dfree(c->d_hist); dfree(c->d_colsum); dfree(c->d_flags); dfree(c->d_ps); dfree(c->d_pp_out);
   dfree(c->d_nseff_out); dfree(c->d_ngap_out); dfree(c->d_left); dfree(c->d_right); dfree(c->d_parent); dfree(c->d_order);
@@ -200,46 +207,91 @@ int build_geo(rsb_ctx *ctx, Geo &g, int S)
   }
   if (make_plane_map(ctx, &g.tmB, ctx->d_planeB, ctx->Kpad, (size_t) g.NBrows, ctx->Rcap, g.NT)) return 1;
   dfree(g.d_wdig); dfree(g.d_wq);
-  RSB_CUDA_OK(cudaMalloc(&g.d_wdig, (size_t) S * ctx->Kpad));
+  RSB_CUDA_OK(cudaMalloc(&g.d_wdig, (size_t) (S + 1) * ctx->Kpad));
   RSB_CUDA_OK(cudaMalloc(&g.d_wq, sizeof(unsigned long long) * ctx->N));
   return 0;
 }
 
 // fixed-point weights: wq = round(w 2^q) < 256^S, digits base 256
+// Fixed-point weights for the u8 x u8 -> s32 tensor-core contraction.  A weight is represented as
+//     wq_s = u_s * V_s,   u_s in [1, 255] (carried by planeA's one-hot rows),  V_s < 256^S (S base-256 digits in planeB)
+// and approximates w_s 2^q.  All arithmetic on wq is exact (int32 accumulators: N * 255 * 255 < 2^31; the digit sums are
+// recombined in int64), so results are bit-reproducible functions of wq; (u_s, V_s) is the pair minimising
+// |w_s 2^q - u V| over u, which buys ~6 more bits than V alone for the same number of slices.  Integer weights <= 255
+// with S = 1 (and the unit weights of the RAF tables) are exact with u = 1, q = 0.
 int quantise(rsb_ctx *ctx, Geo &g, const std::vector<double> &w, bool unit)
 {
   const int N = ctx->N, S = g.S;
   g.wq.assign(N, 1);
   g.q = 0;
+  g.qerr_abs = 0.0; g.maxw = 1.0;
+  std::vector<uint8_t> mul(N, 1);
+  std::vector<long long> V(N, 1);
   if (!unit) {
     double maxw = 0.0;
     for (int s = 0; s < N; s++) {
       if (!(w[s] >= 0.0) || !std::isfinite(w[s])) { rsb_set_error(ctx, "sequence weight %d is negative or not finite", s); return 1; }
       maxw = std::max(maxw, w[s]);
     }
+    g.maxw = maxw;
     bool small_int = true;
     for (int s = 0; s < N && small_int; s++) small_int = (w[s] == std::floor(w[s]) && w[s] <= 255.0);
-    if (small_int && S == 1) g.q = 0;
-    else if (maxw > 0.0) {
-      int e; std::frexp(maxw, &e);                     // maxw < 2^e
-      g.q = 8 * S - e;
-      for (;;) {
-        bool ok = true;
-        for (int s = 0; s < N && ok; s++) ok = std::llround(std::ldexp(w[s], g.q)) < (1LL << (8 * S));
-        if (ok) break;
-        g.q--;
+    const long long vlim = (S >= 8) ? (1LL << 62) : (1LL << (8 * S));                    // V < vlim
+    if (small_int && S == 1) {
+      for (int s = 0; s < N; s++) V[s] = (long long) w[s];
+    } else if (maxw > 0.0) {
+      const long long acc_cap = 2147483647LL / (255LL * std::max(ctx->Kpad, 1));        // keeps sum_s u_s d_s inside int32
+      int umax = (int) std::max(1LL, std::min(255LL, acc_cap));
+      for (;; umax = std::max(1, umax / 2)) {
+        int e; std::frexp(maxw, &e);                                                     // maxw < 2^e
+        int eu = 0; while ((2 << eu) <= umax) eu++;                                      // 2^eu <= umax
+        g.q = 8 * S + eu - e;
+        while (std::ldexp((long double) maxw, g.q) > (long double) umax * (long double) (vlim - 1)) g.q--;
+        long double tot = 0.0L;
+        g.qerr_abs = 0.0;
+        const bool fast = std::ldexp(maxw, g.q) < 1125899906842624.0;                     // W < 2^50: doubles are exact enough
+        double inv_u[256]; for (int u = 1; u <= umax; u++) inv_u[u] = 1.0 / u;
+        for (int s = 0; s < N; s++) {
+          int ub = 1; long long vb = 0; long double best = -1.0L;
+          if (fast) {
+            // |W - u v| with v = W/u rounded by the 2^52 trick (a multiply instead of a divide: a v off by one near .5 only
+            // makes that candidate look worse); u v < 2^53 is exact, and the loop vectorises
+            const double W = std::ldexp(w[s], g.q);
+            const double vmax = (double) (vlim - 1);
+            double be = 1e300;
+            for (int u = 1; u <= umax; u++) {
+              const double v = (W * inv_u[u] + 6755399441055744.0) - 6755399441055744.0;
+              const double err = (v <= vmax) ? std::fabs(W - u * v) : 1e300;
+              if (err < be) { be = err; ub = u; }
+            }
+            if (be < 1e300) { vb = (long long) ((W * inv_u[ub] + 6755399441055744.0) - 6755399441055744.0); best = (long double) be; }
+          } else {
+            const long double W = std::ldexp((long double) w[s], g.q);
+            for (int u = 1; u <= umax; u++) {
+              const long double v = std::nearbyint(W / u);
+              if (v >= (long double) vlim) continue;
+              const long double err = std::fabs(W - u * v);
+              if (best < 0.0L || err < best) { best = err; ub = u; vb = (long long) v; }
+            }
+          }
+          if (best < 0.0L) { rsb_set_error(ctx, "internal: weight %d not representable", s); return 1; }
+          mul[s] = (uint8_t) ub; V[s] = vb;
+          g.qerr_abs = std::max(g.qerr_abs, (double) std::ldexp(best, -g.q));
+          tot += (long double) mul[s] * (long double) V[s];
+        }
+        if (tot < 4.0e18L) break;                                                        // every count <= wtot < 2^62
+        if (umax == 1) { rsb_set_error(ctx, "%d weight slices with %d sequences overflow the 63-bit count (use fewer slices)", S, N); return 1; }
       }
     }
-    for (int s = 0; s < N; s++) g.wq[s] = std::llround(std::ldexp(w[s], g.q));
+    for (int s = 0; s < N; s++) g.wq[s] = (long long) mul[s] * V[s];
   }
-  int nbits = 0; while ((1LL << nbits) < (long long) N + 1) nbits++;
-  if (8 * S + nbits > 63) { rsb_set_error(ctx, "%d weight slices with %d sequences overflow the 63-bit count (use fewer slices)", S, N); return 1; }
   g.scale = std::ldexp(1.0, -g.q);
   g.wtot = 0;
-  std::vector<uint8_t> dig((size_t) S * ctx->Kpad, 0);
+  std::vector<uint8_t> dig((size_t) (S + 1) * ctx->Kpad, 0);                             // rows 0..S-1: digits of V, row S: u
   for (int s = 0; s < N; s++) {
     g.wtot += g.wq[s];
-    for (int k = 0; k < S; k++) dig[(size_t) k * ctx->Kpad + s] = (uint8_t) ((g.wq[s] >> (8 * k)) & 0xFF);
+    for (int k = 0; k < S; k++) dig[(size_t) k * ctx->Kpad + s] = (uint8_t) ((V[s] >> (8 * k)) & 0xFF);
+    dig[(size_t) S * ctx->Kpad + s] = mul[s];
   }
   RSB_CUDA_OK(cudaMemcpyAsync(g.d_wdig, dig.data(), dig.size(), cudaMemcpyHostToDevice, ctx->stream));
   RSB_CUDA_OK(cudaMemcpyAsync(g.d_wq, g.wq.data(), sizeof(long long) * N, cudaMemcpyHostToDevice, ctx->stream));
@@ -305,8 +357,11 @@ int enqueue_gram(rsb_ctx *ctx, int which, int s0, int nrep, cudaStream_t st)
     const int grid = (int) std::min<long long>(work, ctx->sm_count);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (ctx->profile) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
+    // the weighted geometry also emits the marginal partial sums of every tile (slot-indexed like the counts)
+    double *mrow = (which == 0) ? ctx->d_mrow : nullptr, *mcol = (which == 0) ? ctx->d_mcol : nullptr;
+    if (which == 0 && ((size_t) g.nJB * ctx->L * 4 > ctx->mrow_stride)) { rsb_set_error(ctx, "internal: marginal partial capacity"); return 1; }
     RSB_CUDA_OK(rsb_launch_gram_i8(g.S, ctx->tmA, g.tmB, g.d_tiles, g.ntiles, s0, nrep, ctx->L, ctx->Lp, ctx->Kpad / RSB_KSTAGE,
-                                   ctx->d_cnt, grid, st));
+                                   ctx->d_cnt, g.scale, mrow, mcol, g.nJB, ctx->nIB, grid, st));
     if (ctx->profile) { cudaEventRecord(e1, st); ctx->pending.push_back({ e0, e1 }); }
     ctx->launches++;
     ctx->gram_launches++;
@@ -379,24 +434,25 @@ SlotPtrs slot_ptrs(rsb_ctx *c, int s0)
 int enqueue_marginals(rsb_ctx *ctx, int s0, int nrep, double tol, cudaStream_t st, int phase = 3)
 {
   Geo &g = ctx->geo[0];
-  int nJT, nIT; rsb_stat_grid(ctx->L, &nJT, &nIT);
   SlotPtrs p = slot_ptrs(ctx, s0);
-  RSB_CUDA_OK(rsb_launch_marginals(p.cnt, nrep, ctx->L, ctx->Lp, g.scale, g.wtot, tol, ctx->d_rowpart + (size_t) s0 * nJT * ctx->L * 4,
-                                   ctx->d_colpart + (size_t) s0 * nIT * ctx->L * 4, p.nseff, p.msum, p.pm, ctx->d_flags,
+  // partials are addressed [r][block][L][4] with r the absolute slot, as the gram kernel wrote them
+  RSB_CUDA_OK(rsb_launch_marginals(ctx->d_mrow + (size_t) s0 * g.nJB * ctx->L * 4, ctx->d_mcol + (size_t) s0 * 4 * ctx->nIB * ctx->L * 4,
+                                   nrep, ctx->L, g.CJ, g.nJB, ctx->nIB, tol, p.msum, p.pm, ctx->d_flags,
                                    ctx->shard_rank, ctx->shard_world, phase, st));
-  ctx->launches += (phase == 3) ? 3 : (phase == 1 ? 2 : 1);
+  ctx->launches += (phase == 3) ? 2 : 1;
   return 0;
 }
 
 // statistic on the counts of slots [s0, s0+nrep); leaves raw cov and (phase bit 1) the reduced sums covsum, (phase bit 2)
 // COVx, COVavg and the raw min/max
-int enqueue_statistic(rsb_ctx *ctx, int s0, int nrep, int stat, int covclass, unsigned mask, cudaStream_t st, int phase = 3)
+int enqueue_statistic(rsb_ctx *ctx, int s0, int nrep, int stat, int covclass, unsigned mask, cudaStream_t st, int phase = 3, int part = 3)
 {
+  // part: 1 = the statistic kernel(s) only, 2 = the reductions of its partial sums only, 3 = both
   Geo &g = ctx->geo[ctx->cur_geo];
   int nJT, nIT; rsb_stat_grid(ctx->L, &nJT, &nIT);
   SlotPtrs p = slot_ptrs(ctx, s0);
   double *rowpart = ctx->d_rowpart + (size_t) s0 * nJT * ctx->L, *colpart = ctx->d_colpart + (size_t) s0 * nIT * ctx->L;
-  if (phase & 1) {
+  if ((phase & 1) && (part & 1)) {
     if (stat == RSB_RAF || stat == RSB_RAFS) {
       if (ctx->cur_geo != 1) { rsb_set_error(ctx, "internal: RAF needs unit-weight counts"); return 1; }
       if (ctx->shard_world > 1) { rsb_set_error(ctx, "RAF/RAFS are not available with a sharded pair grid"); return 1; }
@@ -404,16 +460,19 @@ int enqueue_statistic(rsb_ctx *ctx, int s0, int nrep, int stat, int covclass, un
       ctx->launches += (stat == RSB_RAFS) ? 3 : 2;
     } else if (stat == RSB_CCF) {
       if (ctx->shard_world > 1) { rsb_set_error(ctx, "CCF is not available with a sharded pair grid"); return 1; }
+      RSB_CUDA_OK(rsb_launch_nseff(p.cnt, nrep, ctx->L, ctx->Lp, ctx->geo[0].scale, p.nseff, st));
       RSB_CUDA_OK(rsb_launch_ccf(p.nseff, p.pm, nrep, ctx->L, ctx->Lp, p.tmp, p.meanp, p.cov, rowpart, colpart, p.mm, st));
-      ctx->launches += 4;
+      ctx->launches += 5;
     } else {
-      RSB_CUDA_OK(rsb_launch_statistic(stat, covclass, p.cnt, p.pm, nrep, ctx->L, ctx->Lp, g.scale, g.wtot, mask, p.cov, rowpart, colpart, p.mm,
+      RSB_CUDA_OK(rsb_launch_statistic(stat, covclass, p.cnt, p.pm, ctx->d_logtab, nrep, ctx->L, ctx->Lp, g.scale, g.wtot, mask, p.cov, rowpart, colpart, p.mm,
                                        ctx->shard_rank, ctx->shard_world, st));
       ctx->launches++;
     }
   }
-  RSB_CUDA_OK(rsb_launch_correct_final(rowpart, colpart, p.mm, nrep, ctx->L, p.covx, p.scal, p.blocksum, p.covsum, phase, st));
-  ctx->launches += (phase == 3) ? 3 : (phase == 1 ? 2 : 1);
+  if (part & 2) {
+    RSB_CUDA_OK(rsb_launch_correct_final(rowpart, colpart, p.mm, nrep, ctx->L, p.covx, p.scal, p.blocksum, p.covsum, phase, st));
+    ctx->launches += (phase == 3) ? 3 : (phase == 1 ? 2 : 1);
+  }
   return 0;
 }
 
@@ -487,6 +546,13 @@ int rsb_create(int device, void *stream, rsb_ctx **out)
     cudaEventCreateWithFlags(&c->ev_up[g], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->ev_counts[g], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->ev_stats[g], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_marg[g], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_statk[g], cudaEventDisableTiming);
+  }
+  if (cudaMalloc(&c->d_logtab, rsb_logtab_bytes()) != cudaSuccess || rsb_launch_logtab(c->d_logtab, c->stream) != cudaSuccess ||
+      cudaStreamSynchronize(c->stream) != cudaSuccess) {
+    snprintf(g_create_err, sizeof(g_create_err), "rsb_create: log table: %s", cudaGetErrorString(cudaGetLastError()));
+    delete c; return 1;
   }
   *out = c;
   return 0;
@@ -501,10 +567,11 @@ void rsb_destroy(rsb_ctx *ctx)
   for (auto &p : ctx->pending_aux) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   for (auto &p : ctx->pending_stage) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   free_plan(ctx);
+  if (ctx->d_logtab) cudaFree(ctx->d_logtab);
   cudaStreamSynchronize(ctx->stream_aux); cudaStreamSynchronize(ctx->stream_copy);
   cudaStreamDestroy(ctx->stream_aux); cudaStreamDestroy(ctx->stream_copy);
   cudaEventDestroy(ctx->ev_entry);
-  for (int g = 0; g < 2; g++) { cudaEventDestroy(ctx->ev_up[g]); cudaEventDestroy(ctx->ev_counts[g]); cudaEventDestroy(ctx->ev_stats[g]); }
+  for (int g = 0; g < 2; g++) { cudaEventDestroy(ctx->ev_up[g]); cudaEventDestroy(ctx->ev_counts[g]); cudaEventDestroy(ctx->ev_stats[g]); cudaEventDestroy(ctx->ev_marg[g]); cudaEventDestroy(ctx->ev_statk[g]); }
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -521,11 +588,12 @@ int rsb_configure(rsb_ctx *ctx, int nseq, int alen, int max_replicates, int nsli
   ctx->nIB  = (alen + RSB_ICOLS - 1) / RSB_ICOLS;
   ctx->MA   = ctx->nIB * RSB_MTILE;
   // planeB must hold the widest geometry (any S in 1..6); rows = nJB * NT
-  size_t rows_cap = 0; int lcover = ctx->nIB * RSB_ICOLS;
+  size_t rows_cap = 0; int lcover = ctx->nIB * RSB_ICOLS, njb_cap = 0;
   for (int S = 1; S <= RSB_MAX_SLICES; S++) {
     if (nslices && S != nslices && S != 1) continue;
     const int CJ = rsb_cj_for(S), nJB = (alen + CJ - 1) / CJ;
     rows_cap = std::max(rows_cap, (size_t) nJB * 4 * S * CJ);
+    njb_cap  = std::max(njb_cap, nJB);
     lcover = std::max(lcover, nJB * CJ);
   }
   ctx->planeB_rows_cap = rows_cap;
@@ -541,8 +609,11 @@ int rsb_configure(rsb_ctx *ctx, int nseq, int alen, int max_replicates, int nsli
   RSB_CUDA_OK(cudaMalloc(&ctx->d_cov, R * L * Lp * sizeof(double)));
   RSB_CUDA_OK(cudaMalloc(&ctx->d_tmp, std::max(R * L * Lp, R * (size_t) nJT * nIT * 4) * sizeof(double)));
   RSB_CUDA_OK(cudaMalloc(&ctx->d_pm, R * L * 4 * sizeof(double)));
-  RSB_CUDA_OK(cudaMalloc(&ctx->d_rowpart, R * nJT * L * 4 * sizeof(double)));
-  RSB_CUDA_OK(cudaMalloc(&ctx->d_colpart, R * nIT * L * 4 * sizeof(double)));
+  RSB_CUDA_OK(cudaMalloc(&ctx->d_rowpart, R * nJT * L * sizeof(double)));
+  RSB_CUDA_OK(cudaMalloc(&ctx->d_colpart, R * nIT * L * sizeof(double)));
+  ctx->mrow_stride = (size_t) njb_cap * L * 4; ctx->mcol_stride = (size_t) 4 * ctx->nIB * L * 4;
+  RSB_CUDA_OK(cudaMalloc(&ctx->d_mrow, R * ctx->mrow_stride * sizeof(double)));
+  RSB_CUDA_OK(cudaMalloc(&ctx->d_mcol, R * ctx->mcol_stride * sizeof(double)));
   RSB_CUDA_OK(cudaMalloc(&ctx->d_mm, R * nJT * nIT * 2 * sizeof(double)));
   RSB_CUDA_OK(cudaMalloc(&ctx->d_scal, R * 4 * sizeof(double)));
   RSB_CUDA_OK(cudaMalloc(&ctx->d_covx, R * L * sizeof(double)));
@@ -577,7 +648,7 @@ int rsb_set_weights(rsb_ctx *ctx, const double *wgt)
   if (S == 0) {
     bool small_int = true;
     for (int s = 0; s < ctx->N && small_int; s++) small_int = (ctx->wgt[s] >= 0 && ctx->wgt[s] == std::floor(ctx->wgt[s]) && ctx->wgt[s] <= 255.0);
-    S = small_int ? 1 : 5;
+    S = small_int ? 1 : 4;
   }
   Geo &g = ctx->geo[0];
   if (g.S != S || !g.d_tiles) { if (build_geo(ctx, g, S)) return 1; }
@@ -591,6 +662,15 @@ int rsb_get_quantisation(rsb_ctx *ctx, int64_t *wq, int *q, int *nslices)
   if (wq) for (int s = 0; s < ctx->N; s++) wq[s] = g.wq[s];
   if (q) *q = g.q;
   if (nslices) *nslices = g.S;
+  return 0;
+}
+
+int rsb_get_quantisation_error(rsb_ctx *ctx, double *max_abs_err, double *effective_bits)
+{
+  Geo &g = ctx->geo[0];
+  if (!g.ready) { rsb_set_error(ctx, "rsb_set_weights has not been called"); return 1; }
+  if (max_abs_err) *max_abs_err = g.qerr_abs;
+  if (effective_bits) *effective_bits = (g.qerr_abs > 0.0) ? std::log2(g.maxw / g.qerr_abs) : 64.0;
   return 0;
 }
 
@@ -790,6 +870,32 @@ static int null_hist_pipelined(rsb_ctx *ctx, const uint8_t *nulls, int nrep, int
   RSB_CUDA_OK(cudaStreamWaitEvent(st_copy, ctx->ev_entry, 0));
   bool used[2] = { false, false };
 
+  // Stream plan.  The statistic kernel is FP64-bound, and FP64 issue collapses (~6x, measured) while the tensor pipe is
+  // busy, so it runs ALONE on the main stream between two contractions; everything light (operand packing on the copy
+  // stream; marginal sums, reductions, correction + histogram on the aux stream) runs beside the contraction.
+  //   main:  G(0) G(1) S(0) G(2) S(1) ...      aux:  M(c) after G(c);  R(c) + C(c) after S(c)
+  auto tail = [&](int pc, int pr0) -> int {                         // S(pc) on main, then its reductions/correction on aux
+    const int pg = pc % G, ps0 = pg * chunk, pn = std::min(chunk, nrep - pr0);
+    cudaEvent_t a0 = nullptr, a1 = nullptr, am = nullptr, as = nullptr;
+    if (ctx->profile) { cudaEventCreate(&a0); cudaEventCreate(&a1); cudaEventCreate(&am); cudaEventCreate(&as); }
+    RSB_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->ev_marg[pg], 0));
+    if (pc >= G) RSB_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->ev_stats[pg], 0));   // the group's scores and partial sums have been consumed
+    if (ctx->profile) cudaEventRecord(a0, ctx->stream);
+    if (enqueue_statistic(ctx, ps0, pn, stat, covclass, mask, ctx->stream, 3, 1)) return 1;
+    if (ctx->profile) cudaEventRecord(am, ctx->stream);
+    RSB_CUDA_OK(cudaEventRecord(ctx->ev_statk[pg], ctx->stream));
+    RSB_CUDA_OK(cudaStreamWaitEvent(st_aux, ctx->ev_statk[pg], 0));
+    if (ctx->profile) cudaEventRecord(as, st_aux);
+    if (enqueue_statistic(ctx, ps0, pn, stat, covclass, mask, st_aux, 3, 2)) return 1;
+    if (enqueue_correct(ctx, ps0, pn, actype, 2, bmin, st_aux)) return 1;
+    if (minmax) RSB_CUDA_OK(cudaMemcpyAsync(ctx->h_mm + 2 * (size_t) pr0, ctx->d_minmax + 2 * (size_t) ps0, sizeof(double) * 2 * pn,
+                                            cudaMemcpyDeviceToHost, st_aux));
+    if (ctx->profile) { cudaEventRecord(a1, st_aux); ctx->pending_aux.push_back({ a0, a1 }); ctx->pending_stage.push_back({ am, as }); ctx->aux_chains++; }
+    RSB_CUDA_OK(cudaEventRecord(ctx->ev_stats[pg], st_aux));
+    if (w > 0.0) ctx->hist_n += (unsigned long long) pn * ((unsigned long long) ctx->L * (ctx->L - 1) / 2);
+    return 0;
+  };
+
   int c = 0;
   for (int r0 = 0; r0 < nrep; r0 += chunk, c++) {
     const int g = c % G, s0 = g * chunk, n = std::min(chunk, nrep - r0);
@@ -803,25 +909,18 @@ static int null_hist_pipelined(rsb_ctx *ctx, const uint8_t *nulls, int nrep, int
     if (enqueue_pack(ctx, raf ? 1 : 0, s0, n, src, st_copy)) return 1;                   // HBM-bound transpose: hides under the previous gram
     RSB_CUDA_OK(cudaEventRecord(ctx->ev_up[g], st_copy));
     RSB_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->ev_up[g], 0));
-    if (used[g]) RSB_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->ev_stats[g], 0));               // counts of this group have been consumed
+    // (the counts and marginal partials of this group were consumed by S(c - G), earlier on this stream)
     if (enqueue_gram(ctx, raf ? 1 : 0, s0, n, ctx->stream)) return 1;
     RSB_CUDA_OK(cudaEventRecord(ctx->ev_counts[g], ctx->stream));
 
     RSB_CUDA_OK(cudaStreamWaitEvent(st_aux, ctx->ev_counts[g], 0));
-    cudaEvent_t a0 = nullptr, a1 = nullptr, am = nullptr, as = nullptr;
-    if (ctx->profile) { cudaEventCreate(&a0); cudaEventCreate(&a1); cudaEventCreate(&am); cudaEventCreate(&as); cudaEventRecord(a0, st_aux); }
     if (!raf && enqueue_marginals(ctx, s0, n, tol, st_aux)) return 1;
-    if (ctx->profile) cudaEventRecord(am, st_aux);
-    if (enqueue_statistic(ctx, s0, n, stat, covclass, mask, st_aux)) return 1;
-    if (ctx->profile) cudaEventRecord(as, st_aux);
-    if (enqueue_correct(ctx, s0, n, actype, 2, bmin, st_aux)) return 1;
-    if (minmax) RSB_CUDA_OK(cudaMemcpyAsync(ctx->h_mm + 2 * (size_t) r0, ctx->d_minmax + 2 * (size_t) s0, sizeof(double) * 2 * n,
-                                            cudaMemcpyDeviceToHost, st_aux));
-    if (ctx->profile) { cudaEventRecord(a1, st_aux); ctx->pending_aux.push_back({ a0, a1 }); ctx->pending_stage.push_back({ am, as }); ctx->aux_chains++; }
-    RSB_CUDA_OK(cudaEventRecord(ctx->ev_stats[g], st_aux));
+    RSB_CUDA_OK(cudaEventRecord(ctx->ev_marg[g], st_aux));
     used[g] = true;
-    if (w > 0.0) ctx->hist_n += (unsigned long long) n * ((unsigned long long) ctx->L * (ctx->L - 1) / 2);
+    if (G == 1) { if (tail(c, r0)) return 1; }
+    else if (c >= 1) { if (tail(c - 1, r0 - chunk)) return 1; }
   }
+  if (G > 1 && c >= 1) { if (tail(c - 1, (c - 1) * chunk)) return 1; }
   for (int g = 0; g < G; g++) if (used[g]) RSB_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->ev_stats[g], 0));
   return 0;
 }
@@ -1197,7 +1296,7 @@ int rsb_counters(rsb_ctx *ctx, int64_t *launches, double *gram_ms, int64_t *gram
   if (gram_launches) *gram_launches = ctx->gram_launches;
   if (getenv("RSCAPE_B200_TRACE")) {
     const double na = ctx->aux_chains ? (double) ctx->aux_chains : 1.0;
-    fprintf(stderr, "[rsb] gram %.3f ms x %lld, statistics chain %.3f ms x %lld (marginals %.3f, statistic %.3f, correct+hist %.3f)\n",
+    fprintf(stderr, "[rsb] gram %.3f ms x %lld, statistics chain %.3f ms x %lld (statistic %.3f, gap %.3f, reductions+correct+hist %.3f)\n",
             ctx->gram_launches ? ctx->gram_ms / ctx->gram_launches : 0.0, ctx->gram_launches, ctx->aux_ms / na, ctx->aux_chains,
             ctx->stage_ms[0] / na, ctx->stage_ms[1] / na, ctx->stage_ms[2] / na);
   }

@@ -86,7 +86,7 @@ template <int S>
 __global__ void __launch_bounds__(GRAM_THREADS, 1)
 gram_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
                const int2 *__restrict__ tiles, int ntiles, int rep0, int nrep, int L, int Lp, int kstages,
-               long long *__restrict__ cnt)
+               long long *__restrict__ cnt, double scale, double *__restrict__ mrow, double *__restrict__ mcol, int nJB, int nIB)
 {
   constexpr int      CJ          = rsb_cj_for(S);
   constexpr int      NT          = 4 * S * CJ;                 // UMMA N
@@ -187,6 +187,7 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t) (ew * 32) << 16) + (uint32_t) acc * 256u;
 
+      double racc = 0.0;                                           // marginal partial of row (i, a) over this tile's columns
       #pragma unroll 1
       for (int jl = 0; jl < CJ; jl += 2) {
         uint32_t d[2][S][4];
@@ -208,22 +209,66 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
             for (int k = S - 1; k >= 0; k--) v = (v << 8) + (unsigned long long) d[u][k][b];
             c[u][b] = v;
           }
-        if (i < L) {
-          const bool ok0 = (j0 < L)     && (i < j0);
-          const bool ok1 = (j0 + 1 < L) && (i < j0 + 1);
-          if (ok0 && ok1) {
-            #pragma unroll
-            for (int b = 0; b < 4; b++)
-              *reinterpret_cast<ulonglong2 *>(base + b * plane + j0) = make_ulonglong2(c[0][b], c[1][b]);
-          } else {
-            #pragma unroll
-            for (int b = 0; b < 4; b++) {
-              if (ok0) base[b * plane + j0]     = (long long) c[0][b];
-              if (ok1) base[b * plane + j0 + 1] = (long long) c[1][b];
-            }
+        const bool ok0 = (i < L) && (j0 < L)     && (i < j0);
+        const bool ok1 = (i < L) && (j0 + 1 < L) && (i < j0 + 1);
+        if (ok0 && ok1) {
+          #pragma unroll
+          for (int b = 0; b < 4; b++)
+            *reinterpret_cast<ulonglong2 *>(base + b * plane + j0) = make_ulonglong2(c[0][b], c[1][b]);
+        } else {
+          #pragma unroll
+          for (int b = 0; b < 4; b++) {
+            if (ok0) base[b * plane + j0]     = (long long) c[0][b];
+            if (ok1) base[b * plane + j0 + 1] = (long long) c[1][b];
           }
         }
+
+        if (mrow != nullptr) {
+          // marginal partials (corr_Probs :1713-1758 + corr_Marginals :1335-1370, the per-pair part): the 16 cells of a
+          // pair sit in 4 adjacent lanes (a = lane & 3) x 4 registers (b).  pp = (1e-10 + c scale) / sum; pairs with
+          // nseff = 0 are skipped (:1354).  Fixed shuffle trees => deterministic.
+          double x[2][4];
+          #pragma unroll
+          for (int u = 0; u < 2; u++) {
+            #pragma unroll
+            for (int b = 0; b < 4; b++) x[u][b] = fma(u64_to_f64(c[u][b]), scale, 1e-10);
+            const double rs = (x[u][0] + x[u][1]) + (x[u][2] + x[u][3]);
+            double sum = rs;
+            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+            const unsigned nz  = __ballot_sync(0xffffffffu, (c[u][0] | c[u][1] | c[u][2] | c[u][3]) != 0ULL);
+            const bool     use = (u ? ok1 : ok0) && ((nz >> (lane & ~3)) & 0xFu) != 0u;
+            const double   inv = use ? 1.0 / sum : 0.0;
+            racc = fma(rs, inv, racc);
+            #pragma unroll
+            for (int b = 0; b < 4; b++) x[u][b] *= inv;
+          }
+          // column partials: 8 values (u, b) summed over the warp's 32 lanes by a halving butterfly -- after the three
+          // halving steps a lane keeps (u, b) = (bit 4, bits 3:2 of its lane id), then two full steps sum over a
+          const bool h4 = lane & 16, h3 = lane & 8, h2 = lane & 4;
+          double y[4], z[2], v1;
+          #pragma unroll
+          for (int b = 0; b < 4; b++) {
+            const double keep = h4 ? x[1][b] : x[0][b], send = h4 ? x[0][b] : x[1][b];
+            y[b] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+          }
+          #pragma unroll
+          for (int q = 0; q < 2; q++) {
+            const double keep = h3 ? y[2 + q] : y[q], send = h3 ? y[q] : y[2 + q];
+            z[q] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+          }
+          {
+            const double keep = h2 ? z[1] : z[0], send = h2 ? z[0] : z[1];
+            v1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+          }
+          v1 += __shfl_xor_sync(0xffffffffu, v1, 2);
+          v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
+          const int jw = j0 + (h4 ? 1 : 0);
+          if ((lane & 3) == 0 && jw < L)
+            mcol[(((size_t) r * 4 * nIB + (size_t) t.x * 4 + ew) * L + jw) * 4 + ((h3 ? 2 : 0) + (h2 ? 1 : 0))] = v1;
+        }
       }
+      if (mrow != nullptr && i < L) mrow[(((size_t) r * nJB + t.y) * L + i) * 4 + a] = racc;
       tc_fence_before();
       mbar_arrive(tempty_bar(acc));
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
@@ -247,7 +292,8 @@ template <int S> constexpr size_t gram_smem_bytes() {
 
 template <int S>
 cudaError_t launch_gram(const CUtensorMap &tmA, const CUtensorMap &tmB, const int2 *tiles, int ntiles, int rep0, int nrep,
-                        int L, int Lp, int kstages, long long *cnt, int grid, cudaStream_t st)
+                        int L, int Lp, int kstages, long long *cnt, double scale, double *mrow, double *mcol, int nJB, int nIB,
+                        int grid, cudaStream_t st)
 {
   constexpr size_t smem = gram_smem_bytes<S>();
   cudaError_t e = cudaFuncSetAttribute(gram_i8_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
@@ -255,7 +301,7 @@ cudaError_t launch_gram(const CUtensorMap &tmA, const CUtensorMap &tmB, const in
   // the ring takes ~190 KB; with the SM's carve-out at its maximum (228 KB) the rest is left for the blocks of the
   // statistics chain, which run beside this kernel (a 196 KB carve-out would leave them no shared memory at all)
   rsb_coreside(gram_i8_kernel<S>);
-  gram_i8_kernel<S><<<grid, GRAM_THREADS, smem, st>>>(tmA, tmB, tiles, ntiles, rep0, nrep, L, Lp, kstages, cnt);
+  gram_i8_kernel<S><<<grid, GRAM_THREADS, smem, st>>>(tmA, tmB, tiles, ntiles, rep0, nrep, L, Lp, kstages, cnt, scale, mrow, mcol, nJB, nIB);
   return cudaGetLastError();
 }
 
@@ -264,15 +310,16 @@ cudaError_t launch_gram(const CUtensorMap &tmA, const CUtensorMap &tmB, const in
 // Host entry used by capi.cu.  tmA/tmB are 3-D tensor maps {Kpad, rows, replicate} with 128B swizzle
 // and boxes {128, 128, 1} / {128, 4*S*CJ, 1}.
 cudaError_t rsb_launch_gram_i8(int S, const CUtensorMap &tmA, const CUtensorMap &tmB, const int2 *tiles, int ntiles,
-                               int rep0, int nrep, int L, int Lp, int kstages, long long *cnt, int grid, cudaStream_t st)
+                               int rep0, int nrep, int L, int Lp, int kstages, long long *cnt, double scale, double *mrow,
+                               double *mcol, int nJB, int nIB, int grid, cudaStream_t st)
 {
   switch (S) {
-  case 1: return launch_gram<1>(tmA, tmB, tiles, ntiles, rep0, nrep, L, Lp, kstages, cnt, grid, st);
-  case 2: return launch_gram<2>(tmA, tmB, tiles, ntiles, rep0, nrep, L, Lp, kstages, cnt, grid, st);
-  case 3: return launch_gram<3>(tmA, tmB, tiles, ntiles, rep0, nrep, L, Lp, kstages, cnt, grid, st);
-  case 4: return launch_gram<4>(tmA, tmB, tiles, ntiles, rep0, nrep, L, Lp, kstages, cnt, grid, st);
-  case 5: return launch_gram<5>(tmA, tmB, tiles, ntiles, rep0, nrep, L, Lp, kstages, cnt, grid, st);
-  case 6: return launch_gram<6>(tmA, tmB, tiles, ntiles, rep0, nrep, L, Lp, kstages, cnt, grid, st);
+  case 1: return launch_gram<1>(tmA, tmB, tiles, ntiles, rep0, nrep, L, Lp, kstages, cnt, scale, mrow, mcol, nJB, nIB, grid, st);
+  case 2: return launch_gram<2>(tmA, tmB, tiles, ntiles, rep0, nrep, L, Lp, kstages, cnt, scale, mrow, mcol, nJB, nIB, grid, st);
+  case 3: return launch_gram<3>(tmA, tmB, tiles, ntiles, rep0, nrep, L, Lp, kstages, cnt, scale, mrow, mcol, nJB, nIB, grid, st);
+  case 4: return launch_gram<4>(tmA, tmB, tiles, ntiles, rep0, nrep, L, Lp, kstages, cnt, scale, mrow, mcol, nJB, nIB, grid, st);
+  case 5: return launch_gram<5>(tmA, tmB, tiles, ntiles, rep0, nrep, L, Lp, kstages, cnt, scale, mrow, mcol, nJB, nIB, grid, st);
+  case 6: return launch_gram<6>(tmA, tmB, tiles, ntiles, rep0, nrep, L, Lp, kstages, cnt, scale, mrow, mcol, nJB, nIB, grid, st);
   }
   return cudaErrorInvalidValue;
 }

@@ -46,13 +46,20 @@ pack_planes_kernel(const uint8_t *__restrict__ res, int N, int L, long long rep_
   for (int q = 0; q < 16; q++) x[q] = tile[chunk * 16 + q][threadIdx.x >> 3];
 
   const size_t koff = (size_t) s0 + chunk * 16;
-  // planeA: four one-hot rows
+  // planeA: four one-hot rows carrying the 8-bit weight multiplier u_s (row S of wdig; 1 for unit / integer weights)
   if (4 * col < MA) {
+    const uint4 ug = *reinterpret_cast<const uint4 *>(wdig + (size_t) S * Kpad + koff);
+    const uint32_t uw[4] = { ug.x, ug.y, ug.z, ug.w };
     #pragma unroll
     for (int a = 0; a < 4; a++) {
-      uint32_t wv[4] = { 0, 0, 0, 0 };
+      uint32_t wv[4];
       #pragma unroll
-      for (int q = 0; q < 16; q++) wv[q >> 2] |= (uint32_t) (x[q] == a) << (8 * (q & 3));
+      for (int g = 0; g < 4; g++) {
+        uint32_t m = 0;
+        #pragma unroll
+        for (int q = 0; q < 4; q++) m |= (x[4 * g + q] == a ? 0xFFu : 0u) << (8 * q);
+        wv[g] = uw[g] & m;
+      }
       *reinterpret_cast<uint4 *>(planeA + ((size_t) r * MA + 4 * col + a) * Kpad + koff) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
     }
   }

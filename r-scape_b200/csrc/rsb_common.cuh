@@ -51,6 +51,23 @@ template <typename K> static inline void rsb_coreside(K kernel)
   cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int) cudaSharedmemCarveoutMaxShared);
 }
 
+// exact uint64 -> double without the slow 64-bit I2F path: both 32-bit halves are planted in the mantissa of a
+// power of two and the offsets subtracted (each half exact, one rounding in the final add = the I2F result)
+__device__ __forceinline__ double u64_to_f64(unsigned long long v)
+{
+  const double lo = __longlong_as_double(0x4330000000000000ULL | (v & 0xffffffffULL)) - 4503599627370496.0;              // 2^52
+  const double hi = __longlong_as_double(0x4530000000000000ULL | (v >> 32))           - 19342813113834066795298816.0;   // 2^84
+  return hi + lo;
+}
+
+// does the gram tile (ib, jb) exist?  Same rule as build_geo (capi.cu): it holds some pair i < j and its row block is
+// owned by this rank
+__host__ __device__ __forceinline__ bool rsb_tile_exists(int ib, int jb, int CJ, int L, int sr, int sw)
+{
+  const int maxj = (jb * CJ + CJ - 1 < L - 1) ? jb * CJ + CJ - 1 : L - 1;
+  return ib * RSB_ICOLS < maxj && (sw <= 1 || ib % sw == sr);
+}
+
 #ifdef RSB_BLOCKTRACE
 // experiment: per-block (kernel id, SM, start, end) records, to see which kernels really share an SM
 __device__ __forceinline__ unsigned long long rsb_gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }

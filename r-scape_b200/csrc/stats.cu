@@ -26,15 +26,6 @@ constexpr int ST_TJ = RSB_TJ;
 
 struct PairProbs { double pp[16]; double ne; double ng; };
 
-// exact uint64 -> double without the slow 64-bit I2F path: both 32-bit halves are planted in the mantissa of a
-// power of two and the offsets subtracted (each half exact, one rounding in the final add = the I2F result)
-__device__ __forceinline__ double u64_to_f64(unsigned long long v)
-{
-  const double lo = __longlong_as_double(0x4330000000000000ULL | (v & 0xffffffffULL)) - 4503599627370496.0;              // 2^52
-  const double hi = __longlong_as_double(0x4530000000000000ULL | (v >> 32))           - 19342813113834066795298816.0;   // 2^84
-  return hi + lo;
-}
-
 // counts below 2^52 (the whole alignment's weight is: wtot < 2^52, checked by the caller) convert with one subtraction
 __device__ __forceinline__ double u52_to_f64(unsigned long long v)
 {
@@ -91,31 +82,89 @@ __device__ __forceinline__ void load_pair(const long long *__restrict__ cnt, siz
   }
 }
 
-// natural log of a positive normal double from a 128-entry table in shared memory: x = 2^e m, m = c (1 + r) with c the
-// centre of m's 1/128 bin, so |r| <= 2^-8 and log1p(r) needs six terms (truncation 2^-58).  About 10 FP64 operations
-// against ~40 for the library log; absolute error <= 4e-16 + 1 ulp(e ln 2).  tab[k] = { 1/c_k rounded, -log of that }.
-constexpr int LOGTAB_N = 128;
-__device__ __forceinline__ void logtab_init(double2 *tab)
+// natural log from a 512-entry table in shared memory: x = 2^e m, m = c (1 + r) with c the centre of m's 1/512 bin, so
+// |r| <= 2^-10 and log1p(r) = r - r^2/2 + r^3/3 - r^4/4 (truncation 2^-52).  8 FP64 operations and no branch, against
+// ~40 and a branchy special-case path for the library log; absolute error <= 4e-16 + 1 ulp(e ln 2).  Arguments are
+// clamped to the smallest normal double: every call site multiplies the log of a zero/subnormal probability by that
+// probability (or discards it under a `> 0` guard), so the clamp never changes a result.  tab[k] = { 1/c_k rounded,
+// -log of that }, built once per context by logtab_kernel and copied to shared memory by each block.
+constexpr int LOGTAB_N = 512;
+__global__ void logtab_kernel(double2 *tab)
 {
-  for (int k = threadIdx.x; k < LOGTAB_N; k += blockDim.x) {
-    const double ic = 1.0 / (1.0 + (k + 0.5) * (1.0 / LOGTAB_N));
-    tab[k] = make_double2(ic, -log(ic));
-  }
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= LOGTAB_N) return;
+  const double ic = 1.0 / (1.0 + (k + 0.5) * (1.0 / LOGTAB_N));
+  tab[k] = make_double2(ic, -log(ic));
+}
+
+__device__ __forceinline__ void logtab_load(double2 *tab, const double2 *__restrict__ gtab)
+{
+  for (int k = threadIdx.x; k < LOGTAB_N; k += blockDim.x) tab[k] = gtab[k];
 }
 
 __device__ __forceinline__ double fast_log(double x, const double2 *__restrict__ tab)
 {
+  x = fmax(x, 2.2250738585072014e-308);
   const int hi = __double2hiint(x), lo = __double2loint(x);
-  if ((unsigned) (hi - 0x00100000) >= 0x7fe00000u) return log(x);        // zero, subnormal, negative, inf, nan
   const double m  = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
-  const double2 t = tab[(hi >> 13) & (LOGTAB_N - 1)];
+  const double2 t = tab[(hi >> 11) & (LOGTAB_N - 1)];
   const double r  = fma(m, t.x, -1.0);
   const double e  = __hiloint2double(0x43300000, ((hi >> 20) - 1023) ^ 0x80000000) - 4503601774854144.0;   // 2^52 + 2^31
-  double p = fma(r, -1.0 / 6.0, 0.2);
-  p = fma(p, r, -0.25);
-  p = fma(p, r, 1.0 / 3.0);
+  double p = fma(r, -0.25, 1.0 / 3.0);
   p = fma(p, r, -0.5);
   return fma(e, 0.6931471805599453094, t.y) + fma(p, r * r, r);
+}
+
+// raw (unnormalised) pair table for the statistics that can work on it: x_k = 1e-10 + c_k scale, T = sum x, ne
+__device__ __forceinline__ void load_pair_raw(const long long *__restrict__ cnt, size_t plane, size_t off,
+                                              double scale, long long wtot, double *x, double &ne)
+{
+  unsigned long long c[16];
+  #pragma unroll
+  for (int k = 0; k < 16; k++) c[k] = (unsigned long long) cnt[k * plane + off];
+  unsigned long long n = 0;
+  #pragma unroll
+  for (int k = 0; k < 16; k++) n += c[k];
+  if (((unsigned long long) wtot >> 52) == 0) {                      // uniform over the grid
+    ne = u52_to_f64(n) * scale;
+    #pragma unroll
+    for (int k = 0; k < 16; k++) x[k] = fma(u52_to_f64(c[k]), scale, 1e-10);
+  } else {
+    ne = u64_to_f64(n) * scale;
+    #pragma unroll
+    for (int k = 0; k < 16; k++) x[k] = fma(u64_to_f64(c[k]), scale, 1e-10);
+  }
+}
+
+// G test, 16 classes (corr_CalculateGT_C16, :383-387): G = 2 sum obs log(obs/exp), obs = ne pp, exp = ne pm_i pm_j.
+// ne cancels inside the log and sum pp = 1, so with the raw table x (pp = x / T), X_a = sum_b x_ab, Y_b = sum_a x_ab
+//     G = 2 ne [ (sum x log x - sum_a X_a log pm_i[a] - sum_b Y_b log pm_j[b]) / T - log T ]
+// : 17 logs, no division per cell, no branch.  The terms kept are the reference's (exp > 0 and obs > 0 <=> ne > 0 and
+// pm > 0; pp > 0 always because of the prior); the rounding differs at the 1e-15 level.
+__device__ __forceinline__ double gt_c16_raw(const double *x, double ne, const double *lmi, const double *lmj,
+                                             const double2 *__restrict__ tab)
+{
+  double X[4], Y[4];
+  #pragma unroll
+  for (int a = 0; a < 4; a++) X[a] = (x[a * 4] + x[a * 4 + 1]) + (x[a * 4 + 2] + x[a * 4 + 3]);
+  #pragma unroll
+  for (int b = 0; b < 4; b++) Y[b] = (x[b] + x[4 + b]) + (x[8 + b] + x[12 + b]);
+  const double T = (X[0] + X[1]) + (X[2] + X[3]);
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;                     // four independent chains
+  #pragma unroll
+  for (int k = 0; k < 16; k += 4) {
+    s0 = fma(x[k],     fast_log(x[k],     tab), s0);
+    s1 = fma(x[k + 1], fast_log(x[k + 1], tab), s1);
+    s2 = fma(x[k + 2], fast_log(x[k + 2], tab), s2);
+    s3 = fma(x[k + 3], fast_log(x[k + 3], tab), s3);
+  }
+  double m = 0.0;
+  #pragma unroll
+  for (int a = 0; a < 4; a++) m = fma(X[a], lmi[a], m);
+  #pragma unroll
+  for (int b = 0; b < 4; b++) m = fma(Y[b], lmj[b], m);
+  const double v = (((s0 + s1) + (s2 + s3)) - m) / T - fast_log(T, tab);
+  return (ne > 0.0) ? 2.0 * ne * v : 0.0;
 }
 
 __device__ __forceinline__ double warp_sum(double v)
@@ -126,76 +175,31 @@ __device__ __forceinline__ double warp_sum(double v)
 }
 
 // ------------------------------------------------------------------------------------------------
-// marginal partials + nseff.  rowpart[r][jt][i][4], colpart[r][it][j][4]
+// marginals.  The per-tile partial sums are produced by the epilogue of the tcgen05 kernel (gram_tcgen05.cu):
+//   mrow[r][jb][i][4]          sum over the tile's columns j of sum_b pp_ij[a][b]     (column i as the left partner)
+//   mcol[r][ib*4 + w][j][4]    sum over the 8 rows i of epilogue warp w of sum_a pp_ij[a][b]
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(ST_TJ)
-marg_partial_kernel(const long long *__restrict__ cnt, int L, int Lp, double scale, long long wtot,
-                    double *__restrict__ rowpart, double *__restrict__ colpart, double *__restrict__ nseff,
-                    int nJT, int nIT, int sr, int sw)
-{
-  __shared__ double rowacc[ST_TJ / 32][ST_TI][4];
-#ifdef RSB_BLOCKTRACE
-  const unsigned long long t0 = rsb_gtime();
-#endif
-  const int jt = blockIdx.x, it = blockIdx.y, r = blockIdx.z;
-  const int j  = jt * ST_TJ + threadIdx.x;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const size_t plane = (size_t) L * Lp;
-  const long long *c = cnt + (size_t) r * 16 * plane;
-  const bool tile_live = (it * ST_TI) < (jt * ST_TJ + ST_TJ - 1) && RSB_OWNED(it, sr, sw);      // some i < some j, rows owned by this rank
-  double col[4] = { 0, 0, 0, 0 };
-
-  for (int il = 0; il < ST_TI; il++) {
-    const int i = it * ST_TI + il;
-    double rs[4] = { 0, 0, 0, 0 };
-    if (tile_live && i < L && j < L && i < j) {
-      PairProbs P;
-      load_pair<false>(c, plane, (size_t) i * Lp + j, scale, wtot, P);
-      nseff[((size_t) r * L + i) * Lp + j] = P.ne;
-      if (P.ne > 0) {                                                    // :1354
-        #pragma unroll
-        for (int a = 0; a < 4; a++)
-          #pragma unroll
-          for (int b = 0; b < 4; b++) { rs[a] += P.pp[a * 4 + b]; col[b] += P.pp[a * 4 + b]; }
-      }
-    }
-    #pragma unroll
-    for (int a = 0; a < 4; a++) { const double v = warp_sum(rs[a]); if (lane == 0) rowacc[warp][il][a] = v; }
-  }
-  if (j < L) {
-    double *cp = colpart + (((size_t) r * nIT + it) * L + j) * 4;
-    #pragma unroll
-    for (int b = 0; b < 4; b++) cp[b] = col[b];
-  }
-  __syncthreads();
-  if (threadIdx.x < ST_TI * 4) {
-    const int il = threadIdx.x >> 2, a = threadIdx.x & 3, i = it * ST_TI + il;
-    if (i < L) {
-      double v = 0.0;
-      #pragma unroll
-      for (int w = 0; w < ST_TJ / 32; w++) v += rowacc[w][il][a];
-      rowpart[(((size_t) r * nJT + jt) * L + i) * 4 + a] = v;
-    }
-  }
-#ifdef RSB_BLOCKTRACE
-  if (threadIdx.x == 0) rsb_trace_put(stats_trace_buf, 2, t0);
-#endif
-}
-
-// unnormalised marginal sums msum[i][a] = sum of the tile partials in a fixed order: one warp per column, lanes stride
-// over the partial blocks, fixed xor-tree over the lanes (deterministic).  With the pair grid sharded over ranks these are
-// the vectors that are summed across ranks before normalisation.
+// unnormalised marginal sums msum[c][x] = sum of the partials of the tiles that exist, in a fixed order: one warp per
+// column, lanes stride over the partial blocks, fixed xor-tree over the lanes (deterministic).  With the pair grid
+// sharded over ranks these are the vectors that are summed across ranks before normalisation.
 __global__ void __launch_bounds__(256)
-marg_sum_kernel(const double *__restrict__ rowpart, const double *__restrict__ colpart, int L,
-                int nJT, int nIT, double *__restrict__ msum)
+marg_sum_kernel(const double *__restrict__ mrow, const double *__restrict__ mcol, int L, int CJ, int nJB, int nIB,
+                int sr, int sw, double *__restrict__ msum)
 {
   const int lane = threadIdx.x & 31;
-  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), r = blockIdx.y;
-  if (i >= L) return;
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), r = blockIdx.y;
+  if (c >= L) return;
+  const int ib_c = c / RSB_ICOLS, jb_c = c / CJ;
   double m[4] = { 0, 0, 0, 0 };
-  for (int k = lane; k < nJT + nIT; k += 32) {
-    const double *src = (k < nJT) ? rowpart + (((size_t) r * nJT + k) * L + i) * 4
-                                  : colpart + (((size_t) r * nIT + (k - nJT)) * L + i) * 4;
+  for (int k = lane; k < nJB + 4 * nIB; k += 32) {
+    const double *src;
+    if (k < nJB) {
+      if (!rsb_tile_exists(ib_c, k, CJ, L, sr, sw)) continue;
+      src = mrow + (((size_t) r * nJB + k) * L + c) * 4;
+    } else {
+      if (!rsb_tile_exists((k - nJB) >> 2, jb_c, CJ, L, sr, sw)) continue;
+      src = mcol + (((size_t) r * 4 * nIB + (k - nJB)) * L + c) * 4;
+    }
     const double2 lo = *reinterpret_cast<const double2 *>(src), hi = *reinterpret_cast<const double2 *>(src + 2);
     m[0] += lo.x; m[1] += lo.y; m[2] += hi.x; m[3] += hi.y;
   }
@@ -206,8 +210,21 @@ marg_sum_kernel(const double *__restrict__ rowpart, const double *__restrict__ c
   }
   if (lane == 0) {
     #pragma unroll
-    for (int a = 0; a < 4; a++) msum[((size_t) r * L + i) * 4 + a] = m[a];
+    for (int a = 0; a < 4; a++) msum[((size_t) r * L + c) * 4 + a] = m[a];
   }
+}
+
+// nseff[i][j] for the statistics that read it (CCF)
+__global__ void nseff_kernel(const long long *__restrict__ cnt, int L, int Lp, double scale, double *__restrict__ nseff)
+{
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y, r = blockIdx.z;
+  if (j >= L || i >= j) return;
+  const size_t plane = (size_t) L * Lp;
+  const long long *c = cnt + (size_t) r * 16 * plane + (size_t) i * Lp + j;
+  unsigned long long ne = 0;
+  #pragma unroll
+  for (int k = 0; k < 16; k++) ne += (unsigned long long) c[k * plane];
+  nseff[((size_t) r * L + i) * Lp + j] = u64_to_f64(ne) * scale;
 }
 
 // pm[i] = normalise(msum[i]); validation flag as corr_Marginals' esl_vec_DValidate (:1363)
@@ -271,21 +288,7 @@ __device__ __forceinline__ double pair_statistic(const PairProbs &P, const doubl
     }
     return v;
   }
-  // lmi / lmj: log of the marginals, taken once per column by the caller.
-  if (STAT == RSB_GT && CLS == RSB_C16) {
-    // G = 2 sum obs fast_log(obs/exp, tab) with obs = ne pp, exp = ne pm_i pm_j (:383-387): ne cancels inside the log, so
-    // G = 2 ne sum pp (log pp - log pm_i - log pm_j), one log per cell and no division.  The terms kept are the
-    // same (exp > 0 and obs > 0 <=> ne > 0, pm_i > 0, pm_j > 0, pp > 0); the rounding differs at the 1e-15 level.
-    if (!(P.ne > 0.)) return 0.0;
-    #pragma unroll
-    for (int x = 0; x < 4; x++)
-      #pragma unroll
-      for (int y = 0; y < 4; y++) {
-        const double pxy = P.pp[x * 4 + y];
-        v += (pxy > 0.0 && mi[x] > 0.0 && mj[y] > 0.0) ? pxy * (fast_log(pxy, tab) - lmi[x] - lmj[y]) : 0.0;
-      }
-    return 2.0 * P.ne * v;
-  }
+  // lmi / lmj: log of the marginals, taken once per column by the caller.  (GT x C16 has its own form, gt_c16_raw.)
   #pragma unroll
   for (int x = 0; x < 4; x++)
     #pragma unroll
@@ -296,11 +299,12 @@ __device__ __forceinline__ double pair_statistic(const PairProbs &P, const doubl
       const double ob  = P.ne * pxy;
       if      (STAT == RSB_CHI)  v += (ex > 0.) ? (ob - ex) * (ob - ex) / ex   : 0.0;
       else if (STAT == RSB_OMES) v += (ex > 0.) ? (ob - ex) * (ob - ex) / P.ne : 0.0;
-      else if (STAT == RSB_GT)   v += (ex > 0. && ob > 0.) ? ob * fast_log(ob / ex, tab) : 0.0;
+      else if (STAT == RSB_GT) { const double t = ob * fast_log(ob / fmax(ex, 2.2250738585072014e-308), tab); v += (ex > 0. && ob > 0.) ? t : 0.0; }
       else {
-        const double lp = (pxy > 0.0) ? fast_log(pxy, tab) : 0.0;
+        const double lp = fast_log(pxy, tab);
+        const double t  = pxy * (lp - lmi[x] - lmj[y]);
         if (STAT == RSB_MIr) H -= (pxy > 0.0) ? pxy * lp : 0.0;
-        v += (pxy > 0.0 && mi[x] > 0.0 && mj[y] > 0.0) ? pxy * (lp - lmi[x] - lmj[y]) : 0.0;
+        v += (pxy > 0.0 && mi[x] > 0.0 && mj[y] > 0.0) ? t : 0.0;
       }
     }
   if (STAT == RSB_GT)  v *= 2.0;
@@ -313,8 +317,8 @@ __device__ __forceinline__ double pair_statistic(const PairProbs &P, const doubl
 // per-block min/max.  rowpart[r][jt][i], colpart[r][it][j], mm[r][block][2]
 template <int STAT, int CLS>
 __global__ void __launch_bounds__(ST_TJ)
-stat_kernel(const long long *__restrict__ cnt, const double *__restrict__ pm, int L, int Lp, double scale, long long wtot,
-            unsigned mask, double *__restrict__ cov, double *__restrict__ rowpart, double *__restrict__ colpart,
+stat_kernel(const long long *__restrict__ cnt, const double *__restrict__ pm, const double2 *__restrict__ gtab, int L, int Lp,
+            double scale, long long wtot, unsigned mask, double *__restrict__ cov, double *__restrict__ rowpart, double *__restrict__ colpart,
             double *__restrict__ mm, int nJT, int nIT, int sr, int sw)
 {
   __shared__ double rowacc[ST_TJ / 32][ST_TI];
@@ -331,29 +335,35 @@ stat_kernel(const long long *__restrict__ cnt, const double *__restrict__ pm, in
   const long long *c = cnt + (size_t) r * 16 * plane;
   const bool tile_live = (it * ST_TI) < (jt * ST_TJ + ST_TJ - 1) && RSB_OWNED(it, sr, sw);
   double col = 0.0, vmin = INFINITY, vmax = -INFINITY;
-  if (tile_live) logtab_init(tab);
+  if (tile_live) logtab_load(tab, gtab);
   double mj[4] = { 0.25, 0.25, 0.25, 0.25 }, lmj[4];
 
   if (threadIdx.x < ST_TI * 4) {
     const int il = threadIdx.x >> 2, a = threadIdx.x & 3, i = it * ST_TI + il;
     pmi[il][a]  = (i < L) ? pm[((size_t) r * L + i) * 4 + a] : 0.25;
-    lpmi[il][a] = log(pmi[il][a]);
+    lpmi[il][a] = (pmi[il][a] > 0.0) ? log(pmi[il][a]) : 0.0;      // pm > 0 always (prior); keep the logs finite regardless
   }
   if (j < L) {
     #pragma unroll
     for (int b = 0; b < 4; b++) mj[b] = pm[((size_t) r * L + j) * 4 + b];
   }
   #pragma unroll
-  for (int b = 0; b < 4; b++) lmj[b] = log(mj[b]);
+  for (int b = 0; b < 4; b++) lmj[b] = (mj[b] > 0.0) ? log(mj[b]) : 0.0;
   __syncthreads();
 
   for (int il = 0; il < ST_TI; il++) {
     const int i = it * ST_TI + il;
     double v = 0.0;
     if (tile_live && i < L && j < L && i < j) {
-      PairProbs P;
-      load_pair<false>(c, plane, (size_t) i * Lp + j, scale, wtot, P);
-      v = pair_statistic<STAT, CLS>(P, pmi[il], mj, lpmi[il], lmj, mask, tab);
+      if (STAT == RSB_GT && CLS == RSB_C16) {
+        double x[16], ne;
+        load_pair_raw(c, plane, (size_t) i * Lp + j, scale, wtot, x, ne);
+        v = gt_c16_raw(x, ne, lpmi[il], lmj, tab);
+      } else {
+        PairProbs P;
+        load_pair<false>(c, plane, (size_t) i * Lp + j, scale, wtot, P);
+        v = pair_statistic<STAT, CLS>(P, pmi[il], mj, lpmi[il], lmj, mask, tab);
+      }
       cov[((size_t) r * L + i) * Lp + j] = v;
       col += v;
       vmin = fmin(vmin, v);
@@ -585,29 +595,40 @@ __global__ void ps_kernel(const unsigned long long *__restrict__ colsum, int L, 
 // ---------------------------------------------------------------------------------------------- launchers
 void rsb_stat_grid(int L, int *nJT, int *nIT) { *nJT = (L + ST_TJ - 1) / ST_TJ; *nIT = (L + ST_TI - 1) / ST_TI; }
 
-// phase: 1 = partial sums only (-> msum), 2 = normalise msum -> pm, 3 = both
-cudaError_t rsb_launch_marginals(const long long *cnt, int nrep, int L, int Lp, double scale, long long wtot, double tol,
-                                 double *rowpart, double *colpart, double *nseff, double *msum, double *pm, int *flags,
-                                 int sr, int sw, int phase, cudaStream_t st)
+// phase: 1 = sum the tile partials (-> msum), 2 = normalise msum -> pm, 3 = both
+cudaError_t rsb_launch_marginals(const double *mrow, const double *mcol, int nrep, int L, int CJ, int nJB, int nIB, double tol,
+                                 double *msum, double *pm, int *flags, int sr, int sw, int phase, cudaStream_t st)
 {
-  int nJT, nIT; rsb_stat_grid(L, &nJT, &nIT);
   if (phase & 1) {
-    rsb_coreside(marg_partial_kernel); marg_partial_kernel<<<dim3(nJT, nIT, nrep), ST_TJ, 0, st>>>(cnt, L, Lp, scale, wtot, rowpart, colpart, nseff, nJT, nIT, sr, sw);
-    rsb_coreside(marg_sum_kernel); marg_sum_kernel<<<dim3((L + 7) / 8, nrep), 256, 0, st>>>(rowpart, colpart, L, nJT, nIT, msum);
+    rsb_coreside(marg_sum_kernel); marg_sum_kernel<<<dim3((L + 7) / 8, nrep), 256, 0, st>>>(mrow, mcol, L, CJ, nJB, nIB, sr, sw, msum);
   }
   rsb_coreside(marg_norm_kernel);
   if (phase & 2) marg_norm_kernel<<<dim3((L + 127) / 128, nrep), 128, 0, st>>>(msum, L, tol, pm, flags);
   return cudaGetLastError();
 }
 
-#define RSB_STAT_CASE(STAT, CLS) \
-  rsb_coreside(stat_kernel<STAT, CLS>); stat_kernel<STAT, CLS><<<grid, ST_TJ, 0, st>>>(cnt, pm, L, Lp, scale, wtot, mask, cov, rowpart, colpart, mm, nJT, nIT, sr, sw); break;
+cudaError_t rsb_launch_nseff(const long long *cnt, int nrep, int L, int Lp, double scale, double *nseff, cudaStream_t st)
+{
+  nseff_kernel<<<dim3((L + 127) / 128, L, nrep), 128, 0, st>>>(cnt, L, Lp, scale, nseff);
+  return cudaGetLastError();
+}
 
-cudaError_t rsb_launch_statistic(int stat, int cls, const long long *cnt, const double *pm, int nrep, int L, int Lp, double scale,
+#define RSB_STAT_CASE(STAT, CLS) \
+  rsb_coreside(stat_kernel<STAT, CLS>); stat_kernel<STAT, CLS><<<grid, ST_TJ, 0, st>>>(cnt, pm, logtab, L, Lp, scale, wtot, mask, cov, rowpart, colpart, mm, nJT, nIT, sr, sw); break;
+
+cudaError_t rsb_launch_logtab(void *tab, cudaStream_t st)
+{
+  logtab_kernel<<<(LOGTAB_N + 127) / 128, 128, 0, st>>>((double2 *) tab);
+  return cudaGetLastError();
+}
+size_t rsb_logtab_bytes() { return sizeof(double2) * LOGTAB_N; }
+
+cudaError_t rsb_launch_statistic(int stat, int cls, const long long *cnt, const double *pm, const void *logtab_, int nrep, int L, int Lp, double scale,
                                  long long wtot, unsigned mask, double *cov, double *rowpart, double *colpart, double *mm, int sr, int sw, cudaStream_t st)
 {
   int nJT, nIT; rsb_stat_grid(L, &nJT, &nIT);
   dim3 grid(nJT, nIT, nrep);
+  const double2 *logtab = (const double2 *) logtab_;
   const int key = stat * 4 + cls;
   switch (key) {
   case RSB_CHI  * 4 + RSB_C16: RSB_STAT_CASE(RSB_CHI,  RSB_C16)

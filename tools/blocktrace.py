@@ -52,3 +52,22 @@ for k in (1, 2, 3):
         s = slice(q * sz, (q + 1) * sz)
         d = (a1[s] - a0[s]) / 1e3
         print(f"   launch {q}: first start {a0[s].min()/1e3:9.1f} us  last end {a1[s].max()/1e3:9.1f} us   block dur mean {d.mean():7.1f} max {d.max():7.1f} us   SMs used {len(set(sm[m][order][s]))}")
+
+# co-residency: how many blocks of a kernel are in flight on one SM at the same time (time-averaged over its busy span)
+for k in (2, 3):
+    m = kid == k
+    if not m.any():
+        continue
+    conc = []
+    for s_ in range(0, 148, 37):
+        mm = m & (sm == s_)
+        ev = sorted([(t, 1) for t in t0[mm]] + [(t, -1) for t in t1[mm]])
+        cur = 0; last = None; area = 0; busy = 0; peak = 0
+        for t, d in ev:
+            if last is not None and cur > 0:
+                area += cur * (t - last); busy += (t - last)
+            cur += d; peak = max(peak, cur); last = t
+        conc.append((s_, round(area / max(busy, 1), 2), peak))
+    print(f"{names[k]}: (SM, mean blocks in flight while busy, peak) {conc}")
+    live = (t1[m] - t0[m]) > 5000
+    print(f"   live blocks: {live.sum()} of {m.sum()}, mean duration {(t1[m] - t0[m])[live].mean() / 1e3:.1f} us")
