@@ -95,7 +95,7 @@ def run_reference(args):
     wl = WORKLOADS[args.workload]
     L, N = wl["L"], wl["N"]
     po = ge.load_oracle()
-    msa, wgt, _ = po.synthetic_msa(N, L, seed=42)
+    msa, wgt, _, _ = po.synthetic_family(N, L, seed=42)
     cores = os.cpu_count() or 1
     nthreads = max(1, min(cores, 64))
     ncols = args.ref_cols                       # columns per thread task (bounded sample of the L x L pair grid)
@@ -210,8 +210,7 @@ def main():
     peaks = load_peaks()
 
     # ---- synthetic inputs (same on every rank: seeded) ------------------------------------------------
-    msa, wgt, _ = synth.synthetic_msa(N, L, seed=42)
-    tree = synth.random_tree(N, np.random.default_rng(42))
+    msa, wgt, _, tree = synth.synthetic_family(N, L, seed=42)        # alignment evolved on the tree the null generator is given
     stream = torch.cuda.current_stream()
     slots = pkg.replicate_slots(N, L, R, args.slices)
     ctx = pkg.Context(local, stream.cuda_stream)

@@ -34,6 +34,7 @@ Tree = _synth.Tree
 _Tree = _synth._TreeStruct
 random_tree = _synth.random_tree
 synthetic_msa = _synth.synthetic_msa
+synthetic_family = _synth.synthetic_family
 
 CHI, GT, MI, MIr, MIg, OMES, RAF, RAFS, CCF = 0, 3, 6, 9, 12, 15, 18, 21, 24
 C16, C2, CWC, CSELECT = 0, 1, 2, 3

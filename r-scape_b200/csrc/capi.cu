@@ -52,7 +52,7 @@ cudaError_t rsb_launch_null_simulate(const int *left, const int *right, const in
                                      uint8_t *res, uint8_t *scratch, cudaStream_t st);
 cudaError_t rsb_launch_fitch_shuffle(const int *left, const int *right, const int *parent, const int *order, const int *level_start,
                                      int nlevels, int N, int L, const uint8_t *msa, unsigned long long seed, unsigned long long id0, int first_rep, int nrep,
-                                     uint8_t *res, uint8_t *anc, uint8_t *shanc, int *perm, cudaStream_t st);
+                                     uint8_t *res, uint8_t *anc, uint8_t *shanc, int *perm, uint8_t *sets_shared, int *d_flag, cudaStream_t st);
 
 namespace {
 constexpr int HIST_BINS = 1 << 22;
@@ -108,7 +108,8 @@ struct rsb_ctx {
   std::vector<double> h_ld, h_rd;
   double *d_pcdf = nullptr;
   std::vector<int> h_level_start;
-  uint8_t *d_root = nullptr, *d_gapmask = nullptr, *d_simscratch = nullptr, *d_msa0 = nullptr, *d_anc = nullptr, *d_shanc = nullptr;
+  uint8_t *d_root = nullptr, *d_gapmask = nullptr, *d_simscratch = nullptr, *d_msa0 = nullptr, *d_anc = nullptr, *d_shanc = nullptr, *d_sets = nullptr;
+  int *d_genflag = nullptr;
   bool have_tree = false;
   uint8_t *d_pool = nullptr;          // device-resident null alignments [Rpool][N][L] (output of the generators)
   int Rpool = 0;
@@ -178,7 +179,7 @@ void free_plan(rsb_ctx *c)
   dfree(c->d_meanp); dfree(c->d_w); dfree(c->d_blocksum); dfree(c->d_msum); dfree(c->d_covsum); dfree(c->d_hist); dfree(c->d_colsum); dfree(c->d_flags); dfree(c->d_ps); dfree(c->d_pp_out);
   dfree(c->d_nseff_out); dfree(c->d_ngap_out); dfree(c->d_left); dfree(c->d_right); dfree(c->d_parent); dfree(c->d_order);
   dfree(c->d_level_start); dfree(c->d_perm); dfree(c->d_pcdf); dfree(c->d_root); dfree(c->d_gapmask); dfree(c->d_simscratch);
-  dfree(c->d_msa0); dfree(c->d_anc); dfree(c->d_shanc); dfree(c->d_pool);
+  dfree(c->d_msa0); dfree(c->d_anc); dfree(c->d_shanc); dfree(c->d_pool); dfree(c->d_sets); dfree(c->d_genflag);
   c->Rpool = 0;
   c->have_tree = false;
 }
@@ -1212,9 +1213,11 @@ int rsb_null_fitch_shuffle(rsb_ctx *ctx, const uint8_t *msa, int64_t row_stride,
   if (!ctx->d_anc)   RSB_CUDA_OK(cudaMalloc(&ctx->d_anc, (size_t) ctx->Rpool * nn * L));
   if (!ctx->d_shanc) RSB_CUDA_OK(cudaMalloc(&ctx->d_shanc, (size_t) ctx->Rpool * nn * L));
   if (!ctx->d_perm)  RSB_CUDA_OK(cudaMalloc(&ctx->d_perm, sizeof(int) * (size_t) ctx->Rpool * L));
+  if (!ctx->d_sets)  RSB_CUDA_OK(cudaMalloc(&ctx->d_sets, (size_t) nn * L));
+  if (!ctx->d_genflag) RSB_CUDA_OK(cudaMalloc(&ctx->d_genflag, sizeof(int)));
   RSB_CUDA_OK(cudaMemcpy2DAsync(ctx->d_msa0, L, msa, (size_t) row_stride, L, N, cudaMemcpyHostToDevice, ctx->stream));
   RSB_CUDA_OK(rsb_launch_fitch_shuffle(ctx->d_left, ctx->d_right, ctx->d_parent, ctx->d_order, ctx->h_level_start.data(), ctx->nlevels, N, L,
-                                       ctx->d_msa0, seed, first_id, first_rep, nrep, ctx->d_pool, ctx->d_anc, ctx->d_shanc, ctx->d_perm, ctx->stream));
+                                       ctx->d_msa0, seed, first_id, first_rep, nrep, ctx->d_pool, ctx->d_anc, ctx->d_shanc, ctx->d_perm, ctx->d_sets, ctx->d_genflag, ctx->stream));
   ctx->launches += 1 + 3 * ctx->nlevels;
   return 0;
 }

@@ -21,6 +21,7 @@
 //                         holding the source residue (one-pass selection sampling instead of the reference's
 //                         Fisher-Yates over an index list: same distribution, exact counts).
 #include "rsb_common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -85,60 +86,104 @@ __device__ __forceinline__ int pick_member(unsigned set, uint32_t rnd)      // u
   return __fns(set, 0, k + 1);
 }
 
-// Fitch sets, one launch per tree level from the deepest up (:1758-1777, :1869-1905): a thread owns one
-// (replicate, node, column).  grid = (columns/128, nodes of the level, replicates).
+// Fitch sets, one launch per tree level from the deepest up (:1758-1777, :1869-1905): a thread owns W columns (W = 4:
+// rows moved as 32-bit words, L % 4 == 0; W = 1 otherwise) of one (replicate, node).
+// grid = (columns/(128 W), nodes of the level, replicates).
+template <int W>
 __global__ void fitch_up_level_kernel(const int *__restrict__ left, const int *__restrict__ right, const int *__restrict__ order, int lvl_begin,
                                       int N, int L, const uint8_t *__restrict__ msa, unsigned long long seed, unsigned long long id0,
                                       int first_rep, uint8_t *__restrict__ ancbuf)
 {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c0 = (blockIdx.x * blockDim.x + threadIdx.x) * W;
   const int v = order[lvl_begin + blockIdx.y];
   const int r = first_rep + blockIdx.z;
   const uint32_t rid = (uint32_t) (id0 + blockIdx.z);
-  if (c >= L) return;
+  if (c0 >= L) return;
   Philox rng; rng.key[0] = (uint32_t) seed ^ 0xF17C4u; rng.key[1] = (uint32_t) (seed >> 32) ^ (0x85EBCA6Bu * (rid + 1u));
   uint8_t *anc = ancbuf + (size_t) r * (N - 1) * L;
-  auto leaf_set = [&](int n) -> unsigned {
-    const int x = msa[(size_t) n * L + c];
-    if (x <= 4) return 1u << x;
-    uint32_t rnd[4]; rng.block((uint32_t) n, (uint32_t) c, 0x1eafu, 0u, rnd);          // unknown -> one of the 5 at random (:1735)
-    return 1u << (int) (((unsigned long long) rnd[0] * 5u) >> 32);
+  auto row_sets = [&](int n) -> uint32_t {                                              // sets of W columns of child n, one per byte
+    if (n > 0) return (W == 4) ? *reinterpret_cast<const uint32_t *>(anc + (size_t) n * L + c0) : (uint32_t) anc[(size_t) n * L + c0];
+    const uint32_t xw = (W == 4) ? *reinterpret_cast<const uint32_t *>(msa + (size_t) (-n) * L + c0) : (uint32_t) msa[(size_t) (-n) * L + c0];
+    uint32_t out = 0;
+    #pragma unroll
+    for (int q = 0; q < W; q++) {
+      const int x = (xw >> (8 * q)) & 0xFF;
+      unsigned S;
+      if (x <= 4) S = 1u << x;
+      else {                                                                            // unknown -> one of the 5 at random (:1735)
+        uint32_t rnd[4]; rng.block((uint32_t) (-n), (uint32_t) (c0 + q), 0x1eafu, 0u, rnd);
+        S = 1u << (int) (((unsigned long long) rnd[0] * 5u) >> 32);
+      }
+      out |= S << (8 * q);
+    }
+    return out;
   };
-  const int l = left[v], rr = right[v];
-  const unsigned Sl = (l > 0) ? anc[(size_t) l * L + c] : leaf_set(-l);
-  const unsigned Sr = (rr > 0) ? anc[(size_t) rr * L + c] : leaf_set(-rr);
-  unsigned S = Sl & Sr;
-  if (!S) S = (Sl | Sr) & 0xFu;                                                         // union of residues; a gap never joins
-  anc[(size_t) v * L + c] = (uint8_t) S;
+  const uint32_t Sl = row_sets(left[v]), Sr = row_sets(right[v]);
+  uint32_t S = Sl & Sr;                                                                 // per byte: intersection ...
+  const uint32_t un = (Sl | Sr) & 0x0F0F0F0Fu;                                          // ... else the union of residues; a gap never joins
+  const uint32_t empty = __vcmpeq4(S, 0u);                                              // 0xFF in the bytes whose intersection is empty
+  S |= un & empty;
+  if (W == 4) *reinterpret_cast<uint32_t *>(anc + (size_t) v * L + c0) = S;
+  else anc[(size_t) v * L + c0] = (uint8_t) S;
 }
 
-// Traceback, one launch per level from the root down (:1779-1815): the stored set of each internal child is replaced by
-// the chosen residue (the parent's residue if it is in the child's set, else a uniform member).
+// Traceback, one launch per level from the root down (:1779-1815): each internal child gets the parent's residue if that
+// is in the child's Fitch set, else a uniform member of the set.  A thread owns W columns (W = 4: rows moved as 32-bit
+// words, L % 4 == 0; W = 1 otherwise) of one (replicate, node).  The sets come from `sets` (replicate stride
+// sets_stride; 0 when the up pass is shared by all replicates, or the residue buffer itself when it ran per replicate);
+// the Philox block of a (node, column) is only computed where a random choice is really needed -- most branches carry
+// no substitution in most columns.
+template <int W>
 __global__ void fitch_down_level_kernel(const int *__restrict__ left, const int *__restrict__ right, const int *__restrict__ order, int lvl_begin,
-                                        int N, int L, unsigned long long seed, unsigned long long id0, int first_rep, uint8_t *__restrict__ ancbuf)
+                                        int N, int L, unsigned long long seed, unsigned long long id0, int first_rep,
+                                        const uint8_t *sets, size_t sets_stride, uint8_t *ancbuf)
 {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c0 = (blockIdx.x * blockDim.x + threadIdx.x) * W;
   const int v = order[lvl_begin + blockIdx.y];
   const int r = first_rep + blockIdx.z;
   const uint32_t rid = (uint32_t) (id0 + blockIdx.z);
-  if (c >= L) return;
+  if (c0 >= L) return;
   Philox rng; rng.key[0] = (uint32_t) seed ^ 0xF17C4u; rng.key[1] = (uint32_t) (seed >> 32) ^ (0x85EBCA6Bu * (rid + 1u));
   uint8_t *anc = ancbuf + (size_t) r * (N - 1) * L;
-  int ax;
+  const uint8_t *st = sets + (size_t) blockIdx.z * sets_stride;
+  uint32_t axw = 0;
   if (v == 0) {                                                                          // root: uniform member of its set (:1779)
-    uint32_t rnd[4]; rng.block(0xffffffffu, (uint32_t) c, 0x600du, 0u, rnd);
-    ax = pick_member(anc[c], rnd[0]);
-    anc[c] = (uint8_t) ax;
-  } else ax = anc[(size_t) v * L + c];
-  uint32_t rnd[4]; rng.block((uint32_t) v, (uint32_t) c, 0xd0c0u, 0u, rnd);
-  const int kids[2] = { left[v], right[v] };
+    #pragma unroll
+    for (int q = 0; q < W; q++) {
+      uint32_t rnd[4]; rng.block(0xffffffffu, (uint32_t) (c0 + q), 0x600du, 0u, rnd);
+      axw |= (uint32_t) pick_member(st[c0 + q], rnd[0]) << (8 * q);
+    }
+    if (W == 4) *reinterpret_cast<uint32_t *>(anc + c0) = axw;
+    else anc[c0] = (uint8_t) axw;
+  } else axw = (W == 4) ? *reinterpret_cast<const uint32_t *>(anc + (size_t) v * L + c0) : (uint32_t) anc[(size_t) v * L + c0];
+  const int kl = left[v], kr = right[v];
+  const uint32_t Sl = (kl <= 0) ? 0u : (W == 4) ? *reinterpret_cast<const uint32_t *>(st + (size_t) kl * L + c0) : (uint32_t) st[(size_t) kl * L + c0];
+  const uint32_t Sr = (kr <= 0) ? 0u : (W == 4) ? *reinterpret_cast<const uint32_t *>(st + (size_t) kr * L + c0) : (uint32_t) st[(size_t) kr * L + c0];
+  uint32_t ol = 0, orr = 0;
   #pragma unroll
-  for (int side = 0; side < 2; side++) {
-    const int ch = kids[side];
-    if (ch <= 0) continue;
-    const unsigned S = anc[(size_t) ch * L + c];
-    anc[(size_t) ch * L + c] = (uint8_t) (((S >> ax) & 1u) ? ax : pick_member(S, rnd[side]));
+  for (int q = 0; q < W; q++) {
+    const int ax = (axw >> (8 * q)) & 0xFF;
+    const unsigned sl = (Sl >> (8 * q)) & 0xFF, sr = (Sr >> (8 * q)) & 0xFF;
+    int xl = ax, xr = ax;
+    const bool needl = (kl > 0) && !((sl >> ax) & 1u), needr = (kr > 0) && !((sr >> ax) & 1u);
+    if (needl || needr) {
+      uint32_t rnd[4]; rng.block((uint32_t) v, (uint32_t) (c0 + q), 0xd0c0u, 0u, rnd);
+      if (needl) xl = pick_member(sl, rnd[0]);
+      if (needr) xr = pick_member(sr, rnd[1]);
+    }
+    ol |= (uint32_t) xl << (8 * q); orr |= (uint32_t) xr << (8 * q);
   }
+  if (kl > 0) { if (W == 4) *reinterpret_cast<uint32_t *>(anc + (size_t) kl * L + c0) = ol;  else anc[(size_t) kl * L + c0] = (uint8_t) ol; }
+  if (kr > 0) { if (W == 4) *reinterpret_cast<uint32_t *>(anc + (size_t) kr * L + c0) = orr; else anc[(size_t) kr * L + c0] = (uint8_t) orr; }
+}
+
+// does the alignment hold residues other than A C G U and the gap?  (they are resolved at random per replicate, :1735,
+// which makes the Fitch sets replicate-specific)
+__global__ void unknown_flag_kernel(const uint8_t *__restrict__ msa, size_t n, int *__restrict__ flag)
+{
+  bool any = false;
+  for (size_t k = (size_t) blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t) gridDim.x * blockDim.x) any |= msa[k] > 4;
+  if (__syncthreads_or(any) && threadIdx.x == 0) *flag = 1;
 }
 
 // one random permutation per replicate (Fisher-Yates by one thread; L is a few thousand) and the permuted root row
@@ -387,6 +432,156 @@ replay_level_warp_kernel(const int *__restrict__ left, const int *__restrict__ r
   }
 }
 
+// Row variant of the replay: one WARP per (replicate, branch), rows moved as coalesced 32-bit words (W = 4 columns per
+// lane; W = 1 when L % 4 != 0).
+//   sweep 1  (Fitch rows of parent and child): composition m_a of the parent row and the substitution counts n[a->d]
+//            (msamanip.c:1634-1643); the shuffled parent row has the same composition (see replay_level_kernel).
+//   draw     for every source class a, k_a = sum_d n[a->d] distinct RANKS in [0, m_a) by parallel rejection sampling:
+//            each lane draws a candidate, duplicates inside the round are resolved towards the lowest lane
+//            (__match_any_sync, deterministic), a 4-bit code table in shared memory (claimed bit + target) says which ranks
+//            are taken; the i-th accepted draw takes the i-th target of the multiset {d x n[a->d]}.  The accepted ranks
+//            are a uniformly random ordered sample without replacement, so every subset of positions and every assignment
+//            of targets is equally likely -- the distribution of the reference's Fisher-Yates shuffle (:1718-1757).
+//   sweep 2  (shuffled parent row -> child row): a column of class a is the (running count of a)-th of its class; the
+//            code table says whether that rank was drawn and what it becomes (:1645-1757).
+// Work per branch is a few coalesced passes over its rows, independent of how the substitutions fall.
+constexpr int RPR_WARPS = 8;
+
+template <int W>
+__global__ void __launch_bounds__(RPR_WARPS * 32)
+replay_level_row_kernel(const int *__restrict__ left, const int *__restrict__ right, const int *__restrict__ order, int lvl_begin, int lvl_count,
+                        int N, int L, const uint8_t *__restrict__ msa, unsigned long long seed, unsigned long long id0, int first_rep, int nrep,
+                        const uint8_t *__restrict__ ancbuf, uint8_t *__restrict__ shancbuf, uint8_t *__restrict__ res, int code_words)
+{
+  extern __shared__ unsigned rpr_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned *code = rpr_smem + (size_t) warp * (5 * code_words + 32);          // [5][code_words] nibbles: bit 3 = rank drawn, bits 2:0 = target
+  int *nsub = reinterpret_cast<int *>(code + 5 * code_words);                  // [25]
+  const long long task = (long long) blockIdx.x * RPR_WARPS + warp;
+  if (task >= 2LL * lvl_count * nrep) return;                                   // whole warp
+  const int side = (int) (task & 1);
+  const long long nt = task >> 1;
+  const int rr = (int) (nt / lvl_count);
+  const int r = first_rep + rr;
+  const uint32_t rid = (uint32_t) (id0 + (unsigned long long) rr);
+  const int v = order[lvl_begin + (int) (nt % lvl_count)];
+  const uint8_t *anc = ancbuf + (size_t) r * (N - 1) * L;
+  uint8_t *shanc = shancbuf + (size_t) r * (N - 1) * L;
+  uint8_t *leaves = res + (size_t) r * N * L;
+  const uint8_t *par_o = anc + (size_t) v * L;
+  const uint8_t *par_s = shanc + (size_t) v * L;
+  const int ch = side ? right[v] : left[v];
+  const uint8_t *kid_o = (ch > 0) ? anc + (size_t) ch * L : msa + (size_t) (-ch) * L;
+  uint8_t *kid_s = (ch > 0) ? shanc + (size_t) ch * L : leaves + (size_t) (-ch) * L;
+  const int LW = (L + W - 1) / W;                                               // row length in lane units
+  const unsigned lt = (1u << lane) - 1u;
+
+  auto load = [&](const uint8_t *row, int u) -> uint32_t {
+    if (W == 4) return __ldcg(reinterpret_cast<const uint32_t *>(row) + u);
+    return (uint32_t) row[u] | 0xFFFFFF00u;
+  };
+
+  for (int k = lane; k < 5 * code_words + 32; k += 32) code[k] = 0u;           // (nsub included)
+  __syncwarp();
+
+  // ---- sweep 1
+  int m[5] = { 0, 0, 0, 0, 0 };
+  for (int u0 = 0; u0 < LW; u0 += 64) {                                         // two units per lane in flight
+    uint32_t wp[2], wk[2];
+    #pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int u = u0 + h * 32 + lane;
+      wp[h] = (u < LW) ? load(par_o, u) : 0xFFFFFFFFu;
+      wk[h] = (u < LW) ? load(kid_o, u) : 0xFFFFFFFFu;
+    }
+    #pragma unroll
+    for (int h = 0; h < 2; h++) {
+      #pragma unroll
+      for (int a = 0; a < 5; a++) m[a] += __popc(__vcmpeq4(wp[h], 0x01010101u * a) & 0x01010101u);
+      if (wp[h] != wk[h]) {
+        #pragma unroll
+        for (int q = 0; q < W; q++) {
+          const int pa = (wp[h] >> (8 * q)) & 0xFF, kd = (wk[h] >> (8 * q)) & 0xFF;
+          if (pa != kd && pa <= 4 && kd <= 4) atomicAdd(&nsub[pa * 5 + kd], 1);
+        }
+      }
+    }
+  }
+  #pragma unroll
+  for (int a = 0; a < 5; a++) {
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m[a] += __shfl_xor_sync(0xffffffffu, m[a], o);
+  }
+  __syncwarp();
+  int ka[5], ktot = 0;
+  #pragma unroll
+  for (int a = 0; a < 5; a++) { ka[a] = nsub[a * 5] + nsub[a * 5 + 1] + nsub[a * 5 + 2] + nsub[a * 5 + 3] + nsub[a * 5 + 4]; ktot += ka[a]; }
+
+  // ---- draw
+  if (ktot > 0) {
+    Philox ph; ph.key[0] = (uint32_t) seed ^ (0xC2B2AE35u * (rid + 1u)); ph.key[1] = (uint32_t) (seed >> 32) ^ 0x5bd1e995u;
+    uint32_t sd[4]; ph.block((uint32_t) v, 0x7ee1u + (uint32_t) side, 0x3041u + (uint32_t) lane, 0u, sd);
+    Pcg32 rng; rng.state = ((unsigned long long) sd[0] << 32) | sd[1]; rng.inc = ((((unsigned long long) sd[2] << 32) | sd[3]) << 1) | 1ULL;
+    rng.next();
+    #pragma unroll 1
+    for (int a = 0; a < 5; a++) {
+      if (ka[a] == 0) continue;                                                 // uniform
+      int c0 = nsub[a * 5], c1 = c0 + nsub[a * 5 + 1], c2 = c1 + nsub[a * 5 + 2], c3 = c2 + nsub[a * 5 + 3];   // cumulative targets
+      unsigned *tab = code + a * code_words;
+      int succ = 0;
+      while (succ < ka[a]) {                                                    // uniform
+        const unsigned cand = __umulhi(rng.next(), (uint32_t) m[a]);
+        const unsigned same = __match_any_sync(0xffffffffu, cand);
+        bool ok = false;
+        const unsigned sh = (cand & 7u) * 4u;
+        if ((same & lt) == 0u) ok = !((atomicOr(&tab[cand >> 3], 8u << sh) >> sh) & 8u);   // lowest lane of its value claims the rank
+        const unsigned bal = __ballot_sync(0xffffffffu, ok);
+        if (ok) {
+          const int idx = succ + __popc(bal & lt);
+          if (idx < ka[a]) atomicOr(&tab[cand >> 3], (unsigned) ((idx >= c0) + (idx >= c1) + (idx >= c2) + (idx >= c3)) << sh);
+          else             atomicAnd(&tab[cand >> 3], ~(0xFu << sh));              // more accepted than needed: give the rank back
+        }
+        succ += __popc(bal);
+      }
+    }
+  }
+  __syncwarp();
+
+  // ---- sweep 2
+  int run[5] = { 0, 0, 0, 0, 0 };
+  for (int u0 = 0; u0 < LW; u0 += 64) {
+    uint32_t w[2];
+    #pragma unroll
+    for (int h = 0; h < 2; h++) { const int u = u0 + h * 32 + lane; w[h] = (u < LW) ? load(par_s, u) : 0xFFFFFFFFu; }
+    #pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int u = u0 + h * 32 + lane;
+      uint32_t o = w[h];
+      if (ktot > 0) {                                                           // uniform
+        #pragma unroll
+        for (int q = 0; q < W; q++) {
+          const int x = (w[h] >> (8 * q)) & 0xFF;
+          #pragma unroll
+          for (int a = 0; a < 5; a++) {
+            if (ka[a] == 0) continue;                                           // uniform
+            const unsigned bal = __ballot_sync(0xffffffffu, x == a);
+            if (x == a) {
+              const int rank = run[a] + __popc(bal & lt);
+              const unsigned nib = (code[a * code_words + (rank >> 3)] >> ((rank & 7) * 4)) & 0xFu;
+              if (nib & 8u) o = (o & ~(0xFFu << (8 * q))) | ((nib & 7u) << (8 * q));
+            }
+            run[a] += __popc(bal);
+          }
+        }
+      }
+      if (u < LW) {
+        if (W == 4) reinterpret_cast<uint32_t *>(kid_s)[u] = o;
+        else kid_s[u] = (uint8_t) o;
+      }
+    }
+  }
+}
+
 } // namespace
 
 cudaError_t rsb_launch_null_simulate(const int *left, const int *right, const int *order, const int *level_start_host, int nlevels,
@@ -405,23 +600,55 @@ cudaError_t rsb_launch_null_simulate(const int *left, const int *right, const in
 
 cudaError_t rsb_launch_fitch_shuffle(const int *left, const int *right, const int *parent, const int *order, const int *level_start_host,
                                      int nlevels, int N, int L, const uint8_t *msa, unsigned long long seed, unsigned long long id0, int first_rep, int nrep,
-                                     uint8_t *res, uint8_t *anc, uint8_t *shanc, int *perm, cudaStream_t st)
+                                     uint8_t *res, uint8_t *anc, uint8_t *shanc, int *perm, uint8_t *sets_shared, int *d_flag, cudaStream_t st)
 {
   (void) parent;
   if (L > 65535) return cudaErrorInvalidValue;            // per-class counters are 16 bit
+  // The Fitch sets do not depend on the replicate unless the alignment holds unknown residues: then one up pass into
+  // `sets_shared` serves every replicate (its cost drops by the number of replicates) and only the traceback is per replicate.
+  int unknown = 1;
+  if (sets_shared && d_flag) {
+    cudaMemsetAsync(d_flag, 0, sizeof(int), st);
+    unknown_flag_kernel<<<296, 256, 0, st>>>(msa, (size_t) N * L, d_flag);
+    cudaMemcpyAsync(&unknown, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return e;
+  }
+  const bool shared = (unknown == 0);
   for (int lv = nlevels - 1; lv >= 0; lv--) {
     const int b = level_start_host[lv], cnt = level_start_host[lv + 1] - b;
-    fitch_up_level_kernel<<<dim3((L + 127) / 128, cnt, nrep), 128, 0, st>>>(left, right, order, b, N, L, msa, seed, id0, first_rep, anc);
+    uint8_t *dst = shared ? sets_shared : anc;
+    const int z = shared ? 1 : nrep, fr = shared ? 0 : first_rep;
+    if (L % 4 == 0) fitch_up_level_kernel<4><<<dim3((L / 4 + 127) / 128, cnt, z), 128, 0, st>>>(left, right, order, b, N, L, msa, seed, id0, fr, dst);
+    else            fitch_up_level_kernel<1><<<dim3((L + 127) / 128, cnt, z), 128, 0, st>>>(left, right, order, b, N, L, msa, seed, id0, fr, dst);
   }
+  const uint8_t *sets = shared ? sets_shared : anc + (size_t) first_rep * (N - 1) * L;
+  const size_t sets_stride = shared ? 0 : (size_t) (N - 1) * L;
   for (int lv = 0; lv < nlevels; lv++) {
     const int b = level_start_host[lv], cnt = level_start_host[lv + 1] - b;
-    fitch_down_level_kernel<<<dim3((L + 127) / 128, cnt, nrep), 128, 0, st>>>(left, right, order, b, N, L, seed, id0, first_rep, anc);
+    if (L % 4 == 0) fitch_down_level_kernel<4><<<dim3((L / 4 + 127) / 128, cnt, nrep), 128, 0, st>>>(left, right, order, b, N, L, seed, id0, first_rep, sets, sets_stride, anc);
+    else            fitch_down_level_kernel<1><<<dim3((L + 127) / 128, cnt, nrep), 128, 0, st>>>(left, right, order, b, N, L, seed, id0, first_rep, sets, sets_stride, anc);
   }
   permute_root_kernel<<<nrep, 256, 0, st>>>(N, L, seed, id0, first_rep, anc, shanc, perm);
   for (int lv = 0; lv < nlevels; lv++) {
     const int b = level_start_host[lv], cnt = level_start_host[lv + 1] - b;
     const long long tasks = 2LL * cnt * nrep;                    // branches of this level over all replicates
-    if (tasks <= RP_WARP_TASKS && L <= RPW_MAXWORDS * 32) {        // few branches: latency variant, one warp per branch
+    const int code_words = (L + 7) / 8;
+    const size_t smem = (size_t) RPR_WARPS * (5 * code_words + 32) * sizeof(unsigned);
+    static const int variant = getenv("RSCAPE_B200_REPLAY") ? atoi(getenv("RSCAPE_B200_REPLAY")) : 0;   // experiments: 1 = thread/warp hybrid
+    if (variant == 0 && smem <= 200 * 1024) {                    // row variant: one warp per branch, coalesced
+      const unsigned grid = (unsigned) ((tasks + RPR_WARPS - 1) / RPR_WARPS);
+      if (L % 4 == 0) {
+        cudaFuncSetAttribute(replay_level_row_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        replay_level_row_kernel<4><<<grid, RPR_WARPS * 32, smem, st>>>(left, right, order, b, cnt, N, L, msa, seed, id0, first_rep, nrep, anc, shanc, res, code_words);
+      } else {
+        cudaFuncSetAttribute(replay_level_row_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        replay_level_row_kernel<1><<<grid, RPR_WARPS * 32, smem, st>>>(left, right, order, b, cnt, N, L, msa, seed, id0, first_rep, nrep, anc, shanc, res, code_words);
+      }
+      continue;
+    }
+    static const long long warp_tasks = getenv("RSCAPE_B200_RPW_TASKS") ? atoll(getenv("RSCAPE_B200_RPW_TASKS")) : RP_WARP_TASKS;
+    if (tasks <= warp_tasks && L <= RPW_MAXWORDS * 32) {        // few branches: latency variant, one warp per branch
       const unsigned grid = (unsigned) ((tasks + RPW_WARPS - 1) / RPW_WARPS);
       replay_level_warp_kernel<<<grid, RPW_WARPS * 32, 0, st>>>(left, right, order, b, cnt, N, L, msa, seed, id0, first_rep, nrep, anc, shanc, res);
       continue;

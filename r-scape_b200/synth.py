@@ -127,3 +127,71 @@ def synthetic_msa(N, L, seed=42, gap_mean=0.11, frac_paired=0.6, n_frac=0.001, m
     else:
         raise ValueError("weights must be 'gamma' or 'ones' (PB / GSC weights are test-side preprocessing)")
     return ax, w, partner
+
+
+def synthetic_family(N, L, seed=42, mean_len=0.01, gap_mean=0.11, frac_paired=0.6, n_frac=0.001, weights="gamma"):
+    """Seeded synthetic alignment TOGETHER WITH the tree it evolved on (R-scape infers its tree from the alignment, so
+    the null generators always see a tree that explains the data; a tree unrelated to the alignment would make the
+    parsimony reconstruction place substitutions on nearly every branch and column).  Same recipe as synthetic_msa
+    otherwise: nested random helices over ~60% of the columns kept complementary 90% of the time, Beta(0.5,4)
+    per-column gap fractions, 0.1% N, Gamma(2,1/2) weights.  Branch lengths are Exp(mean_len) substitutions per site.
+    Returns (ax uint8 [N][L], wgt float64 [N], pair partner array, Tree)."""
+    rng = np.random.default_rng(seed)
+    tree = random_tree(N, rng, mean_len)
+    partner = -np.ones(L, int)
+    target = int(frac_paired * L) // 2
+    tries = 0
+    while (partner >= 0).sum() // 2 < target and tries < 20 * L:
+        tries += 1
+        hl = int(rng.integers(3, 9))
+        i = int(rng.integers(0, max(1, L - 2 * hl - 4)))
+        lo, hi = i + 2 * hl + 3, min(L, i + 2 * hl + 4 + max(4, L // 4))
+        if lo >= hi:
+            continue
+        j = int(rng.integers(lo, hi))
+        if j >= L:
+            continue
+        a = np.arange(i, i + hl)
+        b = j - np.arange(hl)
+        span = np.arange(i, j + 1)
+        if (partner[a] >= 0).any() or (partner[b] >= 0).any():
+            continue
+        inner = partner[span]
+        inner = inner[inner >= 0]
+        if ((inner < i) | (inner > j)).any():
+            continue
+        partner[a] = b
+        partner[b] = a
+    comp = np.array([3, 2, 1, 0], dtype=np.uint8)
+    upper = np.nonzero(partner > np.arange(L))[0]
+    root = rng.integers(0, 4, L).astype(np.uint8)
+    root[partner[upper]] = comp[root[upper]]
+    anc = np.empty((max(N - 1, 1), L), dtype=np.uint8)
+    anc[0] = root
+    ax = np.empty((N, L), dtype=np.uint8)
+    for v in range(N - 1):                                      # parents are numbered before their children
+        for child, t in ((tree.left[v], tree.ld[v]), (tree.right[v], tree.rd[v])):
+            row = anc[v].copy()
+            mut = np.nonzero(rng.random(L) < 1.0 - np.exp(-t))[0]
+            if len(mut):
+                row[mut] = rng.integers(0, 4, len(mut))
+                pm = mut[partner[mut] >= 0]
+                keep = pm[rng.random(len(pm)) < 0.9]
+                lo_side = np.minimum(keep, partner[keep])
+                row[partner[lo_side]] = comp[row[lo_side]]
+            if child > 0:
+                anc[child] = row
+            else:
+                ax[-child] = row
+    gapf = np.minimum(rng.beta(0.5, 4.0, L) * (gap_mean / 0.111), 0.7)
+    ax[rng.random((N, L)) < gapf[None, :]] = 4
+    ax[rng.random((N, L)) < n_frac] = 15
+    if weights == "gamma":
+        w = rng.gamma(2.0, 0.5, N)
+        w *= N / w.sum()
+    elif weights == "ones":
+        w = np.ones(N)
+    else:
+        raise ValueError("weights must be 'gamma' or 'ones'")
+    return ax, w, partner, tree
+
