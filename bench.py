@@ -235,10 +235,10 @@ def main():
         """R-scape's default null model on the device: Fitch + tree-substitution shuffle (null_rscape, R-scape.c:1653-1661).
         Replicates are keyed by their global id, so every rank that needs replicate 0 generates the same alignment."""
         ctx.set_tree(tree.left, tree.right, tree.parent, tree.ld, tree.rd)
+        if not own0:                                                    # the width pass wants replicate 0 first
+            ctx.null_fitch_shuffle(host_msa.numpy(), SEED, 1, first_rep=w0_entry, first_id=0)
         if n_mine:
             ctx.null_fitch_shuffle(host_msa.numpy(), SEED, n_mine, first_rep=0, first_id=my_ids[0])
-        if not own0:
-            ctx.null_fitch_shuffle(host_msa.numpy(), SEED, 1, first_rep=w0_entry, first_id=0)
 
     def sharded_scan(src, hist_w=None, want_cov=False):
         """One scan with the pair grid sharded over the ranks: three phases, one small all-reduce between them."""

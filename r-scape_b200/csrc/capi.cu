@@ -52,7 +52,8 @@ cudaError_t rsb_launch_null_simulate(const int *left, const int *right, const in
                                      uint8_t *res, uint8_t *scratch, cudaStream_t st);
 cudaError_t rsb_launch_fitch_shuffle(const int *left, const int *right, const int *parent, const int *order, const int *level_start,
                                      int nlevels, int N, int L, const uint8_t *msa, unsigned long long seed, unsigned long long id0, int first_rep, int nrep,
-                                     uint8_t *res, uint8_t *anc, uint8_t *shanc, int *perm, uint8_t *sets_shared, int *d_flag, cudaStream_t st);
+                                     uint8_t *res, uint8_t *anc, uint8_t *shanc, int *perm, uint8_t *sets_shared, int build_sets, cudaStream_t st);
+cudaError_t rsb_launch_unknown_check(const uint8_t *msa, size_t n, int *d_flag, int *unknown, cudaStream_t st);
 
 namespace {
 constexpr int HIST_BINS = 1 << 22;
@@ -91,6 +92,12 @@ struct rsb_ctx {
   double *d_nseff = nullptr, *d_pm = nullptr, *d_cov = nullptr, *d_tmp = nullptr;
   double *d_mrow = nullptr, *d_mcol = nullptr; size_t mrow_stride = 0, mcol_stride = 0;   // marginal partials of the gram tiles, per slot
   double *d_rowpart = nullptr, *d_colpart = nullptr, *d_mm = nullptr, *d_scal = nullptr, *d_covx = nullptr, *d_minmax = nullptr;
+  // generation stream: the null generators run beside the scans; pool_ready[rep] is the event after which pool entry
+  // `rep` is complete (NULL: nothing pending), taken from a ring of events
+  cudaStream_t stream_gen = nullptr, stream_hi = nullptr;
+  cudaEvent_t ev_exit = nullptr;
+  std::vector<cudaEvent_t> pool_ready, gen_ring;
+  size_t gen_next = 0;
   void *d_logtab = nullptr;                          // table of the statistic kernels' log (stats.cu), built once
   double *h_mm = nullptr; size_t h_mm_cap = 0;      // pinned staging of the per-replicate min/max: a pageable target would block the enqueuing thread
   double *d_meanp = nullptr, *d_w = nullptr, *d_blocksum = nullptr, *d_msum = nullptr, *d_covsum = nullptr;
@@ -172,6 +179,8 @@ void free_geo(Geo &g) { dfree(g.d_tiles); dfree(g.d_wdig); dfree(g.d_wq); g.read
 
 void free_plan(rsb_ctx *c)
 {
+  if (c->stream_gen) cudaStreamSynchronize(c->stream_gen);
+  c->pool_ready.clear();
   free_geo(c->geo[0]); free_geo(c->geo[1]);
   dfree(c->d_res); dfree(c->d_planeA); dfree(c->d_planeB); dfree(c->d_cnt); dfree(c->d_nseff); dfree(c->d_pm); dfree(c->d_cov);
   dfree(c->d_mrow); dfree(c->d_mcol); dfree(c->d_tmp); dfree(c->d_rowpart); dfree(c->d_colpart); dfree(c->d_mm); dfree(c->d_scal); dfree(c->d_covx); dfree(c->d_minmax);
@@ -512,6 +521,17 @@ static int pool_range_ok(rsb_ctx *ctx, int first_rep, int nrep)
   return 0;
 }
 
+// make `st` wait until the generators have finished pool entries [first_rep, first_rep + nrep)
+static int pool_wait(rsb_ctx *ctx, int first_rep, int nrep, cudaStream_t st)
+{
+  cudaEvent_t last = nullptr;
+  for (int r = first_rep; r < first_rep + nrep && r < (int) ctx->pool_ready.size(); r++) {
+    cudaEvent_t e = ctx->pool_ready[r];
+    if (e && e != last) { RSB_CUDA_OK(cudaStreamWaitEvent(st, e, 0)); last = e; }
+  }
+  return 0;
+}
+
 extern "C" {
 
 const char *rsb_create_error(void) { return g_create_err; }
@@ -542,6 +562,17 @@ int rsb_create(int device, void *stream, rsb_ctx **out)
   else { cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking); c->own_stream = true; }
   cudaStreamCreateWithFlags(&c->stream_aux, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&c->stream_copy, cudaStreamNonBlocking);
+  {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);                     // lo = least, hi = greatest priority
+    cudaStreamCreateWithPriority(&c->stream_gen, cudaStreamNonBlocking, lo);
+    cudaStreamCreateWithPriority(&c->stream_hi, cudaStreamNonBlocking, hi);
+    cudaStreamDestroy(c->stream_copy);
+    cudaStreamCreateWithPriority(&c->stream_copy, cudaStreamNonBlocking, hi);
+  }
+  cudaEventCreateWithFlags(&c->ev_exit, cudaEventDisableTiming);
+  c->gen_ring.resize(64);
+  for (auto &e : c->gen_ring) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&c->ev_entry, cudaEventDisableTiming);
   for (int g = 0; g < 2; g++) {
     cudaEventCreateWithFlags(&c->ev_up[g], cudaEventDisableTiming);
@@ -563,14 +594,15 @@ void rsb_destroy(rsb_ctx *ctx)
 {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
+  cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->stream_gen);
   for (auto &p : ctx->pending) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   for (auto &p : ctx->pending_aux) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   for (auto &p : ctx->pending_stage) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   free_plan(ctx);
   if (ctx->d_logtab) cudaFree(ctx->d_logtab);
-  cudaStreamSynchronize(ctx->stream_aux); cudaStreamSynchronize(ctx->stream_copy);
-  cudaStreamDestroy(ctx->stream_aux); cudaStreamDestroy(ctx->stream_copy);
+  cudaStreamSynchronize(ctx->stream_aux); cudaStreamSynchronize(ctx->stream_copy); cudaStreamSynchronize(ctx->stream_gen);
+  cudaStreamDestroy(ctx->stream_aux); cudaStreamDestroy(ctx->stream_copy); cudaStreamDestroy(ctx->stream_gen); cudaStreamDestroy(ctx->stream_hi); cudaEventDestroy(ctx->ev_exit);
+  for (auto &e : ctx->gen_ring) cudaEventDestroy(e);
   cudaEventDestroy(ctx->ev_entry);
   for (int g = 0; g < 2; g++) { cudaEventDestroy(ctx->ev_up[g]); cudaEventDestroy(ctx->ev_counts[g]); cudaEventDestroy(ctx->ev_stats[g]); cudaEventDestroy(ctx->ev_marg[g]); cudaEventDestroy(ctx->ev_statk[g]); }
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -849,7 +881,7 @@ int rsb_null_width(rsb_ctx *ctx, const uint8_t *null0, int64_t row_stride, int o
 // src_dev: device-resident nulls [nrep][N][L] read in place (no copy), else host/strided input that is uploaded.
 static int null_hist_pipelined(rsb_ctx *ctx, const uint8_t *nulls, int nrep, int64_t row_stride, int64_t rep_stride, int on_device,
                                int stat, int covclass, int actype, unsigned mask, double tol, double w, double bmin,
-                               double *minmax)
+                               double *minmax, int pool_first = -1)
 {
   const bool raf = (stat == RSB_RAF || stat == RSB_RAFS);
   const bool in_place = (on_device && row_stride == ctx->L && rep_stride == (int64_t) ctx->N * ctx->L);
@@ -857,7 +889,10 @@ static int null_hist_pipelined(rsb_ctx *ctx, const uint8_t *nulls, int nrep, int
   const int  chunk = std::max(1, ctx->Rcap / G);
   const size_t repbytes = (size_t) ctx->N * ctx->L;
   static const int serial = getenv("RSCAPE_B200_SERIAL") ? atoi(getenv("RSCAPE_B200_SERIAL")) : 0;      // experiments: 1 = statistics on the main stream, 2 = pack too
-  cudaStream_t st_aux = (serial & 1) ? ctx->stream : ctx->stream_aux, st_copy = (serial & 2) ? ctx->stream : ctx->stream_copy;
+  // contraction + statistic run on an internal high-priority stream, so that their blocks are placed ahead of those of the
+  // null generators working on later replicates (generation stream, lowest priority)
+  cudaStream_t sm = ctx->stream_hi;
+  cudaStream_t st_aux = (serial & 1) ? sm : ctx->stream_aux, st_copy = (serial & 2) ? sm : ctx->stream_copy;
 
   if (minmax && ctx->h_mm_cap < (size_t) nrep) {
     if (ctx->h_mm) cudaFreeHost(ctx->h_mm);
@@ -865,8 +900,10 @@ static int null_hist_pipelined(rsb_ctx *ctx, const uint8_t *nulls, int nrep, int
     RSB_CUDA_OK(cudaMallocHost(&ctx->h_mm, sizeof(double) * 2 * (size_t) nrep));
     ctx->h_mm_cap = (size_t) nrep;
   }
-  RSB_CUDA_OK(cudaMemcpyAsync(ctx->d_w, &w, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   RSB_CUDA_OK(cudaEventRecord(ctx->ev_entry, ctx->stream));
+  RSB_CUDA_OK(cudaStreamWaitEvent(sm, ctx->ev_entry, 0));
+  RSB_CUDA_OK(cudaMemcpyAsync(ctx->d_w, &w, sizeof(double), cudaMemcpyHostToDevice, sm));
+  RSB_CUDA_OK(cudaEventRecord(ctx->ev_entry, sm));
   RSB_CUDA_OK(cudaStreamWaitEvent(st_aux, ctx->ev_entry, 0));
   RSB_CUDA_OK(cudaStreamWaitEvent(st_copy, ctx->ev_entry, 0));
   bool used[2] = { false, false };
@@ -879,12 +916,12 @@ static int null_hist_pipelined(rsb_ctx *ctx, const uint8_t *nulls, int nrep, int
     const int pg = pc % G, ps0 = pg * chunk, pn = std::min(chunk, nrep - pr0);
     cudaEvent_t a0 = nullptr, a1 = nullptr, am = nullptr, as = nullptr;
     if (ctx->profile) { cudaEventCreate(&a0); cudaEventCreate(&a1); cudaEventCreate(&am); cudaEventCreate(&as); }
-    RSB_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->ev_marg[pg], 0));
-    if (pc >= G) RSB_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->ev_stats[pg], 0));   // the group's scores and partial sums have been consumed
-    if (ctx->profile) cudaEventRecord(a0, ctx->stream);
-    if (enqueue_statistic(ctx, ps0, pn, stat, covclass, mask, ctx->stream, 3, 1)) return 1;
-    if (ctx->profile) cudaEventRecord(am, ctx->stream);
-    RSB_CUDA_OK(cudaEventRecord(ctx->ev_statk[pg], ctx->stream));
+    RSB_CUDA_OK(cudaStreamWaitEvent(sm, ctx->ev_marg[pg], 0));
+    if (pc >= G) RSB_CUDA_OK(cudaStreamWaitEvent(sm, ctx->ev_stats[pg], 0));   // the group's scores and partial sums have been consumed
+    if (ctx->profile) cudaEventRecord(a0, sm);
+    if (enqueue_statistic(ctx, ps0, pn, stat, covclass, mask, sm, 3, 1)) return 1;
+    if (ctx->profile) cudaEventRecord(am, sm);
+    RSB_CUDA_OK(cudaEventRecord(ctx->ev_statk[pg], sm));
     RSB_CUDA_OK(cudaStreamWaitEvent(st_aux, ctx->ev_statk[pg], 0));
     if (ctx->profile) cudaEventRecord(as, st_aux);
     if (enqueue_statistic(ctx, ps0, pn, stat, covclass, mask, st_aux, 3, 2)) return 1;
@@ -902,6 +939,7 @@ static int null_hist_pipelined(rsb_ctx *ctx, const uint8_t *nulls, int nrep, int
     const int g = c % G, s0 = g * chunk, n = std::min(chunk, nrep - r0);
     const uint8_t *src;
     if (used[g]) RSB_CUDA_OK(cudaStreamWaitEvent(st_copy, ctx->ev_counts[g], 0));       // the group's slots and planes have been consumed
+    if (pool_first >= 0 && pool_wait(ctx, pool_first + r0, n, st_copy)) return 1;    // entries still being generated
     if (in_place) src = nulls + (size_t) r0 * repbytes;
     else {
       if (upload_msa(ctx, nulls + (size_t) r0 * rep_stride, row_stride, rep_stride, n, s0, on_device, st_copy)) return 1;
@@ -909,10 +947,10 @@ static int null_hist_pipelined(rsb_ctx *ctx, const uint8_t *nulls, int nrep, int
     }
     if (enqueue_pack(ctx, raf ? 1 : 0, s0, n, src, st_copy)) return 1;                   // HBM-bound transpose: hides under the previous gram
     RSB_CUDA_OK(cudaEventRecord(ctx->ev_up[g], st_copy));
-    RSB_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->ev_up[g], 0));
+    RSB_CUDA_OK(cudaStreamWaitEvent(sm, ctx->ev_up[g], 0));
     // (the counts and marginal partials of this group were consumed by S(c - G), earlier on this stream)
-    if (enqueue_gram(ctx, raf ? 1 : 0, s0, n, ctx->stream)) return 1;
-    RSB_CUDA_OK(cudaEventRecord(ctx->ev_counts[g], ctx->stream));
+    if (enqueue_gram(ctx, raf ? 1 : 0, s0, n, sm)) return 1;
+    RSB_CUDA_OK(cudaEventRecord(ctx->ev_counts[g], sm));
 
     RSB_CUDA_OK(cudaStreamWaitEvent(st_aux, ctx->ev_counts[g], 0));
     if (!raf && enqueue_marginals(ctx, s0, n, tol, st_aux)) return 1;
@@ -922,7 +960,9 @@ static int null_hist_pipelined(rsb_ctx *ctx, const uint8_t *nulls, int nrep, int
     else if (c >= 1) { if (tail(c - 1, r0 - chunk)) return 1; }
   }
   if (G > 1 && c >= 1) { if (tail(c - 1, (c - 1) * chunk)) return 1; }
-  for (int g = 0; g < G; g++) if (used[g]) RSB_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->ev_stats[g], 0));
+  for (int g = 0; g < G; g++) if (used[g]) RSB_CUDA_OK(cudaStreamWaitEvent(sm, ctx->ev_stats[g], 0));
+  RSB_CUDA_OK(cudaEventRecord(ctx->ev_exit, sm));                      // back to the caller's stream
+  RSB_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->ev_exit, 0));
   return 0;
 }
 
@@ -946,7 +986,7 @@ int rsb_null_hist_pool(rsb_ctx *ctx, int first_rep, int nrep, int stat, int covc
   if (resolve_stat(ctx, stat, covclass)) return 1;
   const size_t rb = (size_t) ctx->N * ctx->L;
   if (null_hist_pipelined(ctx, ctx->d_pool + (size_t) first_rep * rb, nrep, ctx->L, (int64_t) rb, 1, stat, covclass, actype,
-                          allow_mask(allowpair), tol, w, bmin, minmax)) return 1;
+                          allow_mask(allowpair), tol, w, bmin, minmax, first_rep)) return 1;
   if (check_flags(ctx, "null_rscape")) return 1;
   if (minmax) memcpy(minmax, ctx->h_mm, sizeof(double) * 2 * (size_t) nrep);
   return 0;
@@ -956,6 +996,8 @@ int rsb_null_width_pool(rsb_ctx *ctx, int rep, int stat, int covclass, int actyp
                         double w_old, double bmin, int hpts, double *w_out, double *mincov, double *maxcov)
 {
   if (pool_range_ok(ctx, rep, 1)) return 1;
+  RSB_CUDA_OK(cudaSetDevice(ctx->device));
+  if (pool_wait(ctx, rep, 1, ctx->stream)) return 1;
   return rsb_null_width(ctx, ctx->d_pool + (size_t) rep * ctx->N * ctx->L, ctx->L, 1, stat, covclass, actype, allowpair, tol,
                         w_old, bmin, hpts, w_out, mincov, maxcov);
 }
@@ -987,6 +1029,8 @@ int rsb_sharded_counts(rsb_ctx *ctx, const uint8_t *msa, int64_t row_stride, int
 int rsb_sharded_counts_pool(rsb_ctx *ctx, int rep, double tol, double *marg_sums)
 {
   if (pool_range_ok(ctx, rep, 1)) return 1;
+  RSB_CUDA_OK(cudaSetDevice(ctx->device));
+  if (pool_wait(ctx, rep, 1, ctx->stream)) return 1;
   return rsb_sharded_counts(ctx, ctx->d_pool + (size_t) rep * ctx->N * ctx->L, ctx->L, 1, tol, marg_sums);
 }
 
@@ -1165,7 +1209,9 @@ int rsb_pool_reserve(rsb_ctx *ctx, int nrep)
   if (ctx->N == 0) { rsb_set_error(ctx, "rsb_configure first"); return 1; }
   if (nrep < 1) { rsb_set_error(ctx, "bad pool size"); return 1; }
   if (nrep <= ctx->Rpool) return 0;
+  RSB_CUDA_OK(cudaStreamSynchronize(ctx->stream_gen));
   RSB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  ctx->pool_ready.assign(nrep, nullptr);
   dfree(ctx->d_pool); dfree(ctx->d_simscratch); dfree(ctx->d_anc); dfree(ctx->d_shanc); dfree(ctx->d_perm);
   RSB_CUDA_OK(cudaMalloc(&ctx->d_pool, (size_t) nrep * ctx->N * ctx->L));
   ctx->Rpool = nrep;
@@ -1197,6 +1243,8 @@ int rsb_null_simulate(rsb_ctx *ctx, const double *Q, const uint8_t *root, const 
     RSB_CUDA_OK(cudaMemcpy2DAsync(ctx->d_gapmask, L, gapmask, (size_t) gap_stride, L, N, cudaMemcpyHostToDevice, ctx->stream));
   }
   RSB_CUDA_OK(cudaStreamSynchronize(ctx->stream));       // pb is a host temporary
+  RSB_CUDA_OK(cudaStreamSynchronize(ctx->stream_gen));   // (this generator runs on the main stream)
+  for (int r = first_rep; r < first_rep + nrep; r++) ctx->pool_ready[r] = nullptr;
   RSB_CUDA_OK(rsb_launch_null_simulate(ctx->d_left, ctx->d_right, ctx->d_order, ctx->h_level_start.data(), ctx->nlevels, ctx->d_pcdf, N, L, ctx->d_root, gapmask ? ctx->d_gapmask : nullptr, L,
                                        seed, first_id, first_rep, nrep, ctx->d_pool, ctx->d_simscratch, ctx->stream));
   ctx->launches += ctx->nlevels;
@@ -1215,10 +1263,31 @@ int rsb_null_fitch_shuffle(rsb_ctx *ctx, const uint8_t *msa, int64_t row_stride,
   if (!ctx->d_perm)  RSB_CUDA_OK(cudaMalloc(&ctx->d_perm, sizeof(int) * (size_t) ctx->Rpool * L));
   if (!ctx->d_sets)  RSB_CUDA_OK(cudaMalloc(&ctx->d_sets, (size_t) nn * L));
   if (!ctx->d_genflag) RSB_CUDA_OK(cudaMalloc(&ctx->d_genflag, sizeof(int)));
-  RSB_CUDA_OK(cudaMemcpy2DAsync(ctx->d_msa0, L, msa, (size_t) row_stride, L, N, cudaMemcpyHostToDevice, ctx->stream));
-  RSB_CUDA_OK(rsb_launch_fitch_shuffle(ctx->d_left, ctx->d_right, ctx->d_parent, ctx->d_order, ctx->h_level_start.data(), ctx->nlevels, N, L,
-                                       ctx->d_msa0, seed, first_id, first_rep, nrep, ctx->d_pool, ctx->d_anc, ctx->d_shanc, ctx->d_perm, ctx->d_sets, ctx->d_genflag, ctx->stream));
-  ctx->launches += 1 + 3 * ctx->nlevels;
+  // Runs on the generation stream, after everything already queued on the caller's stream (which may still read the
+  // pool), in chunks of growing size: the first entry alone (the width pass wants it first), then 4, 8, 16 ...  Each chunk
+  // records an event; the scans wait for the event of the entries they pack, so scanning starts while later replicates
+  // are still being generated.
+  cudaStream_t sg = ctx->stream_gen;
+  RSB_CUDA_OK(cudaEventRecord(ctx->ev_entry, ctx->stream));
+  RSB_CUDA_OK(cudaStreamWaitEvent(sg, ctx->ev_entry, 0));
+  RSB_CUDA_OK(cudaMemcpy2DAsync(ctx->d_msa0, L, msa, (size_t) row_stride, L, N, cudaMemcpyHostToDevice, sg));
+  int unknown = 1;
+  RSB_CUDA_OK(rsb_launch_unknown_check(ctx->d_msa0, (size_t) N * L, ctx->d_genflag, &unknown, sg));
+  uint8_t *sets = unknown ? nullptr : ctx->d_sets;
+  int off = 0, chunks = 0, next = 4;                                 // chunk sizes 1, 4, 8, 16, 32, then the rest
+  while (off < nrep) {
+    int n = (off == 0) ? 1 : next;
+    if (off > 0) next *= 2;
+    if (chunks >= 5 || nrep - off - n < 4) n = nrep - off;
+    RSB_CUDA_OK(rsb_launch_fitch_shuffle(ctx->d_left, ctx->d_right, ctx->d_parent, ctx->d_order, ctx->h_level_start.data(), ctx->nlevels, N, L,
+                                         ctx->d_msa0, seed, first_id + (uint64_t) off, first_rep + off, n, ctx->d_pool, ctx->d_anc, ctx->d_shanc,
+                                         ctx->d_perm, sets, off == 0, sg));
+    cudaEvent_t e = ctx->gen_ring[ctx->gen_next++ % ctx->gen_ring.size()];
+    RSB_CUDA_OK(cudaEventRecord(e, sg));
+    for (int r = first_rep + off; r < first_rep + off + n; r++) ctx->pool_ready[r] = e;
+    off += n; chunks++;
+  }
+  ctx->launches += chunks * (1 + 3 * ctx->nlevels);
   return 0;
 }
 
@@ -1227,6 +1296,7 @@ int rsb_pool_get(rsb_ctx *ctx, int first_rep, int nrep, uint8_t *out)
   RSB_CUDA_OK(cudaSetDevice(ctx->device));
   if (pool_range_ok(ctx, first_rep, nrep)) return 1;
   const size_t rb = (size_t) ctx->N * ctx->L;
+  if (pool_wait(ctx, first_rep, nrep, ctx->stream)) return 1;
   RSB_CUDA_OK(cudaMemcpyAsync(out, ctx->d_pool + first_rep * rb, rb * nrep, cudaMemcpyDeviceToHost, ctx->stream));
   RSB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
   return 0;
@@ -1237,6 +1307,8 @@ int rsb_pool_put(rsb_ctx *ctx, int first_rep, int nrep, const uint8_t *in)
   RSB_CUDA_OK(cudaSetDevice(ctx->device));
   if (pool_range_ok(ctx, first_rep, nrep)) return 1;
   const size_t rb = (size_t) ctx->N * ctx->L;
+  if (pool_wait(ctx, first_rep, nrep, ctx->stream)) return 1;                      // a generator may still be writing these entries
+  for (int r = first_rep; r < first_rep + nrep; r++) ctx->pool_ready[r] = nullptr;
   RSB_CUDA_OK(cudaMemcpyAsync(ctx->d_pool + first_rep * rb, in, rb * nrep, cudaMemcpyHostToDevice, ctx->stream));
   RSB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
   return 0;

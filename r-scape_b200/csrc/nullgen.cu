@@ -445,7 +445,7 @@ replay_level_warp_kernel(const int *__restrict__ left, const int *__restrict__ r
 //   sweep 2  (shuffled parent row -> child row): a column of class a is the (running count of a)-th of its class; the
 //            code table says whether that rank was drawn and what it becomes (:1645-1757).
 // Work per branch is a few coalesced passes over its rows, independent of how the substitutions fall.
-constexpr int RPR_WARPS = 8;
+constexpr int RPR_WARPS = 4;        // 4 warps x ~4.6 KB of code table (L = 1800): two such blocks fit beside the tcgen05 kernel's 190 KB ring
 
 template <int W>
 __global__ void __launch_bounds__(RPR_WARPS * 32)
@@ -598,23 +598,26 @@ cudaError_t rsb_launch_null_simulate(const int *left, const int *right, const in
   return cudaGetLastError();
 }
 
+// does the alignment hold residues other than A C G U and the gap?  Synchronises st.
+cudaError_t rsb_launch_unknown_check(const uint8_t *msa, size_t n, int *d_flag, int *unknown, cudaStream_t st)
+{
+  cudaMemsetAsync(d_flag, 0, sizeof(int), st);
+  unknown_flag_kernel<<<296, 256, 0, st>>>(msa, n, d_flag);
+  cudaMemcpyAsync(unknown, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st);
+  return cudaStreamSynchronize(st);
+}
+
 cudaError_t rsb_launch_fitch_shuffle(const int *left, const int *right, const int *parent, const int *order, const int *level_start_host,
                                      int nlevels, int N, int L, const uint8_t *msa, unsigned long long seed, unsigned long long id0, int first_rep, int nrep,
-                                     uint8_t *res, uint8_t *anc, uint8_t *shanc, int *perm, uint8_t *sets_shared, int *d_flag, cudaStream_t st)
+                                     uint8_t *res, uint8_t *anc, uint8_t *shanc, int *perm, uint8_t *sets_shared, int build_sets, cudaStream_t st)
 {
   (void) parent;
   if (L > 65535) return cudaErrorInvalidValue;            // per-class counters are 16 bit
-  // The Fitch sets do not depend on the replicate unless the alignment holds unknown residues: then one up pass into
-  // `sets_shared` serves every replicate (its cost drops by the number of replicates) and only the traceback is per replicate.
-  int unknown = 1;
-  if (sets_shared && d_flag) {
-    cudaMemsetAsync(d_flag, 0, sizeof(int), st);
-    unknown_flag_kernel<<<296, 256, 0, st>>>(msa, (size_t) N * L, d_flag);
-    cudaMemcpyAsync(&unknown, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st);
-    cudaError_t e = cudaStreamSynchronize(st);
-    if (e != cudaSuccess) return e;
-  }
-  const bool shared = (unknown == 0);
+  // The Fitch sets do not depend on the replicate unless the alignment holds unknown residues (rsb_launch_unknown_check):
+  // then one up pass into `sets_shared` serves every replicate (build_sets: run it now; otherwise it is already there)
+  // and only the traceback is per replicate.  sets_shared == NULL: sets per replicate, in the residue buffer itself.
+  const bool shared = sets_shared != nullptr;
+  if (!shared || build_sets)
   for (int lv = nlevels - 1; lv >= 0; lv--) {
     const int b = level_start_host[lv], cnt = level_start_host[lv + 1] - b;
     uint8_t *dst = shared ? sets_shared : anc;
@@ -639,10 +642,10 @@ cudaError_t rsb_launch_fitch_shuffle(const int *left, const int *right, const in
     if (variant == 0 && smem <= 200 * 1024) {                    // row variant: one warp per branch, coalesced
       const unsigned grid = (unsigned) ((tasks + RPR_WARPS - 1) / RPR_WARPS);
       if (L % 4 == 0) {
-        cudaFuncSetAttribute(replay_level_row_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        if (smem > 48 * 1024) cudaFuncSetAttribute(replay_level_row_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
         replay_level_row_kernel<4><<<grid, RPR_WARPS * 32, smem, st>>>(left, right, order, b, cnt, N, L, msa, seed, id0, first_rep, nrep, anc, shanc, res, code_words);
       } else {
-        cudaFuncSetAttribute(replay_level_row_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        if (smem > 48 * 1024) cudaFuncSetAttribute(replay_level_row_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
         replay_level_row_kernel<1><<<grid, RPR_WARPS * 32, smem, st>>>(left, right, order, b, cnt, N, L, msa, seed, id0, first_rep, nrep, anc, shanc, res, code_words);
       }
       continue;
