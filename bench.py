@@ -223,6 +223,7 @@ def main():
     my_ids = list(range(R)) if args.grid_shard else pkg.parallel.null_shard(R, world, rank)   # replicate ids held by this rank
     n_mine = len(my_ids)
     own0 = (n_mine > 0 and my_ids[0] == 0)
+    real_rank = world - 1                                             # the input alignment is scanned by the rank with the fewest nulls
     ctx.pool_reserve(n_mine + (0 if own0 else 1))
     w0_entry = 0 if own0 else n_mine                                  # pool entry holding replicate 0 (width pass)
     SEED = 20261017
@@ -270,7 +271,7 @@ def main():
         if n_mine:
             ctx.null_hist_pool(0, n_mine, w, pkg.GT, pkg.C16, pkg.APC, want_minmax=False)   # run_rscape(RANSS) + null_add2cumranklist
         out = None
-        if rank == 0:
+        if rank == real_rank:
             out = ctx.scan(real, pkg.GT, pkg.C16, pkg.APC, want_cov=isinstance(real, np.ndarray))   # run_rscape(GIVSS)
         bins, n, imax = ctx.hist_read(NB)
         bins = pkg.parallel.reduce_histogram(bins, device="cuda")
@@ -323,19 +324,21 @@ def main():
         ctx.set_weights(wgt)
         generate()
         w, bins, out = job(host_msa.numpy())
-        if rank == 0 and out is not None and out.get("cov") is not None:
+        if rank == real_rank and out is not None and out.get("cov") is not None:
             cov_out[:] = out["cov"]
 
     ms_e2e = timed(job_e2e, args.steps, 1)
     e2e_value = cells_total * args.steps / (ms_e2e * 1e-3)
-    h2d = (2 if rank == 0 else 1) * N * L + (N - 1) * (3 * 4 + 2 * 8) + N * 8 + (N - 1) * 2 * 16 * 8
-    d2h = NB * 8 + (L * L * 8 if rank == 0 else 0)
+    # whole-job bytes per step: every rank uploads the alignment (generator), its tree and weights, and reads its histogram;
+    # the rank scanning the input alignment uploads it once more and reads the score matrix
+    h2d = (world + 1) * N * L + world * ((N - 1) * (3 * 4 + 2 * 8) + N * 8)
+    d2h = world * NB * 8 + L * L * 8
 
     # ---- roofline of the dominant kernel (tcgen05 gram): algorithmic ops / measured launch time -------------
     # launches during the value run: per step, gram launches = width(1) + ceil(nulls/slots) + real(1 on rank 0)
     pairs = L * (L - 1) / 2.0
     gram_ms_avg = cnt["gram_ms"] / max(1, cnt["gram_launches"])
-    scans_this_rank = (n_mine + 1 + (1 if (rank == 0 or args.grid_shard) else 0)) * (args.steps + args.warmup)
+    scans_this_rank = (n_mine + 1 + (1 if (rank == real_rank or args.grid_shard) else 0)) * (args.steps + args.warmup)
     if args.grid_shard:
         scans_this_rank /= world                                     # every rank contracts 1/world of each scan's tiles
     ops_alg_per_launch = 32.0 * pairs * N * scans_this_rank / max(1, cnt["gram_launches"])

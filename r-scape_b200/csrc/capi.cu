@@ -17,6 +17,10 @@
 cudaError_t rsb_launch_gram_i8(int S, const CUtensorMap &tmA, const CUtensorMap &tmB, const int2 *tiles, int ntiles,
                                int rep0, int nrep, int L, int Lp, int kstages, long long *cnt, double scale, double *mrow,
                                double *mcol, int nJB, int nIB, int grid, cudaStream_t st);
+cudaError_t rsb_launch_gram_i8_pair(int S, const CUtensorMap &tmA, const CUtensorMap &tmBh, const int2 *tiles2, int ntiles2,
+                                    int rep0, int nrep, int L, int Lp, int kstages, long long *cnt, double scale, double *mrow,
+                                    double *mcol, int nJB, int nIB, int max_clusters, cudaStream_t st);
+int rsb_gram_pair_clusters(int S);
 cudaError_t rsb_launch_pack(int S, const uint8_t *res, int nrep, int N, int L, long long rep_stride_res, const uint8_t *wdig,
                             int Kpad, uint8_t *planeA, int MA, uint8_t *planeB, int NBrows, int Lcover, cudaStream_t st);
 cudaError_t rsb_launch_colsum(const uint8_t *res, int N, int L, const unsigned long long *wq, unsigned long long *colsum, cudaStream_t st);
@@ -61,8 +65,9 @@ constexpr int HIST_BINS = 1 << 22;
 // operand geometry for one slice count
 struct Geo {
   int S = 0, CJ = 0, NT = 0, nJB = 0, NBrows = 0, ntiles = 0, q = 0;
-  CUtensorMap tmB;
-  int2 *d_tiles = nullptr;
+  CUtensorMap tmB, tmBh;                  // planeB boxes of a whole tile / of half a tile (CTA-pair kernel)
+  int2 *d_tiles = nullptr, *d_tiles2 = nullptr;      // upper-triangle tiles (ib, jb) / row-block pairs (ibp, jb)
+  int ntiles2 = 0, pair_clusters = 0;     // pair_clusters: resident CTA pairs of the pair kernel (0 = use the single-CTA kernel)
   uint8_t *d_wdig = nullptr;
   unsigned long long *d_wq = nullptr;
   std::vector<long long> wq;
@@ -175,7 +180,7 @@ int make_plane_map(rsb_ctx *ctx, CUtensorMap *tm, void *base, int Kpad, size_t r
 
 template <class T> void dfree(T *&p) { if (p) { cudaFree(p); p = nullptr; } }
 
-void free_geo(Geo &g) { dfree(g.d_tiles); dfree(g.d_wdig); dfree(g.d_wq); g.ready = false; }
+void free_geo(Geo &g) { dfree(g.d_tiles); dfree(g.d_tiles2); dfree(g.d_wdig); dfree(g.d_wq); g.ready = false; }
 
 void free_plan(rsb_ctx *c)
 {
@@ -216,6 +221,31 @@ int build_geo(rsb_ctx *ctx, Geo &g, int S)
     RSB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
   }
   if (make_plane_map(ctx, &g.tmB, ctx->d_planeB, ctx->Kpad, (size_t) g.NBrows, ctx->Rcap, g.NT)) return 1;
+  // CTA-pair kernel: row blocks taken two at a time (not with a sharded pair grid, whose ownership is per row block)
+  g.ntiles2 = 0; g.pair_clusters = 0;
+  dfree(g.d_tiles2);
+  // Measured on the SSU shape (S = 4): 0.714 ms per contraction against 0.700 ms for the single-CTA kernel -- the
+  // contraction already runs at the rate of the cuBLAS bf16 reference x2, so halving the planeB traffic buys nothing.
+  // Kept selectable (RSCAPE_B200_GRAM_PAIR=1, read when the tile lists are built) and covered by the count tests.
+  const char *pair_env = getenv("RSCAPE_B200_GRAM_PAIR");
+  const bool use_pair = pair_env && atoi(pair_env) != 0;
+  if (ctx->shard_world <= 1 && use_pair && g.ntiles > 0) {
+    std::vector<int2> t2;
+    for (int jb = 0; jb < g.nJB; jb++) {
+      const int maxj = std::min(jb * g.CJ + g.CJ - 1, ctx->L - 1);
+      for (int ibp = 0; 2 * ibp < ctx->nIB; ibp++) if (2 * ibp * RSB_ICOLS < maxj) t2.push_back(make_int2(ibp, jb));
+    }
+    const int nc = rsb_gram_pair_clusters(S);
+    if (nc > 0 && !t2.empty()) {
+      if (make_plane_map(ctx, &g.tmBh, ctx->d_planeB, ctx->Kpad, (size_t) g.NBrows, ctx->Rcap, g.NT / 2)) return 1;
+      RSB_CUDA_OK(cudaMalloc(&g.d_tiles2, sizeof(int2) * t2.size()));
+      RSB_CUDA_OK(cudaMemcpyAsync(g.d_tiles2, t2.data(), sizeof(int2) * t2.size(), cudaMemcpyHostToDevice, ctx->stream));
+      RSB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+      g.ntiles2 = (int) t2.size();
+      g.pair_clusters = std::min(nc, ctx->sm_count / 2);
+      if (getenv("RSCAPE_B200_TRACE")) fprintf(stderr, "[rsb] CTA-pair contraction: %d resident pairs on %d SMs, %d pair tiles\n", g.pair_clusters, ctx->sm_count, g.ntiles2);
+    }
+  }
   dfree(g.d_wdig); dfree(g.d_wq);
   RSB_CUDA_OK(cudaMalloc(&g.d_wdig, (size_t) (S + 1) * ctx->Kpad));
   RSB_CUDA_OK(cudaMalloc(&g.d_wq, sizeof(unsigned long long) * ctx->N));
@@ -370,8 +400,12 @@ int enqueue_gram(rsb_ctx *ctx, int which, int s0, int nrep, cudaStream_t st)
     // the weighted geometry also emits the marginal partial sums of every tile (slot-indexed like the counts)
     double *mrow = (which == 0) ? ctx->d_mrow : nullptr, *mcol = (which == 0) ? ctx->d_mcol : nullptr;
     if (which == 0 && ((size_t) g.nJB * ctx->L * 4 > ctx->mrow_stride)) { rsb_set_error(ctx, "internal: marginal partial capacity"); return 1; }
-    RSB_CUDA_OK(rsb_launch_gram_i8(g.S, ctx->tmA, g.tmB, g.d_tiles, g.ntiles, s0, nrep, ctx->L, ctx->Lp, ctx->Kpad / RSB_KSTAGE,
-                                   ctx->d_cnt, g.scale, mrow, mcol, g.nJB, ctx->nIB, grid, st));
+    if (g.pair_clusters > 0)
+      RSB_CUDA_OK(rsb_launch_gram_i8_pair(g.S, ctx->tmA, g.tmBh, g.d_tiles2, g.ntiles2, s0, nrep, ctx->L, ctx->Lp, ctx->Kpad / RSB_KSTAGE,
+                                          ctx->d_cnt, g.scale, mrow, mcol, g.nJB, ctx->nIB, g.pair_clusters, st));
+    else
+      RSB_CUDA_OK(rsb_launch_gram_i8(g.S, ctx->tmA, g.tmB, g.d_tiles, g.ntiles, s0, nrep, ctx->L, ctx->Lp, ctx->Kpad / RSB_KSTAGE,
+                                     ctx->d_cnt, g.scale, mrow, mcol, g.nJB, ctx->nIB, grid, st));
     if (ctx->profile) { cudaEventRecord(e1, st); ctx->pending.push_back({ e0, e1 }); }
     ctx->launches++;
     ctx->gram_launches++;
@@ -1273,6 +1307,7 @@ int rsb_null_fitch_shuffle(rsb_ctx *ctx, const uint8_t *msa, int64_t row_stride,
   RSB_CUDA_OK(cudaMemcpy2DAsync(ctx->d_msa0, L, msa, (size_t) row_stride, L, N, cudaMemcpyHostToDevice, sg));
   int unknown = 1;
   RSB_CUDA_OK(rsb_launch_unknown_check(ctx->d_msa0, (size_t) N * L, ctx->d_genflag, &unknown, sg));
+  if (getenv("RSCAPE_B200_FITCH_PER_REPLICATE")) unknown = 1;      // tests: force the general path
   uint8_t *sets = unknown ? nullptr : ctx->d_sets;
   int off = 0, chunks = 0, next = 4;                                 // chunk sizes 1, 4, 8, 16, 32, then the rest
   while (off < nrep) {

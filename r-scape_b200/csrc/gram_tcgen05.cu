@@ -78,6 +78,99 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
         | ((uint64_t) 2u  << 61);
 }
 
+// Epilogue of one tile, shared by the single-CTA and the CTA-pair kernels: this warp's 32 TMEM lanes (rows (i, a)) of the
+// accumulator at `trow` -> int64 count planes, and (part) the tile's marginal partial sums.  Returns the row partial.
+template <int S>
+__device__ __forceinline__ double gram_epilogue_tile(uint32_t trow, int jb, int i, int a, int lane, int ew, int ib, int r, int L, int Lp,
+                                                     long long *__restrict__ base, size_t plane, double scale, bool part,
+                                                     double *__restrict__ mcol, int nIB)
+{
+  constexpr int CJ = rsb_cj_for(S);
+  (void) Lp;
+  double racc = 0.0;                                               // marginal partial of row (i, a) over this tile's columns
+  #pragma unroll 1
+  for (int jl = 0; jl < CJ; jl += 2) {
+    uint32_t d[2][S][4];
+    #pragma unroll
+    for (int u = 0; u < 2; u++)
+      #pragma unroll
+      for (int k = 0; k < S; k++)
+        tmem_ld4(trow + (uint32_t) (((jl + u) * S + k) * 4), d[u][k][0], d[u][k][1], d[u][k][2], d[u][k][3]);
+    tmem_ld_wait();
+
+    const int j0 = jb * CJ + jl;
+    unsigned long long c[2][4];
+    #pragma unroll
+    for (int u = 0; u < 2; u++)
+      #pragma unroll
+      for (int b = 0; b < 4; b++) {
+        unsigned long long v = 0;
+        #pragma unroll
+        for (int k = S - 1; k >= 0; k--) v = (v << 8) + (unsigned long long) d[u][k][b];
+        c[u][b] = v;
+      }
+    const bool ok0 = (i < L) && (j0 < L)     && (i < j0);
+    const bool ok1 = (i < L) && (j0 + 1 < L) && (i < j0 + 1);
+    if (ok0 && ok1) {
+      #pragma unroll
+      for (int b = 0; b < 4; b++)
+        *reinterpret_cast<ulonglong2 *>(base + b * plane + j0) = make_ulonglong2(c[0][b], c[1][b]);
+    } else {
+      #pragma unroll
+      for (int b = 0; b < 4; b++) {
+        if (ok0) base[b * plane + j0]     = (long long) c[0][b];
+        if (ok1) base[b * plane + j0 + 1] = (long long) c[1][b];
+      }
+    }
+
+    if (part) {
+      // marginal partials (corr_Probs :1713-1758 + corr_Marginals :1335-1370, the per-pair part): the 16 cells of a
+      // pair sit in 4 adjacent lanes (a = lane & 3) x 4 registers (b).  pp = (1e-10 + c scale) / sum; pairs with
+      // nseff = 0 are skipped (:1354).  Fixed shuffle trees => deterministic.
+      double x[2][4];
+      #pragma unroll
+      for (int u = 0; u < 2; u++) {
+        #pragma unroll
+        for (int b = 0; b < 4; b++) x[u][b] = fma(u64_to_f64(c[u][b]), scale, 1e-10);
+        const double rs = (x[u][0] + x[u][1]) + (x[u][2] + x[u][3]);
+        double sum = rs;
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+        const unsigned nz  = __ballot_sync(0xffffffffu, (c[u][0] | c[u][1] | c[u][2] | c[u][3]) != 0ULL);
+        const bool     use = (u ? ok1 : ok0) && ((nz >> (lane & ~3)) & 0xFu) != 0u;
+        const double   inv = use ? 1.0 / sum : 0.0;
+        racc = fma(rs, inv, racc);
+        #pragma unroll
+        for (int b = 0; b < 4; b++) x[u][b] *= inv;
+      }
+      // column partials: 8 values (u, b) summed over the warp's 32 lanes by a halving butterfly -- after the three
+      // halving steps a lane keeps (u, b) = (bit 4, bits 3:2 of its lane id), then two full steps sum over a
+      const bool h4 = lane & 16, h3 = lane & 8, h2 = lane & 4;
+      double y[4], z[2], v1;
+      #pragma unroll
+      for (int b = 0; b < 4; b++) {
+        const double keep = h4 ? x[1][b] : x[0][b], send = h4 ? x[0][b] : x[1][b];
+        y[b] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+      }
+      #pragma unroll
+      for (int q = 0; q < 2; q++) {
+        const double keep = h3 ? y[2 + q] : y[q], send = h3 ? y[q] : y[2 + q];
+        z[q] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+      }
+      {
+        const double keep = h2 ? z[1] : z[0], send = h2 ? z[0] : z[1];
+        v1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+      }
+      v1 += __shfl_xor_sync(0xffffffffu, v1, 2);
+      v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
+      const int jw = j0 + (h4 ? 1 : 0);
+      if ((lane & 3) == 0 && jw < L)
+        mcol[(((size_t) r * 4 * nIB + (size_t) ib * 4 + ew) * L + jw) * 4 + ((h3 ? 2 : 0) + (h2 ? 1 : 0))] = v1;
+    }
+  }
+  return racc;
+}
+
 #ifdef RSB_BLOCKTRACE
 __device__ unsigned long long *gram_trace_buf;
 #endif
@@ -187,87 +280,7 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t) (ew * 32) << 16) + (uint32_t) acc * 256u;
 
-      double racc = 0.0;                                           // marginal partial of row (i, a) over this tile's columns
-      #pragma unroll 1
-      for (int jl = 0; jl < CJ; jl += 2) {
-        uint32_t d[2][S][4];
-        #pragma unroll
-        for (int u = 0; u < 2; u++)
-          #pragma unroll
-          for (int k = 0; k < S; k++)
-            tmem_ld4(trow + (uint32_t) (((jl + u) * S + k) * 4), d[u][k][0], d[u][k][1], d[u][k][2], d[u][k][3]);
-        tmem_ld_wait();
-
-        const int j0 = t.y * CJ + jl;
-        unsigned long long c[2][4];
-        #pragma unroll
-        for (int u = 0; u < 2; u++)
-          #pragma unroll
-          for (int b = 0; b < 4; b++) {
-            unsigned long long v = 0;
-            #pragma unroll
-            for (int k = S - 1; k >= 0; k--) v = (v << 8) + (unsigned long long) d[u][k][b];
-            c[u][b] = v;
-          }
-        const bool ok0 = (i < L) && (j0 < L)     && (i < j0);
-        const bool ok1 = (i < L) && (j0 + 1 < L) && (i < j0 + 1);
-        if (ok0 && ok1) {
-          #pragma unroll
-          for (int b = 0; b < 4; b++)
-            *reinterpret_cast<ulonglong2 *>(base + b * plane + j0) = make_ulonglong2(c[0][b], c[1][b]);
-        } else {
-          #pragma unroll
-          for (int b = 0; b < 4; b++) {
-            if (ok0) base[b * plane + j0]     = (long long) c[0][b];
-            if (ok1) base[b * plane + j0 + 1] = (long long) c[1][b];
-          }
-        }
-
-        if (mrow != nullptr) {
-          // marginal partials (corr_Probs :1713-1758 + corr_Marginals :1335-1370, the per-pair part): the 16 cells of a
-          // pair sit in 4 adjacent lanes (a = lane & 3) x 4 registers (b).  pp = (1e-10 + c scale) / sum; pairs with
-          // nseff = 0 are skipped (:1354).  Fixed shuffle trees => deterministic.
-          double x[2][4];
-          #pragma unroll
-          for (int u = 0; u < 2; u++) {
-            #pragma unroll
-            for (int b = 0; b < 4; b++) x[u][b] = fma(u64_to_f64(c[u][b]), scale, 1e-10);
-            const double rs = (x[u][0] + x[u][1]) + (x[u][2] + x[u][3]);
-            double sum = rs;
-            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-            sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-            const unsigned nz  = __ballot_sync(0xffffffffu, (c[u][0] | c[u][1] | c[u][2] | c[u][3]) != 0ULL);
-            const bool     use = (u ? ok1 : ok0) && ((nz >> (lane & ~3)) & 0xFu) != 0u;
-            const double   inv = use ? 1.0 / sum : 0.0;
-            racc = fma(rs, inv, racc);
-            #pragma unroll
-            for (int b = 0; b < 4; b++) x[u][b] *= inv;
-          }
-          // column partials: 8 values (u, b) summed over the warp's 32 lanes by a halving butterfly -- after the three
-          // halving steps a lane keeps (u, b) = (bit 4, bits 3:2 of its lane id), then two full steps sum over a
-          const bool h4 = lane & 16, h3 = lane & 8, h2 = lane & 4;
-          double y[4], z[2], v1;
-          #pragma unroll
-          for (int b = 0; b < 4; b++) {
-            const double keep = h4 ? x[1][b] : x[0][b], send = h4 ? x[0][b] : x[1][b];
-            y[b] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-          }
-          #pragma unroll
-          for (int q = 0; q < 2; q++) {
-            const double keep = h3 ? y[2 + q] : y[q], send = h3 ? y[q] : y[2 + q];
-            z[q] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-          }
-          {
-            const double keep = h2 ? z[1] : z[0], send = h2 ? z[0] : z[1];
-            v1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-          }
-          v1 += __shfl_xor_sync(0xffffffffu, v1, 2);
-          v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
-          const int jw = j0 + (h4 ? 1 : 0);
-          if ((lane & 3) == 0 && jw < L)
-            mcol[(((size_t) r * 4 * nIB + (size_t) t.x * 4 + ew) * L + jw) * 4 + ((h3 ? 2 : 0) + (h2 ? 1 : 0))] = v1;
-        }
-      }
+      const double racc = gram_epilogue_tile<S>(trow, t.y, i, a, lane, ew, t.x, r, L, Lp, base, plane, scale, mrow != nullptr, mcol, nIB);
       if (mrow != nullptr && i < L) mrow[(((size_t) r * nJB + t.y) * L + i) * 4 + a] = racc;
       tc_fence_before();
       mbar_arrive(tempty_bar(acc));
@@ -284,6 +297,172 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
     if ((threadIdx.x & 31) == 0) rsb_trace_put(gram_trace_buf, 1, t0);
 #endif
   }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2): the two CTAs of a cluster, on the two SMs of one TPC, contract a 256-row x
+// N-column tile together.  CTA r owns the accumulator rows of row block ib = 2 ibp + r (its own 128 planeA rows) and
+// loads only HALF of the planeB tile; the tensor cores of both SMs read both halves.  Per CTA and stage that is 32 KB
+// of operands instead of 48 KB -- a third less L2 -> SM traffic, the resource this kernel is bound by -- and six ring
+// stages instead of four in the same shared memory.  Synchronisation:
+//   full[s]    leader CTA's barrier; the TMA loads of BOTH CTAs complete their bytes on it (cp.async.bulk.tensor
+//              .cta_group::2 with the barrier address' peer bit cleared); the leader's producer arms it with the pair's bytes
+//   empty[s]   one per CTA, released by the leader's tcgen05.commit multicast to both CTAs
+//   tfull[a]   one per CTA (commit multicast): accumulator a complete, each CTA's epilogue drains its own 128 TMEM lanes
+//   tempty[a]  leader's barrier, 2 x 128 arrivals: the epilogue threads of both CTAs (the peer's arrive remotely)
+// Only the leader's warp 1 issues MMAs.  The epilogue is the single-CTA kernel's.
+constexpr int      NSTAGE2        = 6;
+constexpr uint32_t PEER_BIT_MASK  = 0xFEFFFFFFu;        // shared::cluster address of the same location in the pair's even CTA
+
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap *tmap, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               :: "r"(dst), "l"(tmap), "r"(bar & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" :: "r"(bar & PEER_BIT_MASK) : "memory");
+}
+__device__ __forceinline__ void umma_i8_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\t"
+               "setp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+               :: "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               :: "r"(bar), "h"((unsigned short) 3) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int S>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GRAM_THREADS, 1)
+gram_i8_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapBh,
+                    const int2 *__restrict__ tiles, int ntiles, int rep0, int nrep, int L, int Lp, int kstages,
+                    long long *__restrict__ cnt, double scale, double *__restrict__ mrow, double *__restrict__ mcol, int nJB, int nIB)
+{
+  constexpr int      CJ          = rsb_cj_for(S);
+  constexpr int      NT          = 4 * S * CJ;                 // UMMA N (whole planeB tile; each CTA stages NT / 2 rows)
+  constexpr uint32_t A_BYTES     = RSB_MTILE * RSB_KSTAGE;
+  constexpr uint32_t B_BYTES     = (NT / 2) * RSB_KSTAGE;
+  constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  // instruction descriptor as in the single-CTA kernel with M = 256 (the pair's rows)
+  constexpr uint32_t IDESC       = (2u << 4) | ((uint32_t) (NT >> 3) << 17) | ((uint32_t) (256 >> 4) << 24);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base  = smem_base + NSTAGE2 * STAGE_BYTES;
+  auto full_bar   = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar  = [&](int s) { return bar_base + 8u * (NSTAGE2 + s); };
+  auto tfull_bar  = [&](int a) { return bar_base + 8u * (2 * NSTAGE2 + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * NSTAGE2 + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * NSTAGE2 + 4);
+  volatile uint32_t *tmem_slot_ptr = (volatile uint32_t *) (smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  uint32_t cta_rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+  const bool leader = (cta_rank == 0);
+  const int  cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < NSTAGE2; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; a++)       { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 256); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                               // both CTAs' barriers exist before anything signals them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const long long nwork = (long long) ntiles * nrep;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (long long w = cluster_id; w < nwork; w += nclusters) {
+        const int  r = rep0 + (int) (w / ntiles);
+        const int2 t = tiles[(int) (w % ntiles)];                  // (ibp, jb)
+        const int  ib = 2 * t.x + (int) cta_rank;
+        for (int ks = 0; ks < kstages; ks++) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          if (leader) mbar_expect_tx(full_bar(stage), 2u * STAGE_BYTES);
+          const uint32_t sA = smem_base + stage * STAGE_BYTES;
+          tma_load_3d_pair(sA,           &tmapA,  full_bar(stage), ks * RSB_KSTAGE, ib * RSB_MTILE,                        r);
+          tma_load_3d_pair(sA + A_BYTES, &tmapBh, full_bar(stage), ks * RSB_KSTAGE, t.y * NT + (int) cta_rank * (NT / 2), r);
+          if (++stage == NSTAGE2) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (one thread of the leader CTA)
+    if (lane == 0 && leader) {
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0;   uint32_t acc_phase = 0;
+      for (long long w = cluster_id; w < nwork; w += nclusters) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);               // both epilogues have drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t) acc * 256u;
+        for (int ks = 0; ks < kstages; ks++) {
+          mbar_wait(full_bar(stage), phase);                       // the bytes of both CTAs have landed
+          tc_fence_after();
+          const uint32_t sA    = smem_base + stage * STAGE_BYTES;
+          const uint64_t adesc = smem_desc_sw128(sA);
+          const uint64_t bdesc = smem_desc_sw128(sA + A_BYTES);
+          #pragma unroll
+          for (int k = 0; k < RSB_KSTAGE / 32; k++)
+            umma_i8_pair(d_tmem, adesc + 2u * k, bdesc + 2u * k, IDESC, (uint32_t) ((ks | k) != 0));
+          umma_commit_pair(empty_bar(stage));                      // frees the slot in both CTAs
+          if (++stage == NSTAGE2) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit_pair(tfull_bar(acc));                          // accumulator complete -> both epilogues
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue: this CTA's 128 TMEM lanes -> int64 count planes
+    const int ew = warp - 4;
+    const int m  = ew * 32 + lane;
+    const int il = m >> 2, a = m & 3;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (long long w = cluster_id; w < nwork; w += nclusters) {
+      const int  r = rep0 + (int) (w / ntiles);
+      const int2 t = tiles[(int) (w % ntiles)];
+      const int  ib = 2 * t.x + (int) cta_rank;
+      const int  i = ib * RSB_ICOLS + il;
+      long long *base = cnt + ((size_t) r * 16 + (size_t) a * 4) * (size_t) L * Lp + (size_t) i * Lp;
+      const size_t plane = (size_t) L * Lp;
+      const bool   part  = (mrow != nullptr) && (ib < nIB);        // marginal partials of this row block
+
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + ((uint32_t) (ew * 32) << 16) + (uint32_t) acc * 256u;
+      const double racc = gram_epilogue_tile<S>(trow, t.y, i, a, lane, ew, ib, r, L, Lp, base, plane, scale, part, mcol, nIB);
+      if (part && i < L) mrow[(((size_t) r * nJB + t.y) * L + i) * 4 + a] = racc;
+      tc_fence_before();
+      mbar_arrive_leader(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                               // the peer may still be using this CTA's barriers / TMEM
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+template <int S> constexpr size_t gram_pair_smem_bytes() {
+  return (size_t) NSTAGE2 * (RSB_MTILE * RSB_KSTAGE + 2 * S * rsb_cj_for(S) * RSB_KSTAGE) + 8 * (2 * NSTAGE2 + 4) + 16 + 1024;
 }
 
 template <int S> constexpr size_t gram_smem_bytes() {
@@ -305,6 +484,38 @@ cudaError_t launch_gram(const CUtensorMap &tmA, const CUtensorMap &tmB, const in
   return cudaGetLastError();
 }
 
+template <int S>
+cudaError_t launch_gram_pair(const CUtensorMap &tmA, const CUtensorMap &tmBh, const int2 *tiles2, int ntiles2, int rep0, int nrep,
+                             int L, int Lp, int kstages, long long *cnt, double scale, double *mrow, double *mcol, int nJB, int nIB,
+                             int max_clusters, cudaStream_t st)
+{
+  constexpr size_t smem = gram_pair_smem_bytes<S>();
+  cudaError_t e = cudaFuncSetAttribute(gram_i8_pair_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+  if (e != cudaSuccess) return e;
+  rsb_coreside(gram_i8_pair_kernel<S>);
+  const long long work = (long long) ntiles2 * nrep;
+  const int nclusters = (int) (work < max_clusters ? work : max_clusters);
+  gram_i8_pair_kernel<S><<<2 * nclusters, GRAM_THREADS, smem, st>>>(tmA, tmBh, tiles2, ntiles2, rep0, nrep, L, Lp, kstages, cnt, scale,
+                                                                      mrow, mcol, nJB, nIB);
+  return cudaGetLastError();
+}
+
+// how many CTA pairs of the pair kernel can be resident at once (SMs that cannot be paired inside their GPC stay idle)
+template <int S>
+int pair_clusters()
+{
+  constexpr size_t smem = gram_pair_smem_bytes<S>();
+  if (cudaFuncSetAttribute(gram_i8_pair_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem) != cudaSuccess) return 0;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * 148); cfg.blockDim = dim3(GRAM_THREADS); cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, gram_i8_pair_kernel<S>, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
 } // namespace
 
 // Host entry used by capi.cu.  tmA/tmB are 3-D tensor maps {Kpad, rows, replicate} with 128B swizzle
@@ -322,6 +533,31 @@ cudaError_t rsb_launch_gram_i8(int S, const CUtensorMap &tmA, const CUtensorMap 
   case 6: return launch_gram<6>(tmA, tmB, tiles, ntiles, rep0, nrep, L, Lp, kstages, cnt, scale, mrow, mcol, nJB, nIB, grid, st);
   }
   return cudaErrorInvalidValue;
+}
+
+// CTA-pair variant: tmBh has boxes {128, 2*S*CJ, 1} (half a planeB tile), tiles2 lists (ibp, jb) = row-block pairs.
+cudaError_t rsb_launch_gram_i8_pair(int S, const CUtensorMap &tmA, const CUtensorMap &tmBh, const int2 *tiles2, int ntiles2,
+                                    int rep0, int nrep, int L, int Lp, int kstages, long long *cnt, double scale, double *mrow,
+                                    double *mcol, int nJB, int nIB, int max_clusters, cudaStream_t st)
+{
+  switch (S) {
+  case 1: return launch_gram_pair<1>(tmA, tmBh, tiles2, ntiles2, rep0, nrep, L, Lp, kstages, cnt, scale, mrow, mcol, nJB, nIB, max_clusters, st);
+  case 2: return launch_gram_pair<2>(tmA, tmBh, tiles2, ntiles2, rep0, nrep, L, Lp, kstages, cnt, scale, mrow, mcol, nJB, nIB, max_clusters, st);
+  case 3: return launch_gram_pair<3>(tmA, tmBh, tiles2, ntiles2, rep0, nrep, L, Lp, kstages, cnt, scale, mrow, mcol, nJB, nIB, max_clusters, st);
+  case 4: return launch_gram_pair<4>(tmA, tmBh, tiles2, ntiles2, rep0, nrep, L, Lp, kstages, cnt, scale, mrow, mcol, nJB, nIB, max_clusters, st);
+  case 5: return launch_gram_pair<5>(tmA, tmBh, tiles2, ntiles2, rep0, nrep, L, Lp, kstages, cnt, scale, mrow, mcol, nJB, nIB, max_clusters, st);
+  case 6: return launch_gram_pair<6>(tmA, tmBh, tiles2, ntiles2, rep0, nrep, L, Lp, kstages, cnt, scale, mrow, mcol, nJB, nIB, max_clusters, st);
+  default: return cudaErrorInvalidValue;
+  }
+}
+
+int rsb_gram_pair_clusters(int S)
+{
+  switch (S) {
+  case 1: return pair_clusters<1>(); case 2: return pair_clusters<2>(); case 3: return pair_clusters<3>();
+  case 4: return pair_clusters<4>(); case 5: return pair_clusters<5>(); case 6: return pair_clusters<6>();
+  default: return 0;
+  }
 }
 
 #ifdef RSB_BLOCKTRACE

@@ -78,3 +78,11 @@ def test_counts_extreme_weights(ctx, po, oracle):
     _check(ctx, oracle, msa, wgt, 6)
     wgt[0] = 0.0
     _check(ctx, oracle, msa, wgt, 5)
+
+
+@pytest.mark.parametrize("nslices,N,L", [(1, 300, 70), (4, 333, 77), (5, 257, 130), (3, 1000, 33)])
+def test_counts_cta_pair_kernel(ctx, po, oracle, monkeypatch, nslices, N, L):
+    """The cta_group::2 variant of the contraction (two SMs per 256-row tile; opt-in) gives the same bits."""
+    monkeypatch.setenv("RSCAPE_B200_GRAM_PAIR", "1")
+    msa, wgt, _ = po.synthetic_msa(N, L, seed=N)
+    _check(ctx, oracle, msa, np.ones(N) if nslices == 1 else wgt, nslices)

@@ -176,3 +176,47 @@ def test_pool_scan_equals_host_scan(ctx, pkg, po, oracle):
     ctx.null_hist(nulls, w)
     b = ctx.hist_read(4096)
     assert np.array_equal(a[0], b[0]) and a[1] == b[1] == R * L * (L - 1) // 2
+
+
+# ------------------------------------------------------------------------------------------------ plumbing of generator A
+def test_fitch_shuffle_is_deterministic_and_chunk_independent(ctx, po):
+    """Replicates are keyed by their global id: generating them in one call, again, or one by one into other pool
+    entries gives the same alignments (the generation stream works in chunks of growing size)."""
+    msa, wgt, tree = _setup(ctx, po, 60, 44, seed=9, R=24)
+    ctx.null_fitch_shuffle(msa, seed=77, nrep=24)
+    a = ctx.pool_get(24)
+    ctx.null_fitch_shuffle(msa, seed=77, nrep=24)
+    assert np.array_equal(ctx.pool_get(24), a)
+    for r in (0, 5, 23):
+        ctx.null_fitch_shuffle(msa, seed=77, nrep=1, first_rep=2, first_id=r)
+        assert np.array_equal(ctx.pool_get(1, 2)[0], a[r])
+
+
+def test_fitch_shuffle_shared_up_pass_equals_per_replicate(ctx, po, monkeypatch):
+    """Without unknown residues the Fitch sets are computed once for all replicates; the result must be what the general
+    per-replicate path gives."""
+    msa, wgt, tree = _setup(ctx, po, 80, 52, seed=4, R=6)
+    msa = np.where(msa > 4, 0, msa).astype(np.uint8)                          # no N
+    ctx.null_fitch_shuffle(msa, seed=3, nrep=6)
+    shared = ctx.pool_get(6)
+    monkeypatch.setenv("RSCAPE_B200_FITCH_PER_REPLICATE", "1")
+    ctx.null_fitch_shuffle(msa, seed=3, nrep=6)
+    assert np.array_equal(ctx.pool_get(6), shared)
+
+
+def test_scans_wait_for_the_generation_stream(ctx, po):
+    """null_hist_pool issued right after the (asynchronous) generator call sees the finished alignments: its histogram
+    equals the one from the same alignments uploaded from the host."""
+    msa, wgt, tree = _setup(ctx, po, 70, 48, seed=12, R=20)
+    ctx.null_fitch_shuffle(msa, seed=11, nrep=20)
+    ctx.hist_reset()
+    w, _, _ = ctx.null_width_pool(0)
+    mm = ctx.null_hist_pool(0, 20, w)
+    bins, n, imax = ctx.hist_read(4096)
+    nulls = ctx.pool_get(20)
+    ctx.hist_reset()
+    w2, _, _ = ctx.null_width(nulls[0])
+    mm2 = ctx.null_hist(nulls, w2)
+    bins2, n2, imax2 = ctx.hist_read(4096)
+    assert w == w2 and n == n2 and imax == imax2
+    assert np.array_equal(bins, bins2) and np.array_equal(mm, mm2)

@@ -20,7 +20,7 @@ N, L = w["N"], w["L"]
 rng = np.random.default_rng(1)
 msa = rng.integers(0, 5, (nrep, N, L)).astype(np.uint8)
 ctx = pkg.Context(0)
-ctx.configure(N, L, 2, 5)
+ctx.configure(N, L, 2, 4)
 ctx.set_weights(rng.gamma(2.0, 0.5, N))
 ctx.hist_reset()
 width = ctx.null_width(msa[0])[0]
