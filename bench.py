@@ -344,8 +344,10 @@ def main():
     ops_alg_per_launch = 32.0 * pairs * N * scans_this_rank / max(1, cnt["gram_launches"])
     achieved = ops_alg_per_launch / (gram_ms_avg * 1e-3) / 1e12 if gram_ms_avg > 0 else 0.0
     peak_i8 = 2.0 * peaks["bf16"]
+    # DRAM bytes of one gram launch from the committed `ncu --set full` capture (profiles/r1_ncu_full_gram_*): read + write
+    traffic = {("ssu", 4): 1.079e9 + 0.229e9}.get((args.workload, args.slices)) if world == 1 and not args.grid_shard else None
     roofline = dict(bound="tensor", achieved=achieved, peak=peak_i8, unit="TOP/s", frac=achieved / peak_i8,
-                    traffic=None,
+                    traffic=traffic,
                     note=f"algorithmic int8 ops (32 per pair-cell) of one gram launch / mean launch time {gram_ms_avg:.3f} ms; "
                          f"the kernel issues {args.slices}x that in tcgen05 kind::i8 MMAs (one pass per 8-bit digit slice of the weights): "
                          f"implementation rate {achieved * args.slices:.1f} TOP/s = {achieved * args.slices / peak_i8:.3f} of peak; "
