@@ -21,6 +21,7 @@ cudaError_t rsb_launch_gram_i8_pair(int S, const CUtensorMap &tmA, const CUtenso
                                     int rep0, int nrep, int L, int Lp, int kstages, long long *cnt, double scale, double *mrow,
                                     double *mcol, int nJB, int nIB, int max_clusters, cudaStream_t st);
 int rsb_gram_pair_clusters(int S);
+cudaError_t rsb_launch_quantise(const double *w, int N, int q, int umax, double vmax, uint8_t *mul, long long *V, double *err, cudaStream_t st);
 cudaError_t rsb_launch_pack(int S, const uint8_t *res, int nrep, int N, int L, long long rep_stride_res, const uint8_t *wdig,
                             int Kpad, uint8_t *planeA, int MA, uint8_t *planeB, int NBrows, int Lcover, cudaStream_t st);
 cudaError_t rsb_launch_colsum(const uint8_t *res, int N, int L, const unsigned long long *wq, unsigned long long *colsum, cudaStream_t st);
@@ -58,6 +59,7 @@ cudaError_t rsb_launch_fitch_shuffle(const int *left, const int *right, const in
                                      int nlevels, int N, int L, const uint8_t *msa, unsigned long long seed, unsigned long long id0, int first_rep, int nrep,
                                      uint8_t *res, uint8_t *anc, uint8_t *shanc, int *perm, uint8_t *sets_shared, int build_sets, cudaStream_t st);
 cudaError_t rsb_launch_unknown_check(const uint8_t *msa, size_t n, int *d_flag, int *unknown, cudaStream_t st);
+cudaError_t rsb_launch_permutations(int L, unsigned long long seed, unsigned long long id0, int first_rep, int nrep, int *perm, cudaStream_t st);
 
 namespace {
 constexpr int HIST_BINS = 1 << 22;
@@ -103,6 +105,7 @@ struct rsb_ctx {
   cudaEvent_t ev_exit = nullptr;
   std::vector<cudaEvent_t> pool_ready, gen_ring;
   size_t gen_next = 0;
+  uint8_t *d_qscratch = nullptr;                     // quantise(): w[N] f64 | V[N] i64 | err[N] f64 | u[N] u8
   void *d_logtab = nullptr;                          // table of the statistic kernels' log (stats.cu), built once
   double *h_mm = nullptr; size_t h_mm_cap = 0;      // pinned staging of the per-replicate min/max: a pageable target would block the enqueuing thread
   double *d_meanp = nullptr, *d_w = nullptr, *d_blocksum = nullptr, *d_msum = nullptr, *d_covsum = nullptr;
@@ -187,6 +190,7 @@ void free_plan(rsb_ctx *c)
   if (c->stream_gen) cudaStreamSynchronize(c->stream_gen);
   c->pool_ready.clear();
   free_geo(c->geo[0]); free_geo(c->geo[1]);
+  dfree(c->d_qscratch);
   dfree(c->d_res); dfree(c->d_planeA); dfree(c->d_planeB); dfree(c->d_cnt); dfree(c->d_nseff); dfree(c->d_pm); dfree(c->d_cov);
   dfree(c->d_mrow); dfree(c->d_mcol); dfree(c->d_tmp); dfree(c->d_rowpart); dfree(c->d_colpart); dfree(c->d_mm); dfree(c->d_scal); dfree(c->d_covx); dfree(c->d_minmax);
   if (c->h_mm) { cudaFreeHost(c->h_mm); c->h_mm = nullptr; c->h_mm_cap = 0; }
@@ -290,22 +294,27 @@ int quantise(rsb_ctx *ctx, Geo &g, const std::vector<double> &w, bool unit)
         long double tot = 0.0L;
         g.qerr_abs = 0.0;
         const bool fast = std::ldexp(maxw, g.q) < 1125899906842624.0;                     // W < 2^50: doubles are exact enough
-        double inv_u[256]; for (int u = 1; u <= umax; u++) inv_u[u] = 1.0 / u;
+        if (fast) {
+          // the search over u runs on the device (quantise_kernel, pack.cu)
+          if (!ctx->d_qscratch) RSB_CUDA_OK(cudaMalloc(&ctx->d_qscratch, (size_t) N * 25));
+          double *d_w = (double *) ctx->d_qscratch; long long *d_V = (long long *) (ctx->d_qscratch + (size_t) N * 8);
+          double *d_err = (double *) (ctx->d_qscratch + (size_t) N * 16); uint8_t *d_mul = ctx->d_qscratch + (size_t) N * 24;
+          std::vector<double> herr(N);
+          RSB_CUDA_OK(cudaMemcpyAsync(d_w, w.data(), sizeof(double) * N, cudaMemcpyHostToDevice, ctx->stream));
+          RSB_CUDA_OK(rsb_launch_quantise(d_w, N, g.q, umax, (double) (vlim - 1), d_mul, d_V, d_err, ctx->stream));
+          RSB_CUDA_OK(cudaMemcpyAsync(V.data(), d_V, sizeof(long long) * N, cudaMemcpyDeviceToHost, ctx->stream));
+          RSB_CUDA_OK(cudaMemcpyAsync(mul.data(), d_mul, N, cudaMemcpyDeviceToHost, ctx->stream));
+          RSB_CUDA_OK(cudaMemcpyAsync(herr.data(), d_err, sizeof(double) * N, cudaMemcpyDeviceToHost, ctx->stream));
+          RSB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+          for (int s = 0; s < N; s++) {
+            if (V[s] < 0) { rsb_set_error(ctx, "internal: weight %d not representable", s); return 1; }
+            g.qerr_abs = std::max(g.qerr_abs, std::ldexp(herr[s], -g.q));
+            tot += (long double) mul[s] * (long double) V[s];
+          }
+        } else
         for (int s = 0; s < N; s++) {
           int ub = 1; long long vb = 0; long double best = -1.0L;
-          if (fast) {
-            // |W - u v| with v = W/u rounded by the 2^52 trick (a multiply instead of a divide: a v off by one near .5 only
-            // makes that candidate look worse); u v < 2^53 is exact, and the loop vectorises
-            const double W = std::ldexp(w[s], g.q);
-            const double vmax = (double) (vlim - 1);
-            double be = 1e300;
-            for (int u = 1; u <= umax; u++) {
-              const double v = (W * inv_u[u] + 6755399441055744.0) - 6755399441055744.0;
-              const double err = (v <= vmax) ? std::fabs(W - u * v) : 1e300;
-              if (err < be) { be = err; ub = u; }
-            }
-            if (be < 1e300) { vb = (long long) ((W * inv_u[ub] + 6755399441055744.0) - 6755399441055744.0); best = (long double) be; }
-          } else {
+          {
             const long double W = std::ldexp((long double) w[s], g.q);
             for (int u = 1; u <= umax; u++) {
               const long double v = std::nearbyint(W / u);
@@ -1309,11 +1318,13 @@ int rsb_null_fitch_shuffle(rsb_ctx *ctx, const uint8_t *msa, int64_t row_stride,
   RSB_CUDA_OK(rsb_launch_unknown_check(ctx->d_msa0, (size_t) N * L, ctx->d_genflag, &unknown, sg));
   if (getenv("RSCAPE_B200_FITCH_PER_REPLICATE")) unknown = 1;      // tests: force the general path
   uint8_t *sets = unknown ? nullptr : ctx->d_sets;
-  int off = 0, chunks = 0, next = 4;                                 // chunk sizes 1, 4, 8, 16, 32, then the rest
+  RSB_CUDA_OK(rsb_launch_permutations(L, seed, first_id, first_rep, nrep, ctx->d_perm, sg));
+  // chunk sizes 1, 4, 8, 16, 32, then the rest; a small batch (every level kernel is latency-bound then) goes in one piece
+  int off = 0, chunks = 0, next = 4;
   while (off < nrep) {
     int n = (off == 0) ? 1 : next;
     if (off > 0) next *= 2;
-    if (chunks >= 5 || nrep - off - n < 4) n = nrep - off;
+    if (nrep <= 16 || chunks >= 5 || nrep - off - n < 4) n = nrep - off;
     RSB_CUDA_OK(rsb_launch_fitch_shuffle(ctx->d_left, ctx->d_right, ctx->d_parent, ctx->d_order, ctx->h_level_start.data(), ctx->nlevels, N, L,
                                          ctx->d_msa0, seed, first_id + (uint64_t) off, first_rep + off, n, ctx->d_pool, ctx->d_anc, ctx->d_shanc,
                                          ctx->d_perm, sets, off == 0, sg));
@@ -1322,7 +1333,7 @@ int rsb_null_fitch_shuffle(rsb_ctx *ctx, const uint8_t *msa, int64_t row_stride,
     for (int r = first_rep + off; r < first_rep + off + n; r++) ctx->pool_ready[r] = e;
     off += n; chunks++;
   }
-  ctx->launches += chunks * (1 + 3 * ctx->nlevels);
+  ctx->launches += 2 + chunks * (1 + 3 * ctx->nlevels);
   return 0;
 }
 

@@ -12,7 +12,7 @@
 // (A) Fitch + shuffle, R-scape's default null (src/R-scape.c:1653-1668):
 //     fitch_up/down_level tree_fitch_column (src/msatree.c:1700-1831): sets as 5-bit masks; post-order = one launch per
 //                         tree level from the deepest up, pre-order = from the root down; thread per (replicate, node, column).
-//     permute_root_kernel msamanip_ShuffleColumns (src/msamanip.c:1164-1233).  Only the root's permuted row is
+//     permutation_kernel + permute_root_kernel msamanip_ShuffleColumns (src/msamanip.c:1164-1233).  Only the root's permuted row is
 //                         ever read (every other row is overwritten by its parent's row at msamanip.c:1645).
 //     replay_level_kernel shuffle_tree_substitutions + shuffle_tree_substitute_all (src/msamanip.c:1597-1780):
 //                         one thread per (replicate, branch) of one tree level; counts the 5x5 substitutions of the
@@ -186,15 +186,13 @@ __global__ void unknown_flag_kernel(const uint8_t *__restrict__ msa, size_t n, i
   if (__syncthreads_or(any) && threadIdx.x == 0) *flag = 1;
 }
 
-// one random permutation per replicate (Fisher-Yates by one thread; L is a few thousand) and the permuted root row
-__global__ void permute_root_kernel(int N, int L, unsigned long long seed, unsigned long long id0, int first_rep, const uint8_t *__restrict__ ancbuf,
-                                    uint8_t *__restrict__ shancbuf, int *__restrict__ permbuf)
+// one random permutation per replicate (Fisher-Yates by one thread; L is a few thousand).  It depends on (seed, replicate id)
+// only, so all replicates of a generator call are done by ONE launch before the per-chunk work.
+__global__ void permutation_kernel(int L, unsigned long long seed, unsigned long long id0, int first_rep, int *__restrict__ permbuf)
 {
   const int r = first_rep + blockIdx.x;
   const uint32_t rid = (uint32_t) (id0 + blockIdx.x);
   int *perm = permbuf + (size_t) r * L;
-  const uint8_t *anc = ancbuf + (size_t) r * (N - 1) * L;
-  uint8_t *sh = shancbuf + (size_t) r * (N - 1) * L;
   for (int c = threadIdx.x; c < L; c += blockDim.x) perm[c] = c;
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -206,8 +204,16 @@ __global__ void permute_root_kernel(int N, int L, unsigned long long seed, unsig
       const int t = perm[w]; perm[w] = perm[n - 1]; perm[n - 1] = t;
     }
   }
-  __syncthreads();
-  for (int c = threadIdx.x; c < L; c += blockDim.x) sh[c] = anc[perm[c]];
+}
+
+// the permuted root row (msamanip_ShuffleColumns, src/msamanip.c:1164-1233; only the root's permuted row is ever read)
+__global__ void permute_root_kernel(int N, int L, int first_rep, const uint8_t *__restrict__ ancbuf, uint8_t *__restrict__ shancbuf,
+                                    const int *__restrict__ permbuf)
+{
+  const int r = first_rep + blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= L) return;
+  shancbuf[(size_t) r * (N - 1) * L + c] = ancbuf[(size_t) r * (N - 1) * L + permbuf[(size_t) r * L + c]];
 }
 
 constexpr int RP_THREADS = 128;
@@ -598,6 +604,13 @@ cudaError_t rsb_launch_null_simulate(const int *left, const int *right, const in
   return cudaGetLastError();
 }
 
+// the column permutations of replicates [first_rep, first_rep + nrep) with ids id0 ... (once per generator call)
+cudaError_t rsb_launch_permutations(int L, unsigned long long seed, unsigned long long id0, int first_rep, int nrep, int *perm, cudaStream_t st)
+{
+  permutation_kernel<<<nrep, 256, 0, st>>>(L, seed, id0, first_rep, perm);
+  return cudaGetLastError();
+}
+
 // does the alignment hold residues other than A C G U and the gap?  Synchronises st.
 cudaError_t rsb_launch_unknown_check(const uint8_t *msa, size_t n, int *d_flag, int *unknown, cudaStream_t st)
 {
@@ -632,7 +645,7 @@ cudaError_t rsb_launch_fitch_shuffle(const int *left, const int *right, const in
     if (L % 4 == 0) fitch_down_level_kernel<4><<<dim3((L / 4 + 127) / 128, cnt, nrep), 128, 0, st>>>(left, right, order, b, N, L, seed, id0, first_rep, sets, sets_stride, anc);
     else            fitch_down_level_kernel<1><<<dim3((L + 127) / 128, cnt, nrep), 128, 0, st>>>(left, right, order, b, N, L, seed, id0, first_rep, sets, sets_stride, anc);
   }
-  permute_root_kernel<<<nrep, 256, 0, st>>>(N, L, seed, id0, first_rep, anc, shanc, perm);
+  permute_root_kernel<<<dim3((L + 255) / 256, nrep), 256, 0, st>>>(N, L, first_rep, anc, shanc, perm);
   for (int lv = 0; lv < nlevels; lv++) {
     const int b = level_start_host[lv], cnt = level_start_host[lv + 1] - b;
     const long long tasks = 2LL * cnt * nrep;                    // branches of this level over all replicates

@@ -129,7 +129,34 @@ __global__ void counts_direct_kernel(const uint8_t *__restrict__ res, int N, int
   for (int c = 0; c < 16; c++) cnt[((size_t) c * L + i) * Lp + j] = (long long) acc[c];
 }
 
+// Fixed-point weights wq_s = u_s V_s ~ w_s 2^q (capi.cu, quantise()): a thread per sequence tries every multiplier u and
+// keeps the (u, V = rint(W / u)) with the smallest |W - u V|.  Same IEEE operations, candidate order and tie-break as the
+// host loop it replaces (correctly rounded reciprocal and product, round-to-nearest-even, exact u V and difference for
+// W < 2^50), so host and device agree bit for bit; ~3 ms of host time per call become microseconds.
+__global__ void quantise_kernel(const double *__restrict__ w, int N, int q, int umax, double vmax,
+                                uint8_t *__restrict__ mul, long long *__restrict__ V, double *__restrict__ err)
+{
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= N) return;
+  const double W = scalbn(w[s], q);
+  double be = 1e300; int ub = 1;
+  for (int u = 1; u <= umax; u++) {
+    const double v = rint(__dmul_rn(W, __drcp_rn((double) u)));
+    const double e = (v <= vmax) ? fabs(__dsub_rn(W, __dmul_rn((double) u, v))) : 1e300;
+    if (e < be) { be = e; ub = u; }
+  }
+  mul[s] = (uint8_t) ub;
+  V[s]   = (be < 1e300) ? (long long) rint(__dmul_rn(W, __drcp_rn((double) ub))) : -1;
+  err[s] = be;
+}
+
 } // namespace
+
+cudaError_t rsb_launch_quantise(const double *w, int N, int q, int umax, double vmax, uint8_t *mul, long long *V, double *err, cudaStream_t st)
+{
+  quantise_kernel<<<(N + 127) / 128, 128, 0, st>>>(w, N, q, umax, vmax, mul, V, err);
+  return cudaGetLastError();
+}
 
 cudaError_t rsb_launch_pack(int S, const uint8_t *res, int nrep, int N, int L, long long rep_stride_res, const uint8_t *wdig,
                             int Kpad, uint8_t *planeA, int MA, uint8_t *planeB, int NBrows, int Lcover, cudaStream_t st)

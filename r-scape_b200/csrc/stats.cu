@@ -102,9 +102,10 @@ __device__ __forceinline__ void logtab_load(double2 *tab, const double2 *__restr
   for (int k = threadIdx.x; k < LOGTAB_N; k += blockDim.x) tab[k] = gtab[k];
 }
 
+template <bool CLAMP = true>
 __device__ __forceinline__ double fast_log(double x, const double2 *__restrict__ tab)
 {
-  x = fmax(x, 2.2250738585072014e-308);
+  if (CLAMP) x = fmax(x, 2.2250738585072014e-308);                  // (not needed where the argument is known to be a positive normal)
   const int hi = __double2hiint(x), lo = __double2loint(x);
   const double m  = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
   const double2 t = tab[(hi >> 11) & (LOGTAB_N - 1)];
@@ -140,7 +141,8 @@ __device__ __forceinline__ void load_pair_raw(const long long *__restrict__ cnt,
 // ne cancels inside the log and sum pp = 1, so with the raw table x (pp = x / T), X_a = sum_b x_ab, Y_b = sum_a x_ab
 //     G = 2 ne [ (sum x log x - sum_a X_a log pm_i[a] - sum_b Y_b log pm_j[b]) / T - log T ]
 // : 17 logs, no division per cell, no branch.  The terms kept are the reference's (exp > 0 and obs > 0 <=> ne > 0 and
-// pm > 0; pp > 0 always because of the prior); the rounding differs at the 1e-15 level.
+// pm > 0; pp > 0 always because of the prior); the rounding differs at the 1e-15 level.  x >= 1e-10 and T >= 1.6e-9 are
+// positive normal numbers, so the log needs no clamp.
 __device__ __forceinline__ double gt_c16_raw(const double *x, double ne, const double *lmi, const double *lmj,
                                              const double2 *__restrict__ tab)
 {
@@ -153,17 +155,17 @@ __device__ __forceinline__ double gt_c16_raw(const double *x, double ne, const d
   double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;                     // four independent chains
   #pragma unroll
   for (int k = 0; k < 16; k += 4) {
-    s0 = fma(x[k],     fast_log(x[k],     tab), s0);
-    s1 = fma(x[k + 1], fast_log(x[k + 1], tab), s1);
-    s2 = fma(x[k + 2], fast_log(x[k + 2], tab), s2);
-    s3 = fma(x[k + 3], fast_log(x[k + 3], tab), s3);
+    s0 = fma(x[k],     fast_log<false>(x[k],     tab), s0);
+    s1 = fma(x[k + 1], fast_log<false>(x[k + 1], tab), s1);
+    s2 = fma(x[k + 2], fast_log<false>(x[k + 2], tab), s2);
+    s3 = fma(x[k + 3], fast_log<false>(x[k + 3], tab), s3);
   }
   double m = 0.0;
   #pragma unroll
   for (int a = 0; a < 4; a++) m = fma(X[a], lmi[a], m);
   #pragma unroll
   for (int b = 0; b < 4; b++) m = fma(Y[b], lmj[b], m);
-  const double v = (((s0 + s1) + (s2 + s3)) - m) / T - fast_log(T, tab);
+  const double v = (((s0 + s1) + (s2 + s3)) - m) / T - fast_log<false>(T, tab);
   return (ne > 0.0) ? 2.0 * ne * v : 0.0;
 }
 
