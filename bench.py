@@ -229,7 +229,7 @@ def main():
     SEED = 20261017
     host_msa = torch.from_numpy(msa).pin_memory()
     dev_msa = torch.from_numpy(msa).cuda()
-    cov_out = np.empty((L, L))
+    cov_out = torch.empty((L, L), dtype=torch.float64).pin_memory().numpy()          # pinned: the score matrix of the input alignment lands here
     NB = 1 << 18
 
     def generate():
@@ -272,7 +272,7 @@ def main():
             ctx.null_hist_pool(0, n_mine, w, pkg.GT, pkg.C16, pkg.APC, want_minmax=False)   # run_rscape(RANSS) + null_add2cumranklist
         out = None
         if rank == real_rank:
-            out = ctx.scan(real, pkg.GT, pkg.C16, pkg.APC, want_cov=isinstance(real, np.ndarray))   # run_rscape(GIVSS)
+            out = ctx.scan(real, pkg.GT, pkg.C16, pkg.APC, want_cov=isinstance(real, np.ndarray), cov_out=cov_out)   # run_rscape(GIVSS)
         bins, n, imax = ctx.hist_read(NB)
         bins = pkg.parallel.reduce_histogram(bins, device="cuda")
         return w, bins, out
@@ -324,8 +324,6 @@ def main():
         ctx.set_weights(wgt)
         generate()
         w, bins, out = job(host_msa.numpy())
-        if rank == real_rank and out is not None and out.get("cov") is not None:
-            cov_out[:] = out["cov"]
 
     ms_e2e = timed(job_e2e, args.steps, 1)
     e2e_value = cells_total * args.steps / (ms_e2e * 1e-3)

@@ -156,12 +156,15 @@ class Context:
             assert msa.shape == (self.N, self.L), (msa.shape, self.N, self.L)
         return msa
 
-    def scan(self, msa, stat=GT, covclass=C16, actype=APC, allowpair=None, tol=1e-6, want_cov=True, want_probs=False):
+    def scan(self, msa, stat=GT, covclass=C16, actype=APC, allowpair=None, tol=1e-6, want_cov=True, want_probs=False, cov_out=None):
+        """cov_out: optional float64 [L][L] array to receive the scores (e.g. a view of pinned memory)."""
         msa = self._msa(msa)
         p, dev = _ptr(msa)
         L = self.L
         ap = None if allowpair is None else np.ascontiguousarray(allowpair, dtype=np.float64)
-        out = dict(cov=np.empty((L, L)) if want_cov else None, pp=None, pm=None, ps=None, nseff=None, ngap=None)
+        if cov_out is not None:
+            assert cov_out.shape == (L, L) and cov_out.dtype == np.float64 and cov_out.flags.c_contiguous
+        out = dict(cov=(cov_out if cov_out is not None else np.empty((L, L))) if want_cov else None, pp=None, pm=None, ps=None, nseff=None, ngap=None)
         if want_probs:
             out.update(pp=np.empty((L, L, 16)), pm=np.empty((L, 4)), ps=np.empty((L, 5)), nseff=np.empty((L, L)), ngap=np.empty((L, L)))
         mn, mx = C.c_double(), C.c_double()

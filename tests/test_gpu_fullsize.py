@@ -55,13 +55,15 @@ def test_full_size_counts_and_properties(ctx, pkg, po, oracle, name):
     assert n == L * (L - 1) // 2 == int(bins.sum())
 
 
-def test_ssu_slice_scores_match_oracle(ctx, pkg, po, oracle):
+@pytest.mark.parametrize("nslices", [4, 5])
+def test_ssu_slice_scores_match_oracle(ctx, pkg, po, oracle, nslices):
     """Scores of a full-size scan cannot be compared pair by pair with an oracle run on a slice (pm and APC depend on all
-    columns), so the comparison runs the device on the same slice: N = 10000 sequences, 160 columns."""
+    columns), so the comparison runs the device on the same slice: N = 10000 sequences, 160 columns.  The oracle gets the
+    DOUBLE weights, so the fixed-point weight error (4 digit slices + 8-bit multiplier is the default) is inside the bound."""
     N, L = 10000, 160
     msa, wgt, _ = pkg.synth.synthetic_msa(N, 1800, seed=42)
     sub = np.ascontiguousarray(msa[:, 400:400 + L])
-    ctx.configure(N, L, 1, 5)
+    ctx.configure(N, L, 1, nslices)
     ctx.set_weights(wgt)
     got = ctx.scan(sub, pkg.GT, pkg.C16, pkg.APC)
     ref = oracle.scan(sub, wgt, po.GT, po.C16, po.APC)
@@ -69,3 +71,42 @@ def test_ssu_slice_scores_match_oracle(ctx, pkg, po, oracle):
     scale = max(abs(raw["maxcov"]), abs(raw["mincov"]), 1.0)
     off = ~np.eye(L, dtype=bool)
     assert np.max(np.abs(got["cov"][off] - ref["cov"][off])) <= 1e-9 * scale
+
+
+@pytest.mark.parametrize("name", ["rnasep", "ssu"])
+def test_full_size_statistic_sweep_is_consistent(ctx, pkg, name):
+    """BASELINE config 5 (statistic sweep) at full size, through relations between the device's own outputs:
+    G = 2 nseff MI and MIg = MI - ngap/nseff pair by pair (correlators.c:383-387, :560-570, :700-712), and the APC / ASC
+    corrections of every statistic recomputed in numpy from its raw scores (:1093-1118)."""
+    N, L = SHAPES[name]
+    msa, wgt, _ = pkg.synth.synthetic_msa(N, L, seed=7)
+    ctx.configure(N, L, 1, 0)
+    ctx.set_weights(wgt)
+    iu = np.triu_indices(L, 1)
+    first = ctx.scan(msa, pkg.MI, pkg.C16, pkg.NOCORR, want_probs=(name == "rnasep"))
+    mi = first["cov"][iu]
+    gt = ctx.scan(msa, pkg.GT, pkg.C16, pkg.NOCORR)["cov"][iu]
+    mig = ctx.scan(msa, pkg.MIg, pkg.C16, pkg.NOCORR)["cov"][iu]
+    ne, ng = ctx.last_nseff()
+    ne, ng = ne[iu], ng[iu]
+    ok = ne > 0
+    assert ok.mean() > 0.99
+    scale = np.abs(gt).max()
+    assert np.max(np.abs(gt[ok] - 2.0 * ne[ok] * mi[ok])) <= 1e-9 * scale
+    assert np.max(np.abs(mig[ok] - (mi[ok] - ng[ok] / ne[ok]))) <= 1e-9 * max(1.0, np.abs(mig).max())
+    if name == "rnasep":
+        assert np.allclose(first["nseff"][iu], ne, rtol=1e-12, atol=0)
+    off = ~np.eye(L, dtype=bool)
+    for stat in (pkg.GT, pkg.MI, pkg.MIr, pkg.CHI, pkg.OMES, pkg.RAFS):
+        raw = ctx.scan(msa, stat, pkg.C16, pkg.NOCORR)["cov"]
+        rawz = np.where(off, raw, 0.0)
+        avg = rawz.sum() / (L * (L - 1.0))
+        covx = rawz.sum(1) / (L - 1.0)
+        scale = max(np.abs(rawz).max(), 1e-300)
+        apc = ctx.scan(msa, stat, pkg.C16, pkg.APC)["cov"]
+        asc = ctx.scan(msa, stat, pkg.C16, pkg.ASC)["cov"]
+        want_apc = rawz - np.outer(covx, covx) / avg
+        want_asc = rawz - (covx[:, None] + covx[None, :] - avg)
+        assert np.max(np.abs(apc[off] - want_apc[off])) <= 1e-9 * scale, stat
+        assert np.max(np.abs(asc[off] - want_asc[off])) <= 1e-9 * scale, stat
+
