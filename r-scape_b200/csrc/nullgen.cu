@@ -11,15 +11,18 @@
 //
 // (A) Fitch + shuffle, R-scape's default null (src/R-scape.c:1653-1668):
 //     fitch_up/down_level tree_fitch_column (src/msatree.c:1700-1831): sets as 5-bit masks; post-order = one launch per
-//                         tree level from the deepest up, pre-order = from the root down; thread per (replicate, node, column).
+//                         tree level from the deepest up, pre-order = from the root down; a thread owns 4 columns of one
+//                         (replicate, node); the up pass is shared by all replicates when no residue is unknown.
 //     permutation_kernel + permute_root_kernel msamanip_ShuffleColumns (src/msamanip.c:1164-1233).  Only the root's permuted row is
 //                         ever read (every other row is overwritten by its parent's row at msamanip.c:1645).
-//     replay_level_kernel shuffle_tree_substitutions + shuffle_tree_substitute_all (src/msamanip.c:1597-1780):
-//                         one thread per (replicate, branch) of one tree level; counts the 5x5 substitutions of the
+//     replay_level_row_kernel shuffle_tree_substitutions + shuffle_tree_substitute_all (src/msamanip.c:1597-1780):
+//                         one warp per (replicate, branch) of one tree level; counts the 5x5 substitutions of the
 //                         branch on the Fitch rows, copies the shuffled parent row to the child and re-places
 //                         the substitutions at positions drawn uniformly without replacement among the columns
-//                         holding the source residue (one-pass selection sampling instead of the reference's
+//                         holding the source residue (rejection-sampled ranks instead of the reference's
 //                         Fisher-Yates over an index list: same distribution, exact counts).
+//     replay_level_kernel the same with one thread per branch and one-pass selection sampling; fallback for alignments
+//                         whose rank table does not fit in shared memory.
 #include "rsb_common.cuh"
 #include <stdlib.h>
 
@@ -218,7 +221,6 @@ __global__ void permute_root_kernel(int N, int L, int first_rep, const uint8_t *
 
 constexpr int RP_THREADS = 128;
 constexpr int RP_BATCH   = 8;        // 32-bit words (4 alignment columns each) loaded together
-constexpr long long RP_WARP_TASKS = 12000;   // levels with at most this many (replicate, branch) tasks use the warp-per-branch variant
 
 // PCG32 (XSH-RR): the cheap sequential stream of one (replicate, branch), seeded from a Philox block
 struct Pcg32 {
@@ -343,98 +345,6 @@ replay_level_kernel(const int *__restrict__ left, const int *__restrict__ right,
     }
   } else {
     for (int c = 0; c < L; c++) { const int cls = par_s[c]; kid_s[c] = (uint8_t) (ktot > 0 ? place(cls) : cls); }
-  }
-}
-
-constexpr int RPW_WARPS = 4;
-constexpr int RPW_MAXWORDS = 128;      // 32-column words per class bitmask (L <= 4096)
-
-// Latency variant of the replay for tree levels with few branches (near the root): one WARP per (replicate, branch).
-// The classes of the shuffled parent row are kept as bitmasks; every substitution picks the k-th remaining candidate of
-// its source class (k uniform) by a warp-wide rank-select and clears that bit -- uniform sampling without replacement,
-// the same distribution as the thread-per-branch kernel and as the reference's Fisher-Yates shuffle.  The work per branch
-// is larger, but a level finishes in tens of microseconds instead of waiting for one thread to walk the whole row.
-__global__ void __launch_bounds__(RPW_WARPS * 32)
-replay_level_warp_kernel(const int *__restrict__ left, const int *__restrict__ right, const int *__restrict__ order, int lvl_begin, int lvl_count,
-                         int N, int L, const uint8_t *__restrict__ msa, unsigned long long seed, unsigned long long id0, int first_rep, int nrep,
-                         const uint8_t *__restrict__ ancbuf, uint8_t *__restrict__ shancbuf, uint8_t *__restrict__ res)
-{
-  __shared__ unsigned masks[RPW_WARPS][5][RPW_MAXWORDS];
-  __shared__ int nsub[RPW_WARPS][25];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long task = (long long) blockIdx.x * RPW_WARPS + warp;
-  if (task >= 2LL * lvl_count * nrep) return;
-  const int side = (int) (task & 1);
-  const long long nt = task >> 1;
-  const int rr = (int) (nt / lvl_count);
-  const int r = first_rep + rr;
-  const uint32_t rid = (uint32_t) (id0 + (unsigned long long) rr);
-  const int v = order[lvl_begin + (int) (nt % lvl_count)];
-  const int nwords = (L + 31) >> 5;
-  const uint8_t *anc = ancbuf + (size_t) r * (N - 1) * L;
-  uint8_t *shanc = shancbuf + (size_t) r * (N - 1) * L;
-  uint8_t *leaves = res + (size_t) r * N * L;
-  const uint8_t *par_o = anc + (size_t) v * L;
-  const uint8_t *par_s = shanc + (size_t) v * L;
-  const int ch = side ? right[v] : left[v];
-  const uint8_t *kid_o = (ch > 0) ? anc + (size_t) ch * L : msa + (size_t) (-ch) * L;
-  uint8_t *kid_s = (ch > 0) ? shanc + (size_t) ch * L : leaves + (size_t) (-ch) * L;
-
-  Philox ph; ph.key[0] = (uint32_t) seed ^ (0xC2B2AE35u * (rid + 1u)); ph.key[1] = (uint32_t) (seed >> 32) ^ 0x5bd1e995u;
-  uint32_t sd[4]; ph.block((uint32_t) v, 0x7ee1u + (uint32_t) side, 0u, 0u, sd);          // same stream as the thread variant's seed
-  Pcg32 rng; rng.state = ((unsigned long long) sd[0] << 32) | sd[1]; rng.inc = ((((unsigned long long) sd[2] << 32) | sd[3]) << 1) | 1ULL;
-  rng.next();
-
-  if (lane < 25) nsub[warp][lane] = 0;
-  __syncwarp();
-  // one sweep: class bitmasks of the shuffled parent row, copy of that row to the child (:1645), substitution counts (:1634-1643)
-  for (int c0 = 0; c0 < L; c0 += 32) {
-    const int c = c0 + lane;
-    const bool in = c < L;
-    const int xs = in ? par_s[c] : 255;
-    #pragma unroll
-    for (int a = 0; a < 5; a++) { const unsigned b = __ballot_sync(0xffffffffu, xs == a); if (lane == 0) masks[warp][a][c0 >> 5] = b; }
-    if (in) {
-      kid_s[c] = (uint8_t) xs;
-      const int pa = par_o[c], kd = kid_o[c];
-      if (pa != kd && pa <= 4 && kd <= 4) atomicAdd(&nsub[warp][pa * 5 + kd], 1);
-    }
-  }
-  __syncwarp();
-  for (int a = 0; a < 5; a++) {
-    // working copy of the class-a mask in registers: lane owns words lane, lane+32, ...
-    unsigned wv[RPW_MAXWORDS / 32]; int pc = 0;
-    #pragma unroll
-    for (int q = 0; q < RPW_MAXWORDS / 32; q++) { const int wd = lane + 32 * q; wv[q] = (wd < nwords) ? masks[warp][a][wd] : 0u; pc += __popc(wv[q]); }
-    int remaining = pc;
-    #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) remaining += __shfl_xor_sync(0xffffffffu, remaining, o);
-    for (int d = 0; d < 5; d++) {
-      int s = nsub[warp][a * 5 + d];
-      while (s > 0 && remaining > 0) {
-        const int k = (int) __umulhi(rng.next(), (uint32_t) remaining);                  // k-th remaining candidate, lane-major order
-        int incl = pc;                                                                     // inclusive scan of the per-lane counts
-        #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-        const int owner = __ffs(__ballot_sync(0xffffffffu, incl > k)) - 1;
-        const int before = __shfl_sync(0xffffffffu, incl - pc, owner);
-        if (lane == owner) {
-          int kk = k - before;
-          #pragma unroll
-          for (int q = 0; q < RPW_MAXWORDS / 32; q++) {
-            const int n = __popc(wv[q]);
-            if (kk >= 0 && kk < n) {
-              const int bit = __fns(wv[q], 0, kk + 1);
-              wv[q] &= ~(1u << bit);
-              kid_s[(lane + 32 * q) * 32 + bit] = (uint8_t) d;
-              kk = -1;
-            } else if (kk >= 0) kk -= n;
-          }
-          pc--;
-        }
-        remaining--; s--;
-      }
-    }
   }
 }
 
@@ -651,8 +561,7 @@ cudaError_t rsb_launch_fitch_shuffle(const int *left, const int *right, const in
     const long long tasks = 2LL * cnt * nrep;                    // branches of this level over all replicates
     const int code_words = (L + 7) / 8;
     const size_t smem = (size_t) RPR_WARPS * (5 * code_words + 32) * sizeof(unsigned);
-    static const int variant = getenv("RSCAPE_B200_REPLAY") ? atoi(getenv("RSCAPE_B200_REPLAY")) : 0;   // experiments: 1 = thread/warp hybrid
-    if (variant == 0 && smem <= 200 * 1024) {                    // row variant: one warp per branch, coalesced
+    if (smem <= 200 * 1024) {                                    // row variant: one warp per branch, coalesced
       const unsigned grid = (unsigned) ((tasks + RPR_WARPS - 1) / RPR_WARPS);
       if (L % 4 == 0) {
         if (smem > 48 * 1024) cudaFuncSetAttribute(replay_level_row_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
@@ -663,12 +572,7 @@ cudaError_t rsb_launch_fitch_shuffle(const int *left, const int *right, const in
       }
       continue;
     }
-    static const long long warp_tasks = getenv("RSCAPE_B200_RPW_TASKS") ? atoll(getenv("RSCAPE_B200_RPW_TASKS")) : RP_WARP_TASKS;
-    if (tasks <= warp_tasks && L <= RPW_MAXWORDS * 32) {        // few branches: latency variant, one warp per branch
-      const unsigned grid = (unsigned) ((tasks + RPW_WARPS - 1) / RPW_WARPS);
-      replay_level_warp_kernel<<<grid, RPW_WARPS * 32, 0, st>>>(left, right, order, b, cnt, N, L, msa, seed, id0, first_rep, nrep, anc, shanc, res);
-      continue;
-    }
+    // alignments too long for the code table in shared memory (L > ~80 000): one thread per branch, selection sampling
     const unsigned grid = (unsigned) ((tasks + RP_THREADS - 1) / RP_THREADS);       // many branches: throughput variant, one thread per branch
     if (L % 4 == 0) replay_level_kernel<true><<<grid, RP_THREADS, 0, st>>>(left, right, order, b, cnt, N, L, msa, seed, id0, first_rep, nrep, anc, shanc, res);
     else            replay_level_kernel<false><<<grid, RP_THREADS, 0, st>>>(left, right, order, b, cnt, N, L, msa, seed, id0, first_rep, nrep, anc, shanc, res);
