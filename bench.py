@@ -37,6 +37,7 @@ WORKLOADS = {
     "rnasep": dict(L=400, N=5000, nulls=20),
     "ssu": dict(L=1800, N=10000, nulls=100),
     "lsu": dict(L=3500, N=20000, nulls=20),
+    "sweep": dict(L=1800, N=10000, nulls=500),      # BASELINE config 5: run once per --stat / --actype
 }
 METRIC = "pair-cells/s (L^2*N/2) GTp+APC incl. nulls"
 
@@ -180,6 +181,9 @@ def main():
     ap.add_argument("--workload", default="ssu", choices=sorted(WORKLOADS))
     ap.add_argument("--slices", type=int, default=4,
                     help="8-bit digit slices S of the fixed-point weights wq = u V (8-bit multiplier u, V < 256^S): ~8(S+1)-bit weights")
+    ap.add_argument("--stat", default="GT", choices=["GT", "MI", "MIr", "MIg", "CHI", "OMES", "RAFS"],
+                    help="covariation statistic of the scans (BASELINE config 5 sweeps them; the headline metric is GT)")
+    ap.add_argument("--actype", default="APC", choices=["APC", "ASC"], help="background correction")
     ap.add_argument("--ref-cols", type=int, default=160)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -241,6 +245,10 @@ def main():
         if n_mine:
             ctx.null_fitch_shuffle(host_msa.numpy(), SEED, n_mine, first_rep=0, first_id=my_ids[0])
 
+    STAT, ACT = getattr(pkg, args.stat), getattr(pkg, args.actype)
+    if args.grid_shard and (args.stat != "GT" or args.actype != "APC"):
+        raise SystemExit("--grid-shard runs the headline statistic (GT, APC) only")
+
     def sharded_scan(src, hist_w=None, want_cov=False):
         """One scan with the pair grid sharded over the ranks: three phases, one small all-reduce between them."""
         ms = ctx.sharded_counts_pool(src) if isinstance(src, int) else ctx.sharded_counts(src)
@@ -267,12 +275,12 @@ def main():
         if args.grid_shard:
             return job_grid(real)
         ctx.hist_reset()
-        w, _, _ = ctx.null_width_pool(w0_entry, pkg.GT, pkg.C16, pkg.APC)             # calculate_width_histo
+        w, _, _ = ctx.null_width_pool(w0_entry, STAT, pkg.C16, ACT)                   # calculate_width_histo
         if n_mine:
-            ctx.null_hist_pool(0, n_mine, w, pkg.GT, pkg.C16, pkg.APC, want_minmax=False)   # run_rscape(RANSS) + null_add2cumranklist
+            ctx.null_hist_pool(0, n_mine, w, STAT, pkg.C16, ACT, want_minmax=False)         # run_rscape(RANSS) + null_add2cumranklist
         out = None
         if rank == real_rank:
-            out = ctx.scan(real, pkg.GT, pkg.C16, pkg.APC, want_cov=isinstance(real, np.ndarray), cov_out=cov_out)   # run_rscape(GIVSS)
+            out = ctx.scan(real, STAT, pkg.C16, ACT, want_cov=isinstance(real, np.ndarray), cov_out=cov_out)   # run_rscape(GIVSS)
         bins, n, imax = ctx.hist_read(NB)
         bins = pkg.parallel.reduce_histogram(bins, device="cuda")
         return w, bins, out
@@ -359,7 +367,7 @@ def main():
         line = dict(metric=METRIC, value=value, unit="pair-cells/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms_dev / args.steps, higher_is_better=True, scaling="strong", vs_baseline=None,
                     dtype="u8 x u8 -> s32 tensor-core counts (fixed-point weights), f64 statistics", data="synthetic",
-                    config=dict(workload=f"{args.workload}: L={L} N={N} nulls={R} GTp+APC, scans per step = {scans_total} "
+                    config=dict(workload=f"{args.workload}: L={L} N={N} nulls={R} {args.stat}+{args.actype}, scans per step = {scans_total} "
                                          f"(width pass + {R} nulls + input alignment)",
                                 weight_slices=args.slices,
                                 weights=f"fixed point wq = u V, u < 256, V < 256^{args.slices}: largest |wq 2^-q - w| = {q_abs:.3g} "

@@ -110,6 +110,13 @@ correct_hist_kernel(double *__restrict__ cov, const double *__restrict__ covx, c
   const double w   = do_hist ? *wptr : 1.0;
   double vmin = INFINITY, vmax = -INFINITY;
 
+  // shared-memory bins cover [b0, b0 + CH_SMEM_BINS), centred on the bin of score 0 (corrected null scores pile up
+  // there, and with a small w -- MI-type statistics -- that bin lies far above bin 0); the rest goes to global atomics
+  int b0 = 0;
+  if (do_hist && w > 0.0) {
+    const double c = ceil((-bmin) / w - 1.0) - (double) (CH_SMEM_BINS / 2);
+    b0 = (c > 0.0 && c < (double) nbins) ? (int) c : 0;
+  }
   if (do_hist) { for (int k = threadIdx.x; k < CH_SMEM_BINS; k += CH_TJ) sh[k] = 0; __syncthreads(); }
 
   if (tile_live && j < L) {
@@ -128,8 +135,8 @@ correct_hist_kernel(double *__restrict__ cov, const double *__restrict__ covx, c
         const double bd = ceil(((x - bmin) / w) - 1.);                // esl_histogram_Score2Bin
         if (bd >= 0.0 && bd < (double) nbins) {
           const int b = (int) bd;
-          if (b < CH_SMEM_BINS) atomicAdd(&sh[b], 1u);
-          else                  atomicAdd(&hist[b], 1ull);
+          if (b >= b0 && b < b0 + CH_SMEM_BINS) atomicAdd(&sh[b - b0], 1u);
+          else                                  atomicAdd(&hist[b], 1ull);
         } else atomicOr(flags, 4);                                    // histogram capacity exceeded
       }
     }
@@ -142,8 +149,8 @@ correct_hist_kernel(double *__restrict__ cov, const double *__restrict__ covx, c
   if (lane == 0) { smin[warp] = vmin; smax[warp] = vmax; }
   __syncthreads();
   if (do_hist)
-    for (int k = threadIdx.x; k < CH_SMEM_BINS && k < nbins; k += CH_TJ)
-      if (sh[k]) atomicAdd(&hist[k], (unsigned long long) sh[k]);
+    for (int k = threadIdx.x; k < CH_SMEM_BINS && b0 + k < nbins; k += CH_TJ)
+      if (sh[k]) atomicAdd(&hist[b0 + k], (unsigned long long) sh[k]);
   if (threadIdx.x == 0) {
     double a = smin[0], b = smax[0];
     for (int q = 1; q < CH_TJ / 32; q++) { a = fmin(a, smin[q]); b = fmax(b, smax[q]); }

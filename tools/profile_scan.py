@@ -15,6 +15,7 @@ import bench  # noqa: E402
 pkg = ge.load_package()
 name = sys.argv[1] if len(sys.argv) > 1 else "ssu"
 nrep = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+stat = getattr(pkg, sys.argv[3]) if len(sys.argv) > 3 else pkg.GT
 w = bench.WORKLOADS[name]
 N, L = w["N"], w["L"]
 rng = np.random.default_rng(1)
@@ -23,7 +24,7 @@ ctx = pkg.Context(0)
 ctx.configure(N, L, 2, 4)
 ctx.set_weights(rng.gamma(2.0, 0.5, N))
 ctx.hist_reset()
-width = ctx.null_width(msa[0])[0]
-ctx.null_hist(msa, width)
+width = ctx.null_width(msa[0], stat)[0]
+ctx.null_hist(msa, width, stat)
 print("bins", int(ctx.hist_read(4000)[1]))
 ctx.close()
