@@ -229,7 +229,8 @@ def main():
     own0 = (n_mine > 0 and my_ids[0] == 0)
     real_rank = world - 1                                             # the input alignment is scanned by the rank with the fewest nulls
     ctx.pool_reserve(n_mine + (0 if own0 else 1))
-    w0_entry = 0 if own0 else n_mine                                  # pool entry holding replicate 0 (width pass)
+    w0_entry = 0                                                      # pool entry holding replicate 0 (width pass)
+    blk0 = 0 if own0 else 1                                           # first pool entry of this rank's block of nulls
     SEED = 20261017
     host_msa = torch.from_numpy(msa).pin_memory()
     dev_msa = torch.from_numpy(msa).cuda()
@@ -240,10 +241,10 @@ def main():
         """R-scape's default null model on the device: Fitch + tree-substitution shuffle (null_rscape, R-scape.c:1653-1661).
         Replicates are keyed by their global id, so every rank that needs replicate 0 generates the same alignment."""
         ctx.set_tree(tree.left, tree.right, tree.parent, tree.ld, tree.rd)
-        if not own0:                                                    # the width pass wants replicate 0 first
-            ctx.null_fitch_shuffle(host_msa.numpy(), SEED, 1, first_rep=w0_entry, first_id=0)
-        if n_mine:
+        if own0:
             ctx.null_fitch_shuffle(host_msa.numpy(), SEED, n_mine, first_rep=0, first_id=my_ids[0])
+        else:                                                           # replicate 0 (width pass) and this rank's block in one call
+            ctx.null_fitch_shuffle(host_msa.numpy(), SEED, n_mine + 1, first_rep=0, ids=[0] + list(my_ids))
 
     STAT, ACT = getattr(pkg, args.stat), getattr(pkg, args.actype)
     if args.grid_shard and (args.stat != "GT" or args.actype != "APC"):
@@ -277,7 +278,7 @@ def main():
         ctx.hist_reset()
         w, _, _ = ctx.null_width_pool(w0_entry, STAT, pkg.C16, ACT)                   # calculate_width_histo
         if n_mine:
-            ctx.null_hist_pool(0, n_mine, w, STAT, pkg.C16, ACT, want_minmax=False)         # run_rscape(RANSS) + null_add2cumranklist
+            ctx.null_hist_pool(blk0, n_mine, w, STAT, pkg.C16, ACT, want_minmax=False)         # run_rscape(RANSS) + null_add2cumranklist
         out = None
         if rank == real_rank:
             out = ctx.scan(real, STAT, pkg.C16, ACT, want_cov=isinstance(real, np.ndarray), cov_out=cov_out)   # run_rscape(GIVSS)

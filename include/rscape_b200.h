@@ -142,6 +142,10 @@ int rsb_null_simulate(rsb_ctx *ctx, const double *Q, const uint8_t *root, const 
 /* default null of R-scape: Fitch ancestral reconstruction + one column permutation + per-branch
  * substitution re-placement (src/msatree.c:173-227,1700-1931; src/msamanip.c:1164-1233,1449-1780) */
 int rsb_null_fitch_shuffle(rsb_ctx *ctx, const uint8_t *msa, int64_t row_stride, uint64_t seed, uint64_t first_id, int first_rep, int nrep);
+/* The same with an explicit list of global replicate ids (host, uint64[nrep]) instead of first_id, first_id+1, ...: a rank
+ * of a multi-GPU run generates replicate 0 (for the width pass, src/R-scape.c:1281) and its own block in one call. */
+int rsb_null_fitch_shuffle_ids(rsb_ctx *ctx, const uint8_t *msa, int64_t row_stride, uint64_t seed, const uint64_t *ids,
+                               int first_rep, int nrep);
 /* calculate_width_histo / the null loop on pool entries */
 int rsb_null_width_pool(rsb_ctx *ctx, int rep, int stat, int covclass, int actype, const double *allowpair, double tol,
                         double w_old, double bmin, int hpts, double *w_out, double *mincov, double *maxcov);

@@ -86,6 +86,7 @@ def lib():
         L.rsb_set_tree.argtypes = [_vp, _ip, _ip, _ip, _dp, _dp]
         L.rsb_null_simulate.argtypes = [_vp, _dp, _u8p, _u8p, C.c_int64, C.c_uint64, C.c_uint64, C.c_int, C.c_int]
         L.rsb_null_fitch_shuffle.argtypes = [_vp, _u8p, C.c_int64, C.c_uint64, C.c_uint64, C.c_int, C.c_int]
+        L.rsb_null_fitch_shuffle_ids.argtypes = [_vp, _u8p, C.c_int64, C.c_uint64, _u64p, C.c_int, C.c_int]
         L.rsb_counters.argtypes = [_vp, _i64p, _dp, _i64p, C.c_int]
         L.rsb_profile_gram.argtypes = [_vp, C.c_int]
         _lib = L
@@ -293,8 +294,14 @@ class Context:
         self._ck(lib().rsb_null_simulate(self._h, _d(Q), root.ctypes.data_as(_u8p), None if gm is None else gm.ctypes.data_as(_u8p),
                                          self.L, seed, first_rep if first_id is None else first_id, first_rep, nrep))
 
-    def null_fitch_shuffle(self, msa, seed, nrep, first_rep=0, first_id=None):
+    def null_fitch_shuffle(self, msa, seed, nrep, first_rep=0, first_id=None, ids=None):
+        """ids: optional explicit global replicate ids (len nrep) instead of first_id, first_id + 1, ..."""
         msa = self._msa(msa)
+        if ids is not None:
+            ids = np.ascontiguousarray(ids, dtype=np.uint64)
+            assert len(ids) == nrep
+            self._ck(lib().rsb_null_fitch_shuffle_ids(self._h, msa.ctypes.data_as(_u8p), self.L, seed, ids.ctypes.data_as(_u64p), first_rep, nrep))
+            return
         self._ck(lib().rsb_null_fitch_shuffle(self._h, msa.ctypes.data_as(_u8p), self.L, seed,
                                               first_rep if first_id is None else first_id, first_rep, nrep))
 

@@ -56,10 +56,12 @@ cudaError_t rsb_launch_null_simulate(const int *left, const int *right, const in
                                      const uint8_t *gapmask, long long gap_stride, unsigned long long seed, unsigned long long id0, int first_rep, int nrep,
                                      uint8_t *res, uint8_t *scratch, cudaStream_t st);
 cudaError_t rsb_launch_fitch_shuffle(const int *left, const int *right, const int *parent, const int *order, const int *level_start,
-                                     int nlevels, int N, int L, const uint8_t *msa, unsigned long long seed, unsigned long long id0, int first_rep, int nrep,
+                                     int nlevels, int N, int L, const uint8_t *msa, unsigned long long seed, unsigned long long id0,
+                                     const unsigned long long *ids, int first_rep, int nrep,
                                      uint8_t *res, uint8_t *anc, uint8_t *shanc, int *perm, uint8_t *sets_shared, int build_sets, cudaStream_t st);
 cudaError_t rsb_launch_unknown_check(const uint8_t *msa, size_t n, int *d_flag, int *unknown, cudaStream_t st);
-cudaError_t rsb_launch_permutations(int L, unsigned long long seed, unsigned long long id0, int first_rep, int nrep, int *perm, cudaStream_t st);
+cudaError_t rsb_launch_permutations(int L, unsigned long long seed, unsigned long long id0, const unsigned long long *ids, int first_rep, int nrep,
+                                    int *perm, cudaStream_t st);
 
 namespace {
 constexpr int HIST_BINS = 1 << 22;
@@ -125,6 +127,7 @@ struct rsb_ctx {
   std::vector<int> h_level_start;
   uint8_t *d_root = nullptr, *d_gapmask = nullptr, *d_simscratch = nullptr, *d_msa0 = nullptr, *d_anc = nullptr, *d_shanc = nullptr, *d_sets = nullptr;
   int *d_genflag = nullptr;
+  unsigned long long *d_ids = nullptr; size_t ids_cap = 0;    // explicit replicate ids of a generator call
   bool have_tree = false;
   uint8_t *d_pool = nullptr;          // device-resident null alignments [Rpool][N][L] (output of the generators)
   int Rpool = 0;
@@ -197,7 +200,7 @@ void free_plan(rsb_ctx *c)
   dfree(c->d_meanp); dfree(c->d_w); dfree(c->d_blocksum); dfree(c->d_msum); dfree(c->d_covsum); dfree(c->d_hist); dfree(c->d_colsum); dfree(c->d_flags); dfree(c->d_ps); dfree(c->d_pp_out);
   dfree(c->d_nseff_out); dfree(c->d_ngap_out); dfree(c->d_left); dfree(c->d_right); dfree(c->d_parent); dfree(c->d_order);
   dfree(c->d_level_start); dfree(c->d_perm); dfree(c->d_pcdf); dfree(c->d_root); dfree(c->d_gapmask); dfree(c->d_simscratch);
-  dfree(c->d_msa0); dfree(c->d_anc); dfree(c->d_shanc); dfree(c->d_pool); dfree(c->d_sets); dfree(c->d_genflag);
+  dfree(c->d_msa0); dfree(c->d_anc); dfree(c->d_shanc); dfree(c->d_pool); dfree(c->d_sets); dfree(c->d_genflag); dfree(c->d_ids); c->ids_cap = 0;
   c->Rpool = 0;
   c->have_tree = false;
 }
@@ -1294,7 +1297,8 @@ int rsb_null_simulate(rsb_ctx *ctx, const double *Q, const uint8_t *root, const 
   return 0;
 }
 
-int rsb_null_fitch_shuffle(rsb_ctx *ctx, const uint8_t *msa, int64_t row_stride, uint64_t seed, uint64_t first_id, int first_rep, int nrep)
+static int fitch_shuffle_impl(rsb_ctx *ctx, const uint8_t *msa, int64_t row_stride, uint64_t seed, uint64_t first_id, const uint64_t *ids,
+                              int first_rep, int nrep)
 {
   RSB_CUDA_OK(cudaSetDevice(ctx->device));
   if (!ctx->have_tree) { rsb_set_error(ctx, "rsb_set_tree first"); return 1; }
@@ -1318,7 +1322,13 @@ int rsb_null_fitch_shuffle(rsb_ctx *ctx, const uint8_t *msa, int64_t row_stride,
   RSB_CUDA_OK(rsb_launch_unknown_check(ctx->d_msa0, (size_t) N * L, ctx->d_genflag, &unknown, sg));
   if (getenv("RSCAPE_B200_FITCH_PER_REPLICATE")) unknown = 1;      // tests: force the general path
   uint8_t *sets = unknown ? nullptr : ctx->d_sets;
-  RSB_CUDA_OK(rsb_launch_permutations(L, seed, first_id, first_rep, nrep, ctx->d_perm, sg));
+  unsigned long long *d_ids = nullptr;
+  if (ids) {                                                         // explicit replicate ids (device copy; small, staged by the driver)
+    if (ctx->ids_cap < (size_t) nrep) { dfree(ctx->d_ids); RSB_CUDA_OK(cudaMalloc(&ctx->d_ids, sizeof(unsigned long long) * (size_t) ctx->Rpool)); ctx->ids_cap = ctx->Rpool; }
+    RSB_CUDA_OK(cudaMemcpyAsync(ctx->d_ids, ids, sizeof(unsigned long long) * (size_t) nrep, cudaMemcpyHostToDevice, sg));
+    d_ids = ctx->d_ids;
+  }
+  RSB_CUDA_OK(rsb_launch_permutations(L, seed, first_id, d_ids, first_rep, nrep, ctx->d_perm, sg));
   // chunk sizes 1, 4, 8, 16, 32, then the rest; a small batch (every level kernel is latency-bound then) goes in one piece
   int off = 0, chunks = 0, next = 4;
   while (off < nrep) {
@@ -1326,7 +1336,7 @@ int rsb_null_fitch_shuffle(rsb_ctx *ctx, const uint8_t *msa, int64_t row_stride,
     if (off > 0) next *= 2;
     if (nrep <= 16 || chunks >= 5 || nrep - off - n < 4) n = nrep - off;
     RSB_CUDA_OK(rsb_launch_fitch_shuffle(ctx->d_left, ctx->d_right, ctx->d_parent, ctx->d_order, ctx->h_level_start.data(), ctx->nlevels, N, L,
-                                         ctx->d_msa0, seed, first_id + (uint64_t) off, first_rep + off, n, ctx->d_pool, ctx->d_anc, ctx->d_shanc,
+                                         ctx->d_msa0, seed, first_id + (uint64_t) off, d_ids ? d_ids + off : nullptr, first_rep + off, n, ctx->d_pool, ctx->d_anc, ctx->d_shanc,
                                          ctx->d_perm, sets, off == 0, sg));
     cudaEvent_t e = ctx->gen_ring[ctx->gen_next++ % ctx->gen_ring.size()];
     RSB_CUDA_OK(cudaEventRecord(e, sg));
@@ -1335,6 +1345,17 @@ int rsb_null_fitch_shuffle(rsb_ctx *ctx, const uint8_t *msa, int64_t row_stride,
   }
   ctx->launches += 2 + chunks * (1 + 3 * ctx->nlevels);
   return 0;
+}
+
+int rsb_null_fitch_shuffle(rsb_ctx *ctx, const uint8_t *msa, int64_t row_stride, uint64_t seed, uint64_t first_id, int first_rep, int nrep)
+{
+  return fitch_shuffle_impl(ctx, msa, row_stride, seed, first_id, nullptr, first_rep, nrep);
+}
+
+int rsb_null_fitch_shuffle_ids(rsb_ctx *ctx, const uint8_t *msa, int64_t row_stride, uint64_t seed, const uint64_t *ids, int first_rep, int nrep)
+{
+  if (!ids) { rsb_set_error(ctx, "rsb_null_fitch_shuffle_ids: no ids"); return 1; }
+  return fitch_shuffle_impl(ctx, msa, row_stride, seed, 0, ids, first_rep, nrep);
 }
 
 int rsb_pool_get(rsb_ctx *ctx, int first_rep, int nrep, uint8_t *out)

@@ -95,12 +95,12 @@ __device__ __forceinline__ int pick_member(unsigned set, uint32_t rnd)      // u
 template <int W>
 __global__ void fitch_up_level_kernel(const int *__restrict__ left, const int *__restrict__ right, const int *__restrict__ order, int lvl_begin,
                                       int N, int L, const uint8_t *__restrict__ msa, unsigned long long seed, unsigned long long id0,
-                                      int first_rep, uint8_t *__restrict__ ancbuf)
+                                      const unsigned long long *__restrict__ ids, int first_rep, uint8_t *__restrict__ ancbuf)
 {
   const int c0 = (blockIdx.x * blockDim.x + threadIdx.x) * W;
   const int v = order[lvl_begin + blockIdx.y];
   const int r = first_rep + blockIdx.z;
-  const uint32_t rid = (uint32_t) (id0 + blockIdx.z);
+  const uint32_t rid = (uint32_t) (ids ? ids[blockIdx.z] : id0 + blockIdx.z);
   if (c0 >= L) return;
   Philox rng; rng.key[0] = (uint32_t) seed ^ 0xF17C4u; rng.key[1] = (uint32_t) (seed >> 32) ^ (0x85EBCA6Bu * (rid + 1u));
   uint8_t *anc = ancbuf + (size_t) r * (N - 1) * L;
@@ -138,13 +138,13 @@ __global__ void fitch_up_level_kernel(const int *__restrict__ left, const int *_
 // no substitution in most columns.
 template <int W>
 __global__ void fitch_down_level_kernel(const int *__restrict__ left, const int *__restrict__ right, const int *__restrict__ order, int lvl_begin,
-                                        int N, int L, unsigned long long seed, unsigned long long id0, int first_rep,
+                                        int N, int L, unsigned long long seed, unsigned long long id0, const unsigned long long *__restrict__ ids, int first_rep,
                                         const uint8_t *sets, size_t sets_stride, uint8_t *ancbuf)
 {
   const int c0 = (blockIdx.x * blockDim.x + threadIdx.x) * W;
   const int v = order[lvl_begin + blockIdx.y];
   const int r = first_rep + blockIdx.z;
-  const uint32_t rid = (uint32_t) (id0 + blockIdx.z);
+  const uint32_t rid = (uint32_t) (ids ? ids[blockIdx.z] : id0 + blockIdx.z);
   if (c0 >= L) return;
   Philox rng; rng.key[0] = (uint32_t) seed ^ 0xF17C4u; rng.key[1] = (uint32_t) (seed >> 32) ^ (0x85EBCA6Bu * (rid + 1u));
   uint8_t *anc = ancbuf + (size_t) r * (N - 1) * L;
@@ -191,10 +191,11 @@ __global__ void unknown_flag_kernel(const uint8_t *__restrict__ msa, size_t n, i
 
 // one random permutation per replicate (Fisher-Yates by one thread; L is a few thousand).  It depends on (seed, replicate id)
 // only, so all replicates of a generator call are done by ONE launch before the per-chunk work.
-__global__ void permutation_kernel(int L, unsigned long long seed, unsigned long long id0, int first_rep, int *__restrict__ permbuf)
+__global__ void permutation_kernel(int L, unsigned long long seed, unsigned long long id0, const unsigned long long *__restrict__ ids, int first_rep,
+                                   int *__restrict__ permbuf)
 {
   const int r = first_rep + blockIdx.x;
-  const uint32_t rid = (uint32_t) (id0 + blockIdx.x);
+  const uint32_t rid = (uint32_t) (ids ? ids[blockIdx.x] : id0 + blockIdx.x);
   int *perm = permbuf + (size_t) r * L;
   for (int c = threadIdx.x; c < L; c += blockDim.x) perm[c] = c;
   __syncthreads();
@@ -249,8 +250,8 @@ struct Pcg32 {
 template <bool WORD>
 __global__ void __launch_bounds__(RP_THREADS)
 replay_level_kernel(const int *__restrict__ left, const int *__restrict__ right, const int *__restrict__ order, int lvl_begin, int lvl_count,
-                    int N, int L, const uint8_t *__restrict__ msa, unsigned long long seed, unsigned long long id0, int first_rep, int nrep,
-                    const uint8_t *__restrict__ ancbuf, uint8_t *__restrict__ shancbuf, uint8_t *__restrict__ res)
+                    int N, int L, const uint8_t *__restrict__ msa, unsigned long long seed, unsigned long long id0, const unsigned long long *__restrict__ ids,
+                    int first_rep, int nrep, const uint8_t *__restrict__ ancbuf, uint8_t *__restrict__ shancbuf, uint8_t *__restrict__ res)
 {
   __shared__ unsigned short nsub[25][RP_THREADS];     // substitutions a -> d still to place (touched on differences / picks only)
   const int t = threadIdx.x;
@@ -261,7 +262,7 @@ replay_level_kernel(const int *__restrict__ left, const int *__restrict__ right,
   const long long nt = task >> 1;
   const int rr = (int) (nt / lvl_count);
   const int r = first_rep + rr;
-  const uint32_t rid = (uint32_t) (id0 + (unsigned long long) rr);
+  const uint32_t rid = (uint32_t) (ids ? ids[rr] : id0 + (unsigned long long) rr);
   const int v = order[lvl_begin + (int) (nt % lvl_count)];
   const uint8_t *anc = ancbuf + (size_t) r * (N - 1) * L;
   uint8_t *shanc = shancbuf + (size_t) r * (N - 1) * L;
@@ -366,8 +367,8 @@ constexpr int RPR_WARPS = 4;        // 4 warps x ~4.6 KB of code table (L = 1800
 template <int W>
 __global__ void __launch_bounds__(RPR_WARPS * 32)
 replay_level_row_kernel(const int *__restrict__ left, const int *__restrict__ right, const int *__restrict__ order, int lvl_begin, int lvl_count,
-                        int N, int L, const uint8_t *__restrict__ msa, unsigned long long seed, unsigned long long id0, int first_rep, int nrep,
-                        const uint8_t *__restrict__ ancbuf, uint8_t *__restrict__ shancbuf, uint8_t *__restrict__ res, int code_words)
+                        int N, int L, const uint8_t *__restrict__ msa, unsigned long long seed, unsigned long long id0, const unsigned long long *__restrict__ ids,
+                        int first_rep, int nrep, const uint8_t *__restrict__ ancbuf, uint8_t *__restrict__ shancbuf, uint8_t *__restrict__ res, int code_words)
 {
   extern __shared__ unsigned rpr_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -379,7 +380,7 @@ replay_level_row_kernel(const int *__restrict__ left, const int *__restrict__ ri
   const long long nt = task >> 1;
   const int rr = (int) (nt / lvl_count);
   const int r = first_rep + rr;
-  const uint32_t rid = (uint32_t) (id0 + (unsigned long long) rr);
+  const uint32_t rid = (uint32_t) (ids ? ids[rr] : id0 + (unsigned long long) rr);
   const int v = order[lvl_begin + (int) (nt % lvl_count)];
   const uint8_t *anc = ancbuf + (size_t) r * (N - 1) * L;
   uint8_t *shanc = shancbuf + (size_t) r * (N - 1) * L;
@@ -515,9 +516,10 @@ cudaError_t rsb_launch_null_simulate(const int *left, const int *right, const in
 }
 
 // the column permutations of replicates [first_rep, first_rep + nrep) with ids id0 ... (once per generator call)
-cudaError_t rsb_launch_permutations(int L, unsigned long long seed, unsigned long long id0, int first_rep, int nrep, int *perm, cudaStream_t st)
+cudaError_t rsb_launch_permutations(int L, unsigned long long seed, unsigned long long id0, const unsigned long long *ids, int first_rep, int nrep,
+                                    int *perm, cudaStream_t st)
 {
-  permutation_kernel<<<nrep, 256, 0, st>>>(L, seed, id0, first_rep, perm);
+  permutation_kernel<<<nrep, 256, 0, st>>>(L, seed, id0, ids, first_rep, perm);
   return cudaGetLastError();
 }
 
@@ -531,7 +533,8 @@ cudaError_t rsb_launch_unknown_check(const uint8_t *msa, size_t n, int *d_flag, 
 }
 
 cudaError_t rsb_launch_fitch_shuffle(const int *left, const int *right, const int *parent, const int *order, const int *level_start_host,
-                                     int nlevels, int N, int L, const uint8_t *msa, unsigned long long seed, unsigned long long id0, int first_rep, int nrep,
+                                     int nlevels, int N, int L, const uint8_t *msa, unsigned long long seed, unsigned long long id0,
+                                     const unsigned long long *ids, int first_rep, int nrep,
                                      uint8_t *res, uint8_t *anc, uint8_t *shanc, int *perm, uint8_t *sets_shared, int build_sets, cudaStream_t st)
 {
   (void) parent;
@@ -545,15 +548,15 @@ cudaError_t rsb_launch_fitch_shuffle(const int *left, const int *right, const in
     const int b = level_start_host[lv], cnt = level_start_host[lv + 1] - b;
     uint8_t *dst = shared ? sets_shared : anc;
     const int z = shared ? 1 : nrep, fr = shared ? 0 : first_rep;
-    if (L % 4 == 0) fitch_up_level_kernel<4><<<dim3((L / 4 + 127) / 128, cnt, z), 128, 0, st>>>(left, right, order, b, N, L, msa, seed, id0, fr, dst);
-    else            fitch_up_level_kernel<1><<<dim3((L + 127) / 128, cnt, z), 128, 0, st>>>(left, right, order, b, N, L, msa, seed, id0, fr, dst);
+    if (L % 4 == 0) fitch_up_level_kernel<4><<<dim3((L / 4 + 127) / 128, cnt, z), 128, 0, st>>>(left, right, order, b, N, L, msa, seed, id0, ids, fr, dst);
+    else            fitch_up_level_kernel<1><<<dim3((L + 127) / 128, cnt, z), 128, 0, st>>>(left, right, order, b, N, L, msa, seed, id0, ids, fr, dst);
   }
   const uint8_t *sets = shared ? sets_shared : anc + (size_t) first_rep * (N - 1) * L;
   const size_t sets_stride = shared ? 0 : (size_t) (N - 1) * L;
   for (int lv = 0; lv < nlevels; lv++) {
     const int b = level_start_host[lv], cnt = level_start_host[lv + 1] - b;
-    if (L % 4 == 0) fitch_down_level_kernel<4><<<dim3((L / 4 + 127) / 128, cnt, nrep), 128, 0, st>>>(left, right, order, b, N, L, seed, id0, first_rep, sets, sets_stride, anc);
-    else            fitch_down_level_kernel<1><<<dim3((L + 127) / 128, cnt, nrep), 128, 0, st>>>(left, right, order, b, N, L, seed, id0, first_rep, sets, sets_stride, anc);
+    if (L % 4 == 0) fitch_down_level_kernel<4><<<dim3((L / 4 + 127) / 128, cnt, nrep), 128, 0, st>>>(left, right, order, b, N, L, seed, id0, ids, first_rep, sets, sets_stride, anc);
+    else            fitch_down_level_kernel<1><<<dim3((L + 127) / 128, cnt, nrep), 128, 0, st>>>(left, right, order, b, N, L, seed, id0, ids, first_rep, sets, sets_stride, anc);
   }
   permute_root_kernel<<<dim3((L + 255) / 256, nrep), 256, 0, st>>>(N, L, first_rep, anc, shanc, perm);
   for (int lv = 0; lv < nlevels; lv++) {
@@ -565,17 +568,17 @@ cudaError_t rsb_launch_fitch_shuffle(const int *left, const int *right, const in
       const unsigned grid = (unsigned) ((tasks + RPR_WARPS - 1) / RPR_WARPS);
       if (L % 4 == 0) {
         if (smem > 48 * 1024) cudaFuncSetAttribute(replay_level_row_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-        replay_level_row_kernel<4><<<grid, RPR_WARPS * 32, smem, st>>>(left, right, order, b, cnt, N, L, msa, seed, id0, first_rep, nrep, anc, shanc, res, code_words);
+        replay_level_row_kernel<4><<<grid, RPR_WARPS * 32, smem, st>>>(left, right, order, b, cnt, N, L, msa, seed, id0, ids, first_rep, nrep, anc, shanc, res, code_words);
       } else {
         if (smem > 48 * 1024) cudaFuncSetAttribute(replay_level_row_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-        replay_level_row_kernel<1><<<grid, RPR_WARPS * 32, smem, st>>>(left, right, order, b, cnt, N, L, msa, seed, id0, first_rep, nrep, anc, shanc, res, code_words);
+        replay_level_row_kernel<1><<<grid, RPR_WARPS * 32, smem, st>>>(left, right, order, b, cnt, N, L, msa, seed, id0, ids, first_rep, nrep, anc, shanc, res, code_words);
       }
       continue;
     }
     // alignments too long for the code table in shared memory (L > ~80 000): one thread per branch, selection sampling
     const unsigned grid = (unsigned) ((tasks + RP_THREADS - 1) / RP_THREADS);       // many branches: throughput variant, one thread per branch
-    if (L % 4 == 0) replay_level_kernel<true><<<grid, RP_THREADS, 0, st>>>(left, right, order, b, cnt, N, L, msa, seed, id0, first_rep, nrep, anc, shanc, res);
-    else            replay_level_kernel<false><<<grid, RP_THREADS, 0, st>>>(left, right, order, b, cnt, N, L, msa, seed, id0, first_rep, nrep, anc, shanc, res);
+    if (L % 4 == 0) replay_level_kernel<true><<<grid, RP_THREADS, 0, st>>>(left, right, order, b, cnt, N, L, msa, seed, id0, ids, first_rep, nrep, anc, shanc, res);
+    else            replay_level_kernel<false><<<grid, RP_THREADS, 0, st>>>(left, right, order, b, cnt, N, L, msa, seed, id0, ids, first_rep, nrep, anc, shanc, res);
   }
   return cudaGetLastError();
 }

@@ -86,3 +86,14 @@ def test_counts_cta_pair_kernel(ctx, po, oracle, monkeypatch, nslices, N, L):
     monkeypatch.setenv("RSCAPE_B200_GRAM_PAIR", "1")
     msa, wgt, _ = po.synthetic_msa(N, L, seed=N)
     _check(ctx, oracle, msa, np.ones(N) if nslices == 1 else wgt, nslices)
+
+
+def test_counts_many_sequences_caps_the_multiplier(ctx, po, oracle):
+    """N > 33 025: the 8-bit multiplier is capped so that sum_s u_s d_s stays inside the int32 accumulators."""
+    rng = np.random.default_rng(21)
+    N, L = 40000, 12
+    msa = rng.integers(0, 3, (N, L)).astype(np.uint8)
+    wgt = rng.uniform(0.5, 1.0, N)
+    _check(ctx, oracle, msa, wgt, 4)
+    wq, q, S = ctx.quantisation()
+    assert int(wq.max()) < 210 * 256 ** 4          # u <= floor((2^31 - 1) / (255 Kpad)) = 210

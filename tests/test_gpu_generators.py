@@ -190,6 +190,12 @@ def test_fitch_shuffle_is_deterministic_and_chunk_independent(ctx, po):
     for r in (0, 5, 23):
         ctx.null_fitch_shuffle(msa, seed=77, nrep=1, first_rep=2, first_id=r)
         assert np.array_equal(ctx.pool_get(1, 2)[0], a[r])
+    # an explicit id list (replicate 0 + a block, as a rank of a multi-GPU run asks for)
+    ids = [0, 17, 18, 19, 20, 5]
+    ctx.null_fitch_shuffle(msa, seed=77, nrep=len(ids), first_rep=3, ids=ids)
+    got = ctx.pool_get(len(ids), 3)
+    for k, r in enumerate(ids):
+        assert np.array_equal(got[k], a[r])
 
 
 def test_fitch_shuffle_shared_up_pass_equals_per_replicate(ctx, po, monkeypatch):
