@@ -282,8 +282,8 @@ def main():
         out = None
         if rank == real_rank:
             out = ctx.scan(real, STAT, pkg.C16, ACT, want_cov=isinstance(real, np.ndarray), cov_out=cov_out)   # run_rscape(GIVSS)
+        pkg.parallel.reduce_histogram_on_device(ctx, NB)                              # null_add2cumranklist across ranks, in place over NCCL
         bins, n, imax = ctx.hist_read(NB)
-        bins = pkg.parallel.reduce_histogram(bins, device="cuda")
         return w, bins, out
 
     t_gen0 = time.perf_counter()
@@ -325,6 +325,10 @@ def main():
     cnt = ctx.counters(reset=True)
     ctx.profile_gram(False)
     value = cells_total * args.steps / (ms_dev * 1e-3)
+    # sanity of what was timed: the cumulative histogram holds every pair of every null exactly once, on every rank
+    _, bins_chk, _ = job(dev_msa)
+    if int(bins_chk.sum()) != R * (L * (L - 1) // 2):
+        raise SystemExit(f"rank {rank}: cumulative null histogram holds {int(bins_chk.sum())} scores, expected {R * (L * (L - 1) // 2)}")
 
     # ---- e2e: host buffers through the C-ABI, copies inside the timed region ------------------------------
     # in : the input alignment (pinned host memory, uploaded twice: generators + scan), the tree, the weights

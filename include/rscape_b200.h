@@ -121,6 +121,11 @@ int rsb_null_hist(rsb_ctx *ctx, const uint8_t *nulls, int nrep, int64_t row_stri
 int rsb_hist_reset(rsb_ctx *ctx);
 /* bins[0..nb_cap), number of scores added, highest non-empty bin (-1 if none) */
 int rsb_hist_read(rsb_ctx *ctx, uint64_t *bins, int nb_cap, uint64_t *n_out, int *imax_out);
+/* Device-to-device copy of the first nb bins between the cumulative histogram and a caller's device buffer (uint64[nb]),
+ * to_library = 0 copies out, 1 copies in; returns when the copy is complete (the caller must have completed its own work on
+ * device_buf before copying in).  Lets a multi-GPU driver sum the histograms of its
+ * ranks with one NCCL all-reduce on the device (null_add2cumranklist across ranks, src/R-scape.c:1565-1612). */
+int rsb_hist_exchange(rsb_ctx *ctx, void *device_buf, int nb, int to_library);
 /* nseff / ngap of the last replicate scanned (quirk Q3: what .cov prints as nseff(%), src/power.c:94-95) */
 int rsb_last_nseff(rsb_ctx *ctx, double *nseff, double *ngap);
 

@@ -81,6 +81,7 @@ def lib():
         L.rsb_pool_get.argtypes = [_vp, C.c_int, C.c_int, _u8p]
         L.rsb_pool_put.argtypes = [_vp, C.c_int, C.c_int, _u8p]
         L.rsb_hist_reset.argtypes = [_vp]
+        L.rsb_hist_exchange.argtypes = [_vp, C.c_void_p, C.c_int, C.c_int]
         L.rsb_hist_read.argtypes = [_vp, _u64p, C.c_int, _u64p, _ip]
         L.rsb_last_nseff.argtypes = [_vp, _dp, _dp]
         L.rsb_set_tree.argtypes = [_vp, _ip, _ip, _ip, _dp, _dp]
@@ -110,6 +111,7 @@ class Context:
     def __init__(self, device=0, stream=None):
         self._h = _vp()
         self.N = self.L = 0
+        self.device = device
         L = lib()
         if L.rsb_create(device, _vp(stream) if stream else None, C.byref(self._h)) != 0:
             raise RscapeB200Error(L.rsb_create_error().decode())
@@ -272,6 +274,11 @@ class Context:
         n, imax = C.c_uint64(), C.c_int()
         self._ck(lib().rsb_hist_read(self._h, bins.ctypes.data_as(_u64p), nb, C.byref(n), C.byref(imax)))
         return bins, n.value, imax.value
+
+    def hist_exchange(self, tensor, to_library):
+        """Copy the first len(tensor) bins between the device histogram and a torch int64/uint64 CUDA tensor (device to device)."""
+        assert tensor.is_cuda and tensor.is_contiguous() and tensor.element_size() == 8
+        self._ck(lib().rsb_hist_exchange(self._h, C.c_void_p(tensor.data_ptr()), tensor.numel(), 1 if to_library else 0))
 
     def last_nseff(self):
         ne, ng = np.empty((self.L, self.L)), np.empty((self.L, self.L))

@@ -1157,6 +1157,16 @@ int rsb_hist_read(rsb_ctx *ctx, uint64_t *bins, int nb_cap, uint64_t *n_out, int
   return 0;
 }
 
+int rsb_hist_exchange(rsb_ctx *ctx, void *device_buf, int nb, int to_library)
+{
+  RSB_CUDA_OK(cudaSetDevice(ctx->device));
+  if (!ctx->d_hist || !device_buf || nb < 1 || nb > HIST_BINS) { rsb_set_error(ctx, "rsb_hist_exchange: bad arguments"); return 1; }
+  if (to_library) RSB_CUDA_OK(cudaMemcpyAsync(ctx->d_hist, device_buf, sizeof(uint64_t) * nb, cudaMemcpyDeviceToDevice, ctx->stream));
+  else            RSB_CUDA_OK(cudaMemcpyAsync(device_buf, ctx->d_hist, sizeof(uint64_t) * nb, cudaMemcpyDeviceToDevice, ctx->stream));
+  RSB_CUDA_OK(cudaStreamSynchronize(ctx->stream));                  // the caller's collective runs on another stream
+  return 0;
+}
+
 int rsb_last_nseff(rsb_ctx *ctx, double *nseff, double *ngap)
 {
   RSB_CUDA_OK(cudaSetDevice(ctx->device));

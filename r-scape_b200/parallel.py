@@ -30,6 +30,21 @@ def reduce_histogram(bins, device=None, group=None):
     return t.cpu().numpy().astype(np.uint64)
 
 
+def reduce_histogram_on_device(ctx, nb, group=None):
+    """Sum the first nb bins of the context's DEVICE histogram over all ranks (device copy out, NCCL all-reduce, device
+    copy back), so that a following hist_read returns the cumulative histogram of the whole job on every rank.
+    No-op without a process group."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return
+    t = torch.empty(int(nb), dtype=torch.int64, device=f"cuda:{ctx.device}")
+    ctx.hist_exchange(t, to_library=False)                      # synchronous: the bins are in t when it returns
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    torch.cuda.current_stream(t.device).synchronize()           # the library copies on its own stream
+    ctx.hist_exchange(t, to_library=True)
+
+
 def reduce_range(lo, hi, device=None, group=None):
     """Global (min, max) of the per-rank score ranges."""
     import torch
