@@ -184,6 +184,7 @@ def main():
     ap.add_argument("--stat", default="GT", choices=["GT", "MI", "MIr", "MIg", "CHI", "OMES", "RAFS"],
                     help="covariation statistic of the scans (BASELINE config 5 sweeps them; the headline metric is GT)")
     ap.add_argument("--actype", default="APC", choices=["APC", "ASC"], help="background correction")
+    ap.add_argument("--slots", type=int, default=0, help="replicate slots (alignments in flight); 0 = choose from the shape")
     ap.add_argument("--ref-cols", type=int, default=160)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -216,7 +217,7 @@ def main():
     # ---- synthetic inputs (same on every rank: seeded) ------------------------------------------------
     msa, wgt, _, tree = synth.synthetic_family(N, L, seed=42)        # alignment evolved on the tree the null generator is given
     stream = torch.cuda.current_stream()
-    slots = pkg.replicate_slots(N, L, R, args.slices)
+    slots = args.slots if args.slots > 0 else pkg.replicate_slots(N, L, R, args.slices)
     ctx = pkg.Context(local, stream.cuda_stream)
     ctx.configure(N, L, slots, args.slices)
     ctx.set_weights(wgt)

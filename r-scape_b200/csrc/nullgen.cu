@@ -362,17 +362,19 @@ replay_level_kernel(const int *__restrict__ left, const int *__restrict__ right,
 //   sweep 2  (shuffled parent row -> child row): a column of class a is the (running count of a)-th of its class; the
 //            code table says whether that rank was drawn and what it becomes (:1645-1757).
 // Work per branch is a few coalesced passes over its rows, independent of how the substitutions fall.
-constexpr int RPR_WARPS = 4;        // 4 warps x ~4.6 KB of code table (L = 1800): two such blocks fit beside the tcgen05 kernel's 190 KB ring
+constexpr int RPR_WARPS = 2;        // 2 warps x ~7 KB (code table + staged row at L = 1800): two such blocks fit beside the tcgen05 kernel's 190 KB ring
 
-template <int W>
+template <int W, bool SEG>
 __global__ void __launch_bounds__(RPR_WARPS * 32)
 replay_level_row_kernel(const int *__restrict__ left, const int *__restrict__ right, const int *__restrict__ order, int lvl_begin, int lvl_count,
                         int N, int L, const uint8_t *__restrict__ msa, unsigned long long seed, unsigned long long id0, const unsigned long long *__restrict__ ids,
-                        int first_rep, int nrep, const uint8_t *__restrict__ ancbuf, uint8_t *__restrict__ shancbuf, uint8_t *__restrict__ res, int code_words)
+                        int first_rep, int nrep, const uint8_t *__restrict__ ancbuf, uint8_t *__restrict__ shancbuf, uint8_t *__restrict__ res, int code_words, int ws_log2)
 {
   extern __shared__ unsigned rpr_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  unsigned *code = rpr_smem + (size_t) warp * (5 * code_words + 32);          // [5][code_words] nibbles: bit 3 = rank drawn, bits 2:0 = target
+  const int WS = 1 << ws_log2, WSP = WS + 1;                                    // SEG: words per lane segment, padded stride (odd: no bank conflicts)
+  const int warp_words = 5 * code_words + 32 + (SEG ? 32 * WSP : 0);
+  unsigned *code = rpr_smem + (size_t) warp * warp_words;          // [5][code_words] nibbles: bit 3 = rank drawn, bits 2:0 = target
   int *nsub = reinterpret_cast<int *>(code + 5 * code_words);                  // [25]
   const long long task = (long long) blockIdx.x * RPR_WARPS + warp;
   if (task >= 2LL * lvl_count * nrep) return;                                   // whole warp
@@ -464,7 +466,55 @@ replay_level_row_kernel(const int *__restrict__ left, const int *__restrict__ ri
   }
   __syncwarp();
 
-  // ---- sweep 2
+  // ---- sweep 2, segment form (SEG): the row is staged in shared memory, every lane owns a contiguous segment of it,
+  // counts its classes (five 12-bit fields of one 64-bit word), one warp scan gives the rank at which its segment starts
+  // in every class, and the lane then walks its segment alone -- no cross-lane traffic per column.
+  if (SEG) {
+    const uint32_t *ps4 = reinterpret_cast<const uint32_t *>(par_s);
+    uint32_t *ks4 = reinterpret_cast<uint32_t *>(kid_s);
+    if (ktot == 0) {                                                            // uniform: nothing to place, plain copy (:1645)
+      for (int u = lane; u < LW; u += 32) ks4[u] = __ldcg(ps4 + u);
+      return;
+    }
+    unsigned *rowbuf = code + 5 * code_words + 32;
+    for (int u = lane; u < LW; u += 32) rowbuf[(u >> ws_log2) * WSP + (u & (WS - 1))] = __ldcg(ps4 + u);
+    __syncwarp();
+    unsigned *seg = rowbuf + lane * WSP;
+    int nw = LW - lane * WS; nw = nw < 0 ? 0 : (nw > WS ? WS : nw);
+    unsigned kmask = 0;
+    #pragma unroll
+    for (int a = 0; a < 5; a++) kmask |= (ka[a] > 0 ? 1u : 0u) << a;
+    unsigned long long cnt = 0;
+    for (int t = 0; t < nw; t++) {
+      const uint32_t w = seg[t];
+      #pragma unroll
+      for (int q = 0; q < 4; q++) { const unsigned x = (w >> (8 * q)) & 0xFFu; cnt += 1ULL << (12u * (x < 5u ? x : 5u)); }
+    }
+    unsigned long long incl = cnt;
+    #pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    unsigned long long runp = incl - cnt;                                       // ranks at which this lane's segment starts
+    for (int t = 0; t < nw; t++) {
+      const uint32_t w = seg[t];
+      uint32_t o = w;
+      #pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const unsigned x = (w >> (8 * q)) & 0xFFu, xs = 12u * (x < 5u ? x : 5u);
+        const unsigned rank = (unsigned) (runp >> xs) & 0xFFFu;
+        runp += 1ULL << xs;
+        if (x < 5u && ((kmask >> x) & 1u)) {
+          const unsigned nib = (code[x * code_words + (rank >> 3)] >> ((rank & 7u) * 4u)) & 0xFu;
+          if (nib & 8u) o = (o & ~(0xFFu << (8 * q))) | ((nib & 7u) << (8 * q));
+        }
+      }
+      seg[t] = o;
+    }
+    __syncwarp();
+    for (int u = lane; u < LW; u += 32) ks4[u] = rowbuf[(u >> ws_log2) * WSP + (u & (WS - 1))];
+    return;
+  }
+
+  // ---- sweep 2, ballot form
   int run[5] = { 0, 0, 0, 0, 0 };
   for (int u0 = 0; u0 < LW; u0 += 64) {
     uint32_t w[2];
@@ -564,14 +614,23 @@ cudaError_t rsb_launch_fitch_shuffle(const int *left, const int *right, const in
     const long long tasks = 2LL * cnt * nrep;                    // branches of this level over all replicates
     const int code_words = (L + 7) / 8;
     const size_t smem = (size_t) RPR_WARPS * (5 * code_words + 32) * sizeof(unsigned);
-    if (smem <= 200 * 1024) {                                    // row variant: one warp per branch, coalesced
+    int ws_log2 = 0; while ((32 << ws_log2) < L / 4) ws_log2++;   // words per lane segment (power of two)
+    const bool seg = (L % 4 == 0) && L <= 4092;                   // segment form of the second sweep: 12-bit class ranks
+    const size_t smem_seg = (size_t) RPR_WARPS * (5 * code_words + 32 + 32 * ((1 << ws_log2) + 1)) * sizeof(unsigned);
+    if (seg && smem_seg <= 200 * 1024) {
+      const unsigned grid = (unsigned) ((tasks + RPR_WARPS - 1) / RPR_WARPS);
+      if (smem_seg > 48 * 1024) cudaFuncSetAttribute(replay_level_row_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_seg);
+      replay_level_row_kernel<4, true><<<grid, RPR_WARPS * 32, smem_seg, st>>>(left, right, order, b, cnt, N, L, msa, seed, id0, ids, first_rep, nrep, anc, shanc, res, code_words, ws_log2);
+      continue;
+    }
+    if (smem <= 200 * 1024) {                                    // ballot form: any L
       const unsigned grid = (unsigned) ((tasks + RPR_WARPS - 1) / RPR_WARPS);
       if (L % 4 == 0) {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(replay_level_row_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-        replay_level_row_kernel<4><<<grid, RPR_WARPS * 32, smem, st>>>(left, right, order, b, cnt, N, L, msa, seed, id0, ids, first_rep, nrep, anc, shanc, res, code_words);
+        if (smem > 48 * 1024) cudaFuncSetAttribute(replay_level_row_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        replay_level_row_kernel<4, false><<<grid, RPR_WARPS * 32, smem, st>>>(left, right, order, b, cnt, N, L, msa, seed, id0, ids, first_rep, nrep, anc, shanc, res, code_words, 0);
       } else {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(replay_level_row_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-        replay_level_row_kernel<1><<<grid, RPR_WARPS * 32, smem, st>>>(left, right, order, b, cnt, N, L, msa, seed, id0, ids, first_rep, nrep, anc, shanc, res, code_words);
+        if (smem > 48 * 1024) cudaFuncSetAttribute(replay_level_row_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        replay_level_row_kernel<1, false><<<grid, RPR_WARPS * 32, smem, st>>>(left, right, order, b, cnt, N, L, msa, seed, id0, ids, first_rep, nrep, anc, shanc, res, code_words, 0);
       }
       continue;
     }
