@@ -236,7 +236,7 @@ def main():
     host_msa = torch.from_numpy(msa).pin_memory()
     dev_msa = torch.from_numpy(msa).cuda()
     cov_out = torch.empty((L, L), dtype=torch.float64).pin_memory().numpy()          # pinned: the score matrix of the input alignment lands here
-    NB = 1 << 18
+    NB = 1 << 18                                                      # bins read per step in --grid-shard mode
 
     def generate():
         """R-scape's default null model on the device: Fitch + tree-substitution shuffle (null_rscape, R-scape.c:1653-1661).
@@ -277,14 +277,19 @@ def main():
         if args.grid_shard:
             return job_grid(real)
         ctx.hist_reset()
-        w, _, _ = ctx.null_width_pool(w0_entry, STAT, pkg.C16, ACT)                   # calculate_width_histo
+        w, _, mx0 = ctx.null_width_pool(w0_entry, STAT, pkg.C16, ACT)                 # calculate_width_histo
         if n_mine:
-            ctx.null_hist_pool(blk0, n_mine, w, STAT, pkg.C16, ACT, want_minmax=False)         # run_rscape(RANSS) + null_add2cumranklist
+            ctx.null_hist_pool(blk0, n_mine, w, STAT, pkg.C16, ACT, want_minmax=False)      # run_rscape(RANSS) + null_add2cumranklist
         out = None
         if rank == real_rank:
             out = ctx.scan(real, STAT, pkg.C16, ACT, want_cov=isinstance(real, np.ndarray), cov_out=cov_out)   # run_rscape(GIVSS)
-        pkg.parallel.reduce_histogram_on_device(ctx, NB)                              # null_add2cumranklist across ranks, in place over NCCL
-        bins, n, imax = ctx.hist_read(NB)
+        # read (and sum over ranks) only the bins the scores can reach: 8 x the first null's range (cov_GrowRankList grows
+        # the reference's rank list the same way); the mass check after the timed region catches a window that was too small
+        nb = 1 << 14
+        while nb < (1 << 22) and w > 0 and nb < 8.0 * (mx0 + 10.0) / w:
+            nb <<= 1
+        pkg.parallel.reduce_histogram_on_device(ctx, nb)                              # null_add2cumranklist across ranks, in place over NCCL
+        bins, n, imax = ctx.hist_read(nb)
         return w, bins, out
 
     t_gen0 = time.perf_counter()
@@ -344,7 +349,7 @@ def main():
     # whole-job bytes per step: every rank uploads the alignment (generator), its tree and weights, and reads its histogram;
     # the rank scanning the input alignment uploads it once more and reads the score matrix
     h2d = (world + 1) * N * L + world * ((N - 1) * (3 * 4 + 2 * 8) + N * 8)
-    d2h = world * NB * 8 + L * L * 8
+    d2h = world * len(bins_chk) * 8 + L * L * 8
 
     # ---- roofline of the dominant kernel (tcgen05 gram): algorithmic ops / measured launch time -------------
     # launches during the value run: per step, gram launches = width(1) + ceil(nulls/slots) + real(1 on rank 0)
