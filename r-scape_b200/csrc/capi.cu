@@ -16,10 +16,10 @@
 // ---- kernel launchers defined in the other translation units
 cudaError_t rsb_launch_gram_i8(int S, const CUtensorMap &tmA, const CUtensorMap &tmB, const int2 *tiles, int ntiles,
                                int rep0, int nrep, int L, int Lp, int kstages, long long *cnt, double scale, double *mrow,
-                               double *mcol, int nJB, int nIB, int grid, cudaStream_t st);
+                               double *mcol, int nJB, int nIB, int small52, int grid, cudaStream_t st);
 cudaError_t rsb_launch_gram_i8_pair(int S, const CUtensorMap &tmA, const CUtensorMap &tmBh, const int2 *tiles2, int ntiles2,
                                     int rep0, int nrep, int L, int Lp, int kstages, long long *cnt, double scale, double *mrow,
-                                    double *mcol, int nJB, int nIB, int max_clusters, cudaStream_t st);
+                                    double *mcol, int nJB, int nIB, int small52, int max_clusters, cudaStream_t st);
 int rsb_gram_pair_clusters(int S);
 cudaError_t rsb_launch_quantise(const double *w, int N, int q, int umax, double vmax, uint8_t *mul, long long *V, double *err, cudaStream_t st);
 cudaError_t rsb_launch_pack(int S, const uint8_t *res, int nrep, int N, int L, long long rep_stride_res, const uint8_t *wdig,
@@ -414,10 +414,10 @@ int enqueue_gram(rsb_ctx *ctx, int which, int s0, int nrep, cudaStream_t st)
     if (which == 0 && ((size_t) g.nJB * ctx->L * 4 > ctx->mrow_stride)) { rsb_set_error(ctx, "internal: marginal partial capacity"); return 1; }
     if (g.pair_clusters > 0)
       RSB_CUDA_OK(rsb_launch_gram_i8_pair(g.S, ctx->tmA, g.tmBh, g.d_tiles2, g.ntiles2, s0, nrep, ctx->L, ctx->Lp, ctx->Kpad / RSB_KSTAGE,
-                                          ctx->d_cnt, g.scale, mrow, mcol, g.nJB, ctx->nIB, g.pair_clusters, st));
+                                          ctx->d_cnt, g.scale, mrow, mcol, g.nJB, ctx->nIB, ((unsigned long long) g.wtot >> 52) == 0, g.pair_clusters, st));
     else
       RSB_CUDA_OK(rsb_launch_gram_i8(g.S, ctx->tmA, g.tmB, g.d_tiles, g.ntiles, s0, nrep, ctx->L, ctx->Lp, ctx->Kpad / RSB_KSTAGE,
-                                     ctx->d_cnt, g.scale, mrow, mcol, g.nJB, ctx->nIB, grid, st));
+                                     ctx->d_cnt, g.scale, mrow, mcol, g.nJB, ctx->nIB, ((unsigned long long) g.wtot >> 52) == 0, grid, st));
     if (ctx->profile) { cudaEventRecord(e1, st); ctx->pending.push_back({ e0, e1 }); }
     ctx->launches++;
     ctx->gram_launches++;
@@ -1340,7 +1340,8 @@ static int fitch_shuffle_impl(rsb_ctx *ctx, const uint8_t *msa, int64_t row_stri
   }
   RSB_CUDA_OK(rsb_launch_permutations(L, seed, first_id, d_ids, first_rep, nrep, ctx->d_perm, sg));
   // chunk sizes 1, 4, 8, 16, 32, then the rest; a small batch (every level kernel is latency-bound then) goes in one piece
-  int off = 0, chunks = 0, next = 4;
+  static const int chunk0 = getenv("RSCAPE_B200_GEN_CHUNK") ? std::max(1, atoi(getenv("RSCAPE_B200_GEN_CHUNK"))) : 4;   // experiments
+  int off = 0, chunks = 0, next = chunk0;
   while (off < nrep) {
     int n = (off == 0) ? 1 : next;
     if (off > 0) next *= 2;

@@ -83,7 +83,7 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
 template <int S>
 __device__ __forceinline__ double gram_epilogue_tile(uint32_t trow, int jb, int i, int a, int lane, int ew, int ib, int r, int L, int Lp,
                                                      long long *__restrict__ base, size_t plane, double scale, bool part,
-                                                     double *__restrict__ mcol, int nIB)
+                                                     double *__restrict__ mcol, int nIB, bool small52)
 {
   constexpr int CJ = rsb_cj_for(S);
   (void) Lp;
@@ -131,7 +131,7 @@ __device__ __forceinline__ double gram_epilogue_tile(uint32_t trow, int jb, int 
       #pragma unroll
       for (int u = 0; u < 2; u++) {
         #pragma unroll
-        for (int b = 0; b < 4; b++) x[u][b] = fma(u64_to_f64(c[u][b]), scale, 1e-10);
+        for (int b = 0; b < 4; b++) x[u][b] = fma(small52 ? u52_to_f64(c[u][b]) : u64_to_f64(c[u][b]), scale, 1e-10);
         const double rs = (x[u][0] + x[u][1]) + (x[u][2] + x[u][3]);
         double sum = rs;
         sum += __shfl_xor_sync(0xffffffffu, sum, 1);
@@ -179,7 +179,7 @@ template <int S>
 __global__ void __launch_bounds__(GRAM_THREADS, 1)
 gram_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
                const int2 *__restrict__ tiles, int ntiles, int rep0, int nrep, int L, int Lp, int kstages,
-               long long *__restrict__ cnt, double scale, double *__restrict__ mrow, double *__restrict__ mcol, int nJB, int nIB)
+               long long *__restrict__ cnt, double scale, double *__restrict__ mrow, double *__restrict__ mcol, int nJB, int nIB, int small52)
 {
   constexpr int      CJ          = rsb_cj_for(S);
   constexpr int      NT          = 4 * S * CJ;                 // UMMA N
@@ -280,7 +280,7 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t) (ew * 32) << 16) + (uint32_t) acc * 256u;
 
-      const double racc = gram_epilogue_tile<S>(trow, t.y, i, a, lane, ew, t.x, r, L, Lp, base, plane, scale, mrow != nullptr, mcol, nIB);
+      const double racc = gram_epilogue_tile<S>(trow, t.y, i, a, lane, ew, t.x, r, L, Lp, base, plane, scale, mrow != nullptr, mcol, nIB, small52 != 0);
       if (mrow != nullptr && i < L) mrow[(((size_t) r * nJB + t.y) * L + i) * 4 + a] = racc;
       tc_fence_before();
       mbar_arrive(tempty_bar(acc));
@@ -339,7 +339,7 @@ template <int S>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GRAM_THREADS, 1)
 gram_i8_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapBh,
                     const int2 *__restrict__ tiles, int ntiles, int rep0, int nrep, int L, int Lp, int kstages,
-                    long long *__restrict__ cnt, double scale, double *__restrict__ mrow, double *__restrict__ mcol, int nJB, int nIB)
+                    long long *__restrict__ cnt, double scale, double *__restrict__ mrow, double *__restrict__ mcol, int nJB, int nIB, int small52)
 {
   constexpr int      CJ          = rsb_cj_for(S);
   constexpr int      NT          = 4 * S * CJ;                 // UMMA N (whole planeB tile; each CTA stages NT / 2 rows)
@@ -444,7 +444,7 @@ gram_i8_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t) (ew * 32) << 16) + (uint32_t) acc * 256u;
-      const double racc = gram_epilogue_tile<S>(trow, t.y, i, a, lane, ew, ib, r, L, Lp, base, plane, scale, part, mcol, nIB);
+      const double racc = gram_epilogue_tile<S>(trow, t.y, i, a, lane, ew, ib, r, L, Lp, base, plane, scale, part, mcol, nIB, small52 != 0);
       if (part && i < L) mrow[(((size_t) r * nJB + t.y) * L + i) * 4 + a] = racc;
       tc_fence_before();
       mbar_arrive_leader(tempty_bar(acc));
@@ -472,7 +472,7 @@ template <int S> constexpr size_t gram_smem_bytes() {
 template <int S>
 cudaError_t launch_gram(const CUtensorMap &tmA, const CUtensorMap &tmB, const int2 *tiles, int ntiles, int rep0, int nrep,
                         int L, int Lp, int kstages, long long *cnt, double scale, double *mrow, double *mcol, int nJB, int nIB,
-                        int grid, cudaStream_t st)
+                        int small52, int grid, cudaStream_t st)
 {
   constexpr size_t smem = gram_smem_bytes<S>();
   cudaError_t e = cudaFuncSetAttribute(gram_i8_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
@@ -480,14 +480,14 @@ cudaError_t launch_gram(const CUtensorMap &tmA, const CUtensorMap &tmB, const in
   // the ring takes ~190 KB; with the SM's carve-out at its maximum (228 KB) the rest is left for the blocks of the
   // statistics chain, which run beside this kernel (a 196 KB carve-out would leave them no shared memory at all)
   rsb_coreside(gram_i8_kernel<S>);
-  gram_i8_kernel<S><<<grid, GRAM_THREADS, smem, st>>>(tmA, tmB, tiles, ntiles, rep0, nrep, L, Lp, kstages, cnt, scale, mrow, mcol, nJB, nIB);
+  gram_i8_kernel<S><<<grid, GRAM_THREADS, smem, st>>>(tmA, tmB, tiles, ntiles, rep0, nrep, L, Lp, kstages, cnt, scale, mrow, mcol, nJB, nIB, small52);
   return cudaGetLastError();
 }
 
 template <int S>
 cudaError_t launch_gram_pair(const CUtensorMap &tmA, const CUtensorMap &tmBh, const int2 *tiles2, int ntiles2, int rep0, int nrep,
                              int L, int Lp, int kstages, long long *cnt, double scale, double *mrow, double *mcol, int nJB, int nIB,
-                             int max_clusters, cudaStream_t st)
+                             int small52, int max_clusters, cudaStream_t st)
 {
   constexpr size_t smem = gram_pair_smem_bytes<S>();
   cudaError_t e = cudaFuncSetAttribute(gram_i8_pair_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
@@ -496,7 +496,7 @@ cudaError_t launch_gram_pair(const CUtensorMap &tmA, const CUtensorMap &tmBh, co
   const long long work = (long long) ntiles2 * nrep;
   const int nclusters = (int) (work < max_clusters ? work : max_clusters);
   gram_i8_pair_kernel<S><<<2 * nclusters, GRAM_THREADS, smem, st>>>(tmA, tmBh, tiles2, ntiles2, rep0, nrep, L, Lp, kstages, cnt, scale,
-                                                                      mrow, mcol, nJB, nIB);
+                                                                      mrow, mcol, nJB, nIB, small52);
   return cudaGetLastError();
 }
 
@@ -522,15 +522,15 @@ int pair_clusters()
 // and boxes {128, 128, 1} / {128, 4*S*CJ, 1}.
 cudaError_t rsb_launch_gram_i8(int S, const CUtensorMap &tmA, const CUtensorMap &tmB, const int2 *tiles, int ntiles,
                                int rep0, int nrep, int L, int Lp, int kstages, long long *cnt, double scale, double *mrow,
-                               double *mcol, int nJB, int nIB, int grid, cudaStream_t st)
+                               double *mcol, int nJB, int nIB, int small52, int grid, cudaStream_t st)
 {
   switch (S) {
-  case 1: return launch_gram<1>(tmA, tmB, tiles, ntiles, rep0, nrep, L, Lp, kstages, cnt, scale, mrow, mcol, nJB, nIB, grid, st);
-  case 2: return launch_gram<2>(tmA, tmB, tiles, ntiles, rep0, nrep, L, Lp, kstages, cnt, scale, mrow, mcol, nJB, nIB, grid, st);
-  case 3: return launch_gram<3>(tmA, tmB, tiles, ntiles, rep0, nrep, L, Lp, kstages, cnt, scale, mrow, mcol, nJB, nIB, grid, st);
-  case 4: return launch_gram<4>(tmA, tmB, tiles, ntiles, rep0, nrep, L, Lp, kstages, cnt, scale, mrow, mcol, nJB, nIB, grid, st);
-  case 5: return launch_gram<5>(tmA, tmB, tiles, ntiles, rep0, nrep, L, Lp, kstages, cnt, scale, mrow, mcol, nJB, nIB, grid, st);
-  case 6: return launch_gram<6>(tmA, tmB, tiles, ntiles, rep0, nrep, L, Lp, kstages, cnt, scale, mrow, mcol, nJB, nIB, grid, st);
+  case 1: return launch_gram<1>(tmA, tmB, tiles, ntiles, rep0, nrep, L, Lp, kstages, cnt, scale, mrow, mcol, nJB, nIB, small52, grid, st);
+  case 2: return launch_gram<2>(tmA, tmB, tiles, ntiles, rep0, nrep, L, Lp, kstages, cnt, scale, mrow, mcol, nJB, nIB, small52, grid, st);
+  case 3: return launch_gram<3>(tmA, tmB, tiles, ntiles, rep0, nrep, L, Lp, kstages, cnt, scale, mrow, mcol, nJB, nIB, small52, grid, st);
+  case 4: return launch_gram<4>(tmA, tmB, tiles, ntiles, rep0, nrep, L, Lp, kstages, cnt, scale, mrow, mcol, nJB, nIB, small52, grid, st);
+  case 5: return launch_gram<5>(tmA, tmB, tiles, ntiles, rep0, nrep, L, Lp, kstages, cnt, scale, mrow, mcol, nJB, nIB, small52, grid, st);
+  case 6: return launch_gram<6>(tmA, tmB, tiles, ntiles, rep0, nrep, L, Lp, kstages, cnt, scale, mrow, mcol, nJB, nIB, small52, grid, st);
   }
   return cudaErrorInvalidValue;
 }
@@ -538,15 +538,15 @@ cudaError_t rsb_launch_gram_i8(int S, const CUtensorMap &tmA, const CUtensorMap 
 // CTA-pair variant: tmBh has boxes {128, 2*S*CJ, 1} (half a planeB tile), tiles2 lists (ibp, jb) = row-block pairs.
 cudaError_t rsb_launch_gram_i8_pair(int S, const CUtensorMap &tmA, const CUtensorMap &tmBh, const int2 *tiles2, int ntiles2,
                                     int rep0, int nrep, int L, int Lp, int kstages, long long *cnt, double scale, double *mrow,
-                                    double *mcol, int nJB, int nIB, int max_clusters, cudaStream_t st)
+                                    double *mcol, int nJB, int nIB, int small52, int max_clusters, cudaStream_t st)
 {
   switch (S) {
-  case 1: return launch_gram_pair<1>(tmA, tmBh, tiles2, ntiles2, rep0, nrep, L, Lp, kstages, cnt, scale, mrow, mcol, nJB, nIB, max_clusters, st);
-  case 2: return launch_gram_pair<2>(tmA, tmBh, tiles2, ntiles2, rep0, nrep, L, Lp, kstages, cnt, scale, mrow, mcol, nJB, nIB, max_clusters, st);
-  case 3: return launch_gram_pair<3>(tmA, tmBh, tiles2, ntiles2, rep0, nrep, L, Lp, kstages, cnt, scale, mrow, mcol, nJB, nIB, max_clusters, st);
-  case 4: return launch_gram_pair<4>(tmA, tmBh, tiles2, ntiles2, rep0, nrep, L, Lp, kstages, cnt, scale, mrow, mcol, nJB, nIB, max_clusters, st);
-  case 5: return launch_gram_pair<5>(tmA, tmBh, tiles2, ntiles2, rep0, nrep, L, Lp, kstages, cnt, scale, mrow, mcol, nJB, nIB, max_clusters, st);
-  case 6: return launch_gram_pair<6>(tmA, tmBh, tiles2, ntiles2, rep0, nrep, L, Lp, kstages, cnt, scale, mrow, mcol, nJB, nIB, max_clusters, st);
+  case 1: return launch_gram_pair<1>(tmA, tmBh, tiles2, ntiles2, rep0, nrep, L, Lp, kstages, cnt, scale, mrow, mcol, nJB, nIB, small52, max_clusters, st);
+  case 2: return launch_gram_pair<2>(tmA, tmBh, tiles2, ntiles2, rep0, nrep, L, Lp, kstages, cnt, scale, mrow, mcol, nJB, nIB, small52, max_clusters, st);
+  case 3: return launch_gram_pair<3>(tmA, tmBh, tiles2, ntiles2, rep0, nrep, L, Lp, kstages, cnt, scale, mrow, mcol, nJB, nIB, small52, max_clusters, st);
+  case 4: return launch_gram_pair<4>(tmA, tmBh, tiles2, ntiles2, rep0, nrep, L, Lp, kstages, cnt, scale, mrow, mcol, nJB, nIB, small52, max_clusters, st);
+  case 5: return launch_gram_pair<5>(tmA, tmBh, tiles2, ntiles2, rep0, nrep, L, Lp, kstages, cnt, scale, mrow, mcol, nJB, nIB, small52, max_clusters, st);
+  case 6: return launch_gram_pair<6>(tmA, tmBh, tiles2, ntiles2, rep0, nrep, L, Lp, kstages, cnt, scale, mrow, mcol, nJB, nIB, small52, max_clusters, st);
   default: return cudaErrorInvalidValue;
   }
 }

@@ -60,6 +60,12 @@ __device__ __forceinline__ double u64_to_f64(unsigned long long v)
   return hi + lo;
 }
 
+// counts below 2^52 (true of every count when the alignment's total weight wtot < 2^52) convert with one subtraction
+__device__ __forceinline__ double u52_to_f64(unsigned long long v)
+{
+  return __longlong_as_double(0x4330000000000000ULL | v) - 4503599627370496.0;
+}
+
 // does the gram tile (ib, jb) exist?  Same rule as build_geo (capi.cu): it holds some pair i < j and its row block is
 // owned by this rank
 __host__ __device__ __forceinline__ bool rsb_tile_exists(int ib, int jb, int CJ, int L, int sr, int sw)

@@ -26,12 +26,6 @@ constexpr int ST_TJ = RSB_TJ;
 
 struct PairProbs { double pp[16]; double ne; double ng; };
 
-// counts below 2^52 (the whole alignment's weight is: wtot < 2^52, checked by the caller) convert with one subtraction
-__device__ __forceinline__ double u52_to_f64(unsigned long long v)
-{
-  return __longlong_as_double(0x4330000000000000ULL | v) - 4503599627370496.0;
-}
-
 // fixed-point counts of one pair -> nseff, ngap, pp (prior 1e-10 per cell).
 // EXACT_DIV (values handed back to the host): Kahan-summed normaliser and a division per cell, as esl_vec_DNorm does
 // (SURVEY 9.7).  Otherwise (statistic kernels, FP64-issue bound): pairwise-tree normaliser and a multiplication by the
