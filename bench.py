@@ -248,6 +248,7 @@ def main():
             ctx.null_fitch_shuffle(host_msa.numpy(), SEED, n_mine + 1, first_rep=0, ids=[0] + list(my_ids))
 
     STAT, ACT = getattr(pkg, args.stat), getattr(pkg, args.actype)
+    PHASES = bool(os.environ.get("BENCH_PHASES"))                    # host-side phase times of every job on stderr
     if args.grid_shard and (args.stat != "GT" or args.actype != "APC"):
         raise SystemExit("--grid-shard runs the headline statistic (GT, APC) only")
 
@@ -276,20 +277,28 @@ def main():
         """null_rscape + run_rscape for this rank's share of the work, nulls already in the device pool."""
         if args.grid_shard:
             return job_grid(real)
+        tp = [time.perf_counter()] if PHASES else None
         ctx.hist_reset()
         w, _, mx0 = ctx.null_width_pool(w0_entry, STAT, pkg.C16, ACT)                 # calculate_width_histo
+        if PHASES: tp.append(time.perf_counter())
         if n_mine:
             ctx.null_hist_pool(blk0, n_mine, w, STAT, pkg.C16, ACT, want_minmax=False)      # run_rscape(RANSS) + null_add2cumranklist
+        if PHASES: tp.append(time.perf_counter())
         out = None
         if rank == real_rank:
             out = ctx.scan(real, STAT, pkg.C16, ACT, want_cov=isinstance(real, np.ndarray), cov_out=cov_out)   # run_rscape(GIVSS)
-        # read (and sum over ranks) only the bins the scores can reach: 8 x the first null's range (cov_GrowRankList grows
+        if PHASES: tp.append(time.perf_counter())
+        # read (and sum over ranks) only the bins the scores can reach: 2 x the first null's range (cov_GrowRankList grows
         # the reference's rank list the same way); the mass check after the timed region catches a window that was too small
         nb = 1 << 14
-        while nb < (1 << 22) and w > 0 and nb < 8.0 * (mx0 + 10.0) / w:
+        while nb < (1 << 22) and w > 0 and nb < 2.0 * (mx0 + 10.0) / w:
             nb <<= 1
         pkg.parallel.reduce_histogram_on_device(ctx, nb)                              # null_add2cumranklist across ranks, in place over NCCL
         bins, n, imax = ctx.hist_read(nb)
+        if PHASES:
+            tp.append(time.perf_counter())
+            print("[bench] rank %d phases ms: width %.2f nulls %.2f input %.2f read %.2f" % ((rank,) + tuple((b - a) * 1e3 for a, b in zip(tp, tp[1:]))),
+                  file=sys.stderr, flush=True)
         return w, bins, out
 
     t_gen0 = time.perf_counter()

@@ -270,7 +270,7 @@ class Context:
         self._ck(lib().rsb_hist_reset(self._h))
 
     def hist_read(self, nb):
-        bins = np.zeros(nb, dtype=np.uint64)
+        bins = np.empty(nb, dtype=np.uint64)            # fully overwritten by the copy
         n, imax = C.c_uint64(), C.c_int()
         self._ck(lib().rsb_hist_read(self._h, bins.ctypes.data_as(_u64p), nb, C.byref(n), C.byref(imax)))
         return bins, n.value, imax.value
