@@ -236,7 +236,7 @@ def main():
     host_msa = torch.from_numpy(msa).pin_memory()
     dev_msa = torch.from_numpy(msa).cuda()
     cov_out = torch.empty((L, L), dtype=torch.float64).pin_memory().numpy()          # pinned: the score matrix of the input alignment lands here
-    NB = 1 << 18                                                      # bins read per step in --grid-shard mode
+    bins_pinned = torch.empty(1 << 22, dtype=torch.int64).pin_memory().numpy().view(np.uint64)   # the histogram lands here
 
     def generate():
         """R-scape's default null model on the device: Fitch + tree-substitution shuffle (null_rscape, R-scape.c:1653-1661).
@@ -269,8 +269,11 @@ def main():
         for k in range(n_mine):
             sharded_scan(k, hist_w=w)
         cov, _, _ = sharded_scan(real, want_cov=isinstance(real, np.ndarray))
-        bins, n, imax = ctx.hist_read(NB)
-        bins = pkg.parallel.reduce_histogram(bins, device="cuda")
+        nb = 1 << 14
+        while nb < (1 << 22) and w > 0 and nb < 2.0 * (hi + 10.0) / w:
+            nb <<= 1
+        pkg.parallel.reduce_histogram_on_device(ctx, nb)
+        bins, n, imax = ctx.hist_read(nb, out=bins_pinned)
         return w, bins, dict(cov=cov)
 
     def job(real):
@@ -294,7 +297,7 @@ def main():
         while nb < (1 << 22) and w > 0 and nb < 2.0 * (mx0 + 10.0) / w:
             nb <<= 1
         pkg.parallel.reduce_histogram_on_device(ctx, nb)                              # null_add2cumranklist across ranks, in place over NCCL
-        bins, n, imax = ctx.hist_read(nb)
+        bins, n, imax = ctx.hist_read(nb, out=bins_pinned)
         if PHASES:
             tp.append(time.perf_counter())
             print("[bench] rank %d phases ms: width %.2f nulls %.2f input %.2f read %.2f" % ((rank,) + tuple((b - a) * 1e3 for a, b in zip(tp, tp[1:]))),

@@ -269,8 +269,11 @@ class Context:
     def hist_reset(self):
         self._ck(lib().rsb_hist_reset(self._h))
 
-    def hist_read(self, nb):
-        bins = np.empty(nb, dtype=np.uint64)            # fully overwritten by the copy
+    def hist_read(self, nb, out=None):
+        """First nb bins of the cumulative histogram -> (bins, n, imax).  out: optional uint64 array of at least nb elements
+        to receive them (e.g. a view of pinned memory)."""
+        bins = np.empty(nb, dtype=np.uint64) if out is None else out[:nb]           # fully overwritten by the copy
+        assert bins.dtype == np.uint64 and bins.flags.c_contiguous and len(bins) == nb
         n, imax = C.c_uint64(), C.c_int()
         self._ck(lib().rsb_hist_read(self._h, bins.ctypes.data_as(_u64p), nb, C.byref(n), C.byref(imax)))
         return bins, n.value, imax.value
