@@ -52,8 +52,8 @@ cudaError_t rsb_launch_symmetrize(double *cov, int L, int Lp, cudaStream_t st);
 cudaError_t rsb_launch_hist3(const double *cov, int L, int Lp, const uint8_t *pairmask, double bmin, double w, int nb,
                              unsigned long long *ha, unsigned long long *hb, unsigned long long *ht, int *flags, cudaStream_t st);
 cudaError_t rsb_launch_null_simulate(const int *left, const int *right, const int *order, const int *level_start_host, int nlevels,
-                                     const double *pcdf, int N, int L, const uint8_t *root,
-                                     const uint8_t *gapmask, long long gap_stride, unsigned long long seed, unsigned long long id0, int first_rep, int nrep,
+                                     const unsigned long long *pthr, int N, int L, const uint8_t *root,
+                                     const uint8_t *gapmask, unsigned long long seed, unsigned long long id0, int first_rep, int nrep,
                                      uint8_t *res, uint8_t *scratch, cudaStream_t st);
 cudaError_t rsb_launch_fitch_shuffle(const int *left, const int *right, const int *parent, const int *order, const int *level_start,
                                      int nlevels, int N, int L, const uint8_t *msa, unsigned long long seed, unsigned long long id0,
@@ -127,6 +127,8 @@ struct rsb_ctx {
   std::vector<int> h_level_start;
   uint8_t *d_root = nullptr, *d_gapmask = nullptr, *d_simscratch = nullptr, *d_msa0 = nullptr, *d_anc = nullptr, *d_shanc = nullptr, *d_sets = nullptr;
   int *d_genflag = nullptr;
+  unsigned long long *d_pthr = nullptr;                   // generator B: branch matrices as cumulative thresholds
+  double sim_Q[16] = { 0 }; bool sim_valid = false;       // ... valid for this rate matrix and the current tree
   unsigned long long *d_ids = nullptr; size_t ids_cap = 0;    // explicit replicate ids of a generator call
   bool have_tree = false;
   uint8_t *d_pool = nullptr;          // device-resident null alignments [Rpool][N][L] (output of the generators)
@@ -200,7 +202,7 @@ void free_plan(rsb_ctx *c)
   dfree(c->d_meanp); dfree(c->d_w); dfree(c->d_blocksum); dfree(c->d_msum); dfree(c->d_covsum); dfree(c->d_hist); dfree(c->d_colsum); dfree(c->d_flags); dfree(c->d_ps); dfree(c->d_pp_out);
   dfree(c->d_nseff_out); dfree(c->d_ngap_out); dfree(c->d_left); dfree(c->d_right); dfree(c->d_parent); dfree(c->d_order);
   dfree(c->d_level_start); dfree(c->d_perm); dfree(c->d_pcdf); dfree(c->d_root); dfree(c->d_gapmask); dfree(c->d_simscratch);
-  dfree(c->d_msa0); dfree(c->d_anc); dfree(c->d_shanc); dfree(c->d_pool); dfree(c->d_sets); dfree(c->d_genflag); dfree(c->d_ids); c->ids_cap = 0;
+  dfree(c->d_msa0); dfree(c->d_anc); dfree(c->d_shanc); dfree(c->d_pool); dfree(c->d_sets); dfree(c->d_genflag); dfree(c->d_ids); c->ids_cap = 0; dfree(c->d_pthr); c->sim_valid = false;
   c->Rpool = 0;
   c->have_tree = false;
 }
@@ -1191,6 +1193,7 @@ int rsb_last_nseff(rsb_ctx *ctx, double *nseff, double *ngap)
 int rsb_set_tree(rsb_ctx *ctx, const int *left, const int *right, const int *parent, const double *ld, const double *rd)
 {
   RSB_CUDA_OK(cudaSetDevice(ctx->device));
+  RSB_CUDA_OK(cudaStreamSynchronize(ctx->stream_gen));        // a generator may still be walking the previous tree
   const int N = ctx->N, nn = N - 1;
   if (N < 2) { rsb_set_error(ctx, "a tree needs at least 2 leaves"); return 1; }
   for (int v = 0; v < nn; v++) {
@@ -1223,6 +1226,7 @@ int rsb_set_tree(rsb_ctx *ctx, const int *left, const int *right, const int *par
   RSB_CUDA_OK(cudaMemcpyAsync(ctx->d_order, order.data(), sizeof(int) * nn, cudaMemcpyHostToDevice, ctx->stream));
   RSB_CUDA_OK(cudaMemcpyAsync(ctx->d_level_start, level_start.data(), sizeof(int) * (maxd + 2), cudaMemcpyHostToDevice, ctx->stream));
   RSB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  ctx->sim_valid = false;                     // branch matrices depend on the branch lengths
   ctx->have_tree = true;
   return 0;
 }
@@ -1281,29 +1285,54 @@ int rsb_null_simulate(rsb_ctx *ctx, const double *Q, const uint8_t *root, const 
   if (!ctx->have_tree) { rsb_set_error(ctx, "rsb_set_tree first"); return 1; }
   if (pool_range_ok(ctx, first_rep, nrep)) return 1;
   const int N = ctx->N, L = ctx->L, nn = N - 1;
-  // cumulative branch matrices [node][side][4][4]: row a holds the CDF over child residues
-  std::vector<double> pb((size_t) nn * 2 * 16);
-  for (int v = 0; v < nn; v++)
-    for (int side = 0; side < 2; side++) {
-      double P[16];
-      if (branch_matrix(Q, side ? ctx->h_rd[v] : ctx->h_ld[v], P)) { rsb_set_error(ctx, "failed to evolve node %d to time %f", v, side ? ctx->h_rd[v] : ctx->h_ld[v]); return 1; }
-      for (int a = 0; a < 4; a++) { double cdf = 0.0; for (int b = 0; b < 4; b++) { cdf += P[a * 4 + b]; pb[((size_t) v * 2 + side) * 16 + a * 4 + b] = cdf; } }
-    }
-  if (!ctx->d_pcdf) RSB_CUDA_OK(cudaMalloc(&ctx->d_pcdf, pb.size() * sizeof(double)));
+  cudaStream_t sg = ctx->stream_gen;                     // generation stream, as generator A: after everything queued by the caller
+  RSB_CUDA_OK(cudaEventRecord(ctx->ev_entry, ctx->stream));
+  RSB_CUDA_OK(cudaStreamWaitEvent(sg, ctx->ev_entry, 0));
+  // branch matrices P(t) = exp(tQ) (ratematrix_ConditionalsFromRate, src/ratematrix.c:185-233) as cumulative integer
+  // thresholds [node][side][4][4]; rebuilt only when the rate matrix or the tree changed
+  if (!ctx->sim_valid || memcmp(ctx->sim_Q, Q, sizeof(ctx->sim_Q)) != 0) {
+    std::vector<unsigned long long> th((size_t) nn * 32);
+    for (int v = 0; v < nn; v++)
+      for (int side = 0; side < 2; side++) {
+        double P[16];
+        if (branch_matrix(Q, side ? ctx->h_rd[v] : ctx->h_ld[v], P)) { rsb_set_error(ctx, "failed to evolve node %d to time %f", v, side ? ctx->h_rd[v] : ctx->h_ld[v]); return 1; }
+        for (int a = 0; a < 4; a++) {
+          double cdf = 0.0;
+          for (int b = 0; b < 4; b++) {
+            cdf += P[a * 4 + b];
+            const double y = std::ceil(std::ldexp(cdf, 32));                             // rnd / 2^32 < cdf  <=>  rnd < ceil(cdf 2^32)
+            th[((size_t) v * 2 + side) * 16 + a * 4 + b] = (y <= 0.0) ? 0ULL : (y >= 4294967296.0) ? 4294967296ULL : (unsigned long long) y;
+          }
+        }
+      }
+    if (!ctx->d_pthr) RSB_CUDA_OK(cudaMalloc(&ctx->d_pthr, th.size() * sizeof(unsigned long long)));
+    RSB_CUDA_OK(cudaMemcpyAsync(ctx->d_pthr, th.data(), th.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, sg));
+    RSB_CUDA_OK(cudaStreamSynchronize(sg));                // th is a host temporary
+    memcpy(ctx->sim_Q, Q, sizeof(ctx->sim_Q));
+    ctx->sim_valid = true;
+  }
   if (!ctx->d_root) RSB_CUDA_OK(cudaMalloc(&ctx->d_root, L));
   if (!ctx->d_simscratch) RSB_CUDA_OK(cudaMalloc(&ctx->d_simscratch, (size_t) ctx->Rpool * nn * L));
-  RSB_CUDA_OK(cudaMemcpyAsync(ctx->d_pcdf, pb.data(), pb.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  RSB_CUDA_OK(cudaMemcpyAsync(ctx->d_root, root, L, cudaMemcpyHostToDevice, ctx->stream));
+  RSB_CUDA_OK(cudaMemcpyAsync(ctx->d_root, root, L, cudaMemcpyHostToDevice, sg));
   if (gapmask) {
     if (!ctx->d_gapmask) RSB_CUDA_OK(cudaMalloc(&ctx->d_gapmask, (size_t) N * L));
-    RSB_CUDA_OK(cudaMemcpy2DAsync(ctx->d_gapmask, L, gapmask, (size_t) gap_stride, L, N, cudaMemcpyHostToDevice, ctx->stream));
+    RSB_CUDA_OK(cudaMemcpy2DAsync(ctx->d_gapmask, L, gapmask, (size_t) gap_stride, L, N, cudaMemcpyHostToDevice, sg));
   }
-  RSB_CUDA_OK(cudaStreamSynchronize(ctx->stream));       // pb is a host temporary
-  RSB_CUDA_OK(cudaStreamSynchronize(ctx->stream_gen));   // (this generator runs on the main stream)
-  for (int r = first_rep; r < first_rep + nrep; r++) ctx->pool_ready[r] = nullptr;
-  RSB_CUDA_OK(rsb_launch_null_simulate(ctx->d_left, ctx->d_right, ctx->d_order, ctx->h_level_start.data(), ctx->nlevels, ctx->d_pcdf, N, L, ctx->d_root, gapmask ? ctx->d_gapmask : nullptr, L,
-                                       seed, first_id, first_rep, nrep, ctx->d_pool, ctx->d_simscratch, ctx->stream));
-  ctx->launches += ctx->nlevels;
+  // chunks of growing size with a readiness event each, as generator A
+  int off = 0, chunks = 0, next = 4;
+  while (off < nrep) {
+    int n = (off == 0) ? 1 : next;
+    if (off > 0) next *= 2;
+    if (nrep <= 16 || chunks >= 5 || nrep - off - n < 4) n = nrep - off;
+    RSB_CUDA_OK(rsb_launch_null_simulate(ctx->d_left, ctx->d_right, ctx->d_order, ctx->h_level_start.data(), ctx->nlevels, ctx->d_pthr, N, L, ctx->d_root,
+                                         gapmask ? ctx->d_gapmask : nullptr, seed, first_id + (uint64_t) off, first_rep + off, n, ctx->d_pool,
+                                         ctx->d_simscratch, sg));
+    cudaEvent_t e = ctx->gen_ring[ctx->gen_next++ % ctx->gen_ring.size()];
+    RSB_CUDA_OK(cudaEventRecord(e, sg));
+    for (int r = first_rep + off; r < first_rep + off + n; r++) ctx->pool_ready[r] = e;
+    off += n; chunks++;
+  }
+  ctx->launches += chunks * ctx->nlevels;
   return 0;
 }
 

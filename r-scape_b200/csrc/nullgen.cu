@@ -44,39 +44,65 @@ struct Philox {
   }
 };
 
-__device__ __forceinline__ double u01(uint32_t x) { return (double) x * (1.0 / 4294967296.0); }   // as esl_random: x / 2^32
 
 // ------------------------------------------------------------------------------------------------ generator B
-// One launch per tree level (nodes of a level are independent given their parents); a thread owns one
-// (replicate, node, column) and emits both children of the node.  grid = (columns/128, nodes of the level, replicates).
-__global__ void null_simulate_level_kernel(const int *__restrict__ left, const int *__restrict__ right, const int *__restrict__ order,
-                                           int lvl_begin, const double *__restrict__ pcdf, int N, int L, const uint8_t *__restrict__ root,
-                                           const uint8_t *__restrict__ gapmask, unsigned long long seed, unsigned long long id0,
-                                           int first_rep, uint8_t *__restrict__ res, uint8_t *__restrict__ scratch)
+// One launch per tree level (nodes of a level are independent given their parents); a thread owns W columns (W = 4: rows
+// moved as 32-bit words, L % 4 == 0; W = 1 otherwise) of one (replicate, node) and emits both children of the node.
+// grid = (columns/(128 W), nodes of the level, replicates).  One Philox block serves two columns (4 draws: 2 children x 2
+// columns; block (node, column >> 1), element 2 (column & 1) + side).  The branch's cumulative matrices arrive as integer
+// thresholds thr = ceil(cdf 2^32): "first k with cdf_k > x", x = rnd / 2^32 (cov_addres, :757-773) is exactly
+// "first k with rnd < thr_k", with no floating point in the kernel.
+template <int W>
+__global__ void __launch_bounds__(128)
+null_simulate_level_kernel(const int *__restrict__ left, const int *__restrict__ right, const int *__restrict__ order,
+                           int lvl_begin, const unsigned long long *__restrict__ pthr, int N, int L, const uint8_t *__restrict__ root,
+                           const uint8_t *__restrict__ gapmask, unsigned long long seed, unsigned long long id0,
+                           int first_rep, uint8_t *__restrict__ res, uint8_t *__restrict__ scratch)
 {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ unsigned long long thr[32];                         // [side][parent residue][k]
+  const int c0 = (blockIdx.x * blockDim.x + threadIdx.x) * W;
   const int v = order[lvl_begin + blockIdx.y];
   const int r = first_rep + blockIdx.z;
   const uint32_t rid = (uint32_t) (id0 + blockIdx.z);            // global replicate id: the stream does not depend on where the replicate is stored
-  if (c >= L) return;
+  if (threadIdx.x < 32) thr[threadIdx.x] = pthr[(size_t) v * 32 + threadIdx.x];
+  __syncthreads();
+  if (c0 >= L) return;
   Philox rng; rng.key[0] = (uint32_t) seed ^ (0x9E3779B9u * (rid + 1u)); rng.key[1] = (uint32_t) (seed >> 32) + rid;
   uint8_t *anc  = scratch + (size_t) r * (N - 1) * L;        // internal node states [N-1][L]
   uint8_t *leaf = res + (size_t) r * N * L;
-  const int par = (v == 0 ? root[c] : anc[(size_t) v * L + c]) & 3;       // cov_add_root for the root
+  const uint8_t *prow = (v == 0) ? root : anc + (size_t) v * L;             // cov_add_root for the root
+  const uint32_t pw = (W == 4) ? *reinterpret_cast<const uint32_t *>(prow + c0) : (uint32_t) prow[c0];
+  const int kl = left[v], kr = right[v];
+  uint32_t ol = 0, orr = 0;
   uint32_t rnd[4];
-  rng.block((uint32_t) v, (uint32_t) c, 0x5eedu, 0u, rnd);
+  #pragma unroll
+  for (int q = 0; q < W; q++) {
+    const int c = c0 + q;
+    if ((q & 1) == 0 || W == 1) rng.block((uint32_t) v, (uint32_t) (c >> 1), 0x5eedu, 0u, rnd);
+    const int par = (pw >> (8 * q)) & 3;
+    #pragma unroll
+    for (int side = 0; side < 2; side++) {
+      const unsigned long long x = rnd[2 * (c & 1) + side];
+      const unsigned long long *t = thr + side * 16 + par * 4;
+      const uint32_t k = (uint32_t) !(x < t[0]) + (uint32_t) !(x < t[1]) + (uint32_t) !(x < t[2]);      // first k with rnd < thr_k, else 3
+      if (side) orr |= k << (8 * q); else ol |= k << (8 * q);
+    }
+  }
   #pragma unroll
   for (int side = 0; side < 2; side++) {
-    const int child = side ? right[v] : left[v];
-    const double *cdf = pcdf + ((size_t) v * 2 + side) * 16 + par * 4;
-    const double x = u01(rnd[side]);
-    int k = 0;                                              // cov_addres: first k with cdf_k > x, else K-1
-    while (k < 3 && !(cdf[k] > x)) k++;
-    if (child > 0) anc[(size_t) child * L + c] = (uint8_t) k;
-    else {
-      uint8_t out = (uint8_t) k;
-      if (gapmask) { const uint8_t g = gapmask[(size_t) (-child) * L + c]; if (g >= 4) out = g; }
-      leaf[(size_t) (-child) * L + c] = out;
+    const int child = side ? kr : kl;
+    uint32_t o = side ? orr : ol;
+    if (child > 0) {
+      if (W == 4) *reinterpret_cast<uint32_t *>(anc + (size_t) child * L + c0) = o;
+      else anc[(size_t) child * L + c0] = (uint8_t) o;
+    } else {
+      if (gapmask) {                                              // gaps and unknowns of the input alignment are stamped on the leaves
+        const uint32_t g = (W == 4) ? *reinterpret_cast<const uint32_t *>(gapmask + (size_t) (-child) * L + c0) : (uint32_t) gapmask[(size_t) (-child) * L + c0];
+        #pragma unroll
+        for (int q = 0; q < W; q++) { const uint32_t gq = (g >> (8 * q)) & 0xFFu; if (gq >= 4u) o = (o & ~(0xFFu << (8 * q))) | (gq << (8 * q)); }
+      }
+      if (W == 4) *reinterpret_cast<uint32_t *>(leaf + (size_t) (-child) * L + c0) = o;
+      else leaf[(size_t) (-child) * L + c0] = (uint8_t) o;
     }
   }
 }
@@ -552,15 +578,14 @@ replay_level_row_kernel(const int *__restrict__ left, const int *__restrict__ ri
 } // namespace
 
 cudaError_t rsb_launch_null_simulate(const int *left, const int *right, const int *order, const int *level_start_host, int nlevels,
-                                     const double *pcdf, int N, int L, const uint8_t *root,
-                                     const uint8_t *gapmask, long long gap_stride, unsigned long long seed, unsigned long long id0, int first_rep, int nrep,
+                                     const unsigned long long *pthr, int N, int L, const uint8_t *root,
+                                     const uint8_t *gapmask, unsigned long long seed, unsigned long long id0, int first_rep, int nrep,
                                      uint8_t *res, uint8_t *scratch, cudaStream_t st)
 {
-  (void) gap_stride;
   for (int lv = 0; lv < nlevels; lv++) {
     const int b = level_start_host[lv], cnt = level_start_host[lv + 1] - b;
-    null_simulate_level_kernel<<<dim3((L + 127) / 128, cnt, nrep), 128, 0, st>>>(left, right, order, b, pcdf, N, L, root, gapmask, seed, id0,
-                                                                                 first_rep, res, scratch);
+    if (L % 4 == 0) null_simulate_level_kernel<4><<<dim3((L / 4 + 127) / 128, cnt, nrep), 128, 0, st>>>(left, right, order, b, pthr, N, L, root, gapmask, seed, id0, first_rep, res, scratch);
+    else            null_simulate_level_kernel<1><<<dim3((L + 127) / 128, cnt, nrep), 128, 0, st>>>(left, right, order, b, pthr, N, L, root, gapmask, seed, id0, first_rep, res, scratch);
   }
   return cudaGetLastError();
 }

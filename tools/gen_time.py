@@ -29,6 +29,16 @@ for it in range(int(os.environ.get("GEN_ITERS", "4"))):
     ctx.null_fitch_shuffle(host, 1234, R)
     torch.cuda.synchronize()
     print(f"generate {R} replicates: {(time.perf_counter() - t0) * 1e3:.2f} ms", flush=True)
+if os.environ.get("GEN_SIMULATE"):
+    # generator B (cov_GenerateAlignment, ungapped, structure-free): rate matrix + root sequence
+    Q = np.array([[-1.00, 0.30, 0.50, 0.20], [0.25, -0.90, 0.15, 0.50], [0.60, 0.10, -0.95, 0.25], [0.20, 0.45, 0.30, -0.95]])
+    root = np.where(msa[0] < 4, msa[0], 0).astype(np.uint8)
+    for it in range(3):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ctx.null_simulate(Q, root, 99, R, gapmask=msa)
+        torch.cuda.synchronize()
+        print(f"simulate {R} replicates: {(time.perf_counter() - t0) * 1e3:.2f} ms", flush=True)
 chk = ctx.pool_get(1, 0)
 print("checksum", int(chk.astype(np.int64).sum()), "subst vs input", int((chk[0] != msa).sum()))
 ctx.close()
