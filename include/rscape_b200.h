@@ -141,7 +141,9 @@ int rsb_pool_reserve(rsb_ctx *ctx, int nrep);
  * Philox4x32-10 keyed by (seed, replicate id, column).  root: uint8[alen] residues 0..3.  gapmask: optional
  * uint8 [nseq][alen] alignment whose non-canonical cells are copied over the result.
  * Replicates with global ids [first_id, first_id+nrep) land in pool entries [first_rep, first_rep+nrep); the
- * residues depend on (seed, id) only, so ranks that generate the same id get the same alignment. */
+ * residues depend on (seed, id) only, so ranks that generate the same id get the same alignment.  Both generators
+ * return once their kernels are queued on the context's generation stream; calls that read the pool wait on the device
+ * for the entries they use. */
 int rsb_null_simulate(rsb_ctx *ctx, const double *Q, const uint8_t *root, const uint8_t *gapmask, int64_t gap_stride,
                       uint64_t seed, uint64_t first_id, int first_rep, int nrep);
 /* default null of R-scape: Fitch ancestral reconstruction + one column permutation + per-branch

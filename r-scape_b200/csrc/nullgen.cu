@@ -1,12 +1,13 @@
 // nullgen.cu -- null-alignment generators on the device.
 //
-// (B) null_simulate_kernel: cov_GenerateAlignment's ungapped, structure-free path
+// (B) null_simulate_level_kernel: cov_GenerateAlignment's ungapped, structure-free path
 //     (src/cov_simulate.c:289-324 tree walk, :585-631 emission, :724-773 inverse-CDF draw) with
 //     P(t) = exp(tQ) per branch (src/ratematrix.c:185-233; matrices are built on the host in capi.cu,
-//     4x4 per branch).  Every (replicate, column) is an independent chain down the tree; the tree is walked one
-//     level per launch (nodes of a level are independent given their parents), one thread per (replicate, node, column).
-//     Randomness: Philox4x32-10 keyed by (seed, replicate), counter (node, column): one 128-bit block
-//     serves both children of a node.  The reference consumes one Mersenne-Twister stream in branch-major
+//     4x4 per branch, and shipped as cumulative integer thresholds).  Every (replicate, column) is an independent chain
+//     down the tree; the tree is walked one level per launch (nodes of a level are independent given their parents), a
+//     thread owns 4 columns of one (replicate, node).
+//     Randomness: Philox4x32-10 keyed by (seed, replicate), counter (node, column pair): one 128-bit block
+//     serves both children of a node in two columns.  The reference consumes one Mersenne-Twister stream in branch-major
 //     order; the streams differ, the per-draw distribution is the same (validated distributionally).
 //
 // (A) Fitch + shuffle, R-scape's default null (src/R-scape.c:1653-1668):
