@@ -384,6 +384,10 @@ typedef struct esl_sq_s {
 typedef struct esl_getopts_s ESL_GETOPTS;
 typedef struct esl_sqfile_s  ESL_SQFILE;
 typedef struct esl_msafile_s ESL_MSAFILE;
+typedef struct esl_fileparser_s ESL_FILEPARSER;
+/* tail-fit survival functions: only their addresses are taken (src/covariation.c:1931,1962); the fits stay Easel code */
+extern double esl_exp_generic_surv(double x, void *params);
+extern double esl_gam_generic_surv(double x, void *params);
 
 #ifdef __cplusplus
 }

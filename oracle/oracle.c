@@ -947,3 +947,100 @@ orc_null_fitch_shuffle(ORC_RNG *g, const ORC_TREE *T, const uint8_t *msa, int L,
   free(sh); free(S); free(stk); free(perm); free(pos);
   return st;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * E-values and the significant-pair list.
+ */
+/* cov2evalue, src/covariation.c:2370-2400: survival of the null scores at `cov`, times Nc.  The fitted tail
+ * (survfit, 2*nb entries, src/covariation.c:1677-1699) serves scores at or above phi, the sampled distribution the rest.
+ * The reference accumulates the bin counts in an int (:2374); the 64-bit sum here agrees up to 2^31 scores. */
+double
+orc_cov2evalue(double cov, int Nc, const ORC_HIST *h, double phi, const double *survfit)
+{
+  double   eval = INFINITY;
+  int      icov = orc_hist_score2bin(h, cov);
+  int64_t  c    = 0;
+  int      i;
+
+  if      (survfit && icov >= 2 * h->nb - 1) eval = survfit[2 * h->nb - 1] * (double) Nc;
+  else if (survfit && cov >= phi)            eval = survfit[icov + 1]      * (double) Nc;
+  else {
+    if (cov >= h->xmax) return (double) Nc / (double) h->Nc;
+    if (icov <= h->imax) {
+      if (icov <  h->imin)     icov = h->imin;
+      if (icov >= h->imax - 1) eval = (double) Nc / (double) h->Nc;
+      else {
+        for (i = h->imax; i >= icov; i--) c += (int64_t) h->obs[i];
+        eval = (double) c * (double) Nc / (double) h->Nc;
+      }
+    }
+    else return NAN;                                                    /* "cannot find evalue", exit(1) at :2394 */
+  }
+  return eval;
+}
+
+/* evalue2cov, src/covariation.c:2404-2435: the score at which the E-value reaches eval_thresh */
+double
+orc_evalue2cov(double eval_thresh, int Nc, const ORC_HIST *h, int cmin, const double *survfit)
+{
+  double  cov = -INFINITY, eval;
+  int64_t c = 0;
+  int     i, b = cmin - 1;
+
+  if (h->No >= 10 && survfit) {
+    for (b = 2 * h->nb - 1; b >= cmin; b--) {
+      eval = survfit[b] * (double) Nc;
+      if (eval >= eval_thresh) break;
+    }
+    cov = h->w * b + h->bmin;
+  }
+  if (b == cmin - 1) {
+    for (i = h->imax; i >= h->imin; i--) {
+      c += (int64_t) h->obs[i];
+      eval = (double) c * (double) Nc / (double) h->Nc;
+      if (eval >= eval_thresh) break;
+    }
+    cov = h->w * (i + 1) + h->bmin;
+  }
+  return cov;
+}
+
+/* The per-pair loop of cov_CreateHitList, src/covariation.c:828-910: p-value of every pair i<j from the null histogram,
+ * E-value = p * (number of tests of the pair's set), hit iff E < thresh (or thresh > MAX_EVAL = 1000: report all).
+ * pairmask (uint8 [L][L], may be NULL) flags the pairs of the structure set (isbp by data->samplesize); expBP > 0 applies
+ * the `h < expBP` rule of :852.  eval (double [L][L], may be NULL) gets mi->Eval (both triangles; diagonal untouched).
+ * Hits are appended in the reference's row-major order; returns their number (entries beyond cap are counted, not stored),
+ * or -1 if a score has no E-value. */
+int64_t
+orc_hitlist(const double *cov, int L, const ORC_HIST *null, double phi, const double *survfit, const uint8_t *pairmask,
+            uint64_t Nb, uint64_t Nt, int expBP, double thresh, double *eval, int64_t cap,
+            int64_t *hit_i, int64_t *hit_j, double *hit_sc, double *hit_eval, double *hit_pval)
+{
+  int64_t h = 0;
+  int     i, j;
+
+  for (i = 0; i < L - 1; i++)
+    for (j = i + 1; j < L; j++) {
+      double sc   = AT(cov, L, i, j);
+      double pval = orc_cov2evalue(sc, 1, null, phi, survfit);
+      double ev;
+      int    isbp = pairmask ? (pairmask[(size_t) i * L + j] != 0) : 0;
+
+      if (isnan(pval)) return -1;
+      if (isbp)             ev = pval * Nb;
+      else if (h < expBP)   ev = pval * expBP;
+      else                  ev = pval * Nt;
+      if (eval) { AT(eval, L, i, j) = ev; AT(eval, L, j, i) = ev; }
+      if (ev < thresh || thresh > 1000.) {
+        if (h < cap) {
+          if (hit_i)    hit_i[h]    = i;
+          if (hit_j)    hit_j[h]    = j;
+          if (hit_sc)   hit_sc[h]   = sc;
+          if (hit_eval) hit_eval[h] = ev;
+          if (hit_pval) hit_pval[h] = pval;
+        }
+        h++;
+      }
+    }
+  return h;
+}

@@ -87,6 +87,13 @@ int       orc_hist_accumulate(ORC_HIST **cum, const ORC_HIST *one);
 /* histogram bin width from the first null: src/R-scape.c:1357-1360 */
 double    orc_null_width(double w_old, double mincov, double maxcov, double bmin, int hpts, double tol);
 
+/* ---- E-values and the significant-pair list (src/covariation.c:2370-2435, 828-910) ---- */
+double    orc_cov2evalue(double cov, int Nc, const ORC_HIST *h, double phi, const double *survfit /* [2 nb] or NULL */);
+double    orc_evalue2cov(double eval_thresh, int Nc, const ORC_HIST *h, int cmin, const double *survfit);
+int64_t   orc_hitlist(const double *cov, int L, const ORC_HIST *null, double phi, const double *survfit, const uint8_t *pairmask,
+                      uint64_t Nb, uint64_t Nt, int expBP, double thresh, double *eval, int64_t cap,
+                      int64_t *hit_i, int64_t *hit_j, double *hit_sc, double *hit_eval, double *hit_pval);
+
 /* ---- null alignment generators ---- */
 /* tree in Easel convention: N leaves, nodes 0..N-2, root 0, child <= 0 means leaf -child */
 typedef struct {

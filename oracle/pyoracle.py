@@ -78,6 +78,48 @@ class Hist:
         self.obs = np.array([h.obs[b] for b in range(h.nb)], dtype=np.uint64)
 
 
+class NullFit:
+    """What cov2evalue reads of data->ranklist_null (src/covariation.c:2370-2400): the cumulative null histogram `ha`
+    (geometry, bins, imin/imax, xmax, Nc), its censoring point phi / first fitted bin cmin and the fitted tail survfit[2 nb]
+    (cov_histogram_SetSurvFitTail, :1677-1699).  The tail FIT itself is Easel code and stays outside the path: tests pass any
+    non-increasing tail, e.g. exp_tail() below, to the oracle, the reference and the device alike."""
+
+    def __init__(self, bmin, w, obs, xmax=None, phi=np.inf, cmin=None, survfit=None):
+        self.obs = np.ascontiguousarray(obs, dtype=np.uint64)
+        nb = len(self.obs)
+        nz = np.nonzero(self.obs)[0]
+        self.bmin, self.w, self.nb = float(bmin), float(w), nb
+        self.imin = int(nz[0]) if len(nz) else nb
+        self.imax = int(nz[-1]) if len(nz) else -1
+        self.Nc = int(self.obs.sum())
+        self.No = self.Nc
+        self.xmax = float(bmin + w * (self.imax + 1)) if xmax is None else float(xmax)   # a score on the upper edge of bin imax
+        self.phi = float(phi)
+        self.cmin = int(nb if cmin is None else cmin)
+        self.survfit = None if survfit is None else np.ascontiguousarray(survfit, dtype=np.float64)
+        assert self.survfit is None or len(self.survfit) == 2 * nb
+        self.chist = _Hist(self.bmin, self.bmin + self.w * nb, self.w, nb, self.imin, self.imax, self.bmin, self.xmax,
+                           self.Nc, self.Nc, self.No, self.obs.ctypes.data_as(C.POINTER(C.c_uint64)))
+
+    def exp_tail(self, pmass=0.01):
+        """A stand-in for the reference's tail fit: censor the top `pmass` of the scores (what esl_histogram_SetTailByMass
+        does to phi / cmin) and give that tail an exponential survival with the decay of its own mean excess."""
+        cum = np.cumsum(self.obs[::-1].astype(np.float64))[::-1]                  # scores in bins >= b
+        tail = np.nonzero(cum <= pmass * self.Nc)[0]
+        cmin = int(tail[0]) if len(tail) else self.imax
+        cmin = max(cmin, self.imin + 1)
+        phi = self.bmin + self.w * cmin                                           # lower bound of bin cmin
+        b = np.arange(cmin, self.imax + 1)
+        n = self.obs[cmin:self.imax + 1].astype(np.float64)
+        mass = n.sum() / self.Nc
+        mean_excess = float((n * (self.bmin + self.w * (b + 0.5) - phi)).sum() / max(n.sum(), 1.0))
+        lam = 1.0 / max(mean_excess, self.w)
+        surv = np.zeros(2 * self.nb)
+        ub = self.bmin + self.w * (np.arange(cmin, 2 * self.nb) + 1)
+        surv[cmin:] = mass * np.exp(-lam * (ub - phi))                            # survfit[b] = pmass * surv(UBound(b)), :1692
+        return NullFit(self.bmin, self.w, self.obs, self.xmax, phi, cmin, surv)
+
+
 class Oracle:
     def __init__(self, path=None):
         path = path or os.path.join(HERE, "liboracle.so")
@@ -99,6 +141,14 @@ class Oracle:
         L.orc_hist_accumulate.argtypes = [C.POINTER(C.POINTER(_Hist)), C.POINTER(_Hist)]
         L.orc_null_width.restype = C.c_double
         L.orc_null_width.argtypes = [C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_double]
+        i64p = C.POINTER(C.c_int64)
+        L.orc_cov2evalue.restype = C.c_double
+        L.orc_cov2evalue.argtypes = [C.c_double, C.c_int, C.POINTER(_Hist), C.c_double, _dp]
+        L.orc_evalue2cov.restype = C.c_double
+        L.orc_evalue2cov.argtypes = [C.c_double, C.c_int, C.POINTER(_Hist), C.c_int, _dp]
+        L.orc_hitlist.restype = C.c_int64
+        L.orc_hitlist.argtypes = [_dp, C.c_int, C.POINTER(_Hist), C.c_double, _dp, _u8p, C.c_uint64, C.c_uint64, C.c_int, C.c_double,
+                                  _dp, C.c_int64, i64p, i64p, _dp, _dp, _dp]
         L.orc_rng_create.restype = C.c_void_p
         L.orc_rng_create.argtypes = [C.c_uint32]
         L.orc_rng_destroy.argtypes = [C.c_void_p]
@@ -185,6 +235,31 @@ class Oracle:
 
     def null_width(self, w_old, mincov, maxcov, bmin=-10.0, hpts=400, tol=1e-6):
         return self.lib.orc_null_width(w_old, mincov, maxcov, bmin, hpts, tol)
+
+    # ---- E-values and hit list ---------------------------------------------------------------
+    def cov2evalue(self, cov, null, Nc=1):
+        """null: a NullFit (cumulative null histogram + optional fitted tail)"""
+        return self.lib.orc_cov2evalue(float(cov), Nc, C.byref(null.chist), null.phi, _d(null.survfit))
+
+    def evalue2cov(self, eval_thresh, null, Nc=1):
+        return self.lib.orc_evalue2cov(float(eval_thresh), Nc, C.byref(null.chist), null.cmin, _d(null.survfit))
+
+    def hitlist(self, cov, null, pairmask=None, Nb=0, Nt=None, expBP=-1, thresh=0.05, want_eval=True):
+        """The per-pair loop of cov_CreateHitList (src/covariation.c:828-910): dict(i, j, sc, eval, pval, Eval matrix)."""
+        cov = np.ascontiguousarray(cov, dtype=np.float64)
+        L = cov.shape[0]
+        P = L * (L - 1) // 2
+        Nt = P if Nt is None else Nt
+        mask = None if pairmask is None else np.ascontiguousarray(pairmask, dtype=np.uint8)
+        ev = np.full((L, L), np.inf) if want_eval else None
+        hi, hj = np.empty(P, np.int64), np.empty(P, np.int64)
+        sc, he, hp = np.empty(P), np.empty(P), np.empty(P)
+        i64p = C.POINTER(C.c_int64)
+        n = self.lib.orc_hitlist(_d(cov), L, C.byref(null.chist), null.phi, _d(null.survfit), _u8(mask), int(Nb), int(Nt), int(expBP),
+                                 float(thresh), _d(ev), P, hi.ctypes.data_as(i64p), hj.ctypes.data_as(i64p), _d(sc), _d(he), _d(hp))
+        if n < 0:
+            raise RuntimeError("cannot find evalue for a covariation score (src/covariation.c:2394)")
+        return dict(i=hi[:n].copy(), j=hj[:n].copy(), sc=sc[:n].copy(), eval=he[:n].copy(), pval=hp[:n].copy(), Eval=ev)
 
     # ---- null generators --------------------------------------------------------------------
     def rng(self, seed):
@@ -294,6 +369,28 @@ class RefLib:
         st = self.lib.glue_ref_ptime(_d(Q), t, _d(P))
         assert st == 0
         return P
+
+    # the reference's own static cov2evalue / evalue2cov (oracle/ref_glue_evalue.c includes src/covariation.c where it lies)
+    def _evalue_args(self, null):
+        geom = np.array([null.bmin, null.w, null.xmax, null.phi])
+        ig = np.array([null.nb, null.imin, null.imax, null.cmin], dtype=np.int32)
+        return geom, ig
+
+    def cov2evalue(self, cov, null, Nc=1):
+        g = self.lib
+        g.glue_ref_cov2evalue.restype = C.c_double
+        g.glue_ref_cov2evalue.argtypes = [C.c_double, C.c_int, _dp, _ip, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64), _dp]
+        geom, ig = self._evalue_args(null)
+        return g.glue_ref_cov2evalue(float(cov), Nc, _d(geom), _i(ig), null.Nc, null.No, null.obs.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                     _d(null.survfit))
+
+    def evalue2cov(self, eval_thresh, null, Nc=1):
+        g = self.lib
+        g.glue_ref_evalue2cov.restype = C.c_double
+        g.glue_ref_evalue2cov.argtypes = [C.c_double, C.c_int, _dp, _ip, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64), _dp]
+        geom, ig = self._evalue_args(null)
+        return g.glue_ref_evalue2cov(float(eval_thresh), Nc, _d(geom), _i(ig), null.Nc, null.No, null.obs.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                     _d(null.survfit))
 
 
 # ---------------------------------------------------------------------------------------------
