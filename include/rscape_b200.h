@@ -85,6 +85,35 @@ int rsb_scan(rsb_ctx *ctx, const uint8_t *msa, int64_t row_stride, int on_device
  * i<j in bin b = ceil((max(x, bmin+w) - bmin)/w - 1), b < nb; with pairmask (uint8 [L][L], nonzero = pair belongs to the
  * structure set chosen by data->samplesize: contacts / base pairs / WC pairs) hb gets the flagged pairs and ht the others. */
 int rsb_scan_hist(rsb_ctx *ctx, const uint8_t *pairmask, double w, double bmin, int nb, uint64_t *ha, uint64_t *hb, uint64_t *ht);
+/* Replace the device copy of the score matrix by the host's (double [L][L], upper triangle read): the reference's ranking and
+ * hit-list code reads whatever mi->COV holds (src/covariation.c:431, :845), which host code may have written or shifted
+ * (e.g. Potts scores, shiftnonneg, src/correlators.c:1130-1134) after the scan. */
+int rsb_load_scores(rsb_ctx *ctx, const double *cov);
+/* What cov2evalue (src/covariation.c:2370-2400) reads of data->ranklist_null: the cumulative null histogram ha and the
+ * fitted tail.  The tail FIT (esl_gam_FitCompleteBinned / esl_exp_FitCompleteBinned, :1915-1973) stays host code of the
+ * caller; this struct carries its result. */
+typedef struct rsb_nullfit {
+  double          bmin, w;    /* ha->bmin, ha->w: bin b covers (bmin + b w, bmin + (b+1) w] */
+  int             nb;         /* ha->nb */
+  int             imin, imax; /* lowest / highest non-empty bin */
+  double          xmax;       /* ha->xmax: the largest null score */
+  double          phi;        /* ha->phi: censoring point of the fit (read only when survfit != NULL) */
+  uint64_t        Nc;         /* ha->Nc: number of null scores */
+  const uint64_t *obs;        /* ha->obs, [nb] */
+  const double   *survfit;    /* ranklist_null->survfit, [2 nb] (cov_histogram_SetSurvFitTail, :1677-1699), or NULL */
+} rsb_nullfit;
+/* E-values and the significant-pair list of the scan left by rsb_scan / rsb_correct (or, on a sharded pair grid, by
+ * rsb_sharded_correct with bit 0 of mode set): the per-pair loop of cov_CreateHitList, src/covariation.c:828-910.
+ * For every pair i<j: pval = cov2evalue(score, 1, null), E = pval * Nb if pairmask[i][j] (pair of the given structure,
+ * by data->samplesize), else pval * Nt -- or pval * expBP while fewer than expBP hits are listed (expBP > 0, :852);
+ * hit iff E < thresh, every pair if thresh > 1000 (MAX_EVAL).  eval (double [L][L], may be NULL) receives mi->Eval: both
+ * triangles, +inf on the diagonal.  Hits come back in the reference's row-major order; *nhit is their total number, of
+ * which the first min(*nhit, cap) are stored (hit_sc / hit_eval / hit_pval may be NULL).
+ * On a sharded pair grid a rank lists the pairs of the rows it owns (entries of other rows in eval are 0), and the caller
+ * concatenates the ranks' lists: the only data besides the histograms that crosses GPUs. */
+int rsb_scan_hits(rsb_ctx *ctx, const rsb_nullfit *null, const uint8_t *pairmask, uint64_t Nb, uint64_t Nt, int expBP, double thresh,
+                  double *eval, int64_t cap, int64_t *hit_i, int64_t *hit_j, double *hit_sc, double *hit_eval, double *hit_pval,
+                  int64_t *nhit);
 /* fixed-point counts of the last rsb_probs/rsb_scan: int64 [16][L][L], upper triangle (parity tests) */
 int rsb_get_counts(rsb_ctx *ctx, int64_t *counts);
 /* the same counts recomputed by the direct verification kernel (no tensor cores); tests only */

@@ -10,8 +10,9 @@
  *
  * The second half declares the host-side callers of that API that this repo mirrors so that the path can
  * be driven end to end without the rest of R-scape: cov_Calculate's dispatch (src/covariation.c:64-306),
- * the rank-list histograms (:415-457, :641-736, :2334-2362) and the null loop (src/R-scape.c:1565-1724),
- * the latter in a batched form (rsb_null_*) that a 20-line edit of null_rscape would call.
+ * the rank-list histograms (:415-457, :641-736, :2334-2362), the E-value / hit-list loop (:828-910) and the null loop
+ * (src/R-scape.c:1565-1724), the latter in a batched form (rsb_null_*) that a 20-line edit of null_rscape would call
+ * (INTEGRATION.md).
  */
 #ifndef RSCAPE_B200_HOST_INCLUDED
 #define RSCAPE_B200_HOST_INCLUDED
@@ -85,6 +86,15 @@ extern int        null_add2cumranklist(RANKLIST *ranklist, RANKLIST **ocumrankli
  * The first null fixes the histogram width (calculate_width_histo), every null is scanned and added to the cumulative
  * rank list, which is returned in the reference's own RANKLIST form.  data->w is updated as cfg->w is at :1359. */
 extern int        null_rscape_b200(struct data_s *data, ESL_MSA **nulls, int nnull, int hpts, RANKLIST **ret_cumranklist);
+
+/* The per-pair loop of cov_CreateHitList (src/covariation.c:828-910) on the device: mi->Eval and the significant pairs
+ * (i, j, sc, Eval, pval) from mi->COV, data->ranklist_null (cumulative null histogram + fitted tail), ranklist->hb/ht->Nc,
+ * data->expBP and data->thresh->val.  pairmask: uint8 [alen][alen], nonzero = the pair belongs to the structure set selected by
+ * data->samplesize (built once by the caller from data->clist), or NULL.  The file output, power and CaCoFold parts of the
+ * reference function (:911-1006) stay host code on the returned list. */
+extern int        cov_CreateHitList_b200(struct data_s *data, struct mutual_s *mi, RANKLIST *ranklist, const uint8_t *pairmask,
+                                         HITLIST **ret_hitlist);
+extern void       cov_FreeHitList(HITLIST *hitlist);
 
 #ifdef __cplusplus
 }

@@ -83,6 +83,30 @@ typedef struct ranklist_s {
   double        *survfit;
 } RANKLIST;
 
+/* src/correlators.h:141-165; bptype is R-view's BPTYPE enum (lib/R-view/src/rview_contacts.h:22-62), an int here */
+#ifndef MAX_EVAL
+#define MAX_EVAL 1000               /* forcing -E > MAX_EVAL reports all pairs, src/correlators.h:24 */
+#endif
+typedef struct hit_s {
+  int64_t i;
+  int64_t j;
+  double  sc;
+  double  Eval;
+  double  pval;
+  int64_t nsubs;
+  double  power;
+  int     bptype;
+  int     is_compatible;
+} HIT;
+
+typedef struct hitlist_s {
+  int       nhit;
+  HIT     **srthit;
+  HIT      *hit;
+  int64_t   Nt;
+  int64_t   Nb;
+} HITLIST;
+
 typedef struct thresh_s {
   THRESHTYPE type;
   double     val;

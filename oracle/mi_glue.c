@@ -117,6 +117,47 @@ glue_null_rscape(struct data_s *data, int nnull, int nseq, int L, const uint8_t 
   free(arr);
   return status;
 }
+/* drive cov_CreateHitList_b200 from flat arrays.  geom: { bmin, w, xmax, phi }, ig: { nb, imin, imax }; survfit may be NULL,
+ * obs == NULL means "no null rank list" (the naive method).  Returns the Easel status; *nhit = length of the list, of which
+ * the first min(*nhit, cap) entries are copied out; eval_out gets mi->Eval. */
+int
+glue_hitlist(struct data_s *data, struct mutual_s *mi, const double *geom, const int *ig, uint64_t *obs, double *survfit,
+             uint64_t Nb, uint64_t Nt, int expBP, double thresh, const uint8_t *pairmask, int64_t cap,
+             int64_t *hi, int64_t *hj, double *sc, double *ev, double *pv, double *eval_out, int64_t *nhit)
+{
+  ESL_HISTOGRAM ha, hb, ht;
+  RANKLIST      null, rl;
+  THRESH        th;
+  HITLIST      *hl = NULL;
+  int64_t       h, L = mi->alen;
+  int           status, i;
+
+  memset(&ha, 0, sizeof(ha)); memset(&hb, 0, sizeof(hb)); memset(&ht, 0, sizeof(ht));
+  memset(&null, 0, sizeof(null)); memset(&rl, 0, sizeof(rl));
+  if (obs) {
+    ha.bmin = geom[0]; ha.w = geom[1]; ha.xmax = geom[2]; ha.phi = geom[3];
+    ha.nb = ig[0]; ha.imin = ig[1]; ha.imax = ig[2]; ha.bmax = ha.bmin + ha.w * ha.nb; ha.obs = obs;
+    for (i = 0; i < ha.nb; i++) { ha.Nc += obs[i]; ha.No += obs[i]; ha.n += obs[i]; }
+    null.ha = &ha; null.survfit = survfit;
+  }
+  hb.Nc = Nb; ht.Nc = Nt;
+  rl.hb = &hb; rl.ht = &ht;
+  th.type = Eval; th.val = thresh; th.sc_bp = th.sc_nbp = 0.;
+  data->ranklist_null = obs ? &null : NULL;
+  data->thresh = &th;
+  data->expBP  = expBP;
+  status = cov_CreateHitList_b200(data, mi, &rl, pairmask, &hl);
+  data->ranklist_null = NULL; data->thresh = NULL;
+  if (status != eslOK) return status;
+  *nhit = hl->nhit;
+  for (h = 0; h < hl->nhit && h < cap; h++) {
+    if (hl->srthit[h] != hl->hit + h) { cov_FreeHitList(hl); return eslFAIL; }
+    hi[h] = hl->hit[h].i; hj[h] = hl->hit[h].j; sc[h] = hl->hit[h].sc; ev[h] = hl->hit[h].Eval; pv[h] = hl->hit[h].pval;
+  }
+  if (eval_out) for (i = 0; i < L; i++) memcpy(eval_out + (size_t) i * L, mi->Eval->mx[i], sizeof(double) * (size_t) L);
+  cov_FreeHitList(hl);
+  return eslOK;
+}
 double glue_data_w(struct data_s *d) { return d->w; }
 int    glue_cov_calculate(struct data_s *d, ESL_MSA *msa) { return cov_CalculateCOV(d, msa); }
 #endif

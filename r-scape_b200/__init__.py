@@ -34,6 +34,12 @@ _vp = C.c_void_p
 _lib = None
 
 
+class NullFitStruct(C.Structure):
+    """rsb_nullfit of include/rscape_b200.h"""
+    _fields_ = [("bmin", C.c_double), ("w", C.c_double), ("nb", C.c_int), ("imin", C.c_int), ("imax", C.c_int), ("xmax", C.c_double),
+                ("phi", C.c_double), ("Nc", C.c_uint64), ("obs", _u64p), ("survfit", _dp)]
+
+
 class RscapeB200Error(RuntimeError):
     pass
 
@@ -62,6 +68,9 @@ def lib():
         L.rsb_scan.argtypes = [_vp, _vp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.c_double,
                                _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp]
         L.rsb_scan_hist.argtypes = [_vp, _u8p, C.c_double, C.c_double, C.c_int, _u64p, _u64p, _u64p]
+        L.rsb_scan_hits.argtypes = [_vp, C.POINTER(NullFitStruct), _u8p, C.c_uint64, C.c_uint64, C.c_int, C.c_double, _dp, C.c_int64,
+                                    _i64p, _i64p, _dp, _dp, _dp, _i64p]
+        L.rsb_load_scores.argtypes = [_vp, _dp]
         L.rsb_set_shard.argtypes = [_vp, C.c_int, C.c_int]
         L.rsb_sharded_counts.argtypes = [_vp, _vp, C.c_int64, C.c_int, C.c_double, _dp]
         L.rsb_sharded_counts_pool.argtypes = [_vp, C.c_int, C.c_double, _dp]
@@ -185,6 +194,38 @@ class Context:
         up = lambda a: None if a is None else a.ctypes.data_as(_u64p)
         self._ck(lib().rsb_scan_hist(self._h, None if pm is None else pm.ctypes.data_as(_u8p), w, bmin, nb, up(ha), up(hb), up(ht)))
         return ha, hb, ht
+
+    def load_scores(self, cov):
+        """Replace the device score matrix by a host matrix [L][L] (the stages after the scan read whatever mi->COV holds)."""
+        cov = np.ascontiguousarray(cov, dtype=np.float64)
+        assert cov.shape == (self.L, self.L)
+        self._ck(lib().rsb_load_scores(self._h, _d(cov)))
+
+    def scan_hits(self, bmin, w, obs, xmax, Nt, Nb=0, pairmask=None, survfit=None, phi=np.inf, expBP=-1, thresh=0.05, want_eval=True, cap=None):
+        """E-values and significant pairs of the last scan (cov_CreateHitList's per-pair loop, src/covariation.c:828-910) against
+        the cumulative null histogram obs[nb] (geometry bmin, w; largest null score xmax) and, optionally, its fitted tail
+        survfit[2 nb] with censoring point phi.  Returns dict(i, j, sc, eval, pval, nhit, Eval)."""
+        obs = np.ascontiguousarray(obs, dtype=np.uint64)
+        nz = np.nonzero(obs)[0]
+        if len(nz) == 0:
+            raise RscapeB200Error("scan_hits: the null histogram is empty")
+        sf = None if survfit is None else np.ascontiguousarray(survfit, dtype=np.float64)
+        assert sf is None or len(sf) == 2 * len(obs)
+        nf = NullFitStruct(float(bmin), float(w), len(obs), int(nz[0]), int(nz[-1]), float(xmax), float(phi), int(obs.sum()),
+                           obs.ctypes.data_as(_u64p), _d(sf))
+        pm = None if pairmask is None else np.ascontiguousarray(pairmask, dtype=np.uint8)
+        assert pm is None or pm.shape == (self.L, self.L)
+        P = self.L * (self.L - 1) // 2
+        cap = P if cap is None else int(cap)
+        ev = np.empty((self.L, self.L)) if want_eval else None
+        hi, hj = np.empty(max(cap, 1), np.int64), np.empty(max(cap, 1), np.int64)
+        sc, he, hp = np.empty(max(cap, 1)), np.empty(max(cap, 1)), np.empty(max(cap, 1))
+        n = C.c_int64()
+        self._ck(lib().rsb_scan_hits(self._h, C.byref(nf), None if pm is None else pm.ctypes.data_as(_u8p), int(Nb), int(Nt), int(expBP),
+                                     float(thresh), _d(ev), cap, hi.ctypes.data_as(_i64p), hj.ctypes.data_as(_i64p), _d(sc), _d(he), _d(hp),
+                                     C.byref(n)))
+        k = min(n.value, cap)
+        return dict(i=hi[:k].copy(), j=hj[:k].copy(), sc=sc[:k].copy(), eval=he[:k].copy(), pval=hp[:k].copy(), nhit=n.value, Eval=ev)
 
     # ---- one scan with the pair grid sharded over ranks ------------------------------------------
     def set_shard(self, rank, world):

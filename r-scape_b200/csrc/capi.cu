@@ -4,6 +4,7 @@
 // the only host synchronisations are the D2H reads the caller asked for.  There is no CPU path:
 // rsb_create fails unless a compute-capability-10.x device is present.
 #include "rsb_common.cuh"
+#include "rsb_evalue.cuh"
 #include "../../include/rscape_b200.h"
 #include <cstdarg>
 #include <cstring>
@@ -51,6 +52,10 @@ cudaError_t rsb_launch_width(const double *minmax, double w_old, double bmin, in
 cudaError_t rsb_launch_symmetrize(double *cov, int L, int Lp, cudaStream_t st);
 cudaError_t rsb_launch_hist3(const double *cov, int L, int Lp, const uint8_t *pairmask, double bmin, double w, int nb,
                              unsigned long long *ha, unsigned long long *hb, unsigned long long *ht, int *flags, cudaStream_t st);
+cudaError_t rsb_launch_evalue_hits(const double *cov, int L, int Lp, const rsb_nullview &nv, const uint8_t *pairmask, double Nb, double Nt,
+                                   double expBP, long long switch_n, double thresh, int report_all, int sr, int sw, double *eval, long long cap,
+                                   long long *hit_ij, double *hit_sc, double *hit_eval, double *hit_pval, unsigned long long *nhit, int *flags,
+                                   cudaStream_t st);
 cudaError_t rsb_launch_null_simulate(const int *left, const int *right, const int *order, const int *level_start_host, int nlevels,
                                      const unsigned long long *pthr, int N, int L, const uint8_t *root,
                                      const uint8_t *gapmask, unsigned long long seed, unsigned long long id0, int first_rep, int nrep,
@@ -445,6 +450,7 @@ int check_flags(rsb_ctx *ctx, const char *what)
     if (f & 1) { rsb_set_error(ctx, "%s: pm validation failed", what); return 1; }           // corr_Marginals / corr_ValidateProbs
     if (f & 2) { rsb_set_error(ctx, "%s: bad covariation (NaN)", what); return 1; }          // correlators.c:1124
     if (f & 4) { rsb_set_error(ctx, "%s: score histogram capacity (%d bins) exceeded", what, HIST_BINS); return 1; }
+    if (f & 8) { rsb_set_error(ctx, "%s: cannot find evalue for a covariation score", what); return 1; }      // covariation.c:2394
   }
   return 0;
 }
@@ -1135,6 +1141,122 @@ int rsb_scan_hist(rsb_ctx *ctx, const uint8_t *pairmask, double w, double bmin, 
   if (ht) RSB_CUDA_OK(cudaMemcpyAsync(ht, d3 + 2 * (size_t) nb, sizeof(uint64_t) * nb, cudaMemcpyDeviceToHost, ctx->stream));
   const int rc = check_flags(ctx, "cov_SignificantPairs_Ranking");
   cudaFree(d3); if (dmask) cudaFree(dmask);
+  return rc;
+}
+
+/* scores written or changed on the host (mi->COV) -> the device matrix the histogram / E-value stages read */
+int rsb_load_scores(rsb_ctx *ctx, const double *cov)
+{
+  RSB_CUDA_OK(cudaSetDevice(ctx->device));
+  if (!cov || !ctx->d_cov) { rsb_set_error(ctx, "rsb_load_scores: no matrix / context not configured"); return 1; }
+  RSB_CUDA_OK(cudaMemcpy2DAsync(ctx->d_cov, sizeof(double) * ctx->Lp, cov, sizeof(double) * ctx->L, sizeof(double) * ctx->L, ctx->L,
+                                cudaMemcpyHostToDevice, ctx->stream));
+  RSB_CUDA_OK(cudaStreamSynchronize(ctx->stream));                                        // the caller may reuse cov at once
+  return 0;
+}
+
+/* E-values and significant pairs of the scan left in d_cov: the per-pair loop of cov_CreateHitList, src/covariation.c:828-910 */
+int rsb_scan_hits(rsb_ctx *ctx, const rsb_nullfit *null, const uint8_t *pairmask, uint64_t Nb, uint64_t Nt, int expBP, double thresh,
+                  double *eval, int64_t cap, int64_t *hit_i, int64_t *hit_j, double *hit_sc, double *hit_eval, double *hit_pval, int64_t *nhit)
+{
+  RSB_CUDA_OK(cudaSetDevice(ctx->device));
+  if (!null || !null->obs || null->nb < 1 || !(null->w > 0.0) || null->imax < null->imin || null->imin < 0 || null->imax >= null->nb || null->Nc == 0) {
+    rsb_set_error(ctx, "rsb_scan_hits: empty or inconsistent null histogram"); return 1;
+  }
+  if (cap < 0 || (cap > 0 && !(hit_i && hit_j))) { rsb_set_error(ctx, "rsb_scan_hits: bad hit list arguments"); return 1; }
+  if (expBP > 0 && ctx->shard_world > 1) {
+    rsb_set_error(ctx, "rsb_scan_hits: the expBP rule (covariation.c:852) follows the order of the whole pair list and is not offered on a sharded pair grid");
+    return 1;
+  }
+  const size_t L = ctx->L, nb = (size_t) null->nb;
+  const long long P = (long long) L * (long long) (L - 1) / 2;
+  const int report_all = thresh > 1000.0;                                                   // MAX_EVAL, src/correlators.h:24
+  const long long dcap = std::max<long long>(1, std::min<long long>(cap, P));
+
+  // suffix sums of the bins (exact): what the reference's loop at :2390 adds up for every pair
+  std::vector<unsigned long long> csum(nb, 0ull);
+  unsigned long long run = 0;
+  for (long long b = null->imax; b >= 0; b--) { run += null->obs[b]; csum[(size_t) b] = run; }
+
+  unsigned long long *d_csum = nullptr, *d_n = nullptr;
+  double *d_surv = nullptr, *d_eval = nullptr, *d_hd = nullptr;
+  long long *d_ij = nullptr;
+  uint8_t *d_mask = nullptr;
+  int rc = 1;
+  std::vector<long long> ij;
+  std::vector<double> hd;
+  unsigned long long n_dev = 0;
+  rsb_nullview nv;
+  long long switch_n = (expBP > 0) ? P : -1;                                               // first pass: every pair outside the structure uses expBP
+#define HITS_OK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    rsb_set_error(ctx, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); goto done; } } while (0)
+  HITS_OK(cudaMalloc(&d_csum, sizeof(unsigned long long) * nb));
+  HITS_OK(cudaMalloc(&d_n, sizeof(unsigned long long)));
+  HITS_OK(cudaMalloc(&d_ij, sizeof(long long) * (size_t) dcap));
+  HITS_OK(cudaMalloc(&d_hd, sizeof(double) * 3 * (size_t) dcap));
+  HITS_OK(cudaMemcpyAsync(d_csum, csum.data(), sizeof(unsigned long long) * nb, cudaMemcpyHostToDevice, ctx->stream));
+  if (null->survfit) {
+    HITS_OK(cudaMalloc(&d_surv, sizeof(double) * 2 * nb));
+    HITS_OK(cudaMemcpyAsync(d_surv, null->survfit, sizeof(double) * 2 * nb, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if (pairmask) {
+    HITS_OK(cudaMalloc(&d_mask, L * L));
+    HITS_OK(cudaMemcpyAsync(d_mask, pairmask, L * L, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if (eval) {
+    HITS_OK(cudaMalloc(&d_eval, sizeof(double) * L * L));
+    HITS_OK(cudaMemsetAsync(d_eval, 0, sizeof(double) * L * L, ctx->stream));               // pairs of other ranks' rows stay 0 on a sharded grid
+  }
+  nv.bmin = null->bmin; nv.w = null->w; nv.xmax = null->xmax; nv.phi = null->phi; nv.Nc = (double) null->Nc;
+  nv.nb = null->nb; nv.imin = null->imin; nv.imax = null->imax; nv.csum = d_csum; nv.survfit = d_surv;
+  ij.resize((size_t) dcap); hd.resize(3 * (size_t) dcap);
+
+  for (int pass = 0; pass < 2; pass++) {
+    HITS_OK(cudaMemsetAsync(d_n, 0, sizeof(unsigned long long), ctx->stream));
+    HITS_OK(rsb_launch_evalue_hits(ctx->d_cov, ctx->L, ctx->Lp, nv, d_mask, (double) Nb, (double) Nt, (double) expBP, switch_n, thresh, report_all,
+                                   ctx->shard_rank, ctx->shard_world, d_eval, cap > 0 ? dcap : 0, d_ij, d_hd, d_hd + dcap, d_hd + 2 * dcap,
+                                   d_n, ctx->d_flags, ctx->stream));
+    ctx->launches++;
+    HITS_OK(cudaMemcpyAsync(&n_dev, d_n, sizeof(n_dev), cudaMemcpyDeviceToHost, ctx->stream));
+    if (check_flags(ctx, "cov_CreateHitList")) goto done;                                   // synchronises the stream
+    const size_t kept = (size_t) std::min<unsigned long long>(n_dev, cap > 0 ? (unsigned long long) dcap : 0ull);
+    if (kept) {
+      HITS_OK(cudaMemcpyAsync(ij.data(), d_ij, sizeof(long long) * kept, cudaMemcpyDeviceToHost, ctx->stream));
+      for (int f = 0; f < 3; f++)
+        HITS_OK(cudaMemcpyAsync(hd.data() + f * (size_t) dcap, d_hd + f * (size_t) dcap, sizeof(double) * kept, cudaMemcpyDeviceToHost, ctx->stream));
+      HITS_OK(cudaStreamSynchronize(ctx->stream));
+    }
+    if (pass == 1 || expBP <= 0) break;
+    // the expBP-th hit in row-major order closes the expBP regime; with fewer hits it never closes and this pass stands
+    if (n_dev < (unsigned long long) expBP) break;
+    if (n_dev > kept) { rsb_set_error(ctx, "rsb_scan_hits: the expBP rule needs the whole first-pass hit list (%llu hits, capacity %lld)", n_dev, (long long) cap); goto done; }
+    std::vector<long long> order(ij.begin(), ij.begin() + kept);
+    std::nth_element(order.begin(), order.begin() + (expBP - 1), order.end());
+    const long long key = order[(size_t) expBP - 1], ki = key >> 32, kj = key & 0xffffffffll;
+    switch_n = ki * (long long) L - ki * (ki + 1) / 2 + (kj - ki - 1);
+  }
+  {
+    const size_t kept = (size_t) std::min<unsigned long long>(n_dev, cap > 0 ? (unsigned long long) dcap : 0ull);
+    std::vector<size_t> idx(kept);
+    for (size_t k = 0; k < kept; k++) idx[k] = k;
+    std::sort(idx.begin(), idx.end(), [&](size_t a, size_t b) { return ij[a] < ij[b]; });   // (i << 32 | j): the reference's row-major order
+    for (size_t k = 0; k < kept; k++) {
+      const size_t s = idx[k];
+      hit_i[k] = ij[s] >> 32; hit_j[k] = ij[s] & 0xffffffffll;
+      if (hit_sc)   hit_sc[k]   = hd[s];
+      if (hit_eval) hit_eval[k] = hd[(size_t) dcap + s];
+      if (hit_pval) hit_pval[k] = hd[2 * (size_t) dcap + s];
+    }
+    if (nhit) *nhit = (int64_t) n_dev;
+    if (eval) {
+      HITS_OK(cudaMemcpyAsync(eval, d_eval, sizeof(double) * L * L, cudaMemcpyDeviceToHost, ctx->stream));
+      HITS_OK(cudaStreamSynchronize(ctx->stream));
+    }
+  }
+  rc = 0;
+done:
+#undef HITS_OK
+  cudaFree(d_csum); cudaFree(d_n); cudaFree(d_ij); cudaFree(d_hd); cudaFree(d_surv); cudaFree(d_mask); cudaFree(d_eval);
   return rc;
 }
 

@@ -7,9 +7,12 @@
  *   null_add2cumranklist    src/R-scape.c:1565-1612
  *   null_rscape_b200        batched form of null_rscape's loop body, src/R-scape.c:1650-1697: all nulls are scanned
  *                           on the device and only the cumulative histogram comes back.
+ *   cov_CreateHitList_b200  the per-pair loop of cov_CreateHitList, src/covariation.c:828-910: E-values of every pair
+ *                           (mi->Eval) and the list of significant pairs, computed on the device from mi->COV and
+ *                           data->ranklist_null.
  *
- * E-values, hit lists, power and CaCoFold (src/covariation.c:460-530, 779-1006) stay R-scape host code; they
- * consume the RANKLIST / mutual_s produced here unchanged.
+ * The tail fit of the null histogram, the output files, power and CaCoFold (src/covariation.c:460-530, 911-1006) stay
+ * R-scape host code; they consume the RANKLIST / HITLIST / mutual_s produced here unchanged.
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -269,5 +272,86 @@ null_rscape_b200(struct data_s *data, ESL_MSA **nulls, int nnull, int hpts, RANK
   if (cum) cov_FreeRankList(cum);
   free(stage); free(minmax); free(bins);
   if (ctx) rsb_destroy(ctx);
+  return status;
+}
+
+/* ------------------------------------------------------------------ E-values and the significant-pair list */
+void
+cov_FreeHitList(HITLIST *hitlist)
+{
+  if (!hitlist) return;
+  free(hitlist->srthit);
+  free(hitlist->hit);
+  free(hitlist);
+}
+
+/* The loop at src/covariation.c:828-910 on the device.  pairmask (uint8 [alen][alen], may be NULL) flags the pairs that the
+ * reference finds with CMAP_GetBPTYPE + data->samplesize (:832-840): building that mask once from data->clist is the
+ * caller's O(ncnt) job and replaces a linear scan of the contact list per pair.  Filled per hit: i, j, sc, Eval, pval;
+ * nsubs / power (data->spair), bptype and is_compatible (:897-899) are O(nhit) lookups left to the caller, as are
+ * data->spair[n].sc / Eval / Pval, which the caller can read from mi->COV / mi->Eval.  mi->Eval is written only when a
+ * null rank list exists (:855), like the reference. */
+int
+cov_CreateHitList_b200(struct data_s *data, struct mutual_s *mi, RANKLIST *ranklist, const uint8_t *pairmask, HITLIST **ret_hitlist)
+{
+  rsb_ctx  *ctx = corr_b200_context(mi);
+  RANKLIST *null = data->ranklist_null;
+  HITLIST  *hitlist = NULL;
+  int64_t  *hi = NULL, *hj = NULL, nhit = 0, h, P, cap;
+  double   *sc = NULL, *ev = NULL, *pv = NULL;
+  int64_t   L = mi->alen, i, j;
+  int       status = eslFAIL;
+  int       all = (data->thresh->val > MAX_EVAL);
+
+  *ret_hitlist = NULL;
+  if (!ctx) ESL_FAIL(eslFAIL, data->errbuf, "mutual_s was not created by corr_Create()");
+  P = L * (L - 1) / 2;
+  if ((hitlist = calloc(1, sizeof(HITLIST))) == NULL) goto ERROR;
+  hitlist->Nt = (int64_t) ranklist->ht->Nc;                                         /* :811-812 */
+  hitlist->Nb = (int64_t) ranklist->hb->Nc;
+
+  if (null == NULL) {                          /* naive method: E-values carry no significance, every pair has pval = eval = 0 (:844-847) */
+    nhit = (0. < data->thresh->val || all) ? P : 0;
+    if ((hitlist->hit = calloc((size_t) nhit + 1, sizeof(HIT))) == NULL) goto ERROR;
+    if (nhit)
+      for (h = 0, i = 0; i < L - 1; i++)
+        for (j = i + 1; j < L; j++, h++) { hitlist->hit[h].i = i; hitlist->hit[h].j = j; hitlist->hit[h].sc = mi->COV->mx[i][j]; }
+  }
+  else {
+    rsb_nullfit nf;
+    nf.bmin = null->ha->bmin; nf.w = null->ha->w; nf.nb = null->ha->nb; nf.imin = null->ha->imin; nf.imax = null->ha->imax;
+    nf.xmax = null->ha->xmax; nf.phi = null->ha->phi; nf.Nc = null->ha->Nc; nf.obs = null->ha->obs; nf.survfit = null->survfit;
+    /* the hit list reads whatever mi->COV holds now (:845) */
+    if (rsb_load_scores(ctx, mi->COV->mx[0]) != 0) { snprintf(data->errbuf, eslERRBUFSIZE, "%s", rsb_error(ctx)); goto ERROR; }
+    /* first call: count the hits and fill mi->Eval; second call: fetch them (lists are short unless every pair is reported) */
+    cap = all ? P : 4096;
+    for (;;) {
+      free(hi); free(hj); free(sc); free(ev); free(pv);
+      hi = malloc(sizeof(int64_t) * (size_t) (cap + 1)); hj = malloc(sizeof(int64_t) * (size_t) (cap + 1));
+      sc = malloc(sizeof(double) * (size_t) (cap + 1));  ev = malloc(sizeof(double) * (size_t) (cap + 1)); pv = malloc(sizeof(double) * (size_t) (cap + 1));
+      if (!hi || !hj || !sc || !ev || !pv) { snprintf(data->errbuf, eslERRBUFSIZE, "allocation failed"); goto ERROR; }
+      if (rsb_scan_hits(ctx, &nf, pairmask, ranklist->hb->Nc, ranklist->ht->Nc, data->expBP, data->thresh->val,
+                        mi->Eval->mx[0], cap, hi, hj, sc, ev, pv, &nhit) != 0) {
+        snprintf(data->errbuf, eslERRBUFSIZE, "%s", rsb_error(ctx));
+        goto ERROR;
+      }
+      if (nhit <= cap) break;
+      cap = nhit;
+    }
+    if ((hitlist->hit = calloc((size_t) nhit + 1, sizeof(HIT))) == NULL) goto ERROR;
+    for (h = 0; h < nhit; h++) {
+      hitlist->hit[h].i = hi[h]; hitlist->hit[h].j = hj[h]; hitlist->hit[h].sc = sc[h]; hitlist->hit[h].Eval = ev[h]; hitlist->hit[h].pval = pv[h];
+    }
+  }
+  if ((hitlist->srthit = calloc((size_t) nhit + 1, sizeof(HIT *))) == NULL) goto ERROR;
+  for (h = 0; h < nhit; h++) hitlist->srthit[h] = hitlist->hit + h;
+  hitlist->srthit[0] = hitlist->hit;                                                /* :817 */
+  hitlist->nhit = (int) nhit;
+  *ret_hitlist = hitlist; hitlist = NULL;
+  status = eslOK;
+
+ ERROR:
+  free(hi); free(hj); free(sc); free(ev); free(pv);
+  if (hitlist) cov_FreeHitList(hitlist);
   return status;
 }

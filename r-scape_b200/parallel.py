@@ -81,3 +81,52 @@ def reduce_cov_sums(cov_sums, L, device=None, group=None):
     lo, hi = reduce_range(out[L + 1], out[L + 2], device, group)
     out[L + 1], out[L + 2] = lo, hi
     return out
+
+
+HIT_FIELDS = ("i", "j", "sc", "eval", "pval")
+
+
+def merge_hit_lists(lists):
+    """Concatenate the ranks' significant-pair lists (dicts of rsb_scan_hits: i, j, sc, eval, pval) and restore the reference's
+    row-major order of cov_CreateHitList (src/covariation.c:828-829).  On a sharded pair grid every pair is listed by the one
+    rank that owns its row, so the merged list is the list of the whole scan."""
+    out = {k: np.concatenate([np.asarray(h[k]) for h in lists]) if lists else np.empty(0) for k in HIT_FIELDS}
+    order = np.lexsort((out["j"], out["i"]))
+    out = {k: v[order] for k, v in out.items()}
+    out["nhit"] = int(sum(int(h.get("nhit", len(h["i"]))) for h in lists))
+    return out
+
+
+def gather_hit_lists(hits, device=None, group=None):
+    """All-gather the significant-pair lists of a sharded scan: one all-gather of the list lengths, one of the lists padded to the
+    longest (5 x 8 bytes per hit; NCCL on the GPU box, gloo in the CPU tests).  Returns the merged list on every rank."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return merge_hit_lists([hits])
+    world = dist.get_world_size(group)
+    n = len(hits["i"])
+    counts = torch.tensor([n, int(hits.get("nhit", n))], dtype=torch.int64)
+    if device is not None:
+        counts = counts.to(device)
+    all_counts = [torch.empty_like(counts) for _ in range(world)]
+    dist.all_gather(all_counts, counts, group=group)
+    lens = [int(c[0]) for c in all_counts]
+    width = max(max(lens), 1)
+    # i and j travel as float64 bit patterns next to the three double fields (exact for any int64)
+    buf = np.zeros((len(HIT_FIELDS), width), dtype=np.float64)
+    buf[0, :n] = np.asarray(hits["i"], dtype=np.int64).view(np.float64)
+    buf[1, :n] = np.asarray(hits["j"], dtype=np.int64).view(np.float64)
+    for f, k in enumerate(HIT_FIELDS[2:], start=2):
+        buf[f, :n] = hits[k]
+    t = torch.from_numpy(buf).view(torch.int64)                     # gathered as integers: no NaN canonicalisation on the way
+    if device is not None:
+        t = t.to(device)
+    parts = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(parts, t, group=group)
+    lists = []
+    for p, m, c in zip(parts, lens, all_counts):
+        a = p.cpu().numpy()
+        lists.append(dict(i=a[0, :m].copy(), j=a[1, :m].copy(), sc=a[2, :m].view(np.float64).copy(), eval=a[3, :m].view(np.float64).copy(),
+                          pval=a[4, :m].view(np.float64).copy(), nhit=int(c[1])))
+    return merge_hit_lists(lists)

@@ -15,6 +15,9 @@ FIELDS_DATA = ["ofile", "r", "samplesize", "ranklist_null", "mi", "pt", "thresh"
                "ctlist", "spair", "power", "r3d", "agg_Eval", "agg_method", "T", "ribosum", "ct", "clist", "msa2pdb", "msamap", "firstpos", "bmin",
                "w", "fracfit", "pmass", "doexpfit", "tau", "mu", "lambda", "allowpair", "tol", "nofigures", "verbose", "errbuf", "prep_RF"]
 
+FIELDS_HIT = ["i", "j", "sc", "Eval", "pval", "nsubs", "power", "bptype", "is_compatible"]
+FIELDS_HITLIST = ["nhit", "srthit", "hit", "Nt", "Nb"]
+
 PROG = r'''
 #include <stdio.h>
 #include <stddef.h>
@@ -24,6 +27,8 @@ int main(void) {
   printf("sizeof data_s %%zu\n", sizeof(struct data_s));
   printf("sizeof RANKLIST %%zu\n", sizeof(RANKLIST));
   printf("sizeof THRESH %%zu\n", sizeof(THRESH));
+  printf("sizeof HIT %%zu\n", sizeof(HIT));
+  printf("sizeof HITLIST %%zu\n", sizeof(HITLIST));
 %s
   return 0;
 }
@@ -33,6 +38,8 @@ int main(void) {
 def _run(includes, incdirs):
     body = "".join(f'  printf("mi.{f} %zu\\n", offsetof(struct mutual_s, {f}));\n' for f in FIELDS_MI)
     body += "".join(f'  printf("data.{f} %zu\\n", offsetof(struct data_s, {f}));\n' for f in FIELDS_DATA)
+    body += "".join(f'  printf("hit.{f} %zu\\n", offsetof(HIT, {f}));\n' for f in FIELDS_HIT)
+    body += "".join(f'  printf("hitlist.{f} %zu\\n", offsetof(HITLIST, {f}));\n' for f in FIELDS_HITLIST)
     with tempfile.TemporaryDirectory() as td:
         src = os.path.join(td, "p.c")
         open(src, "w").write(PROG % (includes, body))

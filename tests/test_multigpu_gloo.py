@@ -66,6 +66,66 @@ def test_null_sharding_two_ranks_gloo(tmp_path, po, oracle, pkg):
     assert int(z["bins"].sum()) == R * L * (L - 1) // 2
 
 
+def _hits_worker(rank, world, port, L, out):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+    pkg = ge.load_package()
+    po = ge.load_oracle()
+    ora = po.Oracle()
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    cov, null, mask = _hits_case(po, ora, L)
+    # this rank's rows of the pair grid (32-column row blocks dealt cyclically, as rsb_set_shard): hits of the other rows are dropped
+    full = ora.hitlist(cov, null, mask, int(mask.sum()), L * (L - 1) // 2 - int(mask.sum()), -1, 5.0)
+    mine = (full["i"] // 32) % world == rank
+    part = {k: full[k][mine] for k in ("i", "j", "sc", "eval", "pval")}
+    part["nhit"] = int(mine.sum())
+    merged = pkg.parallel.gather_hit_lists(part)
+    np.savez(out % rank, **{k: merged[k] for k in ("i", "j", "sc", "eval", "pval")}, nhit=merged["nhit"])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _hits_case(po, ora, L):
+    msa, wgt, partner = po.synthetic_msa(150, L, seed=33)
+    cov = ora.scan(msa, wgt, po.GT, po.C16, po.APC)["cov"]
+    x = np.maximum(np.random.default_rng(5).normal(0, 5, 40000), -10 + 0.05)
+    b = np.ceil((x + 10) / 0.05 - 1).astype(np.int64)
+    null = po.NullFit(-10.0, 0.05, np.bincount(b, minlength=int(b.max()) + 6).astype(np.uint64), xmax=float(x.max())).exp_tail(0.05)
+    mask = np.zeros((L, L), np.uint8)
+    for i, j in enumerate(partner):
+        if j > i:
+            mask[i, j] = 1
+    return cov, null, mask
+
+
+def test_hit_lists_gathered_over_two_ranks_gloo(tmp_path, po, oracle, pkg):
+    """north_star item 4: the significant-pair lists of a sharded scan are the only per-pair data that crosses ranks."""
+    import torch.multiprocessing as mp
+    L = 100
+    out = str(tmp_path / "hits%d.npz")
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_hits_worker, args=(2, port, L, out), nprocs=2, join=True)
+    cov, null, mask = _hits_case(po, oracle, L)
+    want = oracle.hitlist(cov, null, mask, int(mask.sum()), L * (L - 1) // 2 - int(mask.sum()), -1, 5.0)
+    assert len(want["i"]) > 3
+    for rank in range(2):
+        z = np.load(out % rank)
+        assert int(z["nhit"]) == len(want["i"])
+        for k in ("i", "j", "sc", "eval", "pval"):
+            assert np.array_equal(z[k], want[k]), (rank, k)
+
+
+def test_merge_hit_lists_orders_row_major(pkg):
+    a = dict(i=np.array([5, 0]), j=np.array([9, 3]), sc=np.array([1.0, 2.0]), eval=np.array([.1, .2]), pval=np.array([.01, .02]), nhit=2)
+    b = dict(i=np.array([0, 5]), j=np.array([2, 7]), sc=np.array([3.0, 4.0]), eval=np.array([.3, .4]), pval=np.array([.03, .04]), nhit=2)
+    m = pkg.parallel.merge_hit_lists([a, b])
+    assert list(zip(m["i"], m["j"])) == [(0, 2), (0, 3), (5, 7), (5, 9)] and list(m["sc"]) == [3.0, 2.0, 4.0, 1.0] and m["nhit"] == 4
+    e = pkg.parallel.merge_hit_lists([])
+    assert len(e["i"]) == 0 and e["nhit"] == 0
+    assert pkg.parallel.gather_hit_lists(a)["nhit"] == 2          # no process group: the rank's own list, ordered
+
+
 def test_shard_covers_every_replicate_once(pkg):
     for R in (1, 7, 100):
         for world in (1, 2, 4, 8):
