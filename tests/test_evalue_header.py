@@ -1,7 +1,7 @@
 """The score -> p-value function the E-value kernel runs (r-scape_b200/csrc/rsb_evalue.cuh, __host__ __device__) is compiled
 here with g++ and compared with the oracle's restatement of cov2evalue (src/covariation.c:2370-2400) -- which is itself
 pinned against the reference's own static function (tests/test_evalue_oracle.py) -- on scores that hit every branch, bin
-bounds included.  This checks the kernel's arithmetic on the CPU; the kernel itself is checked by tests/test_gpu_hits.py."""
+bounds included.  This checks the kernel's arithmetic on the CPU; the kernel itself is checked by tests/test_gpu_z_hits.py."""
 import ctypes as C
 import os
 import subprocess

@@ -99,65 +99,3 @@ def test_null_rscape_b200_matches_oracle_cumulative_ranklist(po, oracle):
     lib.esl_dmatrix_Destroy(apm)
     lib.corr_Destroy(mi)
 
-
-def test_cov_createhitlist_b200_matches_oracle(po, oracle):
-    """The per-pair loop of cov_CreateHitList (src/covariation.c:828-910) through the host mirror: mi->Eval and the list of
-    significant pairs from mi->COV and data->ranklist_null, against the oracle's loop run on the same mi->COV."""
-    lib = _lib(po)
-    glue = C.CDLL(os.path.join(ROOT, "oracle", "libglue_b200.so"))
-    vp, dp = C.c_void_p, C.POINTER(C.c_double)
-    glue.glue_hitlist.argtypes = [vp, vp, vp, vp, vp, vp, C.c_uint64, C.c_uint64, C.c_int, C.c_double, vp, C.c_int64,
-                                  vp, vp, vp, vp, vp, vp, vp]
-    N, L = 200, 70
-    msa, wgt, partner = po.synthetic_msa(N, L, seed=41)
-    P = L * (L - 1) // 2
-    ap = np.ascontiguousarray(po.ALLOWPAIR_WC_GU)
-    m = lib.glue_msa_create(N, L, msa.ctypes.data_as(C.POINTER(C.c_uint8)), wgt.ctypes.data_as(dp))
-    mi = lib.corr_Create(L, N, 0, 8, 50, lib.glue_abc_rna(), po.C16)
-    apm = lib.glue_allowpair_from(ap.ctypes.data_as(dp))
-    data = lib.glue_data_create(mi, apm, 4, 1e-6)                     # GTp
-    glue.glue_cov_calculate.argtypes = [vp, vp]
-    assert glue.glue_cov_calculate(data, m) == 0, lib.glue_data_errbuf(data)
-    cov = np.empty((L, L))
-    lib.glue_mi_export(mi, None, None, None, None, None, cov.ctypes.data_as(dp), None, None)
-
-    x = np.maximum(np.random.default_rng(4).normal(0, 6, 60000), -10 + 0.05)
-    b = np.ceil((x + 10) / 0.05 - 1).astype(np.int64)
-    null = po.NullFit(-10.0, 0.05, np.bincount(b, minlength=int(b.max()) + 6).astype(np.uint64), xmax=float(x.max())).exp_tail(0.05)
-    mask = np.zeros((L, L), np.uint8)
-    for i, j in enumerate(partner):
-        if j > i:
-            mask[i, j] = 1
-    Nb = int(mask.sum())
-
-    def run(thresh, expBP, use_mask, use_null=True, cap=P):
-        hi, hj = np.zeros(cap + 1, np.int64), np.zeros(cap + 1, np.int64)
-        sc, ev, pv = np.zeros(cap + 1), np.zeros(cap + 1), np.zeros(cap + 1)
-        E = np.zeros((L, L))
-        nhit = C.c_int64()
-        geom = np.array([null.bmin, null.w, null.xmax, null.phi])
-        ig = np.array([null.nb, null.imin, null.imax], np.int32)
-        st = glue.glue_hitlist(data, mi, geom.ctypes.data, ig.ctypes.data, null.obs.ctypes.data if use_null else None,
-                               null.survfit.ctypes.data, Nb if use_mask else 0, P - Nb if use_mask else P, expBP, thresh,
-                               mask.ctypes.data if use_mask else None, cap, hi.ctypes.data, hj.ctypes.data, sc.ctypes.data,
-                               ev.ctypes.data, pv.ctypes.data, E.ctypes.data, C.byref(nhit))
-        assert st == 0, lib.glue_data_errbuf(data)
-        k = min(nhit.value, cap)
-        return dict(i=hi[:k], j=hj[:k], sc=sc[:k], eval=ev[:k], pval=pv[:k], nhit=nhit.value, Eval=E)
-
-    iu = np.triu_indices(L, 1)
-    for thresh, expBP, use_mask in ((0.05, -1, True), (5.0, -1, False), (5.0, 6, True), (2000.0, -1, True)):
-        got = run(thresh, expBP, use_mask)
-        want = oracle.hitlist(cov, null, mask if use_mask else None, Nb if use_mask else 0, P - Nb if use_mask else P, expBP, thresh)
-        assert got["nhit"] == len(want["i"])
-        for k in ("i", "j", "sc", "eval", "pval"):
-            assert np.array_equal(got[k], want[k]), (thresh, expBP, k)
-        assert np.array_equal(got["Eval"][iu], want["Eval"][iu]) and np.array_equal(got["Eval"], got["Eval"].T)
-        assert np.isposinf(np.diag(got["Eval"])).all()
-    # without a null rank list every pair is listed with pval = eval = 0 (the naive method, :844-847)
-    naive = run(0.05, -1, False, use_null=False)
-    assert naive["nhit"] == P and not naive["eval"].any() and np.array_equal(naive["sc"], cov[iu])
-    lib.glue_data_destroy(data)
-    lib.esl_dmatrix_Destroy(apm)
-    lib.corr_Destroy(mi)
-    lib.glue_msa_destroy(m)
