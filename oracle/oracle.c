@@ -1044,3 +1044,40 @@ orc_hitlist(const double *cov, int L, const ORC_HIST *null, double phi, const do
     }
   return h;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Tree_Substitutions, src/msatree.c:1455-1540, on the rows left by the Fitch pass (all = [2N-1][L]: leaves 0..N-1, then
+ * internal node v at row N+v): per column the number of parent->child substitutions over the 2(N-1) branches, per pair
+ * i<j the number of branches on which both columns change (ndouble) / at least one does (njoin).  Without includegaps a
+ * branch only counts where parent and child residues are canonical in the column(s) concerned.
+ * nsubs int [L]; ndouble, njoin int [L][L] (entries i<j, the rest 0).  Any output may be NULL. */
+int
+orc_tree_substitutions(const ORC_TREE *T, const uint8_t *all, int L, int includegaps, int *nsubs, int *ndouble, int *njoin)
+{
+  int N = T->N, v, side, i, j;
+
+  if (nsubs)   memset(nsubs,   0, sizeof(int) * (size_t) L);
+  if (ndouble) memset(ndouble, 0, sizeof(int) * (size_t) L * (size_t) L);
+  if (njoin)   memset(njoin,   0, sizeof(int) * (size_t) L * (size_t) L);
+  for (v = 0; v < N - 1; v++)
+    for (side = 0; side < 2; side++) {
+      int            kid = side ? T->right[v] : T->left[v];
+      const uint8_t *ax  = all + (size_t) (N + v) * L;
+      const uint8_t *axk = (kid > 0) ? all + (size_t) (N + kid) * L : all + (size_t) (-kid) * L;
+      for (i = 0; i < L; i++) {
+        int oki = includegaps || (ax[i] < 4 && axk[i] < 4);
+        int chi = oki && axk[i] != ax[i];
+        if (nsubs && chi) nsubs[i]++;
+        if (!ndouble && !njoin) continue;
+        if (!oki) continue;
+        for (j = i + 1; j < L; j++) {
+          int okj = includegaps || (ax[j] < 4 && axk[j] < 4);
+          int chj = okj && axk[j] != ax[j];
+          if (!okj) continue;
+          if (ndouble && chi && chj)   ndouble[(size_t) i * L + j]++;
+          if (njoin   && (chi || chj)) njoin[(size_t) i * L + j]++;
+        }
+      }
+    }
+  return 0;
+}

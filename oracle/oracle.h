@@ -116,6 +116,9 @@ int  orc_null_simulate(ORC_RNG *r, const ORC_TREE *T, const double *Q, const uin
 int  orc_null_fitch_shuffle(ORC_RNG *r, const ORC_TREE *T, const uint8_t *msa, int L,
                             uint8_t *shmsa /* [N][L] */, uint8_t *allmsa /* [2N-1][L] or NULL */, int *fitch_sc);
 
+/* Tree_Substitutions after its Fitch call, src/msatree.c:1455-1540; all = [2N-1][L] as written by orc_null_fitch_shuffle */
+int  orc_tree_substitutions(const ORC_TREE *T, const uint8_t *all, int L, int includegaps, int *nsubs, int *ndouble, int *njoin);
+
 #ifdef __cplusplus
 }
 #endif

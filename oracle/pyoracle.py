@@ -157,6 +157,7 @@ class Oracle:
         L.orc_ptime.argtypes = [_dp, C.c_double, _dp]
         L.orc_null_simulate.argtypes = [C.c_void_p, C.POINTER(_Tree), _dp, _u8p, C.c_int, _u8p, _u8p]
         L.orc_null_fitch_shuffle.argtypes = [C.c_void_p, C.POINTER(_Tree), _u8p, C.c_int, _u8p, _u8p, _ip]
+        L.orc_tree_substitutions.argtypes = [C.POINTER(_Tree), _u8p, C.c_int, C.c_int, _ip, _ip, _ip]
 
     # ---- one scan -------------------------------------------------------------------------
     def scan(self, msa, wgt, stat=GT, covclass=C16, actype=APC, allowpair=None, tol=1e-6, want_probs=False):
@@ -298,6 +299,18 @@ class Oracle:
         return (sh, allm, sc.value) if want_all else sh
 
 
+    def tree_substitutions(self, tree, allmsa, includegaps=False):
+        """Tree_Substitutions after its Fitch pass (src/msatree.c:1455-1540) on allmsa [2N-1][L] -> (nsubs, ndouble, njoin)."""
+        allmsa = np.ascontiguousarray(allmsa, dtype=np.uint8)
+        assert allmsa.shape[0] == 2 * tree.N - 1
+        L = allmsa.shape[1]
+        ns, nd, nj = np.zeros(L, np.int32), np.zeros((L, L), np.int32), np.zeros((L, L), np.int32)
+        t = tree.cstruct()
+        st = self.lib.orc_tree_substitutions(C.byref(t), _u8(allmsa), L, 1 if includegaps else 0, _i(ns), _i(nd), _i(nj))
+        assert st == 0
+        return ns, nd, nj
+
+
 class RefLib:
     """The reference's own code (oracle/_ref/librscape_ref.so), driven through oracle/mi_glue.c."""
 
@@ -346,6 +359,20 @@ class RefLib:
         self.lib.esl_randomness_Destroy(r)
         self.lib.glue_tree_destroy(T)
         return outs
+
+    def tree_substitutions(self, seed, tree, msa, includegaps=False):
+        """The reference's Tree_Substitutions (its own Fitch pass on the shim's MT19937 stream seeded with `seed`)."""
+        msa = np.ascontiguousarray(msa, dtype=np.uint8)
+        N, L = msa.shape
+        T = self._tree(tree)
+        r = self.lib.esl_randomness_Create(seed)
+        ns, nd, nj = np.zeros(L, np.int32), np.zeros((L, L), np.int32), np.zeros((L, L), np.int32)
+        self.lib.glue_ref_tree_substitutions.argtypes = [C.c_void_p, C.c_void_p, C.c_int, _u8p, C.c_int, _ip, _ip, _ip]
+        st = self.lib.glue_ref_tree_substitutions(r, T, L, _u8(msa), 1 if includegaps else 0, _i(ns), _i(nd), _i(nj))
+        self.lib.esl_randomness_Destroy(r)
+        self.lib.glue_tree_destroy(T)
+        assert st == 0, st
+        return ns, nd, nj
 
     def simulate(self, seed, tree, Q, root, nrep=1):
         Q = np.ascontiguousarray(Q, dtype=np.float64)

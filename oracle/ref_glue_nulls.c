@@ -7,6 +7,7 @@
  *   glue_ref_simulate      : cov_GenerateAlignment (src/cov_simulate.c:61) with noss + noindels, as
  *                            R-scape-sim's SAMPLE_NAIVE path (src/R-scape-sim.c:967)
  *   glue_ref_ptime         : ratematrix_ConditionalsFromRate (src/ratematrix.c:185)
+ *   glue_ref_tree_substitutions : Tree_Substitutions (src/msatree.c:1423), the substitution counts behind R-scape's power
  * Randomness comes from the shim's MT19937 (easel_shim.c), the same stream oracle.c consumes,
  * so the restatement in oracle.c can be compared with the reference residue for residue.
  */
@@ -54,6 +55,25 @@ glue_ref_fitch_shuffle(ESL_RANDOMNESS *r, ESL_TREE *T, int L, const uint8_t *msa
     if (allmsa_flat) flatten(allmsa, 2 * T->N - 1, L, allmsa_flat);
   }
   esl_msa_Destroy(msa); esl_msa_Destroy(allmsa); esl_msa_Destroy(shmsa); free(usecol);
+  return status;
+}
+
+/* Tree_Substitutions (src/msatree.c:1423), Fitch pass included: nsubs int [L], ndouble / njoin int [L][L]; any may be NULL */
+int
+glue_ref_tree_substitutions(ESL_RANDOMNESS *r, ESL_TREE *T, int L, const uint8_t *msa_flat, int includegaps, int *nsubs, int *ndouble, int *njoin)
+{
+  ESL_MSA *msa = glue_msa_create(T->N, L, msa_flat, NULL);
+  char     errbuf[eslERRBUFSIZE];
+  int     *a = NULL, *b = NULL, *c = NULL, status;
+
+  status = Tree_Substitutions(r, msa, T, nsubs ? &a : NULL, ndouble ? &b : NULL, njoin ? &c : NULL, includegaps, errbuf, FALSE);
+  if (status == eslOK) {
+    if (nsubs)   memcpy(nsubs,   a, sizeof(int) * (size_t) L);
+    if (ndouble) memcpy(ndouble, b, sizeof(int) * (size_t) L * (size_t) L);
+    if (njoin)   memcpy(njoin,   c, sizeof(int) * (size_t) L * (size_t) L);
+  }
+  free(a); free(b); free(c);
+  esl_msa_Destroy(msa);
   return status;
 }
 

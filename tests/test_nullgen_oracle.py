@@ -88,3 +88,25 @@ def test_null_width_rule(oracle):
     assert oracle.null_width(0.05, -30.0, 90.0) == 0.05
     assert abs(oracle.null_width(0.05, -3.0, 5.0) - 8.0 / 400) < 1e-15
     assert oracle.null_width(0.05, 1.0, 1.0 + 1e-5) == 0.0
+
+
+@pytest.mark.parametrize("N,L,seed", [(12, 30, 21), (40, 26, 22), (2, 7, 23)])
+@pytest.mark.parametrize("includegaps", [False, True])
+def test_tree_substitutions_match_reference(po, oracle, reflib, N, L, seed, includegaps):
+    """Tree_Substitutions (src/msatree.c:1423-1554): the oracle's counts on its own Fitch rows equal the reference's, whose Fitch
+    pass consumes the same Mersenne-Twister stream."""
+    msa = po.synthetic_msa(N, L, seed=seed)[0]
+    tree = po.random_tree(N, np.random.default_rng(seed))
+    ref = reflib.tree_substitutions(seed, tree, msa, includegaps)
+    rng = oracle.rng(seed)
+    _, allm, _ = oracle.null_fitch_shuffle(rng, tree, msa, want_all=True)
+    oracle.rng_free(rng)
+    got = oracle.tree_substitutions(tree, allm, includegaps)
+    for a, b, name in zip(got, ref, ("nsubs", "ndouble", "njoin")):
+        assert np.array_equal(a, b), name
+    ns, nd, nj = got
+    iu = np.triu_indices(L, 1)
+    assert (nd[iu] <= np.minimum(ns[iu[0]], ns[iu[1]])).all()
+    if includegaps:                                     # every branch counts: |A or B| = |A| + |B| - |A and B|
+        assert np.array_equal(nj[iu], ns[iu[0]] + ns[iu[1]] - nd[iu])
+    assert (N == 2 or ns.sum() > 0) and not np.tril(nd).any() and not np.tril(nj).any()
