@@ -191,6 +191,19 @@ int rsb_null_hist_pool(rsb_ctx *ctx, int first_rep, int nrep, int stat, int covc
 int rsb_pool_get(rsb_ctx *ctx, int first_rep, int nrep, uint8_t *out);
 int rsb_pool_put(rsb_ctx *ctx, int first_rep, int nrep, const uint8_t *in);
 
+/* ---- substitution counts over the tree (input of the power calculation) ------------------------------ */
+/* Tree_Substitutions after its Fitch pass, src/msatree.c:1455-1540 (callers src/R-scape.c:2784-2840): the O(L^2 N) loops
+ * over all column pairs and branches run as the unweighted pair contraction over one row per branch.
+ * The context must be configured with nseq = 2 (ntaxa - 1) (one row per branch), alen = L and at least one replicate slot.
+ * Tree in Easel convention (see rsb_set_tree; only left / right are read); leaves uint8 [ntaxa][leaf_stride] = the alignment,
+ * internal uint8 [ntaxa-1][internal_stride] = the ancestral sequence of every internal node as reconstructed by
+ * Tree_FitchAlgorithmAncenstral (rows ntaxa.. of its allmsa, src/msatree.c:173-227), which stays with the caller: its random
+ * tie-breaking belongs to the caller's RNG stream.
+ * nsubs int [L]; ndouble, njoin int [L][L] with the entries i<j filled and the rest 0, as the reference leaves them.
+ * Any of the three may be NULL (the contraction is skipped when only nsubs is asked for). */
+int rsb_tree_substitutions(rsb_ctx *ctx, int ntaxa, const int *left, const int *right, const uint8_t *leaves, int64_t leaf_stride,
+                           const uint8_t *internal, int64_t internal_stride, int includegaps, int *nsubs, int *ndouble, int *njoin);
+
 /* ---- instrumentation ------------------------------------------------------------------------------ */
 /* kernels launched by this context so far; device milliseconds spent in the gram kernel and number of
  * gram launches since the last call with reset != 0 (CUDA events on the context's stream). */

@@ -96,6 +96,12 @@ extern int        cov_CreateHitList_b200(struct data_s *data, struct mutual_s *m
                                          HITLIST **ret_hitlist);
 extern void       cov_FreeHitList(HITLIST *hitlist);
 
+/* Tree_Substitutions (src/msatree.c:1423-1554) from its Fitch reconstruction on: allmsa holds the 2N-1 rows written by
+ * Tree_FitchAlgorithmAncenstral (:1451; leaves first, internal node v at row N+v).  Same outputs and allocation as the
+ * reference (nsubs int[alen]; ndouble, njoin int[alen*alen], entries i<j), computed on the device. */
+extern int        Tree_Substitutions_b200(ESL_MSA *msa, ESL_MSA *allmsa, ESL_TREE *T, int **ret_nsubs, int **ret_ndouble, int **ret_njoin,
+                                          int includegaps, char *errbuf, int verbose);
+
 #ifdef __cplusplus
 }
 #endif

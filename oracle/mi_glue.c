@@ -158,6 +158,24 @@ glue_hitlist(struct data_s *data, struct mutual_s *mi, const double *geom, const
   cov_FreeHitList(hl);
   return eslOK;
 }
+/* drive Tree_Substitutions_b200 from flat arrays: all = [2N-1][L] rows of the Fitch reconstruction */
+int
+glue_tree_substitutions(int N, const int *left, const int *right, int L, const uint8_t *all, int includegaps, int want_pairs,
+                        int *nsubs, int *ndouble, int *njoin, char *errbuf)
+{
+  ESL_TREE *T = esl_tree_Create(N);
+  ESL_MSA  *msa = glue_msa_create(N, L, all, NULL), *allmsa = glue_msa_create(2 * N - 1, L, all, NULL);
+  int      *a = NULL, *b = NULL, *c = NULL, v, status;
+  for (v = 0; v < N - 1; v++) { T->left[v] = left[v]; T->right[v] = right[v]; }
+  status = Tree_Substitutions_b200(msa, allmsa, T, &a, want_pairs ? &b : NULL, want_pairs ? &c : NULL, includegaps, errbuf, 0);
+  if (status == eslOK) {
+    memcpy(nsubs, a, sizeof(int) * (size_t) L);
+    if (want_pairs) { memcpy(ndouble, b, sizeof(int) * (size_t) L * L); memcpy(njoin, c, sizeof(int) * (size_t) L * L); }
+  }
+  free(a); free(b); free(c);
+  esl_msa_Destroy(msa); esl_msa_Destroy(allmsa); esl_tree_Destroy(T);
+  return status;
+}
 double glue_data_w(struct data_s *d) { return d->w; }
 int    glue_cov_calculate(struct data_s *d, ESL_MSA *msa) { return cov_CalculateCOV(d, msa); }
 #endif

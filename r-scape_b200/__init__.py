@@ -71,6 +71,7 @@ def lib():
         L.rsb_scan_hits.argtypes = [_vp, C.POINTER(NullFitStruct), _u8p, C.c_uint64, C.c_uint64, C.c_int, C.c_double, _dp, C.c_int64,
                                     _i64p, _i64p, _dp, _dp, _dp, _i64p]
         L.rsb_load_scores.argtypes = [_vp, _dp]
+        L.rsb_tree_substitutions.argtypes = [_vp, C.c_int, _ip, _ip, _u8p, C.c_int64, _u8p, C.c_int64, C.c_int, _ip, _ip, _ip]
         L.rsb_set_shard.argtypes = [_vp, C.c_int, C.c_int]
         L.rsb_sharded_counts.argtypes = [_vp, _vp, C.c_int64, C.c_int, C.c_double, _dp]
         L.rsb_sharded_counts_pool.argtypes = [_vp, C.c_int, C.c_double, _dp]
@@ -226,6 +227,22 @@ class Context:
                                      C.byref(n)))
         k = min(n.value, cap)
         return dict(i=hi[:k].copy(), j=hj[:k].copy(), sc=sc[:k].copy(), eval=he[:k].copy(), pval=hp[:k].copy(), nhit=n.value, Eval=ev)
+
+    def tree_substitutions(self, left, right, leaves, internal, includegaps=False, want_pairs=True):
+        """Tree_Substitutions after its Fitch pass (src/msatree.c:1455-1540) -> (nsubs [L], ndouble [L][L], njoin [L][L]).
+        The context must be configured with nseq = 2 (ntaxa - 1) rows (one per branch)."""
+        leaves = np.ascontiguousarray(leaves, dtype=np.uint8)
+        internal = np.ascontiguousarray(internal, dtype=np.uint8)
+        ntaxa, L = leaves.shape
+        assert internal.shape == (ntaxa - 1, L) and L == self.L
+        lf, rt = np.ascontiguousarray(left, dtype=np.int32), np.ascontiguousarray(right, dtype=np.int32)
+        ns = np.empty(L, np.int32)
+        nd = np.empty((L, L), np.int32) if want_pairs else None
+        nj = np.empty((L, L), np.int32) if want_pairs else None
+        ip = lambda a: None if a is None else a.ctypes.data_as(_ip)
+        self._ck(lib().rsb_tree_substitutions(self._h, ntaxa, ip(lf), ip(rt), leaves.ctypes.data_as(_u8p), L, internal.ctypes.data_as(_u8p), L,
+                                              1 if includegaps else 0, ip(ns), ip(nd), ip(nj)))
+        return ns, nd, nj
 
     # ---- one scan with the pair grid sharded over ranks ------------------------------------------
     def set_shard(self, rank, world):

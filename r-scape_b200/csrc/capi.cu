@@ -56,6 +56,10 @@ cudaError_t rsb_launch_evalue_hits(const double *cov, int L, int Lp, const rsb_n
                                    double expBP, long long switch_n, double thresh, int report_all, int sr, int sw, double *eval, long long cap,
                                    long long *hit_ij, double *hit_sc, double *hit_eval, double *hit_pval, unsigned long long *nhit, int *flags,
                                    cudaStream_t st);
+cudaError_t rsb_launch_branch_rows(const uint8_t *leaves, const uint8_t *internal, const int *left, const int *right, int ntaxa, int L,
+                                   int includegaps, uint8_t *rows, cudaStream_t st);
+cudaError_t rsb_launch_nsubs(const uint8_t *rows, int nrows, int L, int *nsubs, cudaStream_t st);
+cudaError_t rsb_launch_subs_tables(const long long *cnt, int L, int Lp, int *ndouble, int *njoin, cudaStream_t st);
 cudaError_t rsb_launch_null_simulate(const int *left, const int *right, const int *order, const int *level_start_host, int nlevels,
                                      const unsigned long long *pthr, int N, int L, const uint8_t *root,
                                      const uint8_t *gapmask, unsigned long long seed, unsigned long long id0, int first_rep, int nrep,
@@ -1257,6 +1261,62 @@ int rsb_scan_hits(rsb_ctx *ctx, const rsb_nullfit *null, const uint8_t *pairmask
 done:
 #undef HITS_OK
   cudaFree(d_csum); cudaFree(d_n); cudaFree(d_ij); cudaFree(d_hd); cudaFree(d_surv); cudaFree(d_mask); cudaFree(d_eval);
+  return rc;
+}
+
+/* Tree_Substitutions after its Fitch pass, src/msatree.c:1455-1540: one row per branch, then the unweighted pair contraction */
+int rsb_tree_substitutions(rsb_ctx *ctx, int ntaxa, const int *left, const int *right, const uint8_t *leaves, int64_t leaf_stride,
+                           const uint8_t *internal, int64_t internal_stride, int includegaps, int *nsubs, int *ndouble, int *njoin)
+{
+  RSB_CUDA_OK(cudaSetDevice(ctx->device));
+  const int nrows = 2 * (ntaxa - 1);
+  if (ntaxa < 2 || !left || !right || !leaves || !internal) { rsb_set_error(ctx, "rsb_tree_substitutions: bad arguments"); return 1; }
+  if (ctx->N != nrows || ctx->Rcap < 1) {
+    rsb_set_error(ctx, "rsb_tree_substitutions: the context must be configured for one row per branch: nseq = 2 (ntaxa - 1) = %d (it is %d)", nrows, ctx->N);
+    return 1;
+  }
+  if (nrows > 65535) { rsb_set_error(ctx, "rsb_tree_substitutions: more than 65535 branches"); return 1; }
+  if (ctx->shard_world > 1) { rsb_set_error(ctx, "rsb_tree_substitutions is not offered on a sharded pair grid"); return 1; }
+  for (int v = 0; v < ntaxa - 1; v++) {
+    const int kids[2] = { left[v], right[v] };
+    for (int k : kids)
+      if (k >= ntaxa - 1 || -k >= ntaxa || k == v) { rsb_set_error(ctx, "rsb_tree_substitutions: node %d has child %d outside the tree", v, k); return 1; }
+  }
+  const size_t L = ctx->L;
+  uint8_t *d_leaves = nullptr, *d_internal = nullptr;
+  int *d_lr = nullptr, *d_ns = nullptr, *d_tab = nullptr;
+  int rc = 1;
+  const bool pairs = (ndouble || njoin);
+#define TS_OK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    rsb_set_error(ctx, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); goto done; } } while (0)
+  TS_OK(cudaMalloc(&d_leaves, (size_t) ntaxa * L));
+  TS_OK(cudaMalloc(&d_internal, (size_t) (ntaxa - 1) * L));
+  TS_OK(cudaMalloc(&d_lr, sizeof(int) * 2 * (size_t) (ntaxa - 1)));
+  TS_OK(cudaMalloc(&d_ns, sizeof(int) * L));
+  if (pairs) TS_OK(cudaMalloc(&d_tab, sizeof(int) * 2 * L * L));
+  TS_OK(cudaMemcpy2DAsync(d_leaves, L, leaves, (size_t) leaf_stride, L, (size_t) ntaxa, cudaMemcpyHostToDevice, ctx->stream));
+  TS_OK(cudaMemcpy2DAsync(d_internal, L, internal, (size_t) internal_stride, L, (size_t) (ntaxa - 1), cudaMemcpyHostToDevice, ctx->stream));
+  TS_OK(cudaMemcpyAsync(d_lr, left, sizeof(int) * (size_t) (ntaxa - 1), cudaMemcpyHostToDevice, ctx->stream));
+  TS_OK(cudaMemcpyAsync(d_lr + (ntaxa - 1), right, sizeof(int) * (size_t) (ntaxa - 1), cudaMemcpyHostToDevice, ctx->stream));
+  TS_OK(rsb_launch_branch_rows(d_leaves, d_internal, d_lr, d_lr + (ntaxa - 1), ntaxa, ctx->L, includegaps, ctx->d_res, ctx->stream));   // replicate slot 0
+  ctx->launches++;
+  if (nsubs) {
+    TS_OK(rsb_launch_nsubs(ctx->d_res, nrows, ctx->L, d_ns, ctx->stream));
+    ctx->launches++;
+    TS_OK(cudaMemcpyAsync(nsubs, d_ns, sizeof(int) * L, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  if (pairs) {
+    if (enqueue_counts(ctx, 1, 0, 1, ctx->d_res, ctx->stream)) goto done;                  // unit weights: the counts are plain integers
+    TS_OK(rsb_launch_subs_tables(ctx->d_cnt, ctx->L, ctx->Lp, ndouble ? d_tab : nullptr, njoin ? d_tab + L * L : nullptr, ctx->stream));
+    ctx->launches++;
+    if (ndouble) TS_OK(cudaMemcpyAsync(ndouble, d_tab, sizeof(int) * L * L, cudaMemcpyDeviceToHost, ctx->stream));
+    if (njoin)   TS_OK(cudaMemcpyAsync(njoin, d_tab + L * L, sizeof(int) * L * L, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  TS_OK(cudaStreamSynchronize(ctx->stream));
+  rc = 0;
+done:
+#undef TS_OK
+  cudaFree(d_leaves); cudaFree(d_internal); cudaFree(d_lr); cudaFree(d_ns); cudaFree(d_tab);
   return rc;
 }
 
