@@ -217,14 +217,20 @@ class Context:
         pm = None if pairmask is None else np.ascontiguousarray(pairmask, dtype=np.uint8)
         assert pm is None or pm.shape == (self.L, self.L)
         P = self.L * (self.L - 1) // 2
-        cap = P if cap is None else int(cap)
         ev = np.empty((self.L, self.L)) if want_eval else None
-        hi, hj = np.empty(max(cap, 1), np.int64), np.empty(max(cap, 1), np.int64)
-        sc, he, hp = np.empty(max(cap, 1)), np.empty(max(cap, 1)), np.empty(max(cap, 1))
-        n = C.c_int64()
-        self._ck(lib().rsb_scan_hits(self._h, C.byref(nf), None if pm is None else pm.ctypes.data_as(_u8p), int(Nb), int(Nt), int(expBP),
-                                     float(thresh), _d(ev), cap, hi.ctypes.data_as(_i64p), hj.ctypes.data_as(_i64p), _d(sc), _d(he), _d(hp),
-                                     C.byref(n)))
+        # cap None: lists are short unless every pair is reported; start small and repeat the call once if the list is longer
+        retry = cap is None
+        cap = (P if thresh > 1000 else min(P, 1 << 16)) if cap is None else int(cap)
+        while True:
+            hi, hj = np.empty(max(cap, 1), np.int64), np.empty(max(cap, 1), np.int64)
+            sc, he, hp = np.empty(max(cap, 1)), np.empty(max(cap, 1)), np.empty(max(cap, 1))
+            n = C.c_int64()
+            self._ck(lib().rsb_scan_hits(self._h, C.byref(nf), None if pm is None else pm.ctypes.data_as(_u8p), int(Nb), int(Nt), int(expBP),
+                                         float(thresh), _d(ev), cap, hi.ctypes.data_as(_i64p), hj.ctypes.data_as(_i64p), _d(sc), _d(he), _d(hp),
+                                         C.byref(n)))
+            if not retry or n.value <= cap:
+                break
+            cap, retry = n.value, False
         k = min(n.value, cap)
         return dict(i=hi[:k].copy(), j=hj[:k].copy(), sc=sc[:k].copy(), eval=he[:k].copy(), pval=hp[:k].copy(), nhit=n.value, Eval=ev)
 

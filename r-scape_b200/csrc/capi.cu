@@ -1213,7 +1213,6 @@ int rsb_scan_hits(rsb_ctx *ctx, const rsb_nullfit *null, const uint8_t *pairmask
   }
   nv.bmin = null->bmin; nv.w = null->w; nv.xmax = null->xmax; nv.phi = null->phi; nv.Nc = (double) null->Nc;
   nv.nb = null->nb; nv.imin = null->imin; nv.imax = null->imax; nv.csum = d_csum; nv.survfit = d_surv;
-  ij.resize((size_t) dcap); hd.resize(3 * (size_t) dcap);
 
   for (int pass = 0; pass < 2; pass++) {
     HITS_OK(cudaMemsetAsync(d_n, 0, sizeof(unsigned long long), ctx->stream));
@@ -1224,10 +1223,11 @@ int rsb_scan_hits(rsb_ctx *ctx, const rsb_nullfit *null, const uint8_t *pairmask
     HITS_OK(cudaMemcpyAsync(&n_dev, d_n, sizeof(n_dev), cudaMemcpyDeviceToHost, ctx->stream));
     if (check_flags(ctx, "cov_CreateHitList")) goto done;                                   // synchronises the stream
     const size_t kept = (size_t) std::min<unsigned long long>(n_dev, cap > 0 ? (unsigned long long) dcap : 0ull);
-    if (kept) {
+    if (kept) {                                                                             // host staging: [kept] keys + 3 x [kept] doubles
+      ij.resize(kept); hd.resize(3 * kept);
       HITS_OK(cudaMemcpyAsync(ij.data(), d_ij, sizeof(long long) * kept, cudaMemcpyDeviceToHost, ctx->stream));
       for (int f = 0; f < 3; f++)
-        HITS_OK(cudaMemcpyAsync(hd.data() + f * (size_t) dcap, d_hd + f * (size_t) dcap, sizeof(double) * kept, cudaMemcpyDeviceToHost, ctx->stream));
+        HITS_OK(cudaMemcpyAsync(hd.data() + f * kept, d_hd + f * (size_t) dcap, sizeof(double) * kept, cudaMemcpyDeviceToHost, ctx->stream));
       HITS_OK(cudaStreamSynchronize(ctx->stream));
     }
     if (pass == 1 || expBP <= 0) break;
@@ -1248,8 +1248,8 @@ int rsb_scan_hits(rsb_ctx *ctx, const rsb_nullfit *null, const uint8_t *pairmask
       const size_t s = idx[k];
       hit_i[k] = ij[s] >> 32; hit_j[k] = ij[s] & 0xffffffffll;
       if (hit_sc)   hit_sc[k]   = hd[s];
-      if (hit_eval) hit_eval[k] = hd[(size_t) dcap + s];
-      if (hit_pval) hit_pval[k] = hd[2 * (size_t) dcap + s];
+      if (hit_eval) hit_eval[k] = hd[kept + s];
+      if (hit_pval) hit_pval[k] = hd[2 * kept + s];
     }
     if (nhit) *nhit = (int64_t) n_dev;
     if (eval) {
@@ -1280,7 +1280,9 @@ int rsb_tree_substitutions(rsb_ctx *ctx, int ntaxa, const int *left, const int *
   for (int v = 0; v < ntaxa - 1; v++) {
     const int kids[2] = { left[v], right[v] };
     for (int k : kids)
-      if (k >= ntaxa - 1 || -k >= ntaxa || k == v) { rsb_set_error(ctx, "rsb_tree_substitutions: node %d has child %d outside the tree", v, k); return 1; }
+      if (k >= ntaxa - 1 || -k >= ntaxa || (k > 0 && k <= v)) {            // k <= 0 is leaf -k; internal children come after their parent
+        rsb_set_error(ctx, "rsb_tree_substitutions: node %d has child %d outside the tree", v, k); return 1;
+      }
   }
   const size_t L = ctx->L;
   uint8_t *d_leaves = nullptr, *d_internal = nullptr;

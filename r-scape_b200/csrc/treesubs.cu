@@ -72,8 +72,12 @@ cudaError_t rsb_launch_nsubs(const uint8_t *rows, int nrows, int L, int *nsubs, 
 {
   cudaError_t e = cudaMemsetAsync(nsubs, 0, sizeof(int) * (size_t) L, st);
   if (e != cudaSuccess) return e;
-  const int ny = nrows < 64 ? (nrows < 1 ? 1 : nrows) : 64;
-  nsubs_kernel<<<dim3((L + 127) / 128, ny), 128, 0, st>>>(rows, nrows, L, nsubs);
+  // few columns, many rows: split the rows over enough blocks to fill the chip (148 SMs x 8 blocks of 128 threads)
+  const int nbx = (L + 127) / 128;
+  int ny = (148 * 8 + nbx - 1) / nbx;
+  if (ny > nrows) ny = nrows;
+  if (ny < 1) ny = 1;
+  nsubs_kernel<<<dim3(nbx, ny), 128, 0, st>>>(rows, nrows, L, nsubs);
   return cudaGetLastError();
 }
 
