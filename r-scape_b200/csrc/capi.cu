@@ -57,8 +57,7 @@ cudaError_t rsb_launch_evalue_hits(const double *cov, int L, int Lp, const rsb_n
                                    long long *hit_ij, double *hit_sc, double *hit_eval, double *hit_pval, unsigned long long *nhit, int *flags,
                                    cudaStream_t st);
 cudaError_t rsb_launch_branch_rows(const uint8_t *leaves, const uint8_t *internal, const int *left, const int *right, int ntaxa, int L,
-                                   int includegaps, uint8_t *rows, cudaStream_t st);
-cudaError_t rsb_launch_nsubs(const uint8_t *rows, int nrows, int L, int *nsubs, cudaStream_t st);
+                                   int includegaps, uint8_t *rows, int *nsubs, cudaStream_t st);
 cudaError_t rsb_launch_subs_tables(const long long *cnt, int L, int Lp, int *ndouble, int *njoin, cudaStream_t st);
 cudaError_t rsb_launch_null_simulate(const int *left, const int *right, const int *order, const int *level_start_host, int nlevels,
                                      const unsigned long long *pthr, int N, int L, const uint8_t *root,
@@ -1300,13 +1299,9 @@ int rsb_tree_substitutions(rsb_ctx *ctx, int ntaxa, const int *left, const int *
   TS_OK(cudaMemcpy2DAsync(d_internal, L, internal, (size_t) internal_stride, L, (size_t) (ntaxa - 1), cudaMemcpyHostToDevice, ctx->stream));
   TS_OK(cudaMemcpyAsync(d_lr, left, sizeof(int) * (size_t) (ntaxa - 1), cudaMemcpyHostToDevice, ctx->stream));
   TS_OK(cudaMemcpyAsync(d_lr + (ntaxa - 1), right, sizeof(int) * (size_t) (ntaxa - 1), cudaMemcpyHostToDevice, ctx->stream));
-  TS_OK(rsb_launch_branch_rows(d_leaves, d_internal, d_lr, d_lr + (ntaxa - 1), ntaxa, ctx->L, includegaps, ctx->d_res, ctx->stream));   // replicate slot 0
+  TS_OK(rsb_launch_branch_rows(d_leaves, d_internal, d_lr, d_lr + (ntaxa - 1), ntaxa, ctx->L, includegaps, ctx->d_res, d_ns, ctx->stream));   // replicate slot 0
   ctx->launches++;
-  if (nsubs) {
-    TS_OK(rsb_launch_nsubs(ctx->d_res, nrows, ctx->L, d_ns, ctx->stream));
-    ctx->launches++;
-    TS_OK(cudaMemcpyAsync(nsubs, d_ns, sizeof(int) * L, cudaMemcpyDeviceToHost, ctx->stream));
-  }
+  if (nsubs) TS_OK(cudaMemcpyAsync(nsubs, d_ns, sizeof(int) * L, cudaMemcpyDeviceToHost, ctx->stream));
   if (pairs) {
     if (enqueue_counts(ctx, 1, 0, 1, ctx->d_res, ctx->stream)) goto done;                  // unit weights: the counts are plain integers
     TS_OK(rsb_launch_subs_tables(ctx->d_cnt, ctx->L, ctx->Lp, ndouble ? d_tab : nullptr, njoin ? d_tab + L * L : nullptr, ctx->stream));

@@ -9,38 +9,61 @@
 // those rows -- the very tcgen05 contraction of the scan with unit weights -- holds the answers:
 //     ndouble[i][j] = C[0,0]                    both columns substituted on the branch (:1496-1500)
 //     njoin[i][j]   = C[0,0] + C[0,1] + C[1,0]  counted in both columns and at least one substituted (:1522-1526)
-// Counts are integers, so the result is exact.  The three small kernels here build the rows, count the single-column
-// substitutions (nsubs, :1462-1476) and pick the two tables out of the count planes.
+// Counts are integers, so the result is exact.  The two small kernels here build the rows (counting the single-column
+// substitutions, nsubs, :1462-1476, on the way) and pick the two tables out of the count planes.
 #include "rsb_common.cuh"
 
 namespace {
 
-// rows[e][c] for branch e = 2 v + side (side 0 = left child of internal node v, 1 = right child).
-// leaves [N][L], internal [N-1][L] (row v = ancestral sequence of node v from the Fitch pass).
-__global__ void __launch_bounds__(256)
-branch_rows_kernel(const uint8_t *__restrict__ leaves, const uint8_t *__restrict__ internal, const int *__restrict__ left,
-                   const int *__restrict__ right, int L, int includegaps, uint8_t *__restrict__ rows)
+// rows[e][c] for branch e = 2 v + side (side 0 = left child of internal node v, 1 = right child), and nsubs[c] = number of
+// rows with code 0 in column c (:1462-1476).  leaves [N][L], internal [N-1][L] (row v = ancestral sequence of node v from the
+// Fitch pass).  A thread owns 4 consecutive columns (one 32-bit word when VEC) of BR_ROWS consecutive branches, keeps the four
+// substitution counts in registers and adds them to nsubs once.
+constexpr int BR_ROWS = 64, BR_THREADS = 128;
+
+__device__ __forceinline__ unsigned branch_code(unsigned p, unsigned x, int includegaps)
 {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x, e = blockIdx.y;
-  if (c >= L) return;
-  const int v = e >> 1, kid = (e & 1) ? right[v] : left[v];
-  const uint8_t p = internal[(size_t) v * L + c];
-  const uint8_t x = (kid > 0) ? internal[(size_t) kid * L + c] : leaves[(size_t) (-kid) * L + c];     // Easel: child <= 0 is leaf -child
-  uint8_t code;
-  if (includegaps) code = (x != p) ? 0 : 1;
-  else             code = (p < RSB_K && x < RSB_K) ? ((x != p) ? 0 : 1) : 4;
-  rows[(size_t) e * L + c] = code;
+  if (includegaps) return (x != p) ? 0u : 1u;
+  return (p < RSB_K && x < RSB_K) ? ((x != p) ? 0u : 1u) : 4u;
 }
 
-// nsubs[c] = number of rows with code 0 in column c; blockIdx.y strides over the rows
-__global__ void __launch_bounds__(128)
-nsubs_kernel(const uint8_t *__restrict__ rows, int nrows, int L, int *__restrict__ nsubs)
+template <bool VEC>
+__global__ void __launch_bounds__(BR_THREADS)
+branch_rows_kernel(const uint8_t *__restrict__ leaves, const uint8_t *__restrict__ internal, const int *__restrict__ left,
+                   const int *__restrict__ right, int L, int nrows, int includegaps, uint8_t *__restrict__ rows, int *__restrict__ nsubs)
 {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= L) return;
-  int n = 0;
-  for (int e = blockIdx.y; e < nrows; e += gridDim.y) n += (rows[(size_t) e * L + c] == 0);
-  if (n) atomicAdd(&nsubs[c], n);
+  const int c0 = (blockIdx.x * BR_THREADS + threadIdx.x) * 4;
+  if (c0 >= L) return;
+  const int e0 = blockIdx.y * BR_ROWS, e1 = (e0 + BR_ROWS < nrows) ? e0 + BR_ROWS : nrows;
+  int cnt[4] = { 0, 0, 0, 0 };
+  for (int e = e0; e < e1; e++) {
+    const int v = e >> 1, kid = (e & 1) ? right[v] : left[v];                      // the same for the whole block
+    const uint8_t *pp = internal + (size_t) v * L + c0;
+    const uint8_t *xp = ((kid > 0) ? internal + (size_t) kid * L : leaves + (size_t) (-kid) * L) + c0;   // Easel: child <= 0 is leaf -child
+    uint8_t *out = rows + (size_t) e * L + c0;
+    if (VEC) {                                                                     // L % 4 == 0: rows are word-aligned
+      const unsigned p = *reinterpret_cast<const unsigned *>(pp), x = *reinterpret_cast<const unsigned *>(xp);
+      unsigned w = 0;
+      #pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const unsigned code = branch_code((p >> (8 * k)) & 0xffu, (x >> (8 * k)) & 0xffu, includegaps);
+        w |= code << (8 * k);
+        cnt[k] += (code == 0u);
+      }
+      *reinterpret_cast<unsigned *>(out) = w;
+    } else {
+      #pragma unroll
+      for (int k = 0; k < 4; k++)
+        if (c0 + k < L) {
+          const unsigned code = branch_code(pp[k], xp[k], includegaps);
+          out[k] = (uint8_t) code;
+          cnt[k] += (code == 0u);
+        }
+    }
+  }
+  #pragma unroll
+  for (int k = 0; k < 4; k++)
+    if (cnt[k] && c0 + k < L) atomicAdd(&nsubs[c0 + k], cnt[k]);
 }
 
 // the two pair tables out of the count planes (plane a*4+b, upper triangle): int [L][L], entries i<j, the rest 0 (:1484-1485)
@@ -61,23 +84,16 @@ subs_tables_kernel(const long long *__restrict__ cnt, int L, int Lp, int *__rest
 
 } // namespace
 
+// rows + nsubs (int [L], zeroed here) in one pass over the reconstruction
 cudaError_t rsb_launch_branch_rows(const uint8_t *leaves, const uint8_t *internal, const int *left, const int *right, int ntaxa, int L,
-                                   int includegaps, uint8_t *rows, cudaStream_t st)
+                                   int includegaps, uint8_t *rows, int *nsubs, cudaStream_t st)
 {
-  branch_rows_kernel<<<dim3((L + 255) / 256, 2 * (ntaxa - 1)), 256, 0, st>>>(leaves, internal, left, right, L, includegaps, rows);
-  return cudaGetLastError();
-}
-
-cudaError_t rsb_launch_nsubs(const uint8_t *rows, int nrows, int L, int *nsubs, cudaStream_t st)
-{
+  const int nrows = 2 * (ntaxa - 1);
   cudaError_t e = cudaMemsetAsync(nsubs, 0, sizeof(int) * (size_t) L, st);
   if (e != cudaSuccess) return e;
-  // few columns, many rows: split the rows over enough blocks to fill the chip (148 SMs x 8 blocks of 128 threads)
-  const int nbx = (L + 127) / 128;
-  int ny = (148 * 8 + nbx - 1) / nbx;
-  if (ny > nrows) ny = nrows;
-  if (ny < 1) ny = 1;
-  nsubs_kernel<<<dim3(nbx, ny), 128, 0, st>>>(rows, nrows, L, nsubs);
+  const dim3 grid((L + 4 * BR_THREADS - 1) / (4 * BR_THREADS), (nrows + BR_ROWS - 1) / BR_ROWS);
+  if (L % 4 == 0) branch_rows_kernel<true><<<grid, BR_THREADS, 0, st>>>(leaves, internal, left, right, L, nrows, includegaps, rows, nsubs);
+  else            branch_rows_kernel<false><<<grid, BR_THREADS, 0, st>>>(leaves, internal, left, right, L, nrows, includegaps, rows, nsubs);
   return cudaGetLastError();
 }
 
