@@ -220,7 +220,7 @@ class Context:
         ev = np.empty((self.L, self.L)) if want_eval else None
         # cap None: lists are short unless every pair is reported; start small and repeat the call once if the list is longer
         retry = cap is None
-        cap = (P if thresh > 1000 else min(P, 1 << 16)) if cap is None else int(cap)
+        cap = (P if (thresh > 1000 or expBP > 0) else min(P, 1 << 16)) if cap is None else int(cap)
         while True:
             hi, hj = np.empty(max(cap, 1), np.int64), np.empty(max(cap, 1), np.int64)
             sc, he, hp = np.empty(max(cap, 1)), np.empty(max(cap, 1)), np.empty(max(cap, 1))

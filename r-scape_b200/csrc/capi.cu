@@ -1131,19 +1131,24 @@ int rsb_scan_hist(rsb_ctx *ctx, const uint8_t *pairmask, double w, double bmin, 
   if (nb < 1 || !(w > 0.0)) { rsb_set_error(ctx, "bad histogram geometry"); return 1; }
   const size_t L = ctx->L;
   unsigned long long *d3 = nullptr; uint8_t *dmask = nullptr;
-  RSB_CUDA_OK(cudaMalloc(&d3, sizeof(unsigned long long) * 3 * (size_t) nb));
-  RSB_CUDA_OK(cudaMemsetAsync(d3, 0, sizeof(unsigned long long) * 3 * (size_t) nb, ctx->stream));
+  int rc = 1;
+#define SH_OK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    rsb_set_error(ctx, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); goto done; } } while (0)
+  SH_OK(cudaMalloc(&d3, sizeof(unsigned long long) * 3 * (size_t) nb));
+  SH_OK(cudaMemsetAsync(d3, 0, sizeof(unsigned long long) * 3 * (size_t) nb, ctx->stream));
   if (pairmask) {
-    RSB_CUDA_OK(cudaMalloc(&dmask, L * L));
-    RSB_CUDA_OK(cudaMemcpyAsync(dmask, pairmask, L * L, cudaMemcpyHostToDevice, ctx->stream));
+    SH_OK(cudaMalloc(&dmask, L * L));
+    SH_OK(cudaMemcpyAsync(dmask, pairmask, L * L, cudaMemcpyHostToDevice, ctx->stream));
   }
-  RSB_CUDA_OK(rsb_launch_hist3(ctx->d_cov, ctx->L, ctx->Lp, dmask, bmin, w, nb, d3, d3 + nb, d3 + 2 * (size_t) nb, ctx->d_flags, ctx->stream));
+  SH_OK(rsb_launch_hist3(ctx->d_cov, ctx->L, ctx->Lp, dmask, bmin, w, nb, d3, d3 + nb, d3 + 2 * (size_t) nb, ctx->d_flags, ctx->stream));
   ctx->launches++;
-  if (ha) RSB_CUDA_OK(cudaMemcpyAsync(ha, d3, sizeof(uint64_t) * nb, cudaMemcpyDeviceToHost, ctx->stream));
-  if (hb) RSB_CUDA_OK(cudaMemcpyAsync(hb, d3 + nb, sizeof(uint64_t) * nb, cudaMemcpyDeviceToHost, ctx->stream));
-  if (ht) RSB_CUDA_OK(cudaMemcpyAsync(ht, d3 + 2 * (size_t) nb, sizeof(uint64_t) * nb, cudaMemcpyDeviceToHost, ctx->stream));
-  const int rc = check_flags(ctx, "cov_SignificantPairs_Ranking");
-  cudaFree(d3); if (dmask) cudaFree(dmask);
+  if (ha) SH_OK(cudaMemcpyAsync(ha, d3, sizeof(uint64_t) * nb, cudaMemcpyDeviceToHost, ctx->stream));
+  if (hb) SH_OK(cudaMemcpyAsync(hb, d3 + nb, sizeof(uint64_t) * nb, cudaMemcpyDeviceToHost, ctx->stream));
+  if (ht) SH_OK(cudaMemcpyAsync(ht, d3 + 2 * (size_t) nb, sizeof(uint64_t) * nb, cudaMemcpyDeviceToHost, ctx->stream));
+  rc = check_flags(ctx, "cov_SignificantPairs_Ranking");
+done:
+#undef SH_OK
+  cudaFree(d3); cudaFree(dmask);
   return rc;
 }
 

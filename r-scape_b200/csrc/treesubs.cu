@@ -17,9 +17,9 @@ namespace {
 
 // rows[e][c] for branch e = 2 v + side (side 0 = left child of internal node v, 1 = right child), and nsubs[c] = number of
 // rows with code 0 in column c (:1462-1476).  leaves [N][L], internal [N-1][L] (row v = ancestral sequence of node v from the
-// Fitch pass).  A thread owns 4 consecutive columns (one 32-bit word when VEC) of BR_ROWS consecutive branches, keeps the four
+// Fitch pass).  A thread owns 4 consecutive columns (one 32-bit word when VEC) of `rpb` consecutive branches, keeps the four
 // substitution counts in registers and adds them to nsubs once.
-constexpr int BR_ROWS = 64, BR_THREADS = 128;
+constexpr int BR_THREADS = 128;
 
 __device__ __forceinline__ unsigned branch_code(unsigned p, unsigned x, int includegaps)
 {
@@ -30,11 +30,12 @@ __device__ __forceinline__ unsigned branch_code(unsigned p, unsigned x, int incl
 template <bool VEC>
 __global__ void __launch_bounds__(BR_THREADS)
 branch_rows_kernel(const uint8_t *__restrict__ leaves, const uint8_t *__restrict__ internal, const int *__restrict__ left,
-                   const int *__restrict__ right, int L, int nrows, int includegaps, uint8_t *__restrict__ rows, int *__restrict__ nsubs)
+                   const int *__restrict__ right, int L, int nrows, int rpb, int includegaps, uint8_t *__restrict__ rows,
+                   int *__restrict__ nsubs)
 {
   const int c0 = (blockIdx.x * BR_THREADS + threadIdx.x) * 4;
   if (c0 >= L) return;
-  const int e0 = blockIdx.y * BR_ROWS, e1 = (e0 + BR_ROWS < nrows) ? e0 + BR_ROWS : nrows;
+  const int e0 = blockIdx.y * rpb, e1 = (e0 + rpb < nrows) ? e0 + rpb : nrows;
   int cnt[4] = { 0, 0, 0, 0 };
   for (int e = e0; e < e1; e++) {
     const int v = e >> 1, kid = (e & 1) ? right[v] : left[v];                      // the same for the whole block
@@ -91,9 +92,13 @@ cudaError_t rsb_launch_branch_rows(const uint8_t *leaves, const uint8_t *interna
   const int nrows = 2 * (ntaxa - 1);
   cudaError_t e = cudaMemsetAsync(nsubs, 0, sizeof(int) * (size_t) L, st);
   if (e != cudaSuccess) return e;
-  const dim3 grid((L + 4 * BR_THREADS - 1) / (4 * BR_THREADS), (nrows + BR_ROWS - 1) / BR_ROWS);
-  if (L % 4 == 0) branch_rows_kernel<true><<<grid, BR_THREADS, 0, st>>>(leaves, internal, left, right, L, nrows, includegaps, rows, nsubs);
-  else            branch_rows_kernel<false><<<grid, BR_THREADS, 0, st>>>(leaves, internal, left, right, L, nrows, includegaps, rows, nsubs);
+  // rows per block: 64 when that still gives the 148 SMs a few blocks each, fewer (down to 8) for short alignments
+  const int nbx = (L + 4 * BR_THREADS - 1) / (4 * BR_THREADS);
+  int rpb = (int) (((long long) nrows * nbx) / (148 * 4));
+  rpb = rpb > 64 ? 64 : (rpb < 8 ? 8 : rpb);
+  const dim3 grid(nbx, (nrows + rpb - 1) / rpb);
+  if (L % 4 == 0) branch_rows_kernel<true><<<grid, BR_THREADS, 0, st>>>(leaves, internal, left, right, L, nrows, rpb, includegaps, rows, nsubs);
+  else            branch_rows_kernel<false><<<grid, BR_THREADS, 0, st>>>(leaves, internal, left, right, L, nrows, rpb, includegaps, rows, nsubs);
   return cudaGetLastError();
 }
 

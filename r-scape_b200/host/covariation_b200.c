@@ -323,8 +323,9 @@ cov_CreateHitList_b200(struct data_s *data, struct mutual_s *mi, RANKLIST *rankl
     nf.xmax = null->ha->xmax; nf.phi = null->ha->phi; nf.Nc = null->ha->Nc; nf.obs = null->ha->obs; nf.survfit = null->survfit;
     /* the hit list reads whatever mi->COV holds now (:845) */
     if (rsb_load_scores(ctx, mi->COV->mx[0]) != 0) { snprintf(data->errbuf, eslERRBUFSIZE, "%s", rsb_error(ctx)); goto ERROR; }
-    /* first call: count the hits and fill mi->Eval; second call: fetch them (lists are short unless every pair is reported) */
-    cap = all ? P : 4096;
+    /* lists are short unless every pair is reported: start with room for 4096 hits and repeat the call once if there are more
+     * (the expBP rule needs its whole first-pass list, so it starts with room for every pair) */
+    cap = (all || data->expBP > 0) ? P : 4096;
     for (;;) {
       free(hi); free(hj); free(sc); free(ev); free(pv);
       hi = malloc(sizeof(int64_t) * (size_t) (cap + 1)); hj = malloc(sizeof(int64_t) * (size_t) (cap + 1));
