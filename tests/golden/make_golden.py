@@ -10,6 +10,9 @@
                                       alignments: every statistic x class x correction on one small alignment, used
                                       to pin the oracle wherever oracle/_ref is not available (e.g. the GPU box)
 
+  tests/golden/ref_evalues.npz        the reference's static cov2evalue / evalue2cov on a seeded null histogram (with / without a tail)
+  tests/golden/ref_treesubs.npz       the reference's Tree_Substitutions on a seeded alignment + tree
+
 Usage: python tests/golden/make_golden.py   (needs /root/reference and a built oracle/_ref)
 """
 import json
@@ -62,6 +65,32 @@ def main():
     for k in ("pp", "pm", "ps", "nseff", "ngap"):
         out["probs_" + k] = r[k]
     np.savez_compressed(os.path.join(HERE, "ref_scans.npz"), **out)
+
+    # E-values: the reference's own static cov2evalue / evalue2cov (src/covariation.c:2370-2435, reached through
+    # oracle/ref_glue_evalue.c) on a seeded null histogram, without and with a fitted tail
+    rng = np.random.default_rng(7)
+    x = np.maximum(rng.gamma(2.0, 2.5, 100000) - 8.0, -10 + 0.05)
+    b = np.ceil((x + 10) / 0.05 - 1).astype(np.int64)
+    obs = np.bincount(b, minlength=int(b.max()) + 6).astype(np.uint64)
+    plain = po.NullFit(-10.0, 0.05, obs, xmax=float(x.max()))
+    fit = plain.exp_tail(0.05)
+    scores = np.concatenate([rng.uniform(-13, plain.bmin + plain.w * (2 * plain.nb + 4), 600), plain.bmin + plain.w * np.arange(0, 2 * plain.nb + 2, 7)])
+    ev = dict(obs=obs, xmax=plain.xmax, phi=fit.phi, cmin=fit.cmin, survfit=fit.survfit, scores=scores,
+              thresholds=np.array([1e-6, 1e-3, 0.05, 1.0, 10.0, 1e4]))
+    for name, null in (("plain", plain), ("fit", fit)):
+        for Nc in (1, 1225):
+            ev[f"{name}_cov2evalue_{Nc}"] = np.array([ref.cov2evalue(v, null, Nc) for v in scores])
+            ev[f"{name}_evalue2cov_{Nc}"] = np.array([ref.evalue2cov(e, null, Nc) for e in ev["thresholds"]])
+    np.savez_compressed(os.path.join(HERE, "ref_evalues.npz"), **ev)
+
+    # Tree_Substitutions (src/msatree.c:1423-1554, its own Fitch pass on the shim's MT19937 stream)
+    msa = po.synthetic_msa(36, 40, seed=77)[0]
+    tree = po.random_tree(36, np.random.default_rng(77))
+    ts = dict(msa=msa, left=tree.left, right=tree.right, parent=tree.parent, ld=tree.ld, rd=tree.rd, seed=77)
+    for g in (0, 1):
+        ns, nd, nj = ref.tree_substitutions(77, tree, msa, bool(g))
+        ts[f"nsubs_{g}"], ts[f"ndouble_{g}"], ts[f"njoin_{g}"] = ns, nd, nj
+    np.savez_compressed(os.path.join(HERE, "ref_treesubs.npz"), **ts)
     print("wrote", sorted(os.listdir(HERE)))
 
 

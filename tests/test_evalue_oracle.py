@@ -91,3 +91,18 @@ def test_hitlist_loop(po, oracle):
         assert np.array_equal(got["eval"], [w_[3] for w_ in want]) and np.array_equal(got["pval"], [w_[4] for w_ in want])
         assert np.isinf(np.diag(got["Eval"])).all()
     assert len(oracle.hitlist(cov, null, mask, Nb, Nt, 0, 2000.0)["i"]) == L * (L - 1) // 2      # -E > MAX_EVAL reports all pairs
+
+
+def test_evalues_match_committed_reference_outputs(po, oracle):
+    """tests/golden/ref_evalues.npz holds outputs of the reference's static cov2evalue / evalue2cov (made by
+    tests/golden/make_golden.py from oracle/_ref), so the pin also holds where /root/reference never existed."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_evalues.npz"))
+    plain = po.NullFit(-10.0, 0.05, z["obs"], xmax=float(z["xmax"]))
+    fit = po.NullFit(-10.0, 0.05, z["obs"], float(z["xmax"]), float(z["phi"]), int(z["cmin"]), z["survfit"])
+    for name, null in (("plain", plain), ("fit", fit)):
+        for Nc in (1, 1225):
+            got = np.array([oracle.cov2evalue(v, null, Nc) for v in z["scores"]])
+            assert np.array_equal(got, z[f"{name}_cov2evalue_{Nc}"]), (name, Nc)
+            got = np.array([oracle.evalue2cov(e, null, Nc) for e in z["thresholds"]])
+            assert np.array_equal(got, z[f"{name}_evalue2cov_{Nc}"]), (name, Nc)

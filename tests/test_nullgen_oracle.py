@@ -110,3 +110,17 @@ def test_tree_substitutions_match_reference(po, oracle, reflib, N, L, seed, incl
     if includegaps:                                     # every branch counts: |A or B| = |A| + |B| - |A and B|
         assert np.array_equal(nj[iu], ns[iu[0]] + ns[iu[1]] - nd[iu])
     assert (N == 2 or ns.sum() > 0) and not np.tril(nd).any() and not np.tril(nj).any()
+
+
+def test_tree_substitutions_match_committed_reference_outputs(po, oracle):
+    """tests/golden/ref_treesubs.npz: the reference's Tree_Substitutions on a seeded alignment and tree (made by
+    tests/golden/make_golden.py from oracle/_ref)."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_treesubs.npz"))
+    tree = po.Tree(z["left"], z["right"], z["parent"], z["ld"], z["rd"])
+    rng = oracle.rng(int(z["seed"]))
+    _, allm, _ = oracle.null_fitch_shuffle(rng, tree, z["msa"], want_all=True)
+    oracle.rng_free(rng)
+    for g in (0, 1):
+        ns, nd, nj = oracle.tree_substitutions(tree, allm, bool(g))
+        assert np.array_equal(ns, z[f"nsubs_{g}"]) and np.array_equal(nd, z[f"ndouble_{g}"]) and np.array_equal(nj, z[f"njoin_{g}"])
