@@ -242,3 +242,40 @@ def test_cov_createhitlist_b200_matches_oracle(po, oracle):
     lib.esl_dmatrix_Destroy(apm)
     lib.corr_Destroy(mi)
     lib.glue_msa_destroy(m)
+
+
+def test_significant_pairs_identical_end_to_end(ctx, pkg, po, oracle):
+    """north_star: "the set of significant pairs called is identical when the same null alignments are supplied".
+    Whole chain on both sides from the same input alignment and the same nulls: width pass, null scans, cumulative histogram,
+    scan of the input alignment, E-values, hit list.  The device's histogram bins equal the oracle's, so both sides see the same
+    null distribution; the scores agree to 1e-9, so they fall in the same bins and the calls are the same."""
+    from test_gpu_nulls import oracle_null_loop
+    N, L, R = 180, 80, 6
+    msa, wgt, partner = po.synthetic_msa(N, L, seed=123)
+    nulls = np.stack([po.synthetic_msa(N, L, seed=900 + r)[0] for r in range(R)])
+    mask = np.zeros((L, L), np.uint8)
+    for i, j in enumerate(partner):
+        if j > i:
+            mask[i, j] = 1
+    Nb, P = int(mask.sum()), L * (L - 1) // 2
+    # reference side (oracle)
+    w_ref, view, mm_ref = oracle_null_loop(po, oracle, nulls, wgt, po.GT, po.C16, po.APC)
+    ref_scan = oracle.scan(msa, wgt, po.GT, po.C16, po.APC)
+    ref_null = po.NullFit(view.bmin, view.w, view.obs, xmax=view.xmax).exp_tail(0.05)
+    ref_hits = oracle.hitlist(ref_scan["cov"], ref_null, mask, Nb, P - Nb, -1, 0.5)
+    # device side
+    ctx.configure(N, L, 2, 0)
+    ctx.set_weights(wgt)
+    w, _, _ = ctx.null_width(nulls[0])
+    mm = ctx.null_hist(nulls, w)
+    dev_scan = ctx.scan(msa, pkg.GT, pkg.C16, pkg.APC)
+    bins, n, imax = ctx.hist_read(view.nb)
+    assert np.array_equal(bins, view.obs) and n == view.n
+    xmax = max(float(mm[:, 1].max()), -10.0 + w)
+    dev_null = po.NullFit(-10.0, w, bins, xmax=xmax).exp_tail(0.05)           # the same host-side "fit" on the device's histogram
+    assert np.array_equal(dev_null.survfit, ref_null.survfit) or abs(w - w_ref) > 0
+    dev_hits = ctx.scan_hits(-10.0, w, bins, xmax, P - Nb, Nb, mask, dev_null.survfit, dev_null.phi, thresh=0.5)
+    assert len(ref_hits["i"]) >= 3
+    assert np.array_equal(dev_hits["i"], ref_hits["i"]) and np.array_equal(dev_hits["j"], ref_hits["j"])
+    assert np.allclose(dev_hits["eval"], ref_hits["eval"], rtol=1e-6, atol=0)
+    assert np.max(np.abs(dev_hits["sc"] - ref_hits["sc"]) / np.maximum(1.0, np.abs(ref_hits["sc"]))) < 1e-8   # 1e-9 of the raw scale: test_gpu_scan_parity
