@@ -60,3 +60,15 @@ def test_product_does_not_reference_the_oracle():
             if f.endswith((".c", ".cu", ".cuh", ".h", ".py")) or f == "Makefile":
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "pyoracle" not in txt and "liboracle" not in txt and "oracle.h" not in txt and "../oracle" not in txt, os.path.join(dirpath, f)
+
+
+def test_headers_compile_as_c_and_cxx(tmp_path):
+    """include/*.h are usable from a C and from a C++ translation unit (extern "C" guards, no C++-only or C-only constructs)."""
+    import subprocess
+    inc = [f"-I{os.path.join(ROOT, 'include')}", f"-I{os.path.join(ROOT, 'include', 'easel_compat')}"]
+    body = '#include "rscape_b200.h"\n#include "rscape_b200_host.h"\n' \
+           'int probe(void) { rsb_nullfit nf; HITLIST hl; nf.nb = 0; hl.nhit = 0; return nf.nb + hl.nhit + (int) sizeof(struct mutual_s); }\n'
+    for name, cc, std in (("t.c", "gcc", "-std=c99"), ("t.cpp", "g++", "-std=c++17")):
+        src = tmp_path / name
+        src.write_text(body)
+        subprocess.run([cc, std, "-Wall", "-Werror", "-c", str(src), "-o", str(tmp_path / (name + ".o"))] + inc, check=True)
