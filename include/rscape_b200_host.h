@@ -95,6 +95,8 @@ extern int        null_rscape_b200(struct data_s *data, ESL_MSA **nulls, int nnu
 extern int        cov_CreateHitList_b200(struct data_s *data, struct mutual_s *mi, RANKLIST *ranklist, const uint8_t *pairmask,
                                          HITLIST **ret_hitlist);
 extern void       cov_FreeHitList(HITLIST *hitlist);
+/* pair mask (uint8 [alen][alen], entries i<j) of the base pairs of a ct array in Easel's convention (1-based, 0 = unpaired) */
+extern int        cov_PairMaskFromCT(const int *ct, int64_t alen, uint8_t *pairmask);
 
 /* Tree_Substitutions (src/msatree.c:1423-1554) from its Fitch reconstruction on: allmsa holds the 2N-1 rows written by
  * Tree_FitchAlgorithmAncenstral (:1451; leaves first, internal node v at row N+v).  Same outputs and allocation as the

@@ -276,6 +276,23 @@ null_rscape_b200(struct data_s *data, ESL_MSA **nulls, int nnull, int hpts, RANK
 }
 
 /* ------------------------------------------------------------------ E-values and the significant-pair list */
+/* The structure's base pairs as the pair mask of rsb_scan_hist / cov_CreateHitList_b200.  ct is data->ct in Easel's convention
+ * (esl_wuss2ct: indices 1..alen, ct[i] = j and ct[j] = i for a pair, 0 = unpaired; ct[0] unused).  Replaces, for a structure
+ * given as SS_cons, the per-pair CMAP_IsBPLocal / CMAP_GetBPTYPE scans of src/covariation.c:437-456 and :832-840. */
+int
+cov_PairMaskFromCT(const int *ct, int64_t alen, uint8_t *pairmask)
+{
+  int64_t i, j;
+  memset(pairmask, 0, (size_t) alen * (size_t) alen);
+  for (i = 1; i <= alen; i++) {
+    j = ct[i];
+    if (j == 0) continue;
+    if (j < 1 || j > alen || j == i || ct[j] != i) return eslFAIL;      /* not a consistent pairing */
+    if (i < j) pairmask[(size_t) (i - 1) * (size_t) alen + (size_t) (j - 1)] = 1;
+  }
+  return eslOK;
+}
+
 void
 cov_FreeHitList(HITLIST *hitlist)
 {

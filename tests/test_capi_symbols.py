@@ -72,3 +72,21 @@ def test_headers_compile_as_c_and_cxx(tmp_path):
         src = tmp_path / name
         src.write_text(body)
         subprocess.run([cc, std, "-Wall", "-Werror", "-c", str(src), "-o", str(tmp_path / (name + ".o"))] + inc, check=True)
+
+
+def test_pair_mask_from_ct(pkg):
+    """cov_PairMaskFromCT: the base pairs of a ct array (Easel convention) as the pair mask the histogram / hit-list stages take."""
+    import numpy as np
+    host = C.CDLL(pkg.HOST_LIB_PATH)
+    host.cov_PairMaskFromCT.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
+    L = 12
+    ct = np.zeros(L + 1, np.int32)
+    for i, j in ((1, 12), (2, 11), (4, 8)):
+        ct[i], ct[j] = j, i
+    mask = np.full((L, L), 7, np.uint8)
+    assert host.cov_PairMaskFromCT(ct.ctypes.data, L, mask.ctypes.data) == 0
+    want = np.zeros((L, L), np.uint8)
+    want[0, 11] = want[1, 10] = want[3, 7] = 1
+    assert np.array_equal(mask, want)
+    ct[5] = 9                                            # 9 does not point back
+    assert host.cov_PairMaskFromCT(ct.ctypes.data, L, mask.ctypes.data) != 0
