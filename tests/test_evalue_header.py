@@ -72,3 +72,34 @@ def test_header_small_histograms(po, oracle, hdr):
         got, nbad = _pvals(hdr, x, null)
         want = np.array([oracle.cov2evalue(v, null, 1) for v in x])
         assert nbad == 0 and np.array_equal(got, want)
+
+
+def test_header_random_histograms(po, oracle, hdr):
+    """Random small histograms (1 to 40 bins, sparse bins, tails starting anywhere) and scores on and around every bin bound:
+    the kernel's p-value function, the oracle and -- when built -- the reference's own cov2evalue agree bit for bit."""
+    ref = po.RefLib() if po.RefLib.available() else None
+    rng = np.random.default_rng(0)
+    ncmp = 0
+    for trial in range(120):
+        nb = int(rng.integers(1, 40))
+        w = float(rng.choice([0.05, 0.5, 1e-3, 2.0]))
+        bmin = float(rng.choice([-10.0, 0.0, -3.3]))
+        obs = np.zeros(nb, np.uint64)
+        k = int(rng.integers(1, nb + 1))
+        obs[rng.choice(nb, k, replace=False)] = rng.integers(1, 1000, k).astype(np.uint64)
+        null = po.NullFit(bmin, w, obs)
+        null = po.NullFit(bmin, w, obs, xmax=bmin + w * (null.imax + float(rng.uniform(0.01, 1.0))))
+        if rng.random() < 0.6:
+            cmin = int(rng.integers(null.imin, null.imax + 1))
+            surv = np.zeros(2 * nb)
+            surv[cmin:] = np.sort(rng.uniform(0, 0.3, 2 * nb - cmin))[::-1]
+            null = po.NullFit(bmin, w, obs, null.xmax, bmin + w * cmin, cmin, surv)
+        x = np.concatenate([rng.uniform(bmin - 2 * w, bmin + w * (2 * nb + 3), 40), bmin + w * np.arange(-1, 2 * nb + 3)])
+        got, nbad = _pvals(hdr, x, null)
+        assert nbad == 0
+        want = np.array([oracle.cov2evalue(v, null, 1) for v in x])
+        assert np.array_equal(got, want), trial
+        if ref is not None:
+            assert np.array_equal(want, np.array([ref.cov2evalue(v, null, 1) for v in x])), trial
+        ncmp += len(x)
+    assert ncmp > 5000
