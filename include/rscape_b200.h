@@ -190,6 +190,10 @@ int rsb_null_hist_pool(rsb_ctx *ctx, int first_rep, int nrep, int stat, int covc
 /* copy pool entries to / from the host: uint8 [nrep][nseq][alen] (e.g. for --outnull, or host-made nulls scanned repeatedly) */
 int rsb_pool_get(rsb_ctx *ctx, int first_rep, int nrep, uint8_t *out);
 int rsb_pool_put(rsb_ctx *ctx, int first_rep, int nrep, const uint8_t *in);
+/* parity tests: the internal-node rows of generator A for pool entries [first_rep, first_rep + nrep), uint8 [nrep][nseq-1][alen]:
+ * which = 0 the Fitch reconstruction (Tree_FitchAlgorithmAncenstral's rows nseq.. of allmsa, src/msatree.c:173-227),
+ * which = 1 the shuffled rows (msamanip_ShuffleTreeSubstitutions' allmsa, src/msamanip.c:1449-1531) */
+int rsb_pool_get_internal(rsb_ctx *ctx, int which, int first_rep, int nrep, uint8_t *out);
 
 /* ---- substitution counts over the tree (input of the power calculation) ------------------------------ */
 /* Tree_Substitutions after its Fitch pass, src/msatree.c:1455-1540 (callers src/R-scape.c:2784-2840): the O(L^2 N) loops

@@ -90,6 +90,7 @@ def lib():
         L.rsb_pool_reserve.argtypes = [_vp, C.c_int]
         L.rsb_pool_get.argtypes = [_vp, C.c_int, C.c_int, _u8p]
         L.rsb_pool_put.argtypes = [_vp, C.c_int, C.c_int, _u8p]
+        L.rsb_pool_get_internal.argtypes = [_vp, C.c_int, C.c_int, C.c_int, _u8p]
         L.rsb_hist_reset.argtypes = [_vp]
         L.rsb_hist_exchange.argtypes = [_vp, C.c_void_p, C.c_int, C.c_int]
         L.rsb_hist_read.argtypes = [_vp, _u64p, C.c_int, _u64p, _ip]
@@ -382,6 +383,12 @@ class Context:
     def pool_get(self, nrep, first_rep=0):
         out = np.empty((nrep, self.N, self.L), dtype=np.uint8)
         self._ck(lib().rsb_pool_get(self._h, first_rep, nrep, out.ctypes.data_as(_u8p)))
+        return out
+
+    def pool_get_internal(self, which, nrep, first_rep=0):
+        """Generator A's internal-node rows [nrep][N-1][L]: which = 0 Fitch reconstruction, 1 shuffled rows (parity tests)."""
+        out = np.empty((nrep, self.N - 1, self.L), dtype=np.uint8)
+        self._ck(lib().rsb_pool_get_internal(self._h, which, first_rep, nrep, out.ctypes.data_as(_u8p)))
         return out
 
     def pool_put(self, nulls, first_rep=0):

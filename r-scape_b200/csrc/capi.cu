@@ -1593,6 +1593,19 @@ int rsb_pool_get(rsb_ctx *ctx, int first_rep, int nrep, uint8_t *out)
   return 0;
 }
 
+int rsb_pool_get_internal(rsb_ctx *ctx, int which, int first_rep, int nrep, uint8_t *out)
+{
+  RSB_CUDA_OK(cudaSetDevice(ctx->device));
+  if (pool_range_ok(ctx, first_rep, nrep)) return 1;
+  const uint8_t *src = (which == 0) ? ctx->d_anc : (which == 1) ? ctx->d_shanc : nullptr;
+  if (!src) { rsb_set_error(ctx, "rsb_pool_get_internal: generator A has not run (or bad selector %d)", which); return 1; }
+  const size_t rb = (size_t) (ctx->N - 1) * ctx->L;
+  if (pool_wait(ctx, first_rep, nrep, ctx->stream)) return 1;
+  RSB_CUDA_OK(cudaMemcpyAsync(out, src + first_rep * rb, rb * nrep, cudaMemcpyDeviceToHost, ctx->stream));
+  RSB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
 int rsb_pool_put(rsb_ctx *ctx, int first_rep, int nrep, const uint8_t *in)
 {
   RSB_CUDA_OK(cudaSetDevice(ctx->device));

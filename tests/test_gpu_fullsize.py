@@ -55,6 +55,39 @@ def test_full_size_counts_and_properties(ctx, pkg, po, oracle, name):
     assert n == L * (L - 1) // 2 == int(bins.sum())
 
 
+@pytest.mark.parametrize("name", ["trna", "rnasep"])
+def test_whole_config_against_the_oracle(ctx, pkg, po, oracle, name):
+    """BASELINE configs 1 and 2 are small enough for the CPU oracle to scan WHOLE (0.03 s and 3 s): every score of the full
+    alignment, pm, nseff, min/max and the null histogram's integer bins against the oracle (double weights), not only a slice."""
+    from _helpers import assert_bins_identical
+    N, L = SHAPES[name]
+    msa, wgt, _ = pkg.synth.synthetic_msa(N, L, seed=42)
+    ctx.configure(N, L, 2, 0)
+    ctx.set_weights(wgt)
+    got = ctx.scan(msa, pkg.GT, pkg.C16, pkg.APC, want_probs=True)
+    ref = oracle.scan(msa, wgt, po.GT, po.C16, po.APC, want_probs=True)
+    raw = oracle.scan(msa, wgt, po.GT, po.C16, po.NOCORR)
+    scale = max(abs(raw["maxcov"]), abs(raw["mincov"]), 1.0)
+    iu = np.triu_indices(L, 1)
+    assert np.max(np.abs(got["cov"][iu] - ref["cov"][iu])) <= 1e-9 * scale
+    assert np.max(np.abs(got["cov"].T[iu] - ref["cov"][iu])) <= 1e-9 * scale
+    assert abs(got["mincov"] - ref["mincov"]) <= 1e-9 * scale and abs(got["maxcov"] - ref["maxcov"]) <= 1e-9 * scale
+    for k in ("pm", "ps", "nseff", "pp"):
+        assert np.max(np.abs(got[k] - ref[k])) <= 1e-9 * max(1.0, np.max(np.abs(ref[k]))), k
+    # the same alignment as a "null": width, then the histogram's integer bins
+    w_ref = oracle.null_width(0.05, ref["mincov"], ref["maxcov"], -10.0, 400, 1e-6)
+    w, mn, mx = ctx.null_width(msa)
+    assert abs(w - w_ref) <= 1e-12 * max(1.0, w_ref)
+    h = oracle.hist_from_cov(ref["cov"], ref["maxcov"], -10.0, w_ref, 1e-6)
+    v = oracle.view(h)
+    oracle.free(h)
+    ctx.hist_reset()
+    ctx.null_hist(msa[None], w_ref, want_minmax=False)
+    bins, n, imax = ctx.hist_read(v.nb + 8)
+    assert n == L * (L - 1) // 2 == v.n
+    assert_bins_identical(bins, v.obs, ref["cov"][iu], -10.0, w_ref, scale=scale)
+
+
 @pytest.mark.parametrize("nslices", [4, 5])
 def test_ssu_slice_scores_match_oracle(ctx, pkg, po, oracle, nslices):
     """Scores of a full-size scan cannot be compared pair by pair with an oracle run on a slice (pm and APC depend on all

@@ -103,6 +103,146 @@ def test_fitch_shuffle_distribution_matches_oracle(ctx, pkg, po, oracle):
         assert abs(a - b) <= 0.08 * max(1.0, abs(b)) + 0.5, (qt, a, b)
 
 
+def _branch_tables(tree, leaves, internal, N):
+    """5x5 table of (parent residue, child residue) over the columns of every branch, residues <= 4 only
+    (the substitution counts of shuffle_tree_substitutions, src/msamanip.c:1634-1646): int [2(N-1)][25]"""
+    rows = np.concatenate([leaves, internal])                                # [2N-1][L]: leaves 0..N-1, node v at N + v
+    par = np.repeat(np.arange(N - 1) + N, 2)
+    kid = np.stack([tree.left, tree.right], 1).ravel()
+    kid = np.where(kid > 0, kid + N, -kid)
+    out = np.zeros((2 * (N - 1), 25), np.int64)
+    step = max(1, (1 << 24) // max(1, rows.shape[1]))
+    for b0 in range(0, len(par), step):
+        pa, kd = rows[par[b0:b0 + step]], rows[kid[b0:b0 + step]]
+        ok = (pa <= 4) & (kd <= 4)
+        code = np.where(ok, pa.astype(np.int64) * 5 + kd, 25)
+        for c in range(25):
+            out[b0:b0 + step, c] = (code == c).sum(1)
+    return out
+
+
+def _check_generator_a_invariants(ctx, tree, msa, R):
+    """What shuffle_tree_substitutions keeps exactly, whatever the random stream: on every branch of every replicate the
+    5x5 substitution table of the shuffled rows equals that of the Fitch rows (msamanip.c:1634-1646, 1718-1757); the
+    shuffled root row is a permutation of the Fitch root row (msamanip_ShuffleColumns, :1164-1233); leaves hold residues
+    and gaps only."""
+    N, L = msa.shape
+    out = ctx.pool_get(R)
+    anc, shanc = ctx.pool_get_internal(0, R), ctx.pool_get_internal(1, R)
+    assert out.max() <= 4 and anc.max() <= 4 and shanc.max() <= 4
+    off = ~np.eye(5, dtype=bool).ravel()
+    for r in range(R):
+        assert np.array_equal(np.bincount(anc[r][0], minlength=5), np.bincount(shanc[r][0], minlength=5))
+        want = _branch_tables(tree, msa, anc[r], N)
+        got = _branch_tables(tree, out[r], shanc[r], N)
+        # substitutions (off-diagonal cells) are reproduced exactly; N in a leaf of the input is not a substitution (:1639)
+        assert np.array_equal(got[:, off], want[:, off]), np.argwhere(got[:, off] != want[:, off])[:5]
+    return out, anc, shanc
+
+
+@pytest.mark.parametrize("N,L,kernel", [(48, 92, "<4,seg>"), (40, 120, "<4,seg>"), (24, 4096, "<4,ballot>"), (48, 90, "<1,ballot>")])
+def test_fitch_shuffle_exact_invariants_every_kernel_variant(ctx, po, N, L, kernel):
+    """The replay kernel variant depends on L (nullgen.cu: L % 4 == 0 && L <= 4092 -> segment form, L % 4 == 0 -> word/ballot,
+    else byte/ballot); every BASELINE shape takes the first.  Exact invariants on each."""
+    R = 6
+    msa, wgt, tree = _setup(ctx, po, N, L, 21, R)
+    ctx.null_fitch_shuffle(msa, seed=13, nrep=R)
+    out, anc, shanc = _check_generator_a_invariants(ctx, tree, msa, R)
+    assert not np.array_equal(out[0], out[1])
+
+
+@pytest.mark.parametrize("N,L", [(48, 92), (40, 120)])
+def test_fitch_shuffle_distribution_matches_oracle_word_kernels(ctx, pkg, po, oracle, N, L):
+    """The KS battery of test_fitch_shuffle_distribution_matches_oracle at L % 4 == 0, i.e. on the kernels every BASELINE
+    shape runs: fitch_up/down_level_kernel<4> and replay_level_row_kernel<4, segment form>."""
+    R = 24
+    msa, wgt, tree = _setup(ctx, po, N, L, 7, R)
+    ctx.null_fitch_shuffle(msa, seed=11, nrep=R)
+    gpu = ctx.pool_get(R)
+    rng = oracle.rng(11)
+    cpu = np.stack([oracle.null_fitch_shuffle(rng, tree, msa) for _ in range(R)])
+    oracle.rng_free(rng)
+    comp_g = np.stack([(gpu == a).mean(axis=(1, 2)) for a in range(5)])
+    comp_c = np.stack([(cpu == a).mean(axis=(1, 2)) for a in range(5)])
+    assert np.max(np.abs(comp_g.mean(1) - comp_c.mean(1))) < 0.01
+    seqcomp_g = np.stack([(gpu == a).mean(axis=2).mean(axis=0) for a in range(5)])
+    seqcomp_c = np.stack([(cpu == a).mean(axis=2).mean(axis=0) for a in range(5)])
+    assert np.max(np.abs(seqcomp_g - seqcomp_c)) < 0.03
+    i, j = np.triu_indices(N, 1)
+    pairdiff = lambda x: np.concatenate([(x[r][i] != x[r][j]).sum(1) for r in range(R)])
+    assert ks_stat(pairdiff(gpu), pairdiff(cpu)) < 0.05
+    iu = np.triu_indices(L, 1)
+    scores = lambda x: np.concatenate([oracle.scan(x[r], wgt, po.GT, po.C16, po.APC)["cov"][iu] for r in range(R)])
+    sg, sc = scores(gpu), scores(cpu)
+    assert ks_stat(sg, sc) < 0.03
+    for qt in (0.5, 0.9, 0.99, 0.999):
+        a, b = np.quantile(sg, qt), np.quantile(sc, qt)
+        assert abs(a - b) <= 0.08 * max(1.0, abs(b)) + 0.5, (qt, a, b)
+
+
+def test_fitch_shuffle_distribution_long_alignment_ballot_kernel(ctx, pkg, po, oracle):
+    """L > 4092 with L % 4 == 0: replay_level_row_kernel<4, ballot form> against the oracle (composition, leaf distances)."""
+    N, L, R = 24, 4096, 8
+    msa, wgt, tree = _setup(ctx, po, N, L, 5, R)
+    ctx.null_fitch_shuffle(msa, seed=3, nrep=R)
+    gpu = ctx.pool_get(R)
+    rng = oracle.rng(3)
+    cpu = np.stack([oracle.null_fitch_shuffle(rng, tree, msa) for _ in range(R)])
+    oracle.rng_free(rng)
+    comp_g = np.stack([(gpu == a).mean(axis=(1, 2)) for a in range(5)])
+    comp_c = np.stack([(cpu == a).mean(axis=(1, 2)) for a in range(5)])
+    assert np.max(np.abs(comp_g.mean(1) - comp_c.mean(1))) < 0.01
+    i, j = np.triu_indices(N, 1)
+    pairdiff = lambda x: np.concatenate([(x[r][i] != x[r][j]).sum(1) for r in range(R)])
+    assert ks_stat(pairdiff(gpu) / L, pairdiff(cpu) / L) < 0.08
+    # leaf-pair distances, pair by pair (means over replicates): the tree's substitution counts are reproduced
+    dg = np.stack([(gpu[r][i] != gpu[r][j]).mean(1) for r in range(R)]).mean(0)
+    dc = np.stack([(cpu[r][i] != cpu[r][j]).mean(1) for r in range(R)]).mean(0)
+    assert np.max(np.abs(dg - dc)) < 0.02
+
+
+def test_fitch_shuffle_byte_and_word_kernels_agree(ctx, pkg, po, oracle):
+    """<1> (L % 4 != 0) against <4> on the same input: an appended all-gap column changes the kernel variant but carries no
+    substitution and never makes two leaves differ, so leaf-pair differences must have the same distribution."""
+    N, L, R = 48, 92, 32
+    msa, wgt, tree = _setup(ctx, po, N, L, 7, R)
+    msa = np.where(msa > 4, 0, msa).astype(np.uint8)
+    ctx.null_fitch_shuffle(msa, seed=17, nrep=R)
+    a = ctx.pool_get(R)
+    msa1 = np.concatenate([msa, np.full((N, 1), 4, np.uint8)], 1)
+    ctx.configure(N, L + 1, 2, 0)
+    ctx.set_weights(None)
+    ctx.set_tree(tree.left, tree.right, tree.parent, tree.ld, tree.rd)
+    ctx.pool_reserve(R)
+    ctx.null_fitch_shuffle(msa1, seed=18, nrep=R)
+    b = ctx.pool_get(R)
+    _check_generator_a_invariants(ctx, tree, msa1, 4)
+    i, j = np.triu_indices(N, 1)
+    pd = lambda x: np.concatenate([(x[r][i] != x[r][j]).sum(1) for r in range(R)])
+    assert ks_stat(pd(a), pd(b)) < 0.04
+    assert abs(pd(a).mean() - pd(b).mean()) < 0.02 * pd(a).mean() + 0.2
+
+
+def test_fitch_shuffle_exact_invariants_at_the_ssu_shape(ctx, pkg):
+    """The BASELINE config 3 shape itself (N = 10000, L = 1800): every one of the 19 998 branches of two replicates keeps its
+    5x5 substitution table; the root row is a permutation; only residues and gaps come out."""
+    N, L, R = 10000, 1800, 2
+    msa, wgt, _, tree = pkg.synth.synthetic_family(N, L, seed=42)
+    ctx.configure(N, L, 2, 4)
+    ctx.set_weights(wgt)
+    ctx.set_tree(tree.left, tree.right, tree.parent, tree.ld, tree.rd)
+    ctx.pool_reserve(R)
+    ctx.null_fitch_shuffle(msa, seed=20261017, nrep=R)
+    out, anc, shanc = _check_generator_a_invariants(ctx, tree, msa, R)
+    # the Fitch rows are a most-parsimonious reconstruction: a child differs from its parent only where the parent's
+    # residue is outside the child's set, so the number of substitutions per column is at most the number of leaves - 1
+    assert not np.array_equal(out[0], out[1])
+    # column composition is NOT kept (columns are permuted), the alignment's total composition nearly is
+    comp_in = np.bincount(np.minimum(msa, 5).ravel(), minlength=6)[:5] / msa.size
+    comp_out = np.bincount(out[0].ravel(), minlength=5) / out[0].size
+    assert np.max(np.abs(comp_in - comp_out)) < 0.02
+
+
 # ------------------------------------------------------------------------------------------------ generator B
 def test_simulate_identity_and_stationary_limits(ctx, po):
     N, L = 30, 200

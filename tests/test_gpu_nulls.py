@@ -8,6 +8,8 @@ import ctypes as C
 import numpy as np
 import pytest
 
+from _helpers import assert_bins_identical
+
 pytestmark = pytest.mark.gpu
 
 
@@ -16,14 +18,18 @@ def oracle_null_loop(po, oracle, nulls, wgt, stat, cls, ac, w_old=0.05, bmin=-10
     w = oracle.null_width(w_old, first["mincov"], first["maxcov"], bmin, hpts, tol)
     cum = None
     mm = []
+    scores = []
+    iu = np.triu_indices(nulls[0].shape[1], 1)
     for msa in nulls:
         res = oracle.scan(msa, wgt, stat, cls, ac)
         h = oracle.hist_from_cov(res["cov"], res["maxcov"], bmin, w, tol)
         cum = oracle.accumulate(cum, h)
         oracle.free(h)
         mm.append((res["mincov"], res["maxcov"]))
+        scores.append(res["cov"][iu])
     view = oracle.view(cum)
     oracle.free(cum)
+    oracle_null_loop.scores = np.concatenate(scores)          # the oracle's scores of the last call (edge-ambiguity check)
     return w, view, np.array(mm)
 
 
@@ -81,9 +87,9 @@ def test_null_histogram_other_statistics(ctx, pkg, po, oracle, stat, cls, ac):
     ctx.set_weights(wgt)
     ctx.null_hist(nulls, w_ref, getattr(pkg, stat), getattr(pkg, cls), getattr(pkg, ac), want_minmax=False)
     bins, n, imax = ctx.hist_read(view.nb)
-    # scores within 1e-12 of a bin edge may legitimately land in the neighbouring bin: allow a handful, none expected
-    diff = np.abs(bins.astype(np.int64) - view.obs.astype(np.int64)).sum()
-    assert diff <= 2, diff
+    # identical integer bins; a count may sit in the neighbouring bin only if the oracle's score lies within the score
+    # tolerance (1e-9 relative) of that bin edge
+    assert_bins_identical(bins, view.obs, oracle_null_loop.scores, -10.0, w_ref)
 
 
 def test_last_null_nseff_quirk_q3(ctx, pkg, po, oracle):

@@ -4,6 +4,8 @@ the same three-phase protocol runs over NCCL in the multi-GPU bench."""
 import numpy as np
 import pytest
 
+from _helpers import assert_bins_identical
+
 pytestmark = pytest.mark.gpu
 
 
@@ -48,6 +50,15 @@ def test_sharded_scan_equals_unsharded(pkg, po, oracle, world, stat, cls, ac):
     assert np.max(np.abs(up[iu] - ref["cov"][iu])) <= 1e-11 * scale
     assert abs(min(los) - ref["mincov"]) <= 1e-11 * scale and abs(max(his) - ref["maxcov"]) <= 1e-11 * scale
     assert n == ref_n == L * (L - 1) // 2
-    assert np.abs(bins - ref_bins.astype(np.int64)).sum() <= 2          # identical up to scores within 1e-11 of a bin edge
+    assert_bins_identical(bins, ref_bins, ref["cov"][iu], -10.0, w, rel=1e-11, scale=scale)
+    # ... and against the ORACLE (not only the unsharded device scan): scores within 1e-9, identical integer bins
+    ora = oracle.scan(msa, wgt, getattr(po, stat), getattr(po, cls), getattr(po, ac))
+    raw = oracle.scan(msa, wgt, getattr(po, stat), getattr(po, cls), po.NOCORR)
+    oscale = max(1.0, abs(raw["maxcov"]), abs(raw["mincov"]))
+    assert np.max(np.abs(up[iu] - ora["cov"][iu]) / np.maximum(np.maximum(1.0, np.abs(ora["cov"][iu])), oscale)) <= 1e-9
+    h = oracle.hist_from_cov(ora["cov"], ora["maxcov"], -10.0, w)
+    v = oracle.view(h)
+    oracle.free(h)
+    assert_bins_identical(bins[:max(v.nb, int(np.nonzero(bins)[0][-1]) + 1)], v.obs, ora["cov"][iu], -10.0, w, scale=oscale)
     for c in ranks + [whole]:
         c.close()

@@ -1,5 +1,5 @@
 """Manual GPU bring-up script (not a pytest file): staged checks of the tcgen05 count kernel with verbose
-mismatch reports.  Usage on the GPU box:  timeout 300 python tests/gpu_debug.py"""
+mismatch reports.  Usage on the GPU box:  timeout 300 python tools/gpu_debug.py"""
 import os
 import sys
 import time
