@@ -85,6 +85,11 @@ int rsb_scan(rsb_ctx *ctx, const uint8_t *msa, int64_t row_stride, int on_device
  * i<j in bin b = ceil((max(x, bmin+w) - bmin)/w - 1), b < nb; with pairmask (uint8 [L][L], nonzero = pair belongs to the
  * structure set chosen by data->samplesize: contacts / base pairs / WC pairs) hb gets the flagged pairs and ht the others. */
 int rsb_scan_hist(rsb_ctx *ctx, const uint8_t *pairmask, double w, double bmin, int nb, uint64_t *ha, uint64_t *hb, uint64_t *ht);
+/* The PDB-distance rule of the histogram fill, src/covariation.c:421-427: pairs i<j with msa2pdb[i] >= 0, msa2pdb[j] >= 0 and
+ * msa2pdb[j] - msa2pdb[i] < mind are left out of ha / hb / ht and of the null histogram (data->msa2pdb, data->clist->mind;
+ * R-scape's defaults msa2pdb[i] = i, mind = 1 exclude nothing).  msa2pdb: int[alen] on the host, NULL = no exclusion.
+ * Stays in force until changed or until rsb_configure.  Scores, min/max, E-values and the hit list are not affected. */
+int rsb_set_pair_exclusion(rsb_ctx *ctx, const int *msa2pdb, int mind);
 /* Replace the device copy of the score matrix by the host's (double [L][L], upper triangle read): the reference's ranking and
  * hit-list code reads whatever mi->COV holds (src/covariation.c:431, :845), which host code may have written or shifted
  * (e.g. Potts scores, shiftnonneg, src/correlators.c:1130-1134) after the scan. */

@@ -76,7 +76,12 @@ extern RANKLIST  *cov_CreateRankList(double bmax, double bmin, double w);
 extern int        cov_GrowRankList(RANKLIST **oranklist, double bmax, double bmin);
 extern void       cov_FreeRankList(RANKLIST *ranklist);
 extern int        cov_ranklist_Bin2Bin(int b, ESL_HISTOGRAM *h, ESL_HISTOGRAM *newh, int *ret_newb);
-/* the "ha" histogram fill of cov_SignificantPairs_Ranking, src/covariation.c:415-432, from mi->COV on the host */
+/* The histogram fill of cov_SignificantPairs_Ranking, src/covariation.c:415-457, from mi->COV on the host: every pair that passes
+ * the PDB-distance rule (:421-427, data->msa2pdb and the contact list's mind) goes to ha; in GIVSS / FOLDSS mode also to hb when
+ * pairmask flags it as a member of the structure set chosen by data->samplesize (never for SAMPLE_ALL), else to ht.
+ * pairmask: uint8 [alen][alen], entries i<j, or NULL for an empty structure (what CMAP_Is*Local return on an empty contact list). */
+extern int        cov_RankListFromCOV_b200(struct data_s *data, const uint8_t *pairmask, RANKLIST **ret_ranklist);
+/* the same with no structure mask */
 extern int        cov_RankListFromCOV(struct data_s *data, RANKLIST **ret_ranklist);
 /* src/R-scape.c:1565-1612 */
 extern int        null_add2cumranklist(RANKLIST *ranklist, RANKLIST **ocumranklist, int verbose, char *errbuf);

@@ -14,7 +14,13 @@
 #ifdef RSB_USE_RSCAPE_HEADERS
 #include "correlators.h"
 #include "covariation.h"
+/* minimum backbone distance of the contact list (lib/R-view/src/rview_contacts.h:102), read by the histogram fill */
+#define RSB_DATA_MIND(data) ((data)->clist ? (data)->clist->mind : 1)
 #else
+/* Without R-view's headers CLIST is opaque; the one field the hot path reads (mind, rview_contacts.h:102) is reached through
+ * this stand-in: in the compat build data->clist, when set, points to a struct rsb_clist_compat. */
+struct rsb_clist_compat { int mind; };
+#define RSB_DATA_MIND(data) ((data)->clist ? ((const struct rsb_clist_compat *) (data)->clist)->mind : 1)
 
 #include "easel.h"
 

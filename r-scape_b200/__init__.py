@@ -17,7 +17,7 @@ from . import synth  # noqa: F401  (seeded synthetic workloads, host-side utilit
 from . import parallel  # noqa: F401  (null-replicate sharding over torch.distributed)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "librscape_b200.so")
+LIB_PATH = os.environ.get("RSCAPE_B200_LIB") or os.path.join(HERE, "librscape_b200.so")     # (override: experimental builds, tools/build_variant.sh)
 HOST_LIB_PATH = os.path.join(HERE, "librscape_b200_host.so")
 
 CHI, GT, MI, MIr, MIg, OMES, RAF, RAFS, CCF = 0, 3, 6, 9, 12, 15, 18, 21, 24
@@ -71,6 +71,7 @@ def lib():
         L.rsb_scan_hits.argtypes = [_vp, C.POINTER(NullFitStruct), _u8p, C.c_uint64, C.c_uint64, C.c_int, C.c_double, _dp, C.c_int64,
                                     _i64p, _i64p, _dp, _dp, _dp, _i64p]
         L.rsb_load_scores.argtypes = [_vp, _dp]
+        L.rsb_set_pair_exclusion.argtypes = [_vp, _ip, C.c_int]
         L.rsb_tree_substitutions.argtypes = [_vp, C.c_int, _ip, _ip, _u8p, C.c_int64, _u8p, C.c_int64, C.c_int, _ip, _ip, _ip]
         L.rsb_set_shard.argtypes = [_vp, C.c_int, C.c_int]
         L.rsb_sharded_counts.argtypes = [_vp, _vp, C.c_int64, C.c_int, C.c_double, _dp]
@@ -196,6 +197,12 @@ class Context:
         up = lambda a: None if a is None else a.ctypes.data_as(_u64p)
         self._ck(lib().rsb_scan_hist(self._h, None if pm is None else pm.ctypes.data_as(_u8p), w, bmin, nb, up(ha), up(hb), up(ht)))
         return ha, hb, ht
+
+    def set_pair_exclusion(self, msa2pdb=None, mind=1):
+        """Pairs with both columns in the PDB sequence and closer than mind stay out of the histograms (covariation.c:421-427)."""
+        m = None if msa2pdb is None else np.ascontiguousarray(msa2pdb, dtype=np.int32)
+        assert m is None or len(m) == self.L
+        self._ck(lib().rsb_set_pair_exclusion(self._h, None if m is None else m.ctypes.data_as(_ip), int(mind)))
 
     def load_scores(self, cov):
         """Replace the device score matrix by a host matrix [L][L] (the stages after the scan read whatever mi->COV holds)."""

@@ -17,7 +17,10 @@
 // ---- kernel launchers defined in the other translation units
 cudaError_t rsb_launch_gram_i8(int S, const CUtensorMap &tmA, const CUtensorMap &tmB, const int2 *tiles, int ntiles,
                                int rep0, int nrep, int L, int Lp, int kstages, long long *cnt, double scale, double *mrow,
-                               double *mcol, int nJB, int nIB, int small52, int grid, cudaStream_t st);
+                               double *mcol, int nJB, int nIB, int small52, int grid, const void *logtab, cudaStream_t st);
+cudaError_t rsb_launch_gt_finish(const double *rec, size_t slot_stride, const double *pm, int nrep, int L, int Lp, double *cov,
+                                 double *rowpart, double *colpart, double *mm, int sr, int sw, cudaStream_t st);
+cudaError_t rsb_launch_export_nseff_rec(const double *rec, int L, int Lp, double wtot_scaled, double *nseff, double *ngap, cudaStream_t st);
 cudaError_t rsb_launch_gram_i8_pair(int S, const CUtensorMap &tmA, const CUtensorMap &tmBh, const int2 *tiles2, int ntiles2,
                                     int rep0, int nrep, int L, int Lp, int kstages, long long *cnt, double scale, double *mrow,
                                     double *mcol, int nJB, int nIB, int small52, int max_clusters, cudaStream_t st);
@@ -29,7 +32,8 @@ cudaError_t rsb_launch_colsum(const uint8_t *res, int N, int L, const unsigned l
 cudaError_t rsb_launch_counts_direct(const uint8_t *res, int N, int L, int Lp, const unsigned long long *wq, long long *cnt, cudaStream_t st);
 void        rsb_stat_grid(int L, int *nJT, int *nIT);
 cudaError_t rsb_launch_marginals(const double *mrow, const double *mcol, int nrep, int L, int CJ, int nJB, int nIB, double tol,
-                                 double *msum, double *pm, int *flags, int sr, int sw, int phase, cudaStream_t st);
+                                 double *msum, double *pm, int *flags, int sr, int sw, int phase, int mrow_blocks, cudaStream_t st);
+int rsb_gram_mrow_blocks(int pair);
 cudaError_t rsb_launch_nseff(const long long *cnt, int nrep, int L, int Lp, double scale, double *nseff, cudaStream_t st);
 cudaError_t rsb_launch_logtab(void *tab, cudaStream_t st);
 size_t rsb_logtab_bytes();
@@ -47,11 +51,11 @@ cudaError_t rsb_launch_correct_final(const double *rowpart, const double *colpar
                                      double *covx, double *scal, double *blocksum, double *covsum, int phase, cudaStream_t st);
 cudaError_t rsb_launch_correct_hist(double *cov, const double *covx, const double *scal, int nrep, int L, int Lp, int actype, int mode,
                                     double bmin, const double *wptr, unsigned long long *hist, int nbins, double *mm, double *minmax_out,
-                                    int *flags, int sr, int sw, cudaStream_t st);
+                                    int *flags, int sr, int sw, const int *m2p, int mind, cudaStream_t st);
 cudaError_t rsb_launch_width(const double *minmax, double w_old, double bmin, int hpts, double tol, double *wout, cudaStream_t st);
 cudaError_t rsb_launch_symmetrize(double *cov, int L, int Lp, cudaStream_t st);
 cudaError_t rsb_launch_hist3(const double *cov, int L, int Lp, const uint8_t *pairmask, double bmin, double w, int nb,
-                             unsigned long long *ha, unsigned long long *hb, unsigned long long *ht, int *flags, cudaStream_t st);
+                             unsigned long long *ha, unsigned long long *hb, unsigned long long *ht, int *flags, const int *m2p, int mind, cudaStream_t st);
 cudaError_t rsb_launch_evalue_hits(const double *cov, int L, int Lp, const rsb_nullview &nv, const uint8_t *pairmask, double Nb, double Nt,
                                    double expBP, long long switch_n, double thresh, int report_all, int sr, int sw, double *eval, long long cap,
                                    long long *hit_ij, double *hit_sc, double *hit_eval, double *hit_pval, unsigned long long *nhit, int *flags,
@@ -100,6 +104,8 @@ struct rsb_ctx {
   size_t planeB_rows_cap = 0;
   Geo geo[2];                         // [0] weighted, [1] unit weights (RAF/RAFS)
   int cur_geo = 0;                    // geometry of the counts currently in d_cnt
+  bool cur_rec = false;               // ... which hold per-pair G-test records instead of counts (record epilogue, gram_tcgen05.cu)
+  bool fused_gt = true;               // nulls scored with GT x C16 use the record epilogue (RSCAPE_B200_FUSED_GT=0: counts + stat_kernel)
   int last_slot = 0;                  // replicate slot scanned last (quirk Q3)
   CUtensorMap tmA;
   std::vector<double> wgt;
@@ -120,7 +126,7 @@ struct rsb_ctx {
   double *h_mm = nullptr; size_t h_mm_cap = 0;      // pinned staging of the per-replicate min/max: a pageable target would block the enqueuing thread
   double *d_meanp = nullptr, *d_w = nullptr, *d_blocksum = nullptr, *d_msum = nullptr, *d_covsum = nullptr;
   int shard_rank = 0, shard_world = 1;  // row-block sharding of the pair grid across ranks
-  cudaStream_t stream_aux = nullptr, stream_copy = nullptr;     // statistics / uploads of the pipelined null loop
+  cudaStream_t stream_aux = nullptr, stream_aux2 = nullptr, stream_copy = nullptr;     // statistics (one per slot group) / uploads of the pipelined null loop
   cudaEvent_t ev_entry = nullptr, ev_up[2] = { nullptr, nullptr }, ev_counts[2] = { nullptr, nullptr }, ev_stats[2] = { nullptr, nullptr },
               ev_marg[2] = { nullptr, nullptr }, ev_statk[2] = { nullptr, nullptr };
   unsigned long long *d_hist = nullptr, *d_colsum = nullptr;
@@ -143,6 +149,8 @@ struct rsb_ctx {
   int Rpool = 0;
 
   unsigned long long hist_n = 0;
+  int *d_m2p = nullptr; int mind = 1;                 // PDB positions of the columns + minimum distance: pairs kept out of the histograms
+  unsigned long long pairs_in_hist = 0;               // pairs i<j that are not excluded by that rule
   long long launches = 0, gram_launches = 0;
   double gram_ms = 0.0;
   bool profile = false;
@@ -210,6 +218,7 @@ void free_plan(rsb_ctx *c)
   dfree(c->d_meanp); dfree(c->d_w); dfree(c->d_blocksum); dfree(c->d_msum); dfree(c->d_covsum); dfree(c->d_hist); dfree(c->d_colsum); dfree(c->d_flags); dfree(c->d_ps); dfree(c->d_pp_out);
   dfree(c->d_nseff_out); dfree(c->d_ngap_out); dfree(c->d_left); dfree(c->d_right); dfree(c->d_parent); dfree(c->d_order);
   dfree(c->d_level_start); dfree(c->d_perm); dfree(c->d_pcdf); dfree(c->d_root); dfree(c->d_gapmask); dfree(c->d_simscratch);
+  dfree(c->d_m2p); c->mind = 1;
   dfree(c->d_msa0); dfree(c->d_anc); dfree(c->d_shanc); dfree(c->d_pool); dfree(c->d_sets); dfree(c->d_genflag); dfree(c->d_ids); c->ids_cap = 0; dfree(c->d_pthr); c->sim_valid = false;
   c->Rpool = 0;
   c->have_tree = false;
@@ -411,9 +420,10 @@ int enqueue_pack(rsb_ctx *ctx, int which, int s0, int nrep, const uint8_t *src, 
 }
 
 // tcgen05 contraction of the planes of slots [s0, s0 + nrep) -> count planes, on stream st
-int enqueue_gram(rsb_ctx *ctx, int which, int s0, int nrep, cudaStream_t st)
+int enqueue_gram(rsb_ctx *ctx, int which, int s0, int nrep, cudaStream_t st, bool rec = false)
 {
   Geo &g = ctx->geo[which];
+  if (rec && (which != 0 || g.pair_clusters > 0)) { rsb_set_error(ctx, "internal: record epilogue not available here"); return 1; }
   if (g.ntiles > 0) {
     const long long work = (long long) g.ntiles * nrep;
     const int grid = (int) std::min<long long>(work, ctx->sm_count);
@@ -421,26 +431,34 @@ int enqueue_gram(rsb_ctx *ctx, int which, int s0, int nrep, cudaStream_t st)
     if (ctx->profile) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
     // the weighted geometry also emits the marginal partial sums of every tile (slot-indexed like the counts)
     double *mrow = (which == 0) ? ctx->d_mrow : nullptr, *mcol = (which == 0) ? ctx->d_mcol : nullptr;
-    if (which == 0 && ((size_t) g.nJB * ctx->L * 4 > ctx->mrow_stride)) { rsb_set_error(ctx, "internal: marginal partial capacity"); return 1; }
+    if (which == 0 && ((size_t) g.nJB * rsb_gram_mrow_blocks(0) * ctx->L * 4 > ctx->mrow_stride)) { rsb_set_error(ctx, "internal: marginal partial capacity"); return 1; }
     if (g.pair_clusters > 0)
       RSB_CUDA_OK(rsb_launch_gram_i8_pair(g.S, ctx->tmA, g.tmBh, g.d_tiles2, g.ntiles2, s0, nrep, ctx->L, ctx->Lp, ctx->Kpad / RSB_KSTAGE,
                                           ctx->d_cnt, g.scale, mrow, mcol, g.nJB, ctx->nIB, ((unsigned long long) g.wtot >> 52) == 0, g.pair_clusters, st));
     else
       RSB_CUDA_OK(rsb_launch_gram_i8(g.S, ctx->tmA, g.tmB, g.d_tiles, g.ntiles, s0, nrep, ctx->L, ctx->Lp, ctx->Kpad / RSB_KSTAGE,
-                                     ctx->d_cnt, g.scale, mrow, mcol, g.nJB, ctx->nIB, ((unsigned long long) g.wtot >> 52) == 0, grid, st));
+                                     ctx->d_cnt, g.scale, mrow, mcol, g.nJB, ctx->nIB, ((unsigned long long) g.wtot >> 52) == 0, grid,
+                                     rec ? ctx->d_logtab : nullptr, st));
     if (ctx->profile) { cudaEventRecord(e1, st); ctx->pending.push_back({ e0, e1 }); }
     ctx->launches++;
     ctx->gram_launches++;
   }
   ctx->cur_geo = which;
+  ctx->cur_rec = rec;
   ctx->last_slot = s0 + nrep - 1;
   return 0;
 }
 
-int enqueue_counts(rsb_ctx *ctx, int which, int s0, int nrep, const uint8_t *src, cudaStream_t st)
+int enqueue_counts(rsb_ctx *ctx, int which, int s0, int nrep, const uint8_t *src, cudaStream_t st, bool rec = false)
 {
   if (enqueue_pack(ctx, which, s0, nrep, src, st)) return 1;
-  return enqueue_gram(ctx, which, s0, nrep, st);
+  return enqueue_gram(ctx, which, s0, nrep, st, rec);
+}
+
+// may the nulls of this (statistic, class) be scored through the record epilogue?
+bool use_record(rsb_ctx *ctx, int stat, int covclass)
+{
+  return ctx->fused_gt && stat == RSB_GT && covclass == RSB_C16 && ctx->geo[0].pair_clusters == 0;
 }
 
 int check_flags(rsb_ctx *ctx, const char *what)
@@ -503,9 +521,10 @@ int enqueue_marginals(rsb_ctx *ctx, int s0, int nrep, double tol, cudaStream_t s
   Geo &g = ctx->geo[0];
   SlotPtrs p = slot_ptrs(ctx, s0);
   // partials are addressed [r][block][L][4] with r the absolute slot, as the gram kernel wrote them
-  RSB_CUDA_OK(rsb_launch_marginals(ctx->d_mrow + (size_t) s0 * g.nJB * ctx->L * 4, ctx->d_mcol + (size_t) s0 * 4 * ctx->nIB * ctx->L * 4,
+  const int E = rsb_gram_mrow_blocks(g.pair_clusters > 0);
+  RSB_CUDA_OK(rsb_launch_marginals(ctx->d_mrow + (size_t) s0 * g.nJB * E * ctx->L * 4, ctx->d_mcol + (size_t) s0 * 4 * ctx->nIB * ctx->L * 4,
                                    nrep, ctx->L, g.CJ, g.nJB, ctx->nIB, tol, p.msum, p.pm, ctx->d_flags,
-                                   ctx->shard_rank, ctx->shard_world, phase, st));
+                                   ctx->shard_rank, ctx->shard_world, phase, E, st));
   ctx->launches += (phase == 3) ? 2 : 1;
   return 0;
 }
@@ -530,6 +549,11 @@ int enqueue_statistic(rsb_ctx *ctx, int s0, int nrep, int stat, int covclass, un
       RSB_CUDA_OK(rsb_launch_nseff(p.cnt, nrep, ctx->L, ctx->Lp, ctx->geo[0].scale, p.nseff, st));
       RSB_CUDA_OK(rsb_launch_ccf(p.nseff, p.pm, nrep, ctx->L, ctx->Lp, p.tmp, p.meanp, p.cov, rowpart, colpart, p.mm, st));
       ctx->launches += 5;
+    } else if (ctx->cur_rec) {
+      if (!(stat == RSB_GT && covclass == RSB_C16)) { rsb_set_error(ctx, "internal: the slots hold G-test records, not counts"); return 1; }
+      RSB_CUDA_OK(rsb_launch_gt_finish((const double *) p.cnt, (size_t) 16 * ctx->L * ctx->Lp, p.pm, nrep, ctx->L, ctx->Lp, p.cov, rowpart, colpart, p.mm,
+                                       ctx->shard_rank, ctx->shard_world, st));
+      ctx->launches++;
     } else {
       RSB_CUDA_OK(rsb_launch_statistic(stat, covclass, p.cnt, p.pm, ctx->d_logtab, nrep, ctx->L, ctx->Lp, g.scale, g.wtot, mask, p.cov, rowpart, colpart, p.mm,
                                        ctx->shard_rank, ctx->shard_world, st));
@@ -548,7 +572,7 @@ int enqueue_correct(rsb_ctx *ctx, int s0, int nrep, int actype, int mode, double
 {
   SlotPtrs p = slot_ptrs(ctx, s0);
   RSB_CUDA_OK(rsb_launch_correct_hist(p.cov, p.covx, p.scal, nrep, ctx->L, ctx->Lp, actype, mode, bmin, ctx->d_w, ctx->d_hist, HIST_BINS,
-                                      p.mm, p.minmax, ctx->d_flags, ctx->shard_rank, ctx->shard_world, st));
+                                      p.mm, p.minmax, ctx->d_flags, ctx->shard_rank, ctx->shard_world, ctx->d_m2p, ctx->mind, st));
   ctx->launches += 2;
   return 0;
 }
@@ -557,7 +581,7 @@ int enqueue_correct(rsb_ctx *ctx, int s0, int nrep, int actype, int mode, double
 int run_pipeline(rsb_ctx *ctx, int nrep, int stat, int covclass, unsigned mask, double tol)
 {
   const bool raf = (stat == RSB_RAF || stat == RSB_RAFS);
-  if (enqueue_counts(ctx, raf ? 1 : 0, 0, nrep, ctx->d_res, ctx->stream)) return 1;
+  if (enqueue_counts(ctx, raf ? 1 : 0, 0, nrep, ctx->d_res, ctx->stream, use_record(ctx, stat, covclass))) return 1;
   if (!raf && enqueue_marginals(ctx, 0, nrep, tol, ctx->stream)) return 1;
   return enqueue_statistic(ctx, 0, nrep, stat, covclass, mask, ctx->stream);
 }
@@ -618,6 +642,7 @@ int rsb_create(int device, void *stream, rsb_ctx **out)
   if (stream) c->stream = (cudaStream_t) stream;
   else { cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking); c->own_stream = true; }
   cudaStreamCreateWithFlags(&c->stream_aux, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&c->stream_aux2, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&c->stream_copy, cudaStreamNonBlocking);
   {
     int lo = 0, hi = 0;
@@ -643,6 +668,7 @@ int rsb_create(int device, void *stream, rsb_ctx **out)
     snprintf(g_create_err, sizeof(g_create_err), "rsb_create: log table: %s", cudaGetErrorString(cudaGetLastError()));
     delete c; return 1;
   }
+  if (const char *e = getenv("RSCAPE_B200_FUSED_GT")) c->fused_gt = atoi(e) != 0;
   *out = c;
   return 0;
 }
@@ -657,7 +683,8 @@ void rsb_destroy(rsb_ctx *ctx)
   for (auto &p : ctx->pending_stage) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   free_plan(ctx);
   if (ctx->d_logtab) cudaFree(ctx->d_logtab);
-  cudaStreamSynchronize(ctx->stream_aux); cudaStreamSynchronize(ctx->stream_copy); cudaStreamSynchronize(ctx->stream_gen);
+  cudaStreamSynchronize(ctx->stream_aux); cudaStreamSynchronize(ctx->stream_aux2); cudaStreamSynchronize(ctx->stream_copy); cudaStreamSynchronize(ctx->stream_gen);
+  cudaStreamDestroy(ctx->stream_aux2);
   cudaStreamDestroy(ctx->stream_aux); cudaStreamDestroy(ctx->stream_copy); cudaStreamDestroy(ctx->stream_gen); cudaStreamDestroy(ctx->stream_hi); cudaEventDestroy(ctx->ev_exit);
   for (auto &e : ctx->gen_ring) cudaEventDestroy(e);
   cudaEventDestroy(ctx->ev_entry);
@@ -701,7 +728,7 @@ int rsb_configure(rsb_ctx *ctx, int nseq, int alen, int max_replicates, int nsli
   RSB_CUDA_OK(cudaMalloc(&ctx->d_pm, R * L * 4 * sizeof(double)));
   RSB_CUDA_OK(cudaMalloc(&ctx->d_rowpart, R * nJT * L * sizeof(double)));
   RSB_CUDA_OK(cudaMalloc(&ctx->d_colpart, R * nIT * L * sizeof(double)));
-  ctx->mrow_stride = (size_t) njb_cap * L * 4; ctx->mcol_stride = (size_t) 4 * ctx->nIB * L * 4;
+  ctx->mrow_stride = (size_t) njb_cap * rsb_gram_mrow_blocks(0) * L * 4; ctx->mcol_stride = (size_t) 4 * ctx->nIB * L * 4;
   RSB_CUDA_OK(cudaMalloc(&ctx->d_mrow, R * ctx->mrow_stride * sizeof(double)));
   RSB_CUDA_OK(cudaMalloc(&ctx->d_mcol, R * ctx->mcol_stride * sizeof(double)));
   RSB_CUDA_OK(cudaMalloc(&ctx->d_mm, R * nJT * nIT * 2 * sizeof(double)));
@@ -723,6 +750,7 @@ int rsb_configure(rsb_ctx *ctx, int nseq, int alen, int max_replicates, int nsli
   RSB_CUDA_OK(cudaMemsetAsync(ctx->d_cnt, 0, R * 16 * L * Lp * sizeof(long long), ctx->stream));
   RSB_CUDA_OK(cudaMemsetAsync(ctx->d_cov, 0, R * L * Lp * sizeof(double), ctx->stream));
   ctx->hist_n = 0;
+  ctx->pairs_in_hist = (unsigned long long) L * (L - 1) / 2;
   if (make_plane_map(ctx, &ctx->tmA, ctx->d_planeA, ctx->Kpad, (size_t) ctx->MA, ctx->Rcap, RSB_MTILE)) return 1;
   ctx->wgt.assign(nseq, 1.0);
   RSB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
@@ -768,7 +796,7 @@ int rsb_fetch_probs(rsb_ctx *ctx, double *pp, double *pm, double *ps, double *ns
 {
   RSB_CUDA_OK(cudaSetDevice(ctx->device));
   Geo &g = ctx->geo[0];
-  if (!g.ready || ctx->cur_geo != 0) { rsb_set_error(ctx, "no weighted counts resident (call rsb_probs)"); return 1; }
+  if (!g.ready || ctx->cur_geo != 0 || ctx->cur_rec) { rsb_set_error(ctx, "no weighted counts resident (call rsb_probs)"); return 1; }
   const size_t L = ctx->L;
   if (pp || nseff || ngap) {
     if (!ctx->d_pp_out) {
@@ -828,7 +856,7 @@ int rsb_statistic(rsb_ctx *ctx, int stat, int covclass, const double *allowpair,
     if (!msa) { rsb_set_error(ctx, "RAF/RAFS need the alignment"); return 1; }
     if (upload_msa(ctx, msa, row_stride, 0, 1, 0, on_device, ctx->stream)) return 1;
     if (enqueue_counts(ctx, 1, 0, 1, ctx->d_res, ctx->stream)) return 1;
-  } else if (ctx->cur_geo != 0) { rsb_set_error(ctx, "rsb_probs must precede this statistic"); return 1; }
+  } else if (ctx->cur_geo != 0 || ctx->cur_rec) { rsb_set_error(ctx, "rsb_probs must precede this statistic"); return 1; }
   if (enqueue_statistic(ctx, 0, 1, stat, covclass, allow_mask(allowpair), ctx->stream)) return 1;
   double sc[4];
   if (cov) {
@@ -884,6 +912,7 @@ int rsb_scan(rsb_ctx *ctx, const uint8_t *msa, int64_t row_stride, int on_device
 int rsb_get_counts(rsb_ctx *ctx, int64_t *counts)
 {
   RSB_CUDA_OK(cudaSetDevice(ctx->device));
+  if (ctx->cur_rec) { rsb_set_error(ctx, "no counts resident: the last scan was a null scored through the record epilogue"); return 1; }
   const size_t L = ctx->L;
   RSB_CUDA_OK(cudaMemcpy2DAsync(counts, sizeof(int64_t) * L, ctx->d_cnt, sizeof(int64_t) * ctx->Lp, sizeof(int64_t) * L, 16 * L,
                                 cudaMemcpyDeviceToHost, ctx->stream));
@@ -941,6 +970,9 @@ static int null_hist_pipelined(rsb_ctx *ctx, const uint8_t *nulls, int nrep, int
                                double *minmax, int pool_first = -1)
 {
   const bool raf = (stat == RSB_RAF || stat == RSB_RAFS);
+  // GT x C16: the contraction's epilogue leaves per-pair records and the statistic finishes with an HBM-bound kernel on the
+  // aux stream -- nothing but contractions on the main stream
+  const bool rec = !raf && use_record(ctx, stat, covclass);
   const bool in_place = (on_device && row_stride == ctx->L && rep_stride == (int64_t) ctx->N * ctx->L);
   const int  G = (ctx->Rcap >= 2) ? 2 : 1;
   const int  chunk = std::max(1, ctx->Rcap / G);
@@ -949,7 +981,10 @@ static int null_hist_pipelined(rsb_ctx *ctx, const uint8_t *nulls, int nrep, int
   // contraction + statistic run on an internal high-priority stream, so that their blocks are placed ahead of those of the
   // null generators working on later replicates (generation stream, lowest priority)
   cudaStream_t sm = ctx->stream_hi;
-  cudaStream_t st_aux = (serial & 1) ? sm : ctx->stream_aux, st_copy = (serial & 2) ? sm : ctx->stream_copy;
+  cudaStream_t st_copy = (serial & 2) ? sm : ctx->stream_copy;
+  // one statistics stream per slot group: the chains of consecutive chunks overlap each other (they run beside the
+  // contraction at low occupancy, bound by latency rather than by a pipe)
+  auto aux_of = [&](int g) -> cudaStream_t { return (serial & 1) ? sm : (g & 1) ? ctx->stream_aux2 : ctx->stream_aux; };
 
   if (minmax && ctx->h_mm_cap < (size_t) nrep) {
     if (ctx->h_mm) cudaFreeHost(ctx->h_mm);
@@ -961,7 +996,8 @@ static int null_hist_pipelined(rsb_ctx *ctx, const uint8_t *nulls, int nrep, int
   RSB_CUDA_OK(cudaStreamWaitEvent(sm, ctx->ev_entry, 0));
   RSB_CUDA_OK(cudaMemcpyAsync(ctx->d_w, &w, sizeof(double), cudaMemcpyHostToDevice, sm));
   RSB_CUDA_OK(cudaEventRecord(ctx->ev_entry, sm));
-  RSB_CUDA_OK(cudaStreamWaitEvent(st_aux, ctx->ev_entry, 0));
+  RSB_CUDA_OK(cudaStreamWaitEvent(ctx->stream_aux, ctx->ev_entry, 0));
+  RSB_CUDA_OK(cudaStreamWaitEvent(ctx->stream_aux2, ctx->ev_entry, 0));
   RSB_CUDA_OK(cudaStreamWaitEvent(st_copy, ctx->ev_entry, 0));
   bool used[2] = { false, false };
 
@@ -971,8 +1007,14 @@ static int null_hist_pipelined(rsb_ctx *ctx, const uint8_t *nulls, int nrep, int
   //   main:  G(0) G(1) S(0) G(2) S(1) ...      aux:  M(c) after G(c);  R(c) + C(c) after S(c)
   auto tail = [&](int pc, int pr0) -> int {                         // S(pc) on main, then its reductions/correction on aux
     const int pg = pc % G, ps0 = pg * chunk, pn = std::min(chunk, nrep - pr0);
+    cudaStream_t st_aux = aux_of(pg);
     cudaEvent_t a0 = nullptr, a1 = nullptr, am = nullptr, as = nullptr;
     if (ctx->profile) { cudaEventCreate(&a0); cudaEventCreate(&a1); cudaEventCreate(&am); cudaEventCreate(&as); }
+    if (rec) {                                                       // the whole chain on the aux stream, behind M(pc)
+      if (ctx->profile) cudaEventRecord(a0, st_aux);
+      if (enqueue_statistic(ctx, ps0, pn, stat, covclass, mask, st_aux, 3, 1)) return 1;
+      if (ctx->profile) { cudaEventRecord(am, st_aux); cudaEventRecord(as, st_aux); }
+    } else {
     RSB_CUDA_OK(cudaStreamWaitEvent(sm, ctx->ev_marg[pg], 0));
     if (pc >= G) RSB_CUDA_OK(cudaStreamWaitEvent(sm, ctx->ev_stats[pg], 0));   // the group's scores and partial sums have been consumed
     if (ctx->profile) cudaEventRecord(a0, sm);
@@ -981,13 +1023,14 @@ static int null_hist_pipelined(rsb_ctx *ctx, const uint8_t *nulls, int nrep, int
     RSB_CUDA_OK(cudaEventRecord(ctx->ev_statk[pg], sm));
     RSB_CUDA_OK(cudaStreamWaitEvent(st_aux, ctx->ev_statk[pg], 0));
     if (ctx->profile) cudaEventRecord(as, st_aux);
+    }
     if (enqueue_statistic(ctx, ps0, pn, stat, covclass, mask, st_aux, 3, 2)) return 1;
     if (enqueue_correct(ctx, ps0, pn, actype, 2, bmin, st_aux)) return 1;
     if (minmax) RSB_CUDA_OK(cudaMemcpyAsync(ctx->h_mm + 2 * (size_t) pr0, ctx->d_minmax + 2 * (size_t) ps0, sizeof(double) * 2 * pn,
                                             cudaMemcpyDeviceToHost, st_aux));
     if (ctx->profile) { cudaEventRecord(a1, st_aux); ctx->pending_aux.push_back({ a0, a1 }); ctx->pending_stage.push_back({ am, as }); ctx->aux_chains++; }
     RSB_CUDA_OK(cudaEventRecord(ctx->ev_stats[pg], st_aux));
-    if (w > 0.0) ctx->hist_n += (unsigned long long) pn * ((unsigned long long) ctx->L * (ctx->L - 1) / 2);
+    if (w > 0.0) ctx->hist_n += (unsigned long long) pn * ctx->pairs_in_hist;
     return 0;
   };
 
@@ -1005,18 +1048,20 @@ static int null_hist_pipelined(rsb_ctx *ctx, const uint8_t *nulls, int nrep, int
     if (enqueue_pack(ctx, raf ? 1 : 0, s0, n, src, st_copy)) return 1;                   // HBM-bound transpose: hides under the previous gram
     RSB_CUDA_OK(cudaEventRecord(ctx->ev_up[g], st_copy));
     RSB_CUDA_OK(cudaStreamWaitEvent(sm, ctx->ev_up[g], 0));
-    // (the counts and marginal partials of this group were consumed by S(c - G), earlier on this stream)
-    if (enqueue_gram(ctx, raf ? 1 : 0, s0, n, sm)) return 1;
+    // (the counts and marginal partials of this group were consumed by S(c - G), earlier on this stream; with the record
+    // epilogue their consumers run on the aux stream)
+    if (rec && used[g]) RSB_CUDA_OK(cudaStreamWaitEvent(sm, ctx->ev_stats[g], 0));
+    if (enqueue_gram(ctx, raf ? 1 : 0, s0, n, sm, rec)) return 1;
     RSB_CUDA_OK(cudaEventRecord(ctx->ev_counts[g], sm));
 
-    RSB_CUDA_OK(cudaStreamWaitEvent(st_aux, ctx->ev_counts[g], 0));
-    if (!raf && enqueue_marginals(ctx, s0, n, tol, st_aux)) return 1;
-    RSB_CUDA_OK(cudaEventRecord(ctx->ev_marg[g], st_aux));
+    RSB_CUDA_OK(cudaStreamWaitEvent(aux_of(g), ctx->ev_counts[g], 0));
+    if (!raf && enqueue_marginals(ctx, s0, n, tol, aux_of(g))) return 1;
+    RSB_CUDA_OK(cudaEventRecord(ctx->ev_marg[g], aux_of(g)));
     used[g] = true;
-    if (G == 1) { if (tail(c, r0)) return 1; }
+    if (G == 1 || rec) { if (tail(c, r0)) return 1; }
     else if (c >= 1) { if (tail(c - 1, r0 - chunk)) return 1; }
   }
-  if (G > 1 && c >= 1) { if (tail(c - 1, (c - 1) * chunk)) return 1; }
+  if (G > 1 && c >= 1 && !rec) { if (tail(c - 1, (c - 1) * chunk)) return 1; }
   for (int g = 0; g < G; g++) if (used[g]) RSB_CUDA_OK(cudaStreamWaitEvent(sm, ctx->ev_stats[g], 0));
   RSB_CUDA_OK(cudaEventRecord(ctx->ev_exit, sm));                      // back to the caller's stream
   RSB_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->ev_exit, 0));
@@ -1114,6 +1159,7 @@ int rsb_sharded_correct(rsb_ctx *ctx, const double *cov_sums, int actype, int mo
   if ((mode & 2) && w > 0.0) {                                                                            // pairs owned by this rank
     unsigned long long mine = 0;
     for (int i = 0; i < ctx->L; i++) if ((i / RSB_ICOLS) % ctx->shard_world == ctx->shard_rank) mine += (unsigned long long) (ctx->L - 1 - i);
+    if (ctx->d_m2p) { rsb_set_error(ctx, "a pair exclusion (rsb_set_pair_exclusion) is not offered on a sharded pair grid"); return 1; }
     ctx->hist_n += mine;
   }
   double mmx[2];
@@ -1140,7 +1186,7 @@ int rsb_scan_hist(rsb_ctx *ctx, const uint8_t *pairmask, double w, double bmin, 
     SH_OK(cudaMalloc(&dmask, L * L));
     SH_OK(cudaMemcpyAsync(dmask, pairmask, L * L, cudaMemcpyHostToDevice, ctx->stream));
   }
-  SH_OK(rsb_launch_hist3(ctx->d_cov, ctx->L, ctx->Lp, dmask, bmin, w, nb, d3, d3 + nb, d3 + 2 * (size_t) nb, ctx->d_flags, ctx->stream));
+  SH_OK(rsb_launch_hist3(ctx->d_cov, ctx->L, ctx->Lp, dmask, bmin, w, nb, d3, d3 + nb, d3 + 2 * (size_t) nb, ctx->d_flags, ctx->d_m2p, ctx->mind, ctx->stream));
   ctx->launches++;
   if (ha) SH_OK(cudaMemcpyAsync(ha, d3, sizeof(uint64_t) * nb, cudaMemcpyDeviceToHost, ctx->stream));
   if (hb) SH_OK(cudaMemcpyAsync(hb, d3 + nb, sizeof(uint64_t) * nb, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1150,6 +1196,25 @@ done:
 #undef SH_OK
   cudaFree(d3); cudaFree(dmask);
   return rc;
+}
+
+/* pairs with both columns in the PDB sequence and fewer than `mind` positions apart stay out of every histogram, src/covariation.c:421-427 */
+int rsb_set_pair_exclusion(rsb_ctx *ctx, const int *msa2pdb, int mind)
+{
+  RSB_CUDA_OK(cudaSetDevice(ctx->device));
+  if (ctx->N == 0) { rsb_set_error(ctx, "rsb_configure first"); return 1; }
+  RSB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  const size_t L = ctx->L;
+  ctx->pairs_in_hist = (unsigned long long) L * (L - 1) / 2;
+  if (!msa2pdb) { dfree(ctx->d_m2p); ctx->mind = 1; return 0; }
+  if (!ctx->d_m2p) RSB_CUDA_OK(cudaMalloc(&ctx->d_m2p, sizeof(int) * L));
+  RSB_CUDA_OK(cudaMemcpy(ctx->d_m2p, msa2pdb, sizeof(int) * L, cudaMemcpyHostToDevice));
+  ctx->mind = mind;
+  unsigned long long excl = 0;
+  for (size_t i = 0; i + 1 < L; i++)
+    for (size_t j = i + 1; j < L; j++) excl += (msa2pdb[i] >= 0 && msa2pdb[j] >= 0 && msa2pdb[j] - msa2pdb[i] < mind);
+  ctx->pairs_in_hist -= excl;
+  return 0;
 }
 
 /* scores written or changed on the host (mi->COV) -> the device matrix the histogram / E-value stages read */
@@ -1364,8 +1429,12 @@ int rsb_last_nseff(rsb_ctx *ctx, double *nseff, double *ngap)
     RSB_CUDA_OK(cudaMalloc(&ctx->d_nseff_out, L * L * sizeof(double)));
     RSB_CUDA_OK(cudaMalloc(&ctx->d_ngap_out, L * L * sizeof(double)));
   }
-  RSB_CUDA_OK(rsb_launch_export_probs(ctx->d_cnt + (size_t) ctx->last_slot * 16 * L * ctx->Lp, ctx->L, ctx->Lp, g.scale, g.wtot,
-                                      ctx->d_pp_out, ctx->d_nseff_out, ctx->d_ngap_out, ctx->stream));
+  if (ctx->cur_rec)
+    RSB_CUDA_OK(rsb_launch_export_nseff_rec((const double *) (ctx->d_cnt + (size_t) ctx->last_slot * 16 * L * ctx->Lp), ctx->L, ctx->Lp,
+                                            (double) g.wtot * g.scale, ctx->d_nseff_out, ctx->d_ngap_out, ctx->stream));
+  else
+    RSB_CUDA_OK(rsb_launch_export_probs(ctx->d_cnt + (size_t) ctx->last_slot * 16 * L * ctx->Lp, ctx->L, ctx->Lp, g.scale, g.wtot,
+                                        ctx->d_pp_out, ctx->d_nseff_out, ctx->d_ngap_out, ctx->stream));
   ctx->launches++;
   if (nseff) RSB_CUDA_OK(cudaMemcpyAsync(nseff, ctx->d_nseff_out, L * L * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   if (ngap)  RSB_CUDA_OK(cudaMemcpyAsync(ngap, ctx->d_ngap_out, L * L * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1659,6 +1728,7 @@ int rsb_counters(rsb_ctx *ctx, int64_t *launches, double *gram_ms, int64_t *gram
   }
   if (!ctx->pending_aux.empty()) {
     RSB_CUDA_OK(cudaStreamSynchronize(ctx->stream_aux));
+    RSB_CUDA_OK(cudaStreamSynchronize(ctx->stream_aux2));
     for (size_t k = 0; k < ctx->pending_aux.size(); k++) {
       auto &p = ctx->pending_aux[k]; auto &q = ctx->pending_stage[k];
       float ms = 0.f;

@@ -13,7 +13,7 @@ namespace {
 
 constexpr int CH_TI = RSB_TI;
 constexpr int CH_TJ = RSB_TJ;
-constexpr int CH_SMEM_BINS = 4096;
+constexpr int CH_SMEM_BINS = 2048;        // 8 KB: several blocks fit beside the tcgen05 kernel's ring
 
 // covsum[i] = sum_{j != i} COV[i][j] from the tile partials (one thread per column, fixed summation order); each block
 // also leaves the sum of its row partials (= its share of sum_{i<j} COV) in blocksum[r][block].
@@ -94,10 +94,11 @@ __device__ __forceinline__ double corrected(int actype, double raw, double xi, d
 //   mode bit 1: add max(x, bmin+w) into the histogram (w read from *wptr so that it can come from the
 //               device-side width computation without a host round trip)
 // Always: per-block min/max of the corrected score, NaN flag (:1124).
-__global__ void __launch_bounds__(CH_TJ)
+__global__ void __launch_bounds__(CH_TJ, 6)
 correct_hist_kernel(double *__restrict__ cov, const double *__restrict__ covx, const double *__restrict__ scal, int L, int Lp,
                     int actype, int mode, double bmin, const double *__restrict__ wptr, unsigned long long *__restrict__ hist,
-                    int nbins, double *__restrict__ mm, int *__restrict__ flags, int nJT, int nIT, int sr, int sw)
+                    int nbins, double *__restrict__ mm, int *__restrict__ flags, int nJT, int nIT, int sr, int sw,
+                    const int *__restrict__ m2p, int mind)
 {
   __shared__ unsigned int sh[CH_SMEM_BINS];
   __shared__ double smin[CH_TJ / 32], smax[CH_TJ / 32];
@@ -117,20 +118,35 @@ correct_hist_kernel(double *__restrict__ cov, const double *__restrict__ covx, c
     const double c = ceil((-bmin) / w - 1.0) - (double) (CH_SMEM_BINS / 2);
     b0 = (c > 0.0 && c < (double) nbins) ? (int) c : 0;
   }
-  if (do_hist) { for (int k = threadIdx.x; k < CH_SMEM_BINS; k += CH_TJ) sh[k] = 0; __syncthreads(); }
+  __shared__ double sxi[CH_TI];                                       // COVx of the tile's rows
+  if (do_hist) { for (int k = threadIdx.x; k < CH_SMEM_BINS; k += CH_TJ) sh[k] = 0; }
+  if (threadIdx.x < CH_TI) { const int i = it * CH_TI + threadIdx.x; sxi[threadIdx.x] = (i < L) ? covx[(size_t) r * L + i] : 0.0; }
+  __syncthreads();
 
   if (tile_live && j < L) {
     const double xj = covx[(size_t) r * L + j];
+    const int mpj = m2p ? m2p[j] : -1;
     double *C = cov + (size_t) r * L * Lp;
-    for (int il = 0; il < CH_TI; il++) {
-      const int i = it * CH_TI + il;
+    #pragma unroll 1
+    for (int il0 = 0; il0 < CH_TI; il0 += 8) {
+    double raw[8];                                                    // the loads of 8 rows first (few resident warps beside the contraction)
+    #pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const int i = it * CH_TI + il0 + u;
+      raw[u] = (i < L && i < j) ? C[(size_t) i * Lp + j] : 0.0;
+    }
+    #pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const int il = il0 + u, i = it * CH_TI + il;
       if (i >= L || i >= j) continue;
-      const double v = corrected(actype, C[(size_t) i * Lp + j], covx[(size_t) r * L + i], xj, avg);
+      const double v = corrected(actype, raw[u], sxi[il], xj, avg);
       if (isnan(v)) atomicOr(flags, 2);
       vmin = fmin(vmin, v);
       vmax = fmax(vmax, v);
       if (mode & 1) C[(size_t) i * Lp + j] = v;                     // mirrored by symmetrize_kernel
-      if (do_hist && w > 0.0) {
+      // pairs closer than `mind` in the PDB sequence stay out of the histogram (covariation.c:421-427); min/max keep them
+      const bool excl = m2p && m2p[i] >= 0 && mpj >= 0 && mpj - m2p[i] < mind;
+      if (do_hist && w > 0.0 && !excl) {
         const double x = fmax(v, bmin + w);                           // ESL_MAX(cov, bmin+w), covariation.c:431
         const double bd = ceil(((x - bmin) / w) - 1.);                // esl_histogram_Score2Bin
         if (bd >= 0.0 && bd < (double) nbins) {
@@ -139,6 +155,7 @@ correct_hist_kernel(double *__restrict__ cov, const double *__restrict__ covx, c
           else                                  atomicAdd(&hist[b], 1ull);
         } else atomicOr(flags, 4);                                    // histogram capacity exceeded
       }
+    }
     }
   }
   #pragma unroll
@@ -203,10 +220,11 @@ __global__ void symmetrize_kernel(double *__restrict__ cov, int L, int Lp)
 // flagged in pairmask (the structure's contacts / base pairs, by data->samplesize), ht the others.
 __global__ void hist3_kernel(const double *__restrict__ cov, int L, int Lp, const uint8_t *__restrict__ pairmask, double bmin, double w,
                              int nb, unsigned long long *__restrict__ ha, unsigned long long *__restrict__ hb, unsigned long long *__restrict__ ht,
-                             int *__restrict__ flags)
+                             int *__restrict__ flags, const int *__restrict__ m2p, int mind)
 {
   const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
   if (j >= L || i >= j) return;
+  if (m2p && m2p[i] >= 0 && m2p[j] >= 0 && m2p[j] - m2p[i] < mind) return;          // covariation.c:421-427
   const double x  = fmax(cov[(size_t) i * Lp + j], bmin + w);
   const double bd = ceil(((x - bmin) / w) - 1.);
   if (!(bd >= 0.0 && bd < (double) nb)) { atomicOr(flags, 4); return; }
@@ -236,10 +254,10 @@ cudaError_t rsb_launch_correct_final(const double *rowpart, const double *colpar
 
 cudaError_t rsb_launch_correct_hist(double *cov, const double *covx, const double *scal, int nrep, int L, int Lp, int actype, int mode,
                                     double bmin, const double *wptr, unsigned long long *hist, int nbins, double *mm, double *minmax_out,
-                                    int *flags, int sr, int sw, cudaStream_t st)
+                                    int *flags, int sr, int sw, const int *m2p, int mind, cudaStream_t st)
 {
   int nJT, nIT; rsb_corr_grid(L, &nJT, &nIT);
-  rsb_coreside(correct_hist_kernel); correct_hist_kernel<<<dim3(nJT, nIT, nrep), CH_TJ, 0, st>>>(cov, covx, scal, L, Lp, actype, mode, bmin, wptr, hist, nbins, mm, flags, nJT, nIT, sr, sw);
+  rsb_coreside(correct_hist_kernel); correct_hist_kernel<<<dim3(nJT, nIT, nrep), CH_TJ, 0, st>>>(cov, covx, scal, L, Lp, actype, mode, bmin, wptr, hist, nbins, mm, flags, nJT, nIT, sr, sw, m2p, mind);
   rsb_coreside(minmax_final_kernel); minmax_final_kernel<<<nrep, 256, 0, st>>>(mm, nJT * nIT, minmax_out);
   return cudaGetLastError();
 }
@@ -257,8 +275,8 @@ cudaError_t rsb_launch_symmetrize(double *cov, int L, int Lp, cudaStream_t st)
 }
 
 cudaError_t rsb_launch_hist3(const double *cov, int L, int Lp, const uint8_t *pairmask, double bmin, double w, int nb,
-                             unsigned long long *ha, unsigned long long *hb, unsigned long long *ht, int *flags, cudaStream_t st)
+                             unsigned long long *ha, unsigned long long *hb, unsigned long long *ht, int *flags, const int *m2p, int mind, cudaStream_t st)
 {
-  hist3_kernel<<<dim3((L + 127) / 128, L), 128, 0, st>>>(cov, L, Lp, pairmask, bmin, w, nb, ha, hb, ht, flags);
+  hist3_kernel<<<dim3((L + 127) / 128, L), 128, 0, st>>>(cov, L, Lp, pairmask, bmin, w, nb, ha, hb, ht, flags, m2p, mind);
   return cudaGetLastError();
 }

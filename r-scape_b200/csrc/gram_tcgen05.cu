@@ -22,7 +22,12 @@
 namespace {
 
 constexpr int NSTAGE       = 4;
-constexpr int GRAM_THREADS = 256;
+constexpr int GRAM_THREADS = 256;              // CTA-pair kernel: warps 0-3 roles, warps 4-7 epilogue
+// single-CTA kernel: RSB_EPI_GROUPS groups of 4 epilogue warps; group g drains the columns [g, g+1) * cpg of every tile, so that
+// the latency of one tile's epilogue -- what the MMAs of the tile after next wait for -- is divided by the number of groups
+constexpr int GRAM_EPI_GROUPS = RSB_EPI_GROUPS;
+constexpr int GRAM1_THREADS   = 128 + 128 * GRAM_EPI_GROUPS;
+__host__ __device__ constexpr int gram_cols_per_group(int CJ, int E) { return ((CJ / 2 + E - 1) / E) * 2; }
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
 
@@ -80,16 +85,32 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
 
 // Epilogue of one tile, shared by the single-CTA and the CTA-pair kernels: this warp's 32 TMEM lanes (rows (i, a)) of the
 // accumulator at `trow` -> int64 count planes, and (part) the tile's marginal partial sums.  Returns the row partial.
-template <int S>
+//
+// REC (the G test on 16 classes, corr_CalculateGT_C16, src/correlators.c:361-395, for alignments whose counts nobody reads:
+// the nulls): instead of the 16 int64 counts (128 B) the epilogue leaves a 64-byte record per pair from which the statistic
+// follows with 14 multiply-adds once the marginals pm are known (gt_finish_kernel, stats.cu).  With the raw table
+// x_ab = 1e-10 + c_ab scale, X_a = sum_b x_ab, Y_b = sum_a x_ab, T = sum x, ne = nseff_ij (stats.cu, gt_c16_raw):
+//     G = 2 ne [ (sum x log x)/T - log T ]  -  sum_a (2 ne X_a/T) log pm_i[a]  -  sum_b (2 ne Y_b/T) log pm_j[b]
+//       =           A                       -  sum_a      U_a     log pm_i[a]  -  sum_b      V_b     log pm_j[b]
+// and, because sum_a U_a = sum_b V_b = 2 ne, only U_0..2, V_0..2 and N2 = 2 ne are stored:
+//     record planes  0: A   1: N2   2..4: U_0..U_2   5..7: V_0..V_2        (double [8][L][Lp], i < j; aliases the count planes)
+// The 17 logs per pair -- the FP64 work that needed a serial window of its own as a separate kernel -- are spread over the
+// 4 lanes that hold the pair's 16 cells and run here under the MMAs of the next tile.
+template <int S, bool REC>
 __device__ __forceinline__ double gram_epilogue_tile(uint32_t trow, int jb, int i, int a, int lane, int ew, int ib, int r, int L, int Lp,
                                                      long long *__restrict__ base, size_t plane, double scale, bool part,
-                                                     double *__restrict__ mcol, int nIB, bool small52)
+                                                     double *__restrict__ mcol, int nIB, bool small52, const double2 *__restrict__ ltab,
+                                                     int jl_begin = 0, int jl_end = rsb_cj_for(S))
 {
   constexpr int CJ = rsb_cj_for(S);
-  (void) Lp;
+  (void) Lp; (void) CJ;
   double racc = 0.0;                                               // marginal partial of row (i, a) over this tile's columns
+  // REC: this lane's record planes (row i): lanes a < 3 write U_a and V_a, lane 3 writes N2, lane 0 also A
+  double *const recrow = reinterpret_cast<double *>(base) - (size_t) a * 4 * plane;          // plane 0 of this slot, row i
+  double *const pU = recrow + (size_t) (a < 3 ? 2 + a : 1) * plane;
+  double *const pV = recrow + (size_t) (5 + (a < 3 ? a : 0)) * plane;
   #pragma unroll 1
-  for (int jl = 0; jl < CJ; jl += 2) {
+  for (int jl = jl_begin; jl < jl_end; jl += 2) {
     uint32_t d[2][S][4];
     #pragma unroll
     for (int u = 0; u < 2; u++)
@@ -111,7 +132,8 @@ __device__ __forceinline__ double gram_epilogue_tile(uint32_t trow, int jb, int 
       }
     const bool ok0 = (i < L) && (j0 < L)     && (i < j0);
     const bool ok1 = (i < L) && (j0 + 1 < L) && (i < j0 + 1);
-    if (ok0 && ok1) {
+    if (REC) {
+    } else if (ok0 && ok1) {
       #pragma unroll
       for (int b = 0; b < 4; b++)
         *reinterpret_cast<ulonglong2 *>(base + b * plane + j0) = make_ulonglong2(c[0][b], c[1][b]);
@@ -128,6 +150,7 @@ __device__ __forceinline__ double gram_epilogue_tile(uint32_t trow, int jb, int 
       // pair sit in 4 adjacent lanes (a = lane & 3) x 4 registers (b).  pp = (1e-10 + c scale) / sum; pairs with
       // nseff = 0 are skipped (:1354).  Fixed shuffle trees => deterministic.
       double x[2][4];
+      double rA[2], rU[2], rV[2];                                    // REC: this lane's record values of the two pairs
       #pragma unroll
       for (int u = 0; u < 2; u++) {
         #pragma unroll
@@ -138,10 +161,60 @@ __device__ __forceinline__ double gram_epilogue_tile(uint32_t trow, int jb, int 
         sum += __shfl_xor_sync(0xffffffffu, sum, 2);
         const unsigned nz  = __ballot_sync(0xffffffffu, (c[u][0] | c[u][1] | c[u][2] | c[u][3]) != 0ULL);
         const bool     use = (u ? ok1 : ok0) && ((nz >> (lane & ~3)) & 0xFu) != 0u;
-        const double   inv = use ? 1.0 / sum : 0.0;
-        racc = fma(rs, inv, racc);
-        #pragma unroll
-        for (int b = 0; b < 4; b++) x[u][b] *= inv;
+        if (REC) {
+          // sum x log x over the pair's 16 cells: 4 logs per lane (x >= 1e-10 and T >= 1.6e-9 are positive normals: no clamp)
+          double sl = x[u][0] * fast_log<false>(x[u][0], ltab);
+          sl = fma(x[u][1], fast_log<false>(x[u][1], ltab), sl);
+          double s2 = x[u][2] * fast_log<false>(x[u][2], ltab);
+          s2 = fma(x[u][3], fast_log<false>(x[u][3], ltab), s2);
+          sl += s2;
+          sl += __shfl_xor_sync(0xffffffffu, sl, 1);
+          sl += __shfl_xor_sync(0xffffffffu, sl, 2);
+          // Y_b = sum over the 4 lanes (a) of x[b], transposed so that lane a ends up with Y_a: 3 shuffles
+          const bool q2 = lane & 2, q1 = lane & 1;
+          const double k0 = q2 ? x[u][2] : x[u][0], k1 = q2 ? x[u][3] : x[u][1];
+          const double t0 = q2 ? x[u][0] : x[u][2], t1 = q2 ? x[u][1] : x[u][3];
+          const double h0 = k0 + __shfl_xor_sync(0xffffffffu, t0, 2), h1 = k1 + __shfl_xor_sync(0xffffffffu, t1, 2);
+          const double yb = (q1 ? h1 : h0) + __shfl_xor_sync(0xffffffffu, q1 ? h0 : h1, 1);
+          // nseff exactly: integer sum of the 16 counts
+          const unsigned long long nl = (c[u][0] + c[u][1]) + (c[u][2] + c[u][3]);
+          double ne;
+          if (small52) {                                              // every partial sum < 2^52: the double adds are exact
+            ne = u52_to_f64(nl);
+            ne += __shfl_xor_sync(0xffffffffu, ne, 1);
+            ne += __shfl_xor_sync(0xffffffffu, ne, 2);
+          } else {
+            unsigned long long nn = nl;
+            nn += __shfl_xor_sync(0xffffffffu, nn, 1);
+            nn += __shfl_xor_sync(0xffffffffu, nn, 2);
+            ne = u64_to_f64(nn);
+          }
+          const double n2   = 2.0 * (ne * scale);
+          const double invT = 1.0 / sum;
+          const double coef = n2 * invT;
+          rA[u] = fma(coef, sl, -n2 * fast_log<false>(sum, ltab));
+          rU[u] = (a < 3) ? coef * rs : n2;
+          rV[u] = coef * yb;
+          const double inv = use ? invT : 0.0;
+          racc = fma(rs, inv, racc);
+          #pragma unroll
+          for (int b = 0; b < 4; b++) x[u][b] *= inv;
+        } else {
+          const double   inv = use ? 1.0 / sum : 0.0;
+          racc = fma(rs, inv, racc);
+          #pragma unroll
+          for (int b = 0; b < 4; b++) x[u][b] *= inv;
+        }
+      }
+      if (REC) {
+        if (ok0 && ok1) {
+          *reinterpret_cast<double2 *>(pU + j0) = make_double2(rU[0], rU[1]);
+          if (a < 3)  *reinterpret_cast<double2 *>(pV + j0) = make_double2(rV[0], rV[1]);
+          if (a == 0) *reinterpret_cast<double2 *>(recrow + j0) = make_double2(rA[0], rA[1]);
+        } else {
+          if (ok0) { pU[j0] = rU[0];     if (a < 3) pV[j0] = rV[0];     if (a == 0) recrow[j0] = rA[0]; }
+          if (ok1) { pU[j0 + 1] = rU[1]; if (a < 3) pV[j0 + 1] = rV[1]; if (a == 0) recrow[j0 + 1] = rA[1]; }
+        }
       }
       // column partials: 8 values (u, b) summed over the warp's 32 lanes by a halving butterfly -- after the three
       // halving steps a lane keeps (u, b) = (bit 4, bits 3:2 of its lane id), then two full steps sum over a
@@ -175,11 +248,12 @@ __device__ __forceinline__ double gram_epilogue_tile(uint32_t trow, int jb, int 
 __device__ unsigned long long *gram_trace_buf;
 #endif
 
-template <int S>
-__global__ void __launch_bounds__(GRAM_THREADS, 1)
+template <int S, bool REC>
+__global__ void __launch_bounds__(RSB_GRAM_BOUND > GRAM1_THREADS ? RSB_GRAM_BOUND : GRAM1_THREADS, 1)
 gram_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
                const int2 *__restrict__ tiles, int ntiles, int rep0, int nrep, int L, int Lp, int kstages,
-               long long *__restrict__ cnt, double scale, double *__restrict__ mrow, double *__restrict__ mcol, int nJB, int nIB, int small52)
+               long long *__restrict__ cnt, double scale, double *__restrict__ mrow, double *__restrict__ mcol, int nJB, int nIB, int small52,
+               const double2 *__restrict__ glogtab)
 {
   constexpr int      CJ          = rsb_cj_for(S);
   constexpr int      NT          = 4 * S * CJ;                 // UMMA N
@@ -201,18 +275,24 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * NSTAGE + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * NSTAGE + 4);
   volatile uint32_t *tmem_slot_ptr = (volatile uint32_t *) (smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  // REC: the log table of the statistic (rsb_common.cuh, fast_log), 8 KB behind the barriers
+  const double2 *ltab = reinterpret_cast<const double2 *>(smem_raw + (bar_base + 128u - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < NSTAGE; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; a++)      { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
+    for (int a = 0; a < 2; a++)      { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128 * GRAM_EPI_GROUPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tmem_slot), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (REC && warp >= 4) {
+    double2 *dst = const_cast<double2 *>(ltab);
+    for (int k = threadIdx.x - 128; k < LOGTAB_N; k += 128 * GRAM_EPI_GROUPS) dst[k] = glogtab[k];
   }
   tc_fence_before();
   __syncthreads();
@@ -265,7 +345,10 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue: TMEM -> int64 count planes
-    const int ew = warp - 4;                                       // TMEM lane quarter owned by this warp
+    const int ew = (warp - 4) & 3;                                 // TMEM lane quarter owned by this warp (= warp id % 4)
+    const int eg = (warp - 4) >> 2;                                // epilogue group: its share of every tile's columns
+    constexpr int CPG = gram_cols_per_group(rsb_cj_for(S), GRAM_EPI_GROUPS);
+    const int jl0 = eg * CPG, jl1 = (jl0 + CPG < rsb_cj_for(S)) ? jl0 + CPG : rsb_cj_for(S);
     const int m  = ew * 32 + lane;                                 // accumulator row = planeA row within the tile
     const int il = m >> 2, a = m & 3;
     int acc = 0; uint32_t acc_phase = 0;
@@ -280,8 +363,8 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t) (ew * 32) << 16) + (uint32_t) acc * 256u;
 
-      const double racc = gram_epilogue_tile<S>(trow, t.y, i, a, lane, ew, t.x, r, L, Lp, base, plane, scale, mrow != nullptr, mcol, nIB, small52 != 0);
-      if (mrow != nullptr && i < L) mrow[(((size_t) r * nJB + t.y) * L + i) * 4 + a] = racc;
+      const double racc = gram_epilogue_tile<S, REC>(trow, t.y, i, a, lane, ew, t.x, r, L, Lp, base, plane, scale, mrow != nullptr, mcol, nIB, small52 != 0, ltab, jl0, jl1);
+      if (mrow != nullptr && i < L) mrow[((((size_t) r * nJB + t.y) * GRAM_EPI_GROUPS + eg) * L + i) * 4 + a] = racc;
       tc_fence_before();
       mbar_arrive(tempty_bar(acc));
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
@@ -444,7 +527,7 @@ gram_i8_pair_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t) (ew * 32) << 16) + (uint32_t) acc * 256u;
-      const double racc = gram_epilogue_tile<S>(trow, t.y, i, a, lane, ew, ib, r, L, Lp, base, plane, scale, part, mcol, nIB, small52 != 0);
+      const double racc = gram_epilogue_tile<S, false>(trow, t.y, i, a, lane, ew, ib, r, L, Lp, base, plane, scale, part, mcol, nIB, small52 != 0, nullptr);
       if (part && i < L) mrow[(((size_t) r * nJB + t.y) * L + i) * 4 + a] = racc;
       tc_fence_before();
       mbar_arrive_leader(tempty_bar(acc));
@@ -465,22 +548,22 @@ template <int S> constexpr size_t gram_pair_smem_bytes() {
   return (size_t) NSTAGE2 * (RSB_MTILE * RSB_KSTAGE + 2 * S * rsb_cj_for(S) * RSB_KSTAGE) + 8 * (2 * NSTAGE2 + 4) + 16 + 1024;
 }
 
-template <int S> constexpr size_t gram_smem_bytes() {
-  return (size_t) NSTAGE * (RSB_MTILE * RSB_KSTAGE + 4 * S * rsb_cj_for(S) * RSB_KSTAGE) + 8 * (2 * NSTAGE + 4) + 16 + 1024;
+template <int S, bool REC> constexpr size_t gram_smem_bytes() {
+  return (size_t) NSTAGE * (RSB_MTILE * RSB_KSTAGE + 4 * S * rsb_cj_for(S) * RSB_KSTAGE) + 128 + (REC ? sizeof(double2) * LOGTAB_N : 0) + 1024;
 }
 
-template <int S>
+template <int S, bool REC>
 cudaError_t launch_gram(const CUtensorMap &tmA, const CUtensorMap &tmB, const int2 *tiles, int ntiles, int rep0, int nrep,
                         int L, int Lp, int kstages, long long *cnt, double scale, double *mrow, double *mcol, int nJB, int nIB,
-                        int small52, int grid, cudaStream_t st)
+                        int small52, int grid, const double2 *logtab, cudaStream_t st)
 {
-  constexpr size_t smem = gram_smem_bytes<S>();
-  cudaError_t e = cudaFuncSetAttribute(gram_i8_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+  constexpr size_t smem = gram_smem_bytes<S, REC>();
+  cudaError_t e = cudaFuncSetAttribute(gram_i8_kernel<S, REC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
   if (e != cudaSuccess) return e;
   // the ring takes ~190 KB; with the SM's carve-out at its maximum (228 KB) the rest is left for the blocks of the
   // statistics chain, which run beside this kernel (a 196 KB carve-out would leave them no shared memory at all)
-  rsb_coreside(gram_i8_kernel<S>);
-  gram_i8_kernel<S><<<grid, GRAM_THREADS, smem, st>>>(tmA, tmB, tiles, ntiles, rep0, nrep, L, Lp, kstages, cnt, scale, mrow, mcol, nJB, nIB, small52);
+  rsb_coreside(gram_i8_kernel<S, REC>);
+  gram_i8_kernel<S, REC><<<grid, GRAM1_THREADS, smem, st>>>(tmA, tmB, tiles, ntiles, rep0, nrep, L, Lp, kstages, cnt, scale, mrow, mcol, nJB, nIB, small52, logtab);
   return cudaGetLastError();
 }
 
@@ -519,19 +602,21 @@ int pair_clusters()
 } // namespace
 
 // Host entry used by capi.cu.  tmA/tmB are 3-D tensor maps {Kpad, rows, replicate} with 128B swizzle
-// and boxes {128, 128, 1} / {128, 4*S*CJ, 1}.
+// and boxes {128, 128, 1} / {128, 4*S*CJ, 1}.  logtab != NULL selects the record epilogue (G test, 16 classes): the slot's
+// count planes then hold double [8][L][Lp] records instead of counts, and mrow / mcol must be given.
 cudaError_t rsb_launch_gram_i8(int S, const CUtensorMap &tmA, const CUtensorMap &tmB, const int2 *tiles, int ntiles,
                                int rep0, int nrep, int L, int Lp, int kstages, long long *cnt, double scale, double *mrow,
-                               double *mcol, int nJB, int nIB, int small52, int grid, cudaStream_t st)
+                               double *mcol, int nJB, int nIB, int small52, int grid, const void *logtab, cudaStream_t st)
 {
+  const double2 *lt = (const double2 *) logtab;
+  if (lt && !(mrow && mcol)) return cudaErrorInvalidValue;
+#define RSB_GRAM_CASE(SS) \
+  case SS: return lt ? launch_gram<SS, true>(tmA, tmB, tiles, ntiles, rep0, nrep, L, Lp, kstages, cnt, scale, mrow, mcol, nJB, nIB, small52, grid, lt, st) \
+                     : launch_gram<SS, false>(tmA, tmB, tiles, ntiles, rep0, nrep, L, Lp, kstages, cnt, scale, mrow, mcol, nJB, nIB, small52, grid, nullptr, st);
   switch (S) {
-  case 1: return launch_gram<1>(tmA, tmB, tiles, ntiles, rep0, nrep, L, Lp, kstages, cnt, scale, mrow, mcol, nJB, nIB, small52, grid, st);
-  case 2: return launch_gram<2>(tmA, tmB, tiles, ntiles, rep0, nrep, L, Lp, kstages, cnt, scale, mrow, mcol, nJB, nIB, small52, grid, st);
-  case 3: return launch_gram<3>(tmA, tmB, tiles, ntiles, rep0, nrep, L, Lp, kstages, cnt, scale, mrow, mcol, nJB, nIB, small52, grid, st);
-  case 4: return launch_gram<4>(tmA, tmB, tiles, ntiles, rep0, nrep, L, Lp, kstages, cnt, scale, mrow, mcol, nJB, nIB, small52, grid, st);
-  case 5: return launch_gram<5>(tmA, tmB, tiles, ntiles, rep0, nrep, L, Lp, kstages, cnt, scale, mrow, mcol, nJB, nIB, small52, grid, st);
-  case 6: return launch_gram<6>(tmA, tmB, tiles, ntiles, rep0, nrep, L, Lp, kstages, cnt, scale, mrow, mcol, nJB, nIB, small52, grid, st);
+  RSB_GRAM_CASE(1) RSB_GRAM_CASE(2) RSB_GRAM_CASE(3) RSB_GRAM_CASE(4) RSB_GRAM_CASE(5) RSB_GRAM_CASE(6)
   }
+#undef RSB_GRAM_CASE
   return cudaErrorInvalidValue;
 }
 
@@ -550,6 +635,9 @@ cudaError_t rsb_launch_gram_i8_pair(int S, const CUtensorMap &tmA, const CUtenso
   default: return cudaErrorInvalidValue;
   }
 }
+
+// row-partial blocks per tile column block jb in mrow: one per epilogue group (single-CTA kernel), one (CTA-pair kernel)
+int rsb_gram_mrow_blocks(int pair) { return pair ? 1 : GRAM_EPI_GROUPS; }
 
 int rsb_gram_pair_clusters(int S)
 {

@@ -25,6 +25,12 @@
 #define RSB_ICOLS  32
 #define RSB_KSTAGE 128          // bytes of K (sequences) per pipeline stage = one 128B swizzle atom
 #define RSB_MAX_SLICES 6
+#ifndef RSB_EPI_GROUPS
+#define RSB_EPI_GROUPS 2        // groups of 4 epilogue warps in the tcgen05 kernel (gram_tcgen05.cu)
+#endif
+#ifndef RSB_GRAM_BOUND
+#define RSB_GRAM_BOUND 0        // thread count declared in the tcgen05 kernel's __launch_bounds__ when larger than its real one: caps its
+#endif                          // registers (65536 / bound) so that blocks of the statistics chain fit beside it
 // pair-tile of the HBM-bound passes (marginals, statistic, correction, histogram): a block owns
 // RSB_TI rows x RSB_TJ columns of the upper triangle, one thread per column j
 #define RSB_TI     16
@@ -64,6 +70,27 @@ __device__ __forceinline__ double u64_to_f64(unsigned long long v)
 __device__ __forceinline__ double u52_to_f64(unsigned long long v)
 {
   return __longlong_as_double(0x4330000000000000ULL | v) - 4503599627370496.0;
+}
+
+// natural log from a 512-entry table in shared memory: x = 2^e m, m = c (1 + r) with c the centre of m's 1/512 bin, so
+// |r| <= 2^-10 and log1p(r) = r - r^2/2 + r^3/3 - r^4/4 (truncation 2^-52).  8 FP64 operations and no branch, against
+// ~40 and a branchy special-case path for the library log; absolute error <= 4e-16 + 1 ulp(e ln 2).  Arguments are
+// clamped to the smallest normal double: every call site multiplies the log of a zero/subnormal probability by that
+// probability (or discards it under a `> 0` guard), so the clamp never changes a result.  tab[k] = { 1/c_k rounded,
+// -log of that }, built once per context by logtab_kernel and copied to shared memory by each block.
+constexpr int LOGTAB_N = 512;
+template <bool CLAMP = true>
+__device__ __forceinline__ double fast_log(double x, const double2 *__restrict__ tab)
+{
+  if (CLAMP) x = fmax(x, 2.2250738585072014e-308);                  // (not needed where the argument is known to be a positive normal)
+  const int hi = __double2hiint(x), lo = __double2loint(x);
+  const double m  = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
+  const double2 t = tab[(hi >> 11) & (LOGTAB_N - 1)];
+  const double r  = fma(m, t.x, -1.0);
+  const double e  = __hiloint2double(0x43300000, ((hi >> 20) - 1023) ^ 0x80000000) - 4503601774854144.0;   // 2^52 + 2^31
+  double p = fma(r, -0.25, 1.0 / 3.0);
+  p = fma(p, r, -0.5);
+  return fma(e, 0.6931471805599453094, t.y) + fma(p, r * r, r);
 }
 
 // does the gram tile (ib, jb) exist?  Same rule as build_geo (capi.cu): it holds some pair i < j and its row block is

@@ -76,13 +76,6 @@ __device__ __forceinline__ void load_pair(const long long *__restrict__ cnt, siz
   }
 }
 
-// natural log from a 512-entry table in shared memory: x = 2^e m, m = c (1 + r) with c the centre of m's 1/512 bin, so
-// |r| <= 2^-10 and log1p(r) = r - r^2/2 + r^3/3 - r^4/4 (truncation 2^-52).  8 FP64 operations and no branch, against
-// ~40 and a branchy special-case path for the library log; absolute error <= 4e-16 + 1 ulp(e ln 2).  Arguments are
-// clamped to the smallest normal double: every call site multiplies the log of a zero/subnormal probability by that
-// probability (or discards it under a `> 0` guard), so the clamp never changes a result.  tab[k] = { 1/c_k rounded,
-// -log of that }, built once per context by logtab_kernel and copied to shared memory by each block.
-constexpr int LOGTAB_N = 512;
 __global__ void logtab_kernel(double2 *tab)
 {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -94,20 +87,6 @@ __global__ void logtab_kernel(double2 *tab)
 __device__ __forceinline__ void logtab_load(double2 *tab, const double2 *__restrict__ gtab)
 {
   for (int k = threadIdx.x; k < LOGTAB_N; k += blockDim.x) tab[k] = gtab[k];
-}
-
-template <bool CLAMP = true>
-__device__ __forceinline__ double fast_log(double x, const double2 *__restrict__ tab)
-{
-  if (CLAMP) x = fmax(x, 2.2250738585072014e-308);                  // (not needed where the argument is known to be a positive normal)
-  const int hi = __double2hiint(x), lo = __double2loint(x);
-  const double m  = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
-  const double2 t = tab[(hi >> 11) & (LOGTAB_N - 1)];
-  const double r  = fma(m, t.x, -1.0);
-  const double e  = __hiloint2double(0x43300000, ((hi >> 20) - 1023) ^ 0x80000000) - 4503601774854144.0;   // 2^52 + 2^31
-  double p = fma(r, -0.25, 1.0 / 3.0);
-  p = fma(p, r, -0.5);
-  return fma(e, 0.6931471805599453094, t.y) + fma(p, r * r, r);
 }
 
 // raw (unnormalised) pair table for the statistics that can work on it: x_k = 1e-10 + c_k scale, T = sum x, ne
@@ -180,21 +159,22 @@ __device__ __forceinline__ double warp_sum(double v)
 // sharded over ranks these are the vectors that are summed across ranks before normalisation.
 __global__ void __launch_bounds__(256)
 marg_sum_kernel(const double *__restrict__ mrow, const double *__restrict__ mcol, int L, int CJ, int nJB, int nIB,
-                int sr, int sw, double *__restrict__ msum)
+                int sr, int sw, double *__restrict__ msum, int E)
 {
   const int lane = threadIdx.x & 31;
   const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), r = blockIdx.y;
   if (c >= L) return;
   const int ib_c = c / RSB_ICOLS, jb_c = c / CJ;
+  const int nR = nJB * E;                                             // row-partial blocks: E per tile column block (one per epilogue group)
   double m[4] = { 0, 0, 0, 0 };
-  for (int k = lane; k < nJB + 4 * nIB; k += 32) {
+  for (int k = lane; k < nR + 4 * nIB; k += 32) {
     const double *src;
-    if (k < nJB) {
-      if (!rsb_tile_exists(ib_c, k, CJ, L, sr, sw)) continue;
-      src = mrow + (((size_t) r * nJB + k) * L + c) * 4;
+    if (k < nR) {
+      if (!rsb_tile_exists(ib_c, k / E, CJ, L, sr, sw)) continue;
+      src = mrow + (((size_t) r * nR + k) * L + c) * 4;
     } else {
-      if (!rsb_tile_exists((k - nJB) >> 2, jb_c, CJ, L, sr, sw)) continue;
-      src = mcol + (((size_t) r * 4 * nIB + (k - nJB)) * L + c) * 4;
+      if (!rsb_tile_exists((k - nR) >> 2, jb_c, CJ, L, sr, sw)) continue;
+      src = mcol + (((size_t) r * 4 * nIB + (k - nR)) * L + c) * 4;
     }
     const double2 lo = *reinterpret_cast<const double2 *>(src), hi = *reinterpret_cast<const double2 *>(src + 2);
     m[0] += lo.x; m[1] += lo.y; m[2] += hi.x; m[3] += hi.y;
@@ -397,6 +377,116 @@ stat_kernel(const long long *__restrict__ cnt, const double *__restrict__ pm, co
 #endif
 }
 
+// G test on 16 classes from the per-pair records left by the record epilogue of the tcgen05 kernel (gram_tcgen05.cu): with
+// l_i[a] = log pm_i[a],
+//     G_ij = A - [ N2 l_i[3] + sum_{a<3} U_a (l_i[a] - l_i[3]) ] - [ N2 l_j[3] + sum_{b<3} V_b (l_j[b] - l_j[3]) ]
+// (corr_CalculateGT_C16, src/correlators.c:383-387; pairs with nseff = 0 carry an all-zero record and score 0, as the
+// reference's `exp > 0 && obs > 0` guard leaves them).  64 B read + 8 B written per pair and 14 multiply-adds: HBM-bound, so
+// unlike stat_kernel it can run beside the contraction.  Same tiling, partial sums and min/max as stat_kernel.
+__global__ void __launch_bounds__(ST_TJ, 5)
+gt_finish_kernel(const double *__restrict__ rec, const double *__restrict__ pm, int L, int Lp, double *__restrict__ cov,
+                 double *__restrict__ rowpart, double *__restrict__ colpart, double *__restrict__ mm, int nJT, int nIT, int sr, int sw,
+                 size_t slot_stride)
+{
+  __shared__ double rowacc[ST_TJ / 32][ST_TI];
+  __shared__ double li[ST_TI][4];                                    // { l_i[0]-l_i[3], l_i[1]-l_i[3], l_i[2]-l_i[3], l_i[3] }
+  __shared__ double smin[ST_TJ / 32], smax[ST_TJ / 32];
+  const int jt = blockIdx.x, it = blockIdx.y, r = blockIdx.z;
+  const int j  = jt * ST_TJ + threadIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t plane = (size_t) L * Lp;
+  const double *R = rec + (size_t) r * slot_stride;
+  const bool tile_live = (it * ST_TI) < (jt * ST_TJ + ST_TJ - 1) && RSB_OWNED(it, sr, sw);
+  double col = 0.0, vmin = INFINITY, vmax = -INFINITY;
+
+  if (threadIdx.x < ST_TI) {
+    const int i = it * ST_TI + threadIdx.x;
+    double l[4];
+    #pragma unroll
+    for (int a = 0; a < 4; a++) { const double p = (i < L) ? pm[((size_t) r * L + i) * 4 + a] : 0.25; l[a] = (p > 0.0) ? log(p) : 0.0; }
+    li[threadIdx.x][0] = l[0] - l[3]; li[threadIdx.x][1] = l[1] - l[3]; li[threadIdx.x][2] = l[2] - l[3]; li[threadIdx.x][3] = l[3];
+  }
+  double lj[4] = { 0.0, 0.0, 0.0, 0.0 };
+  if (tile_live && j < L) {
+    double l[4];
+    #pragma unroll
+    for (int b = 0; b < 4; b++) { const double p = pm[((size_t) r * L + j) * 4 + b]; l[b] = (p > 0.0) ? log(p) : 0.0; }
+    lj[0] = l[0] - l[3]; lj[1] = l[1] - l[3]; lj[2] = l[2] - l[3]; lj[3] = l[3];
+  }
+  __syncthreads();
+
+  // the kernel runs beside the persistent tcgen05 kernel, at a few blocks per SM: the loads of FIN_U rows (8 planes each) are
+  // issued together so that the few resident warps keep enough bytes in flight
+  constexpr int FIN_U = 4;
+  #pragma unroll 1
+  for (int il0 = 0; il0 < ST_TI; il0 += FIN_U) {
+    double q[FIN_U][8];
+    bool ok[FIN_U];
+    #pragma unroll
+    for (int u = 0; u < FIN_U; u++) {
+      const int i = it * ST_TI + il0 + u;
+      ok[u] = tile_live && i < L && j < L && i < j;
+      const double *p = R + (size_t) i * Lp + j;
+      #pragma unroll
+      for (int k = 0; k < 8; k++) q[u][k] = ok[u] ? __ldcs(p + k * plane) : 0.0;
+    }
+    #pragma unroll
+    for (int u = 0; u < FIN_U; u++) {
+      const int il = il0 + u, i = it * ST_TI + il;
+      double v = 0.0;
+      if (ok[u]) {
+        double m = q[u][1] * (li[il][3] + lj[3]);
+        m = fma(q[u][2], li[il][0], m); m = fma(q[u][3], li[il][1], m); m = fma(q[u][4], li[il][2], m);
+        m = fma(q[u][5], lj[0], m);     m = fma(q[u][6], lj[1], m);     m = fma(q[u][7], lj[2], m);
+        v = q[u][0] - m;
+        cov[((size_t) r * L + i) * Lp + j] = v;
+        col += v;
+        vmin = fmin(vmin, v);
+        vmax = fmax(vmax, v);
+      }
+      const double rs = warp_sum(v);
+      if (lane == 0) rowacc[warp][il] = rs;
+    }
+  }
+  if (j < L) colpart[((size_t) r * nIT + it) * L + j] = col;
+  #pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    vmin = fmin(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+    vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+  }
+  if (lane == 0) { smin[warp] = vmin; smax[warp] = vmax; }
+  __syncthreads();
+  if (threadIdx.x < ST_TI) {
+    const int i = it * ST_TI + threadIdx.x;
+    if (i < L) {
+      double v = 0.0;
+      #pragma unroll
+      for (int w = 0; w < ST_TJ / 32; w++) v += rowacc[w][threadIdx.x];
+      rowpart[((size_t) r * nJT + jt) * L + i] = v;
+    }
+  }
+  if (threadIdx.x == 0) {
+    double a = smin[0], b = smax[0];
+    #pragma unroll
+    for (int w = 1; w < ST_TJ / 32; w++) { a = fmin(a, smin[w]); b = fmax(b, smax[w]); }
+    double *o = mm + (((size_t) r * nIT + it) * nJT + jt) * 2;
+    o[0] = a; o[1] = b;
+  }
+}
+
+// nseff / ngap in the host layout from a slot that holds records instead of counts (quirk Q3, rsb_last_nseff): nseff = N2 / 2
+// (exact), ngap = wtot scale - nseff
+__global__ void export_nseff_rec_kernel(const double *__restrict__ rec, int L, int Lp, double wtot_scaled, double *__restrict__ nseff, double *__restrict__ ngap)
+{
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+  if (j >= L) return;
+  if (i >= j) { ngap[(size_t) i * L + j] = 0.0; if (i == j) nseff[(size_t) i * L + j] = 0.0; return; }
+  const double ne = 0.5 * rec[(size_t) L * Lp + (size_t) i * Lp + j];
+  nseff[(size_t) i * L + j] = ne;
+  nseff[(size_t) j * L + i] = ne;
+  ngap[(size_t) i * L + j]  = wtot_scaled - ne;
+}
+
 // RAF from the UNWEIGHTED count table (planes built with wq = 1, S = 1): integer arithmetic up to the
 // final divisions, so the result is bit-identical to the reference's O(N^2) loop (:903-918).
 __global__ void __launch_bounds__(ST_TJ)
@@ -593,10 +683,10 @@ void rsb_stat_grid(int L, int *nJT, int *nIT) { *nJT = (L + ST_TJ - 1) / ST_TJ; 
 
 // phase: 1 = sum the tile partials (-> msum), 2 = normalise msum -> pm, 3 = both
 cudaError_t rsb_launch_marginals(const double *mrow, const double *mcol, int nrep, int L, int CJ, int nJB, int nIB, double tol,
-                                 double *msum, double *pm, int *flags, int sr, int sw, int phase, cudaStream_t st)
+                                 double *msum, double *pm, int *flags, int sr, int sw, int phase, int mrow_blocks, cudaStream_t st)
 {
   if (phase & 1) {
-    rsb_coreside(marg_sum_kernel); marg_sum_kernel<<<dim3((L + 7) / 8, nrep), 256, 0, st>>>(mrow, mcol, L, CJ, nJB, nIB, sr, sw, msum);
+    rsb_coreside(marg_sum_kernel); marg_sum_kernel<<<dim3((L + 7) / 8, nrep), 256, 0, st>>>(mrow, mcol, L, CJ, nJB, nIB, sr, sw, msum, mrow_blocks);
   }
   rsb_coreside(marg_norm_kernel);
   if (phase & 2) marg_norm_kernel<<<dim3((L + 127) / 128, nrep), 128, 0, st>>>(msum, L, tol, pm, flags);
@@ -642,6 +732,21 @@ cudaError_t rsb_launch_statistic(int stat, int cls, const long long *cnt, const 
   case RSB_MIg  * 4 + RSB_C2:  RSB_STAT_CASE(RSB_MIg,  RSB_C2)
   default: return cudaErrorInvalidValue;
   }
+  return cudaGetLastError();
+}
+
+cudaError_t rsb_launch_gt_finish(const double *rec, size_t slot_stride, const double *pm, int nrep, int L, int Lp, double *cov,
+                                 double *rowpart, double *colpart, double *mm, int sr, int sw, cudaStream_t st)
+{
+  int nJT, nIT; rsb_stat_grid(L, &nJT, &nIT);
+  rsb_coreside(gt_finish_kernel);
+  gt_finish_kernel<<<dim3(nJT, nIT, nrep), ST_TJ, 0, st>>>(rec, pm, L, Lp, cov, rowpart, colpart, mm, nJT, nIT, sr, sw, slot_stride);
+  return cudaGetLastError();
+}
+
+cudaError_t rsb_launch_export_nseff_rec(const double *rec, int L, int Lp, double wtot_scaled, double *nseff, double *ngap, cudaStream_t st)
+{
+  export_nseff_rec_kernel<<<dim3((L + 127) / 128, L), 128, 0, st>>>(rec, L, Lp, wtot_scaled, nseff, ngap);
   return cudaGetLastError();
 }
 

@@ -123,23 +123,37 @@ cov_GrowRankList(RANKLIST **oranklist, double bmax, double bmin)
 }
 
 int
-cov_RankListFromCOV(struct data_s *data, RANKLIST **ret_ranklist)
+cov_RankListFromCOV_b200(struct data_s *data, const uint8_t *pairmask, RANKLIST **ret_ranklist)
 {
   struct mutual_s *mi = data->mi;
   RANKLIST *rl;
   double    bmax = mi->maxCOV + 5 * data->w, add;
-  int       i, j;
+  int64_t   L = mi->alen, i, j;
+  int       mind = data->msa2pdb ? RSB_DATA_MIND(data) : 1;
+  int       two_sets = (data->mode == GIVSS || data->mode == FOLDSS);                /* :436 */
+  int       select;
 
+  *ret_ranklist = NULL;
   while (fabs(bmax - data->bmin) < data->tol) bmax += data->w;
   if ((rl = cov_CreateRankList(bmax, data->bmin, data->w)) == NULL) ESL_FAIL(eslFAIL, data->errbuf, "rank list allocation failed");
-  for (i = 0; i < mi->alen - 1; i++)
-    for (j = i + 1; j < mi->alen; j++) {
-      if (data->msa2pdb && data->clist == NULL) continue;                          /* PDB distance filter needs R-view's CLIST: out of scope */
+  for (i = 0; i < L - 1; i++)
+    for (j = i + 1; j < L; j++) {
+      if (data->msa2pdb && data->msa2pdb[i] >= 0 && data->msa2pdb[j] >= 0 && data->msa2pdb[j] - data->msa2pdb[i] < mind) continue;   /* :421-427 */
       add = ESL_MAX(mi->COV->mx[i][j], data->bmin + data->w);
       esl_histogram_Add(rl->ha, add);
+      if (two_sets) {
+        select = (data->samplesize != SAMPLE_ALL && pairmask) ? (pairmask[(size_t) i * (size_t) L + (size_t) j] != 0) : FALSE;
+        esl_histogram_Add(select ? rl->hb : rl->ht, add);
+      }
     }
   *ret_ranklist = rl;
   return eslOK;
+}
+
+int
+cov_RankListFromCOV(struct data_s *data, RANKLIST **ret_ranklist)
+{
+  return cov_RankListFromCOV_b200(data, NULL, ret_ranklist);
 }
 
 int
@@ -221,7 +235,8 @@ null_rscape_b200(struct data_s *data, ESL_MSA **nulls, int nnull, int hpts, RANK
   slots = slots_for((int) N, (int) L, nnull);
   if (rsb_create(device, NULL, &ctx) != 0) { snprintf(data->errbuf, eslERRBUFSIZE, "%s", rsb_create_error()); goto DONE; }
   if (rsb_configure(ctx, (int) N, (int) L, slots, slices) != 0 ||
-      rsb_set_weights(ctx, nulls[0]->wgt) != 0)                                    /* nulls carry the input's weights (:1668) */
+      rsb_set_weights(ctx, nulls[0]->wgt) != 0 ||                                  /* nulls carry the input's weights (:1668) */
+      (data->msa2pdb && rsb_set_pair_exclusion(ctx, data->msa2pdb, RSB_DATA_MIND(data)) != 0))   /* covariation.c:421-427 */
     { snprintf(data->errbuf, eslERRBUFSIZE, "%s", rsb_error(ctx)); goto DONE; }
 
   stage  = malloc((size_t) slots * N * L);
@@ -326,6 +341,9 @@ cov_CreateHitList_b200(struct data_s *data, struct mutual_s *mi, RANKLIST *rankl
   if ((hitlist = calloc(1, sizeof(HITLIST))) == NULL) goto ERROR;
   hitlist->Nt = (int64_t) ranklist->ht->Nc;                                         /* :811-812 */
   hitlist->Nb = (int64_t) ranklist->hb->Nc;
+
+  if (null != NULL && ranklist->ht->Nc + ranklist->hb->Nc == 0)                    /* every E-value would be pval * 0 */
+    ESL_XFAIL(eslFAIL, data->errbuf, "cov_CreateHitList_b200: the rank list's ht / hb histograms are empty (fill them with cov_RankListFromCOV_b200 in GIVSS or FOLDSS mode)");
 
   if (null == NULL) {                          /* naive method: E-values carry no significance, every pair has pval = eval = 0 (:844-847) */
     nhit = (0. < data->thresh->val || all) ? P : 0;

@@ -130,3 +130,67 @@ def test_scan_histograms_ha_hb_ht(ctx, pkg, po, oracle):
     b = np.ceil((x - bmin) / w - 1).astype(int)
     want_hb = np.bincount(b[mask[iu] > 0], minlength=v.nb)
     assert np.array_equal(hb, want_hb.astype(np.uint64))
+
+
+@pytest.mark.parametrize("N,L,R,S", [(300, 150, 5, 0), (257, 97, 3, 5), (64, 40, 4, 1)])
+def test_record_epilogue_equals_count_path(pkg, po, oracle, monkeypatch, N, L, R, S):
+    """Nulls scored with GT x C16 take the record epilogue of the tcgen05 kernel (64-byte records + gt_finish_kernel) instead of
+    int64 counts + stat_kernel.  Both paths against the oracle and against each other: identical integer bins, min/max within
+    1e-12, nseff/ngap of the last null identical (quirk Q3)."""
+    nulls = _nulls(po, R, N, L, 900)
+    wgt = po.synthetic_msa(N, L, seed=5)[1] if S != 1 else np.ones(N)
+    w_ref, view, mm_ref = oracle_null_loop(po, oracle, nulls, wgt, po.GT, po.C16, po.APC)
+    out = {}
+    for fused in ("1", "0"):
+        monkeypatch.setenv("RSCAPE_B200_FUSED_GT", fused)
+        c = pkg.Context(0)
+        c.configure(N, L, 2, S)
+        c.set_weights(wgt)
+        w, mn, mx = c.null_width(nulls[0])
+        mm = c.null_hist(nulls, w_ref)
+        bins, n, imax = c.hist_read(view.nb + 8)
+        ne, ng = c.last_nseff()
+        out[fused] = (w, mn, mx, mm, bins, n, ne, ng)
+        c.close()
+        assert abs(w - w_ref) <= 1e-12 * max(1.0, w_ref)
+        assert n == view.n
+        assert_bins_identical(bins, view.obs, oracle_null_loop.scores, -10.0, w_ref)
+        assert np.max(np.abs(mm - mm_ref)) <= 1e-9 * max(1.0, np.max(np.abs(mm_ref)))
+    a, b = out["1"], out["0"]
+    assert np.array_equal(a[4], b[4])                                                    # the two device paths: same bins
+    assert np.max(np.abs(a[3] - b[3])) <= 1e-11 * max(1.0, np.max(np.abs(b[3])))
+    assert np.array_equal(a[6], b[6]) and np.array_equal(a[7], b[7])
+
+
+def test_pdb_distance_rule_keeps_pairs_out_of_the_histograms(ctx, pkg, po, oracle):
+    """src/covariation.c:421-427: pairs with both columns in the PDB sequence and closer than `mind` are skipped by the histogram
+    fill (null and input alignment alike); scores and min/max are not affected."""
+    N, L, R = 150, 64, 3
+    nulls = _nulls(po, R, N, L, 40)
+    wgt = po.synthetic_msa(N, L, seed=6)[1]
+    rng = np.random.default_rng(0)
+    m2p = np.where(rng.random(L) < 0.8, np.cumsum(rng.integers(1, 3, L)), -1).astype(np.int32)
+    mind = 5
+    iu = np.triu_indices(L, 1)
+    keep = ~((m2p[iu[0]] >= 0) & (m2p[iu[1]] >= 0) & (m2p[iu[1]] - m2p[iu[0]] < mind))
+    assert 0 < keep.sum() < keep.size
+    w_ref, view, mm_ref = oracle_null_loop(po, oracle, nulls, wgt, po.GT, po.C16, po.APC)
+    sc = oracle_null_loop.scores.reshape(R, -1)
+    x = np.maximum(sc[:, keep].ravel(), -10.0 + w_ref)
+    want = np.bincount(np.ceil((x + 10.0) / w_ref - 1).astype(np.int64), minlength=view.nb)
+    ctx.configure(N, L, 2, 0)
+    ctx.set_weights(wgt)
+    ctx.set_pair_exclusion(m2p, mind)
+    mm = ctx.null_hist(nulls, w_ref)
+    bins, n, imax = ctx.hist_read(view.nb)
+    assert n == R * int(keep.sum())
+    assert_bins_identical(bins, want, sc[:, keep].ravel(), -10.0, w_ref)
+    assert np.max(np.abs(mm - mm_ref)) <= 1e-9 * max(1.0, np.max(np.abs(mm_ref)))       # min/max over ALL pairs
+    # the input alignment's three histograms follow the same rule
+    res = ctx.scan(nulls[0], pkg.GT, pkg.C16, pkg.APC)
+    ha, _, _ = ctx.scan_hist(w_ref, -10.0, view.nb)
+    x0 = np.maximum(res["cov"][iu][keep], -10.0 + w_ref)
+    assert np.array_equal(ha, np.bincount(np.ceil((x0 + 10.0) / w_ref - 1).astype(np.int64), minlength=view.nb).astype(np.uint64))
+    ctx.set_pair_exclusion(None)
+    ha2, _, _ = ctx.scan_hist(w_ref, -10.0, view.nb)
+    assert int(ha2.sum()) == L * (L - 1) // 2
