@@ -11,9 +11,12 @@ reported with the metric's own definition of a pair-cell count per scan, L^2*N/2
   e2e     the same job through the C-ABI with HOST buffers: the input alignment (pinned), tree and weights in, null
           alignments generated on the device (Fitch + shuffle), cumulative histogram and the input alignment's score
           matrix out, all copies inside the timed region
-  N > 1   the 100 nulls are split into one contiguous block per rank (one process per GPU, torchrun), every rank
-          repeats the width pass on replicate 0 (no communication needed to agree on w), rank 0 also scans the input
-          alignment; the per-rank histograms are summed with one NCCL all-reduce.  Total work is fixed: "scaling": "strong".
+  N > 1   the 100 nulls are split into one contiguous block per rank (one process per GPU, torchrun); the width pass is fused
+          with the scan of replicate 0 (every rank histograms with the default w = 0.05, the owner of replicate 0 checks it:
+          32 bytes over NCCL), the last rank also scans the input alignment; the per-rank histograms are summed with one
+          all-reduce of the bins the scores reach, on the library's own NCCL communicator.  --grid-shard: the L x L pair grid
+          of EVERY scan is dealt to the ranks instead (BASELINE config 4) and the per-scan vectors (marginal sums, APC row
+          sums, score range) are all-reduced on the device inside the pipeline.  Total work is fixed: "scaling": "strong".
 
 --impl reference times the reference's own CPU implementation of the path (oracle/_ref: src/correlators.c compiled
 unchanged; the oracle port if that build is absent) on the host cores, on a bounded sample of the same workload.
@@ -216,6 +219,8 @@ def main():
 
     pkg = ge.load_package()
     synth = pkg.synth
+    if world == 1:
+        args.grid_shard = False                                       # one GPU owns the whole pair grid
 
     wl = WORKLOADS[args.workload]
     L, N, R = wl["L"], wl["N"], wl["nulls"]
@@ -229,17 +234,22 @@ def main():
     ctx.configure(N, L, slots, args.slices)
     ctx.set_weights(wgt)
     q_abs, q_bits = ctx.quantisation_error()
+    if world > 1:
+        # the library's own NCCL communicator (histogram sum; with --grid-shard also the per-scan vectors, inside the pipeline):
+        # rank 0 makes the id, torch.distributed only carries its 128 bytes
+        box = [pkg.comm_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        ctx.comm_init(box[0], world, rank)
     if args.grid_shard:
         ctx.set_shard(rank, world)                                    # row blocks of the pair grid of EVERY scan dealt to the ranks
         ctx.set_weights(wgt)
     my_ids = list(range(R)) if args.grid_shard else pkg.parallel.null_shard(R, world, rank)   # replicate ids held by this rank
     n_mine = len(my_ids)
-    own0 = (n_mine > 0 and my_ids[0] == 0)
+    own0 = (n_mine > 0 and my_ids[0] == 0)                            # replicate 0 defines the histogram width (R-scape.c:1681-1684)
     real_rank = world - 1                                             # the input alignment is scanned by the rank with the fewest nulls
-    ctx.pool_reserve(n_mine + (0 if own0 else 1))
-    w0_entry = 0                                                      # pool entry holding replicate 0 (width pass)
-    blk0 = 0 if own0 else 1                                           # first pool entry of this rank's block of nulls
+    ctx.pool_reserve(max(n_mine, 1))
     SEED = 20261017
+    W0, BMIN, HPTS, TOL = 0.05, -10.0, 400, 1e-6                      # cfg->w, BMIN, HPTS, tol (src/R-scape.c:426, covariation.h:22)
     host_msa = torch.from_numpy(msa).pin_memory()
     dev_msa = torch.from_numpy(msa).cuda()
     cov_out = torch.empty((L, L), dtype=torch.float64).pin_memory().numpy()          # pinned: the score matrix of the input alignment lands here
@@ -247,67 +257,61 @@ def main():
 
     def generate():
         """R-scape's default null model on the device: Fitch + tree-substitution shuffle (null_rscape, R-scape.c:1653-1661).
-        Replicates are keyed by their global id, so every rank that needs replicate 0 generates the same alignment."""
+        Replicates are keyed by their global id: a rank generates exactly its own block (every rank all of them with --grid-shard)."""
         ctx.set_tree(tree.left, tree.right, tree.parent, tree.ld, tree.rd)
-        if own0:
+        if n_mine:
             ctx.null_fitch_shuffle(host_msa.numpy(), SEED, n_mine, first_rep=0, first_id=my_ids[0])
-        else:                                                           # replicate 0 (width pass) and this rank's block in one call
-            ctx.null_fitch_shuffle(host_msa.numpy(), SEED, n_mine + 1, first_rep=0, ids=[0] + list(my_ids))
 
     STAT, ACT = getattr(pkg, args.stat), getattr(pkg, args.actype)
     PHASES = bool(os.environ.get("BENCH_PHASES"))                    # host-side phase times of every job on stderr
-    if args.grid_shard and (args.stat != "GT" or args.actype != "APC"):
-        raise SystemExit("--grid-shard runs the headline statistic (GT, APC) only")
+    if args.grid_shard and args.stat in ("RAFS",):
+        raise SystemExit("--grid-shard does not offer RAFS")
 
-    def sharded_scan(src, hist_w=None, want_cov=False):
-        """One scan with the pair grid sharded over the ranks: three phases, one small all-reduce between them."""
-        ms = ctx.sharded_counts_pool(src) if isinstance(src, int) else ctx.sharded_counts(src)
-        ms = pkg.parallel.reduce_sum(ms, device="cuda")
-        cs = pkg.parallel.reduce_cov_sums(ctx.sharded_statistic(ms, pkg.GT, pkg.C16), L, device="cuda")
-        cov, lo, hi = ctx.sharded_correct(cs, pkg.APC, want_cov=want_cov, hist_w=hist_w)
-        lo, hi = pkg.parallel.reduce_range(lo, hi, device="cuda")
-        return cov, lo, hi
-
-    def job_grid(real):
-        """the same job with every scan sharded over all ranks (config 4: L x L tile grid over the GPUs)"""
-        ctx.hist_reset()
-        _, lo, hi = sharded_scan(w0_entry)                                            # calculate_width_histo
-        w = min(0.05, (hi - max(-10.0, lo)) / 400.0)
-        for k in range(n_mine):
-            sharded_scan(k, hist_w=w)
-        cov, _, _ = sharded_scan(real, want_cov=isinstance(real, np.ndarray))
-        nb = 1 << 14
-        while nb < (1 << 22) and w > 0 and nb < 2.0 * (hi + 10.0) / w:
-            nb <<= 1
-        pkg.parallel.reduce_histogram_on_device(ctx, nb)
-        bins, n, imax = ctx.hist_read(nb, out=bins_pinned)
-        return w, bins, dict(cov=cov)
+    def width_of(lo, hi):
+        """calculate_width_histo, src/R-scape.c:1355-1360, from the score range of replicate 0"""
+        w = min(W0, (hi - max(BMIN, lo)) / HPTS)
+        return 0.0 if w < TOL else w
 
     def job(real):
-        """null_rscape + run_rscape for this rank's share of the work, nulls already in the device pool."""
-        if args.grid_shard:
-            return job_grid(real)
+        """null_rscape + run_rscape for this rank's share of the work, nulls already in the device pool.
+
+        The width pass is FUSED with the scan of replicate 0 (quirk Q2: the reference scans the first null twice, the scan consumes
+        no randomness): every rank histograms its nulls at once with the default width w = 0.05, the owner of replicate 0 derives
+        the width calculate_width_histo would return from that replicate's score range, and only if it differs from 0.05 (score
+        range of the first null below 20) is the loop repeated with it -- the histogram is then exactly the reference's."""
         tp = [time.perf_counter()] if PHASES else None
         ctx.hist_reset()
-        w, _, mx0 = ctx.null_width_pool(w0_entry, STAT, pkg.C16, ACT)                 # calculate_width_histo
-        if PHASES: tp.append(time.perf_counter())
-        if n_mine:
-            ctx.null_hist_pool(blk0, n_mine, w, STAT, pkg.C16, ACT, want_minmax=False)      # run_rscape(RANSS) + null_add2cumranklist
+        w = W0
+        for attempt in range(2):
+            lo, hi, w_true = np.inf, -np.inf, np.inf
+            if n_mine:
+                mm = ctx.null_hist_pool(0, n_mine, w, STAT, pkg.C16, ACT)                # run_rscape(RANSS) + null_add2cumranklist
+                lo, hi = float(mm[:, 0].min()), float(mm[:, 1].max())
+                if own0:
+                    if not mm[0, 1] > BMIN:
+                        raise SystemExit("bmin should be larger than maxCOV (R-scape.c:1355)")
+                    w_true = width_of(mm[0, 0], mm[0, 1])
+            if world > 1 and not args.grid_shard:
+                lo, hi, w_true = ctx.comm_range(lo, hi, w_true)                          # 32 bytes over NCCL
+            if w_true == w or attempt == 1:
+                break
+            w = w_true                                                                   # rare: redo with the width of replicate 0
+            ctx.hist_reset()
         if PHASES: tp.append(time.perf_counter())
         out = None
-        if rank == real_rank:
+        if args.grid_shard:
+            out = ctx.sharded_scan(real, STAT, pkg.C16, ACT, want_cov=isinstance(real, np.ndarray), cov_out=cov_out)
+        elif rank == real_rank:
             out = ctx.scan(real, STAT, pkg.C16, ACT, want_cov=isinstance(real, np.ndarray), cov_out=cov_out)   # run_rscape(GIVSS)
         if PHASES: tp.append(time.perf_counter())
-        # read (and sum over ranks) only the bins the scores can reach: 2 x the first null's range (cov_GrowRankList grows
-        # the reference's rank list the same way); the mass check after the timed region catches a window that was too small
-        nb = 1 << 14
-        while nb < (1 << 22) and w > 0 and nb < 2.0 * (mx0 + 10.0) / w:
-            nb <<= 1
-        pkg.parallel.reduce_histogram_on_device(ctx, nb)                              # null_add2cumranklist across ranks, in place over NCCL
+        # sum over ranks and read only the bins the null scores reach: bin of the largest score + cov_GrowRankList's 5 w margin
+        nb = int(min(1 << 22, max(64, np.ceil((hi - BMIN) / w) + 8))) if (w > 0 and np.isfinite(hi)) else 64
+        if world > 1:
+            ctx.hist_allreduce(nb)                                                       # null_add2cumranklist across ranks, on the device
         bins, n, imax = ctx.hist_read(nb, out=bins_pinned)
         if PHASES:
             tp.append(time.perf_counter())
-            print("[bench] rank %d phases ms: width %.2f nulls %.2f input %.2f read %.2f" % ((rank,) + tuple((b - a) * 1e3 for a, b in zip(tp, tp[1:]))),
+            print("[bench] rank %d phases ms: nulls %.2f input %.2f hist %.2f" % ((rank,) + tuple((b - a) * 1e3 for a, b in zip(tp, tp[1:]))),
                   file=sys.stderr, flush=True)
         return w, bins, out
 
@@ -355,12 +359,6 @@ def main():
     _, bins_chk, _ = job(dev_msa)
     expected = R * (L * (L - 1) // 2)
     mass = int(bins_chk.sum())
-    if mass != expected:
-        full, _, _ = ctx.hist_read(1 << 22)
-        tail = torch.tensor([int(full[len(bins_chk):].sum())], dtype=torch.int64, device="cuda")
-        if world > 1:
-            dist.all_reduce(tail)
-        mass += int(tail.item())
     hist_ok = (mass == expected)
     if not hist_ok:
         print(f"[bench] rank {rank}: cumulative null histogram holds {mass} scores, expected {expected}", file=sys.stderr, flush=True)
@@ -384,7 +382,7 @@ def main():
     # launches during the value run: per step, gram launches = width(1) + ceil(nulls/slots) + real(1 on rank 0)
     pairs = L * (L - 1) / 2.0
     gram_ms_avg = cnt["gram_ms"] / max(1, cnt["gram_launches"])
-    scans_this_rank = (n_mine + 1 + (1 if (rank == real_rank or args.grid_shard) else 0)) * (args.steps + args.warmup)
+    scans_this_rank = (n_mine + (1 if (rank == real_rank or args.grid_shard) else 0)) * (args.steps + args.warmup)
     if args.grid_shard:
         scans_this_rank /= world                                     # every rank contracts 1/world of each scan's tiles
     ops_alg_per_launch = 32.0 * pairs * N * scans_this_rank / max(1, cnt["gram_launches"])
@@ -408,7 +406,8 @@ def main():
                     ms_per_step=ms_dev / args.steps, higher_is_better=True, scaling="strong", vs_baseline=None,
                     dtype="u8 x u8 -> s32 tensor-core counts (fixed-point weights), f64 statistics", data="synthetic",
                     config=dict(workload=f"{args.workload}: L={L} N={N} nulls={R} {args.stat}+{args.actype}, scans per step = {scans_total} "
-                                         f"(width pass + {R} nulls + input alignment)",
+                                         f"(width pass + {R} nulls + input alignment, the reference's count; the width pass is fused with the "
+                                         f"scan of replicate 0, so {R + 1} contractions are executed)",
                                 weight_slices=args.slices,
                                 weights=f"fixed point wq = u V, u < 256, V < 256^{args.slices}: largest |wq 2^-q - w| = {q_abs:.3g} "
                                         f"({q_bits:.1f} bits below the largest weight); counts are exact integer arithmetic on wq",

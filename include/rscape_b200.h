@@ -142,6 +142,26 @@ int rsb_sharded_counts_pool(rsb_ctx *ctx, int rep, double tol, double *marg_sums
 int rsb_sharded_statistic(rsb_ctx *ctx, const double *marg_sums, double tol, int stat, int covclass, const double *allowpair, double *cov_sums);
 int rsb_sharded_correct(rsb_ctx *ctx, const double *cov_sums, int actype, int mode, double w, double bmin, double *cov, double *minmax);
 
+/* ---- communicator over the GPUs of the job (NCCL, bound at run time) --------------------------------------
+ * One process per GPU: rank 0 calls rsb_comm_id, ships the 128 bytes to the other ranks by any means (the bench uses
+ * torch.distributed's store), every rank calls rsb_comm_init.  One process driving several GPUs: rsb_comm_init_all over its
+ * contexts (one per device).  With a communicator
+ *   - rsb_hist_allreduce sums the cumulative null histograms of all ranks on the device (null_add2cumranklist across ranks,
+ *     src/R-scape.c:1565-1612): the only exchange when the NULL REPLICATES are dealt to the ranks;
+ *   - when the PAIR GRID is sharded as well (rsb_set_shard with world = the communicator's size), the null loop
+ *     (rsb_null_hist / _pool, rsb_null_width / _pool) and rsb_sharded_scan all-reduce the marginal sums [L][4], the APC row
+ *     sums [L+1] and the score range on the device, inside the pipeline: no host round trip per scan. */
+int rsb_comm_id(uint8_t *id128);
+int rsb_comm_init(rsb_ctx *ctx, const uint8_t *id128, int nranks, int rank);
+int rsb_comm_init_all(rsb_ctx **ctxs, int n);
+int rsb_comm_destroy(rsb_ctx *ctx);
+int rsb_hist_allreduce(rsb_ctx *ctx, int nb);
+/* in place: lo = min over ranks, hi = max over ranks, aux_min (may be NULL) = min over ranks */
+int rsb_comm_range(rsb_ctx *ctx, double *lo, double *hi, double *aux_min);
+/* rsb_scan on a pair grid sharded over the communicator's ranks; cov [L][L] (may be NULL) is assembled on every rank */
+int rsb_sharded_scan(rsb_ctx *ctx, const uint8_t *msa, int64_t row_stride, int on_device, int stat, int covclass, int actype,
+                     const double *allowpair, double tol, double *cov, double *mincov, double *maxcov);
+
 /* ---- null alignments: the loop body of null_rscape (src/R-scape.c:1650-1697) ------------------- */
 /* calculate_width_histo (src/R-scape.c:1281-1371): scan one null, w = min(w_old, (max - max(bmin,min))/hpts). */
 int rsb_null_width(rsb_ctx *ctx, const uint8_t *null0, int64_t row_stride, int on_device,

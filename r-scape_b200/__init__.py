@@ -101,6 +101,13 @@ def lib():
         L.rsb_null_fitch_shuffle.argtypes = [_vp, _u8p, C.c_int64, C.c_uint64, C.c_uint64, C.c_int, C.c_int]
         L.rsb_null_fitch_shuffle_ids.argtypes = [_vp, _u8p, C.c_int64, C.c_uint64, _u64p, C.c_int, C.c_int]
         L.rsb_counters.argtypes = [_vp, _i64p, _dp, _i64p, C.c_int]
+        L.rsb_comm_id.argtypes = [_u8p]
+        L.rsb_comm_init.argtypes = [_vp, _u8p, C.c_int, C.c_int]
+        L.rsb_comm_init_all.argtypes = [C.POINTER(_vp), C.c_int]
+        L.rsb_comm_destroy.argtypes = [_vp]
+        L.rsb_hist_allreduce.argtypes = [_vp, C.c_int]
+        L.rsb_comm_range.argtypes = [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.rsb_sharded_scan.argtypes = [_vp, _vp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.c_double, _dp, _dp, _dp]
         L.rsb_profile_gram.argtypes = [_vp, C.c_int]
         _lib = L
     return _lib
@@ -115,6 +122,21 @@ def _ptr(x):
     if isinstance(x, np.ndarray):
         return x.ctypes.data_as(_vp), 0
     return C.c_void_p(x.data_ptr()), (1 if x.is_cuda else 0)
+
+
+def comm_id():
+    """128-byte NCCL unique id (rank 0 creates it and ships it to the other ranks)."""
+    buf = (C.c_uint8 * 128)()
+    if lib().rsb_comm_id(buf) != 0:
+        raise RscapeB200Error(lib().rsb_create_error().decode())
+    return bytes(buf)
+
+
+def comm_init_all(contexts):
+    """One process driving several devices: a communicator over the contexts (rank k = contexts[k])."""
+    arr = (_vp * len(contexts))(*[c._h for c in contexts])
+    if lib().rsb_comm_init_all(arr, len(contexts)) != 0:
+        raise RscapeB200Error(lib().rsb_error(contexts[0]._h).decode())
 
 
 class Context:
@@ -257,6 +279,35 @@ class Context:
         self._ck(lib().rsb_tree_substitutions(self._h, ntaxa, ip(lf), ip(rt), leaves.ctypes.data_as(_u8p), L, internal.ctypes.data_as(_u8p), L,
                                               1 if includegaps else 0, ip(ns), ip(nd), ip(nj)))
         return ns, nd, nj
+
+    # ---- communicator ----------------------------------------------------------------------------
+    def comm_init(self, id128, nranks, rank):
+        buf = (C.c_uint8 * 128).from_buffer_copy(id128)
+        self._ck(lib().rsb_comm_init(self._h, buf, nranks, rank))
+
+    def comm_destroy(self):
+        self._ck(lib().rsb_comm_destroy(self._h))
+
+    def hist_allreduce(self, nb):
+        """Sum the first nb bins of the device histograms of all ranks, in place (null_add2cumranklist across ranks)."""
+        self._ck(lib().rsb_hist_allreduce(self._h, int(nb)))
+
+    def comm_range(self, lo, hi, aux_min=np.inf):
+        """(min over ranks of lo, max over ranks of hi, min over ranks of aux_min)."""
+        a, b, c = C.c_double(lo), C.c_double(hi), C.c_double(aux_min)
+        self._ck(lib().rsb_comm_range(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def sharded_scan(self, msa, stat=GT, covclass=C16, actype=APC, allowpair=None, tol=1e-6, want_cov=True, cov_out=None):
+        """rsb_scan on a pair grid sharded over the communicator's ranks; the corrected matrix is assembled on every rank."""
+        msa = self._msa(msa)
+        p, dev = _ptr(msa)
+        L = self.L
+        ap = None if allowpair is None else np.ascontiguousarray(allowpair, dtype=np.float64)
+        cov = (cov_out if cov_out is not None else np.empty((L, L))) if want_cov else None
+        mn, mx = C.c_double(), C.c_double()
+        self._ck(lib().rsb_sharded_scan(self._h, p, L, dev, stat, covclass, actype, _d(ap), tol, _d(cov), C.byref(mn), C.byref(mx)))
+        return dict(cov=cov, mincov=mn.value, maxcov=mx.value)
 
     # ---- one scan with the pair grid sharded over ranks ------------------------------------------
     def set_shard(self, rank, world):

@@ -5,6 +5,7 @@
 // rsb_create fails unless a compute-capability-10.x device is present.
 #include "rsb_common.cuh"
 #include "rsb_evalue.cuh"
+#include "nccl_dyn.h"
 #include "../../include/rscape_b200.h"
 #include <cstdarg>
 #include <cstring>
@@ -54,6 +55,8 @@ cudaError_t rsb_launch_correct_hist(double *cov, const double *covx, const doubl
                                     int *flags, int sr, int sw, const int *m2p, int mind, cudaStream_t st);
 cudaError_t rsb_launch_width(const double *minmax, double w_old, double bmin, int hpts, double tol, double *wout, cudaStream_t st);
 cudaError_t rsb_launch_symmetrize(double *cov, int L, int Lp, cudaStream_t st);
+cudaError_t rsb_launch_negate_min(double *minmax, int n, cudaStream_t st);
+cudaError_t rsb_launch_zero_unowned_rows(double *cov, int L, int Lp, int sr, int sw, cudaStream_t st);
 cudaError_t rsb_launch_hist3(const double *cov, int L, int Lp, const uint8_t *pairmask, double bmin, double w, int nb,
                              unsigned long long *ha, unsigned long long *hb, unsigned long long *ht, int *flags, const int *m2p, int mind, cudaStream_t st);
 cudaError_t rsb_launch_evalue_hits(const double *cov, int L, int Lp, const rsb_nullview &nv, const uint8_t *pairmask, double Nb, double Nt,
@@ -126,6 +129,7 @@ struct rsb_ctx {
   double *h_mm = nullptr; size_t h_mm_cap = 0;      // pinned staging of the per-replicate min/max: a pageable target would block the enqueuing thread
   double *d_meanp = nullptr, *d_w = nullptr, *d_blocksum = nullptr, *d_msum = nullptr, *d_covsum = nullptr;
   int shard_rank = 0, shard_world = 1;  // row-block sharding of the pair grid across ranks
+  rsb_nccl::ncclComm_t comm = nullptr; int comm_rank = 0, comm_size = 1;   // NCCL communicator over the ranks / devices of the job (rsb_comm_*)
   cudaStream_t stream_aux = nullptr, stream_aux2 = nullptr, stream_copy = nullptr;     // statistics (one per slot group) / uploads of the pipelined null loop
   cudaEvent_t ev_entry = nullptr, ev_up[2] = { nullptr, nullptr }, ev_counts[2] = { nullptr, nullptr }, ev_stats[2] = { nullptr, nullptr },
               ev_marg[2] = { nullptr, nullptr }, ev_statk[2] = { nullptr, nullptr };
@@ -426,7 +430,10 @@ int enqueue_gram(rsb_ctx *ctx, int which, int s0, int nrep, cudaStream_t st, boo
   if (rec && (which != 0 || g.pair_clusters > 0)) { rsb_set_error(ctx, "internal: record epilogue not available here"); return 1; }
   if (g.ntiles > 0) {
     const long long work = (long long) g.ntiles * nrep;
-    const int grid = (int) std::min<long long>(work, ctx->sm_count);
+    // with in-library collectives a few SMs stay free: the NCCL kernels cannot share an SM with the persistent contraction
+    // (its ring fills the shared memory) and would otherwise wait for the end of every launch
+    const int sms = (ctx->shard_world > 1 && ctx->comm && ctx->comm_size == ctx->shard_world) ? std::max(1, ctx->sm_count - 4) : ctx->sm_count;
+    const int grid = (int) std::min<long long>(work, sms);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (ctx->profile) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
     // the weighted geometry also emits the marginal partial sums of every tile (slot-indexed like the counts)
@@ -515,6 +522,29 @@ SlotPtrs slot_ptrs(rsb_ctx *c, int s0)
   return p;
 }
 
+// in-place all-reduce over the job's ranks on stream st (no-op without a communicator of more than one rank)
+int comm_allreduce(rsb_ctx *ctx, void *buf, size_t count, int dtype, int op, cudaStream_t st)
+{
+  if (!ctx->comm || ctx->comm_size <= 1) return 0;
+  const int rc = rsb_nccl::api().AllReduce(buf, buf, count, dtype, op, ctx->comm, st);
+  if (rc != rsb_nccl::ncclSuccess) { rsb_set_error(ctx, "ncclAllReduce: %s", rsb_nccl::api().GetErrorString(rc)); return 1; }
+  ctx->launches++;
+  return 0;
+}
+// is the pair grid sharded over the communicator's ranks (the data-path all-reduces are then done inside the library)?
+bool grid_comm(rsb_ctx *ctx) { return ctx->shard_world > 1 && ctx->comm && ctx->comm_size == ctx->shard_world; }
+
+// per-replicate (min, max) pairs -> global: MIN on [0], MAX on [1] as one MAX all-reduce of (-min, max)
+int comm_reduce_minmax(rsb_ctx *ctx, double *minmax, int n, cudaStream_t st)
+{
+  if (!ctx->comm || ctx->comm_size <= 1) return 0;
+  RSB_CUDA_OK(rsb_launch_negate_min(minmax, n, st));
+  if (comm_allreduce(ctx, minmax, (size_t) 2 * n, rsb_nccl::ncclFloat64, rsb_nccl::ncclMax, st)) return 1;
+  RSB_CUDA_OK(rsb_launch_negate_min(minmax, n, st));
+  ctx->launches += 2;
+  return 0;
+}
+
 // marginals (corr_Marginals) for slots [s0, s0+nrep) on stream st.  phase 1 = partial sums -> msum, 2 = normalise, 3 = both
 int enqueue_marginals(rsb_ctx *ctx, int s0, int nrep, double tol, cudaStream_t st, int phase = 3)
 {
@@ -522,6 +552,11 @@ int enqueue_marginals(rsb_ctx *ctx, int s0, int nrep, double tol, cudaStream_t s
   SlotPtrs p = slot_ptrs(ctx, s0);
   // partials are addressed [r][block][L][4] with r the absolute slot, as the gram kernel wrote them
   const int E = rsb_gram_mrow_blocks(g.pair_clusters > 0);
+  if (phase == 3 && grid_comm(ctx)) {                               // partial sums of the owned tiles, summed over the ranks, then normalised
+    if (enqueue_marginals(ctx, s0, nrep, tol, st, 1)) return 1;
+    if (comm_allreduce(ctx, p.msum, (size_t) nrep * ctx->L * 4, rsb_nccl::ncclFloat64, rsb_nccl::ncclSum, st)) return 1;
+    return enqueue_marginals(ctx, s0, nrep, tol, st, 2);
+  }
   RSB_CUDA_OK(rsb_launch_marginals(ctx->d_mrow + (size_t) s0 * g.nJB * E * ctx->L * 4, ctx->d_mcol + (size_t) s0 * 4 * ctx->nIB * ctx->L * 4,
                                    nrep, ctx->L, g.CJ, g.nJB, ctx->nIB, tol, p.msum, p.pm, ctx->d_flags,
                                    ctx->shard_rank, ctx->shard_world, phase, E, st));
@@ -561,8 +596,17 @@ int enqueue_statistic(rsb_ctx *ctx, int s0, int nrep, int stat, int covclass, un
     }
   }
   if (part & 2) {
+    if (phase == 3 && grid_comm(ctx)) {                             // row sums + total of the owned rows, summed over the ranks
+      RSB_CUDA_OK(rsb_launch_correct_final(rowpart, colpart, p.mm, nrep, ctx->L, p.covx, p.scal, p.blocksum, p.covsum, 1, st));
+      // (entries L+1, L+2 -- the raw min / max of the owned rows -- are summed too and mean nothing afterwards; nobody reads
+      // them on this path: the corrected range is reduced separately)
+      if (comm_allreduce(ctx, p.covsum, (size_t) nrep * (ctx->L + 4), rsb_nccl::ncclFloat64, rsb_nccl::ncclSum, st)) return 1;
+      RSB_CUDA_OK(rsb_launch_correct_final(rowpart, colpart, p.mm, nrep, ctx->L, p.covx, p.scal, p.blocksum, p.covsum, 2, st));
+      ctx->launches += 3;
+    } else {
     RSB_CUDA_OK(rsb_launch_correct_final(rowpart, colpart, p.mm, nrep, ctx->L, p.covx, p.scal, p.blocksum, p.covsum, phase, st));
     ctx->launches += (phase == 3) ? 3 : (phase == 1 ? 2 : 1);
+    }
   }
   return 0;
 }
@@ -574,7 +618,17 @@ int enqueue_correct(rsb_ctx *ctx, int s0, int nrep, int actype, int mode, double
   RSB_CUDA_OK(rsb_launch_correct_hist(p.cov, p.covx, p.scal, nrep, ctx->L, ctx->Lp, actype, mode, bmin, ctx->d_w, ctx->d_hist, HIST_BINS,
                                       p.mm, p.minmax, ctx->d_flags, ctx->shard_rank, ctx->shard_world, ctx->d_m2p, ctx->mind, st));
   ctx->launches += 2;
+  if (grid_comm(ctx) && comm_reduce_minmax(ctx, p.minmax, nrep, st)) return 1;
   return 0;
+}
+
+// pairs i<j whose row this rank owns (all of them without a sharded pair grid), minus those kept out of the histograms
+unsigned long long owned_pairs_in_hist(rsb_ctx *ctx)
+{
+  if (ctx->shard_world <= 1) return ctx->pairs_in_hist;
+  unsigned long long mine = 0;
+  for (int i = 0; i < ctx->L; i++) if ((i / RSB_ICOLS) % ctx->shard_world == ctx->shard_rank) mine += (unsigned long long) (ctx->L - 1 - i);
+  return mine;
 }
 
 // serial pipeline on the main stream, slots [0,nrep): counts -> (marginals) -> statistic
@@ -681,6 +735,7 @@ void rsb_destroy(rsb_ctx *ctx)
   for (auto &p : ctx->pending) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   for (auto &p : ctx->pending_aux) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   for (auto &p : ctx->pending_stage) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+  if (ctx->comm) { rsb_nccl::api().CommDestroy(ctx->comm); ctx->comm = nullptr; }
   free_plan(ctx);
   if (ctx->d_logtab) cudaFree(ctx->d_logtab);
   cudaStreamSynchronize(ctx->stream_aux); cudaStreamSynchronize(ctx->stream_aux2); cudaStreamSynchronize(ctx->stream_copy); cudaStreamSynchronize(ctx->stream_gen);
@@ -942,6 +997,7 @@ int rsb_null_width(rsb_ctx *ctx, const uint8_t *null0, int64_t row_stride, int o
 {
   RSB_CUDA_OK(cudaSetDevice(ctx->device));
   if (resolve_stat(ctx, stat, covclass)) return 1;
+  if (ctx->shard_world > 1 && !grid_comm(ctx)) { rsb_set_error(ctx, "calculate_width_histo on a sharded pair grid needs a communicator (rsb_comm_init)"); return 1; }
   if (null0 && upload_msa(ctx, null0, row_stride, 0, 1, 0, on_device, ctx->stream)) return 1;
   if (run_pipeline(ctx, 1, stat, covclass, allow_mask(allowpair), tol)) return 1;
   if (enqueue_correct(ctx, 0, 1, actype, 0, bmin, ctx->stream)) return 1;
@@ -973,6 +1029,12 @@ static int null_hist_pipelined(rsb_ctx *ctx, const uint8_t *nulls, int nrep, int
   // GT x C16: the contraction's epilogue leaves per-pair records and the statistic finishes with an HBM-bound kernel on the
   // aux stream -- nothing but contractions on the main stream
   const bool rec = !raf && use_record(ctx, stat, covclass);
+  if (ctx->shard_world > 1 && !grid_comm(ctx)) {
+    rsb_set_error(ctx, "the null loop on a sharded pair grid needs a communicator over the %d shards (rsb_comm_init); "
+                       "without one use rsb_sharded_counts / _statistic / _correct and reduce on the host", ctx->shard_world);
+    return 1;
+  }
+  if (ctx->shard_world > 1 && ctx->d_m2p) { rsb_set_error(ctx, "a pair exclusion (rsb_set_pair_exclusion) is not offered on a sharded pair grid"); return 1; }
   const bool in_place = (on_device && row_stride == ctx->L && rep_stride == (int64_t) ctx->N * ctx->L);
   const int  G = (ctx->Rcap >= 2) ? 2 : 1;
   const int  chunk = std::max(1, ctx->Rcap / G);
@@ -984,7 +1046,9 @@ static int null_hist_pipelined(rsb_ctx *ctx, const uint8_t *nulls, int nrep, int
   cudaStream_t st_copy = (serial & 2) ? sm : ctx->stream_copy;
   // one statistics stream per slot group: the chains of consecutive chunks overlap each other (they run beside the
   // contraction at low occupancy, bound by latency rather than by a pipe)
-  auto aux_of = [&](int g) -> cudaStream_t { return (serial & 1) ? sm : (g & 1) ? ctx->stream_aux2 : ctx->stream_aux; };
+  // (with in-library collectives everything that talks to NCCL stays on ONE stream: same order of collectives on every rank)
+  const bool one_aux = grid_comm(ctx);
+  auto aux_of = [&](int g) -> cudaStream_t { return (serial & 1) ? sm : ((g & 1) && !one_aux) ? ctx->stream_aux2 : ctx->stream_aux; };
 
   if (minmax && ctx->h_mm_cap < (size_t) nrep) {
     if (ctx->h_mm) cudaFreeHost(ctx->h_mm);
@@ -1030,7 +1094,7 @@ static int null_hist_pipelined(rsb_ctx *ctx, const uint8_t *nulls, int nrep, int
                                             cudaMemcpyDeviceToHost, st_aux));
     if (ctx->profile) { cudaEventRecord(a1, st_aux); ctx->pending_aux.push_back({ a0, a1 }); ctx->pending_stage.push_back({ am, as }); ctx->aux_chains++; }
     RSB_CUDA_OK(cudaEventRecord(ctx->ev_stats[pg], st_aux));
-    if (w > 0.0) ctx->hist_n += (unsigned long long) pn * ctx->pairs_in_hist;
+    if (w > 0.0) ctx->hist_n += (unsigned long long) pn * owned_pairs_in_hist(ctx);
     return 0;
   };
 
@@ -1684,6 +1748,135 @@ int rsb_pool_put(rsb_ctx *ctx, int first_rep, int nrep, const uint8_t *in)
   for (int r = first_rep; r < first_rep + nrep; r++) ctx->pool_ready[r] = nullptr;
   RSB_CUDA_OK(cudaMemcpyAsync(ctx->d_pool + first_rep * rb, in, rb * nrep, cudaMemcpyHostToDevice, ctx->stream));
   RSB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- communicator (multi-GPU)
+int rsb_comm_id(uint8_t *id128)
+{
+  rsb_nccl::Api &a = rsb_nccl::api();
+  if (!a.ok) { snprintf(g_create_err, sizeof(g_create_err), "NCCL is not available: %s", a.why); return 1; }
+  rsb_nccl::ncclUniqueId id;
+  const int rc = a.GetUniqueId(&id);
+  if (rc != rsb_nccl::ncclSuccess) { snprintf(g_create_err, sizeof(g_create_err), "ncclGetUniqueId: %s", a.GetErrorString(rc)); return 1; }
+  memcpy(id128, id.internal, 128);
+  return 0;
+}
+
+int rsb_comm_init(rsb_ctx *ctx, const uint8_t *id128, int nranks, int rank)
+{
+  RSB_CUDA_OK(cudaSetDevice(ctx->device));
+  rsb_nccl::Api &a = rsb_nccl::api();
+  if (!a.ok) { rsb_set_error(ctx, "NCCL is not available: %s", a.why); return 1; }
+  if (nranks < 1 || rank < 0 || rank >= nranks) { rsb_set_error(ctx, "bad rank %d of %d", rank, nranks); return 1; }
+  if (ctx->comm) { a.CommDestroy(ctx->comm); ctx->comm = nullptr; }
+  rsb_nccl::ncclUniqueId id;
+  memcpy(id.internal, id128, 128);
+  const int rc = a.CommInitRank(&ctx->comm, nranks, id, rank);
+  if (rc != rsb_nccl::ncclSuccess) { ctx->comm = nullptr; rsb_set_error(ctx, "ncclCommInitRank: %s", a.GetErrorString(rc)); return 1; }
+  ctx->comm_rank = rank; ctx->comm_size = nranks;
+  return 0;
+}
+
+/* one process driving several devices: a communicator over the n contexts (one per device), rank k = ctxs[k] */
+int rsb_comm_init_all(rsb_ctx **ctxs, int n)
+{
+  if (n < 1 || !ctxs || !ctxs[0]) return 1;
+  rsb_nccl::Api &a = rsb_nccl::api();
+  if (!a.ok) { rsb_set_error(ctxs[0], "NCCL is not available: %s", a.why); return 1; }
+  std::vector<int> devs(n);
+  std::vector<rsb_nccl::ncclComm_t> comms(n, nullptr);
+  for (int k = 0; k < n; k++) {
+    devs[k] = ctxs[k]->device;
+    for (int q = 0; q < k; q++) if (devs[q] == devs[k]) { rsb_set_error(ctxs[0], "rsb_comm_init_all: device %d appears twice", devs[k]); return 1; }
+  }
+  const int rc = a.CommInitAll(comms.data(), n, devs.data());
+  if (rc != rsb_nccl::ncclSuccess) { rsb_set_error(ctxs[0], "ncclCommInitAll: %s", a.GetErrorString(rc)); return 1; }
+  for (int k = 0; k < n; k++) {
+    if (ctxs[k]->comm) a.CommDestroy(ctxs[k]->comm);
+    ctxs[k]->comm = comms[k]; ctxs[k]->comm_rank = k; ctxs[k]->comm_size = n;
+  }
+  return 0;
+}
+
+int rsb_comm_destroy(rsb_ctx *ctx)
+{
+  if (ctx->comm) {
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->stream_aux);
+    rsb_nccl::api().CommDestroy(ctx->comm);
+    ctx->comm = nullptr; ctx->comm_size = 1; ctx->comm_rank = 0;
+  }
+  return 0;
+}
+
+/* null_add2cumranklist across ranks (src/R-scape.c:1565-1612): sum the first nb bins of the device histograms of all ranks in place */
+int rsb_hist_allreduce(rsb_ctx *ctx, int nb)
+{
+  RSB_CUDA_OK(cudaSetDevice(ctx->device));
+  if (nb < 1 || nb > HIST_BINS) { rsb_set_error(ctx, "rsb_hist_allreduce: bad bin count"); return 1; }
+  if (!ctx->comm) { rsb_set_error(ctx, "rsb_hist_allreduce: no communicator (rsb_comm_init)"); return 1; }
+  if (comm_allreduce(ctx, ctx->d_hist, (size_t) nb, rsb_nccl::ncclUint64, rsb_nccl::ncclSum, ctx->stream)) return 1;
+  unsigned long long *d_n = nullptr;                                  // the number of scores travels the same way
+  RSB_CUDA_OK(cudaMalloc(&d_n, sizeof(unsigned long long)));
+  RSB_CUDA_OK(cudaMemcpyAsync(d_n, &ctx->hist_n, sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
+  int rc = comm_allreduce(ctx, d_n, 1, rsb_nccl::ncclUint64, rsb_nccl::ncclSum, ctx->stream);
+  if (!rc) {
+    cudaError_t e = cudaMemcpyAsync(&ctx->hist_n, d_n, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { rsb_set_error(ctx, "rsb_hist_allreduce: %s", cudaGetErrorString(e)); rc = 1; }
+  }
+  cudaFree(d_n);
+  return rc;
+}
+
+/* global (min over ranks of lo, max over ranks of hi, min over ranks of aux): the score range of a rank's nulls and e.g. the
+ * histogram width its replicate 0 asks for */
+int rsb_comm_range(rsb_ctx *ctx, double *lo, double *hi, double *aux_min)
+{
+  RSB_CUDA_OK(cudaSetDevice(ctx->device));
+  if (!ctx->comm || ctx->comm_size <= 1) return 0;
+  double h[4] = { -*lo, *hi, aux_min ? -*aux_min : 0.0, 0.0 }, *d = nullptr;
+  RSB_CUDA_OK(cudaMalloc(&d, sizeof(h)));
+  int rc = 1;
+  if (cudaMemcpyAsync(d, h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess &&
+      comm_allreduce(ctx, d, 4, rsb_nccl::ncclFloat64, rsb_nccl::ncclMax, ctx->stream) == 0 &&
+      cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream) == cudaSuccess &&
+      cudaStreamSynchronize(ctx->stream) == cudaSuccess) {
+    *lo = -h[0]; *hi = h[1]; if (aux_min) *aux_min = -h[2];
+    rc = 0;
+  } else if (!ctx->err[0]) rsb_set_error(ctx, "rsb_comm_range failed");
+  cudaFree(d);
+  return rc;
+}
+
+/* rsb_scan with the pair grid sharded over the communicator's ranks (BASELINE config 4): every rank contracts and scores the
+ * rows it owns, the marginal sums / APC row sums / score range are all-reduced on the device, and the corrected matrix is
+ * assembled on every rank by one SUM all-reduce (rows of other ranks are zero).  Probabilities are not exported here. */
+int rsb_sharded_scan(rsb_ctx *ctx, const uint8_t *msa, int64_t row_stride, int on_device, int stat, int covclass, int actype,
+                     const double *allowpair, double tol, double *cov, double *mincov, double *maxcov)
+{
+  RSB_CUDA_OK(cudaSetDevice(ctx->device));
+  if (resolve_stat(ctx, stat, covclass)) return 1;
+  if (!grid_comm(ctx)) { rsb_set_error(ctx, "rsb_sharded_scan needs rsb_set_shard and a communicator over the shards"); return 1; }
+  if (stat == RSB_RAF || stat == RSB_RAFS || stat == RSB_CCF) { rsb_set_error(ctx, "statistic not available with a sharded pair grid"); return 1; }
+  if (actype != RSB_APC && actype != RSB_ASC) { rsb_set_error(ctx, "rsb_sharded_scan: APC or ASC"); return 1; }
+  if (ensure_geo(ctx, 0)) return 1;
+  if (upload_msa(ctx, msa, row_stride, 0, 1, 0, on_device, ctx->stream)) return 1;
+  if (run_pipeline(ctx, 1, stat, covclass, allow_mask(allowpair), tol)) return 1;          // all-reduces inside (grid_comm)
+  if (enqueue_correct(ctx, 0, 1, actype, 1, 0.0, ctx->stream)) return 1;
+  if (cov) {
+    RSB_CUDA_OK(rsb_launch_zero_unowned_rows(ctx->d_cov, ctx->L, ctx->Lp, ctx->shard_rank, ctx->shard_world, ctx->stream));
+    if (comm_allreduce(ctx, ctx->d_cov, (size_t) ctx->L * ctx->Lp, rsb_nccl::ncclFloat64, rsb_nccl::ncclSum, ctx->stream)) return 1;
+    RSB_CUDA_OK(rsb_launch_symmetrize(ctx->d_cov, ctx->L, ctx->Lp, ctx->stream));
+    ctx->launches += 2;
+    if (copy_matrix_out(ctx, ctx->d_cov, cov)) return 1;
+  }
+  double mmx[2];
+  RSB_CUDA_OK(cudaMemcpyAsync(mmx, ctx->d_minmax, sizeof(mmx), cudaMemcpyDeviceToHost, ctx->stream));
+  if (check_flags(ctx, "corr_CalculateCOVCorrected")) return 1;
+  if (mincov) *mincov = mmx[0];
+  if (maxcov) *maxcov = mmx[1];
   return 0;
 }
 

@@ -196,6 +196,21 @@ minmax_final_kernel(const double *__restrict__ mm, int nblocks, double *__restri
   if (threadIdx.x == 0) { out[r * 2] = rmin[0]; out[r * 2 + 1] = rmax[0]; }
 }
 
+// (min, max) pairs <-> (-min, max): one MAX all-reduce then serves both ends of the range
+__global__ void negate_min_kernel(double *__restrict__ minmax, int n)
+{
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) minmax[2 * k] = -minmax[2 * k];
+}
+
+// scores of rows owned by other ranks -> 0, so that a SUM all-reduce assembles the whole upper triangle
+__global__ void zero_unowned_rows_kernel(double *__restrict__ cov, int L, int Lp, int sr, int sw)
+{
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+  if (j >= Lp) return;
+  if ((i / RSB_ICOLS) % sw != sr || j <= i) cov[(size_t) i * Lp + j] = 0.0;
+}
+
 // w = min(w_old, (maxCOV - max(bmin, minCOV)) / hpts), zeroed below tol: src/R-scape.c:1357-1360
 __global__ void width_kernel(const double *__restrict__ minmax, double w_old, double bmin, int hpts, double tol, double *__restrict__ wout)
 {
@@ -265,6 +280,18 @@ cudaError_t rsb_launch_correct_hist(double *cov, const double *covx, const doubl
 cudaError_t rsb_launch_width(const double *minmax, double w_old, double bmin, int hpts, double tol, double *wout, cudaStream_t st)
 {
   width_kernel<<<1, 32, 0, st>>>(minmax, w_old, bmin, hpts, tol, wout);
+  return cudaGetLastError();
+}
+
+cudaError_t rsb_launch_negate_min(double *minmax, int n, cudaStream_t st)
+{
+  negate_min_kernel<<<(n + 127) / 128, 128, 0, st>>>(minmax, n);
+  return cudaGetLastError();
+}
+
+cudaError_t rsb_launch_zero_unowned_rows(double *cov, int L, int Lp, int sr, int sw, cudaStream_t st)
+{
+  zero_unowned_rows_kernel<<<dim3((Lp + 127) / 128, L), 128, 0, st>>>(cov, L, Lp, sr, sw);
   return cudaGetLastError();
 }
 
