@@ -36,6 +36,8 @@ enum { RSB_CORR_APC = 0, RSB_CORR_ASC = 1, RSB_CORR_NONE = 2 };
 /* device: CUDA ordinal.  stream: a cudaStream_t to enqueue on (e.g. torch's current stream), or NULL
  * for a stream owned by the context. */
 int         rsb_create(int device, void *stream, rsb_ctx **out);
+/* number of CUDA devices visible to the process (0 if none) */
+int         rsb_device_count(void);
 void        rsb_destroy(rsb_ctx *ctx);
 const char *rsb_error(const rsb_ctx *ctx);
 /* last error of a failed rsb_create (no context exists yet) */
@@ -232,6 +234,24 @@ int rsb_pool_get_internal(rsb_ctx *ctx, int which, int first_rep, int nrep, uint
  * Any of the three may be NULL (the contraction is skipped when only nsubs is asked for). */
 int rsb_tree_substitutions(rsb_ctx *ctx, int ntaxa, const int *left, const int *right, const uint8_t *leaves, int64_t leaf_stride,
                            const uint8_t *internal, int64_t internal_stride, int includegaps, int *nsubs, int *ndouble, int *njoin);
+
+/* ---- alignment preprocessing: what defines the scanned matrix and its weights ----------------------------
+ * Independent of rsb_configure (any shape); msa: uint8 [nseq][row_stride], host or device.
+ * Easel is not vendored by the reference: these follow SURVEY 9.7's restatement of the Easel routines R-scape calls. */
+/* The column test of msamanip_RemoveGapColumns (src/msamanip.c:486-500): useme[c] = 1 iff r > 0 and r / (r + gap) >= 1 - gapthresh,
+ * r / gap = summed weights of the sequences holding a residue / a gap in column c (wgt NULL: all 1, counted as integers). */
+int rsb_msa_gap_columns(rsb_ctx *ctx, const uint8_t *msa, int nseq, int alen, int64_t row_stride, int on_device, const double *wgt,
+                        double gapthresh, uint8_t *useme);
+/* the residues of the kept columns (struct_ColumnSubset): out uint8 [nseq][nkeep], host or device */
+int rsb_msa_column_subset(rsb_ctx *ctx, const uint8_t *msa, int nseq, int alen, int64_t row_stride, int on_device, const uint8_t *useme,
+                          uint8_t *out, int out_on_device, int *nkeep);
+/* esl_msaweight_PB, Henikoff position-based weights normalised to sum nseq (R-scape's choice for nseq > 1000, src/R-scape.c:1555-1556) */
+int rsb_msa_pb_weights(rsb_ctx *ctx, const uint8_t *msa, int nseq, int alen, int64_t row_stride, int on_device, double *wgt);
+/* esl_dst_XPairId: pid = identical canonical positions / min(canonical lengths).  pairs int [npairs][2] -> out[npairs] (the sampled or
+ * exhaustive pair list of esl_dst_XAverageId, src/msamanip.c:1967); pairs NULL -> out double [nseq][nseq] = 1 - pid, the distance
+ * matrix esl_msaweight_GSC builds its UPGMA tree from (nseq <= 1000). */
+int rsb_msa_pair_identity(rsb_ctx *ctx, const uint8_t *msa, int nseq, int alen, int64_t row_stride, int on_device, const int *pairs, int64_t npairs,
+                          double *out);
 
 /* ---- instrumentation ------------------------------------------------------------------------------ */
 /* kernels launched by this context so far; device milliseconds spent in the gram kernel and number of

@@ -109,6 +109,19 @@ extern int        cov_PairMaskFromCT(const int *ct, int64_t alen, uint8_t *pairm
 extern int        Tree_Substitutions_b200(ESL_MSA *msa, ESL_MSA *allmsa, ESL_TREE *T, int **ret_nsubs, int **ret_ndouble, int **ret_njoin,
                                           int includegaps, char *errbuf, int verbose);
 
+/* ---- preprocessing that defines the scanned alignment and its weights (r-scape_b200/host/msaprep_b200.c) ---- */
+/* msaweight's default branch, src/R-scape.c:1545-1562: esl_msaweight_GSC for nseq <= maxsq_gsc, else esl_msaweight_PB; fills msa->wgt */
+extern int        msaweight_b200(ESL_MSA *msa, int maxsq_gsc);
+extern int        esl_msaweight_PB_b200(ESL_MSA *msa);
+extern int        esl_msaweight_GSC_b200(ESL_MSA *msa);
+/* the column test of msamanip_RemoveGapColumns, src/msamanip.c:486-500: useme int[alen] */
+extern int        msamanip_GapColumns_b200(double gapthresh, ESL_MSA *msa, int *useme, char *errbuf);
+/* esl_dst_XAverageId as msamanip_XStats calls it (max_comparisons = 10000), src/msamanip.c:1967: fraction, not percent */
+extern int        esl_dst_XAverageId_b200(ESL_MSA *msa, int max_comparisons, double *ret_id);
+/* the device context these calls share (created on first use, RSCAPE_B200_DEVICE), and its release */
+extern rsb_ctx   *rsb_host_prep_context(char *errbuf);
+extern void       rsb_host_prep_release(void);
+
 #ifdef __cplusplus
 }
 #endif

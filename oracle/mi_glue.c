@@ -179,3 +179,24 @@ glue_tree_substitutions(int N, const int *left, const int *right, int L, const u
 double glue_data_w(struct data_s *d) { return d->w; }
 int    glue_cov_calculate(struct data_s *d, ESL_MSA *msa) { return cov_CalculateCOV(d, msa); }
 #endif
+#ifndef GLUE_REFERENCE
+/* drive the preprocessing mirrors (host/msaprep_b200.c) from flat arrays: what = 0 msaweight_b200 (GSC | PB by maxsq_gsc),
+ * 1 esl_msaweight_PB_b200, 2 esl_msaweight_GSC_b200 -> wgt[nseq]; useme (int[L], may be NULL) <- msamanip_GapColumns_b200 with
+ * the INPUT weights; avgid (may be NULL) <- esl_dst_XAverageId_b200(max_comparisons) */
+int
+glue_msaprep(int nseq, int L, const uint8_t *res, const double *wgt_in, int what, int maxsq_gsc, double gapthresh, int max_comparisons,
+             double *wgt_out, int *useme, double *avgid)
+{
+  ESL_MSA *msa = glue_msa_create(nseq, L, res, wgt_in);
+  char     errbuf[eslERRBUFSIZE];
+  int      status = eslOK, s;
+  if (useme && status == eslOK) status = msamanip_GapColumns_b200(gapthresh, msa, useme, errbuf);
+  if (avgid && status == eslOK) status = esl_dst_XAverageId_b200(msa, max_comparisons, avgid);
+  if (wgt_out && status == eslOK) {
+    status = (what == 0) ? msaweight_b200(msa, maxsq_gsc) : (what == 1) ? esl_msaweight_PB_b200(msa) : esl_msaweight_GSC_b200(msa);
+    for (s = 0; s < nseq; s++) wgt_out[s] = msa->wgt[s];
+  }
+  esl_msa_Destroy(msa);
+  return status;
+}
+#endif

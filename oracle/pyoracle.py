@@ -266,6 +266,10 @@ class Oracle:
     def rng(self, seed):
         return self.lib.orc_rng_create(seed)
 
+    def random(self, r):
+        """next uniform deviate of the stream (esl_random)"""
+        return self.lib.orc_rng_uniform(r)
+
     def rng_free(self, r):
         self.lib.orc_rng_destroy(r)
 
@@ -541,7 +545,7 @@ def remove_gap_columns(ax, wgt=None, gapthresh=0.75):
     N, L = ax.shape
     w = np.ones(N) if wgt is None else wgt
     is_res = (ax < 4) | ((ax > 4) & (ax < 16))         # esl_abc_XIsResidue
-    is_gap = (ax == 4) | (ax == 17)                    # gap or missing
+    is_gap = (ax == 4)                                 # esl_abc_XIsGap; missing data (17) and '*' (16) count on neither side (:497)
     r = (w[:, None] * is_res).sum(0)
     tot = (w[:, None] * (is_res | is_gap)).sum(0)
     frac = np.where(tot > 0, r / np.maximum(tot, 1e-300), 0.0)
@@ -643,6 +647,28 @@ def weights_gsc(ax):
             wgt[-right[v]] = rx + rd[v]
     s = wgt.sum()
     return wgt * (N / s) if s > 0 else np.ones(N)
+
+
+def pair_identity(ax, a, b):
+    """esl_dst_XPairId: identical canonical positions / min(canonical lengths) (0 if that is 0)."""
+    ca, cb = ax[a] < 4, ax[b] < 4
+    same = int((ca & cb & (ax[a] == ax[b])).sum())
+    ln = min(int(ca.sum()), int(cb.sum()))
+    return same / ln if ln > 0 else 0.0
+
+
+def average_id(ax, max_comparisons=10000, pairs=None):
+    """esl_dst_XAverageId (src/msamanip.c:1967): exhaustive when N(N-1)/2 <= max_comparisons; else over `pairs` (the sampled list)."""
+    N = ax.shape[0]
+    if N <= 1:
+        return 1.0
+    if pairs is None:
+        assert N * (N - 1) // 2 <= max_comparisons
+        pairs = [(i, j) for i in range(N) for j in range(i + 1, N)]
+    s = 0.0
+    for i, j in pairs:
+        s += pair_identity(ax, i, j)
+    return s / len(pairs)
 
 
 def weights_pb(ax):

@@ -101,6 +101,10 @@ def lib():
         L.rsb_null_fitch_shuffle.argtypes = [_vp, _u8p, C.c_int64, C.c_uint64, C.c_uint64, C.c_int, C.c_int]
         L.rsb_null_fitch_shuffle_ids.argtypes = [_vp, _u8p, C.c_int64, C.c_uint64, _u64p, C.c_int, C.c_int]
         L.rsb_counters.argtypes = [_vp, _i64p, _dp, _i64p, C.c_int]
+        L.rsb_msa_gap_columns.argtypes = [_vp, _vp, C.c_int, C.c_int, C.c_int64, C.c_int, _dp, C.c_double, _u8p]
+        L.rsb_msa_column_subset.argtypes = [_vp, _vp, C.c_int, C.c_int, C.c_int64, C.c_int, _u8p, _vp, C.c_int, _ip]
+        L.rsb_msa_pb_weights.argtypes = [_vp, _vp, C.c_int, C.c_int, C.c_int64, C.c_int, _dp]
+        L.rsb_msa_pair_identity.argtypes = [_vp, _vp, C.c_int, C.c_int, C.c_int64, C.c_int, _ip, C.c_int64, _dp]
         L.rsb_comm_id.argtypes = [_u8p]
         L.rsb_comm_init.argtypes = [_vp, _u8p, C.c_int, C.c_int]
         L.rsb_comm_init_all.argtypes = [C.POINTER(_vp), C.c_int]
@@ -279,6 +283,52 @@ class Context:
         self._ck(lib().rsb_tree_substitutions(self._h, ntaxa, ip(lf), ip(rt), leaves.ctypes.data_as(_u8p), L, internal.ctypes.data_as(_u8p), L,
                                               1 if includegaps else 0, ip(ns), ip(nd), ip(nj)))
         return ns, nd, nj
+
+    # ---- alignment preprocessing (any shape, independent of configure) ----------------------------
+    @staticmethod
+    def _any_msa(msa):
+        if isinstance(msa, np.ndarray):
+            msa = np.ascontiguousarray(msa, dtype=np.uint8)
+        return msa, int(msa.shape[0]), int(msa.shape[1])
+
+    def msa_gap_columns(self, msa, wgt=None, gapthresh=0.75):
+        """useme uint8 [alen]: the column test of msamanip_RemoveGapColumns (src/msamanip.c:486-500)."""
+        msa, N, L = self._any_msa(msa)
+        p, dev = _ptr(msa)
+        w = None if wgt is None else np.ascontiguousarray(wgt, dtype=np.float64)
+        use = np.empty(L, np.uint8)
+        self._ck(lib().rsb_msa_gap_columns(self._h, p, N, L, L, dev, _d(w), gapthresh, use.ctypes.data_as(_u8p)))
+        return use
+
+    def msa_column_subset(self, msa, useme):
+        msa, N, L = self._any_msa(msa)
+        p, dev = _ptr(msa)
+        use = np.ascontiguousarray(useme, dtype=np.uint8)
+        out = np.empty((N, int(np.count_nonzero(use))), np.uint8)
+        n = C.c_int()
+        self._ck(lib().rsb_msa_column_subset(self._h, p, N, L, L, dev, use.ctypes.data_as(_u8p), out.ctypes.data_as(_vp), 0, C.byref(n)))
+        assert n.value == out.shape[1]
+        return out
+
+    def msa_pb_weights(self, msa):
+        msa, N, L = self._any_msa(msa)
+        p, dev = _ptr(msa)
+        w = np.empty(N)
+        self._ck(lib().rsb_msa_pb_weights(self._h, p, N, L, L, dev, _d(w)))
+        return w
+
+    def msa_pair_identity(self, msa, pairs=None):
+        """pairs int [npairs][2] -> pid [npairs]; None -> the distance matrix 1 - pid [N][N]."""
+        msa, N, L = self._any_msa(msa)
+        p, dev = _ptr(msa)
+        if pairs is None:
+            out = np.empty((N, N))
+            self._ck(lib().rsb_msa_pair_identity(self._h, p, N, L, L, dev, None, 0, _d(out)))
+            return out
+        pr = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+        out = np.empty(len(pr))
+        self._ck(lib().rsb_msa_pair_identity(self._h, p, N, L, L, dev, pr.ctypes.data_as(_ip), len(pr), _d(out)))
+        return out
 
     # ---- communicator ----------------------------------------------------------------------------
     def comm_init(self, id128, nranks, rank):

@@ -78,6 +78,11 @@ cudaError_t rsb_launch_unknown_check(const uint8_t *msa, size_t n, int *d_flag, 
 cudaError_t rsb_launch_permutations(int L, unsigned long long seed, unsigned long long id0, const unsigned long long *ids, int first_rep, int nrep,
                                     int *perm, cudaStream_t st);
 
+cudaError_t rsb_launch_gap_columns(const uint8_t *msa, int N, int L, long long row_stride, const double *wgt, double idthresh, uint8_t *useme, cudaStream_t st);
+cudaError_t rsb_launch_pb_weights(const uint8_t *msa, int N, int L, long long row_stride, double *coef, double *w, cudaStream_t st);
+cudaError_t rsb_launch_pair_identity(const uint8_t *msa, int N, int L, long long row_stride, const int *pairs, long long npairs, double *out, cudaStream_t st);
+cudaError_t rsb_launch_column_subset(const uint8_t *msa, int N, long long row_stride, const int *cols, int nkeep, uint8_t *out, cudaStream_t st);
+
 namespace {
 constexpr int HIST_BINS = 1 << 22;
 
@@ -671,6 +676,13 @@ extern "C" {
 
 const char *rsb_create_error(void) { return g_create_err; }
 const char *rsb_error(const rsb_ctx *ctx) { return ctx ? ctx->err : g_create_err; }
+
+int rsb_device_count(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
 
 int rsb_create(int device, void *stream, rsb_ctx **out)
 {
@@ -1750,6 +1762,116 @@ int rsb_pool_put(rsb_ctx *ctx, int first_rep, int nrep, const uint8_t *in)
   RSB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------- alignment preprocessing
+namespace {
+// the alignment on the device: the caller's buffer itself (on_device), else a temporary copy.  `owned` must be freed by the caller.
+int stage_msa(rsb_ctx *ctx, const uint8_t *msa, int nseq, int alen, int64_t row_stride, int on_device, const uint8_t **dev, long long *dev_stride, uint8_t **owned)
+{
+  *owned = nullptr;
+  if (nseq < 1 || alen < 1 || !msa || row_stride < alen) { rsb_set_error(ctx, "bad alignment arguments"); return 1; }
+  if (on_device) { *dev = msa; *dev_stride = row_stride; return 0; }
+  RSB_CUDA_OK(cudaMalloc(owned, (size_t) nseq * alen));
+  cudaError_t e = cudaMemcpy2DAsync(*owned, alen, msa, (size_t) row_stride, alen, nseq, cudaMemcpyHostToDevice, ctx->stream);
+  if (e != cudaSuccess) { cudaFree(*owned); *owned = nullptr; rsb_set_error(ctx, "alignment upload: %s", cudaGetErrorString(e)); return 1; }
+  *dev = *owned; *dev_stride = alen;
+  return 0;
+}
+} // namespace
+
+#define PREP_OK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    rsb_set_error(ctx, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); goto done; } } while (0)
+
+/* msamanip_RemoveGapColumns' column test, src/msamanip.c:486-500 */
+int rsb_msa_gap_columns(rsb_ctx *ctx, const uint8_t *msa, int nseq, int alen, int64_t row_stride, int on_device, const double *wgt,
+                        double gapthresh, uint8_t *useme)
+{
+  RSB_CUDA_OK(cudaSetDevice(ctx->device));
+  const uint8_t *d = nullptr; long long ds = 0; uint8_t *owned = nullptr, *d_use = nullptr; double *d_w = nullptr;
+  int rc = 1;
+  if (stage_msa(ctx, msa, nseq, alen, row_stride, on_device, &d, &ds, &owned)) return 1;
+  PREP_OK(cudaMalloc(&d_use, alen));
+  if (wgt) { PREP_OK(cudaMalloc(&d_w, sizeof(double) * nseq)); PREP_OK(cudaMemcpyAsync(d_w, wgt, sizeof(double) * nseq, cudaMemcpyHostToDevice, ctx->stream)); }
+  PREP_OK(rsb_launch_gap_columns(d, nseq, alen, ds, d_w, 1.0 - gapthresh, d_use, ctx->stream));
+  ctx->launches++;
+  PREP_OK(cudaMemcpyAsync(useme, d_use, alen, cudaMemcpyDeviceToHost, ctx->stream));
+  PREP_OK(cudaStreamSynchronize(ctx->stream));
+  rc = 0;
+done:
+  cudaFree(owned); cudaFree(d_use); cudaFree(d_w);
+  return rc;
+}
+
+/* esl_msaweight_PB (src/R-scape.c:1556) */
+int rsb_msa_pb_weights(rsb_ctx *ctx, const uint8_t *msa, int nseq, int alen, int64_t row_stride, int on_device, double *wgt)
+{
+  RSB_CUDA_OK(cudaSetDevice(ctx->device));
+  const uint8_t *d = nullptr; long long ds = 0; uint8_t *owned = nullptr; double *d_coef = nullptr, *d_w = nullptr;
+  int rc = 1;
+  if (stage_msa(ctx, msa, nseq, alen, row_stride, on_device, &d, &ds, &owned)) return 1;
+  PREP_OK(cudaMalloc(&d_coef, sizeof(double) * 4 * (size_t) alen));
+  PREP_OK(cudaMalloc(&d_w, sizeof(double) * nseq));
+  PREP_OK(rsb_launch_pb_weights(d, nseq, alen, ds, d_coef, d_w, ctx->stream));
+  ctx->launches += 3;
+  PREP_OK(cudaMemcpyAsync(wgt, d_w, sizeof(double) * nseq, cudaMemcpyDeviceToHost, ctx->stream));
+  PREP_OK(cudaStreamSynchronize(ctx->stream));
+  rc = 0;
+done:
+  cudaFree(owned); cudaFree(d_coef); cudaFree(d_w);
+  return rc;
+}
+
+/* esl_dst_XPairId for a list of sequence pairs (pairs: int [npairs][2]) -> pid[npairs]; pairs == NULL: every pair, and out is the
+ * distance matrix double [nseq][nseq] = 1 - pid (diagonal 0), what esl_msaweight_GSC builds its UPGMA tree from */
+int rsb_msa_pair_identity(rsb_ctx *ctx, const uint8_t *msa, int nseq, int alen, int64_t row_stride, int on_device, const int *pairs, int64_t npairs,
+                          double *out)
+{
+  RSB_CUDA_OK(cudaSetDevice(ctx->device));
+  const uint8_t *d = nullptr; long long ds = 0; uint8_t *owned = nullptr; int *d_pairs = nullptr; double *d_out = nullptr;
+  int rc = 1;
+  const long long np = pairs ? (long long) npairs : (long long) nseq * (nseq - 1) / 2;
+  const size_t nout = pairs ? (size_t) npairs : (size_t) nseq * nseq;
+  if (pairs) for (int64_t k = 0; k < npairs; k++)
+    if (pairs[2 * k] < 0 || pairs[2 * k] >= nseq || pairs[2 * k + 1] < 0 || pairs[2 * k + 1] >= nseq) { rsb_set_error(ctx, "rsb_msa_pair_identity: pair %lld out of range", (long long) k); return 1; }
+  if (stage_msa(ctx, msa, nseq, alen, row_stride, on_device, &d, &ds, &owned)) return 1;
+  PREP_OK(cudaMalloc(&d_out, sizeof(double) * std::max<size_t>(nout, 1)));
+  if (pairs && npairs > 0) { PREP_OK(cudaMalloc(&d_pairs, sizeof(int) * 2 * (size_t) npairs)); PREP_OK(cudaMemcpyAsync(d_pairs, pairs, sizeof(int) * 2 * (size_t) npairs, cudaMemcpyHostToDevice, ctx->stream)); }
+  PREP_OK(rsb_launch_pair_identity(d, nseq, alen, ds, d_pairs, np, d_out, ctx->stream));
+  ctx->launches += pairs ? 1 : 2;
+  PREP_OK(cudaMemcpyAsync(out, d_out, sizeof(double) * nout, cudaMemcpyDeviceToHost, ctx->stream));
+  PREP_OK(cudaStreamSynchronize(ctx->stream));
+  rc = 0;
+done:
+  cudaFree(owned); cudaFree(d_pairs); cudaFree(d_out);
+  return rc;
+}
+
+/* struct_ColumnSubset's residue part: out [nseq][nkeep] = the columns with useme != 0 (out may be a device pointer when out_on_device) */
+int rsb_msa_column_subset(rsb_ctx *ctx, const uint8_t *msa, int nseq, int alen, int64_t row_stride, int on_device, const uint8_t *useme,
+                          uint8_t *out, int out_on_device, int *nkeep_out)
+{
+  RSB_CUDA_OK(cudaSetDevice(ctx->device));
+  const uint8_t *d = nullptr; long long ds = 0; uint8_t *owned = nullptr, *d_out = nullptr; int *d_cols = nullptr;
+  int rc = 1;
+  std::vector<int> cols;
+  for (int c = 0; c < alen; c++) if (useme[c]) cols.push_back(c);
+  const int nkeep = (int) cols.size();
+  if (nkeep_out) *nkeep_out = nkeep;
+  if (nkeep == 0) return 0;
+  if (stage_msa(ctx, msa, nseq, alen, row_stride, on_device, &d, &ds, &owned)) return 1;
+  PREP_OK(cudaMalloc(&d_cols, sizeof(int) * nkeep));
+  PREP_OK(cudaMemcpyAsync(d_cols, cols.data(), sizeof(int) * nkeep, cudaMemcpyHostToDevice, ctx->stream));
+  if (!out_on_device) PREP_OK(cudaMalloc(&d_out, (size_t) nseq * nkeep));
+  PREP_OK(rsb_launch_column_subset(d, nseq, ds, d_cols, nkeep, out_on_device ? out : d_out, ctx->stream));
+  ctx->launches++;
+  if (!out_on_device) PREP_OK(cudaMemcpyAsync(out, d_out, (size_t) nseq * nkeep, cudaMemcpyDeviceToHost, ctx->stream));
+  PREP_OK(cudaStreamSynchronize(ctx->stream));
+  rc = 0;
+done:
+  cudaFree(owned); cudaFree(d_cols); cudaFree(d_out);
+  return rc;
+}
+#undef PREP_OK
 
 // ---------------------------------------------------------------------------------------------- communicator (multi-GPU)
 int rsb_comm_id(uint8_t *id128)

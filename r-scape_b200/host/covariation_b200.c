@@ -19,6 +19,7 @@
 #include <string.h>
 #include <math.h>
 #include <limits.h>
+#include <pthread.h>
 
 #include "rscape_b200_host.h"
 
@@ -206,18 +207,78 @@ slots_for(int nseq, int alen, int nnull)
   return r;
 }
 
+/* One device's share of the null loop: replicates [r0, r1) scanned into that device's histogram with bin width w. */
+struct null_worker {
+  /* in */
+  struct data_s *data; ESL_MSA **nulls; int r0, r1, device, slices, base, cls, corr; double w; const double *ap; int want_last;
+  /* out */
+  double *minmax;            /* [r1 - r0][2] */
+  uint64_t *bins; int nb;    /* the device's histogram up to the bin of its largest score (+ margin) */
+  uint64_t n_added;
+  int status; char err[eslERRBUFSIZE];
+};
+
+static void *
+null_worker_run(void *arg)
+{
+  struct null_worker *wk = arg;
+  struct data_s   *data = wk->data;
+  struct mutual_s *mi = data->mi;
+  rsb_ctx  *ctx = NULL;
+  uint8_t  *stage = NULL;
+  size_t    N = (size_t) mi->nseq, L = (size_t) mi->alen;
+  int       nmine = wk->r1 - wk->r0, slots, r0, r, s, imax;
+  double    hi = -eslINFINITY;
+
+  wk->status = eslFAIL; wk->err[0] = 0; wk->bins = NULL; wk->nb = 0; wk->n_added = 0;
+  slots = slots_for((int) N, (int) L, nmine);
+  if (rsb_create(wk->device, NULL, &ctx) != 0) { snprintf(wk->err, eslERRBUFSIZE, "%s", rsb_create_error()); goto DONE; }
+  if (rsb_configure(ctx, (int) N, (int) L, slots, wk->slices) != 0 ||
+      rsb_set_weights(ctx, wk->nulls[0]->wgt) != 0 ||                              /* nulls carry the input's weights (:1668) */
+      (data->msa2pdb && rsb_set_pair_exclusion(ctx, data->msa2pdb, RSB_DATA_MIND(data)) != 0))   /* covariation.c:421-427 */
+    { snprintf(wk->err, eslERRBUFSIZE, "%s", rsb_error(ctx)); goto DONE; }
+  if ((stage = malloc((size_t) slots * N * L)) == NULL) { snprintf(wk->err, eslERRBUFSIZE, "allocation failed"); goto DONE; }
+  for (r0 = wk->r0; r0 < wk->r1; r0 += slots) {
+    int n = ESL_MIN(slots, wk->r1 - r0);
+    for (r = 0; r < n; r++)
+      for (s = 0; s < (int) N; s++) memcpy(stage + ((size_t) r * N + (size_t) s) * L, wk->nulls[r0 + r]->ax[s] + 1, L);
+    if (rsb_null_hist(ctx, stage, n, (int64_t) L, (int64_t) (N * L), 0, wk->base, wk->cls, wk->corr, wk->ap,
+                      data->tol, wk->w, data->bmin, wk->minmax + 2 * (r0 - wk->r0)) != 0)
+      { snprintf(wk->err, eslERRBUFSIZE, "%s.\nFailed to run null R-scape", rsb_error(ctx)); goto DONE; }
+  }
+  for (r = 0; r < nmine; r++) hi = ESL_MAX(hi, wk->minmax[2 * r + 1]);
+  if (wk->w > 0.) {
+    double nbd = ceil((ESL_MAX(hi, data->bmin + wk->w) - data->bmin) / wk->w) + 8.;
+    wk->nb = (nbd < 64.) ? 64 : (nbd > 4194304.) ? 4194304 : (int) nbd;
+    if ((wk->bins = calloc((size_t) wk->nb, sizeof(uint64_t))) == NULL) { snprintf(wk->err, eslERRBUFSIZE, "allocation failed"); goto DONE; }
+    if (rsb_hist_read(ctx, wk->bins, wk->nb, &wk->n_added, &imax) != 0) { snprintf(wk->err, eslERRBUFSIZE, "%s", rsb_error(ctx)); goto DONE; }
+  }
+  /* quirk Q3: mi keeps the last null's nseff / ngap (read by power_SPAIR_Create, src/power.c:94-95) */
+  if (wk->want_last && wk->base != RAF && wk->base != RAFS && rsb_last_nseff(ctx, mi->nseff[0], mi->ngap[0]) != 0)
+    { snprintf(wk->err, eslERRBUFSIZE, "%s", rsb_error(ctx)); goto DONE; }
+  wk->status = eslOK;
+ DONE:
+  free(stage);
+  if (ctx) rsb_destroy(ctx);
+  return NULL;
+}
+
+/* The null loop of null_rscape (src/R-scape.c:1650-1697) on RSCAPE_B200_GPUS devices (default 1; "all" = every visible device):
+ * contiguous blocks of replicates per device, one host thread and one context per device, the integer histograms summed on the
+ * host (tens of KB).  The width pass (calculate_width_histo, :1681-1684) is fused with the scan of replicate 0: every device
+ * histograms with the incoming data->w (cfg->w, 0.05) and the loop is repeated only if the width replicate 0 asks for is
+ * different -- the scan draws no random numbers, so the result is the reference's either way. */
 int
 null_rscape_b200(struct data_s *data, ESL_MSA **nulls, int nnull, int hpts, RANKLIST **ret_cumranklist)
 {
   struct mutual_s *mi = data->mi;
-  rsb_ctx  *ctx = NULL;
-  RANKLIST *cum = NULL;
-  uint8_t  *stage = NULL;
-  uint64_t *bins = NULL, n_added = 0;
-  double   *minmax = NULL, ap[16], w, mn, mx, bmax = -eslINFINITY, xmin = eslINFINITY, xmax = -eslINFINITY;
+  struct null_worker *wk = NULL;
+  pthread_t *th = NULL;
+  RANKLIST  *cum = NULL;
+  double    *minmax = NULL, ap[16], w, w_true, bmax = -eslINFINITY, xmin = eslINFINITY, xmax = -eslINFINITY;
   const char *env;
-  size_t    N = (size_t) mi->nseq, L = (size_t) mi->alen;
-  int       base, corr, cls, slots, device = 0, slices = 0, r0, r, s, imax, status = eslFAIL, x, y, nb;
+  uint64_t   n_added = 0;
+  int        base, corr, cls, device = 0, slices = 0, ngpu = 1, ndev = 1, attempt, k, r, s, b, status = eslFAIL, x, y;
 
   *ret_cumranklist = NULL;
   if (nnull < 1) return eslOK;
@@ -232,33 +293,41 @@ null_rscape_b200(struct data_s *data, ESL_MSA **nulls, int nnull, int hpts, RANK
 
   if ((env = getenv("RSCAPE_B200_DEVICE")) != NULL) device = atoi(env);
   if ((env = getenv("RSCAPE_B200_SLICES")) != NULL) slices = atoi(env);
-  slots = slots_for((int) N, (int) L, nnull);
-  if (rsb_create(device, NULL, &ctx) != 0) { snprintf(data->errbuf, eslERRBUFSIZE, "%s", rsb_create_error()); goto DONE; }
-  if (rsb_configure(ctx, (int) N, (int) L, slots, slices) != 0 ||
-      rsb_set_weights(ctx, nulls[0]->wgt) != 0 ||                                  /* nulls carry the input's weights (:1668) */
-      (data->msa2pdb && rsb_set_pair_exclusion(ctx, data->msa2pdb, RSB_DATA_MIND(data)) != 0))   /* covariation.c:421-427 */
-    { snprintf(data->errbuf, eslERRBUFSIZE, "%s", rsb_error(ctx)); goto DONE; }
+  ndev = rsb_device_count();
+  if ((env = getenv("RSCAPE_B200_GPUS")) != NULL) ngpu = (strcmp(env, "all") == 0) ? ndev : atoi(env);
+  if (ngpu > ndev && !getenv("RSCAPE_B200_GPUS_OVERSUBSCRIBE")) ngpu = ndev;      /* (tests: several contexts on one device) */
+  if (ngpu > nnull) ngpu = nnull;
+  if (ngpu < 1) ngpu = 1;
 
-  stage  = malloc((size_t) slots * N * L);
+  wk = calloc((size_t) ngpu, sizeof(*wk)); th = calloc((size_t) ngpu, sizeof(*th));
   minmax = malloc(sizeof(double) * 2 * (size_t) nnull);
-  if (!stage || !minmax) { snprintf(data->errbuf, eslERRBUFSIZE, "allocation failed"); goto DONE; }
+  if (!wk || !th || !minmax) { snprintf(data->errbuf, eslERRBUFSIZE, "allocation failed"); goto DONE; }
 
-  /* first null: width of the histogram (calculate_width_histo, :1681-1684) */
-  for (s = 0; s < (int) N; s++) memcpy(stage + (size_t) s * L, nulls[0]->ax[s] + 1, L);
-  if (rsb_null_width(ctx, stage, (int64_t) L, 0, base, cls, corr, data->allowpair ? ap : NULL, data->tol,
-                     data->w, data->bmin, hpts, &w, &mn, &mx) != 0)
-    { snprintf(data->errbuf, eslERRBUFSIZE, "%s.\nFailed to calculate the width of the histogram", rsb_error(ctx)); goto DONE; }
+  w = data->w;
+  for (attempt = 0; attempt < 2; attempt++) {
+    for (k = 0; k < ngpu; k++) {
+      int q = nnull / ngpu, extra = nnull % ngpu;
+      free(wk[k].bins); wk[k].bins = NULL;
+      wk[k].data = data; wk[k].nulls = nulls; wk[k].r0 = k * q + ESL_MIN(k, extra); wk[k].r1 = wk[k].r0 + q + (k < extra ? 1 : 0);
+      wk[k].device = (ngpu == 1) ? device : (ndev > 0 ? k % ndev : 0); wk[k].slices = slices; wk[k].base = base; wk[k].cls = cls; wk[k].corr = corr;
+      wk[k].w = w; wk[k].ap = data->allowpair ? ap : NULL; wk[k].minmax = minmax + 2 * wk[k].r0; wk[k].want_last = (wk[k].r1 == nnull);
+    }
+    if (ngpu == 1) null_worker_run(&wk[0]);
+    else {
+      for (k = 0; k < ngpu; k++) if (pthread_create(&th[k], NULL, null_worker_run, &wk[k]) != 0) { wk[k].status = eslFAIL; snprintf(wk[k].err, eslERRBUFSIZE, "pthread_create failed"); th[k] = 0; }
+      for (k = 0; k < ngpu; k++) if (th[k]) pthread_join(th[k], NULL);
+    }
+    for (k = 0; k < ngpu; k++) if (wk[k].status != eslOK) { snprintf(data->errbuf, eslERRBUFSIZE, "%s", wk[k].err); goto DONE; }
+    /* calculate_width_histo on replicate 0's score range (src/R-scape.c:1355-1360) */
+    if (!(minmax[1] > data->bmin)) { snprintf(data->errbuf, eslERRBUFSIZE, "bmin %f should be larger than maxCOV %f.\nFailed to calculate the width of the histogram", data->bmin, minmax[1]); goto DONE; }
+    w_true = ESL_MIN(data->w, (minmax[1] - ESL_MAX(data->bmin, minmax[0])) / (double) hpts);
+    if (w_true < data->tol) w_true = 0.0;
+    if (w_true == w) break;
+    w = w_true;                                                                    /* rare: the first null spans less than hpts * w */
+  }
   data->w = w;
 
   if (w >= 1e-20) {                                                                /* else "covariation scores are almost constant" (covariation.c:349) */
-    for (r0 = 0; r0 < nnull; r0 += slots) {
-      int n = ESL_MIN(slots, nnull - r0);
-      for (r = 0; r < n; r++)
-        for (s = 0; s < (int) N; s++) memcpy(stage + ((size_t) r * N + (size_t) s) * L, nulls[r0 + r]->ax[s] + 1, L);
-      if (rsb_null_hist(ctx, stage, n, (int64_t) L, (int64_t) (N * L), 0, base, cls, corr, data->allowpair ? ap : NULL,
-                        data->tol, w, data->bmin, minmax + 2 * r0) != 0)
-        { snprintf(data->errbuf, eslERRBUFSIZE, "%s.\nFailed to run null R-scape", rsb_error(ctx)); goto DONE; }
-    }
     /* cumulative rank list in the reference's form: bmax = largest per-replicate maxCOV + 5w (covariation.c:415, :699) */
     for (r = 0; r < nnull; r++) {
       double lo = ESL_MAX(minmax[2 * r], data->bmin + w), hi = ESL_MAX(minmax[2 * r + 1], data->bmin + w), bm = minmax[2 * r + 1] + 5 * w;
@@ -266,27 +335,29 @@ null_rscape_b200(struct data_s *data, ESL_MSA **nulls, int nnull, int hpts, RANK
       bmax = ESL_MAX(bmax, bm); xmin = ESL_MIN(xmin, lo); xmax = ESL_MAX(xmax, hi);
     }
     if ((cum = cov_CreateRankList(bmax, data->bmin, w)) == NULL) { snprintf(data->errbuf, eslERRBUFSIZE, "rank list allocation failed"); goto DONE; }
-    nb = cum->ha->nb;
-    if ((bins = calloc((size_t) nb + 1, sizeof(uint64_t))) == NULL) goto DONE;
-    if (rsb_hist_read(ctx, bins, nb, &n_added, &imax) != 0) { snprintf(data->errbuf, eslERRBUFSIZE, "%s", rsb_error(ctx)); goto DONE; }
-    for (s = 0; s < nb; s++) { cum->ha->obs[s] = bins[s]; cum->ha->Nc += bins[s]; cum->ha->No += bins[s]; }
+    for (k = 0; k < ngpu; k++) {                                                   /* null_add2cumranklist across devices: integer sums */
+      for (b = 0; b < wk[k].nb; b++) {
+        if (wk[k].bins[b] == 0) continue;
+        if (b >= cum->ha->nb) { snprintf(data->errbuf, eslERRBUFSIZE, "internal: null score beyond the rank list"); goto DONE; }
+        cum->ha->obs[b] += wk[k].bins[b]; cum->ha->Nc += wk[k].bins[b]; cum->ha->No += wk[k].bins[b];
+      }
+      n_added += wk[k].n_added;
+    }
     cum->ha->n    = n_added;
     cum->ha->xmin = xmin;
     cum->ha->xmax = xmax;
     esl_histogram_Score2Bin(cum->ha, xmin, &cum->ha->imin);
     esl_histogram_Score2Bin(cum->ha, xmax, &cum->ha->imax);
+    (void) s;
   }
-  /* quirk Q3: mi keeps the last null's nseff / ngap (read by power_SPAIR_Create, src/power.c:94-95) */
-  if (w >= 1e-20 && base != RAF && base != RAFS && rsb_last_nseff(ctx, mi->nseff[0], mi->ngap[0]) != 0)
-    { snprintf(data->errbuf, eslERRBUFSIZE, "%s", rsb_error(ctx)); goto DONE; }
 
   *ret_cumranklist = cum; cum = NULL;
   status = eslOK;
 
  DONE:
   if (cum) cov_FreeRankList(cum);
-  free(stage); free(minmax); free(bins);
-  if (ctx) rsb_destroy(ctx);
+  if (wk) for (k = 0; k < ngpu; k++) free(wk[k].bins);
+  free(wk); free(th); free(minmax);
   return status;
 }
 

@@ -70,18 +70,26 @@ def test_corr_api_error_convention(po):
     lib.glue_msa_destroy(m)
 
 
-def test_null_rscape_b200_matches_oracle_cumulative_ranklist(po, oracle):
+@pytest.mark.parametrize("covtype,stat", [(4, "GT"), (7, "MI")])            # GTp: w stays 0.05; MIp: the first null asks for a narrower bin -> the loop is redone
+@pytest.mark.parametrize("gpus", [None, "3", "all"])
+def test_null_rscape_b200_matches_oracle_cumulative_ranklist(po, oracle, monkeypatch, gpus, covtype, stat):
+    """gpus: RSCAPE_B200_GPUS -- the C-level multi-GPU entry (one host thread + one context per device, histograms summed on the
+    host).  On a one-GPU box the three contexts share the device (RSCAPE_B200_GPUS_OVERSUBSCRIBE): same protocol, same result."""
     from test_gpu_nulls import oracle_null_loop
+    if gpus is not None:
+        monkeypatch.setenv("RSCAPE_B200_GPUS", gpus)
+        monkeypatch.setenv("RSCAPE_B200_GPUS_OVERSUBSCRIBE", "1")
     lib = _lib(po)
     glue = C.CDLL(os.path.join(ROOT, "oracle", "libglue_b200.so"))
     N, L, R = 180, 55, 6
     nulls = np.stack([po.synthetic_msa(N, L, seed=900 + r)[0] for r in range(R)])
     wgt = po.synthetic_msa(N, L, seed=9)[1]
-    w_ref, view, _ = oracle_null_loop(po, oracle, nulls, wgt, po.GT, po.C16, po.APC)
+    w_ref, view, _ = oracle_null_loop(po, oracle, nulls, wgt, getattr(po, stat), po.C16, po.APC)
+    assert (w_ref == 0.05) == (stat == "GT")
     ap = np.ascontiguousarray(po.ALLOWPAIR_WC_GU)
     mi = lib.corr_Create(L, N, 0, 8, 50, lib.glue_abc_rna(), po.C16)
     apm = lib.glue_allowpair_from(ap.ctypes.data_as(C.POINTER(C.c_double)))
-    data = lib.glue_data_create(mi, apm, 4, 1e-6)                     # GTp
+    data = lib.glue_data_create(mi, apm, covtype, 1e-6)
     meta, imeta, cnt = np.zeros(5), np.zeros(3, np.int32), np.zeros(3, np.uint64)
     bins = np.zeros(view.nb + 16, np.uint64)
     glue.glue_null_rscape.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
@@ -93,7 +101,11 @@ def test_null_rscape_b200_matches_oracle_cumulative_ranklist(po, oracle):
     assert imeta[0] == view.nb and imeta[1] == view.imin and imeta[2] == view.imax
     assert abs(meta[1] - view.bmax) <= 1e-9 * abs(view.bmax)
     assert cnt[0] == view.n and cnt[1] == view.Nc and cnt[2] == view.No
-    assert np.array_equal(bins[:view.nb], view.obs)
+    if stat == "GT":
+        assert np.array_equal(bins[:view.nb], view.obs)
+    else:
+        from _helpers import assert_bins_identical
+        assert_bins_identical(bins[:view.nb], view.obs, oracle_null_loop.scores, -10.0, w_ref)
     assert abs(meta[3] - view.xmin) <= 1e-9 * max(1, abs(view.xmin)) and abs(meta[4] - view.xmax) <= 1e-9 * max(1, abs(view.xmax))
     lib.glue_data_destroy(data)
     lib.esl_dmatrix_Destroy(apm)
