@@ -320,6 +320,13 @@ typedef struct {
 } ESL_TREE;
 extern ESL_TREE *esl_tree_Create(int ntaxa);
 extern void      esl_tree_Destroy(ESL_TREE *T);
+/* easel_shim_fit.c: what Tree_CalculateExtFromMSA / Tree_RootAtMidPoint (src/msatree.c:49-105, 524-790) call around FastTree's output */
+extern int       esl_tree_ReadNewick(FILE *fp, char *errbuf, ESL_TREE **ret_T);
+extern int       esl_tree_RenumberNodes(ESL_TREE *T);
+extern int       esl_tree_SetTaxaParents(ESL_TREE *T);
+extern int       esl_tree_SetCladesizes(ESL_TREE *T);
+extern int       esl_tree_Validate(ESL_TREE *T, char *errbuf);
+extern int       esl_tree_Grow(ESL_TREE *T);
 
 /* ---- histogram ("full" histogram subset used by src/covariation.c) ---- */
 typedef struct {
@@ -385,9 +392,15 @@ typedef struct esl_getopts_s ESL_GETOPTS;
 typedef struct esl_sqfile_s  ESL_SQFILE;
 typedef struct esl_msafile_s ESL_MSAFILE;
 typedef struct esl_fileparser_s ESL_FILEPARSER;
-/* tail-fit survival functions: only their addresses are taken (src/covariation.c:1931,1962); the fits stay Easel code */
+/* tail fits of the null histogram (src/covariation.c:1915-1973), restated in easel_shim_fit.c */
 extern double esl_exp_generic_surv(double x, void *params);
 extern double esl_gam_generic_surv(double x, void *params);
+extern double esl_gam_cdf (double x, double mu, double lambda, double tau);
+extern double esl_gam_surv(double x, double mu, double lambda, double tau);
+extern int    esl_stats_IncompleteGamma(double a, double x, double *ret_pax, double *ret_qax);
+extern int    esl_histogram_SetTailByMass(ESL_HISTOGRAM *h, double pmass, double *ret_newmass);
+extern int    esl_exp_FitCompleteBinned(ESL_HISTOGRAM *h, double *ret_mu, double *ret_lambda);
+extern int    esl_gam_FitCompleteBinned(ESL_HISTOGRAM *h, double *ret_mu, double *ret_lambda, double *ret_tau);
 
 #ifdef __cplusplus
 }

@@ -58,6 +58,14 @@ int rsb_get_quantisation(rsb_ctx *ctx, int64_t *wq, int *q, int *nslices);
 /* Largest |wq_s 2^-q - w_s| over the sequences (weight units) and log2(max weight / that error): how faithfully the
  * fixed-point weights follow the double weights of msa->wgt (src/correlators.c:1716 reads them as double). */
 int rsb_get_quantisation_error(rsb_ctx *ctx, double *max_abs_err, double *effective_bits);
+/* Mixed precision (the "split path with a stated bound" of the weighted counts): contract the NULL alignments (rsb_null_width*,
+ * rsb_null_hist*) with nslices <= S base-256 digits of the same weights, the input alignment keeps all S.  The nulls only feed
+ * the score histogram whose tail gives the E-values (src/R-scape.c:1650-1697); with 2 slices their weights carry ~21 bits and
+ * the null scores move by less than 1e-5 of the histogram's bin width (bound measured in tests/test_gpu_mixed.py).
+ * 0 = off (default): one set of weights everywhere.  Takes effect at the next rsb_set_weights. */
+int rsb_set_null_slices(rsb_ctx *ctx, int nslices);
+/* the quantisation the nulls are scored with (= rsb_get_quantisation / _error when rsb_set_null_slices is off); any pointer may be NULL */
+int rsb_get_null_quantisation(rsb_ctx *ctx, int64_t *wq, int *q, int *nslices, double *max_abs_err, double *effective_bits);
 
 /* ---- one alignment: the corr_* sequence of cov_Calculate (src/covariation.c:78-258) ----------- */
 /* corr_Probs (src/correlators.c:1424): counts -> pp, nseff, ngap, ps, pm.  Host outputs may be NULL.
@@ -214,6 +222,21 @@ int rsb_null_width_pool(rsb_ctx *ctx, int rep, int stat, int covclass, int actyp
                         double w_old, double bmin, int hpts, double *w_out, double *mincov, double *maxcov);
 int rsb_null_hist_pool(rsb_ctx *ctx, int first_rep, int nrep, int stat, int covclass, int actype, const double *allowpair,
                        double tol, double w, double bmin, double *minmax);
+/* Several (statistic, correction) combinations from ONE contraction per null -- the statistic sweep of BASELINE config 5.
+ * cov_Calculate (src/covariation.c:100-258) computes the probabilities once (corr_Probs) and then dispatches on covtype; a sweep
+ * over covtypes repeats everything.  Here each null is packed and contracted once, all requested statistics of
+ * {CHI, OMES, GT, MI, MIr, MIg} are evaluated from the same count planes in one pass, and combination k = (stat[k], actype[k])
+ * is corrected and added to its own cumulative histogram with its own bin width w[k] (w[k] <= 0: score range only, no histogram
+ * -- the width pass).  covclass is shared.  minmax: double [ncombo][nrep][2] (may be NULL).  Every histogram equals the one
+ * rsb_null_hist leaves for that combination alone.  RAF / RAFS use unit weights, i.e. another contraction: rsb_null_hist. */
+int rsb_null_hist_multi(rsb_ctx *ctx, const uint8_t *nulls, int nrep, int64_t row_stride, int64_t rep_stride, int on_device, int ncombo,
+                        const int *stat, const int *actype, int covclass, const double *allowpair, double tol, const double *w, double bmin,
+                        double *minmax);
+int rsb_null_hist_multi_pool(rsb_ctx *ctx, int first_rep, int nrep, int ncombo, const int *stat, const int *actype, int covclass,
+                             const double *allowpair, double tol, const double *w, double bmin, double *minmax);
+/* histogram of combination `combo` (as rsb_hist_read); rsb_hist_reset_multi clears all of them */
+int rsb_hist_read_multi(rsb_ctx *ctx, int combo, uint64_t *bins, int nb_cap, uint64_t *n_out, int *imax_out);
+int rsb_hist_reset_multi(rsb_ctx *ctx);
 /* copy pool entries to / from the host: uint8 [nrep][nseq][alen] (e.g. for --outnull, or host-made nulls scanned repeatedly) */
 int rsb_pool_get(rsb_ctx *ctx, int first_rep, int nrep, uint8_t *out);
 int rsb_pool_put(rsb_ctx *ctx, int first_rep, int nrep, const uint8_t *in);
@@ -259,6 +282,9 @@ int rsb_msa_pair_identity(rsb_ctx *ctx, const uint8_t *msa, int nseq, int alen, 
 int rsb_counters(rsb_ctx *ctx, int64_t *launches, double *gram_ms, int64_t *gram_launches, int reset);
 /* enable (1) / disable (0) event timing around the gram kernel */
 int rsb_profile_gram(rsb_ctx *ctx, int enable);
+/* the same per operand geometry, as of the last rsb_counters call (before its reset): which = 0 the input alignment's weights,
+ * 1 unit weights (RAF tables, substitution counts), 2 the nulls' own weights (rsb_set_null_slices); *nslices = its digit slices */
+int rsb_counters_geometry(rsb_ctx *ctx, int which, double *gram_ms, int64_t *gram_launches, int *nslices);
 
 #ifdef __cplusplus
 }

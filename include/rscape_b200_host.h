@@ -100,6 +100,13 @@ extern int        null_rscape_b200(struct data_s *data, ESL_MSA **nulls, int nnu
 extern int        cov_CreateHitList_b200(struct data_s *data, struct mutual_s *mi, RANKLIST *ranklist, const uint8_t *pairmask,
                                          HITLIST **ret_hitlist);
 extern void       cov_FreeHitList(HITLIST *hitlist);
+/* "Histogram and Fit" of cov_SignificantPairs_Ranking, src/covariation.c:459-487: choose the censored tail mass
+ * (cov_histogram_pmass, :2484-2505, a `static` of the reference), fit an exponential (data->doexpfit) or a gamma to the tail of
+ * the cumulative null histogram h (cov_NullFitExponential / cov_NullFitGamma, :1915-1973) and tabulate the fitted survival
+ * (cov_histogram_SetSurvFitTail, :1677-1699).  *ret_survfit: double[2 h->nb], malloc'd, NULL when the fit has no finite rate.
+ * Sets h->phi / cmin / z as esl_histogram_SetTailByMass does.  Host arithmetic on O(bins) data; the device never sees it. */
+extern int        cov_NullFit_b200(ESL_HISTOGRAM *h, double pmass, double fracfit, int doexpfit, double **ret_survfit, double *ret_newmass,
+                                   double *ret_mu, double *ret_lambda, double *ret_tau, char *errbuf);
 /* pair mask (uint8 [alen][alen], entries i<j) of the base pairs of a ct array in Easel's convention (1-based, 0 = unpaired) */
 extern int        cov_PairMaskFromCT(const int *ct, int64_t alen, uint8_t *pairmask);
 

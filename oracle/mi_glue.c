@@ -200,3 +200,27 @@ glue_msaprep(int nseq, int L, const uint8_t *res, const double *wgt_in, int what
   return status;
 }
 #endif
+
+/* Tail fit of a null histogram given as flat arrays: geom = { bmin, w, xmax }, ig = { nb, imin, imax }; n = scores held.
+ * out = { newmass, mu, lambda, tau, phi, cmin }; survfit: double [2 nb] (zeros when the fit has no finite rate).
+ *   host library : cov_NullFit_b200 (the mirror of src/covariation.c:459-487)
+ *   reference    : its own cov_histogram_pmass + cov_NullFitGamma / cov_NullFitExponential (ref_glue_evalue.c) */
+#ifndef GLUE_REFERENCE
+int
+glue_nullfit(const double *geom, const int *ig, uint64_t n, uint64_t *obs, double pmass, double fracfit, int doexpfit, double *survfit, double *out)
+{
+  ESL_HISTOGRAM h;
+  double       *sf = NULL;
+  char          errbuf[eslERRBUFSIZE];
+  int           status, b;
+  memset(&h, 0, sizeof(h));
+  h.bmin = geom[0]; h.w = geom[1]; h.xmax = geom[2]; h.nb = ig[0]; h.imin = ig[1]; h.imax = ig[2]; h.cmin = h.imin;
+  h.bmax = h.bmin + h.w * h.nb; h.n = h.Nc = h.No = n; h.obs = obs;
+  status = cov_NullFit_b200(&h, pmass, fracfit, doexpfit, &sf, &out[0], &out[1], &out[2], &out[3], errbuf);
+  if (status != eslOK) return status;
+  out[4] = h.phi; out[5] = (double) h.cmin;
+  for (b = 0; b < 2 * h.nb; b++) survfit[b] = sf ? sf[b] : 0.0;
+  free(sf);
+  return eslOK;
+}
+#endif

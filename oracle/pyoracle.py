@@ -120,6 +120,27 @@ class NullFit:
         return NullFit(self.bmin, self.w, self.obs, self.xmax, phi, cmin, surv)
 
 
+def _nullfit_call(fn, null, pmass, fracfit, doexpfit):
+    geom = np.array([null.bmin, null.w, null.xmax])
+    ig = np.array([null.nb, null.imin, null.imax], dtype=np.int32)
+    surv, out = np.zeros(2 * null.nb), np.zeros(6)
+    fn.argtypes = [_dp, _ip, C.c_uint64, C.POINTER(C.c_uint64), C.c_double, C.c_double, C.c_int, _dp, _dp]
+    rc = fn(_d(geom), _i(ig), null.Nc, null.obs.ctypes.data_as(C.POINTER(C.c_uint64)), pmass, fracfit, 1 if doexpfit else 0, _d(surv), _d(out))
+    if rc != 0:
+        raise RuntimeError(f"tail fit failed with status {rc}")
+    fit = NullFit(null.bmin, null.w, null.obs, null.xmax, phi=out[4], cmin=int(out[5]), survfit=surv if surv.any() else None)
+    fit.newmass, fit.mu, fit.lam, fit.tau = out[0], out[1], out[2], out[3]
+    return fit
+
+
+def nullfit_host(null, pmass=0.0005, fracfit=1.0, doexpfit=False):
+    """The "Histogram and Fit" block of cov_SignificantPairs_Ranking (src/covariation.c:459-487) as the host library runs it
+    (cov_NullFit_b200 in r-scape_b200/host/covariation_b200.c, through oracle/libglue_b200.so): R-scape's defaults --pmass 0.0005,
+    --fracfit 1.0, gamma fit (src/R-scape.c:428-429).  Returns a NullFit with phi / cmin / survfit set."""
+    lib = C.CDLL(os.path.join(HERE, "libglue_b200.so"))
+    return _nullfit_call(lib.glue_nullfit, null, pmass, fracfit, doexpfit)
+
+
 class Oracle:
     def __init__(self, path=None):
         path = path or os.path.join(HERE, "liboracle.so")
@@ -402,6 +423,24 @@ class RefLib:
         return P
 
     # the reference's own static cov2evalue / evalue2cov (oracle/ref_glue_evalue.c includes src/covariation.c where it lies)
+    def nullfit(self, null, pmass=0.0005, fracfit=1.0, doexpfit=False):
+        """The reference's own cov_histogram_pmass + cov_NullFitGamma / cov_NullFitExponential (src/covariation.c:459-487, 1915-1973)."""
+        return _nullfit_call(self.lib.glue_ref_nullfit, null, pmass, fracfit, doexpfit)
+
+    def tree_from_newick(self, path, names, rootatmid=True):
+        """FastTree's Newick -> the rooted tree of Tree_CalculateExtFromMSA (src/msatree.c:84-95): the shim's Newick reader, then the
+        reference's own Tree_ReorderTaxaAccordingMSA + Tree_RootAtMidPoint."""
+        n = len(names)
+        arr = (C.c_char_p * n)(*[x.encode() for x in names])
+        left, right, parent = (np.zeros(n - 1, np.int32) for _ in range(3))
+        ld, rd = np.zeros(n - 1), np.zeros(n - 1)
+        g = self.lib
+        g.glue_ref_tree_from_newick.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_char_p), C.c_int, _ip, _ip, _ip, _dp, _dp]
+        rc = g.glue_ref_tree_from_newick(path.encode(), n, arr, 1 if rootatmid else 0, _i(left), _i(right), _i(parent), _d(ld), _d(rd))
+        if rc != 0:
+            raise RuntimeError(f"tree_from_newick failed with status {rc}")
+        return Tree(left, right, parent, ld, rd)
+
     def _evalue_args(self, null):
         geom = np.array([null.bmin, null.w, null.xmax, null.phi])
         ig = np.array([null.nb, null.imin, null.imax, null.cmin], dtype=np.int32)

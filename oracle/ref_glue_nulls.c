@@ -123,4 +123,33 @@ glue_ref_simulate(ESL_RANDOMNESS *r, ESL_TREE *T, const double *Q16, const uint8
   esl_msa_Destroy(root); esl_msa_Destroy(full);
   return status;
 }
+
+/* FastTree's Newick file -> the rooted tree R-scape hands to its null generator, as Tree_CalculateExtFromMSA does after the
+ * FastTree run (src/msatree.c:84-95): esl_tree_ReadNewick (the shim's restatement) + esl_tree_Validate, then the REFERENCE's own
+ * Tree_ReorderTaxaAccordingMSA (:823-912) and Tree_RootAtMidPoint (:524-790).  names: the alignment's sequence names in row order.
+ * Outputs: int [N-1] left / right / parent, double [N-1] ld / rd in Easel's convention (children <= 0 are taxa = alignment rows). */
+int
+glue_ref_tree_from_newick(const char *path, int nseq, const char **names, int rootatmid, int *left, int *right, int *parent, double *ld, double *rd)
+{
+  ESL_MSA  *msa = esl_msa_CreateDigital(glue_abc_rna(), nseq, 1);
+  ESL_TREE *T = NULL;
+  FILE     *fp = fopen(path, "r");
+  char      errbuf[eslERRBUFSIZE];
+  int       status = eslFAIL, v;
+
+  if (!fp || !msa) goto done;
+  for (v = 0; v < nseq; v++) { free(msa->sqname[v]); msa->sqname[v] = NULL; esl_strdup(names[v], -1, &msa->sqname[v]); }
+  if ((status = esl_tree_ReadNewick(fp, errbuf, &T)) != eslOK) { fprintf(stderr, "%s\n", errbuf); goto done; }
+  if (T->N != nseq) { status = eslFAIL; goto done; }
+  if ((status = esl_tree_Validate(T, errbuf)) != eslOK) { fprintf(stderr, "%s\n", errbuf); goto done; }
+  if ((status = Tree_ReorderTaxaAccordingMSA(msa, T, errbuf, FALSE)) != eslOK) { fprintf(stderr, "%s\n", errbuf); goto done; }
+  if (rootatmid && (status = Tree_RootAtMidPoint(&T, NULL, errbuf, FALSE)) != eslOK) { fprintf(stderr, "%s\n", errbuf); goto done; }
+  for (v = 0; v < nseq - 1; v++) { left[v] = T->left[v]; right[v] = T->right[v]; parent[v] = T->parent[v]; ld[v] = T->ld[v]; rd[v] = T->rd[v]; }
+  status = eslOK;
+done:
+  if (fp) fclose(fp);
+  esl_tree_Destroy(T);
+  esl_msa_Destroy(msa);
+  return status;
+}
 #endif

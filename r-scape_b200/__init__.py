@@ -60,6 +60,8 @@ def lib():
         L.rsb_set_weights.argtypes = [_vp, _dp]
         L.rsb_get_quantisation.argtypes = [_vp, _i64p, _ip, _ip]
         L.rsb_get_quantisation_error.argtypes = [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.rsb_set_null_slices.argtypes = [_vp, C.c_int]
+        L.rsb_get_null_quantisation.argtypes = [_vp, _i64p, _ip, _ip, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.rsb_probs.argtypes = [_vp, _vp, C.c_int64, C.c_int, C.c_double, _dp, _dp, _dp, _dp, _dp]
         L.rsb_fetch_probs.argtypes = [_vp, _dp, _dp, _dp, _dp, _dp]
         L.rsb_statistic.argtypes = [_vp, C.c_int, C.c_int, _dp, _vp, C.c_int64, C.c_int, _dp, _dp, _dp]
@@ -88,6 +90,11 @@ def lib():
                                          C.c_double, _dp]
         L.rsb_null_width_pool.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.c_double, C.c_double, C.c_double, C.c_int,
                                           _dp, _dp, _dp]
+        L.rsb_null_hist_multi.argtypes = [_vp, _vp, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int, _ip, _ip, C.c_int, _dp, C.c_double, _dp,
+                                          C.c_double, _dp]
+        L.rsb_null_hist_multi_pool.argtypes = [_vp, C.c_int, C.c_int, C.c_int, _ip, _ip, C.c_int, _dp, C.c_double, _dp, C.c_double, _dp]
+        L.rsb_hist_read_multi.argtypes = [_vp, C.c_int, _u64p, C.c_int, _u64p, _ip]
+        L.rsb_hist_reset_multi.argtypes = [_vp]
         L.rsb_pool_reserve.argtypes = [_vp, C.c_int]
         L.rsb_pool_get.argtypes = [_vp, C.c_int, C.c_int, _u8p]
         L.rsb_pool_put.argtypes = [_vp, C.c_int, C.c_int, _u8p]
@@ -113,6 +120,7 @@ def lib():
         L.rsb_comm_range.argtypes = [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.rsb_sharded_scan.argtypes = [_vp, _vp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.c_double, _dp, _dp, _dp]
         L.rsb_profile_gram.argtypes = [_vp, C.c_int]
+        L.rsb_counters_geometry.argtypes = [_vp, C.c_int, C.POINTER(C.c_double), _i64p, _ip]
         _lib = L
     return _lib
 
@@ -189,6 +197,17 @@ class Context:
         a, b = C.c_double(), C.c_double()
         self._ck(lib().rsb_get_quantisation_error(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def set_null_slices(self, nslices):
+        """Mixed precision: the nulls are contracted with `nslices` digit slices of the weights (0 = off); call before set_weights."""
+        self._ck(lib().rsb_set_null_slices(self._h, nslices))
+
+    def null_quantisation(self):
+        """(wq, q, S, largest |wq 2^-q - w|, effective bits) of the weights the null alignments are scored with."""
+        wq = np.zeros(self.N, dtype=np.int64)
+        q, S, a, b = C.c_int(), C.c_int(), C.c_double(), C.c_double()
+        self._ck(lib().rsb_get_null_quantisation(self._h, wq.ctypes.data_as(_i64p), C.byref(q), C.byref(S), C.byref(a), C.byref(b)))
+        return wq, q.value, S.value, a.value, b.value
 
     # ---- one alignment ------------------------------------------------------------------------
     def _msa(self, msa):
@@ -439,6 +458,40 @@ class Context:
         self._ck(lib().rsb_null_hist_pool(self._h, first_rep, nrep, stat, covclass, actype, _d(ap), tol, w, bmin, _d(mm)))
         return mm
 
+    def null_hist_multi(self, nulls, combos, w, covclass=C16, allowpair=None, tol=1e-6, bmin=-10.0, first_rep=None):
+        """Several (statistic, correction) combinations from one contraction per null (rsb_null_hist_multi).
+        combos: list of (stat, actype); w: one bin width per combination (<= 0: score range only).  nulls: uint8 [R][N][L] numpy /
+        torch CUDA tensor, or an int R with first_rep for pool entries.  Returns minmax [ncombo][R][2]."""
+        ap = None if allowpair is None else np.ascontiguousarray(allowpair, dtype=np.float64)
+        st = np.ascontiguousarray([c[0] for c in combos], dtype=np.int32)
+        ac = np.ascontiguousarray([c[1] for c in combos], dtype=np.int32)
+        ww = np.ascontiguousarray(w, dtype=np.float64)
+        assert len(ww) == len(combos)
+        if first_rep is not None:
+            R = int(nulls)
+            mm = np.empty((len(combos), R, 2))
+            self._ck(lib().rsb_null_hist_multi_pool(self._h, first_rep, R, len(combos), st.ctypes.data_as(_ip), ac.ctypes.data_as(_ip), covclass,
+                                                    _d(ap), tol, _d(ww), bmin, _d(mm)))
+            return mm
+        if isinstance(nulls, np.ndarray):
+            nulls = np.ascontiguousarray(nulls, dtype=np.uint8)
+        R = nulls.shape[0]
+        assert tuple(nulls.shape[1:]) == (self.N, self.L)
+        p, dev = _ptr(nulls)
+        mm = np.empty((len(combos), R, 2))
+        self._ck(lib().rsb_null_hist_multi(self._h, p, R, self.L, self.N * self.L, dev, len(combos), st.ctypes.data_as(_ip), ac.ctypes.data_as(_ip),
+                                           covclass, _d(ap), tol, _d(ww), bmin, _d(mm)))
+        return mm
+
+    def hist_read_multi(self, combo, nb):
+        bins = np.empty(nb, dtype=np.uint64)
+        n, imax = C.c_uint64(), C.c_int()
+        self._ck(lib().rsb_hist_read_multi(self._h, combo, bins.ctypes.data_as(_u64p), nb, C.byref(n), C.byref(imax)))
+        return bins, n.value, imax.value
+
+    def hist_reset_multi(self):
+        self._ck(lib().rsb_hist_reset_multi(self._h))
+
     def hist_reset(self):
         self._ck(lib().rsb_hist_reset(self._h))
 
@@ -510,7 +563,12 @@ class Context:
     def counters(self, reset=False):
         a, b, c = C.c_int64(), C.c_double(), C.c_int64()
         self._ck(lib().rsb_counters(self._h, C.byref(a), C.byref(b), C.byref(c), 1 if reset else 0))
-        return dict(launches=a.value, gram_ms=b.value, gram_launches=c.value)
+        out = dict(launches=a.value, gram_ms=b.value, gram_launches=c.value, geometry=[])
+        for which in range(3):                                       # contractions per operand geometry (input weights, unit weights, nulls' weights)
+            ms, n, S = C.c_double(), C.c_int64(), C.c_int()
+            self._ck(lib().rsb_counters_geometry(self._h, which, C.byref(ms), C.byref(n), C.byref(S)))
+            out["geometry"].append(dict(gram_ms=ms.value, gram_launches=n.value, slices=S.value))
+        return out
 
 
 def replicate_slots(nseq, alen, nnull, nslices=4, budget_bytes=24e9, sm_count=148):

@@ -40,6 +40,8 @@ cudaError_t rsb_launch_logtab(void *tab, cudaStream_t st);
 size_t rsb_logtab_bytes();
 cudaError_t rsb_launch_statistic(int stat, int cls, const long long *cnt, const double *pm, const void *logtab, int nrep, int L, int Lp, double scale,
                                  long long wtot, unsigned mask, double *cov, double *rowpart, double *colpart, double *mm, int sr, int sw, cudaStream_t st);
+cudaError_t rsb_launch_multi_statistic(int cls, const long long *cnt, const double *pm, const void *logtab, int nrep, int L, int Lp, double scale,
+                                       long long wtot, unsigned mask, double *const *cov6, int sr, int sw, cudaStream_t st);
 cudaError_t rsb_launch_raf(const long long *cnt, int nrep, int L, int Lp, int nseq, unsigned mask, int smooth, double *tmp, double *cov,
                            double *rowpart, double *colpart, double *mm, cudaStream_t st);
 cudaError_t rsb_launch_ccf(const double *nseff, const double *pm, int nrep, int L, int Lp, double *part, double *meanp, double *cov,
@@ -110,7 +112,8 @@ struct rsb_ctx {
 
   int N = 0, L = 0, Lp = 0, Kpad = 0, MA = 0, nIB = 0, Rcap = 0, Sreq = 0, Lcover = 0;
   size_t planeB_rows_cap = 0;
-  Geo geo[2];                         // [0] weighted, [1] unit weights (RAF/RAFS)
+  Geo geo[3];                         // [0] weighted, [1] unit weights (RAF/RAFS), [2] weighted with Snull digit slices: the null alignments
+  int Snull = 0;                      // digit slices of the null alignments' weights (0 = those of the input alignment), rsb_set_null_slices
   int cur_geo = 0;                    // geometry of the counts currently in d_cnt
   bool cur_rec = false;               // ... which hold per-pair G-test records instead of counts (record epilogue, gram_tcgen05.cu)
   bool fused_gt = true;               // nulls scored with GT x C16 use the record epilogue (RSCAPE_B200_FUSED_GT=0: counts + stat_kernel)
@@ -158,12 +161,18 @@ struct rsb_ctx {
   int Rpool = 0;
 
   unsigned long long hist_n = 0;
+  // several statistics per contraction (rsb_null_hist_multi): raw matrices [6][Rcap][L][Lp], one histogram / width / range per combination
+  double *d_covm = nullptr, *d_wm = nullptr, *d_minmaxm = nullptr; unsigned long long *d_histm = nullptr;
+  int multi_cap = 0; std::vector<unsigned long long> hist_n_m;
   int *d_m2p = nullptr; int mind = 1;                 // PDB positions of the columns + minimum distance: pairs kept out of the histograms
   unsigned long long pairs_in_hist = 0;               // pairs i<j that are not excluded by that rule
   long long launches = 0, gram_launches = 0;
   double gram_ms = 0.0;
   bool profile = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+  std::vector<int> pending_geo;                                   // geometry of each timed contraction
+  double gram_ms_geo[3] = { 0.0, 0.0, 0.0 }; long long gram_launches_geo[3] = { 0, 0, 0 };
+  double last_gram_ms_geo[3] = { 0.0, 0.0, 0.0 }; long long last_gram_launches_geo[3] = { 0, 0, 0 };   // as of the last rsb_counters call
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending_aux;   // statistics chain of the pipelined null loop
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending_stage; // its stage boundaries (after marginals, after statistic)
   double stage_ms[3] = { 0.0, 0.0, 0.0 };
@@ -219,7 +228,7 @@ void free_plan(rsb_ctx *c)
 {
   if (c->stream_gen) cudaStreamSynchronize(c->stream_gen);
   c->pool_ready.clear();
-  free_geo(c->geo[0]); free_geo(c->geo[1]);
+  free_geo(c->geo[0]); free_geo(c->geo[1]); free_geo(c->geo[2]);
   dfree(c->d_qscratch);
   dfree(c->d_res); dfree(c->d_planeA); dfree(c->d_planeB); dfree(c->d_cnt); dfree(c->d_nseff); dfree(c->d_pm); dfree(c->d_cov);
   dfree(c->d_mrow); dfree(c->d_mcol); dfree(c->d_tmp); dfree(c->d_rowpart); dfree(c->d_colpart); dfree(c->d_mm); dfree(c->d_scal); dfree(c->d_covx); dfree(c->d_minmax);
@@ -228,6 +237,7 @@ void free_plan(rsb_ctx *c)
   dfree(c->d_nseff_out); dfree(c->d_ngap_out); dfree(c->d_left); dfree(c->d_right); dfree(c->d_parent); dfree(c->d_order);
   dfree(c->d_level_start); dfree(c->d_perm); dfree(c->d_pcdf); dfree(c->d_root); dfree(c->d_gapmask); dfree(c->d_simscratch);
   dfree(c->d_m2p); c->mind = 1;
+  dfree(c->d_covm); dfree(c->d_wm); dfree(c->d_minmaxm); dfree(c->d_histm); c->multi_cap = 0; c->hist_n_m.clear();
   dfree(c->d_msa0); dfree(c->d_anc); dfree(c->d_shanc); dfree(c->d_pool); dfree(c->d_sets); dfree(c->d_genflag); dfree(c->d_ids); c->ids_cap = 0; dfree(c->d_pthr); c->sim_valid = false;
   c->Rpool = 0;
   c->have_tree = false;
@@ -392,6 +402,9 @@ int ensure_geo(rsb_ctx *ctx, int which)
   return 1;
 }
 
+// geometry that scores the null alignments: their own (coarser) fixed-point weights when rsb_set_null_slices asked for them
+int null_geo(rsb_ctx *ctx) { return (ctx->Snull > 0 && ctx->geo[2].ready && ctx->geo[2].S != ctx->geo[0].S) ? 2 : 0; }
+
 unsigned allow_mask(const double *allowpair)
 {
   // default WC + GU (src/R-scape.c:883-887)
@@ -432,7 +445,7 @@ int enqueue_pack(rsb_ctx *ctx, int which, int s0, int nrep, const uint8_t *src, 
 int enqueue_gram(rsb_ctx *ctx, int which, int s0, int nrep, cudaStream_t st, bool rec = false)
 {
   Geo &g = ctx->geo[which];
-  if (rec && (which != 0 || g.pair_clusters > 0)) { rsb_set_error(ctx, "internal: record epilogue not available here"); return 1; }
+  if (rec && (which == 1 || g.pair_clusters > 0)) { rsb_set_error(ctx, "internal: record epilogue not available here"); return 1; }
   if (g.ntiles > 0) {
     const long long work = (long long) g.ntiles * nrep;
     // with in-library collectives a few SMs stay free: the NCCL kernels cannot share an SM with the persistent contraction
@@ -442,8 +455,8 @@ int enqueue_gram(rsb_ctx *ctx, int which, int s0, int nrep, cudaStream_t st, boo
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (ctx->profile) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
     // the weighted geometry also emits the marginal partial sums of every tile (slot-indexed like the counts)
-    double *mrow = (which == 0) ? ctx->d_mrow : nullptr, *mcol = (which == 0) ? ctx->d_mcol : nullptr;
-    if (which == 0 && ((size_t) g.nJB * rsb_gram_mrow_blocks(0) * ctx->L * 4 > ctx->mrow_stride)) { rsb_set_error(ctx, "internal: marginal partial capacity"); return 1; }
+    double *mrow = (which != 1) ? ctx->d_mrow : nullptr, *mcol = (which != 1) ? ctx->d_mcol : nullptr;
+    if (which != 1 && ((size_t) g.nJB * rsb_gram_mrow_blocks(0) * ctx->L * 4 > ctx->mrow_stride)) { rsb_set_error(ctx, "internal: marginal partial capacity"); return 1; }
     if (g.pair_clusters > 0)
       RSB_CUDA_OK(rsb_launch_gram_i8_pair(g.S, ctx->tmA, g.tmBh, g.d_tiles2, g.ntiles2, s0, nrep, ctx->L, ctx->Lp, ctx->Kpad / RSB_KSTAGE,
                                           ctx->d_cnt, g.scale, mrow, mcol, g.nJB, ctx->nIB, ((unsigned long long) g.wtot >> 52) == 0, g.pair_clusters, st));
@@ -451,9 +464,10 @@ int enqueue_gram(rsb_ctx *ctx, int which, int s0, int nrep, cudaStream_t st, boo
       RSB_CUDA_OK(rsb_launch_gram_i8(g.S, ctx->tmA, g.tmB, g.d_tiles, g.ntiles, s0, nrep, ctx->L, ctx->Lp, ctx->Kpad / RSB_KSTAGE,
                                      ctx->d_cnt, g.scale, mrow, mcol, g.nJB, ctx->nIB, ((unsigned long long) g.wtot >> 52) == 0, grid,
                                      rec ? ctx->d_logtab : nullptr, st));
-    if (ctx->profile) { cudaEventRecord(e1, st); ctx->pending.push_back({ e0, e1 }); }
+    if (ctx->profile) { cudaEventRecord(e1, st); ctx->pending.push_back({ e0, e1 }); ctx->pending_geo.push_back(which); }
     ctx->launches++;
     ctx->gram_launches++;
+    ctx->gram_launches_geo[which]++;
   }
   ctx->cur_geo = which;
   ctx->cur_rec = rec;
@@ -470,7 +484,7 @@ int enqueue_counts(rsb_ctx *ctx, int which, int s0, int nrep, const uint8_t *src
 // may the nulls of this (statistic, class) be scored through the record epilogue?
 bool use_record(rsb_ctx *ctx, int stat, int covclass)
 {
-  return ctx->fused_gt && stat == RSB_GT && covclass == RSB_C16 && ctx->geo[0].pair_clusters == 0;
+  return ctx->fused_gt && stat == RSB_GT && covclass == RSB_C16 && ctx->geo[0].pair_clusters == 0 && ctx->geo[2].pair_clusters == 0;
 }
 
 int check_flags(rsb_ctx *ctx, const char *what)
@@ -553,7 +567,7 @@ int comm_reduce_minmax(rsb_ctx *ctx, double *minmax, int n, cudaStream_t st)
 // marginals (corr_Marginals) for slots [s0, s0+nrep) on stream st.  phase 1 = partial sums -> msum, 2 = normalise, 3 = both
 int enqueue_marginals(rsb_ctx *ctx, int s0, int nrep, double tol, cudaStream_t st, int phase = 3)
 {
-  Geo &g = ctx->geo[0];
+  Geo &g = ctx->geo[ctx->cur_geo];                                  // (0 or 2: the weighted geometry the contraction just ran with)
   SlotPtrs p = slot_ptrs(ctx, s0);
   // partials are addressed [r][block][L][4] with r the absolute slot, as the gram kernel wrote them
   const int E = rsb_gram_mrow_blocks(g.pair_clusters > 0);
@@ -586,7 +600,7 @@ int enqueue_statistic(rsb_ctx *ctx, int s0, int nrep, int stat, int covclass, un
       ctx->launches += (stat == RSB_RAFS) ? 3 : 2;
     } else if (stat == RSB_CCF) {
       if (ctx->shard_world > 1) { rsb_set_error(ctx, "CCF is not available with a sharded pair grid"); return 1; }
-      RSB_CUDA_OK(rsb_launch_nseff(p.cnt, nrep, ctx->L, ctx->Lp, ctx->geo[0].scale, p.nseff, st));
+      RSB_CUDA_OK(rsb_launch_nseff(p.cnt, nrep, ctx->L, ctx->Lp, g.scale, p.nseff, st));
       RSB_CUDA_OK(rsb_launch_ccf(p.nseff, p.pm, nrep, ctx->L, ctx->Lp, p.tmp, p.meanp, p.cov, rowpart, colpart, p.mm, st));
       ctx->launches += 5;
     } else if (ctx->cur_rec) {
@@ -637,10 +651,10 @@ unsigned long long owned_pairs_in_hist(rsb_ctx *ctx)
 }
 
 // serial pipeline on the main stream, slots [0,nrep): counts -> (marginals) -> statistic
-int run_pipeline(rsb_ctx *ctx, int nrep, int stat, int covclass, unsigned mask, double tol)
+int run_pipeline(rsb_ctx *ctx, int nrep, int stat, int covclass, unsigned mask, double tol, int weighted_geo = 0)
 {
   const bool raf = (stat == RSB_RAF || stat == RSB_RAFS);
-  if (enqueue_counts(ctx, raf ? 1 : 0, 0, nrep, ctx->d_res, ctx->stream, use_record(ctx, stat, covclass))) return 1;
+  if (enqueue_counts(ctx, raf ? 1 : weighted_geo, 0, nrep, ctx->d_res, ctx->stream, use_record(ctx, stat, covclass))) return 1;
   if (!raf && enqueue_marginals(ctx, 0, nrep, tol, ctx->stream)) return 1;
   return enqueue_statistic(ctx, 0, nrep, stat, covclass, mask, ctx->stream);
 }
@@ -763,6 +777,7 @@ void rsb_destroy(rsb_ctx *ctx)
 int rsb_configure(rsb_ctx *ctx, int nseq, int alen, int max_replicates, int nslices)
 {
   if (nseq < 1 || alen < 1 || max_replicates < 1 || nslices < 0 || nslices > RSB_MAX_SLICES) { rsb_set_error(ctx, "bad configuration"); return 1; }
+  if (nslices && ctx->Snull > nslices) { rsb_set_error(ctx, "the nulls are set to %d weight slices, more than the %d of the input alignment", ctx->Snull, nslices); return 1; }
   RSB_CUDA_OK(cudaSetDevice(ctx->device));
   RSB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
   free_plan(ctx);
@@ -774,7 +789,7 @@ int rsb_configure(rsb_ctx *ctx, int nseq, int alen, int max_replicates, int nsli
   // planeB must hold the widest geometry (any S in 1..6); rows = nJB * NT
   size_t rows_cap = 0; int lcover = ctx->nIB * RSB_ICOLS, njb_cap = 0;
   for (int S = 1; S <= RSB_MAX_SLICES; S++) {
-    if (nslices && S != nslices && S != 1) continue;
+    if (nslices && S > nslices) continue;                          // (fewer slices: the unit-weight tables, the nulls' own weights)
     const int CJ = rsb_cj_for(S), nJB = (alen + CJ - 1) / CJ;
     rows_cap = std::max(rows_cap, (size_t) nJB * 4 * S * CJ);
     njb_cap  = std::max(njb_cap, nJB);
@@ -837,7 +852,39 @@ int rsb_set_weights(rsb_ctx *ctx, const double *wgt)
   }
   Geo &g = ctx->geo[0];
   if (g.S != S || !g.d_tiles) { if (build_geo(ctx, g, S)) return 1; }
-  return quantise(ctx, g, ctx->wgt, false);
+  if (quantise(ctx, g, ctx->wgt, false)) return 1;
+  // the null alignments' own, coarser representation of the same weights (rsb_set_null_slices)
+  Geo &gn = ctx->geo[2];
+  gn.ready = false;
+  if (ctx->Snull > 0 && ctx->Snull < S) {
+    if (gn.S != ctx->Snull || !gn.d_tiles) { if (build_geo(ctx, gn, ctx->Snull)) return 1; }
+    if (quantise(ctx, gn, ctx->wgt, false)) return 1;
+  }
+  return 0;
+}
+
+/* Mixed precision (north_star: "a stated bound (split path)"): the null alignments are contracted with nslices base-256 digits
+ * of the weights instead of the input alignment's.  0 = the same weights everywhere (default).  Takes effect at the next
+ * rsb_set_weights. */
+int rsb_set_null_slices(rsb_ctx *ctx, int nslices)
+{
+  if (nslices < 0 || nslices > RSB_MAX_SLICES) { rsb_set_error(ctx, "bad slice count %d", nslices); return 1; }
+  if (ctx->N && ctx->Sreq && nslices > ctx->Sreq) { rsb_set_error(ctx, "the nulls cannot carry more weight slices (%d) than the input alignment (%d)", nslices, ctx->Sreq); return 1; }
+  ctx->Snull = nslices;
+  ctx->geo[2].ready = false;
+  return 0;
+}
+
+int rsb_get_null_quantisation(rsb_ctx *ctx, int64_t *wq, int *q, int *nslices, double *max_abs_err, double *effective_bits)
+{
+  if (!ctx->geo[0].ready) { rsb_set_error(ctx, "rsb_set_weights has not been called"); return 1; }
+  Geo &g = ctx->geo[null_geo(ctx)];
+  if (wq) for (int s = 0; s < ctx->N; s++) wq[s] = g.wq[s];
+  if (q) *q = g.q;
+  if (nslices) *nslices = g.S;
+  if (max_abs_err) *max_abs_err = g.qerr_abs;
+  if (effective_bits) *effective_bits = (g.qerr_abs > 0.0) ? std::log2(g.maxw / g.qerr_abs) : 64.0;
+  return 0;
 }
 
 int rsb_get_quantisation(rsb_ctx *ctx, int64_t *wq, int *q, int *nslices)
@@ -1011,7 +1058,7 @@ int rsb_null_width(rsb_ctx *ctx, const uint8_t *null0, int64_t row_stride, int o
   if (resolve_stat(ctx, stat, covclass)) return 1;
   if (ctx->shard_world > 1 && !grid_comm(ctx)) { rsb_set_error(ctx, "calculate_width_histo on a sharded pair grid needs a communicator (rsb_comm_init)"); return 1; }
   if (null0 && upload_msa(ctx, null0, row_stride, 0, 1, 0, on_device, ctx->stream)) return 1;
-  if (run_pipeline(ctx, 1, stat, covclass, allow_mask(allowpair), tol)) return 1;
+  if (run_pipeline(ctx, 1, stat, covclass, allow_mask(allowpair), tol, null_geo(ctx))) return 1;     // a null: scored as the nulls are
   if (enqueue_correct(ctx, 0, 1, actype, 0, bmin, ctx->stream)) return 1;
   RSB_CUDA_OK(rsb_launch_width(ctx->d_minmax, w_old, bmin, hpts, tol, ctx->d_w, ctx->stream));
   ctx->launches++;
@@ -1038,6 +1085,7 @@ static int null_hist_pipelined(rsb_ctx *ctx, const uint8_t *nulls, int nrep, int
                                double *minmax, int pool_first = -1)
 {
   const bool raf = (stat == RSB_RAF || stat == RSB_RAFS);
+  const int  wgeo = raf ? 1 : null_geo(ctx);
   // GT x C16: the contraction's epilogue leaves per-pair records and the statistic finishes with an HBM-bound kernel on the
   // aux stream -- nothing but contractions on the main stream
   const bool rec = !raf && use_record(ctx, stat, covclass);
@@ -1121,13 +1169,13 @@ static int null_hist_pipelined(rsb_ctx *ctx, const uint8_t *nulls, int nrep, int
       if (upload_msa(ctx, nulls + (size_t) r0 * rep_stride, row_stride, rep_stride, n, s0, on_device, st_copy)) return 1;
       src = ctx->d_res + (size_t) s0 * repbytes;
     }
-    if (enqueue_pack(ctx, raf ? 1 : 0, s0, n, src, st_copy)) return 1;                   // HBM-bound transpose: hides under the previous gram
+    if (enqueue_pack(ctx, wgeo, s0, n, src, st_copy)) return 1;                   // HBM-bound transpose: hides under the previous gram
     RSB_CUDA_OK(cudaEventRecord(ctx->ev_up[g], st_copy));
     RSB_CUDA_OK(cudaStreamWaitEvent(sm, ctx->ev_up[g], 0));
     // (the counts and marginal partials of this group were consumed by S(c - G), earlier on this stream; with the record
     // epilogue their consumers run on the aux stream)
     if (rec && used[g]) RSB_CUDA_OK(cudaStreamWaitEvent(sm, ctx->ev_stats[g], 0));
-    if (enqueue_gram(ctx, raf ? 1 : 0, s0, n, sm, rec)) return 1;
+    if (enqueue_gram(ctx, wgeo, s0, n, sm, rec)) return 1;
     RSB_CUDA_OK(cudaEventRecord(ctx->ev_counts[g], sm));
 
     RSB_CUDA_OK(cudaStreamWaitEvent(aux_of(g), ctx->ev_counts[g], 0));
@@ -1141,6 +1189,180 @@ static int null_hist_pipelined(rsb_ctx *ctx, const uint8_t *nulls, int nrep, int
   for (int g = 0; g < G; g++) if (used[g]) RSB_CUDA_OK(cudaStreamWaitEvent(sm, ctx->ev_stats[g], 0));
   RSB_CUDA_OK(cudaEventRecord(ctx->ev_exit, sm));                      // back to the caller's stream
   RSB_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->ev_exit, 0));
+  return 0;
+}
+
+
+// ---------------------------------------------------------------------------------------------- several statistics per contraction
+// BASELINE config 5 (statistic sweep): cov_Calculate (src/covariation.c:100-258) runs corr_Probs once per alignment and then ONE
+// corr_Calculate*; a sweep over statistics and corrections repeats the whole scan.  Here a null is contracted once, every
+// requested statistic is evaluated from the same count planes in one pass (multi_stat_kernel), and each (statistic, correction)
+// combination gets its own reductions, correction and histogram on the aux stream, beside the next contraction.
+static int stat_slot(int stat)
+{
+  switch (stat) { case RSB_CHI: return 0; case RSB_OMES: return 1; case RSB_GT: return 2; case RSB_MI: return 3; case RSB_MIr: return 4; case RSB_MIg: return 5; }
+  return -1;
+}
+
+static int multi_reserve(rsb_ctx *ctx, int ncombo)
+{
+  const size_t L = ctx->L, Lp = ctx->Lp;
+  if (!ctx->d_covm) RSB_CUDA_OK(cudaMalloc(&ctx->d_covm, sizeof(double) * 6 * (size_t) ctx->Rcap * L * Lp));
+  if (ncombo > ctx->multi_cap) {
+    dfree(ctx->d_wm); dfree(ctx->d_minmaxm); dfree(ctx->d_histm);
+    RSB_CUDA_OK(cudaMalloc(&ctx->d_wm, sizeof(double) * ncombo));
+    RSB_CUDA_OK(cudaMalloc(&ctx->d_minmaxm, sizeof(double) * 2 * (size_t) ncombo * ctx->Rcap));
+    RSB_CUDA_OK(cudaMalloc(&ctx->d_histm, sizeof(unsigned long long) * (size_t) ncombo * HIST_BINS));
+    RSB_CUDA_OK(cudaMemsetAsync(ctx->d_histm, 0, sizeof(unsigned long long) * (size_t) ncombo * HIST_BINS, ctx->stream));
+    ctx->multi_cap = ncombo;
+    ctx->hist_n_m.assign(ncombo, 0);
+  }
+  return 0;
+}
+
+static int null_hist_multi(rsb_ctx *ctx, const uint8_t *nulls, int nrep, int64_t row_stride, int64_t rep_stride, int on_device, int pool_first,
+                           int ncombo, const int *stat, const int *actype, int covclass, unsigned mask, double tol, const double *w, double bmin,
+                           double *minmax)
+{
+  if (ncombo < 1 || ncombo > 64) { rsb_set_error(ctx, "bad number of (statistic, correction) combinations %d", ncombo); return 1; }
+  if (ctx->shard_world > 1) { rsb_set_error(ctx, "rsb_null_hist_multi is not offered on a sharded pair grid"); return 1; }
+  if (covclass != RSB_C16 && covclass != RSB_C2 && covclass != RSB_CWC) { rsb_set_error(ctx, "covclass must be resolved by the caller"); return 1; }
+  bool want[6] = { false, false, false, false, false, false };
+  for (int k = 0; k < ncombo; k++) {
+    const int sl = stat_slot(stat[k]);
+    if (sl < 0) { rsb_set_error(ctx, "statistic %d is not computed from the weighted counts (RAF/RAFS/CCF: use rsb_null_hist)", stat[k]); return 1; }
+    if (resolve_stat(ctx, stat[k], covclass)) return 1;
+    if (actype[k] != RSB_APC && actype[k] != RSB_ASC && actype[k] != RSB_NOCORR) { rsb_set_error(ctx, "wrong correction type %d", actype[k]); return 1; }
+    want[sl] = true;
+  }
+  if (multi_reserve(ctx, ncombo)) return 1;
+  const int  wgeo = null_geo(ctx);
+  Geo &g = ctx->geo[wgeo];
+  if (!g.ready) { rsb_set_error(ctx, "rsb_set_weights has not been called"); return 1; }
+  const bool in_place = (on_device && row_stride == ctx->L && rep_stride == (int64_t) ctx->N * ctx->L);
+  const int  G = (ctx->Rcap >= 2) ? 2 : 1;
+  const int  chunk = std::max(1, ctx->Rcap / G);
+  const size_t repbytes = (size_t) ctx->N * ctx->L, LL = (size_t) ctx->L * ctx->Lp;
+  cudaStream_t sm = ctx->stream_hi, st_copy = ctx->stream_copy;
+  auto aux_of = [&](int gi) -> cudaStream_t { return (gi & 1) ? ctx->stream_aux2 : ctx->stream_aux; };
+  const size_t need = (size_t) nrep * ncombo;
+  if (ctx->h_mm_cap < need) {
+    if (ctx->h_mm) cudaFreeHost(ctx->h_mm);
+    ctx->h_mm = nullptr; ctx->h_mm_cap = 0;
+    RSB_CUDA_OK(cudaMallocHost(&ctx->h_mm, sizeof(double) * 2 * need));
+    ctx->h_mm_cap = need;
+  }
+  RSB_CUDA_OK(cudaEventRecord(ctx->ev_entry, ctx->stream));
+  RSB_CUDA_OK(cudaStreamWaitEvent(sm, ctx->ev_entry, 0));
+  RSB_CUDA_OK(cudaMemcpyAsync(ctx->d_wm, w, sizeof(double) * ncombo, cudaMemcpyHostToDevice, sm));
+  RSB_CUDA_OK(cudaEventRecord(ctx->ev_entry, sm));
+  RSB_CUDA_OK(cudaStreamWaitEvent(ctx->stream_aux, ctx->ev_entry, 0));
+  RSB_CUDA_OK(cudaStreamWaitEvent(ctx->stream_aux2, ctx->ev_entry, 0));
+  RSB_CUDA_OK(cudaStreamWaitEvent(st_copy, ctx->ev_entry, 0));
+  bool used[2] = { false, false };
+  int nJT, nIT; rsb_stat_grid(ctx->L, &nJT, &nIT);
+
+  // S(pc): all statistics of chunk pc in one pass on the main stream (FP64: alone between two contractions), then per statistic
+  // the reductions and per combination the correction + histogram on the aux stream
+  auto tail = [&](int pc, int pr0) -> int {
+    const int pg = pc % G, ps0 = pg * chunk, pn = std::min(chunk, nrep - pr0);
+    cudaStream_t st_aux = aux_of(pg);
+    SlotPtrs p = slot_ptrs(ctx, ps0);
+    double *cov6[6];
+    for (int sl = 0; sl < 6; sl++) cov6[sl] = want[sl] ? ctx->d_covm + ((size_t) sl * ctx->Rcap + ps0) * LL : nullptr;
+    RSB_CUDA_OK(cudaStreamWaitEvent(sm, ctx->ev_marg[pg], 0));
+    if (pc >= G) RSB_CUDA_OK(cudaStreamWaitEvent(sm, ctx->ev_stats[pg], 0));   // the group's matrices have been consumed
+    RSB_CUDA_OK(rsb_launch_multi_statistic(covclass, p.cnt, p.pm, ctx->d_logtab, pn, ctx->L, ctx->Lp, g.scale, g.wtot, mask, cov6, 0, 1, sm));
+    ctx->launches++;
+    RSB_CUDA_OK(cudaEventRecord(ctx->ev_statk[pg], sm));
+    RSB_CUDA_OK(cudaStreamWaitEvent(st_aux, ctx->ev_statk[pg], 0));
+    double *rowpart = ctx->d_rowpart + (size_t) ps0 * nJT * ctx->L, *colpart = ctx->d_colpart + (size_t) ps0 * nIT * ctx->L;
+    for (int sl = 0; sl < 6; sl++) {
+      if (!want[sl]) continue;
+      RSB_CUDA_OK(rsb_launch_reduce_cov(cov6[sl], pn, ctx->L, ctx->Lp, rowpart, colpart, p.mm, st_aux));
+      RSB_CUDA_OK(rsb_launch_correct_final(rowpart, colpart, p.mm, pn, ctx->L, p.covx, p.scal, p.blocksum, p.covsum, 3, st_aux));
+      ctx->launches += 4;
+      for (int k = 0; k < ncombo; k++) {
+        if (stat_slot(stat[k]) != sl) continue;
+        double *mmk = ctx->d_minmaxm + ((size_t) k * ctx->Rcap + ps0) * 2;
+        RSB_CUDA_OK(rsb_launch_correct_hist(cov6[sl], p.covx, p.scal, pn, ctx->L, ctx->Lp, actype[k], (w[k] > 0.0) ? 2 : 0, bmin, ctx->d_wm + k,
+                                            ctx->d_histm + (size_t) k * HIST_BINS, HIST_BINS, p.mm, mmk, ctx->d_flags, 0, 1, ctx->d_m2p, ctx->mind, st_aux));
+        ctx->launches += 2;
+        if (minmax) RSB_CUDA_OK(cudaMemcpyAsync(ctx->h_mm + 2 * ((size_t) k * nrep + pr0), mmk, sizeof(double) * 2 * pn, cudaMemcpyDeviceToHost, st_aux));
+        if (w[k] > 0.0) ctx->hist_n_m[k] += (unsigned long long) pn * ctx->pairs_in_hist;
+      }
+    }
+    RSB_CUDA_OK(cudaEventRecord(ctx->ev_stats[pg], st_aux));
+    return 0;
+  };
+
+  int c = 0;
+  for (int r0 = 0; r0 < nrep; r0 += chunk, c++) {
+    const int gi = c % G, s0 = gi * chunk, n = std::min(chunk, nrep - r0);
+    const uint8_t *src;
+    if (used[gi]) RSB_CUDA_OK(cudaStreamWaitEvent(st_copy, ctx->ev_counts[gi], 0));
+    if (pool_first >= 0 && pool_wait(ctx, pool_first + r0, n, st_copy)) return 1;
+    if (in_place) src = nulls + (size_t) r0 * repbytes;
+    else {
+      if (upload_msa(ctx, nulls + (size_t) r0 * rep_stride, row_stride, rep_stride, n, s0, on_device, st_copy)) return 1;
+      src = ctx->d_res + (size_t) s0 * repbytes;
+    }
+    if (enqueue_pack(ctx, wgeo, s0, n, src, st_copy)) return 1;
+    RSB_CUDA_OK(cudaEventRecord(ctx->ev_up[gi], st_copy));
+    RSB_CUDA_OK(cudaStreamWaitEvent(sm, ctx->ev_up[gi], 0));
+    if (enqueue_gram(ctx, wgeo, s0, n, sm, false)) return 1;           // (its counts were consumed by S(c - G), earlier on this stream)
+    RSB_CUDA_OK(cudaEventRecord(ctx->ev_counts[gi], sm));
+    RSB_CUDA_OK(cudaStreamWaitEvent(aux_of(gi), ctx->ev_counts[gi], 0));
+    if (enqueue_marginals(ctx, s0, n, tol, aux_of(gi))) return 1;
+    RSB_CUDA_OK(cudaEventRecord(ctx->ev_marg[gi], aux_of(gi)));
+    used[gi] = true;
+    if (G == 1) { if (tail(c, r0)) return 1; }
+    else if (c >= 1) { if (tail(c - 1, r0 - chunk)) return 1; }
+  }
+  if (G > 1 && c >= 1) { if (tail(c - 1, (c - 1) * chunk)) return 1; }
+  for (int gi = 0; gi < G; gi++) if (used[gi]) RSB_CUDA_OK(cudaStreamWaitEvent(sm, ctx->ev_stats[gi], 0));
+  RSB_CUDA_OK(cudaEventRecord(ctx->ev_exit, sm));
+  RSB_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->ev_exit, 0));
+  if (check_flags(ctx, "null_rscape")) return 1;
+  if (minmax) memcpy(minmax, ctx->h_mm, sizeof(double) * 2 * need);
+  return 0;
+}
+
+int rsb_null_hist_multi(rsb_ctx *ctx, const uint8_t *nulls, int nrep, int64_t row_stride, int64_t rep_stride, int on_device, int ncombo,
+                        const int *stat, const int *actype, int covclass, const double *allowpair, double tol, const double *w, double bmin,
+                        double *minmax)
+{
+  RSB_CUDA_OK(cudaSetDevice(ctx->device));
+  return null_hist_multi(ctx, nulls, nrep, row_stride, rep_stride, on_device, -1, ncombo, stat, actype, covclass, allow_mask(allowpair), tol, w, bmin, minmax);
+}
+
+int rsb_null_hist_multi_pool(rsb_ctx *ctx, int first_rep, int nrep, int ncombo, const int *stat, const int *actype, int covclass,
+                             const double *allowpair, double tol, const double *w, double bmin, double *minmax)
+{
+  RSB_CUDA_OK(cudaSetDevice(ctx->device));
+  if (pool_range_ok(ctx, first_rep, nrep)) return 1;
+  const size_t rb = (size_t) ctx->N * ctx->L;
+  return null_hist_multi(ctx, ctx->d_pool + (size_t) first_rep * rb, nrep, ctx->L, (int64_t) rb, 1, first_rep, ncombo, stat, actype, covclass,
+                         allow_mask(allowpair), tol, w, bmin, minmax);
+}
+
+int rsb_hist_read_multi(rsb_ctx *ctx, int combo, uint64_t *bins, int nb_cap, uint64_t *n_out, int *imax_out)
+{
+  RSB_CUDA_OK(cudaSetDevice(ctx->device));
+  if (combo < 0 || combo >= ctx->multi_cap) { rsb_set_error(ctx, "combination %d out of range (%d histograms)", combo, ctx->multi_cap); return 1; }
+  const int nb = std::min(nb_cap, HIST_BINS);
+  RSB_CUDA_OK(cudaMemcpyAsync(bins, ctx->d_histm + (size_t) combo * HIST_BINS, sizeof(uint64_t) * nb, cudaMemcpyDeviceToHost, ctx->stream));
+  RSB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  if (n_out) *n_out = ctx->hist_n_m[combo];
+  if (imax_out) { int im = -1; for (int b = nb - 1; b >= 0; b--) if (bins[b]) { im = b; break; } *imax_out = im; }
+  return 0;
+}
+
+int rsb_hist_reset_multi(rsb_ctx *ctx)
+{
+  RSB_CUDA_OK(cudaSetDevice(ctx->device));
+  if (ctx->d_histm) RSB_CUDA_OK(cudaMemsetAsync(ctx->d_histm, 0, sizeof(unsigned long long) * (size_t) ctx->multi_cap * HIST_BINS, ctx->stream));
+  std::fill(ctx->hist_n_m.begin(), ctx->hist_n_m.end(), 0ULL);
   return 0;
 }
 
@@ -1187,8 +1409,8 @@ int rsb_set_shard(rsb_ctx *ctx, int rank, int world)
   RSB_CUDA_OK(cudaSetDevice(ctx->device));
   RSB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
   ctx->shard_rank = rank; ctx->shard_world = world;
-  free_geo(ctx->geo[0]); free_geo(ctx->geo[1]);          // tile lists depend on the shard: rsb_set_weights rebuilds them
-  ctx->geo[0].S = 0; ctx->geo[1].S = 0;
+  free_geo(ctx->geo[0]); free_geo(ctx->geo[1]); free_geo(ctx->geo[2]);          // tile lists depend on the shard: rsb_set_weights rebuilds them
+  ctx->geo[0].S = 0; ctx->geo[1].S = 0; ctx->geo[2].S = 0;
   return 0;
 }
 
@@ -1497,9 +1719,9 @@ int rsb_hist_exchange(rsb_ctx *ctx, void *device_buf, int nb, int to_library)
 int rsb_last_nseff(rsb_ctx *ctx, double *nseff, double *ngap)
 {
   RSB_CUDA_OK(cudaSetDevice(ctx->device));
-  Geo &g = ctx->geo[0];
+  if (ctx->cur_geo == 1) { rsb_set_error(ctx, "no weighted counts resident"); return 1; }
+  Geo &g = ctx->geo[ctx->cur_geo];
   const size_t L = ctx->L;
-  if (ctx->cur_geo != 0) { rsb_set_error(ctx, "no weighted counts resident"); return 1; }
   if (!ctx->d_pp_out) {
     RSB_CUDA_OK(cudaMalloc(&ctx->d_pp_out, L * L * 16 * sizeof(double)));
     RSB_CUDA_OK(cudaMalloc(&ctx->d_nseff_out, L * L * sizeof(double)));
@@ -2005,6 +2227,17 @@ int rsb_sharded_scan(rsb_ctx *ctx, const uint8_t *msa, int64_t row_stride, int o
 // ---------------------------------------------------------------------------------------------- instrumentation
 int rsb_profile_gram(rsb_ctx *ctx, int enable) { ctx->profile = enable != 0; return 0; }
 
+/* contraction launches and their summed CUDA-event time per operand geometry, as of the last rsb_counters call (before its reset):
+ * which = 0 input-alignment weights, 1 unit weights (RAF tables, substitution counts), 2 the nulls' own weights (rsb_set_null_slices) */
+int rsb_counters_geometry(rsb_ctx *ctx, int which, double *gram_ms, int64_t *gram_launches, int *nslices)
+{
+  if (which < 0 || which > 2) { rsb_set_error(ctx, "geometry %d out of range", which); return 1; }
+  if (gram_ms) *gram_ms = ctx->last_gram_ms_geo[which];
+  if (gram_launches) *gram_launches = ctx->last_gram_launches_geo[which];
+  if (nslices) *nslices = ctx->geo[which].S;
+  return 0;
+}
+
 #ifdef RSB_BLOCKTRACE
 extern "C" void rsb_trace_set_stats(unsigned long long *buf);
 extern "C" void rsb_trace_set_gram(unsigned long long *buf);
@@ -2034,12 +2267,13 @@ int rsb_counters(rsb_ctx *ctx, int64_t *launches, double *gram_ms, int64_t *gram
   RSB_CUDA_OK(cudaSetDevice(ctx->device));
   if (!ctx->pending.empty()) {
     RSB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
-    for (auto &p : ctx->pending) {
+    for (size_t k = 0; k < ctx->pending.size(); k++) {
+      auto &p = ctx->pending[k];
       float ms = 0.f;
-      if (cudaEventElapsedTime(&ms, p.first, p.second) == cudaSuccess) ctx->gram_ms += ms;
+      if (cudaEventElapsedTime(&ms, p.first, p.second) == cudaSuccess) { ctx->gram_ms += ms; ctx->gram_ms_geo[ctx->pending_geo[k]] += ms; }
       cudaEventDestroy(p.first); cudaEventDestroy(p.second);
     }
-    ctx->pending.clear();
+    ctx->pending.clear(); ctx->pending_geo.clear();
   }
   if (!ctx->pending_aux.empty()) {
     RSB_CUDA_OK(cudaStreamSynchronize(ctx->stream_aux));
@@ -2064,7 +2298,9 @@ int rsb_counters(rsb_ctx *ctx, int64_t *launches, double *gram_ms, int64_t *gram
             ctx->gram_launches ? ctx->gram_ms / ctx->gram_launches : 0.0, ctx->gram_launches, ctx->aux_ms / na, ctx->aux_chains,
             ctx->stage_ms[0] / na, ctx->stage_ms[1] / na, ctx->stage_ms[2] / na);
   }
-  if (reset) { ctx->launches = 0; ctx->gram_ms = 0.0; ctx->gram_launches = 0; ctx->aux_ms = 0.0; ctx->aux_chains = 0; ctx->stage_ms[0] = ctx->stage_ms[1] = ctx->stage_ms[2] = 0.0; }
+  for (int k = 0; k < 3; k++) { ctx->last_gram_ms_geo[k] = ctx->gram_ms_geo[k]; ctx->last_gram_launches_geo[k] = ctx->gram_launches_geo[k]; }
+  if (reset) { for (int k = 0; k < 3; k++) { ctx->gram_ms_geo[k] = 0.0; ctx->gram_launches_geo[k] = 0; }
+               ctx->launches = 0; ctx->gram_ms = 0.0; ctx->gram_launches = 0; ctx->aux_ms = 0.0; ctx->aux_chains = 0; ctx->stage_ms[0] = ctx->stage_ms[1] = ctx->stage_ms[2] = 0.0; }
   return 0;
 }
 

@@ -96,6 +96,12 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
 //     record planes  0: A   1: N2   2..4: U_0..U_2   5..7: V_0..V_2        (double [8][L][Lp], i < j; aliases the count planes)
 // The 17 logs per pair -- the FP64 work that needed a serial window of its own as a separate kernel -- are spread over the
 // 4 lanes that hold the pair's 16 cells and run here under the MMAs of the next tile.
+// timing experiments only (tools/build_variant.sh): parts of the record epilogue switched off -- results are then wrong
+#ifdef RSB_EXP_NOLOG
+#define GLOG(x) (x)
+#else
+#define GLOG(x) fast_log<false>((x), ltab)
+#endif
 template <int S, bool REC>
 __device__ __forceinline__ double gram_epilogue_tile(uint32_t trow, int jb, int i, int a, int lane, int ew, int ib, int r, int L, int Lp,
                                                      long long *__restrict__ base, size_t plane, double scale, bool part,
@@ -163,10 +169,10 @@ __device__ __forceinline__ double gram_epilogue_tile(uint32_t trow, int jb, int 
         const bool     use = (u ? ok1 : ok0) && ((nz >> (lane & ~3)) & 0xFu) != 0u;
         if (REC) {
           // sum x log x over the pair's 16 cells: 4 logs per lane (x >= 1e-10 and T >= 1.6e-9 are positive normals: no clamp)
-          double sl = x[u][0] * fast_log<false>(x[u][0], ltab);
-          sl = fma(x[u][1], fast_log<false>(x[u][1], ltab), sl);
-          double s2 = x[u][2] * fast_log<false>(x[u][2], ltab);
-          s2 = fma(x[u][3], fast_log<false>(x[u][3], ltab), s2);
+          double sl = x[u][0] * GLOG(x[u][0]);
+          sl = fma(x[u][1], GLOG(x[u][1]), sl);
+          double s2 = x[u][2] * GLOG(x[u][2]);
+          s2 = fma(x[u][3], GLOG(x[u][3]), s2);
           sl += s2;
           sl += __shfl_xor_sync(0xffffffffu, sl, 1);
           sl += __shfl_xor_sync(0xffffffffu, sl, 2);
@@ -192,7 +198,7 @@ __device__ __forceinline__ double gram_epilogue_tile(uint32_t trow, int jb, int 
           const double n2   = 2.0 * (ne * scale);
           const double invT = 1.0 / sum;
           const double coef = n2 * invT;
-          rA[u] = fma(coef, sl, -n2 * fast_log<false>(sum, ltab));
+          rA[u] = fma(coef, sl, -n2 * GLOG(sum));
           rU[u] = (a < 3) ? coef * rs : n2;
           rV[u] = coef * yb;
           const double inv = use ? invT : 0.0;
@@ -206,7 +212,11 @@ __device__ __forceinline__ double gram_epilogue_tile(uint32_t trow, int jb, int 
           for (int b = 0; b < 4; b++) x[u][b] *= inv;
         }
       }
+#ifdef RSB_EXP_NORECSTORE
+      if (REC && rA[0] + rU[0] + rV[0] + rA[1] + rU[1] + rV[1] == -1.2345) {
+#else
       if (REC) {
+#endif
         if (ok0 && ok1) {
           *reinterpret_cast<double2 *>(pU + j0) = make_double2(rU[0], rU[1]);
           if (a < 3)  *reinterpret_cast<double2 *>(pV + j0) = make_double2(rV[0], rV[1]);
@@ -216,6 +226,7 @@ __device__ __forceinline__ double gram_epilogue_tile(uint32_t trow, int jb, int 
           if (ok1) { pU[j0 + 1] = rU[1]; if (a < 3) pV[j0 + 1] = rV[1]; if (a == 0) recrow[j0 + 1] = rA[1]; }
         }
       }
+#ifndef RSB_EXP_NOCOLPART
       // column partials: 8 values (u, b) summed over the warp's 32 lanes by a halving butterfly -- after the three
       // halving steps a lane keeps (u, b) = (bit 4, bits 3:2 of its lane id), then two full steps sum over a
       const bool h4 = lane & 16, h3 = lane & 8, h2 = lane & 4;
@@ -239,6 +250,7 @@ __device__ __forceinline__ double gram_epilogue_tile(uint32_t trow, int jb, int 
       const int jw = j0 + (h4 ? 1 : 0);
       if ((lane & 3) == 0 && jw < L)
         mcol[(((size_t) r * 4 * nIB + (size_t) ib * 4 + ew) * L + jw) * 4 + ((h3 ? 2 : 0) + (h2 ? 1 : 0))] = v1;
+#endif
     }
   }
   return racc;
@@ -333,9 +345,11 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
           const uint32_t sA    = smem_base + stage * STAGE_BYTES;
           const uint64_t adesc = smem_desc_sw128(sA);
           const uint64_t bdesc = smem_desc_sw128(sA + A_BYTES);
+#ifndef RSB_EXP_NOMMA
           #pragma unroll
           for (int k = 0; k < RSB_KSTAGE / 32; k++)                // UMMA K = 32 bytes: +32 B = +2 in the address field
             umma_i8(d_tmem, adesc + 2u * k, bdesc + 2u * k, IDESC, (uint32_t) ((ks | k) != 0));
+#endif
           umma_commit(empty_bar(stage));                           // frees the smem slot when these MMAs retire
           if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
         }
@@ -363,8 +377,13 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t) (ew * 32) << 16) + (uint32_t) acc * 256u;
 
+#ifdef RSB_EXP_NOEPI
+      const double racc = 0.0;
+      if (mrow != nullptr && i < L && trow == 0xffffffffu) mrow[(size_t) 0] = 0.0;
+#else
       const double racc = gram_epilogue_tile<S, REC>(trow, t.y, i, a, lane, ew, t.x, r, L, Lp, base, plane, scale, mrow != nullptr, mcol, nIB, small52 != 0, ltab, jl0, jl1);
       if (mrow != nullptr && i < L) mrow[((((size_t) r * nJB + t.y) * GRAM_EPI_GROUPS + eg) * L + i) * 4 + a] = racc;
+#endif
       tc_fence_before();
       mbar_arrive(tempty_bar(acc));
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }

@@ -377,6 +377,63 @@ stat_kernel(const long long *__restrict__ cnt, const double *__restrict__ pm, co
 #endif
 }
 
+// Several statistics of one (weighted) count table in one pass -- BASELINE config 5 sweeps MI, MIr, MIg, CHI, OMES and GT over the
+// same alignments, and cov_Calculate's dispatch (src/covariation.c:100-258) differs only in which corr_Calculate* it calls on
+// the probabilities of one corr_Probs.  The 128 B of counts per pair are read once and every requested raw statistic is written
+// to its own matrix; each is computed by the very functions the single-statistic kernel uses (pair_statistic / gt_c16_raw), so a
+// matrix equals that kernel's.  Row/column partials and the score range come from reduce_cov_kernel afterwards (same tiling,
+// same summation order as stat_kernel's own).
+struct MultiOut { double *cov[6]; };                                 // CHI, OMES, GT, MI, MIr, MIg; NULL = not requested
+template <int CLS>
+__global__ void __launch_bounds__(ST_TJ)
+multi_stat_kernel(const long long *__restrict__ cnt, const double *__restrict__ pm, const double2 *__restrict__ gtab, int L, int Lp,
+                  double scale, long long wtot, unsigned mask, MultiOut out, int sr, int sw)
+{
+  __shared__ double pmi[ST_TI][4], lpmi[ST_TI][4];
+  __shared__ double2 tab[LOGTAB_N];
+  const int jt = blockIdx.x, it = blockIdx.y, r = blockIdx.z;
+  const int j  = jt * ST_TJ + threadIdx.x;
+  const size_t plane = (size_t) L * Lp;
+  const long long *c = cnt + (size_t) r * 16 * plane;
+  const bool tile_live = (it * ST_TI) < (jt * ST_TJ + ST_TJ - 1) && RSB_OWNED(it, sr, sw);
+  if (!tile_live) return;
+  logtab_load(tab, gtab);
+  double mj[4] = { 0.25, 0.25, 0.25, 0.25 }, lmj[4];
+  if (threadIdx.x < ST_TI * 4) {
+    const int il = threadIdx.x >> 2, a = threadIdx.x & 3, i = it * ST_TI + il;
+    pmi[il][a]  = (i < L) ? pm[((size_t) r * L + i) * 4 + a] : 0.25;
+    lpmi[il][a] = (pmi[il][a] > 0.0) ? log(pmi[il][a]) : 0.0;
+  }
+  if (j < L) {
+    #pragma unroll
+    for (int b = 0; b < 4; b++) mj[b] = pm[((size_t) r * L + j) * 4 + b];
+  }
+  #pragma unroll
+  for (int b = 0; b < 4; b++) lmj[b] = (mj[b] > 0.0) ? log(mj[b]) : 0.0;
+  __syncthreads();
+  if (j >= L) return;
+  #pragma unroll 1
+  for (int il = 0; il < ST_TI; il++) {
+    const int i = it * ST_TI + il;
+    if (i >= L || i >= j) continue;
+    const size_t off = (size_t) i * Lp + j, o = (size_t) r * plane + off;
+    PairProbs P;
+    load_pair<false>(c, plane, off, scale, wtot, P);
+    if (out.cov[0]) out.cov[0][o] = pair_statistic<RSB_CHI,  CLS == RSB_CWC ? RSB_C16 : CLS>(P, pmi[il], mj, lpmi[il], lmj, mask, tab);
+    if (out.cov[1]) out.cov[1][o] = pair_statistic<RSB_OMES, CLS == RSB_CWC ? RSB_C16 : CLS>(P, pmi[il], mj, lpmi[il], lmj, mask, tab);
+    if (out.cov[2]) {
+      if (CLS == RSB_C16) {
+        double x[16], ne;
+        load_pair_raw(c, plane, off, scale, wtot, x, ne);
+        out.cov[2][o] = gt_c16_raw(x, ne, lpmi[il], lmj, tab);
+      } else out.cov[2][o] = pair_statistic<RSB_GT, CLS>(P, pmi[il], mj, lpmi[il], lmj, mask, tab);
+    }
+    if (out.cov[3]) out.cov[3][o] = pair_statistic<RSB_MI,  CLS == RSB_CWC ? RSB_C16 : CLS>(P, pmi[il], mj, lpmi[il], lmj, mask, tab);
+    if (out.cov[4]) out.cov[4][o] = pair_statistic<RSB_MIr, CLS == RSB_CWC ? RSB_C16 : CLS>(P, pmi[il], mj, lpmi[il], lmj, mask, tab);
+    if (out.cov[5]) out.cov[5][o] = pair_statistic<RSB_MIg, CLS == RSB_CWC ? RSB_C16 : CLS>(P, pmi[il], mj, lpmi[il], lmj, mask, tab);
+  }
+}
+
 // G test on 16 classes from the per-pair records left by the record epilogue of the tcgen05 kernel (gram_tcgen05.cu): with
 // l_i[a] = log pm_i[a],
 //     G_ij = A - [ N2 l_i[3] + sum_{a<3} U_a (l_i[a] - l_i[3]) ] - [ N2 l_j[3] + sum_{b<3} V_b (l_j[b] - l_j[3]) ]
@@ -730,6 +787,26 @@ cudaError_t rsb_launch_statistic(int stat, int cls, const long long *cnt, const 
   case RSB_MIr  * 4 + RSB_C2:  RSB_STAT_CASE(RSB_MIr,  RSB_C2)
   case RSB_MIg  * 4 + RSB_C16: RSB_STAT_CASE(RSB_MIg,  RSB_C16)
   case RSB_MIg  * 4 + RSB_C2:  RSB_STAT_CASE(RSB_MIg,  RSB_C2)
+  default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+// cov6[k] (k = CHI, OMES, GT, MI, MIr, MIg; NULL = skip): raw statistic matrices [nrep][L][Lp] of the counts in cnt
+cudaError_t rsb_launch_multi_statistic(int cls, const long long *cnt, const double *pm, const void *logtab_, int nrep, int L, int Lp, double scale,
+                                       long long wtot, unsigned mask, double *const *cov6, int sr, int sw, cudaStream_t st)
+{
+  int nJT, nIT; rsb_stat_grid(L, &nJT, &nIT);
+  dim3 grid(nJT, nIT, nrep);
+  const double2 *logtab = (const double2 *) logtab_;
+  MultiOut out;
+  for (int k = 0; k < 6; k++) out.cov[k] = cov6[k];
+  switch (cls) {
+  case RSB_C16: rsb_coreside(multi_stat_kernel<RSB_C16>); multi_stat_kernel<RSB_C16><<<grid, ST_TJ, 0, st>>>(cnt, pm, logtab, L, Lp, scale, wtot, mask, out, sr, sw); break;
+  case RSB_C2:  rsb_coreside(multi_stat_kernel<RSB_C2>);  multi_stat_kernel<RSB_C2><<<grid, ST_TJ, 0, st>>>(cnt, pm, logtab, L, Lp, scale, wtot, mask, out, sr, sw); break;
+  case RSB_CWC:                                                       // only the G test is defined on the Watson-Crick cells (correlators.c:72)
+    for (int k = 0; k < 6; k++) if (k != 2 && cov6[k]) return cudaErrorInvalidValue;
+    rsb_coreside(multi_stat_kernel<RSB_CWC>); multi_stat_kernel<RSB_CWC><<<grid, ST_TJ, 0, st>>>(cnt, pm, logtab, L, Lp, scale, wtot, mask, out, sr, sw); break;
   default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();

@@ -462,3 +462,53 @@ cov_CreateHitList_b200(struct data_s *data, struct mutual_s *mi, RANKLIST *rankl
   if (hitlist) cov_FreeHitList(hitlist);
   return status;
 }
+
+/* ---------------------------------------------------------------------------------------------------------------------------
+ * Tail fit of the cumulative null histogram: the "Histogram and Fit" block of cov_SignificantPairs_Ranking
+ * (src/covariation.c:459-487).  O(bins) host arithmetic between the device's histogram and the device's E-value pass. */
+static double
+histogram_pmass(ESL_HISTOGRAM *h, double target_pmass, double target_fracfit)       /* cov_histogram_pmass, :2484-2505 */
+{
+  int      i, tp = 0, nfit = 0;
+  uint64_t c = 0;
+  double   pmass = NAN;                                                            /* stays undefined when no bin holds a score */
+  for (i = h->imax; i >= h->imin; i--) if (h->obs[i] > 0) tp++;
+  for (i = h->imax; i >= h->imin; i--) {
+    c += h->obs[i];
+    if (h->obs[i] > 0) {
+      nfit++;
+      pmass = (double) c / (double) h->Nc;
+      if ((double) nfit / (double) tp >= target_fracfit || pmass >= target_pmass) break;
+    }
+  }
+  return pmass;
+}
+
+int
+cov_NullFit_b200(ESL_HISTOGRAM *h, double pmass_target, double fracfit, int doexpfit, double **ret_survfit, double *ret_newmass,
+                 double *ret_mu, double *ret_lambda, double *ret_tau, char *errbuf)
+{
+  double  ep[3] = { 0.0, 0.0, 0.0 }, newmass = 0.0, pmass, *survfit = NULL;
+  int     b, status;
+
+  *ret_survfit = NULL;
+  pmass = histogram_pmass(h, pmass_target, fracfit);
+  if (isnan(pmass)) ESL_FAIL(eslFAIL, errbuf, "bad Null histogram fit, pmass is nan.");                          /* :470 */
+  if (esl_histogram_SetTailByMass(h, pmass, &newmass) != eslOK) ESL_FAIL(eslFAIL, errbuf, "could not set TailByMass");
+  if (doexpfit) status = esl_exp_FitCompleteBinned(h, &ep[0], &ep[1]);
+  else          status = esl_gam_FitCompleteBinned(h, &ep[0], &ep[1], &ep[2]);
+  if (status != eslOK) ESL_FAIL(eslFAIL, errbuf, doexpfit ? "could not do exponential fit" : "could not do a Gamma fit");
+  if (!isinf(ep[1])) {                                                                                          /* :1930, :1961 */
+    if ((survfit = calloc((size_t) 2 * (size_t) h->nb, sizeof(double))) == NULL) ESL_FAIL(eslEMEM, errbuf, "allocation failed");
+    for (b = h->cmin; b < 2 * h->nb; b++) {                                                                     /* cov_histogram_SetSurvFitTail */
+      const double bi = esl_histogram_Bin2UBound(h, b);
+      survfit[b] = newmass * (doexpfit ? esl_exp_generic_surv(bi, ep) : esl_gam_generic_surv(bi, ep));
+    }
+  }
+  *ret_survfit = survfit;
+  if (ret_newmass) *ret_newmass = newmass;
+  if (ret_mu)      *ret_mu      = ep[0];
+  if (ret_lambda)  *ret_lambda  = ep[1];
+  if (ret_tau)     *ret_tau     = ep[2];
+  return eslOK;
+}

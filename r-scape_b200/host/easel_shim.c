@@ -592,6 +592,8 @@ esl_tree_Destroy(ESL_TREE *T)
   if (T == NULL) return;
   free(T->parent); free(T->left); free(T->right); free(T->ld); free(T->rd);
   free(T->taxaparent); free(T->cladesize);
+  if (T->taxonlabel) { int i; for (i = 0; i < T->nalloc; i++) free(T->taxonlabel[i]); free(T->taxonlabel); }
+  if (T->nodelabel)  { int i; for (i = 0; i < T->nalloc - 1; i++) free(T->nodelabel[i]); free(T->nodelabel); }
   free(T);
 }
 

@@ -10,6 +10,8 @@
                                       alignments: every statistic x class x correction on one small alignment, used
                                       to pin the oracle wherever oracle/_ref is not available (e.g. the GPU box)
 
+  tests/golden/arisong_fasttree.nwk   FastTree 2.1.11 (the reference's vendored copy, `-quiet -nt`) on the analysed tutorial alignment
+  tests/golden/arisong_fasttree.npz   ... read, re-ordered to the alignment's rows and rooted at the midpoint by the reference's own code
   tests/golden/ref_evalues.npz        the reference's static cov2evalue / evalue2cov on a seeded null histogram (with / without a tail)
   tests/golden/ref_treesubs.npz       the reference's Tree_Substitutions on a seeded alignment + tree
 
@@ -28,6 +30,33 @@ sys.path.insert(0, ROOT)
 import __graft_entry__ as ge  # noqa: E402
 
 REF = "/root/reference"
+
+
+def make_fasttree_fixture(po, names, ax):
+    """tests/golden/arisong_fasttree.{nwk,npz}: the tree R-scape's default null model is built on for the tutorial alignment
+    (Tree_CalculateExtFromMSA, src/msatree.c:49-105): the analysed alignment (gap columns removed) written as aligned FASTA, the
+    reference's vendored FastTree 2.1.11 run as `FastTree -quiet -nt` (:149), its Newick output read by the shim's
+    esl_tree_ReadNewick and re-ordered / rooted at the midpoint by the reference's own Tree_ReorderTaxaAccordingMSA +
+    Tree_RootAtMidPoint (oracle/_ref).  FastTree is deterministic, so the fixture is reproducible from the reference tree."""
+    import subprocess
+    import tempfile
+    sub, keep = po.remove_gap_columns(ax)
+    sub = po.degen_to_N(sub)
+    text = {0: "A", 1: "C", 2: "G", 3: "U", 4: "-", 15: "N"}
+    fasttree = os.path.join(ROOT, "oracle", "_ref", "FastTree")
+    with tempfile.TemporaryDirectory() as tmp:
+        afa = os.path.join(tmp, "msa.afa")
+        with open(afa, "w") as fh:
+            for name, row in zip(names, sub):
+                fh.write(">" + name + "\n" + "".join(text[int(c)] for c in row) + "\n")
+        nwk = subprocess.run([fasttree, "-quiet", "-nt", afa], check=True, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
+    path = os.path.join(HERE, "arisong_fasttree.nwk")
+    with open(path, "w") as fh:
+        fh.write(nwk)
+    tree = po.RefLib().tree_from_newick(path, names, rootatmid=True)
+    np.savez_compressed(os.path.join(HERE, "arisong_fasttree.npz"), left=tree.left, right=tree.right, parent=tree.parent, ld=tree.ld, rd=tree.rd,
+                        names=np.array(names))
+    return tree
 
 
 def main():
@@ -49,6 +78,8 @@ def main():
                 avgid=float(m.group(5)), nbpairs=int(m.group(7)), summary=summary, pairs=pairs)
     with open(os.path.join(HERE, "arisong_tutorial.json"), "w") as fh:
         json.dump(gold, fh, indent=1)
+
+    make_fasttree_fixture(po, names, ax)
 
     ref = po.RefLib()
     msa, wgt, _ = po.synthetic_msa(90, 58, seed=2024)
