@@ -18,6 +18,7 @@
  */
 #ifndef RSCAPE_B200_INCLUDED
 #define RSCAPE_B200_INCLUDED
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -61,7 +62,7 @@ int rsb_get_quantisation_error(rsb_ctx *ctx, double *max_abs_err, double *effect
 /* Mixed precision (the "split path with a stated bound" of the weighted counts): contract the NULL alignments (rsb_null_width*,
  * rsb_null_hist*) with nslices <= S base-256 digits of the same weights, the input alignment keeps all S.  The nulls only feed
  * the score histogram whose tail gives the E-values (src/R-scape.c:1650-1697); with 2 slices their weights carry ~21 bits and
- * the null scores move by less than 1e-5 of the histogram's bin width (bound measured in tests/test_gpu_mixed.py).
+ * a null's scores move by at most 2e-4 max(1,|score|), under 1e-2 of the histogram's bin width (bound measured in tests/test_gpu_mixed.py).
  * 0 = off (default): one set of weights everywhere.  Takes effect at the next rsb_set_weights. */
 int rsb_set_null_slices(rsb_ctx *ctx, int nslices);
 /* the quantisation the nulls are scored with (= rsb_get_quantisation / _error when rsb_set_null_slices is off); any pointer may be NULL */
@@ -122,8 +123,9 @@ typedef struct rsb_nullfit {
  * For every pair i<j: pval = cov2evalue(score, 1, null), E = pval * Nb if pairmask[i][j] (pair of the given structure,
  * by data->samplesize), else pval * Nt -- or pval * expBP while fewer than expBP hits are listed (expBP > 0, :852);
  * hit iff E < thresh, every pair if thresh > 1000 (MAX_EVAL).  eval (double [L][L], may be NULL) receives mi->Eval: both
- * triangles, +inf on the diagonal.  Hits come back in the reference's row-major order; *nhit is their total number, of
- * which the first min(*nhit, cap) are stored (hit_sc / hit_eval / hit_pval may be NULL).
+ * triangles, +inf on the diagonal.  Hits come back in the reference's row-major order; *nhit is their total number.  When
+ * *nhit <= cap the arrays hold all of them; when *nhit > cap their contents are UNSPECIFIED (some subset of the hits, not a prefix)
+ * and the call must be repeated with cap >= *nhit, as cov_CreateHitList_b200 does (hit_sc / hit_eval / hit_pval may be NULL).
  * On a sharded pair grid a rank lists the pairs of the rows it owns (entries of other rows in eval are 0), and the caller
  * concatenates the ranks' lists: the only data besides the histograms that crosses GPUs. */
 int rsb_scan_hits(rsb_ctx *ctx, const rsb_nullfit *null, const uint8_t *pairmask, uint64_t Nb, uint64_t Nt, int expBP, double thresh,
@@ -275,6 +277,13 @@ int rsb_msa_pb_weights(rsb_ctx *ctx, const uint8_t *msa, int nseq, int alen, int
  * matrix esl_msaweight_GSC builds its UPGMA tree from (nseq <= 1000). */
 int rsb_msa_pair_identity(rsb_ctx *ctx, const uint8_t *msa, int nseq, int alen, int64_t row_stride, int on_device, const int *pairs, int64_t npairs,
                           double *out);
+
+/* ---- pinned host buffers --------------------------------------------------------------------------- */
+/* Page-lock / release a host buffer that is handed to the library repeatedly (mi->COV, mi->Eval, the pp slab, alignment rows):
+ * copies then run at the PCIe rate instead of through the driver's pageable staging.  0 = registered, 1 = left pageable
+ * (never an error of the path).  corr_Create registers the buffers of struct mutual_s it allocates; corr_Destroy releases them. */
+int rsb_host_register(void *ptr, size_t bytes);
+int rsb_host_unregister(void *ptr);
 
 /* ---- instrumentation ------------------------------------------------------------------------------ */
 /* kernels launched by this context so far; device milliseconds spent in the gram kernel and number of

@@ -120,6 +120,8 @@ def lib():
         L.rsb_comm_range.argtypes = [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.rsb_sharded_scan.argtypes = [_vp, _vp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.c_double, _dp, _dp, _dp]
         L.rsb_profile_gram.argtypes = [_vp, C.c_int]
+        L.rsb_host_register.argtypes = [_vp, C.c_size_t]
+        L.rsb_host_unregister.argtypes = [_vp]
         L.rsb_counters_geometry.argtypes = [_vp, C.c_int, C.POINTER(C.c_double), _i64p, _ip]
         _lib = L
     return _lib
@@ -134,6 +136,17 @@ def _ptr(x):
     if isinstance(x, np.ndarray):
         return x.ctypes.data_as(_vp), 0
     return C.c_void_p(x.data_ptr()), (1 if x.is_cuda else 0)
+
+
+def pin(array):
+    """Page-lock a numpy buffer that is handed to the library repeatedly (rsb_host_register): copies then run at the PCIe rate.
+    Returns True if it is now pinned; call unpin() before the array is freed."""
+    assert isinstance(array, np.ndarray) and array.flags.c_contiguous
+    return lib().rsb_host_register(array.ctypes.data_as(_vp), array.nbytes) == 0
+
+
+def unpin(array):
+    return lib().rsb_host_unregister(array.ctypes.data_as(_vp)) == 0
 
 
 def comm_id():
@@ -255,7 +268,7 @@ class Context:
         assert cov.shape == (self.L, self.L)
         self._ck(lib().rsb_load_scores(self._h, _d(cov)))
 
-    def scan_hits(self, bmin, w, obs, xmax, Nt, Nb=0, pairmask=None, survfit=None, phi=np.inf, expBP=-1, thresh=0.05, want_eval=True, cap=None):
+    def scan_hits(self, bmin, w, obs, xmax, Nt, Nb=0, pairmask=None, survfit=None, phi=np.inf, expBP=-1, thresh=0.05, want_eval=True, cap=None, eval_out=None):
         """E-values and significant pairs of the last scan (cov_CreateHitList's per-pair loop, src/covariation.c:828-910) against
         the cumulative null histogram obs[nb] (geometry bmin, w; largest null score xmax) and, optionally, its fitted tail
         survfit[2 nb] with censoring point phi.  Returns dict(i, j, sc, eval, pval, nhit, Eval)."""
@@ -270,7 +283,8 @@ class Context:
         pm = None if pairmask is None else np.ascontiguousarray(pairmask, dtype=np.uint8)
         assert pm is None or pm.shape == (self.L, self.L)
         P = self.L * (self.L - 1) // 2
-        ev = np.empty((self.L, self.L)) if want_eval else None
+        ev = (eval_out if eval_out is not None else np.empty((self.L, self.L))) if want_eval else None
+        assert ev is None or (ev.shape == (self.L, self.L) and ev.dtype == np.float64 and ev.flags.c_contiguous)
         # cap None: lists are short unless every pair is reported; start small and repeat the call once if the list is longer
         retry = cap is None
         cap = (P if (thresh > 1000 or expBP > 0) else min(P, 1 << 16)) if cap is None else int(cap)
@@ -287,7 +301,7 @@ class Context:
         k = min(n.value, cap)
         return dict(i=hi[:k].copy(), j=hj[:k].copy(), sc=sc[:k].copy(), eval=he[:k].copy(), pval=hp[:k].copy(), nhit=n.value, Eval=ev)
 
-    def tree_substitutions(self, left, right, leaves, internal, includegaps=False, want_pairs=True):
+    def tree_substitutions(self, left, right, leaves, internal, includegaps=False, want_pairs=True, out=None):
         """Tree_Substitutions after its Fitch pass (src/msatree.c:1455-1540) -> (nsubs [L], ndouble [L][L], njoin [L][L]).
         The context must be configured with nseq = 2 (ntaxa - 1) rows (one per branch)."""
         leaves = np.ascontiguousarray(leaves, dtype=np.uint8)
@@ -296,8 +310,8 @@ class Context:
         assert internal.shape == (ntaxa - 1, L) and L == self.L
         lf, rt = np.ascontiguousarray(left, dtype=np.int32), np.ascontiguousarray(right, dtype=np.int32)
         ns = np.empty(L, np.int32)
-        nd = np.empty((L, L), np.int32) if want_pairs else None
-        nj = np.empty((L, L), np.int32) if want_pairs else None
+        nd = (out[0] if out is not None else np.empty((L, L), np.int32)) if want_pairs else None       # out: caller's (e.g. pinned) tables
+        nj = (out[1] if out is not None else np.empty((L, L), np.int32)) if want_pairs else None
         ip = lambda a: None if a is None else a.ctypes.data_as(_ip)
         self._ck(lib().rsb_tree_substitutions(self._h, ntaxa, ip(lf), ip(rt), leaves.ctypes.data_as(_u8p), L, internal.ctypes.data_as(_u8p), L,
                                               1 if includegaps else 0, ip(ns), ip(nd), ip(nj)))

@@ -85,7 +85,12 @@ cudaError_t rsb_launch_pb_weights(const uint8_t *msa, int N, int L, long long ro
 cudaError_t rsb_launch_pair_identity(const uint8_t *msa, int N, int L, long long row_stride, const int *pairs, long long npairs, double *out, cudaStream_t st);
 cudaError_t rsb_launch_column_subset(const uint8_t *msa, int N, long long row_stride, const int *cols, int nkeep, uint8_t *out, cudaStream_t st);
 
+#include <nvtx3/nvToolsExt.h>
 namespace {
+// NVTX ranges (tracing): one per C-ABI phase on the calling thread, so that a timeline tool shows which host call
+// enqueued which kernels; header-only NVTX v3, a no-op unless a tool is attached
+struct NvtxRange { explicit NvtxRange(const char *name) { nvtxRangePushA(name); } ~NvtxRange() { nvtxRangePop(); } };
+#define RSB_RANGE(name) NvtxRange nvtx_range_(name)
 constexpr int HIST_BINS = 1 << 22;
 
 // operand geometry for one slice count
@@ -432,6 +437,7 @@ int upload_msa(rsb_ctx *ctx, const uint8_t *msa, int64_t row_stride, int64_t rep
 // src: [nrep][N][L] contiguous (the slots themselves, or a caller's device buffer read in place).
 int enqueue_pack(rsb_ctx *ctx, int which, int s0, int nrep, const uint8_t *src, cudaStream_t st)
 {
+  RSB_RANGE("rsb:pack_planes");
   if (ensure_geo(ctx, which)) return 1;
   Geo &g = ctx->geo[which];
   RSB_CUDA_OK(rsb_launch_pack(g.S, src, nrep, ctx->N, ctx->L, (long long) ctx->N * ctx->L, g.d_wdig, ctx->Kpad,
@@ -444,6 +450,7 @@ int enqueue_pack(rsb_ctx *ctx, int which, int s0, int nrep, const uint8_t *src, 
 // tcgen05 contraction of the planes of slots [s0, s0 + nrep) -> count planes, on stream st
 int enqueue_gram(rsb_ctx *ctx, int which, int s0, int nrep, cudaStream_t st, bool rec = false)
 {
+  RSB_RANGE("rsb:gram_tcgen05");
   Geo &g = ctx->geo[which];
   if (rec && (which == 1 || g.pair_clusters > 0)) { rsb_set_error(ctx, "internal: record epilogue not available here"); return 1; }
   if (g.ntiles > 0) {
@@ -567,6 +574,7 @@ int comm_reduce_minmax(rsb_ctx *ctx, double *minmax, int n, cudaStream_t st)
 // marginals (corr_Marginals) for slots [s0, s0+nrep) on stream st.  phase 1 = partial sums -> msum, 2 = normalise, 3 = both
 int enqueue_marginals(rsb_ctx *ctx, int s0, int nrep, double tol, cudaStream_t st, int phase = 3)
 {
+  RSB_RANGE("rsb:marginals");
   Geo &g = ctx->geo[ctx->cur_geo];                                  // (0 or 2: the weighted geometry the contraction just ran with)
   SlotPtrs p = slot_ptrs(ctx, s0);
   // partials are addressed [r][block][L][4] with r the absolute slot, as the gram kernel wrote them
@@ -587,6 +595,7 @@ int enqueue_marginals(rsb_ctx *ctx, int s0, int nrep, double tol, cudaStream_t s
 // COVx, COVavg and the raw min/max
 int enqueue_statistic(rsb_ctx *ctx, int s0, int nrep, int stat, int covclass, unsigned mask, cudaStream_t st, int phase = 3, int part = 3)
 {
+  RSB_RANGE("rsb:statistic");
   // part: 1 = the statistic kernel(s) only, 2 = the reductions of its partial sums only, 3 = both
   Geo &g = ctx->geo[ctx->cur_geo];
   int nJT, nIT; rsb_stat_grid(ctx->L, &nJT, &nIT);
@@ -633,6 +642,7 @@ int enqueue_statistic(rsb_ctx *ctx, int s0, int nrep, int stat, int covclass, un
 // correction + min/max (+ optional write-back / histogram) for slots [s0, s0+nrep)
 int enqueue_correct(rsb_ctx *ctx, int s0, int nrep, int actype, int mode, double bmin, cudaStream_t st)
 {
+  RSB_RANGE("rsb:correct_hist");
   SlotPtrs p = slot_ptrs(ctx, s0);
   RSB_CUDA_OK(rsb_launch_correct_hist(p.cov, p.covx, p.scal, nrep, ctx->L, ctx->Lp, actype, mode, bmin, ctx->d_w, ctx->d_hist, HIST_BINS,
                                       p.mm, p.minmax, ctx->d_flags, ctx->shard_rank, ctx->shard_world, ctx->d_m2p, ctx->mind, st));
@@ -743,6 +753,11 @@ int rsb_create(int device, void *stream, rsb_ctx **out)
     cudaEventCreateWithFlags(&c->ev_marg[g], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->ev_statk[g], cudaEventDisableTiming);
   }
+  if ((e = cudaGetLastError()) != cudaSuccess || !c->stream || !c->stream_aux || !c->stream_aux2 || !c->stream_copy || !c->stream_gen || !c->stream_hi ||
+      !c->ev_exit || !c->ev_entry) {
+    snprintf(g_create_err, sizeof(g_create_err), "rsb_create: streams / events: %s", cudaGetErrorString(e));
+    delete c; return 1;
+  }
   if (cudaMalloc(&c->d_logtab, rsb_logtab_bytes()) != cudaSuccess || rsb_launch_logtab(c->d_logtab, c->stream) != cudaSuccess ||
       cudaStreamSynchronize(c->stream) != cudaSuccess) {
     snprintf(g_create_err, sizeof(g_create_err), "rsb_create: log table: %s", cudaGetErrorString(cudaGetLastError()));
@@ -774,7 +789,19 @@ void rsb_destroy(rsb_ctx *ctx)
   delete ctx;
 }
 
+static int configure_impl(rsb_ctx *ctx, int nseq, int alen, int max_replicates, int nslices);
 int rsb_configure(rsb_ctx *ctx, int nseq, int alen, int max_replicates, int nslices)
+{
+  const int rc = configure_impl(ctx, nseq, alen, max_replicates, nslices);
+  if (rc != 0 && ctx) {                                              // never leave a half-allocated plan that later calls would accept
+    cudaGetLastError();
+    free_plan(ctx);
+    ctx->N = ctx->L = ctx->Rcap = 0;
+  }
+  return rc;
+}
+
+static int configure_impl(rsb_ctx *ctx, int nseq, int alen, int max_replicates, int nslices)
 {
   if (nseq < 1 || alen < 1 || max_replicates < 1 || nslices < 0 || nslices > RSB_MAX_SLICES) { rsb_set_error(ctx, "bad configuration"); return 1; }
   if (nslices && ctx->Snull > nslices) { rsb_set_error(ctx, "the nulls are set to %d weight slices, more than the %d of the input alignment", ctx->Snull, nslices); return 1; }
@@ -938,6 +965,7 @@ int rsb_fetch_probs(rsb_ctx *ctx, double *pp, double *pm, double *ps, double *ns
 int rsb_probs(rsb_ctx *ctx, const uint8_t *msa, int64_t row_stride, int on_device, double tol,
               double *pp, double *pm, double *ps, double *nseff, double *ngap)
 {
+  RSB_RANGE("rsb_probs");
   RSB_CUDA_OK(cudaSetDevice(ctx->device));
   if (ensure_geo(ctx, 0)) return 1;
   if (upload_msa(ctx, msa, row_stride, 0, 1, 0, on_device, ctx->stream)) return 1;
@@ -1005,6 +1033,7 @@ int rsb_scan(rsb_ctx *ctx, const uint8_t *msa, int64_t row_stride, int on_device
              const double *allowpair, double tol, double *cov, double *mincov, double *maxcov,
              double *pp, double *pm, double *ps, double *nseff, double *ngap)
 {
+  RSB_RANGE("rsb_scan");
   RSB_CUDA_OK(cudaSetDevice(ctx->device));
   if (resolve_stat(ctx, stat, covclass)) return 1;
   const bool raf = (stat == RSB_RAF || stat == RSB_RAFS);
@@ -1054,6 +1083,7 @@ int rsb_get_counts_direct(rsb_ctx *ctx, const uint8_t *msa, int64_t row_stride, 
 int rsb_null_width(rsb_ctx *ctx, const uint8_t *null0, int64_t row_stride, int on_device, int stat, int covclass, int actype,
                    const double *allowpair, double tol, double w_old, double bmin, int hpts, double *w_out, double *mincov, double *maxcov)
 {
+  RSB_RANGE("rsb_null_width");
   RSB_CUDA_OK(cudaSetDevice(ctx->device));
   if (resolve_stat(ctx, stat, covclass)) return 1;
   if (ctx->shard_world > 1 && !grid_comm(ctx)) { rsb_set_error(ctx, "calculate_width_histo on a sharded pair grid needs a communicator (rsb_comm_init)"); return 1; }
@@ -1084,6 +1114,7 @@ static int null_hist_pipelined(rsb_ctx *ctx, const uint8_t *nulls, int nrep, int
                                int stat, int covclass, int actype, unsigned mask, double tol, double w, double bmin,
                                double *minmax, int pool_first = -1)
 {
+  RSB_RANGE("rsb:null_loop");
   const bool raf = (stat == RSB_RAF || stat == RSB_RAFS);
   const int  wgeo = raf ? 1 : null_geo(ctx);
   // GT x C16: the contraction's epilogue leaves per-pair records and the statistic finishes with an HBM-bound kernel on the
@@ -1224,6 +1255,7 @@ static int null_hist_multi(rsb_ctx *ctx, const uint8_t *nulls, int nrep, int64_t
                            int ncombo, const int *stat, const int *actype, int covclass, unsigned mask, double tol, const double *w, double bmin,
                            double *minmax)
 {
+  RSB_RANGE("rsb:null_loop_multi");
   if (ncombo < 1 || ncombo > 64) { rsb_set_error(ctx, "bad number of (statistic, correction) combinations %d", ncombo); return 1; }
   if (ctx->shard_world > 1) { rsb_set_error(ctx, "rsb_null_hist_multi is not offered on a sharded pair grid"); return 1; }
   if (covclass != RSB_C16 && covclass != RSB_C2 && covclass != RSB_CWC) { rsb_set_error(ctx, "covclass must be resolved by the caller"); return 1; }
@@ -1471,6 +1503,7 @@ int rsb_sharded_correct(rsb_ctx *ctx, const double *cov_sums, int actype, int mo
 /* histograms of the scan left by rsb_scan / rsb_correct / rsb_statistic: ha (all pairs), and with pairmask also hb / ht */
 int rsb_scan_hist(rsb_ctx *ctx, const uint8_t *pairmask, double w, double bmin, int nb, uint64_t *ha, uint64_t *hb, uint64_t *ht)
 {
+  RSB_RANGE("rsb_scan_hist");
   RSB_CUDA_OK(cudaSetDevice(ctx->device));
   if (nb < 1 || !(w > 0.0)) { rsb_set_error(ctx, "bad histogram geometry"); return 1; }
   const size_t L = ctx->L;
@@ -1530,6 +1563,7 @@ int rsb_load_scores(rsb_ctx *ctx, const double *cov)
 int rsb_scan_hits(rsb_ctx *ctx, const rsb_nullfit *null, const uint8_t *pairmask, uint64_t Nb, uint64_t Nt, int expBP, double thresh,
                   double *eval, int64_t cap, int64_t *hit_i, int64_t *hit_j, double *hit_sc, double *hit_eval, double *hit_pval, int64_t *nhit)
 {
+  RSB_RANGE("rsb_scan_hits");
   RSB_CUDA_OK(cudaSetDevice(ctx->device));
   if (!null || !null->obs || null->nb < 1 || !(null->w > 0.0) || null->imax < null->imin || null->imin < 0 || null->imax >= null->nb || null->Nc == 0) {
     rsb_set_error(ctx, "rsb_scan_hits: empty or inconsistent null histogram"); return 1;
@@ -1635,6 +1669,7 @@ done:
 int rsb_tree_substitutions(rsb_ctx *ctx, int ntaxa, const int *left, const int *right, const uint8_t *leaves, int64_t leaf_stride,
                            const uint8_t *internal, int64_t internal_stride, int includegaps, int *nsubs, int *ndouble, int *njoin)
 {
+  RSB_RANGE("rsb_tree_substitutions");
   RSB_CUDA_OK(cudaSetDevice(ctx->device));
   const int nrows = 2 * (ntaxa - 1);
   if (ntaxa < 2 || !left || !right || !leaves || !internal) { rsb_set_error(ctx, "rsb_tree_substitutions: bad arguments"); return 1; }
@@ -1695,6 +1730,7 @@ int rsb_hist_reset(rsb_ctx *ctx)
 
 int rsb_hist_read(rsb_ctx *ctx, uint64_t *bins, int nb_cap, uint64_t *n_out, int *imax_out)
 {
+  RSB_RANGE("rsb_hist_read");
   RSB_CUDA_OK(cudaSetDevice(ctx->device));
   const int nb = std::min(nb_cap, HIST_BINS);
   RSB_CUDA_OK(cudaMemcpyAsync(bins, ctx->d_hist, sizeof(uint64_t) * nb, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1832,6 +1868,7 @@ int rsb_pool_reserve(rsb_ctx *ctx, int nrep)
 int rsb_null_simulate(rsb_ctx *ctx, const double *Q, const uint8_t *root, const uint8_t *gapmask, int64_t gap_stride,
                       uint64_t seed, uint64_t first_id, int first_rep, int nrep)
 {
+  RSB_RANGE("rsb_null_simulate");
   RSB_CUDA_OK(cudaSetDevice(ctx->device));
   if (!ctx->have_tree) { rsb_set_error(ctx, "rsb_set_tree first"); return 1; }
   if (pool_range_ok(ctx, first_rep, nrep)) return 1;
@@ -1890,6 +1927,7 @@ int rsb_null_simulate(rsb_ctx *ctx, const double *Q, const uint8_t *root, const 
 static int fitch_shuffle_impl(rsb_ctx *ctx, const uint8_t *msa, int64_t row_stride, uint64_t seed, uint64_t first_id, const uint64_t *ids,
                               int first_rep, int nrep)
 {
+  RSB_RANGE("rsb:null_fitch_shuffle");
   RSB_CUDA_OK(cudaSetDevice(ctx->device));
   if (!ctx->have_tree) { rsb_set_error(ctx, "rsb_set_tree first"); return 1; }
   if (pool_range_ok(ctx, first_rep, nrep)) return 1;
@@ -1910,6 +1948,11 @@ static int fitch_shuffle_impl(rsb_ctx *ctx, const uint8_t *msa, int64_t row_stri
   RSB_CUDA_OK(cudaMemcpy2DAsync(ctx->d_msa0, L, msa, (size_t) row_stride, L, N, cudaMemcpyHostToDevice, sg));
   int unknown = 1;
   RSB_CUDA_OK(rsb_launch_unknown_check(ctx->d_msa0, (size_t) N * L, ctx->d_genflag, &unknown, sg));
+  if (unknown & 2) {                                                 // the reference fails here too: "S not set up properly" (msatree.c:1740)
+    rsb_set_error(ctx, "the alignment holds residue codes other than A C G U, gap and N (degenerate symbols must be converted to N first, "
+                       "msamanip_ConvertDegen2N, src/R-scape.c:1855): the Fitch pass of the null generator cannot set them up");
+    return 1;
+  }
   if (getenv("RSCAPE_B200_FITCH_PER_REPLICATE")) unknown = 1;      // tests: force the general path
   uint8_t *sets = unknown ? nullptr : ctx->d_sets;
   unsigned long long *d_ids = nullptr;
@@ -2157,6 +2200,7 @@ int rsb_comm_destroy(rsb_ctx *ctx)
 /* null_add2cumranklist across ranks (src/R-scape.c:1565-1612): sum the first nb bins of the device histograms of all ranks in place */
 int rsb_hist_allreduce(rsb_ctx *ctx, int nb)
 {
+  RSB_RANGE("rsb_hist_allreduce");
   RSB_CUDA_OK(cudaSetDevice(ctx->device));
   if (nb < 1 || nb > HIST_BINS) { rsb_set_error(ctx, "rsb_hist_allreduce: bad bin count"); return 1; }
   if (!ctx->comm) { rsb_set_error(ctx, "rsb_hist_allreduce: no communicator (rsb_comm_init)"); return 1; }
@@ -2200,6 +2244,7 @@ int rsb_comm_range(rsb_ctx *ctx, double *lo, double *hi, double *aux_min)
 int rsb_sharded_scan(rsb_ctx *ctx, const uint8_t *msa, int64_t row_stride, int on_device, int stat, int covclass, int actype,
                      const double *allowpair, double tol, double *cov, double *mincov, double *maxcov)
 {
+  RSB_RANGE("rsb_sharded_scan");
   RSB_CUDA_OK(cudaSetDevice(ctx->device));
   if (resolve_stat(ctx, stat, covclass)) return 1;
   if (!grid_comm(ctx)) { rsb_set_error(ctx, "rsb_sharded_scan needs rsb_set_shard and a communicator over the shards"); return 1; }
@@ -2221,6 +2266,23 @@ int rsb_sharded_scan(rsb_ctx *ctx, const uint8_t *msa, int64_t row_stride, int o
   if (check_flags(ctx, "corr_CalculateCOVCorrected")) return 1;
   if (mincov) *mincov = mmx[0];
   if (maxcov) *maxcov = mmx[1];
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- pinned host buffers
+/* Page-lock a host buffer the caller keeps handing to the library (mi->COV, mi->Eval, the pp slab, the residue rows ...): copies
+ * to and from a registered buffer run at the PCIe rate and do not block the enqueuing thread; a pageable buffer costs the driver's
+ * staging (about half the rate).  Failure is not an error of the path: the buffer simply stays pageable (return 1). */
+int rsb_host_register(void *ptr, size_t bytes)
+{
+  if (!ptr || bytes == 0) return 1;
+  if (cudaHostRegister(ptr, bytes, cudaHostRegisterPortable) != cudaSuccess) { cudaGetLastError(); return 1; }
+  return 0;
+}
+int rsb_host_unregister(void *ptr)
+{
+  if (!ptr) return 1;
+  if (cudaHostUnregister(ptr) != cudaSuccess) { cudaGetLastError(); return 1; }
   return 0;
 }
 

@@ -256,6 +256,117 @@ __device__ __forceinline__ double gram_epilogue_tile(uint32_t trow, int jb, int 
   return racc;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Record epilogue, pair-per-thread form (S = 1, 2, 4).  The accumulator hands a thread ONE residue row (i, a) of every pair, so
+// the form above pays ~30 shuffles and as many selects per pair to bring the 4 rows of a pair together -- and every ALU
+// instruction issued beside the running MMAs is throttled (ncu: "math pipe throttle" is the top stall of this kernel).  Here a
+// warp moves the digits of 32 pairs (its 8 columns i x 4 columns j) through 2 KB of shared memory, 16 bytes per lane and store,
+// bank-conflict free by an XOR swizzle, after which every lane owns the whole 4 x 4 table of one pair: sums, the 17 logs, the
+// one division and the record are thread-local; what stays across lanes are 4 double shuffles per pair for the column marginal
+// partials and two reductions per tile for the row partials.  Same record, same arithmetic per value as the form above.
+template <int S>
+__device__ __forceinline__ void gram_epilogue_rec_pairs(uint32_t trow, int jb, int i0w, int lane, int ew, int ib, int r, int L, int Lp,
+                                                        double *__restrict__ rec0, size_t plane, double scale, double *__restrict__ mrow_blk,
+                                                        double *__restrict__ mcol, int nIB, bool small52, const double2 *__restrict__ ltab,
+                                                        uint4 *__restrict__ xbuf, int jl_begin, int jl_end)
+{
+  constexpr int CJ = rsb_cj_for(S);
+  const int il_w = lane >> 2, a_w = lane & 3;                       // what this lane's TMEM row is: column i0w + il_w, residue a_w
+  const int il_t = lane & 7, jj = lane >> 3;                        // the pair this lane owns after the exchange: column i0w + il_t, j0 + jj
+  const int i = i0w + il_t;
+  const int wslot = a_w ^ ((il_w >> 1) & 3);                        // swizzled 16-byte slot of row a_w inside the pair's 64 bytes
+  const int rsw = (lane >> 1) & 3;
+  double racc[4] = { 0.0, 0.0, 0.0, 0.0 };                          // row marginal partials of (i, a) over this lane's columns
+  #pragma unroll 1
+  for (int jl = jl_begin; jl < jl_end; jl += 4) {
+    unsigned long long c[4][4];
+    #pragma unroll
+    for (int k = 0; k < S; k++) {
+      uint32_t d[4][4];
+      #pragma unroll
+      for (int u = 0; u < 4; u++) tmem_ld4(trow + (uint32_t) (((jl + u) * S + k) * 4), d[u][0], d[u][1], d[u][2], d[u][3]);
+      tmem_ld_wait();
+      #pragma unroll
+      for (int u = 0; u < 4; u++) xbuf[(u * 8 + il_w) * 4 + wslot] = make_uint4(d[u][0], d[u][1], d[u][2], d[u][3]);
+      __syncwarp();
+      #pragma unroll
+      for (int a = 0; a < 4; a++) {
+        const uint4 v = xbuf[lane * 4 + (a ^ rsw)];
+        if (k == 0) { c[a][0] = v.x; c[a][1] = v.y; c[a][2] = v.z; c[a][3] = v.w; }
+        else {
+          c[a][0] += (unsigned long long) v.x << (8 * k); c[a][1] += (unsigned long long) v.y << (8 * k);
+          c[a][2] += (unsigned long long) v.z << (8 * k); c[a][3] += (unsigned long long) v.w << (8 * k);
+        }
+      }
+      __syncwarp();
+    }
+    const int  j  = jb * CJ + jl + jj;
+    const bool ok = (i < L) && (j < L) && (i < j);
+
+    double x[4][4], X[4], Y[4], sl[4];
+    unsigned long long nl = 0;
+    #pragma unroll
+    for (int a = 0; a < 4; a++) {
+      #pragma unroll
+      for (int b = 0; b < 4; b++) x[a][b] = fma(small52 ? u52_to_f64(c[a][b]) : u64_to_f64(c[a][b]), scale, 1e-10);
+      X[a] = (x[a][0] + x[a][1]) + (x[a][2] + x[a][3]);
+      nl += (c[a][0] + c[a][1]) + (c[a][2] + c[a][3]);
+      double s1 = x[a][0] * GLOG(x[a][0]);
+      s1 = fma(x[a][1], GLOG(x[a][1]), s1);
+      double s2 = x[a][2] * GLOG(x[a][2]);
+      s2 = fma(x[a][3], GLOG(x[a][3]), s2);
+      sl[a] = s1 + s2;
+    }
+    #pragma unroll
+    for (int b = 0; b < 4; b++) Y[b] = (x[b][b] + x[b ^ 2][b]) + (x[b ^ 1][b] + x[b ^ 3][b]);
+    const double sum  = (X[0] + X[1]) + (X[2] + X[3]);
+    const double slog = (sl[0] + sl[1]) + (sl[2] + sl[3]);
+    const double ne   = small52 ? u52_to_f64(nl) : u64_to_f64(nl);
+    const double n2   = 2.0 * (ne * scale);
+    const double invT = 1.0 / sum;
+    const double coef = n2 * invT;
+    const double rA   = fma(coef, slog, -n2 * GLOG(sum));
+    if (ok) {
+      double *q = rec0 + (size_t) i * Lp + j;
+      q[0] = rA;
+      q[plane] = n2;
+      q[2 * plane] = coef * X[0]; q[3 * plane] = coef * X[1]; q[4 * plane] = coef * X[2];
+      q[5 * plane] = coef * Y[0]; q[6 * plane] = coef * Y[1]; q[7 * plane] = coef * Y[2];
+    }
+    // marginal partials (corr_Marginals :1335-1370, the per-pair part); pairs with nseff = 0 are skipped (:1354)
+    const double inv = (ok && nl != 0ULL) ? invT : 0.0;
+    #pragma unroll
+    for (int a = 0; a < 4; a++) racc[a] = fma(X[a], inv, racc[a]);
+    // column partials of (j, b): sum over the warp's 8 columns i (lanes jj * 8 .. jj * 8 + 7), halving butterfly
+    {
+      const bool h4 = lane & 4, h2 = lane & 2;
+      const double y0 = Y[0] * inv, y1 = Y[1] * inv, y2 = Y[2] * inv, y3 = Y[3] * inv;
+      const double k0 = h4 ? y2 : y0, k1 = h4 ? y3 : y1, t0 = h4 ? y0 : y2, t1 = h4 ? y1 : y3;
+      const double z0 = k0 + __shfl_xor_sync(0xffffffffu, t0, 4), z1 = k1 + __shfl_xor_sync(0xffffffffu, t1, 4);
+      double v = (h2 ? z1 : z0) + __shfl_xor_sync(0xffffffffu, h2 ? z0 : z1, 2);
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      if ((lane & 1) == 0 && j < L)
+        mcol[(((size_t) r * 4 * nIB + (size_t) ib * 4 + ew) * L + j) * 4 + ((h4 ? 2 : 0) + (h2 ? 1 : 0))] = v;
+    }
+  }
+  // row partials: sum over the 4 lanes (jj) that share a column i, then one lane per column writes its 4 values
+  #pragma unroll
+  for (int a = 0; a < 4; a++) {
+    racc[a] += __shfl_xor_sync(0xffffffffu, racc[a], 8);
+    racc[a] += __shfl_xor_sync(0xffffffffu, racc[a], 16);
+  }
+  if (lane < 8 && i < L) {
+    double *o = mrow_blk + (size_t) i * 4;
+    *reinterpret_cast<double2 *>(o)     = make_double2(racc[0], racc[1]);
+    *reinterpret_cast<double2 *>(o + 2) = make_double2(racc[2], racc[3]);
+  }
+}
+
+#ifndef RSB_REC_PAIRS
+#define RSB_REC_PAIRS 1         // 1: pair-per-thread record epilogue for S = 1, 2, 4 (0: the row-per-thread form everywhere)
+#endif
+template <int S> __host__ __device__ constexpr bool rec_pairs_form() { return RSB_REC_PAIRS && (S == 1 || S == 2 || S == 4) && (gram_cols_per_group(rsb_cj_for(S), GRAM_EPI_GROUPS) % 4 == 0) && (rsb_cj_for(S) % 4 == 0); }
+
 #ifdef RSB_BLOCKTRACE
 __device__ unsigned long long *gram_trace_buf;
 #endif
@@ -289,6 +400,8 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
   volatile uint32_t *tmem_slot_ptr = (volatile uint32_t *) (smem_raw + (tmem_slot - smem_u32(smem_raw)));
   // REC: the log table of the statistic (rsb_common.cuh, fast_log), 8 KB behind the barriers
   const double2 *ltab = reinterpret_cast<const double2 *>(smem_raw + (bar_base + 128u - smem_u32(smem_raw)));
+  // REC, pair-per-thread form: 2 KB of exchange space per epilogue warp behind the table
+  uint4 *xbuf_all = reinterpret_cast<uint4 *>(smem_raw + (bar_base + 128u + (uint32_t) (sizeof(double2) * LOGTAB_N) - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -381,6 +494,16 @@ gram_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant_
       const double racc = 0.0;
       if (mrow != nullptr && i < L && trow == 0xffffffffu) mrow[(size_t) 0] = 0.0;
 #else
+      if (REC && rec_pairs_form<S>()) {
+        double *rec0 = reinterpret_cast<double *>(cnt) + (size_t) r * 16 * plane;
+        double *mrow_blk = mrow + (((size_t) r * nJB + t.y) * GRAM_EPI_GROUPS + eg) * (size_t) L * 4;
+        gram_epilogue_rec_pairs<S>(trow, t.y, t.x * RSB_ICOLS + ew * 8, lane, ew, t.x, r, L, Lp, rec0, plane, scale, mrow_blk, mcol, nIB, small52 != 0, ltab,
+                                   xbuf_all + (size_t) (warp - 4) * 128, jl0, jl1);
+        tc_fence_before();
+        mbar_arrive(tempty_bar(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        continue;
+      }
       const double racc = gram_epilogue_tile<S, REC>(trow, t.y, i, a, lane, ew, t.x, r, L, Lp, base, plane, scale, mrow != nullptr, mcol, nIB, small52 != 0, ltab, jl0, jl1);
       if (mrow != nullptr && i < L) mrow[((((size_t) r * nJB + t.y) * GRAM_EPI_GROUPS + eg) * L + i) * 4 + a] = racc;
 #endif
@@ -568,7 +691,8 @@ template <int S> constexpr size_t gram_pair_smem_bytes() {
 }
 
 template <int S, bool REC> constexpr size_t gram_smem_bytes() {
-  return (size_t) NSTAGE * (RSB_MTILE * RSB_KSTAGE + 4 * S * rsb_cj_for(S) * RSB_KSTAGE) + 128 + (REC ? sizeof(double2) * LOGTAB_N : 0) + 1024;
+  return (size_t) NSTAGE * (RSB_MTILE * RSB_KSTAGE + 4 * S * rsb_cj_for(S) * RSB_KSTAGE) + 128 +
+         (REC ? sizeof(double2) * LOGTAB_N + (rec_pairs_form<S>() ? (size_t) 2048 * 4 * GRAM_EPI_GROUPS : 0) : 0) + 1024;
 }
 
 template <int S, bool REC>

@@ -211,9 +211,16 @@ __global__ void fitch_down_level_kernel(const int *__restrict__ left, const int 
 // which makes the Fitch sets replicate-specific)
 __global__ void unknown_flag_kernel(const uint8_t *__restrict__ msa, size_t n, int *__restrict__ flag)
 {
-  bool any = false;
-  for (size_t k = (size_t) blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t) gridDim.x * blockDim.x) any |= msa[k] > 4;
-  if (__syncthreads_or(any) && threadIdx.x == 0) *flag = 1;
+  // bit 0: unknown residues (N = 15) present; bit 1: codes the reference's Fitch pass cannot set up (degenerate symbols, '*', '~':
+  // only esl_abc_XIsUnknown gets the uniform set, anything else fails with "S not set up properly", src/msatree.c:1731-1740)
+  bool any = false, bad = false;
+  for (size_t k = (size_t) blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t) gridDim.x * blockDim.x) {
+    const uint8_t c = msa[k];
+    any |= c > 4;
+    bad |= c > 4 && c != 15;
+  }
+  const int a1 = __syncthreads_or(any), b1 = __syncthreads_or(bad);
+  if (threadIdx.x == 0 && (a1 || b1)) atomicOr(flag, (a1 ? 1 : 0) | (b1 ? 2 : 0));
 }
 
 // one random permutation per replicate (Fisher-Yates by one thread; L is a few thousand).  It depends on (seed, replicate id)

@@ -31,6 +31,7 @@ typedef struct side_s {
   rsb_ctx         *ctx;
   uint8_t         *stage;       /* contiguous copy of the alignment rows (ESL_MSA keeps one malloc per row) */
   double          *pp_slab, *nseff_slab, *ngap_slab, *pm_slab, *ps_slab;
+  int              pinned;       /* the slabs, mi->COV and mi->Eval are page-locked (rsb_host_register) */
   struct side_s   *next;
 } SIDE;
 
@@ -106,6 +107,17 @@ corr_Create(int64_t alen, int64_t nseq, int ishuffled, int nseqthresh, int alent
   if (rsb_create(device, NULL, &sd->ctx) != 0) { fprintf(stderr, "corr_Create(): %s\n", rsb_create_error()); goto ERROR; }
   if (rsb_configure(sd->ctx, (int) nseq, (int) alen, 1, slices) != 0) { fprintf(stderr, "corr_Create(): %s\n", rsb_error(sd->ctx)); goto ERROR; }
 
+  /* page-lock what the device writes into on every scan (a pageable target costs about half the copy rate and blocks the
+   * enqueuing thread); RSCAPE_B200_PIN=0 leaves everything pageable */
+  sd->pinned = !(getenv("RSCAPE_B200_PIN") && atoi(getenv("RSCAPE_B200_PIN")) == 0);
+  if (sd->pinned && mi->COV && mi->Eval && sd->pp_slab && sd->nseff_slab && sd->ngap_slab && sd->stage) {
+    rsb_host_register(mi->COV->mx[0],  sizeof(double) * L * L);
+    rsb_host_register(mi->Eval->mx[0], sizeof(double) * L * L);
+    rsb_host_register(sd->pp_slab,     sizeof(double) * L * L * 16);
+    rsb_host_register(sd->nseff_slab,  sizeof(double) * L * L);
+    rsb_host_register(sd->ngap_slab,   sizeof(double) * L * L);
+    rsb_host_register(sd->stage,       (size_t) nseq * L);
+  }
   sd->mi = mi;
   sd->next = side_head;
   side_head = sd;
@@ -158,6 +170,16 @@ corr_ReuseCOV(struct mutual_s *mi, COVTYPE mitype, COVCLASS miclass)
   return eslOK;
 }
 
+static void
+unpin_buffers(SIDE *sd, struct mutual_s *mi)
+{
+  if (!sd || !sd->pinned) return;
+  if (mi && mi->COV)  rsb_host_unregister(mi->COV->mx[0]);
+  if (mi && mi->Eval) rsb_host_unregister(mi->Eval->mx[0]);
+  rsb_host_unregister(sd->pp_slab); rsb_host_unregister(sd->nseff_slab); rsb_host_unregister(sd->ngap_slab); rsb_host_unregister(sd->stage);
+  sd->pinned = 0;
+}
+
 void
 corr_Destroy(struct mutual_s *mi)
 {
@@ -168,6 +190,7 @@ corr_Destroy(struct mutual_s *mi)
   for (pp = &side_head; (sd = *pp) != NULL; pp = &sd->next)
     if (sd->mi == mi) {
       *pp = sd->next;
+      unpin_buffers(sd, mi);
       rsb_destroy(sd->ctx);
       free(sd->pp_slab); free(sd->nseff_slab); free(sd->ngap_slab); free(sd->pm_slab); free(sd->ps_slab); free(sd->stage);
       free(sd);

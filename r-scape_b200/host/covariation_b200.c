@@ -233,6 +233,9 @@ null_worker_run(void *arg)
   wk->status = eslFAIL; wk->err[0] = 0; wk->bins = NULL; wk->nb = 0; wk->n_added = 0;
   slots = slots_for((int) N, (int) L, nmine);
   if (rsb_create(wk->device, NULL, &ctx) != 0) { snprintf(wk->err, eslERRBUFSIZE, "%s", rsb_create_error()); goto DONE; }
+  /* RSCAPE_B200_NULL_SLICES: mixed precision -- the nulls contracted with fewer digit slices of the weights than the input alignment */
+  if (getenv("RSCAPE_B200_NULL_SLICES") && rsb_set_null_slices(ctx, atoi(getenv("RSCAPE_B200_NULL_SLICES"))) != 0)
+    { snprintf(wk->err, eslERRBUFSIZE, "%s", rsb_error(ctx)); goto DONE; }
   if (rsb_configure(ctx, (int) N, (int) L, slots, wk->slices) != 0 ||
       rsb_set_weights(ctx, wk->nulls[0]->wgt) != 0 ||                              /* nulls carry the input's weights (:1668) */
       (data->msa2pdb && rsb_set_pair_exclusion(ctx, data->msa2pdb, RSB_DATA_MIND(data)) != 0))   /* covariation.c:421-427 */

@@ -366,3 +366,20 @@ def test_scans_wait_for_the_generation_stream(ctx, po):
     bins2, n2, imax2 = ctx.hist_read(4096)
     assert w == w2 and n == n2 and imax == imax2
     assert np.array_equal(bins, bins2) and np.array_equal(mm, mm2)
+
+
+def test_fitch_shuffle_rejects_codes_the_reference_cannot_set_up(ctx, pkg, po):
+    """Only esl_abc_XIsUnknown (N) gets the uniform Fitch set; any other non-canonical code makes the reference fail with
+    "S not set up properly" (src/msatree.c:1731-1740).  The device refuses such an alignment instead of resolving the code at random."""
+    N, L = 24, 40
+    msa, wgt, _, tree = pkg.synth.synthetic_family(N, L, seed=9)
+    ctx.configure(N, L, 2, 0)
+    ctx.set_tree(tree.left, tree.right, tree.parent, tree.ld, tree.rd)
+    ctx.pool_reserve(2)
+    ok = msa.copy()
+    ok[3, 5] = 15                                                     # N: fine
+    ctx.null_fitch_shuffle(ok, 1, 2)
+    bad = msa.copy()
+    bad[3, 5] = 5                                                     # R (degenerate): msamanip_ConvertDegen2N must have run first
+    with pytest.raises(pkg.RscapeB200Error, match="Fitch"):
+        ctx.null_fitch_shuffle(bad, 1, 2)

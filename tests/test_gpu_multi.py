@@ -50,12 +50,10 @@ def test_multi_equals_single_statistic_runs_and_oracle(ctx, pkg, po, oracle, cls
         mm1 = ctx.null_hist(nulls, w[k], getattr(pkg, s), getattr(pkg, cls), getattr(pkg, a))
         bins1, n1, _ = ctx.hist_read(view.nb + 8)
         assert n1 == n
-        if (s, cls) == ("GT", "C16"):                   # the single run scores GT x C16 through the record epilogue: same values up to rounding
-            assert_bins_identical(bins, bins1, scores, -10.0, w[k], scale=max(1.0, float(np.max(np.abs(mm_ref)))))
-            assert np.max(np.abs(mm[k] - mm1)) <= 1e-9 * max(1.0, np.max(np.abs(mm1)))
-        else:
-            assert np.array_equal(bins, bins1), (s, a)
-            assert np.array_equal(mm[k], mm1), (s, a)
+        # same code per statistic, but compiled into another kernel (GT x C16 of the single run even goes through the record epilogue):
+        # values may differ in the last bits, so bins are compared with the bin-edge rule and the score range to 1e-12
+        assert_bins_identical(bins, bins1, scores, -10.0, w[k], rel=1e-12, scale=max(1.0, float(np.max(np.abs(mm_ref)))))
+        assert np.max(np.abs(mm[k] - mm1)) <= 1e-12 * max(1.0, np.max(np.abs(mm1))), (s, a)
 
 
 def test_multi_on_pool_entries_and_accumulation(ctx, pkg, po):

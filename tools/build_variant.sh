@@ -9,5 +9,5 @@ for f in gram_tcgen05 pack stats correct_hist hits treesubs nullgen msaprep capi
   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC "$@" -c csrc/$f.cu -o build/alt/$name/$f.o &
 done
 wait
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o build/alt/$name.so build/alt/$name/*.o -lcudart
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o build/alt/$name.so build/alt/$name/*.o -lcudart -ldl
 echo built build/alt/$name.so

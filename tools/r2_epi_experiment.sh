@@ -3,4 +3,4 @@
 cd "$(dirname "$0")/.."
 A=r-scape_b200/build/alt
 python tools/gram_time.py ssu 1,2,4
-for v in noepi nomma nomma_e4 nolog e4; do RSCAPE_B200_LIB=$PWD/$A/$v.so python tools/gram_time.py ssu 1,2,4; done
+for v in rowform noepi nomma nomma_row; do RSCAPE_B200_LIB=$PWD/$A/$v.so python tools/gram_time.py ssu 1,2,4; done

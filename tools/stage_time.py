@@ -44,10 +44,14 @@ nb = int(np.ceil((max(mm[:, 1].max(), res["maxcov"]) + 10.0) / w)) + 6
 bins, n, _ = ctx.hist_read(nb)
 P = L * (L - 1) // 2
 mask = np.zeros((L, L), np.uint8)
-for variant, kw in (("E-values + mi->Eval + hit list", dict(want_eval=True)), ("hit list only", dict(want_eval=False))):
+ev_pinned = np.empty((L, L))
+pinned = pkg.pin(mask) and pkg.pin(ev_pinned)                         # what corr_Create does for mi->Eval (rsb_host_register)
+for variant, kw in (("E-values + mi->Eval + hit list", dict(want_eval=True)), ("hit list only", dict(want_eval=False)),
+                    ("E-values + mi->Eval + hit list, page-locked mi->Eval and mask", dict(want_eval=True, eval_out=ev_pinned))):
     best, med = timed(lambda: ctx.scan_hits(-10.0, w, bins, float(mm[:, 1].max()), P, 0, mask, thresh=0.6, **kw))
     print(json.dumps(dict(stage="rsb_scan_hits", variant=variant, L=L, pairs=P, ms_best=best, ms_median=med,
-                          algorithmic_bytes=P * (8 + 1 + (16 if kw["want_eval"] else 0)))), flush=True)
+                          algorithmic_bytes=P * (8 + 1 + (16 if kw["want_eval"] else 0)), pinned=bool(pinned))), flush=True)
+pkg.unpin(mask); pkg.unpin(ev_pinned)
 ctx.close()
 
 # ---- Tree_Substitutions ---------------------------------------------------------------------------------------
@@ -57,9 +61,14 @@ for ntaxa, L in ((5000, 400),) if quick else ((5000, 400), (10000, 1800)):
     internal = rng.integers(0, 4, (ntaxa - 1, L), dtype=np.uint8)
     ctx = pkg.Context(0)
     ctx.configure(2 * (ntaxa - 1), L, 1, 1)
-    for variant, kw in (("nsubs + ndouble + njoin", dict(want_pairs=True)), ("nsubs only", dict(want_pairs=False))):
+    tables = (np.empty((L, L), np.int32), np.empty((L, L), np.int32))
+    pins = [leaves, internal, tables[0], tables[1]]
+    pinned = all(pkg.pin(a) for a in pins)
+    for variant, kw in (("nsubs + ndouble + njoin", dict(want_pairs=True, out=tables)), ("nsubs only", dict(want_pairs=False))):
         best, med = timed(lambda: ctx.tree_substitutions(tree.left, tree.right, leaves, internal, False, **kw))
         cells = L * L * 2 * (ntaxa - 1) / 2.0
         print(json.dumps(dict(stage="rsb_tree_substitutions", variant=variant, ntaxa=ntaxa, L=L, branch_rows=2 * (ntaxa - 1),
-                              pair_cells=cells, ms_best=best, ms_median=med)), flush=True)
+                              pair_cells=cells, ms_best=best, ms_median=med, pinned=bool(pinned))), flush=True)
+    for a in pins:
+        pkg.unpin(a)
     ctx.close()
