@@ -303,6 +303,7 @@ def main():
         state = {}
 
         def job():
+            tp = [time.perf_counter()]
             ctx.hist_reset_multi()
             mm0 = ctx.null_hist_multi(1, pc, [0.0] * len(pc), pkg.C16, first_rep=0)          # calculate_width_histo for every combination
             w = [width_of(mm0[k, 0, 0], mm0[k, 0, 1]) for k in range(len(pc))]
@@ -311,15 +312,23 @@ def main():
             for k in range(len(pc)):
                 nb = int(min(1 << 22, max(64, np.ceil((float(mm[k, :, 1].max()) - BMIN) / w[k]) + 8))) if w[k] > 0 else 64
                 hists.append(ctx.hist_read_multi(k, nb)[0])
-            for st, ac in rafs:                                                              # unit weights: their own (single-slice) contraction
-                ctx.hist_reset()
-                wr = ctx.null_width_pool(0, st, pkg.C16, ac)[0]
-                m2 = ctx.null_hist_pool(0, R, wr, st, pkg.C16, ac)
-                nb = int(min(1 << 22, max(64, np.ceil((float(m2[:, 1].max()) - BMIN) / wr) + 8))) if wr > 0 else 64
-                hists.append(ctx.hist_read(nb)[0].copy())
+            tp.append(time.perf_counter())
+            # RAFS x {APC, ASC}: unit weights, one single-slice contraction per null shared by the two corrections
+            mr0 = ctx.null_hist_multi(1, rafs, [0.0] * len(rafs), pkg.C16, first_rep=0)
+            wr = [width_of(mr0[k, 0, 0], mr0[k, 0, 1]) for k in range(len(rafs))]
+            ctx.hist_reset_multi()                                                           # (the weighted histograms have been read)
+            mr = ctx.null_hist_multi(R, rafs, wr, pkg.C16, first_rep=0)
+            for k in range(len(rafs)):
+                nb = int(min(1 << 22, max(64, np.ceil((float(mr[k, :, 1].max()) - BMIN) / wr[k]) + 8))) if wr[k] > 0 else 64
+                hists.append(ctx.hist_read_multi(k, nb)[0])
+            tp.append(time.perf_counter())
             for st, ac in pc + rafs:                                                         # run_rscape(GIVSS) per combination
                 ctx.scan(dev_msa, st, pkg.C16, ac, want_cov=False)
             state["hists"] = hists
+            if PHASES:
+                tp.append(time.perf_counter())
+                print("[bench] sweep phases ms: 12 weighted combinations %.1f, RAFS x 2 %.1f, %d scans of the input alignment %.1f" %
+                      ((tp[1] - tp[0]) * 1e3, (tp[2] - tp[1]) * 1e3, len(pc) + len(rafs), (tp[3] - tp[2]) * 1e3), file=sys.stderr, flush=True)
 
         sampler = ClockSampler(local)
         ctx.counters(reset=True)
@@ -337,8 +346,8 @@ def main():
                     warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True, scaling="strong", vs_baseline=None,
                     dtype="u8 x u8 -> s32 tensor-core counts (fixed-point weights), f64 statistics", data="synthetic",
                     config=dict(workload=f"sweep (BASELINE config 5): L={L} N={N} nulls={R}, {ncombo} (statistic, correction) combinations = {ncombo} x {scans_total} "
-                                         f"reference scans per step; executed: {R + 1} weighted contractions shared by 12 combinations (rsb_null_hist_multi) + "
-                                         f"{2 * (R + 1)} single-slice unweighted ones for RAFS + {ncombo} scans of the input alignment",
+                                         f"reference scans per step; executed: {R + 1} weighted contractions shared by 12 combinations + "
+                                         f"{R + 1} single-slice unweighted ones shared by RAFS+APC / RAFS+ASC (rsb_null_hist_multi) + {ncombo} scans of the input alignment",
                                 combinations=[f"{a}+{b}" for a, b in weighted] + ["RAFS+APC", "RAFS+ASC"], weight_slices=args.slices,
                                 histogram=dict(mass_ok=bool(ok))),
                     gpu_launches=int(cnt["launches"] * args.steps / (args.steps + args.warmup)), clocks=clocks,
@@ -431,7 +440,7 @@ def main():
         t_gen = time.perf_counter() - t_gen0
 
         # ---- value: inputs resident in HBM -------------------------------------------------------------------
-        sampler = ClockSampler(local) if (sample_clocks and rank == 0) else None
+        sampler = ClockSampler(local) if (sample_clocks and rank == 0 and not os.environ.get("BENCH_NO_SAMPLER")) else None
         ctx.counters(reset=True)
         ctx.profile_gram(True)
         if sampler:

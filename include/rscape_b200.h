@@ -230,7 +230,8 @@ int rsb_null_hist_pool(rsb_ctx *ctx, int first_rep, int nrep, int stat, int covc
  * {CHI, OMES, GT, MI, MIr, MIg} are evaluated from the same count planes in one pass, and combination k = (stat[k], actype[k])
  * is corrected and added to its own cumulative histogram with its own bin width w[k] (w[k] <= 0: score range only, no histogram
  * -- the width pass).  covclass is shared.  minmax: double [ncombo][nrep][2] (may be NULL).  Every histogram equals the one
- * rsb_null_hist leaves for that combination alone.  RAF / RAFS use unit weights, i.e. another contraction: rsb_null_hist. */
+ * rsb_null_hist leaves for that combination alone.  RAF / RAFS use unit weights, i.e. another contraction: a call holds either
+ * weighted statistics or {RAF, RAFS} x corrections (which then share one single-slice contraction per null), not both. */
 int rsb_null_hist_multi(rsb_ctx *ctx, const uint8_t *nulls, int nrep, int64_t row_stride, int64_t rep_stride, int on_device, int ncombo,
                         const int *stat, const int *actype, int covclass, const double *allowpair, double tol, const double *w, double bmin,
                         double *minmax);

@@ -41,7 +41,10 @@ size_t rsb_logtab_bytes();
 cudaError_t rsb_launch_statistic(int stat, int cls, const long long *cnt, const double *pm, const void *logtab, int nrep, int L, int Lp, double scale,
                                  long long wtot, unsigned mask, double *cov, double *rowpart, double *colpart, double *mm, int sr, int sw, cudaStream_t st);
 cudaError_t rsb_launch_multi_statistic(int cls, const long long *cnt, const double *pm, const void *logtab, int nrep, int L, int Lp, double scale,
-                                       long long wtot, unsigned mask, double *const *cov6, int sr, int sw, cudaStream_t st);
+                                       long long wtot, unsigned mask, double *const *cov6, size_t rep_stride, int sr, int sw, cudaStream_t st);
+cudaError_t rsb_launch_correct_hist_multi(const double *cov, const double *covx, const double *scal, int nrep, int L, int Lp, int ncombo, int nw,
+                                          const int *kidx, const int *act, double bmin, const double *wptr, unsigned long long *hist, int nbins,
+                                          double *mm, double *minmax_out, int *flags, const int *m2p, int mind, cudaStream_t st);
 cudaError_t rsb_launch_raf(const long long *cnt, int nrep, int L, int Lp, int nseq, unsigned mask, int smooth, double *tmp, double *cov,
                            double *rowpart, double *colpart, double *mm, cudaStream_t st);
 cudaError_t rsb_launch_ccf(const double *nseff, const double *pm, int nrep, int L, int Lp, double *part, double *meanp, double *cov,
@@ -168,6 +171,8 @@ struct rsb_ctx {
   unsigned long long hist_n = 0;
   // several statistics per contraction (rsb_null_hist_multi): raw matrices [6][Rcap][L][Lp], one histogram / width / range per combination
   double *d_covm = nullptr, *d_wm = nullptr, *d_minmaxm = nullptr; unsigned long long *d_histm = nullptr;
+  double *d_rowpart_m = nullptr, *d_colpart_m = nullptr, *d_mmr_m = nullptr, *d_covx_m = nullptr, *d_scal_m = nullptr, *d_blocksum_m = nullptr,
+         *d_covsum_m = nullptr, *d_mmc_m = nullptr;                  // the statistics chain's buffers with (slot, statistic) as the replicate index
   int multi_cap = 0; std::vector<unsigned long long> hist_n_m;
   int *d_m2p = nullptr; int mind = 1;                 // PDB positions of the columns + minimum distance: pairs kept out of the histograms
   unsigned long long pairs_in_hist = 0;               // pairs i<j that are not excluded by that rule
@@ -243,6 +248,7 @@ void free_plan(rsb_ctx *c)
   dfree(c->d_level_start); dfree(c->d_perm); dfree(c->d_pcdf); dfree(c->d_root); dfree(c->d_gapmask); dfree(c->d_simscratch);
   dfree(c->d_m2p); c->mind = 1;
   dfree(c->d_covm); dfree(c->d_wm); dfree(c->d_minmaxm); dfree(c->d_histm); c->multi_cap = 0; c->hist_n_m.clear();
+  dfree(c->d_rowpart_m); dfree(c->d_colpart_m); dfree(c->d_mmr_m); dfree(c->d_covx_m); dfree(c->d_scal_m); dfree(c->d_blocksum_m); dfree(c->d_covsum_m); dfree(c->d_mmc_m);
   dfree(c->d_msa0); dfree(c->d_anc); dfree(c->d_shanc); dfree(c->d_pool); dfree(c->d_sets); dfree(c->d_genflag); dfree(c->d_ids); c->ids_cap = 0; dfree(c->d_pthr); c->sim_valid = false;
   c->Rpool = 0;
   c->have_tree = false;
@@ -1234,13 +1240,27 @@ static int stat_slot(int stat)
   switch (stat) { case RSB_CHI: return 0; case RSB_OMES: return 1; case RSB_GT: return 2; case RSB_MI: return 3; case RSB_MIr: return 4; case RSB_MIg: return 5; }
   return -1;
 }
+// the unweighted statistics share a contraction of their own (unit weights, one digit slice): matrix slots 0 = RAF, 1 = RAFS
+static int unit_stat_slot(int stat) { return stat == RSB_RAF ? 0 : stat == RSB_RAFS ? 1 : -1; }
 
 static int multi_reserve(rsb_ctx *ctx, int ncombo)
 {
   const size_t L = ctx->L, Lp = ctx->Lp;
-  if (!ctx->d_covm) RSB_CUDA_OK(cudaMalloc(&ctx->d_covm, sizeof(double) * 6 * (size_t) ctx->Rcap * L * Lp));
+  int nJT, nIT; rsb_stat_grid(ctx->L, &nJT, &nIT);
+  const size_t V = 6 * (size_t) ctx->Rcap, tiles = (size_t) nJT * nIT;       // virtual replicates (slot, statistic)
+  if (!ctx->d_covm) {
+    RSB_CUDA_OK(cudaMalloc(&ctx->d_covm, sizeof(double) * V * L * Lp));
+    RSB_CUDA_OK(cudaMalloc(&ctx->d_rowpart_m, sizeof(double) * V * nJT * L));
+    RSB_CUDA_OK(cudaMalloc(&ctx->d_colpart_m, sizeof(double) * V * nIT * L));
+    RSB_CUDA_OK(cudaMalloc(&ctx->d_mmr_m, sizeof(double) * V * tiles * 2));
+    RSB_CUDA_OK(cudaMalloc(&ctx->d_covx_m, sizeof(double) * V * L));
+    RSB_CUDA_OK(cudaMalloc(&ctx->d_scal_m, sizeof(double) * V * 4));
+    RSB_CUDA_OK(cudaMalloc(&ctx->d_blocksum_m, sizeof(double) * V * ((L + 127) / 128)));
+    RSB_CUDA_OK(cudaMalloc(&ctx->d_covsum_m, sizeof(double) * V * (L + 4)));
+  }
   if (ncombo > ctx->multi_cap) {
-    dfree(ctx->d_wm); dfree(ctx->d_minmaxm); dfree(ctx->d_histm);
+    dfree(ctx->d_wm); dfree(ctx->d_minmaxm); dfree(ctx->d_histm); dfree(ctx->d_mmc_m);
+    RSB_CUDA_OK(cudaMalloc(&ctx->d_mmc_m, sizeof(double) * (size_t) ncombo * ctx->Rcap * tiles * 2));
     RSB_CUDA_OK(cudaMalloc(&ctx->d_wm, sizeof(double) * ncombo));
     RSB_CUDA_OK(cudaMalloc(&ctx->d_minmaxm, sizeof(double) * 2 * (size_t) ncombo * ctx->Rcap));
     RSB_CUDA_OK(cudaMalloc(&ctx->d_histm, sizeof(unsigned long long) * (size_t) ncombo * HIST_BINS));
@@ -1260,17 +1280,20 @@ static int null_hist_multi(rsb_ctx *ctx, const uint8_t *nulls, int nrep, int64_t
   if (ctx->shard_world > 1) { rsb_set_error(ctx, "rsb_null_hist_multi is not offered on a sharded pair grid"); return 1; }
   if (covclass != RSB_C16 && covclass != RSB_C2 && covclass != RSB_CWC) { rsb_set_error(ctx, "covclass must be resolved by the caller"); return 1; }
   bool want[6] = { false, false, false, false, false, false };
+  const bool unit = unit_stat_slot(stat[0]) >= 0;                    // RAF / RAFS combinations: the unit-weight contraction, shared by their corrections
+  auto slot_of = [&](int st) { return unit ? unit_stat_slot(st) : stat_slot(st); };
   for (int k = 0; k < ncombo; k++) {
-    const int sl = stat_slot(stat[k]);
-    if (sl < 0) { rsb_set_error(ctx, "statistic %d is not computed from the weighted counts (RAF/RAFS/CCF: use rsb_null_hist)", stat[k]); return 1; }
+    const int sl = slot_of(stat[k]);
+    if (sl < 0) { rsb_set_error(ctx, "statistic %d cannot share a contraction with statistic %d (weighted: CHI OMES GT MI MIr MIg; unit weights: RAF RAFS; "
+                                     "CCF: rsb_null_hist)", stat[k], stat[0]); return 1; }
     if (resolve_stat(ctx, stat[k], covclass)) return 1;
     if (actype[k] != RSB_APC && actype[k] != RSB_ASC && actype[k] != RSB_NOCORR) { rsb_set_error(ctx, "wrong correction type %d", actype[k]); return 1; }
     want[sl] = true;
   }
   if (multi_reserve(ctx, ncombo)) return 1;
-  const int  wgeo = null_geo(ctx);
+  const int  wgeo = unit ? 1 : null_geo(ctx);
+  if (ensure_geo(ctx, wgeo)) return 1;
   Geo &g = ctx->geo[wgeo];
-  if (!g.ready) { rsb_set_error(ctx, "rsb_set_weights has not been called"); return 1; }
   const bool in_place = (on_device && row_stride == ctx->L && rep_stride == (int64_t) ctx->N * ctx->L);
   const int  G = (ctx->Rcap >= 2) ? 2 : 1;
   const int  chunk = std::max(1, ctx->Rcap / G);
@@ -1294,36 +1317,47 @@ static int null_hist_multi(rsb_ctx *ctx, const uint8_t *nulls, int nrep, int64_t
   bool used[2] = { false, false };
   int nJT, nIT; rsb_stat_grid(ctx->L, &nJT, &nIT);
 
-  // S(pc): all statistics of chunk pc in one pass on the main stream (FP64: alone between two contractions), then per statistic
-  // the reductions and per combination the correction + histogram on the aux stream
+  // S(pc): all statistics of chunk pc in one pass on the main stream (FP64: alone between two contractions), then on the aux
+  // stream ONE reduction over the stacked matrices (virtual replicate q = slot * nw + index of the statistic), one set of row-mean
+  // kernels, and ONE launch that corrects and histograms every (replicate, combination)
+  int nw = 0, kidx_of[6], kidx[64], act[64];
+  for (int sl = 0; sl < 6; sl++) kidx_of[sl] = want[sl] ? nw++ : -1;
+  for (int k = 0; k < ncombo; k++) { kidx[k] = kidx_of[slot_of(stat[k])]; act[k] = actype[k]; }
+  const size_t tiles = (size_t) nJT * nIT, nblk = (size_t) (ctx->L + 127) / 128;
   auto tail = [&](int pc, int pr0) -> int {
     const int pg = pc % G, ps0 = pg * chunk, pn = std::min(chunk, nrep - pr0);
     cudaStream_t st_aux = aux_of(pg);
     SlotPtrs p = slot_ptrs(ctx, ps0);
+    const size_t q0 = (size_t) ps0 * nw;
+    double *covq = ctx->d_covm + q0 * LL;
     double *cov6[6];
-    for (int sl = 0; sl < 6; sl++) cov6[sl] = want[sl] ? ctx->d_covm + ((size_t) sl * ctx->Rcap + ps0) * LL : nullptr;
+    for (int sl = 0; sl < 6; sl++) cov6[sl] = want[sl] ? covq + (size_t) kidx_of[sl] * LL : nullptr;
     RSB_CUDA_OK(cudaStreamWaitEvent(sm, ctx->ev_marg[pg], 0));
     if (pc >= G) RSB_CUDA_OK(cudaStreamWaitEvent(sm, ctx->ev_stats[pg], 0));   // the group's matrices have been consumed
-    RSB_CUDA_OK(rsb_launch_multi_statistic(covclass, p.cnt, p.pm, ctx->d_logtab, pn, ctx->L, ctx->Lp, g.scale, g.wtot, mask, cov6, 0, 1, sm));
-    ctx->launches++;
+    if (unit) {                                                      // RAF from the count-table identity, RAFS = its 3-point stencil (stats.cu)
+      double *rp = ctx->d_rowpart + (size_t) ps0 * nJT * ctx->L, *cp = ctx->d_colpart + (size_t) ps0 * nIT * ctx->L;
+      for (int r = 0; r < pn; r++) {                                 // (the RAF kernels index replicates L * Lp apart: one replicate per launch)
+        SlotPtrs pr = slot_ptrs(ctx, ps0 + r);
+        if (want[0]) { RSB_CUDA_OK(rsb_launch_raf(pr.cnt, 1, ctx->L, ctx->Lp, ctx->N, mask, 0, pr.tmp, cov6[0] + (size_t) r * nw * LL, rp, cp, pr.mm, sm)); ctx->launches += 2; }
+        if (want[1]) { RSB_CUDA_OK(rsb_launch_raf(pr.cnt, 1, ctx->L, ctx->Lp, ctx->N, mask, 1, pr.tmp, cov6[1] + (size_t) r * nw * LL, rp, cp, pr.mm, sm)); ctx->launches += 3; }
+      }
+    } else {
+      RSB_CUDA_OK(rsb_launch_multi_statistic(covclass, p.cnt, p.pm, ctx->d_logtab, pn, ctx->L, ctx->Lp, g.scale, g.wtot, mask, cov6, (size_t) nw * LL, 0, 1, sm));
+      ctx->launches++;
+    }
     RSB_CUDA_OK(cudaEventRecord(ctx->ev_statk[pg], sm));
     RSB_CUDA_OK(cudaStreamWaitEvent(st_aux, ctx->ev_statk[pg], 0));
-    double *rowpart = ctx->d_rowpart + (size_t) ps0 * nJT * ctx->L, *colpart = ctx->d_colpart + (size_t) ps0 * nIT * ctx->L;
-    for (int sl = 0; sl < 6; sl++) {
-      if (!want[sl]) continue;
-      RSB_CUDA_OK(rsb_launch_reduce_cov(cov6[sl], pn, ctx->L, ctx->Lp, rowpart, colpart, p.mm, st_aux));
-      RSB_CUDA_OK(rsb_launch_correct_final(rowpart, colpart, p.mm, pn, ctx->L, p.covx, p.scal, p.blocksum, p.covsum, 3, st_aux));
-      ctx->launches += 4;
-      for (int k = 0; k < ncombo; k++) {
-        if (stat_slot(stat[k]) != sl) continue;
-        double *mmk = ctx->d_minmaxm + ((size_t) k * ctx->Rcap + ps0) * 2;
-        RSB_CUDA_OK(rsb_launch_correct_hist(cov6[sl], p.covx, p.scal, pn, ctx->L, ctx->Lp, actype[k], (w[k] > 0.0) ? 2 : 0, bmin, ctx->d_wm + k,
-                                            ctx->d_histm + (size_t) k * HIST_BINS, HIST_BINS, p.mm, mmk, ctx->d_flags, 0, 1, ctx->d_m2p, ctx->mind, st_aux));
-        ctx->launches += 2;
-        if (minmax) RSB_CUDA_OK(cudaMemcpyAsync(ctx->h_mm + 2 * ((size_t) k * nrep + pr0), mmk, sizeof(double) * 2 * pn, cudaMemcpyDeviceToHost, st_aux));
-        if (w[k] > 0.0) ctx->hist_n_m[k] += (unsigned long long) pn * ctx->pairs_in_hist;
-      }
-    }
+    double *rowpart = ctx->d_rowpart_m + q0 * nJT * ctx->L, *colpart = ctx->d_colpart_m + q0 * nIT * ctx->L, *mmr = ctx->d_mmr_m + q0 * tiles * 2;
+    double *covx = ctx->d_covx_m + q0 * ctx->L, *scal = ctx->d_scal_m + q0 * 4;
+    RSB_CUDA_OK(rsb_launch_reduce_cov(covq, pn * nw, ctx->L, ctx->Lp, rowpart, colpart, mmr, st_aux));
+    RSB_CUDA_OK(rsb_launch_correct_final(rowpart, colpart, mmr, pn * nw, ctx->L, covx, scal, ctx->d_blocksum_m + q0 * nblk, ctx->d_covsum_m + q0 * (ctx->L + 4), 3, st_aux));
+    double *mmk = ctx->d_minmaxm + (size_t) ps0 * ncombo * 2;
+    RSB_CUDA_OK(rsb_launch_correct_hist_multi(covq, covx, scal, pn, ctx->L, ctx->Lp, ncombo, nw, kidx, act, bmin, ctx->d_wm, ctx->d_histm, HIST_BINS,
+                                              ctx->d_mmc_m + (size_t) ps0 * ncombo * tiles * 2, mmk, ctx->d_flags, ctx->d_m2p, ctx->mind, st_aux));
+    ctx->launches += 6;
+    // (replicate-major here; transposed to [combination][replicate] on the host at the end)
+    if (minmax) RSB_CUDA_OK(cudaMemcpyAsync(ctx->h_mm + 2 * (size_t) pr0 * ncombo, mmk, sizeof(double) * 2 * (size_t) pn * ncombo, cudaMemcpyDeviceToHost, st_aux));
+    for (int k = 0; k < ncombo; k++) if (w[k] > 0.0) ctx->hist_n_m[k] += (unsigned long long) pn * ctx->pairs_in_hist;
     RSB_CUDA_OK(cudaEventRecord(ctx->ev_stats[pg], st_aux));
     return 0;
   };
@@ -1345,7 +1379,7 @@ static int null_hist_multi(rsb_ctx *ctx, const uint8_t *nulls, int nrep, int64_t
     if (enqueue_gram(ctx, wgeo, s0, n, sm, false)) return 1;           // (its counts were consumed by S(c - G), earlier on this stream)
     RSB_CUDA_OK(cudaEventRecord(ctx->ev_counts[gi], sm));
     RSB_CUDA_OK(cudaStreamWaitEvent(aux_of(gi), ctx->ev_counts[gi], 0));
-    if (enqueue_marginals(ctx, s0, n, tol, aux_of(gi))) return 1;
+    if (!unit && enqueue_marginals(ctx, s0, n, tol, aux_of(gi))) return 1;
     RSB_CUDA_OK(cudaEventRecord(ctx->ev_marg[gi], aux_of(gi)));
     used[gi] = true;
     if (G == 1) { if (tail(c, r0)) return 1; }
@@ -1356,7 +1390,12 @@ static int null_hist_multi(rsb_ctx *ctx, const uint8_t *nulls, int nrep, int64_t
   RSB_CUDA_OK(cudaEventRecord(ctx->ev_exit, sm));
   RSB_CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->ev_exit, 0));
   if (check_flags(ctx, "null_rscape")) return 1;
-  if (minmax) memcpy(minmax, ctx->h_mm, sizeof(double) * 2 * need);
+  if (minmax)
+    for (int r = 0; r < nrep; r++)
+      for (int k = 0; k < ncombo; k++) {
+        minmax[2 * ((size_t) k * nrep + r)]     = ctx->h_mm[2 * ((size_t) r * ncombo + k)];
+        minmax[2 * ((size_t) k * nrep + r) + 1] = ctx->h_mm[2 * ((size_t) r * ncombo + k) + 1];
+      }
   return 0;
 }
 

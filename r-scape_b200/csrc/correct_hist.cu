@@ -176,6 +176,84 @@ correct_hist_kernel(double *__restrict__ cov, const double *__restrict__ covx, c
   }
 }
 
+// Several (statistic, correction) combinations in ONE launch (rsb_null_hist_multi): blockIdx.z = r * ncombo + k.  Combination k
+// reads the raw matrix of its statistic, virtual replicate q = r * nw + kidx[k] of the stacked buffers (cov, covx, scal), corrects with
+// act[k], and adds into its own histogram hist + k * nbins with its own width w[k] (<= 0: score range only).  Body = correct_hist_kernel's.
+struct ComboTab { int kidx[64]; int act[64]; };
+__global__ void __launch_bounds__(CH_TJ, 6)
+correct_hist_multi_kernel(const double *__restrict__ cov, const double *__restrict__ covx, const double *__restrict__ scal, int L, int Lp,
+                          ComboTab tab, int ncombo, int nw, double bmin, const double *__restrict__ wptr, unsigned long long *__restrict__ hist,
+                          int nbins, double *__restrict__ mm, int *__restrict__ flags, int nJT, int nIT, const int *__restrict__ m2p, int mind)
+{
+  __shared__ unsigned int sh[CH_SMEM_BINS];
+  __shared__ double smin[CH_TJ / 32], smax[CH_TJ / 32];
+  __shared__ double sxi[CH_TI];
+  const int jt = blockIdx.x, it = blockIdx.y, z = blockIdx.z;
+  const int r = z / ncombo, k = z % ncombo, q = r * nw + tab.kidx[k], actype = tab.act[k];
+  const int j  = jt * CH_TJ + threadIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool tile_live = (it * CH_TI) < (jt * CH_TJ + CH_TJ - 1);
+  const double w = wptr[k];
+  const bool do_hist = w > 0.0;
+  const double avg = scal[q * 4];
+  unsigned long long *H = hist + (size_t) k * nbins;
+  double vmin = INFINITY, vmax = -INFINITY;
+  int b0 = 0;
+  if (do_hist) {
+    const double c = ceil((-bmin) / w - 1.0) - (double) (CH_SMEM_BINS / 2);
+    b0 = (c > 0.0 && c < (double) nbins) ? (int) c : 0;
+    for (int t = threadIdx.x; t < CH_SMEM_BINS; t += CH_TJ) sh[t] = 0;
+  }
+  if (threadIdx.x < CH_TI) { const int i = it * CH_TI + threadIdx.x; sxi[threadIdx.x] = (i < L) ? covx[(size_t) q * L + i] : 0.0; }
+  __syncthreads();
+  if (tile_live && j < L) {
+    const double xj = covx[(size_t) q * L + j];
+    const int mpj = m2p ? m2p[j] : -1;
+    const double *C = cov + (size_t) q * L * Lp;
+    #pragma unroll 1
+    for (int il0 = 0; il0 < CH_TI; il0 += 8) {
+      double raw[8];
+      #pragma unroll
+      for (int u = 0; u < 8; u++) { const int i = it * CH_TI + il0 + u; raw[u] = (i < L && i < j) ? C[(size_t) i * Lp + j] : 0.0; }
+      #pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int il = il0 + u, i = it * CH_TI + il;
+        if (i >= L || i >= j) continue;
+        const double v = corrected(actype, raw[u], sxi[il], xj, avg);
+        if (isnan(v)) atomicOr(flags, 2);
+        vmin = fmin(vmin, v);
+        vmax = fmax(vmax, v);
+        const bool excl = m2p && m2p[i] >= 0 && mpj >= 0 && mpj - m2p[i] < mind;
+        if (do_hist && !excl) {
+          const double x = fmax(v, bmin + w);
+          const double bd = ceil(((x - bmin) / w) - 1.);
+          if (bd >= 0.0 && bd < (double) nbins) {
+            const int b = (int) bd;
+            if (b >= b0 && b < b0 + CH_SMEM_BINS) atomicAdd(&sh[b - b0], 1u);
+            else                                  atomicAdd(&H[b], 1ull);
+          } else atomicOr(flags, 4);
+        }
+      }
+    }
+  }
+  #pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    vmin = fmin(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+    vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+  }
+  if (lane == 0) { smin[warp] = vmin; smax[warp] = vmax; }
+  __syncthreads();
+  if (do_hist)
+    for (int t = threadIdx.x; t < CH_SMEM_BINS && b0 + t < nbins; t += CH_TJ)
+      if (sh[t]) atomicAdd(&H[b0 + t], (unsigned long long) sh[t]);
+  if (threadIdx.x == 0) {
+    double a = smin[0], b = smax[0];
+    for (int t = 1; t < CH_TJ / 32; t++) { a = fmin(a, smin[t]); b = fmax(b, smax[t]); }
+    double *o = mm + (((size_t) z * nIT + it) * nJT + jt) * 2;
+    o[0] = a; o[1] = b;
+  }
+}
+
 // out[r][0..1] = min/max over the block partials
 __global__ void __launch_bounds__(256)
 minmax_final_kernel(const double *__restrict__ mm, int nblocks, double *__restrict__ out)
@@ -274,6 +352,20 @@ cudaError_t rsb_launch_correct_hist(double *cov, const double *covx, const doubl
   int nJT, nIT; rsb_corr_grid(L, &nJT, &nIT);
   rsb_coreside(correct_hist_kernel); correct_hist_kernel<<<dim3(nJT, nIT, nrep), CH_TJ, 0, st>>>(cov, covx, scal, L, Lp, actype, mode, bmin, wptr, hist, nbins, mm, flags, nJT, nIT, sr, sw, m2p, mind);
   rsb_coreside(minmax_final_kernel); minmax_final_kernel<<<nrep, 256, 0, st>>>(mm, nJT * nIT, minmax_out);
+  return cudaGetLastError();
+}
+
+// nrep x ncombo corrections + histograms in one launch; minmax_out[(r * ncombo + k) * 2]; mm scratch: nrep * ncombo * tiles * 2 doubles
+cudaError_t rsb_launch_correct_hist_multi(const double *cov, const double *covx, const double *scal, int nrep, int L, int Lp, int ncombo, int nw,
+                                          const int *kidx, const int *act, double bmin, const double *wptr, unsigned long long *hist, int nbins,
+                                          double *mm, double *minmax_out, int *flags, const int *m2p, int mind, cudaStream_t st)
+{
+  int nJT, nIT; rsb_corr_grid(L, &nJT, &nIT);
+  ComboTab tab;
+  for (int k = 0; k < 64; k++) { tab.kidx[k] = k < ncombo ? kidx[k] : 0; tab.act[k] = k < ncombo ? act[k] : RSB_NOCORR; }
+  rsb_coreside(correct_hist_multi_kernel);
+  correct_hist_multi_kernel<<<dim3(nJT, nIT, nrep * ncombo), CH_TJ, 0, st>>>(cov, covx, scal, L, Lp, tab, ncombo, nw, bmin, wptr, hist, nbins, mm, flags, nJT, nIT, m2p, mind);
+  rsb_coreside(minmax_final_kernel); minmax_final_kernel<<<nrep * ncombo, 256, 0, st>>>(mm, nJT * nIT, minmax_out);
   return cudaGetLastError();
 }
 

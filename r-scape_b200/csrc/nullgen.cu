@@ -583,6 +583,157 @@ replay_level_row_kernel(const int *__restrict__ left, const int *__restrict__ ri
   }
 }
 
+// Position form of the replay (RSCAPE_B200_REPLAY=position): one warp per (replicate, branch) of one tree level.
+//   pass 1   one coalesced pass over three rows: the shuffled parent row is copied to the child (msamanip.c:1645) while the Fitch
+//            rows of parent and child are compared word by word; the (rare) differences are counted per (source, target) class,
+//            n[a->d] (:1634-1643).
+//   place    substitution number s of the branch (in the canonical order a-major, d) belongs to lane s % 32; the lane draws columns
+//            uniformly until it hits one that holds its source class in the shuffled parent row and has not been substituted yet
+//            on this branch (child byte still equal to the parent's), all lanes of a round in parallel, two lanes on the same
+//            column resolved towards the lower lane.  Each acceptance picks uniformly among the still-free columns of the class,
+//            so the placement is a uniformly random injection of the substitutions into the columns of their source class --
+//            the distribution of the reference's Fisher-Yates shuffle of the position list (:1718-1757) -- and the counts are
+//            reproduced exactly.  A lane still without a column after RPP_ROUNDS rounds (a source class that is rare in the row)
+//            selects exactly: the warp counts the free columns of the class and takes the one of a uniformly drawn rank.
+// Work per branch: 3 rows read + 1 written, a handful of instructions per word, plus ~L/m_a probes per substitution: a few
+// times less issue work than the rank form above, and 256 bytes of shared memory per warp instead of 7 KB.
+constexpr int RPP_WARPS  = 8;
+constexpr int RPP_ROUNDS = 48;
+
+template <int W>
+__global__ void __launch_bounds__(RPP_WARPS * 32)
+replay_level_pos_kernel(const int *__restrict__ left, const int *__restrict__ right, const int *__restrict__ order, int lvl_begin, int lvl_count,
+                        int N, int L, const uint8_t *__restrict__ msa, unsigned long long seed, unsigned long long id0, const unsigned long long *__restrict__ ids,
+                        int first_rep, int nrep, const uint8_t *__restrict__ ancbuf, uint8_t *__restrict__ shancbuf, uint8_t *__restrict__ res)
+{
+  __shared__ int nsub_all[RPP_WARPS][64];                                       // [25] n[a->d], then [26] their exclusive prefix sums
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int *nsub = nsub_all[warp], *cum = nsub_all[warp] + 32;
+  const long long task = (long long) blockIdx.x * RPP_WARPS + warp;
+  if (task >= 2LL * lvl_count * nrep) return;                                   // whole warp
+  const int side = (int) (task & 1);
+  const long long nt = task >> 1;
+  const int rr = (int) (nt / lvl_count);
+  const int r = first_rep + rr;
+  const uint32_t rid = (uint32_t) (ids ? ids[rr] : id0 + (unsigned long long) rr);
+  const int v = order[lvl_begin + (int) (nt % lvl_count)];
+  const uint8_t *anc = ancbuf + (size_t) r * (N - 1) * L;
+  uint8_t *shanc = shancbuf + (size_t) r * (N - 1) * L;
+  uint8_t *leaves = res + (size_t) r * N * L;
+  const uint8_t *par_o = anc + (size_t) v * L;
+  const uint8_t *par_s = shanc + (size_t) v * L;
+  const int ch = side ? right[v] : left[v];
+  const uint8_t *kid_o = (ch > 0) ? anc + (size_t) ch * L : msa + (size_t) (-ch) * L;
+  uint8_t *kid_s = (ch > 0) ? shanc + (size_t) ch * L : leaves + (size_t) (-ch) * L;
+  const int LW = (L + W - 1) / W;
+  const unsigned lt = (1u << lane) - 1u;
+
+  nsub[lane] = 0;
+  __syncwarp();
+  // ---- pass 1: copy + compare
+  auto load = [&](const uint8_t *row, int u) -> uint32_t {
+    if (W == 4) return __ldcg(reinterpret_cast<const uint32_t *>(row) + u);
+    return (uint32_t) row[u] | 0xFFFFFF00u;
+  };
+  for (int u0 = 0; u0 < LW; u0 += 64) {                                         // two units per lane in flight
+    uint32_t wp[2], wk[2], ws[2];
+    #pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int u = u0 + h * 32 + lane;
+      const bool in = u < LW;
+      wp[h] = in ? load(par_o, u) : 0xFFFFFFFFu;
+      wk[h] = in ? load(kid_o, u) : 0xFFFFFFFFu;
+      ws[h] = in ? load(par_s, u) : 0u;
+    }
+    #pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int u = u0 + h * 32 + lane;
+      if (u < LW) {
+        if (W == 4) reinterpret_cast<uint32_t *>(kid_s)[u] = ws[h];
+        else kid_s[u] = (uint8_t) ws[h];
+      }
+      if (wp[h] != wk[h]) {
+        #pragma unroll
+        for (int q = 0; q < W; q++) {
+          const int pa = (wp[h] >> (8 * q)) & 0xFF, kd = (wk[h] >> (8 * q)) & 0xFF;
+          if (pa != kd && pa <= 4 && kd <= 4) atomicAdd(&nsub[pa * 5 + kd], 1);
+        }
+      }
+    }
+  }
+  __syncwarp();
+  // exclusive prefix sums of the 25 counts (lane k holds n_k)
+  {
+    const int nk = (lane < 25) ? nsub[lane] : 0;
+    int incl = nk;
+    #pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    cum[lane] = incl - nk;                                                      // cum[25..31] = total
+  }
+  __syncwarp();
+  const int ktot = cum[25];
+  if (ktot == 0) return;                                                        // uniform: most branches of a shallow tree
+
+  // ---- place
+  Philox ph; ph.key[0] = (uint32_t) seed ^ (0xC2B2AE35u * (rid + 1u)); ph.key[1] = (uint32_t) (seed >> 32) ^ 0x5bd1e995u;
+  uint32_t sd[4]; ph.block((uint32_t) v, 0x7ee1u + (uint32_t) side, 0x9051u + (uint32_t) lane, 0u, sd);
+  Pcg32 rng; rng.state = ((unsigned long long) sd[0] << 32) | sd[1]; rng.inc = ((((unsigned long long) sd[2] << 32) | sd[3]) << 1) | 1ULL;
+  rng.next();
+  volatile uint8_t *kid_v = kid_s;
+  #pragma unroll 1
+  for (int base = 0; base < ktot; base += 32) {
+    const int sidx = base + lane;
+    bool pending = sidx < ktot;
+    int a = 0, d = 0;
+    if (pending) {
+      int k = 0;
+      while (k < 24 && cum[k + 1] <= sidx) k++;                                 // the (a, d) this substitution belongs to
+      a = k / 5; d = k % 5;
+    }
+    #pragma unroll 1
+    for (int round = 0; round < RPP_ROUNDS && __any_sync(0xffffffffu, pending); round++) {
+      unsigned key = 0x80000000u | (unsigned) lane;                            // lanes without a valid candidate never match anyone
+      int c = 0;
+      if (pending) {
+        c = (int) __umulhi(rng.next(), (uint32_t) L);
+        const int xp = par_s[c], xk = kid_v[c];
+        if (xp == a && xk == xp) key = (unsigned) c;
+      }
+      const unsigned same = __match_any_sync(0xffffffffu, key);
+      if (pending && !(key & 0x80000000u) && (same & lt) == 0u) { kid_v[c] = (uint8_t) d; pending = false; }
+      __syncwarp();
+    }
+    // exact selection for whoever is still waiting (rare source class): one lane at a time, the whole warp scans the row
+    unsigned waiting = __ballot_sync(0xffffffffu, pending);
+    while (waiting) {
+      const int src = __ffs(waiting) - 1;
+      waiting &= waiting - 1;
+      const int      aa = __shfl_sync(0xffffffffu, a, src), dd = __shfl_sync(0xffffffffu, d, src);
+      const uint32_t rn = __shfl_sync(0xffffffffu, rng.next(), src);
+      int nfree = 0;
+      for (int c0 = 0; c0 < L; c0 += 32) {
+        const int c = c0 + lane;
+        const bool fr = c < L && par_s[c] == aa && kid_v[c] == aa;
+        nfree += __popc(__ballot_sync(0xffffffffu, fr));
+      }
+      if (nfree == 0) continue;                                                 // cannot happen: the parent row holds >= k_a columns of class a
+      int target = (int) __umulhi(rn, (uint32_t) nfree);
+      for (int c0 = 0; c0 < L; c0 += 32) {
+        const int c = c0 + lane;
+        const bool fr = c < L && par_s[c] == aa && kid_v[c] == aa;
+        const unsigned bal = __ballot_sync(0xffffffffu, fr);
+        const int n = __popc(bal);
+        if (target < n) {
+          if (fr && __popc(bal & lt) == target) kid_v[c] = (uint8_t) dd;
+          break;
+        }
+        target -= n;
+      }
+      __syncwarp();
+    }
+  }
+}
+
 } // namespace
 
 cudaError_t rsb_launch_null_simulate(const int *left, const int *right, const int *order, const int *level_start_host, int nlevels,
@@ -642,9 +793,19 @@ cudaError_t rsb_launch_fitch_shuffle(const int *left, const int *right, const in
     else            fitch_down_level_kernel<1><<<dim3((L + 127) / 128, cnt, nrep), 128, 0, st>>>(left, right, order, b, N, L, seed, id0, ids, first_rep, sets, sets_stride, anc);
   }
   permute_root_kernel<<<dim3((L + 255) / 256, nrep), 256, 0, st>>>(N, L, first_rep, anc, shanc, perm);
+  // RSCAPE_B200_REPLAY=position selects the position-form kernel (same distribution, tested side by side; faster when a branch
+  // carries few substitutions, slower on the bench family, whose leaf branches carry ~200 each: 52 vs 27 ms per 100 SSU replicates)
+  const char *form = getenv("RSCAPE_B200_REPLAY");
+  const bool rank_form = !(form && form[0] == 'p');
   for (int lv = 0; lv < nlevels; lv++) {
     const int b = level_start_host[lv], cnt = level_start_host[lv + 1] - b;
     const long long tasks = 2LL * cnt * nrep;                    // branches of this level over all replicates
+    if (!rank_form) {
+      const unsigned grid = (unsigned) ((tasks + RPP_WARPS - 1) / RPP_WARPS);
+      if (L % 4 == 0) replay_level_pos_kernel<4><<<grid, RPP_WARPS * 32, 0, st>>>(left, right, order, b, cnt, N, L, msa, seed, id0, ids, first_rep, nrep, anc, shanc, res);
+      else            replay_level_pos_kernel<1><<<grid, RPP_WARPS * 32, 0, st>>>(left, right, order, b, cnt, N, L, msa, seed, id0, ids, first_rep, nrep, anc, shanc, res);
+      continue;
+    }
     const int code_words = (L + 7) / 8;
     const size_t smem = (size_t) RPR_WARPS * (5 * code_words + 32) * sizeof(unsigned);
     int ws_log2 = 0; while ((32 << ws_log2) < L / 4) ws_log2++;   // words per lane segment (power of two)

@@ -29,8 +29,10 @@
 #define RSB_EPI_GROUPS 2        // groups of 4 epilogue warps in the tcgen05 kernel (gram_tcgen05.cu)
 #endif
 #ifndef RSB_GRAM_BOUND
-#define RSB_GRAM_BOUND 0        // thread count declared in the tcgen05 kernel's __launch_bounds__ when larger than its real one: caps its
-#endif                          // registers (65536 / bound) so that blocks of the statistics chain fit beside it
+#define RSB_GRAM_BOUND 512      // thread count declared in the tcgen05 kernel's __launch_bounds__ when larger than its real one: caps its
+#endif                          // registers (65536 / bound = 128, no spills) so that blocks of the statistics chain fit beside it.  Uncapped,
+                                // the pair-per-thread record epilogue takes 154 registers x 384 threads = 90 % of the SM's file, no block of
+                                // gt_finish / correct_hist can be co-resident and the chain only runs between two contractions
 // pair-tile of the HBM-bound passes (marginals, statistic, correction, histogram): a block owns
 // RSB_TI rows x RSB_TJ columns of the upper triangle, one thread per column j
 #define RSB_TI     16

@@ -383,7 +383,7 @@ stat_kernel(const long long *__restrict__ cnt, const double *__restrict__ pm, co
 // to its own matrix; each is computed by the very functions the single-statistic kernel uses (pair_statistic / gt_c16_raw), so a
 // matrix equals that kernel's.  Row/column partials and the score range come from reduce_cov_kernel afterwards (same tiling,
 // same summation order as stat_kernel's own).
-struct MultiOut { double *cov[6]; };                                 // CHI, OMES, GT, MI, MIr, MIg; NULL = not requested
+struct MultiOut { double *cov[6]; size_t rep_stride; };             // CHI, OMES, GT, MI, MIr, MIg (NULL = not requested); doubles between replicates
 template <int CLS>
 __global__ void __launch_bounds__(ST_TJ)
 multi_stat_kernel(const long long *__restrict__ cnt, const double *__restrict__ pm, const double2 *__restrict__ gtab, int L, int Lp,
@@ -416,7 +416,7 @@ multi_stat_kernel(const long long *__restrict__ cnt, const double *__restrict__ 
   for (int il = 0; il < ST_TI; il++) {
     const int i = it * ST_TI + il;
     if (i >= L || i >= j) continue;
-    const size_t off = (size_t) i * Lp + j, o = (size_t) r * plane + off;
+    const size_t off = (size_t) i * Lp + j, o = (size_t) r * out.rep_stride + off;
     PairProbs P;
     load_pair<false>(c, plane, off, scale, wtot, P);
     if (out.cov[0]) out.cov[0][o] = pair_statistic<RSB_CHI,  CLS == RSB_CWC ? RSB_C16 : CLS>(P, pmi[il], mj, lpmi[il], lmj, mask, tab);
@@ -792,15 +792,16 @@ cudaError_t rsb_launch_statistic(int stat, int cls, const long long *cnt, const 
   return cudaGetLastError();
 }
 
-// cov6[k] (k = CHI, OMES, GT, MI, MIr, MIg; NULL = skip): raw statistic matrices [nrep][L][Lp] of the counts in cnt
+// cov6[k] (k = CHI, OMES, GT, MI, MIr, MIg; NULL = skip): raw statistic matrices [L][Lp] of the counts in cnt, rep_stride doubles apart per replicate
 cudaError_t rsb_launch_multi_statistic(int cls, const long long *cnt, const double *pm, const void *logtab_, int nrep, int L, int Lp, double scale,
-                                       long long wtot, unsigned mask, double *const *cov6, int sr, int sw, cudaStream_t st)
+                                       long long wtot, unsigned mask, double *const *cov6, size_t rep_stride, int sr, int sw, cudaStream_t st)
 {
   int nJT, nIT; rsb_stat_grid(L, &nJT, &nIT);
   dim3 grid(nJT, nIT, nrep);
   const double2 *logtab = (const double2 *) logtab_;
   MultiOut out;
   for (int k = 0; k < 6; k++) out.cov[k] = cov6[k];
+  out.rep_stride = rep_stride;
   switch (cls) {
   case RSB_C16: rsb_coreside(multi_stat_kernel<RSB_C16>); multi_stat_kernel<RSB_C16><<<grid, ST_TJ, 0, st>>>(cnt, pm, logtab, L, Lp, scale, wtot, mask, out, sr, sw); break;
   case RSB_C2:  rsb_coreside(multi_stat_kernel<RSB_C2>);  multi_stat_kernel<RSB_C2><<<grid, ST_TJ, 0, st>>>(cnt, pm, logtab, L, Lp, scale, wtot, mask, out, sr, sw); break;

@@ -22,6 +22,15 @@ def ks_stat(a, b):
     return float(np.max(np.abs(ca - cb)))
 
 
+@pytest.fixture(params=["rank", "position"])
+def replay_form(request, monkeypatch):
+    """Generator A's replay step has two kernels (nullgen.cu): the rank-table form (default) and the position form
+    (RSCAPE_B200_REPLAY=position: copy the shuffled parent row, re-place each substitution on a uniformly drawn free column of its
+    source class).  Same distribution, same exact invariants: the tests below run on both."""
+    monkeypatch.setenv("RSCAPE_B200_REPLAY", request.param)
+    return request.param
+
+
 def _setup(ctx, po, N, L, seed, R):
     msa, wgt, _ = po.synthetic_msa(N, L, seed=seed)
     tree = po.random_tree(N, np.random.default_rng(seed))
@@ -43,7 +52,7 @@ def _branch_subs(tree, allrows, N):
 
 
 # ------------------------------------------------------------------------------------------------ generator A
-def test_fitch_shuffle_identical_sequences_is_a_column_permutation(ctx, po):
+def test_fitch_shuffle_identical_sequences_is_a_column_permutation(ctx, po, replay_form):
     N, L = 12, 50
     row = np.random.default_rng(1).integers(0, 5, L).astype(np.uint8)
     msa = np.tile(row, (N, 1))
@@ -71,7 +80,7 @@ def test_fitch_shuffle_is_keyed_by_replicate_id(ctx, po):
     assert a.max() <= 4                                                      # only residues and gaps, never N (msamanip.c:1634-1645)
 
 
-def test_fitch_shuffle_distribution_matches_oracle(ctx, pkg, po, oracle):
+def test_fitch_shuffle_distribution_matches_oracle(ctx, pkg, po, oracle, replay_form):
     N, L, R = 48, 90, 24
     msa, wgt, tree = _setup(ctx, po, N, L, 7, R)
     ctx.null_fitch_shuffle(msa, seed=11, nrep=R)
@@ -141,7 +150,7 @@ def _check_generator_a_invariants(ctx, tree, msa, R):
 
 
 @pytest.mark.parametrize("N,L,kernel", [(48, 92, "<4,seg>"), (40, 120, "<4,seg>"), (24, 4096, "<4,ballot>"), (48, 90, "<1,ballot>")])
-def test_fitch_shuffle_exact_invariants_every_kernel_variant(ctx, po, N, L, kernel):
+def test_fitch_shuffle_exact_invariants_every_kernel_variant(ctx, po, N, L, kernel, replay_form):
     """The replay kernel variant depends on L (nullgen.cu: L % 4 == 0 && L <= 4092 -> segment form, L % 4 == 0 -> word/ballot,
     else byte/ballot); every BASELINE shape takes the first.  Exact invariants on each."""
     R = 6
@@ -152,7 +161,7 @@ def test_fitch_shuffle_exact_invariants_every_kernel_variant(ctx, po, N, L, kern
 
 
 @pytest.mark.parametrize("N,L", [(48, 92), (40, 120)])
-def test_fitch_shuffle_distribution_matches_oracle_word_kernels(ctx, pkg, po, oracle, N, L):
+def test_fitch_shuffle_distribution_matches_oracle_word_kernels(ctx, pkg, po, oracle, N, L, replay_form):
     """The KS battery of test_fitch_shuffle_distribution_matches_oracle at L % 4 == 0, i.e. on the kernels every BASELINE
     shape runs: fitch_up/down_level_kernel<4> and replay_level_row_kernel<4, segment form>."""
     R = 24
@@ -180,7 +189,7 @@ def test_fitch_shuffle_distribution_matches_oracle_word_kernels(ctx, pkg, po, or
         assert abs(a - b) <= 0.08 * max(1.0, abs(b)) + 0.5, (qt, a, b)
 
 
-def test_fitch_shuffle_distribution_long_alignment_ballot_kernel(ctx, pkg, po, oracle):
+def test_fitch_shuffle_distribution_long_alignment_ballot_kernel(ctx, pkg, po, oracle, replay_form):
     """L > 4092 with L % 4 == 0: replay_level_row_kernel<4, ballot form> against the oracle (composition, leaf distances)."""
     N, L, R = 24, 4096, 8
     msa, wgt, tree = _setup(ctx, po, N, L, 5, R)
@@ -201,7 +210,7 @@ def test_fitch_shuffle_distribution_long_alignment_ballot_kernel(ctx, pkg, po, o
     assert np.max(np.abs(dg - dc)) < 0.02
 
 
-def test_fitch_shuffle_byte_and_word_kernels_agree(ctx, pkg, po, oracle):
+def test_fitch_shuffle_byte_and_word_kernels_agree(ctx, pkg, po, oracle, replay_form):
     """<1> (L % 4 != 0) against <4> on the same input: an appended all-gap column changes the kernel variant but carries no
     substitution and never makes two leaves differ, so leaf-pair differences must have the same distribution."""
     N, L, R = 48, 92, 32
@@ -223,7 +232,7 @@ def test_fitch_shuffle_byte_and_word_kernels_agree(ctx, pkg, po, oracle):
     assert abs(pd(a).mean() - pd(b).mean()) < 0.02 * pd(a).mean() + 0.2
 
 
-def test_fitch_shuffle_exact_invariants_at_the_ssu_shape(ctx, pkg):
+def test_fitch_shuffle_exact_invariants_at_the_ssu_shape(ctx, pkg, replay_form):
     """The BASELINE config 3 shape itself (N = 10000, L = 1800): every one of the 19 998 branches of two replicates keeps its
     5x5 substitution table; the root row is a permutation; only residues and gaps come out."""
     N, L, R = 10000, 1800, 2
@@ -319,7 +328,7 @@ def test_pool_scan_equals_host_scan(ctx, pkg, po, oracle):
 
 
 # ------------------------------------------------------------------------------------------------ plumbing of generator A
-def test_fitch_shuffle_is_deterministic_and_chunk_independent(ctx, po):
+def test_fitch_shuffle_is_deterministic_and_chunk_independent(ctx, po, replay_form):
     """Replicates are keyed by their global id: generating them in one call, again, or one by one into other pool
     entries gives the same alignments (the generation stream works in chunks of growing size)."""
     msa, wgt, tree = _setup(ctx, po, 60, 44, seed=9, R=24)

@@ -80,12 +80,35 @@ def test_multi_on_pool_entries_and_accumulation(ctx, pkg, po):
     assert ctx.hist_read_multi(1, 1000)[1] == 0
 
 
-def test_multi_rejects_unweighted_statistics(ctx, pkg, po):
+def test_multi_unit_weight_statistics_share_their_own_contraction(ctx, pkg, po, oracle):
+    """RAF / RAFS (unweighted, src/correlators.c:877-982) x corrections from one unit-weight contraction per null: identical to the
+    single-statistic loops, which are bit-exact against the reference's O(N^2) loop (test_gpu_scan_parity::test_raf_bit_exact)."""
+    N, L, R = 90, 40, 4
+    wgt = po.synthetic_msa(N, L, seed=2)[1]
+    nulls = np.stack([po.synthetic_msa(N, L, seed=40 + r)[0] for r in range(R)])
+    ctx.configure(N, L, 2, 0)
+    ctx.set_weights(wgt)
+    combos = [(pkg.RAFS, pkg.APC), (pkg.RAFS, pkg.ASC), (pkg.RAF, pkg.APC), (pkg.RAFS, pkg.NOCORR)]
+    w = [0.01, 0.01, 0.01, 0.01]
+    ctx.hist_reset_multi()
+    mm = ctx.null_hist_multi(nulls, combos, w)
+    for k, (st, ac) in enumerate(combos):
+        ctx.hist_reset()
+        mm1 = ctx.null_hist(nulls, w[k], st, pkg.C16, ac)
+        bins1, n1, _ = ctx.hist_read(6000)
+        bins, n, _ = ctx.hist_read_multi(k, 6000)
+        assert n == n1 == R * L * (L - 1) // 2 == int(bins.sum())
+        assert np.array_equal(bins, bins1) and np.array_equal(mm[k], mm1), (st, ac)
+
+
+def test_multi_rejects_what_cannot_share_a_contraction(ctx, pkg, po):
     N, L = 60, 30
     ctx.configure(N, L, 2, 0)
     ctx.set_weights(None)
     nulls = po.synthetic_msa(N, L, seed=1)[0][None]
     with pytest.raises(pkg.RscapeB200Error):
-        ctx.null_hist_multi(nulls, [(pkg.RAFS, pkg.APC)], [0.05])
+        ctx.null_hist_multi(nulls, [(pkg.RAFS, pkg.APC), (pkg.MI, pkg.APC)], [0.05, 0.05])   # unit-weight and weighted counts
+    with pytest.raises(pkg.RscapeB200Error):
+        ctx.null_hist_multi(nulls, [(pkg.CCF, pkg.APC)], [0.05])
     with pytest.raises(pkg.RscapeB200Error):
         ctx.null_hist_multi(nulls, [(pkg.MI, pkg.APC)], [0.05], pkg.CWC)       # CWC is defined for the G test only

@@ -43,4 +43,14 @@ for S in slices:
     c = ctx.counters(reset=True)
     print(f"{os.path.basename(pkg.LIB_PATH)} fused={os.environ.get('RSCAPE_B200_FUSED_GT', '1')} {name} S={S}: gram {c['gram_ms'] / max(1, c['gram_launches']):.3f} ms/launch "
           f"({c['gram_launches']} launches), loop {wall / nrep:.3f} ms/replicate", flush=True)
+    # the input alignment's path (count epilogue + stat_kernel + correction, results staying on the device)
+    ctx.scan(msa[0], want_cov=False)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        ctx.scan(msa[0], want_cov=False)
+    torch.cuda.synchronize()
+    print(f"   rsb_scan of a device-resident alignment, no host outputs: {(time.perf_counter() - t0) * 200:.3f} ms", flush=True)
+    if os.environ.get("RSCAPE_B200_TRACE"):
+        ctx.counters()
     ctx.close()
