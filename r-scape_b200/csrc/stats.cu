@@ -440,7 +440,11 @@ multi_stat_kernel(const long long *__restrict__ cnt, const double *__restrict__ 
 // (corr_CalculateGT_C16, src/correlators.c:383-387; pairs with nseff = 0 carry an all-zero record and score 0, as the
 // reference's `exp > 0 && obs > 0` guard leaves them).  64 B read + 8 B written per pair and 14 multiply-adds: HBM-bound, so
 // unlike stat_kernel it can run beside the contraction.  Same tiling, partial sums and min/max as stat_kernel.
-__global__ void __launch_bounds__(ST_TJ, 5)
+#ifndef RSB_FIN_U
+#define RSB_FIN_U 2             // rows whose 8 record planes a thread loads together; 2 -> <= 64 registers, 8 blocks per SM: the ~960 live tiles
+#define RSB_FIN_BLOCKS 8        // of the SSU shape fit in ONE wave (4 rows / 5 blocks: 1.3 waves, the second nearly empty)
+#endif
+__global__ void __launch_bounds__(ST_TJ, RSB_FIN_BLOCKS)
 gt_finish_kernel(const double *__restrict__ rec, const double *__restrict__ pm, int L, int Lp, double *__restrict__ cov,
                  double *__restrict__ rowpart, double *__restrict__ colpart, double *__restrict__ mm, int nJT, int nIT, int sr, int sw,
                  size_t slot_stride)
@@ -474,7 +478,7 @@ gt_finish_kernel(const double *__restrict__ rec, const double *__restrict__ pm, 
 
   // the kernel runs beside the persistent tcgen05 kernel, at a few blocks per SM: the loads of FIN_U rows (8 planes each) are
   // issued together so that the few resident warps keep enough bytes in flight
-  constexpr int FIN_U = 4;
+  constexpr int FIN_U = RSB_FIN_U;
   #pragma unroll 1
   for (int il0 = 0; il0 < ST_TI; il0 += FIN_U) {
     double q[FIN_U][8];

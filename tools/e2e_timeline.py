@@ -15,6 +15,7 @@ pkg = ge.load_package()
 N, L, R = 10000, 1800, 100
 msa, wgt, _, tree = pkg.synth.synthetic_family(N, L, seed=42)
 ctx = pkg.Context(0, torch.cuda.current_stream().cuda_stream)
+ctx.set_null_slices(int(sys.argv[1]) if len(sys.argv) > 1 else 0)
 ctx.configure(N, L, 2, 4)
 ctx.set_weights(wgt)
 ctx.pool_reserve(R)
@@ -41,6 +42,6 @@ def step(sync_between):
     return [round((b - a) * 1e3, 2) for a, b in ((t0, t1), (t1, t2), (t2, t3), (t3, t4), (t4, t5), (t0, t5))]
 
 
-for sync_between in (1, 0, 1, 0):
+for sync_between in (1, 0, 1, 0, 1, 0):
     print("sync" if sync_between else "overlap", "enqueue-gen, wait, width, nulls, read, TOTAL =", step(sync_between), flush=True)
 ctx.close()

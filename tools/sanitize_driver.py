@@ -26,15 +26,17 @@ for S, Snull in ((4, 0), (4, 2), (2, 0), (1, 0)):
     ctx.scan(msa, pkg.GT, pkg.CWC, pkg.NOCORR)
     ctx.hist_reset()
     w, _, _ = ctx.null_width(nulls[0])
-    ctx.null_hist(nulls, w)                                        # record epilogue (pair-per-thread form for S = 1, 2, 4)
-    ctx.null_hist(nulls, 0.01, pkg.MI, pkg.C16, pkg.ASC)           # count epilogue + stat_kernel
     ctx.null_hist(nulls, 0.01, pkg.RAFS)
+    ctx.null_hist(nulls, 0.01, pkg.MI, pkg.C16, pkg.ASC)           # count epilogue + stat_kernel
+    ctx.last_nseff()
+    ctx.null_hist(nulls, w)                                        # record epilogue (pair-per-thread form for S = 1, 2, 4)
     ctx.hist_read(4000)
     ctx.last_nseff()
     combos = [(pkg.GT, pkg.APC), (pkg.MI, pkg.ASC), (pkg.CHI, pkg.APC), (pkg.OMES, pkg.NOCORR), (pkg.MIr, pkg.APC), (pkg.MIg, pkg.APC)]
     ctx.hist_reset_multi()
     ctx.null_hist_multi(nulls, combos, [0.05, 0.001, 0.05, 0.01, 0.001, 0.001])
     ctx.hist_read_multi(2, 1000)
+    ctx.null_hist_multi(nulls, [(pkg.RAFS, pkg.APC), (pkg.RAF, pkg.ASC)], [0.01, 0.01])
     # generators + pool
     ctx.set_tree(tree.left, tree.right, tree.parent, tree.ld, tree.rd)
     ctx.pool_reserve(R)
@@ -58,7 +60,8 @@ for S, Snull in ((4, 0), (4, 2), (2, 0), (1, 0)):
 po = ge.load_oracle()
 ora = po.Oracle()
 r = ora.rng(3)
-_, allm, _ = ora.null_fitch_shuffle(r, tree, msa, want_all=True)
+_, _, _, otree = po.synthetic_family(N, L, seed=5)              # the oracle's own tree type (same family, same seed)
+_, allm, _ = ora.null_fitch_shuffle(r, otree, msa, want_all=True)
 ora.rng_free(r)
 ctx = pkg.Context(0)
 ctx.configure(2 * (N - 1), L, 1, 1)
