@@ -217,6 +217,16 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    # stdout carries exactly ONE line, the JSON line: libraries that print there (NCCL's version banner under NCCL_DEBUG, torchrun's
+    # children) are sent to stderr for the duration of the run
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+
     import torch
     import torch.distributed as dist
 
@@ -355,7 +365,7 @@ def main():
                                      unit_weight_ms=cnt["geometry"][1]["gram_ms"] / max(1, cnt["geometry"][1]["gram_launches"]),
                                      unit_weight_launches=cnt["geometry"][1]["gram_launches"],
                                      share_of_step=cnt["gram_ms"] / (ms * (args.steps + args.warmup) / args.steps)))
-        print(json.dumps(line))
+        emit(line)
         ctx.close()
         return 0
 
@@ -558,7 +568,7 @@ def main():
                                                 e2e=dict(value=alt["e2e_value"], ms_per_step=alt["ms_e2e"] / alt["steps"]),
                                                 roofline={k: alt["roofline"][k] for k in ("achieved", "peak", "unit", "frac", "gram_ms", "gram_slices", "gram_share_of_step")},
                                                 histogram_mass_ok=bool(alt["hist_ok"]))
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -377,19 +377,56 @@ stat_kernel(const long long *__restrict__ cnt, const double *__restrict__ pm, co
 #endif
 }
 
+// The six 16-class statistics of one pair from ONE set of 16 logs and no per-cell division (multi_stat_kernel).  With
+// d = pp - pm_i pm_j per cell (obs - exp = ne d, exp = ne pm_i pm_j; src/correlators.c:150-159, 283-292, 383-387, 583-590, 712-722, 842-849):
+//     CHI = ne sum d^2 / (pm_i pm_j)    OMES = ne sum d^2    MI = sum pp (log pp - log pm_i - log pm_j)    GT = 2 ne MI
+//     MIr = MI / H (H = -sum pp log pp > 1e-2, else 0)      MIg = MI - ngap / ne
+// rmi / rmj are the reciprocals of the marginals, taken once per column like their logs.  The guards of the reference (exp > 0,
+// obs > 0, pp > 0, pm > 0) reduce to ne > 0: pp and pm are positive because of the 1e-10 prior.  The values differ from
+// pair_statistic's (the reference's operation order) by rounding only, ~1e-15 relative; tests/test_gpu_multi.py bounds it.
+__device__ __forceinline__ void multi_c16(const PairProbs &P, const double *mi, const double *mj, const double *rmi, const double *rmj,
+                                          const double *lmi, const double *lmj, const double2 *__restrict__ tab, double *o)
+{
+  double chi = 0.0, om0 = 0.0, om1 = 0.0, m0 = 0.0, m1 = 0.0, h0 = 0.0, h1 = 0.0;
+  #pragma unroll
+  for (int x = 0; x < 4; x++) {
+    double cx = 0.0;
+    #pragma unroll
+    for (int y = 0; y < 4; y++) {
+      const double pxy = P.pp[x * 4 + y];
+      const double d   = fma(-mi[x], mj[y], pxy);
+      const double d2  = d * d;
+      cx = fma(d2, rmj[y], cx);
+      const double lp = fast_log<false>(pxy, tab);
+      const double t  = (lp - lmi[x]) - lmj[y];
+      if (y & 1) { om1 += d2; m1 = fma(pxy, t, m1); h1 = fma(pxy, lp, h1); }
+      else       { om0 += d2; m0 = fma(pxy, t, m0); h0 = fma(pxy, lp, h0); }
+    }
+    chi = fma(cx, rmi[x], chi);
+  }
+  const double mi_v = m0 + m1, H = -(h0 + h1);
+  const bool live = P.ne > 0.0;
+  o[0] = live ? P.ne * chi : 0.0;
+  o[1] = live ? P.ne * (om0 + om1) : 0.0;
+  o[2] = live ? 2.0 * P.ne * mi_v : 0.0;
+  o[3] = mi_v;
+  o[4] = (H > 1e-2) ? mi_v / H : 0.0;
+  o[5] = mi_v - (live ? P.ng / P.ne : 0.0);
+}
+
 // Several statistics of one (weighted) count table in one pass -- BASELINE config 5 sweeps MI, MIr, MIg, CHI, OMES and GT over the
 // same alignments, and cov_Calculate's dispatch (src/covariation.c:100-258) differs only in which corr_Calculate* it calls on
 // the probabilities of one corr_Probs.  The 128 B of counts per pair are read once and every requested raw statistic is written
-// to its own matrix; each is computed by the very functions the single-statistic kernel uses (pair_statistic / gt_c16_raw), so a
-// matrix equals that kernel's.  Row/column partials and the score range come from reduce_cov_kernel afterwards (same tiling,
-// same summation order as stat_kernel's own).
+// to its own matrix.  16 classes: multi_c16 (one set of logs for all six).  2 classes: the very pair_statistic code of the
+// single-statistic kernel.  Row/column partials and the score range come from reduce_cov_kernel afterwards (same tiling, same
+// summation order as stat_kernel's own).
 struct MultiOut { double *cov[6]; size_t rep_stride; };             // CHI, OMES, GT, MI, MIr, MIg (NULL = not requested); doubles between replicates
 template <int CLS>
 __global__ void __launch_bounds__(ST_TJ)
 multi_stat_kernel(const long long *__restrict__ cnt, const double *__restrict__ pm, const double2 *__restrict__ gtab, int L, int Lp,
                   double scale, long long wtot, unsigned mask, MultiOut out, int sr, int sw)
 {
-  __shared__ double pmi[ST_TI][4], lpmi[ST_TI][4];
+  __shared__ double pmi[ST_TI][4], lpmi[ST_TI][4], rpmi[ST_TI][4];
   __shared__ double2 tab[LOGTAB_N];
   const int jt = blockIdx.x, it = blockIdx.y, r = blockIdx.z;
   const int j  = jt * ST_TJ + threadIdx.x;
@@ -398,18 +435,19 @@ multi_stat_kernel(const long long *__restrict__ cnt, const double *__restrict__ 
   const bool tile_live = (it * ST_TI) < (jt * ST_TJ + ST_TJ - 1) && RSB_OWNED(it, sr, sw);
   if (!tile_live) return;
   logtab_load(tab, gtab);
-  double mj[4] = { 0.25, 0.25, 0.25, 0.25 }, lmj[4];
+  double mj[4] = { 0.25, 0.25, 0.25, 0.25 }, lmj[4], rmj[4];
   if (threadIdx.x < ST_TI * 4) {
     const int il = threadIdx.x >> 2, a = threadIdx.x & 3, i = it * ST_TI + il;
     pmi[il][a]  = (i < L) ? pm[((size_t) r * L + i) * 4 + a] : 0.25;
     lpmi[il][a] = (pmi[il][a] > 0.0) ? log(pmi[il][a]) : 0.0;
+    rpmi[il][a] = (pmi[il][a] > 0.0) ? 1.0 / pmi[il][a] : 0.0;
   }
   if (j < L) {
     #pragma unroll
     for (int b = 0; b < 4; b++) mj[b] = pm[((size_t) r * L + j) * 4 + b];
   }
   #pragma unroll
-  for (int b = 0; b < 4; b++) lmj[b] = (mj[b] > 0.0) ? log(mj[b]) : 0.0;
+  for (int b = 0; b < 4; b++) { lmj[b] = (mj[b] > 0.0) ? log(mj[b]) : 0.0; rmj[b] = (mj[b] > 0.0) ? 1.0 / mj[b] : 0.0; }
   __syncthreads();
   if (j >= L) return;
   #pragma unroll 1
@@ -419,6 +457,13 @@ multi_stat_kernel(const long long *__restrict__ cnt, const double *__restrict__ 
     const size_t off = (size_t) i * Lp + j, o = (size_t) r * out.rep_stride + off;
     PairProbs P;
     load_pair<false>(c, plane, off, scale, wtot, P);
+    if (CLS == RSB_C16) {                                 // all six from one set of logs
+      double v[6];
+      multi_c16(P, pmi[il], mj, rpmi[il], rmj, lpmi[il], lmj, tab, v);
+      #pragma unroll
+      for (int k = 0; k < 6; k++) if (out.cov[k]) out.cov[k][o] = v[k];
+      continue;
+    }
     if (out.cov[0]) out.cov[0][o] = pair_statistic<RSB_CHI,  CLS == RSB_CWC ? RSB_C16 : CLS>(P, pmi[il], mj, lpmi[il], lmj, mask, tab);
     if (out.cov[1]) out.cov[1][o] = pair_statistic<RSB_OMES, CLS == RSB_CWC ? RSB_C16 : CLS>(P, pmi[il], mj, lpmi[il], lmj, mask, tab);
     if (out.cov[2]) {

@@ -62,3 +62,17 @@ def test_raf_bit_exact(ctx, pkg, po, oracle, stat, ac):
         assert np.array_equal(got["cov"][iu], direct[iu])
     ref = oracle.scan(msa, wgt, getattr(po, stat), po.C2, getattr(po, ac))
     assert _close(got["cov"], ref["cov"]) <= TOL
+
+
+def test_validation_failure_is_reported(ctx, pkg, po):
+    """corr_ValidateProbs / corr_Marginals fail when a marginal does not sum to 1 within tol (src/correlators.c:1363, 1500-1545:
+    esl_vec_DValidate -> eslFAIL "pm validation failed").  A tolerance no sum can meet must make the device scan fail the same
+    way (the flag set by marg_norm_kernel), and the context must stay usable afterwards."""
+    N, L = 120, 37
+    msa, wgt, _ = po.synthetic_msa(N, L, seed=4)
+    ctx.configure(N, L, 1, 0)
+    ctx.set_weights(wgt)
+    with pytest.raises(pkg.RscapeB200Error, match="validation failed"):
+        ctx.scan(msa, pkg.GT, pkg.C16, pkg.APC, tol=-1.0)
+    got = ctx.scan(msa, pkg.GT, pkg.C16, pkg.APC)          # the flag is cleared: the next scan succeeds
+    assert np.isfinite(got["maxcov"])

@@ -13,7 +13,7 @@ if [ "$N" != 1 ]; then
 fi
 for f in gpurun_out/r2_bench_ssu_${N}gpu.json gpurun_out/r2_bench_ssu_mixed_${N}gpu.json gpurun_out/r2_bench_lsu_${N}gpu.json gpurun_out/r2_bench_lsu_gridshard_${N}gpu.json; do
   [ -s $f ] && python -c "
-import json,sys; d=json.load(open('$f')); print('$f'.split('/')[-1], 'value %.3g ms %.2f e2e %.3g ms %.2f frac %.3f share %.2f' % (d['value'], d['ms_per_step'], d['e2e']['value'], d['e2e']['ms_per_step'], d['roofline']['frac'], d['roofline']['gram_share_of_step']))"
+import json,sys; d=[json.loads(l) for l in open('$f') if l[0]=='{'][-1]; print('$f'.split('/')[-1], 'value %.3g ms %.2f e2e %.3g ms %.2f frac %.3f share %.2f' % (d['value'], d['ms_per_step'], d['e2e']['value'], d['e2e']['ms_per_step'], d['roofline']['frac'], d['roofline']['gram_share_of_step']))"
 done
 grep -h "phases" gpurun_out/r2_bench_ssu_${N}gpu.err | tail -$((2*N))
 tail -3 gpurun_out/r2_bench_lsu_${N}gpu.err
