@@ -21,7 +21,10 @@
 
 namespace {
 
-constexpr int NSTAGE       = 4;
+#ifndef RSB_NSTAGE
+#define RSB_NSTAGE 4                          // TMA ring depth (48 KB per stage at S = 4)
+#endif
+constexpr int NSTAGE       = RSB_NSTAGE;
 constexpr int GRAM_THREADS = 256;              // CTA-pair kernel: warps 0-3 roles, warps 4-7 epilogue
 // single-CTA kernel: RSB_EPI_GROUPS groups of 4 epilogue warps; group g drains the columns [g, g+1) * cpg of every tile, so that
 // the latency of one tile's epilogue -- what the MMAs of the tile after next wait for -- is divided by the number of groups
