@@ -513,8 +513,9 @@ def main():
                              f"run (dram__bytes of the ncu --set full capture: profiles/)",
                         gram_ms=gram_ms_avg, gram_slices=S_dom,
                         gram_share_of_step=cnt["gram_ms"] / (ms_dev * (steps + warmup) / steps) if ms_dev > 0 else None)
+        comm = ctx.comm_info() if world > 1 else None
         ctx.close()
-        return dict(value=value, ms_dev=ms_dev, e2e_value=e2e_value, ms_e2e=ms_e2e, h2d=h2d, d2h=d2h, roofline=roofline, clocks=clocks, cnt=cnt,
+        return dict(comm=comm, value=value, ms_dev=ms_dev, e2e_value=e2e_value, ms_e2e=ms_e2e, h2d=h2d, d2h=d2h, roofline=roofline, clocks=clocks, cnt=cnt,
                     hist_ok=hist_ok, nbins=int(len(bins_chk)), slots=slots, t_gen=t_gen, q_abs=q_abs, q_bits=q_bits, s_null=s_null,
                     qn_abs=qn_abs, qn_bits=qn_bits, steps=steps, warmup=warmup)
 
@@ -561,6 +562,10 @@ def main():
                              ms_per_step=ms_e2e / args.steps),
                     gpu_launches=int(cnt["launches"] * args.steps / (args.steps + args.warmup)),
                     clocks=clocks, roofline=roofline, cpu_baseline=cpu)
+        if m["comm"] is not None:
+            # how the small vectors crossed the GPUs: the library's one-shot kernel over NVLink peer memory (csrc/peer_reduce.cu) or NCCL
+            line["config"]["collectives"] = dict(small_vectors="one-shot all-reduce kernel over NVLink peer memory" if m["comm"]["peer_path"] else "ncclAllReduce",
+                                                 peer_reductions=m["comm"]["reductions"], histogram="ncclAllReduce (uint64 bins, once per job)")
         if alt is not None:
             # the same job in the other precision mode, measured in the same run (not the headline)
             line["other_precision_mode"] = dict(precision=mode_text(alt), null_weight_slices=alt["s_null"], value=alt["value"],

@@ -167,6 +167,11 @@ int rsb_comm_id(uint8_t *id128);
 int rsb_comm_init(rsb_ctx *ctx, const uint8_t *id128, int nranks, int rank);
 int rsb_comm_init_all(rsb_ctx **ctxs, int n);
 int rsb_comm_destroy(rsb_ctx *ctx);
+/* The per-scan vectors of a sharded pair grid (marginal sums [L][4], APC row sums [L+4], score range) are summed over the ranks
+ * by a one-shot kernel over NVLink peer memory (csrc/peer_reduce.cu) when the ranks can map each other's memory
+ * (cudaIpc between processes, peer access inside one), else by ncclAllReduce; RSCAPE_B200_PEER_REDUCE=0 forces NCCL.
+ * *peer_path = 1 when the kernel is in use, *reductions = all-reduces it has done so far. */
+int rsb_comm_info(rsb_ctx *ctx, int *nranks, int *rank, int *peer_path, int64_t *reductions);
 int rsb_hist_allreduce(rsb_ctx *ctx, int nb);
 /* in place: lo = min over ranks, hi = max over ranks, aux_min (may be NULL) = min over ranks */
 int rsb_comm_range(rsb_ctx *ctx, double *lo, double *hi, double *aux_min);

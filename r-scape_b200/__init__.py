@@ -116,6 +116,7 @@ def lib():
         L.rsb_comm_init.argtypes = [_vp, _u8p, C.c_int, C.c_int]
         L.rsb_comm_init_all.argtypes = [C.POINTER(_vp), C.c_int]
         L.rsb_comm_destroy.argtypes = [_vp]
+        L.rsb_comm_info.argtypes = [_vp, _ip, _ip, _ip, _i64p]
         L.rsb_hist_allreduce.argtypes = [_vp, C.c_int]
         L.rsb_comm_range.argtypes = [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.rsb_sharded_scan.argtypes = [_vp, _vp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.c_double, _dp, _dp, _dp]
@@ -370,6 +371,13 @@ class Context:
 
     def comm_destroy(self):
         self._ck(lib().rsb_comm_destroy(self._h))
+
+    def comm_info(self):
+        """dict(nranks, rank, peer_path, reductions): peer_path = the small per-scan all-reduces go through the one-shot kernel
+        over NVLink peer memory (csrc/peer_reduce.cu) rather than NCCL; reductions = how many it has done."""
+        n, r, p, k = C.c_int(), C.c_int(), C.c_int(), C.c_int64()
+        self._ck(lib().rsb_comm_info(self._h, C.byref(n), C.byref(r), C.byref(p), C.byref(k)))
+        return dict(nranks=n.value, rank=r.value, peer_path=bool(p.value), reductions=k.value)
 
     def hist_allreduce(self, nb):
         """Sum the first nb bins of the device histograms of all ranks, in place (null_add2cumranklist across ranks)."""

@@ -4,6 +4,7 @@
 // the only host synchronisations are the D2H reads the caller asked for.  There is no CPU path:
 // rsb_create fails unless a compute-capability-10.x device is present.
 #include "rsb_common.cuh"
+#include "peer_reduce.h"
 #include "rsb_evalue.cuh"
 #include "nccl_dyn.h"
 #include "../../include/rscape_b200.h"
@@ -146,6 +147,11 @@ struct rsb_ctx {
   double *d_meanp = nullptr, *d_w = nullptr, *d_blocksum = nullptr, *d_msum = nullptr, *d_covsum = nullptr;
   int shard_rank = 0, shard_world = 1;  // row-block sharding of the pair grid across ranks
   rsb_nccl::ncclComm_t comm = nullptr; int comm_rank = 0, comm_size = 1;   // NCCL communicator over the ranks / devices of the job (rsb_comm_*)
+  // one-shot all-reduce of the per-scan vectors over peer memory (peer_reduce.cu): this rank's exchange block, the peers' blocks as
+  // mapped here, the sequence number of the last all-reduce and the event that serialises them
+  void *peer_block = nullptr; void *peer_map[RSB_PEER_MAX] = { nullptr }; bool peer_ipc = false;
+  RsbPeerView peer_view; int peer_state = 0;       // 0 not tried, 1 in use, -1 unavailable (NCCL all-reduce instead)
+  unsigned long long peer_seq = 0, peer_reductions = 0; cudaEvent_t ev_peer = nullptr;
   cudaStream_t stream_aux = nullptr, stream_aux2 = nullptr, stream_copy = nullptr;     // statistics (one per slot group) / uploads of the pipelined null loop
   cudaEvent_t ev_entry = nullptr, ev_up[2] = { nullptr, nullptr }, ev_counts[2] = { nullptr, nullptr }, ev_stats[2] = { nullptr, nullptr },
               ev_marg[2] = { nullptr, nullptr }, ev_statk[2] = { nullptr, nullptr };
@@ -554,10 +560,91 @@ SlotPtrs slot_ptrs(rsb_ctx *c, int s0)
   return p;
 }
 
-// in-place all-reduce over the job's ranks on stream st (no-op without a communicator of more than one rank)
+// ---- exchange blocks of the one-shot all-reduce (peer_reduce.cu)
+void peer_teardown(rsb_ctx *ctx)
+{
+  if (ctx->peer_ipc) for (int q = 0; q < RSB_PEER_MAX; q++) if (ctx->peer_map[q]) cudaIpcCloseMemHandle(ctx->peer_map[q]);
+  for (int q = 0; q < RSB_PEER_MAX; q++) ctx->peer_map[q] = nullptr;
+  if (ctx->peer_block) cudaFree(ctx->peer_block);
+  ctx->peer_block = nullptr; ctx->peer_ipc = false; ctx->peer_state = 0; ctx->peer_seq = 0;
+}
+
+void peer_fill_view(rsb_ctx *ctx, void *const *blocks, size_t cap)
+{
+  RsbPeerView &v = ctx->peer_view;
+  v.W = ctx->comm_size; v.rank = ctx->comm_rank; v.cap = cap;
+  for (int q = 0; q < ctx->comm_size; q++) {
+    v.x[q]    = (double *) blocks[q];
+    v.flag[q] = (unsigned long long *) ((char *) blocks[q] + 2 * (size_t) ctx->comm_size * cap * sizeof(double));
+  }
+}
+
+// One process per GPU: every rank allocates its block, the cudaIpc handles travel by an NCCL all-gather, every rank maps the
+// others' blocks, and an NCCL all-reduce of a flag makes the ranks agree on whether all of them succeeded (a rank that fell back
+// to NCCL alone would deadlock the others).  Collective: every rank calls it at the same point (the first small all-reduce).
+int peer_setup_ipc(rsb_ctx *ctx, size_t need)
+{
+  rsb_nccl::Api &a = rsb_nccl::api();
+  const int W = ctx->comm_size;
+  if (ctx->peer_block) RSB_CUDA_OK(cudaDeviceSynchronize());          // (re-sizing: nothing of this rank may still use the old block)
+  peer_teardown(ctx);
+  ctx->peer_state = -1;
+  if (getenv("RSCAPE_B200_PEER_REDUCE") && atoi(getenv("RSCAPE_B200_PEER_REDUCE")) == 0) return 0;
+  if (W > RSB_PEER_MAX || !a.AllGather) return 0;
+  const size_t cap = std::max(need, (size_t) 4 * ctx->L * std::max(1, ctx->Rcap) + 64);
+  const size_t bytes = rsb_peer_block_bytes(W, cap);
+  long long ok = 1;
+  cudaIpcMemHandle_t mine;
+  char *d_h = nullptr; long long *d_ok = nullptr;
+  std::vector<cudaIpcMemHandle_t> all(W);
+  void *blocks[RSB_PEER_MAX] = { nullptr };
+  if (cudaMalloc(&ctx->peer_block, bytes) != cudaSuccess) { cudaGetLastError(); ctx->peer_block = nullptr; ok = 0; }
+  if (ok && cudaMemsetAsync(ctx->peer_block, 0, bytes, ctx->stream) != cudaSuccess) ok = 0;
+  memset(&mine, 0, sizeof(mine));
+  if (ok && cudaIpcGetMemHandle(&mine, ctx->peer_block) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+  RSB_CUDA_OK(cudaMalloc(&d_h, sizeof(cudaIpcMemHandle_t) * (W + 1)));
+  RSB_CUDA_OK(cudaMalloc(&d_ok, sizeof(long long)));
+  RSB_CUDA_OK(cudaMemcpyAsync(d_h + sizeof(mine) * W, &mine, sizeof(mine), cudaMemcpyHostToDevice, ctx->stream));
+  int rc = a.AllGather(d_h + sizeof(mine) * W, d_h, sizeof(mine), 0 /* ncclInt8 */, ctx->comm, ctx->stream);
+  if (rc == rsb_nccl::ncclSuccess) {
+    RSB_CUDA_OK(cudaMemcpyAsync(all.data(), d_h, sizeof(mine) * W, cudaMemcpyDeviceToHost, ctx->stream));
+    RSB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    for (int q = 0; q < W && ok; q++) {
+      if (q == ctx->comm_rank) { blocks[q] = ctx->peer_block; continue; }
+      if (cudaIpcOpenMemHandle(&ctx->peer_map[q], all[q], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ctx->peer_map[q] = nullptr; ok = 0; }
+      blocks[q] = ctx->peer_map[q];
+    }
+    ctx->peer_ipc = true;
+  } else ok = 0;
+  // agreement (and a barrier: every rank's block is zeroed before anyone pushes into it)
+  RSB_CUDA_OK(cudaMemcpyAsync(d_ok, &ok, sizeof(ok), cudaMemcpyHostToDevice, ctx->stream));
+  rc = a.AllReduce(d_ok, d_ok, 1, rsb_nccl::ncclInt64, rsb_nccl::ncclMin, ctx->comm, ctx->stream);
+  if (rc != rsb_nccl::ncclSuccess) { cudaFree(d_h); cudaFree(d_ok); rsb_set_error(ctx, "ncclAllReduce: %s", a.GetErrorString(rc)); return 1; }
+  RSB_CUDA_OK(cudaMemcpyAsync(&ok, d_ok, sizeof(ok), cudaMemcpyDeviceToHost, ctx->stream));
+  RSB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  cudaFree(d_h); cudaFree(d_ok);
+  if (!ok) { peer_teardown(ctx); ctx->peer_state = -1; return 0; }
+  peer_fill_view(ctx, blocks, cap);
+  ctx->peer_state = 1;
+  return 0;
+}
+
+// in-place all-reduce over the job's ranks on stream st (no-op without a communicator of more than one rank).  Small fp64 vectors
+// (sum / max) go through the one-shot kernel over peer memory when the ranks could map each other's exchange blocks.
 int comm_allreduce(rsb_ctx *ctx, void *buf, size_t count, int dtype, int op, cudaStream_t st)
 {
   if (!ctx->comm || ctx->comm_size <= 1) return 0;
+  if (dtype == rsb_nccl::ncclFloat64 && (op == rsb_nccl::ncclSum || op == rsb_nccl::ncclMax) && count <= ((size_t) 1 << 20)) {
+    if (ctx->peer_state == 0 && peer_setup_ipc(ctx, count)) return 1;                   // (collective: the first small all-reduce of every rank)
+    if (ctx->peer_state == 1 && count <= ctx->peer_view.cap) {                            // (a vector beyond the block's capacity: NCCL, on every rank alike)
+      if (!ctx->ev_peer) RSB_CUDA_OK(cudaEventCreateWithFlags(&ctx->ev_peer, cudaEventDisableTiming));
+      if (ctx->peer_seq > 0) RSB_CUDA_OK(cudaStreamWaitEvent(st, ctx->ev_peer, 0));       // the all-reduces of a rank are serialised
+      RSB_CUDA_OK(rsb_launch_peer_allreduce((double *) buf, count, op == rsb_nccl::ncclMax, ctx->peer_view, ++ctx->peer_seq, st));
+      RSB_CUDA_OK(cudaEventRecord(ctx->ev_peer, st));
+      ctx->launches++; ctx->peer_reductions++;
+      return 0;
+    }
+  }
   const int rc = rsb_nccl::api().AllReduce(buf, buf, count, dtype, op, ctx->comm, st);
   if (rc != rsb_nccl::ncclSuccess) { rsb_set_error(ctx, "ncclAllReduce: %s", rsb_nccl::api().GetErrorString(rc)); return 1; }
   ctx->launches++;
@@ -782,7 +869,8 @@ void rsb_destroy(rsb_ctx *ctx)
   for (auto &p : ctx->pending) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   for (auto &p : ctx->pending_aux) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   for (auto &p : ctx->pending_stage) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
-  if (ctx->comm) { rsb_nccl::api().CommDestroy(ctx->comm); ctx->comm = nullptr; }
+  if (ctx->comm) { cudaDeviceSynchronize(); peer_teardown(ctx); rsb_nccl::api().CommDestroy(ctx->comm); ctx->comm = nullptr; }
+  if (ctx->ev_peer) cudaEventDestroy(ctx->ev_peer);
   free_plan(ctx);
   if (ctx->d_logtab) cudaFree(ctx->d_logtab);
   cudaStreamSynchronize(ctx->stream_aux); cudaStreamSynchronize(ctx->stream_aux2); cudaStreamSynchronize(ctx->stream_copy); cudaStreamSynchronize(ctx->stream_gen);
@@ -2195,7 +2283,7 @@ int rsb_comm_init(rsb_ctx *ctx, const uint8_t *id128, int nranks, int rank)
   rsb_nccl::Api &a = rsb_nccl::api();
   if (!a.ok) { rsb_set_error(ctx, "NCCL is not available: %s", a.why); return 1; }
   if (nranks < 1 || rank < 0 || rank >= nranks) { rsb_set_error(ctx, "bad rank %d of %d", rank, nranks); return 1; }
-  if (ctx->comm) { a.CommDestroy(ctx->comm); ctx->comm = nullptr; }
+  if (ctx->comm) { cudaDeviceSynchronize(); peer_teardown(ctx); a.CommDestroy(ctx->comm); ctx->comm = nullptr; }
   rsb_nccl::ncclUniqueId id;
   memcpy(id.internal, id128, 128);
   const int rc = a.CommInitRank(&ctx->comm, nranks, id, rank);
@@ -2219,9 +2307,44 @@ int rsb_comm_init_all(rsb_ctx **ctxs, int n)
   const int rc = a.CommInitAll(comms.data(), n, devs.data());
   if (rc != rsb_nccl::ncclSuccess) { rsb_set_error(ctxs[0], "ncclCommInitAll: %s", a.GetErrorString(rc)); return 1; }
   for (int k = 0; k < n; k++) {
-    if (ctxs[k]->comm) a.CommDestroy(ctxs[k]->comm);
+    if (ctxs[k]->comm) { cudaSetDevice(devs[k]); cudaDeviceSynchronize(); peer_teardown(ctxs[k]); a.CommDestroy(ctxs[k]->comm); }
     ctxs[k]->comm = comms[k]; ctxs[k]->comm_rank = k; ctxs[k]->comm_size = n;
   }
+  // exchange blocks of the one-shot all-reduce: inside one process the devices map each other's memory directly
+  bool peer = n >= 2 && n <= RSB_PEER_MAX && !(getenv("RSCAPE_B200_PEER_REDUCE") && atoi(getenv("RSCAPE_B200_PEER_REDUCE")) == 0);
+  size_t cap = 0;
+  for (int k = 0; k < n && peer; k++) {
+    if (ctxs[k]->L <= 0) peer = false;
+    cap = std::max(cap, (size_t) 4 * ctxs[k]->L * std::max(1, ctxs[k]->Rcap) + 64);
+    for (int q = 0; q < n && peer; q++) {
+      int can = 0;
+      if (q != k && (cudaDeviceCanAccessPeer(&can, devs[k], devs[q]) != cudaSuccess || !can)) peer = false;
+    }
+  }
+  void *blocks[RSB_PEER_MAX] = { nullptr };
+  for (int k = 0; k < n && peer; k++) {
+    cudaSetDevice(devs[k]);
+    for (int q = 0; q < n; q++) if (q != k) { const cudaError_t e = cudaDeviceEnablePeerAccess(devs[q], 0); if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) peer = false; cudaGetLastError(); }
+    const size_t bytes = rsb_peer_block_bytes(n, cap);
+    if (peer && (cudaMalloc(&ctxs[k]->peer_block, bytes) != cudaSuccess || cudaMemset(ctxs[k]->peer_block, 0, bytes) != cudaSuccess)) { cudaGetLastError(); peer = false; }
+    blocks[k] = ctxs[k]->peer_block;
+  }
+  for (int k = 0; k < n; k++) {
+    cudaSetDevice(devs[k]);
+    if (peer) { cudaDeviceSynchronize(); peer_fill_view(ctxs[k], blocks, cap); ctxs[k]->peer_state = 1; }
+    else { peer_teardown(ctxs[k]); ctxs[k]->peer_state = -1; }
+  }
+  return 0;
+}
+
+/* how the small per-scan vectors are reduced: *peer_path = 1 one-shot kernel over peer memory, 0 NCCL (or not decided yet);
+ * *reductions = all-reduces done by that kernel so far */
+int rsb_comm_info(rsb_ctx *ctx, int *nranks, int *rank, int *peer_path, int64_t *reductions)
+{
+  if (nranks) *nranks = ctx->comm ? ctx->comm_size : 1;
+  if (rank) *rank = ctx->comm ? ctx->comm_rank : 0;
+  if (peer_path) *peer_path = ctx->peer_state == 1 ? 1 : 0;
+  if (reductions) *reductions = (int64_t) ctx->peer_reductions;
   return 0;
 }
 
@@ -2229,7 +2352,8 @@ int rsb_comm_destroy(rsb_ctx *ctx)
 {
   if (ctx->comm) {
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->stream_aux);
+    cudaDeviceSynchronize();
+    peer_teardown(ctx);
     rsb_nccl::api().CommDestroy(ctx->comm);
     ctx->comm = nullptr; ctx->comm_size = 1; ctx->comm_rank = 0;
   }

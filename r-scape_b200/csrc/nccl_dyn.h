@@ -20,6 +20,7 @@ struct Api {
   int (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
   int (*CommDestroy)(ncclComm_t) = nullptr;
   int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;     // optional (peer-memory setup)
   int (*GroupStart)() = nullptr;
   int (*GroupEnd)() = nullptr;
   const char *(*GetErrorString)(int) = nullptr;
@@ -41,6 +42,7 @@ inline Api &api()
   a.CommInitAll    = (int (*)(ncclComm_t *, int, const int *)) dlsym(h, "ncclCommInitAll");
   a.CommDestroy    = (int (*)(ncclComm_t)) dlsym(h, "ncclCommDestroy");
   a.AllReduce      = (int (*)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t)) dlsym(h, "ncclAllReduce");
+  a.AllGather      = (int (*)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t)) dlsym(h, "ncclAllGather");
   a.GroupStart     = (int (*)()) dlsym(h, "ncclGroupStart");
   a.GroupEnd       = (int (*)()) dlsym(h, "ncclGroupEnd");
   a.GetErrorString = (const char *(*)(int)) dlsym(h, "ncclGetErrorString");

@@ -5,7 +5,7 @@ set -e
 name=$1; shift
 cd "$(dirname "$0")/../r-scape_b200"
 mkdir -p build/alt/$name
-for f in gram_tcgen05 pack stats correct_hist hits treesubs nullgen msaprep capi; do
+for f in gram_tcgen05 pack stats correct_hist hits treesubs nullgen msaprep peer_reduce capi; do
   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC "$@" -c csrc/$f.cu -o build/alt/$name/$f.o &
 done
 wait
