@@ -599,5 +599,5 @@ def replicate_slots(nseq, alen, nnull, nslices=4, budget_bytes=24e9, sm_count=14
     tiles = (alen / 32.0) * (alen / cj) * 0.5 + 1.0
     per_rep = (4 + 4 * nslices) * alen * nseq + 16 * 8 * alen * alen + 3 * 8 * alen * alen + nseq * alen
     r = int(np.ceil(4.0 * sm_count / tiles))
-    r = max(r, 2)                       # two slot groups: statistics of one chunk overlap the contraction of the next
+    r = max(r, 4)                       # four slot groups: the statistics chain of a chunk has three contractions to finish in
     return int(max(1, min(r, int(budget_bytes // per_rep), max(nnull, 2), 64)))

@@ -113,6 +113,8 @@ struct Geo {
 };
 } // namespace
 
+constexpr int RSB_GROUPS = 4;          // slot groups of the pipelined null loop at most (alignments in flight: being packed / contracted / scored)
+
 struct rsb_ctx {
   int device = 0, sm_count = 0;
   cudaStream_t stream = nullptr;
@@ -151,10 +153,10 @@ struct rsb_ctx {
   // mapped here, the sequence number of the last all-reduce and the event that serialises them
   void *peer_block = nullptr; void *peer_map[RSB_PEER_MAX] = { nullptr }; bool peer_ipc = false;
   RsbPeerView peer_view; int peer_state = 0;       // 0 not tried, 1 in use, -1 unavailable (NCCL all-reduce instead)
-  unsigned long long peer_seq = 0, peer_reductions = 0; cudaEvent_t ev_peer = nullptr;
-  cudaStream_t stream_aux = nullptr, stream_aux2 = nullptr, stream_copy = nullptr;     // statistics (one per slot group) / uploads of the pipelined null loop
-  cudaEvent_t ev_entry = nullptr, ev_up[2] = { nullptr, nullptr }, ev_counts[2] = { nullptr, nullptr }, ev_stats[2] = { nullptr, nullptr },
-              ev_marg[2] = { nullptr, nullptr }, ev_statk[2] = { nullptr, nullptr };
+  unsigned long long peer_seq[RSB_PEER_CHANNELS] = { 0 }, peer_reductions = 0; cudaEvent_t ev_peer[RSB_PEER_CHANNELS] = { nullptr };
+  cudaStream_t stream_aux = nullptr, stream_aux2 = nullptr, stream_aux3 = nullptr, stream_aux4 = nullptr, stream_copy = nullptr;   // statistics (one per slot group) / uploads of the pipelined null loop
+  cudaEvent_t ev_entry = nullptr, ev_up[RSB_GROUPS] = { nullptr }, ev_counts[RSB_GROUPS] = { nullptr }, ev_stats[RSB_GROUPS] = { nullptr },
+              ev_marg[RSB_GROUPS] = { nullptr }, ev_statk[RSB_GROUPS] = { nullptr };
   unsigned long long *d_hist = nullptr, *d_colsum = nullptr;
   int *d_flags = nullptr;
   double *d_ps = nullptr, *d_pp_out = nullptr, *d_nseff_out = nullptr, *d_ngap_out = nullptr;
@@ -566,7 +568,8 @@ void peer_teardown(rsb_ctx *ctx)
   if (ctx->peer_ipc) for (int q = 0; q < RSB_PEER_MAX; q++) if (ctx->peer_map[q]) cudaIpcCloseMemHandle(ctx->peer_map[q]);
   for (int q = 0; q < RSB_PEER_MAX; q++) ctx->peer_map[q] = nullptr;
   if (ctx->peer_block) cudaFree(ctx->peer_block);
-  ctx->peer_block = nullptr; ctx->peer_ipc = false; ctx->peer_state = 0; ctx->peer_seq = 0;
+  ctx->peer_block = nullptr; ctx->peer_ipc = false; ctx->peer_state = 0;
+  for (int k = 0; k < RSB_PEER_CHANNELS; k++) ctx->peer_seq[k] = 0;
 }
 
 void peer_fill_view(rsb_ctx *ctx, void *const *blocks, size_t cap)
@@ -575,7 +578,7 @@ void peer_fill_view(rsb_ctx *ctx, void *const *blocks, size_t cap)
   v.W = ctx->comm_size; v.rank = ctx->comm_rank; v.cap = cap;
   for (int q = 0; q < ctx->comm_size; q++) {
     v.x[q]    = (double *) blocks[q];
-    v.flag[q] = (unsigned long long *) ((char *) blocks[q] + 2 * (size_t) ctx->comm_size * cap * sizeof(double));
+    v.flag[q] = (unsigned long long *) ((char *) blocks[q] + rsb_peer_doubles(ctx->comm_size, cap) * sizeof(double));
   }
 }
 
@@ -637,10 +640,12 @@ int comm_allreduce(rsb_ctx *ctx, void *buf, size_t count, int dtype, int op, cud
   if (dtype == rsb_nccl::ncclFloat64 && (op == rsb_nccl::ncclSum || op == rsb_nccl::ncclMax) && count <= ((size_t) 1 << 20)) {
     if (ctx->peer_state == 0 && peer_setup_ipc(ctx, count)) return 1;                   // (collective: the first small all-reduce of every rank)
     if (ctx->peer_state == 1 && count <= ctx->peer_view.cap) {                            // (a vector beyond the block's capacity: NCCL, on every rank alike)
-      if (!ctx->ev_peer) RSB_CUDA_OK(cudaEventCreateWithFlags(&ctx->ev_peer, cudaEventDisableTiming));
-      if (ctx->peer_seq > 0) RSB_CUDA_OK(cudaStreamWaitEvent(st, ctx->ev_peer, 0));       // the all-reduces of a rank are serialised
-      RSB_CUDA_OK(rsb_launch_peer_allreduce((double *) buf, count, op == rsb_nccl::ncclMax, ctx->peer_view, ++ctx->peer_seq, st));
-      RSB_CUDA_OK(cudaEventRecord(ctx->ev_peer, st));
+      // one channel per statistics stream (the chains of consecutive replicates overlap), channel 0 for everything else
+      const int ch = (st == ctx->stream_aux2) ? 1 : (st == ctx->stream_aux3) ? 2 : (st == ctx->stream_aux4) ? 3 : 0;
+      if (!ctx->ev_peer[ch]) RSB_CUDA_OK(cudaEventCreateWithFlags(&ctx->ev_peer[ch], cudaEventDisableTiming));
+      if (ctx->peer_seq[ch] > 0) RSB_CUDA_OK(cudaStreamWaitEvent(st, ctx->ev_peer[ch], 0));   // the all-reduces of a channel are serialised
+      RSB_CUDA_OK(rsb_launch_peer_allreduce((double *) buf, count, op == rsb_nccl::ncclMax, ctx->peer_view, ch, ++ctx->peer_seq[ch], st));
+      RSB_CUDA_OK(cudaEventRecord(ctx->ev_peer[ch], st));
       ctx->launches++; ctx->peer_reductions++;
       return 0;
     }
@@ -826,6 +831,8 @@ int rsb_create(int device, void *stream, rsb_ctx **out)
   else { cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking); c->own_stream = true; }
   cudaStreamCreateWithFlags(&c->stream_aux, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&c->stream_aux2, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&c->stream_aux3, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&c->stream_aux4, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&c->stream_copy, cudaStreamNonBlocking);
   {
     int lo = 0, hi = 0;
@@ -839,14 +846,14 @@ int rsb_create(int device, void *stream, rsb_ctx **out)
   c->gen_ring.resize(64);
   for (auto &e : c->gen_ring) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&c->ev_entry, cudaEventDisableTiming);
-  for (int g = 0; g < 2; g++) {
+  for (int g = 0; g < RSB_GROUPS; g++) {
     cudaEventCreateWithFlags(&c->ev_up[g], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->ev_counts[g], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->ev_stats[g], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->ev_marg[g], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->ev_statk[g], cudaEventDisableTiming);
   }
-  if ((e = cudaGetLastError()) != cudaSuccess || !c->stream || !c->stream_aux || !c->stream_aux2 || !c->stream_copy || !c->stream_gen || !c->stream_hi ||
+  if ((e = cudaGetLastError()) != cudaSuccess || !c->stream || !c->stream_aux || !c->stream_aux2 || !c->stream_aux3 || !c->stream_aux4 || !c->stream_copy || !c->stream_gen || !c->stream_hi ||
       !c->ev_exit || !c->ev_entry) {
     snprintf(g_create_err, sizeof(g_create_err), "rsb_create: streams / events: %s", cudaGetErrorString(e));
     delete c; return 1;
@@ -870,11 +877,12 @@ void rsb_destroy(rsb_ctx *ctx)
   for (auto &p : ctx->pending_aux) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   for (auto &p : ctx->pending_stage) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   if (ctx->comm) { cudaDeviceSynchronize(); peer_teardown(ctx); rsb_nccl::api().CommDestroy(ctx->comm); ctx->comm = nullptr; }
-  if (ctx->ev_peer) cudaEventDestroy(ctx->ev_peer);
+  for (int k = 0; k < RSB_PEER_CHANNELS; k++) if (ctx->ev_peer[k]) cudaEventDestroy(ctx->ev_peer[k]);
   free_plan(ctx);
   if (ctx->d_logtab) cudaFree(ctx->d_logtab);
-  cudaStreamSynchronize(ctx->stream_aux); cudaStreamSynchronize(ctx->stream_aux2); cudaStreamSynchronize(ctx->stream_copy); cudaStreamSynchronize(ctx->stream_gen);
-  cudaStreamDestroy(ctx->stream_aux2);
+  cudaStreamSynchronize(ctx->stream_aux); cudaStreamSynchronize(ctx->stream_aux2); cudaStreamSynchronize(ctx->stream_aux3); cudaStreamSynchronize(ctx->stream_aux4);
+  cudaStreamSynchronize(ctx->stream_copy); cudaStreamSynchronize(ctx->stream_gen);
+  cudaStreamDestroy(ctx->stream_aux2); cudaStreamDestroy(ctx->stream_aux3); cudaStreamDestroy(ctx->stream_aux4);
   cudaStreamDestroy(ctx->stream_aux); cudaStreamDestroy(ctx->stream_copy); cudaStreamDestroy(ctx->stream_gen); cudaStreamDestroy(ctx->stream_hi); cudaEventDestroy(ctx->ev_exit);
   for (auto &e : ctx->gen_ring) cudaEventDestroy(e);
   cudaEventDestroy(ctx->ev_entry);
@@ -1221,7 +1229,13 @@ static int null_hist_pipelined(rsb_ctx *ctx, const uint8_t *nulls, int nrep, int
   }
   if (ctx->shard_world > 1 && ctx->d_m2p) { rsb_set_error(ctx, "a pair exclusion (rsb_set_pair_exclusion) is not offered on a sharded pair grid"); return 1; }
   const bool in_place = (on_device && row_stride == ctx->L && rep_stride == (int64_t) ctx->N * ctx->L);
-  const int  G = (ctx->Rcap >= 2) ? 2 : 1;
+  // Slot groups: chunk c is contracted in group c % G, and the contraction of chunk c + G waits for the statistics chain of chunk c.
+  // The chain runs beside the contractions at a few blocks per SM, bound by latency (0.3 - 0.5 ms at the SSU shape whatever the share
+  // of the grid a rank owns): with two groups the loop's period is max(contraction, chain); with three or four groups (slots that
+  // are a multiple of 3 or 4) a chain has G - 1 contractions to finish in and consecutive chains overlap on their own streams.
+  if (grid_comm(ctx) && ctx->peer_state == 0 && peer_setup_ipc(ctx, (size_t) 4 * ctx->L * std::max(1, ctx->Rcap) + 64)) return 1;   // (collective)
+  static const int gmax = getenv("RSCAPE_B200_GROUPS") ? std::min(RSB_GROUPS, std::max(1, atoi(getenv("RSCAPE_B200_GROUPS")))) : RSB_GROUPS;
+  const int  G = std::min(gmax, (ctx->Rcap % 4 == 0 && ctx->Rcap >= 4) ? 4 : (ctx->Rcap % 3 == 0 && ctx->Rcap >= 3) ? 3 : (ctx->Rcap >= 2) ? 2 : 1);
   const int  chunk = std::max(1, ctx->Rcap / G);
   const size_t repbytes = (size_t) ctx->N * ctx->L;
   static const int serial = getenv("RSCAPE_B200_SERIAL") ? atoi(getenv("RSCAPE_B200_SERIAL")) : 0;      // experiments: 1 = statistics on the main stream, 2 = pack too
@@ -1231,9 +1245,12 @@ static int null_hist_pipelined(rsb_ctx *ctx, const uint8_t *nulls, int nrep, int
   cudaStream_t st_copy = (serial & 2) ? sm : ctx->stream_copy;
   // one statistics stream per slot group: the chains of consecutive chunks overlap each other (they run beside the
   // contraction at low occupancy, bound by latency rather than by a pipe)
-  // (with in-library collectives everything that talks to NCCL stays on ONE stream: same order of collectives on every rank)
-  const bool one_aux = grid_comm(ctx);
-  auto aux_of = [&](int g) -> cudaStream_t { return (serial & 1) ? sm : ((g & 1) && !one_aux) ? ctx->stream_aux2 : ctx->stream_aux; };
+  // (sharded grid: the one-shot all-reduce kernel has one ordered channel per statistics stream, so the chains keep their own
+  // streams; if the ranks could not map each other's memory everything that talks to NCCL stays on ONE stream -- same order of
+  // collectives on every rank)
+  const bool one_aux = grid_comm(ctx) && ctx->peer_state != 1;
+  cudaStream_t aux_streams[RSB_GROUPS] = { ctx->stream_aux, ctx->stream_aux2, ctx->stream_aux3, ctx->stream_aux4 };
+  auto aux_of = [&](int g) -> cudaStream_t { return (serial & 1) ? sm : one_aux ? ctx->stream_aux : aux_streams[g % RSB_GROUPS]; };
 
   if (minmax && ctx->h_mm_cap < (size_t) nrep) {
     if (ctx->h_mm) cudaFreeHost(ctx->h_mm);
@@ -1245,10 +1262,9 @@ static int null_hist_pipelined(rsb_ctx *ctx, const uint8_t *nulls, int nrep, int
   RSB_CUDA_OK(cudaStreamWaitEvent(sm, ctx->ev_entry, 0));
   RSB_CUDA_OK(cudaMemcpyAsync(ctx->d_w, &w, sizeof(double), cudaMemcpyHostToDevice, sm));
   RSB_CUDA_OK(cudaEventRecord(ctx->ev_entry, sm));
-  RSB_CUDA_OK(cudaStreamWaitEvent(ctx->stream_aux, ctx->ev_entry, 0));
-  RSB_CUDA_OK(cudaStreamWaitEvent(ctx->stream_aux2, ctx->ev_entry, 0));
+  for (int g = 0; g < RSB_GROUPS; g++) RSB_CUDA_OK(cudaStreamWaitEvent(aux_streams[g], ctx->ev_entry, 0));
   RSB_CUDA_OK(cudaStreamWaitEvent(st_copy, ctx->ev_entry, 0));
-  bool used[2] = { false, false };
+  bool used[RSB_GROUPS] = { false, false, false, false };
 
   // Stream plan.  The statistic kernel is FP64-bound, and FP64 issue collapses (~6x, measured) while the tensor pipe is
   // busy, so it runs ALONE on the main stream between two contractions; everything light (operand packing on the copy
@@ -2503,6 +2519,8 @@ int rsb_counters(rsb_ctx *ctx, int64_t *launches, double *gram_ms, int64_t *gram
   if (!ctx->pending_aux.empty()) {
     RSB_CUDA_OK(cudaStreamSynchronize(ctx->stream_aux));
     RSB_CUDA_OK(cudaStreamSynchronize(ctx->stream_aux2));
+    RSB_CUDA_OK(cudaStreamSynchronize(ctx->stream_aux3));
+    RSB_CUDA_OK(cudaStreamSynchronize(ctx->stream_aux4));
     for (size_t k = 0; k < ctx->pending_aux.size(); k++) {
       auto &p = ctx->pending_aux[k]; auto &q = ctx->pending_stage[k];
       float ms = 0.f;

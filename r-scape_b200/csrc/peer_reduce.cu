@@ -7,15 +7,19 @@
 // loop an NCCL kernel waits for a contraction to END before it starts -- three times per scan.  This kernel needs no shared memory
 // beyond a few words and runs beside the contraction:
 //
-//   every rank owns an exchange block  x[2][W][cap] doubles + flag[2][W][PEER_CTAS]  mapped into all ranks (cudaIpc handles
-//   between processes, direct peer access inside one process).  All-reduce number `seq` uses half seq & 1:
+//   every rank owns an exchange block  x[channel][2][W][cap] doubles + flag[channel][2][W][PEER_CTAS]  mapped into all ranks
+//   (cudaIpc handles between processes, direct peer access inside one process).  All-reduce number `seq` of a channel uses
+//   half seq & 1 of that channel:
 //     push   each CTA copies its chunk of the vector into x[half][my rank] of EVERY rank (stores over NVLink), fences, and
 //            sets flag[half][my rank][cta] = seq on every rank;
 //     wait   it spins until its own flag[half][q][cta] >= seq for every rank q;
 //     sum    it adds the W copies in rank order 0..W-1 -- the same order on every rank, so all ranks hold bit-identical
 //            results and the result does not depend on arrival order (no floating-point atomics).
-//   Two halves suffice because the all-reduces of a rank are serialised (an event chain in capi.cu): a rank can start number
-//   seq + 2 only after it has finished seq + 1, for which every peer must have pushed seq + 1, i.e. finished reading seq.
+//   Two halves suffice because the all-reduces of one channel are serialised on every rank (an event chain in capi.cu): a rank
+//   can start number seq + 2 only after it has finished seq + 1, for which every peer must have pushed seq + 1, i.e. finished
+//   reading seq.  Channels are independent sequences (own halves, flags and event chain): the statistics chains of consecutive
+//   replicates run on different streams and overlap, each with its own channel; every rank issues the same calls in the same
+//   order per channel.
 #include "rsb_common.cuh"
 #include "peer_reduce.h"
 
@@ -34,9 +38,9 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 
 template <int OP>     // 0 sum, 1 max
 __global__ void __launch_bounds__(RSB_PEER_THREADS)
-peer_allreduce_kernel(double *__restrict__ buf, int count, int chunk, RsbPeerView pv, unsigned long long seq)
+peer_allreduce_kernel(double *__restrict__ buf, int count, int chunk, RsbPeerView pv, int channel, unsigned long long seq)
 {
-  const int W = pv.W, me = pv.rank, half = (int) (seq & 1ULL), cta = blockIdx.x;
+  const int W = pv.W, me = pv.rank, half = channel * 2 + (int) (seq & 1ULL), cta = blockIdx.x;
   const int i0 = cta * chunk, i1 = min(count, i0 + chunk);
   // push my chunk to every rank (my own block included)
   for (int q = 0; q < W; q++) {
@@ -66,12 +70,12 @@ peer_allreduce_kernel(double *__restrict__ buf, int count, int chunk, RsbPeerVie
 
 } // namespace
 
-cudaError_t rsb_launch_peer_allreduce(double *buf, size_t count, int op_max, const RsbPeerView &pv, unsigned long long seq, cudaStream_t st)
+cudaError_t rsb_launch_peer_allreduce(double *buf, size_t count, int op_max, const RsbPeerView &pv, int channel, unsigned long long seq, cudaStream_t st)
 {
   int ctas = (int) ((count + 2047) / 2048);
   ctas = ctas < 1 ? 1 : (ctas > RSB_PEER_CTAS ? RSB_PEER_CTAS : ctas);
   const int chunk = (int) ((count + ctas - 1) / ctas);
-  if (op_max) peer_allreduce_kernel<1><<<ctas, RSB_PEER_THREADS, 0, st>>>(buf, (int) count, chunk, pv, seq);
-  else        peer_allreduce_kernel<0><<<ctas, RSB_PEER_THREADS, 0, st>>>(buf, (int) count, chunk, pv, seq);
+  if (op_max) peer_allreduce_kernel<1><<<ctas, RSB_PEER_THREADS, 0, st>>>(buf, (int) count, chunk, pv, channel, seq);
+  else        peer_allreduce_kernel<0><<<ctas, RSB_PEER_THREADS, 0, st>>>(buf, (int) count, chunk, pv, channel, seq);
   return cudaGetLastError();
 }
