@@ -2,10 +2,13 @@
 //
 // With the L x L pair grid of a scan dealt to the GPUs of the box, three vectors per scan are summed over the ranks: the marginal
 // partial sums [L][4], the APC row sums [L+4] and the score range (src/correlators.c:1338-1375, 1064-1157 are the loops whose
-// totals they are).  They are a few KB to ~100 KB: latency-bound.  An NCCL all-reduce needs a channel's worth of shared memory
-// on an SM, and the persistent tcgen05 contraction (gram_tcgen05.cu) leaves ~10 KB free on every SM, so inside the pipelined null
-// loop an NCCL kernel waits for a contraction to END before it starts -- three times per scan.  This kernel needs no shared memory
-// beyond a few words and runs beside the contraction:
+// totals they are).  They are a few KB to ~100 KB: latency-bound, and they sit inside the statistics chain of every replicate,
+// which runs beside the persistent tcgen05 contraction (gram_tcgen05.cu; ~10 KB of shared memory left per SM).  The chains of
+// consecutive replicates overlap on their own streams (capi.cu), so the reductions need (a) no shared memory, (b) an order that
+// is the same on every rank PER STREAM rather than globally, (c) results that are bit-identical on all ranks.  NCCL gives (c) only
+// by luck of its algorithm choice and wants all collectives of a communicator in one global order, i.e. all chains on one stream
+// (measured on 2 GPUs at the SSU shape: 51.8 ms per step against 43.7 with this kernel and one channel per stream; with a single
+// stream the two are equal).  The kernel:
 //
 //   every rank owns an exchange block  x[channel][2][W][cap] doubles + flag[channel][2][W][PEER_CTAS]  mapped into all ranks
 //   (cudaIpc handles between processes, direct peer access inside one process).  All-reduce number `seq` of a channel uses

@@ -17,3 +17,8 @@ import json,sys; d=[json.loads(l) for l in open('$f') if l[0]=='{'][-1]; print('
 done
 grep -h "phases" gpurun_out/r2_bench_ssu_${N}gpu.err | tail -$((2*N))
 tail -3 gpurun_out/r2_bench_lsu_${N}gpu.err
+if [ "$N" != 1 ]; then
+  RSCAPE_B200_PEER_REDUCE=0 run --workload lsu --grid-shard --steps 2 --warmup 3 --no-alt --no-cpu-baseline > gpurun_out/r2_bench_lsu_gridshard_${N}gpu_nccl.json 2>> gpurun_out/r2_bench_lsu_${N}gpu.err
+  python -c "
+import json; d=[json.loads(l) for l in open('gpurun_out/r2_bench_lsu_gridshard_${N}gpu_nccl.json') if l[0]=='{'][-1]; print('lsu grid-shard with ncclAllReduce: value %.3g ms %.2f e2e %.3g ms %.2f share %.2f' % (d['value'], d['ms_per_step'], d['e2e']['value'], d['e2e']['ms_per_step'], d['roofline']['gram_share_of_step']), d['config'].get('collectives'))"
+fi
