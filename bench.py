@@ -398,7 +398,15 @@ def main():
             """R-scape's default null model on the device: Fitch + tree-substitution shuffle (null_rscape, R-scape.c:1653-1661).
             Replicates are keyed by their global id: a rank generates exactly its own block (every rank all of them with --grid-shard)."""
             ctx.set_tree(tree.left, tree.right, tree.parent, tree.ld, tree.rd)
-            if n_mine:
+            if args.grid_shard and world > 1 and not os.environ.get("BENCH_GEN_ALL"):
+                # every rank scans every null: generate 1/world of them each and exchange the blocks over NVLink (rsb_pool_broadcast)
+                blocks = [pkg.parallel.null_shard(R, world, r) for r in range(world)]
+                if blocks[rank]:
+                    ctx.null_fitch_shuffle(host_msa.numpy(), SEED, len(blocks[rank]), first_rep=blocks[rank][0], first_id=blocks[rank][0])
+                for r, b in enumerate(blocks):
+                    if b:
+                        ctx.pool_broadcast(b[0], len(b), r)
+            elif n_mine:
                 ctx.null_fitch_shuffle(host_msa.numpy(), SEED, n_mine, first_rep=0, first_id=my_ids[0])
 
         def job(real):

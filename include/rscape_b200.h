@@ -167,6 +167,11 @@ int rsb_comm_id(uint8_t *id128);
 int rsb_comm_init(rsb_ctx *ctx, const uint8_t *id128, int nranks, int rank);
 int rsb_comm_init_all(rsb_ctx **ctxs, int n);
 int rsb_comm_destroy(rsb_ctx *ctx);
+/* pool entries [first_rep, first_rep + nrep) generated by rank `root` made resident on every rank (ncclBroadcast over NVLink, on the
+ * generation stream; scans of those entries wait for it).  With a sharded pair grid every rank scans every null: each rank generates
+ * its share (rsb_null_fitch_shuffle with first_id = first_rep = the block's first replicate) and every rank calls this once per
+ * block, in the same order. */
+int rsb_pool_broadcast(rsb_ctx *ctx, int first_rep, int nrep, int root);
 /* The per-scan vectors of a sharded pair grid (marginal sums [L][4], APC row sums [L+4], score range) are summed over the ranks
  * by a one-shot kernel over NVLink peer memory (csrc/peer_reduce.cu) when the ranks can map each other's memory
  * (cudaIpc between processes, peer access inside one), else by ncclAllReduce; RSCAPE_B200_PEER_REDUCE=0 forces NCCL.

@@ -2376,6 +2376,33 @@ int rsb_comm_destroy(rsb_ctx *ctx)
   return 0;
 }
 
+/* Null alignments generated by ONE rank made resident on all of them: pool entries [first_rep, first_rep + nrep) are broadcast from
+ * rank `root` over the communicator (NVLink), on the generation stream -- behind the generator calls already queued there -- and
+ * the entries' readiness events are renewed, so scans of those entries wait for the copy.  With a sharded pair grid every rank
+ * scans every null; each rank then generates 1/W of them and the blocks are exchanged (1.4 GB in all at the LSU shape) instead of
+ * every rank generating all of them.  Every rank calls this for every block, in the same order. */
+int rsb_pool_broadcast(rsb_ctx *ctx, int first_rep, int nrep, int root)
+{
+  RSB_RANGE("rsb_pool_broadcast");
+  RSB_CUDA_OK(cudaSetDevice(ctx->device));
+  if (pool_range_ok(ctx, first_rep, nrep)) return 1;
+  rsb_nccl::Api &a = rsb_nccl::api();
+  if (!ctx->comm || !a.Broadcast) { rsb_set_error(ctx, "rsb_pool_broadcast: no communicator (rsb_comm_init)"); return 1; }
+  if (root < 0 || root >= ctx->comm_size) { rsb_set_error(ctx, "rsb_pool_broadcast: bad root %d", root); return 1; }
+  cudaStream_t sg = ctx->stream_gen;
+  RSB_CUDA_OK(cudaEventRecord(ctx->ev_entry, ctx->stream));          // the caller's stream may still read these entries
+  RSB_CUDA_OK(cudaStreamWaitEvent(sg, ctx->ev_entry, 0));
+  const size_t rb = (size_t) ctx->N * ctx->L;
+  uint8_t *p = ctx->d_pool + (size_t) first_rep * rb;
+  const int rc = a.Broadcast(p, p, rb * (size_t) nrep, 0 /* ncclInt8 */, root, ctx->comm, sg);
+  if (rc != rsb_nccl::ncclSuccess) { rsb_set_error(ctx, "ncclBroadcast: %s", a.GetErrorString(rc)); return 1; }
+  cudaEvent_t e = ctx->gen_ring[ctx->gen_next++ % ctx->gen_ring.size()];
+  RSB_CUDA_OK(cudaEventRecord(e, sg));
+  for (int r = first_rep; r < first_rep + nrep; r++) ctx->pool_ready[r] = e;
+  ctx->launches++;
+  return 0;
+}
+
 /* null_add2cumranklist across ranks (src/R-scape.c:1565-1612): sum the first nb bins of the device histograms of all ranks in place */
 int rsb_hist_allreduce(rsb_ctx *ctx, int nb)
 {

@@ -21,6 +21,7 @@ struct Api {
   int (*CommDestroy)(ncclComm_t) = nullptr;
   int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;     // optional (peer-memory setup)
+  int (*Broadcast)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;  // optional (rsb_pool_broadcast)
   int (*GroupStart)() = nullptr;
   int (*GroupEnd)() = nullptr;
   const char *(*GetErrorString)(int) = nullptr;
@@ -43,6 +44,7 @@ inline Api &api()
   a.CommDestroy    = (int (*)(ncclComm_t)) dlsym(h, "ncclCommDestroy");
   a.AllReduce      = (int (*)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t)) dlsym(h, "ncclAllReduce");
   a.AllGather      = (int (*)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t)) dlsym(h, "ncclAllGather");
+  a.Broadcast      = (int (*)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t)) dlsym(h, "ncclBroadcast");
   a.GroupStart     = (int (*)()) dlsym(h, "ncclGroupStart");
   a.GroupEnd       = (int (*)()) dlsym(h, "ncclGroupEnd");
   a.GetErrorString = (const char *(*)(int)) dlsym(h, "ncclGetErrorString");

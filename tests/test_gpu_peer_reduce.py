@@ -98,3 +98,51 @@ def test_sharded_null_loop_peer_kernel_equals_nccl_and_unsharded(pkg, po, oracle
     assert not bins[view.nb:].any()
     assert_bins_identical(bins[:view.nb], view.obs, oscores, -10.0, w, scale=oscale)
     assert np.max(np.abs(peer[0][0] - mm_o)) <= 1e-9 * oscale
+
+
+def test_pool_broadcast_makes_every_rank_hold_all_nulls(pkg, po):
+    """rsb_pool_broadcast: each of two ranks generates its own block of nulls (generator A, keyed by the global replicate id), the
+    blocks are exchanged over NVLink, and both pools equal the pool of one rank that generated everything."""
+    if _ndev(pkg) < 2:
+        pytest.skip("needs two GPUs")
+    N, L, R = 120, 64, 6
+    msa, wgt, _, tree = pkg.synth.synthetic_family(N, L, seed=9)
+    whole = pkg.Context(0)
+    whole.configure(N, L, 2, 0)
+    whole.set_tree(tree.left, tree.right, tree.parent, tree.ld, tree.rd)
+    whole.pool_reserve(R)
+    whole.null_fitch_shuffle(msa, 77, R)
+    ref = whole.pool_get(R, 0)
+    whole.close()
+    ctxs = []
+    for k in range(2):
+        c = pkg.Context(k)
+        c.configure(N, L, 2, 0)
+        c.set_tree(tree.left, tree.right, tree.parent, tree.ld, tree.rd)
+        c.pool_reserve(R)
+        ctxs.append(c)
+    pkg.comm_init_all(ctxs)
+    blocks = [(0, 4), (4, 2)]
+    got, err = [None, None], [None, None]
+
+    def work(k):
+        try:
+            c = ctxs[k]
+            c.null_fitch_shuffle(msa, 77, blocks[k][1], first_rep=blocks[k][0], first_id=blocks[k][0])
+            for root, (f, n) in enumerate(blocks):
+                c.pool_broadcast(f, n, root)
+            got[k] = c.pool_get(R, 0)
+        except Exception as e:                                      # noqa: BLE001
+            err[k] = e
+
+    th = [threading.Thread(target=work, args=(k,)) for k in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=120)
+    assert not any(t.is_alive() for t in th), "broadcast hung"
+    for c in ctxs:
+        c.comm_destroy()
+        c.close()
+    assert err == [None, None], err
+    assert np.array_equal(got[0], ref) and np.array_equal(got[1], ref)
