@@ -396,7 +396,7 @@ replay_level_kernel(const int *__restrict__ left, const int *__restrict__ right,
 //   sweep 2  (shuffled parent row -> child row): a column of class a is the (running count of a)-th of its class; the
 //            code table says whether that rank was drawn and what it becomes (:1645-1757).
 // Work per branch is a few coalesced passes over its rows, independent of how the substitutions fall.
-constexpr int RPR_WARPS = 2;        // 2 warps x ~7 KB (code table + staged row at L = 1800): two such blocks fit beside the tcgen05 kernel's 190 KB ring
+constexpr int RPR_WARPS = 2;        // 2 warps x 3.2 KB (packed code table + staged row at L = 1800)
 
 template <int W, bool SEG>
 __global__ void __launch_bounds__(RPR_WARPS * 32)
@@ -407,9 +407,12 @@ replay_level_row_kernel(const int *__restrict__ left, const int *__restrict__ ri
   extern __shared__ unsigned rpr_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int WS = 1 << ws_log2, WSP = WS + 1;                                    // SEG: words per lane segment, padded stride (odd: no bank conflicts)
-  const int warp_words = 5 * code_words + 32 + (SEG ? 32 * WSP : 0);
-  unsigned *code = rpr_smem + (size_t) warp * warp_words;          // [5][code_words] nibbles: bit 3 = rank drawn, bits 2:0 = target
-  int *nsub = reinterpret_cast<int *>(code + 5 * code_words);                  // [25]
+  const int warp_words = code_words + 32 + (SEG ? 32 * WSP : 0);
+  // one nibble per column: bit 3 = rank drawn, bits 2:0 = target.  The five classes' tables are packed back to back -- class a
+  // starts at nibble m_0 + ... + m_{a-1}, the compositions sum to <= L -- so the table is L nibbles instead of 5 L: half the
+  // shared memory per warp, twice the resident warps of this latency-bound kernel
+  unsigned *code = rpr_smem + (size_t) warp * warp_words;
+  int *nsub = reinterpret_cast<int *>(code + code_words);                      // [25]
   const long long task = (long long) blockIdx.x * RPR_WARPS + warp;
   if (task >= 2LL * lvl_count * nrep) return;                                   // whole warp
   const int side = (int) (task & 1);
@@ -434,7 +437,7 @@ replay_level_row_kernel(const int *__restrict__ left, const int *__restrict__ ri
     return (uint32_t) row[u] | 0xFFFFFF00u;
   };
 
-  for (int k = lane; k < 5 * code_words + 32; k += 32) code[k] = 0u;           // (nsub included)
+  for (int k = lane; k < code_words + 32; k += 32) code[k] = 0u;               // (nsub included)
   __syncwarp();
 
   // ---- sweep 1
@@ -476,23 +479,26 @@ replay_level_row_kernel(const int *__restrict__ left, const int *__restrict__ ri
     uint32_t sd[4]; ph.block((uint32_t) v, 0x7ee1u + (uint32_t) side, 0x3041u + (uint32_t) lane, 0u, sd);
     Pcg32 rng; rng.state = ((unsigned long long) sd[0] << 32) | sd[1]; rng.inc = ((((unsigned long long) sd[2] << 32) | sd[3]) << 1) | 1ULL;
     rng.next();
+    unsigned offa = 0;                                                          // first nibble of class a's table
     #pragma unroll 1
     for (int a = 0; a < 5; a++) {
+      const unsigned o = offa;
+      offa += (unsigned) m[a];
       if (ka[a] == 0) continue;                                                 // uniform
       int c0 = nsub[a * 5], c1 = c0 + nsub[a * 5 + 1], c2 = c1 + nsub[a * 5 + 2], c3 = c2 + nsub[a * 5 + 3];   // cumulative targets
-      unsigned *tab = code + a * code_words;
       int succ = 0;
       while (succ < ka[a]) {                                                    // uniform
         const unsigned cand = __umulhi(rng.next(), (uint32_t) m[a]);
         const unsigned same = __match_any_sync(0xffffffffu, cand);
         bool ok = false;
-        const unsigned sh = (cand & 7u) * 4u;
-        if ((same & lt) == 0u) ok = !((atomicOr(&tab[cand >> 3], 8u << sh) >> sh) & 8u);   // lowest lane of its value claims the rank
+        const unsigned nibble = o + cand, sh = (nibble & 7u) * 4u;
+        unsigned *slot = code + (nibble >> 3);
+        if ((same & lt) == 0u) ok = !((atomicOr(slot, 8u << sh) >> sh) & 8u);  // lowest lane of its value claims the rank
         const unsigned bal = __ballot_sync(0xffffffffu, ok);
         if (ok) {
           const int idx = succ + __popc(bal & lt);
-          if (idx < ka[a]) atomicOr(&tab[cand >> 3], (unsigned) ((idx >= c0) + (idx >= c1) + (idx >= c2) + (idx >= c3)) << sh);
-          else             atomicAnd(&tab[cand >> 3], ~(0xFu << sh));              // more accepted than needed: give the rank back
+          if (idx < ka[a]) atomicOr(slot, (unsigned) ((idx >= c0) + (idx >= c1) + (idx >= c2) + (idx >= c3)) << sh);
+          else             atomicAnd(slot, ~(0xFu << sh));                         // more accepted than needed: give the rank back
         }
         succ += __popc(bal);
       }
@@ -510,7 +516,7 @@ replay_level_row_kernel(const int *__restrict__ left, const int *__restrict__ ri
       for (int u = lane; u < LW; u += 32) ks4[u] = __ldcg(ps4 + u);
       return;
     }
-    unsigned *rowbuf = code + 5 * code_words + 32;
+    unsigned *rowbuf = code + code_words + 32;
     for (int u = lane; u < LW; u += 32) rowbuf[(u >> ws_log2) * WSP + (u & (WS - 1))] = __ldcg(ps4 + u);
     __syncwarp();
     unsigned *seg = rowbuf + lane * WSP;
@@ -527,7 +533,13 @@ replay_level_row_kernel(const int *__restrict__ left, const int *__restrict__ ri
     unsigned long long incl = cnt;
     #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-    unsigned long long runp = incl - cnt;                                       // ranks at which this lane's segment starts
+    unsigned long long runp = incl - cnt;                                       // ranks at which this lane's segment starts ...
+    {                                                                           // ... as nibble indices into the packed table
+      unsigned long long offs = 0; unsigned o = 0;
+      #pragma unroll
+      for (int a = 0; a < 5; a++) { offs |= (unsigned long long) o << (12 * a); o += (unsigned) m[a]; }
+      runp += offs;                                                             // (first nibble + rank < L <= 4092: the 12-bit fields hold)
+    }
     for (int t = 0; t < nw; t++) {
       const uint32_t w = seg[t];
       uint32_t o = w;
@@ -537,7 +549,7 @@ replay_level_row_kernel(const int *__restrict__ left, const int *__restrict__ ri
         const unsigned rank = (unsigned) (runp >> xs) & 0xFFFu;
         runp += 1ULL << xs;
         if (x < 5u && ((kmask >> x) & 1u)) {
-          const unsigned nib = (code[x * code_words + (rank >> 3)] >> ((rank & 7u) * 4u)) & 0xFu;
+          const unsigned nib = (code[rank >> 3] >> ((rank & 7u) * 4u)) & 0xFu;
           if (nib & 8u) o = (o & ~(0xFFu << (8 * q))) | ((nib & 7u) << (8 * q));
         }
       }
@@ -549,7 +561,7 @@ replay_level_row_kernel(const int *__restrict__ left, const int *__restrict__ ri
   }
 
   // ---- sweep 2, ballot form
-  int run[5] = { 0, 0, 0, 0, 0 };
+  int run[5] = { 0, m[0], m[0] + m[1], m[0] + m[1] + m[2], m[0] + m[1] + m[2] + m[3] };   // running nibble index of every class in the packed table
   for (int u0 = 0; u0 < LW; u0 += 64) {
     uint32_t w[2];
     #pragma unroll
@@ -568,7 +580,7 @@ replay_level_row_kernel(const int *__restrict__ left, const int *__restrict__ ri
             const unsigned bal = __ballot_sync(0xffffffffu, x == a);
             if (x == a) {
               const int rank = run[a] + __popc(bal & lt);
-              const unsigned nib = (code[a * code_words + (rank >> 3)] >> ((rank & 7) * 4)) & 0xFu;
+              const unsigned nib = (code[rank >> 3] >> ((rank & 7) * 4)) & 0xFu;
               if (nib & 8u) o = (o & ~(0xFFu << (8 * q))) | ((nib & 7u) << (8 * q));
             }
             run[a] += __popc(bal);
@@ -806,11 +818,11 @@ cudaError_t rsb_launch_fitch_shuffle(const int *left, const int *right, const in
       else            replay_level_pos_kernel<1><<<grid, RPP_WARPS * 32, 0, st>>>(left, right, order, b, cnt, N, L, msa, seed, id0, ids, first_rep, nrep, anc, shanc, res);
       continue;
     }
-    const int code_words = (L + 7) / 8;
-    const size_t smem = (size_t) RPR_WARPS * (5 * code_words + 32) * sizeof(unsigned);
+    const int code_words = (L + 7) / 8 + 1;                       // one nibble per column (the classes' tables packed back to back)
+    const size_t smem = (size_t) RPR_WARPS * (code_words + 32) * sizeof(unsigned);
     int ws_log2 = 0; while ((32 << ws_log2) < L / 4) ws_log2++;   // words per lane segment (power of two)
     const bool seg = (L % 4 == 0) && L <= 4092;                   // segment form of the second sweep: 12-bit class ranks
-    const size_t smem_seg = (size_t) RPR_WARPS * (5 * code_words + 32 + 32 * ((1 << ws_log2) + 1)) * sizeof(unsigned);
+    const size_t smem_seg = (size_t) RPR_WARPS * (code_words + 32 + 32 * ((1 << ws_log2) + 1)) * sizeof(unsigned);
     if (seg && smem_seg <= 200 * 1024) {
       const unsigned grid = (unsigned) ((tasks + RPR_WARPS - 1) / RPR_WARPS);
       if (smem_seg > 48 * 1024) cudaFuncSetAttribute(replay_level_row_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_seg);
