@@ -1248,7 +1248,7 @@ static int null_hist_pipelined(rsb_ctx *ctx, const uint8_t *nulls, int nrep, int
   // (sharded grid: the one-shot all-reduce kernel has one ordered channel per statistics stream, so the chains keep their own
   // streams; if the ranks could not map each other's memory everything that talks to NCCL stays on ONE stream -- same order of
   // collectives on every rank)
-  const bool one_aux = grid_comm(ctx) && ctx->peer_state != 1;
+  const bool one_aux = grid_comm(ctx) && !(ctx->peer_state == 1 && ctx->peer_view.cap >= (size_t) 4 * ctx->L * chunk);   // (a block sized for an earlier, smaller plan: NCCL)
   cudaStream_t aux_streams[RSB_GROUPS] = { ctx->stream_aux, ctx->stream_aux2, ctx->stream_aux3, ctx->stream_aux4 };
   auto aux_of = [&](int g) -> cudaStream_t { return (serial & 1) ? sm : one_aux ? ctx->stream_aux : aux_streams[g % RSB_GROUPS]; };
 
