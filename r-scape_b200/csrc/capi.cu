@@ -1399,11 +1399,15 @@ static int null_hist_multi(rsb_ctx *ctx, const uint8_t *nulls, int nrep, int64_t
   if (ensure_geo(ctx, wgeo)) return 1;
   Geo &g = ctx->geo[wgeo];
   const bool in_place = (on_device && row_stride == ctx->L && rep_stride == (int64_t) ctx->N * ctx->L);
-  const int  G = (ctx->Rcap >= 2) ? 2 : 1;
+  // slot groups as in null_hist_pipelined: the reductions + correction/histogram chain of a chunk (one launch each for all its
+  // statistics and combinations) runs beside the following contractions and has G - 1 of them to finish in
+  static const int gmax = getenv("RSCAPE_B200_GROUPS") ? std::min(RSB_GROUPS, std::max(1, atoi(getenv("RSCAPE_B200_GROUPS")))) : RSB_GROUPS;
+  const int  G = std::min(gmax, (ctx->Rcap % 4 == 0 && ctx->Rcap >= 4) ? 4 : (ctx->Rcap % 3 == 0 && ctx->Rcap >= 3) ? 3 : (ctx->Rcap >= 2) ? 2 : 1);
   const int  chunk = std::max(1, ctx->Rcap / G);
   const size_t repbytes = (size_t) ctx->N * ctx->L, LL = (size_t) ctx->L * ctx->Lp;
   cudaStream_t sm = ctx->stream_hi, st_copy = ctx->stream_copy;
-  auto aux_of = [&](int gi) -> cudaStream_t { return (gi & 1) ? ctx->stream_aux2 : ctx->stream_aux; };
+  cudaStream_t aux_streams[RSB_GROUPS] = { ctx->stream_aux, ctx->stream_aux2, ctx->stream_aux3, ctx->stream_aux4 };
+  auto aux_of = [&](int gi) -> cudaStream_t { return aux_streams[gi % RSB_GROUPS]; };
   const size_t need = (size_t) nrep * ncombo;
   if (ctx->h_mm_cap < need) {
     if (ctx->h_mm) cudaFreeHost(ctx->h_mm);
@@ -1415,10 +1419,9 @@ static int null_hist_multi(rsb_ctx *ctx, const uint8_t *nulls, int nrep, int64_t
   RSB_CUDA_OK(cudaStreamWaitEvent(sm, ctx->ev_entry, 0));
   RSB_CUDA_OK(cudaMemcpyAsync(ctx->d_wm, w, sizeof(double) * ncombo, cudaMemcpyHostToDevice, sm));
   RSB_CUDA_OK(cudaEventRecord(ctx->ev_entry, sm));
-  RSB_CUDA_OK(cudaStreamWaitEvent(ctx->stream_aux, ctx->ev_entry, 0));
-  RSB_CUDA_OK(cudaStreamWaitEvent(ctx->stream_aux2, ctx->ev_entry, 0));
+  for (int g = 0; g < RSB_GROUPS; g++) RSB_CUDA_OK(cudaStreamWaitEvent(aux_streams[g], ctx->ev_entry, 0));
   RSB_CUDA_OK(cudaStreamWaitEvent(st_copy, ctx->ev_entry, 0));
-  bool used[2] = { false, false };
+  bool used[RSB_GROUPS] = { false, false, false, false };
   int nJT, nIT; rsb_stat_grid(ctx->L, &nJT, &nIT);
 
   // S(pc): all statistics of chunk pc in one pass on the main stream (FP64: alone between two contractions), then on the aux
