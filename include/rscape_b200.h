@@ -177,6 +177,9 @@ int rsb_pool_broadcast(rsb_ctx *ctx, int first_rep, int nrep, int root);
  * (cudaIpc between processes, peer access inside one), else by ncclAllReduce; RSCAPE_B200_PEER_REDUCE=0 forces NCCL.
  * *peer_path = 1 when the kernel is in use, *reductions = all-reduces it has done so far. */
 int rsb_comm_info(rsb_ctx *ctx, int *nranks, int *rank, int *peer_path, int64_t *reductions);
+/* self-test and latency of that all-reduce (collective): `count` doubles summed once and checked (*max_err, 0 expected), then
+ * all-reduced `iters` times between two CUDA events (*us_per_allreduce, device time) */
+int rsb_comm_selftest(rsb_ctx *ctx, int count, int iters, double *us_per_allreduce, double *max_err);
 int rsb_hist_allreduce(rsb_ctx *ctx, int nb);
 /* in place: lo = min over ranks, hi = max over ranks, aux_min (may be NULL) = min over ranks */
 int rsb_comm_range(rsb_ctx *ctx, double *lo, double *hi, double *aux_min);

@@ -118,6 +118,7 @@ def lib():
         L.rsb_comm_destroy.argtypes = [_vp]
         L.rsb_comm_info.argtypes = [_vp, _ip, _ip, _ip, _i64p]
         L.rsb_pool_broadcast.argtypes = [_vp, C.c_int, C.c_int, C.c_int]
+        L.rsb_comm_selftest.argtypes = [_vp, C.c_int, C.c_int, _dp, _dp]
         L.rsb_hist_allreduce.argtypes = [_vp, C.c_int]
         L.rsb_comm_range.argtypes = [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.rsb_sharded_scan.argtypes = [_vp, _vp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.c_double, _dp, _dp, _dp]
@@ -376,6 +377,12 @@ class Context:
     def pool_broadcast(self, first_rep, nrep, root):
         """Pool entries generated by rank `root` made resident on every rank of the communicator (collective)."""
         self._ck(lib().rsb_pool_broadcast(self._h, first_rep, nrep, root))
+
+    def comm_selftest(self, count, iters=200):
+        """(microseconds per all-reduce of `count` doubles, largest error of a checked sum) -- collective."""
+        us, err = C.c_double(), C.c_double()
+        self._ck(lib().rsb_comm_selftest(self._h, count, iters, C.byref(us), C.byref(err)))
+        return us.value, err.value
 
     def comm_info(self):
         """dict(nranks, rank, peer_path, reductions): peer_path = the small per-scan all-reduces go through the one-shot kernel

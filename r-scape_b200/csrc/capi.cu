@@ -2367,6 +2367,47 @@ int rsb_comm_info(rsb_ctx *ctx, int *nranks, int *rank, int *peer_path, int64_t 
   return 0;
 }
 
+/* Self-test and latency of the small all-reduce (collective: every rank calls it with the same arguments).  A vector of `count`
+ * doubles with rank-dependent contents is summed over the ranks once and checked against the closed form (*max_err = largest
+ * deviation; 0 expected: the values are small integers), then all-reduced `iters` times (MAX, so that the values stay put)
+ * between two CUDA events: *us_per_allreduce = mean device time of one all-reduce on the path rsb_comm_info reports. */
+int rsb_comm_selftest(rsb_ctx *ctx, int count, int iters, double *us_per_allreduce, double *max_err)
+{
+  RSB_CUDA_OK(cudaSetDevice(ctx->device));
+  if (!ctx->comm || ctx->comm_size < 2) { rsb_set_error(ctx, "rsb_comm_selftest: no communicator of at least two ranks"); return 1; }
+  if (count < 1 || iters < 1) { rsb_set_error(ctx, "rsb_comm_selftest: bad arguments"); return 1; }
+  std::vector<double> h((size_t) count);
+  for (int i = 0; i < count; i++) h[i] = (double) ((ctx->comm_rank + 1) * (i % 7 + 1));
+  double *d = nullptr;
+  RSB_CUDA_OK(cudaMalloc(&d, sizeof(double) * (size_t) count));
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  int rc = 1;
+  float ms = 0.f;
+  double err = 0.0;
+  const double tot = 0.5 * ctx->comm_size * (ctx->comm_size + 1);
+  if (cudaMemcpyAsync(d, h.data(), sizeof(double) * (size_t) count, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) goto done;
+  if (comm_allreduce(ctx, d, (size_t) count, rsb_nccl::ncclFloat64, rsb_nccl::ncclSum, ctx->stream)) goto done;
+  if (cudaMemcpyAsync(h.data(), d, sizeof(double) * (size_t) count, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) goto done;
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) goto done;
+  for (int i = 0; i < count; i++) err = std::max(err, std::fabs(h[i] - tot * (i % 7 + 1)));
+  if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) goto done;
+  for (int k = 0; k < 3; k++) if (comm_allreduce(ctx, d, (size_t) count, rsb_nccl::ncclFloat64, rsb_nccl::ncclMax, ctx->stream)) goto done;   // warm-up
+  cudaEventRecord(e0, ctx->stream);
+  for (int k = 0; k < iters; k++) if (comm_allreduce(ctx, d, (size_t) count, rsb_nccl::ncclFloat64, rsb_nccl::ncclMax, ctx->stream)) goto done;
+  cudaEventRecord(e1, ctx->stream);
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) goto done;
+  cudaEventElapsedTime(&ms, e0, e1);
+  if (us_per_allreduce) *us_per_allreduce = 1e3 * (double) ms / iters;
+  if (max_err) *max_err = err;
+  rc = 0;
+done:
+  if (rc && !ctx->err[0]) rsb_set_error(ctx, "rsb_comm_selftest: %s", cudaGetErrorString(cudaGetLastError()));
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  cudaFree(d);
+  return rc;
+}
+
 int rsb_comm_destroy(rsb_ctx *ctx)
 {
   if (ctx->comm) {
