@@ -2378,8 +2378,10 @@ int rsb_comm_selftest(rsb_ctx *ctx, int count, int iters, double *us_per_allredu
   if (count < 1 || iters < 1) { rsb_set_error(ctx, "rsb_comm_selftest: bad arguments"); return 1; }
   std::vector<double> h((size_t) count);
   for (int i = 0; i < count; i++) h[i] = (double) ((ctx->comm_rank + 1) * (i % 7 + 1));
-  double *d = nullptr;
-  RSB_CUDA_OK(cudaMalloc(&d, sizeof(double) * (size_t) count));
+  // (no cudaMalloc / cudaFree here: with peer access enabled they synchronise the peer devices, and a peer whose all-reduce kernel
+  // is waiting for THIS rank would never go idle.  The plan's scratch matrix serves.)
+  if (ctx->L <= 0 || !ctx->d_tmp || (size_t) count > (size_t) ctx->L * ctx->Lp) { rsb_set_error(ctx, "rsb_comm_selftest: configure a plan with L * L >= count first"); return 1; }
+  double *d = ctx->d_tmp;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   int rc = 1;
   float ms = 0.f;
@@ -2404,7 +2406,6 @@ done:
   if (rc && !ctx->err[0]) rsb_set_error(ctx, "rsb_comm_selftest: %s", cudaGetErrorString(cudaGetLastError()));
   if (e0) cudaEventDestroy(e0);
   if (e1) cudaEventDestroy(e1);
-  cudaFree(d);
   return rc;
 }
 
