@@ -9,12 +9,22 @@ that width pass on the same replicate 0, so no broadcast is needed to agree on w
 import numpy as np
 
 
-def null_shard(nnull, world, rank):
+def null_shard(nnull, world, rank, last_rank_extra=0):
     """Replicate ids scanned by `rank`: one contiguous block per rank (so that a generator call covers it), sizes
-    floor or ceil of nnull/world."""
-    base, extra = divmod(nnull, world)
-    first = rank * base + min(rank, extra)
-    return list(range(first, first + base + (1 if rank < extra else 0)))
+    floor or ceil of nnull/world.
+
+    last_rank_extra: work the LAST rank carries besides its nulls, in units of one null -- the rank that also scans the
+    input alignment (run_rscape(GIVSS), src/R-scape.c:2548) gets that many nulls fewer, the others share them.  The
+    blocks stay contiguous and cover 0..nnull-1 exactly once."""
+    if last_rank_extra <= 0 or world == 1:
+        base, extra = divmod(nnull, world)
+        first = rank * base + min(rank, extra)
+        return list(range(first, first + base + (1 if rank < extra else 0)))
+    share = (nnull + last_rank_extra) / world                       # units of work per rank
+    n_last = int(min(nnull, max(0, round(share - last_rank_extra))))
+    if rank == world - 1:
+        return list(range(nnull - n_last, nnull))
+    return [r for r in null_shard(nnull - n_last, world - 1, rank)]
 
 
 def reduce_histogram(bins, device=None, group=None):

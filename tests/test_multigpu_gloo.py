@@ -133,3 +133,17 @@ def test_shard_covers_every_replicate_once(pkg):
             assert got == list(range(R))
             sizes = [len(pkg.parallel.null_shard(R, world, k)) for k in range(world)]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_null_shard_with_extra_work_on_the_last_rank(pkg):
+    """The rank that also scans the input alignment takes fewer nulls (bench.py: last_rank_extra=2): blocks stay contiguous, cover
+    every replicate once, and the largest block -- which sets the job's time with resident nulls -- is the even split's."""
+    for R in (100, 20, 13, 1):
+        for world in (1, 2, 4, 8):
+            blocks = [pkg.parallel.null_shard(R, world, k, last_rank_extra=2) for k in range(world)]
+            assert sum(blocks, []) == list(range(R))
+            even = [len(pkg.parallel.null_shard(R, world, k)) for k in range(world)]
+            assert len(blocks[-1]) <= even[-1]
+            if world > 1:
+                scans = max([len(b) for b in blocks[:-1]] + [len(blocks[-1]) + 1])
+                assert scans <= max(even[:-1] + [even[-1] + 1])
