@@ -420,6 +420,12 @@ def main():
             range of the first null below 20) is the loop repeated with it -- the histogram is then exactly the reference's."""
             tp = [time.perf_counter()] if PHASES else None
             ctx.hist_reset()
+            out = None
+            if not args.grid_shard and rank == real_rank:
+                # run_rscape(GIVSS): independent of the nulls, and done BEFORE the ranks meet in the width agreement below, so that the
+                # others do not wait for it
+                out = ctx.scan(real, STAT, pkg.C16, ACT, want_cov=isinstance(real, np.ndarray), cov_out=cov_out)
+            if PHASES: tp.append(time.perf_counter())
             w = W0
             for attempt in range(2):
                 lo, hi, w_true = np.inf, -np.inf, np.inf
@@ -437,11 +443,8 @@ def main():
                 w = w_true                                                                   # rare: redo with the width of replicate 0
                 ctx.hist_reset()
             if PHASES: tp.append(time.perf_counter())
-            out = None
             if args.grid_shard:
                 out = ctx.sharded_scan(real, STAT, pkg.C16, ACT, want_cov=isinstance(real, np.ndarray), cov_out=cov_out)
-            elif rank == real_rank:
-                out = ctx.scan(real, STAT, pkg.C16, ACT, want_cov=isinstance(real, np.ndarray), cov_out=cov_out)   # run_rscape(GIVSS)
             if PHASES: tp.append(time.perf_counter())
             # sum over ranks and read only the bins the null scores reach: bin of the largest score + cov_GrowRankList's 5 w margin
             nb = int(min(1 << 22, max(64, np.ceil((hi - BMIN) / w) + 8))) if (w > 0 and np.isfinite(hi)) else 64
@@ -450,7 +453,7 @@ def main():
             bins, n, imax = ctx.hist_read(nb, out=bins_pinned)
             if PHASES:
                 tp.append(time.perf_counter())
-                print("[bench] rank %d phases ms: nulls %.2f input %.2f hist %.2f" % ((rank,) + tuple((b - a) * 1e3 for a, b in zip(tp, tp[1:]))),
+                print("[bench] rank %d phases ms: input %.2f nulls %.2f sharded input %.2f hist %.2f" % ((rank,) + tuple((b - a) * 1e3 for a, b in zip(tp, tp[1:]))),
                       file=sys.stderr, flush=True)
             return w, bins, out
 
