@@ -392,6 +392,12 @@ typedef struct esl_getopts_s ESL_GETOPTS;
 typedef struct esl_sqfile_s  ESL_SQFILE;
 typedef struct esl_msafile_s ESL_MSAFILE;
 typedef struct esl_fileparser_s ESL_FILEPARSER;
+/* whitespace-delimited token files (esl_fileparser): what cov_ReadNullHistogram (--givennull, src/covariation.c:1718-1843) reads with */
+extern int  esl_fileparser_Open(const char *filename, const char *envvar, ESL_FILEPARSER **ret_efp);
+extern int  esl_fileparser_SetCommentChar(ESL_FILEPARSER *efp, char c);
+extern int  esl_fileparser_NextLine(ESL_FILEPARSER *efp);
+extern int  esl_fileparser_GetTokenOnLine(ESL_FILEPARSER *efp, char **opt_tok, int *opt_toklen);
+extern void esl_fileparser_Close(ESL_FILEPARSER *efp);
 /* tail fits of the null histogram (src/covariation.c:1915-1973), restated in easel_shim_fit.c */
 extern double esl_exp_generic_surv(double x, void *params);
 extern double esl_gam_generic_surv(double x, void *params);

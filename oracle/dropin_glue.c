@@ -77,3 +77,33 @@ dropin_cov_calculate(int nseq, int L, const uint8_t *res, const double *wgt, int
   free(msa2pdb); free(msamap);
   return status;
 }
+
+
+/* --savenull / --givennull (src/R-scape.c:2466, 2480): the reference's own cov_WriteNullHistogram and cov_ReadNullHistogram
+ * (src/covariation.c:1845-1866, 1718-1843), unmodified, on a cumulative null histogram as the B200 null loop leaves it
+ * (bmin, w, integer bins).  The list is built by the reference's cov_CreateRankList; the file is then read back by the reference's
+ * reader.  out_meta: { bmin, bmax, w, xmin, xmax } of the list read back; out_imeta: { nb, imin, imax }; its bins go to out_bins. */
+int
+dropin_null_histogram_roundtrip(const char *path, double bmin, double w, int nb, const uint64_t *bins,
+                                double *out_meta, int *out_imeta, uint64_t *out_n, uint64_t *out_bins, int out_cap)
+{
+  RANKLIST *rl = cov_CreateRankList(bmin + nb * w, bmin, w), *back = NULL;
+  int       b, status = eslFAIL;
+  dropin_err[0] = 0;
+  if (rl == NULL) return eslEMEM;
+  for (b = 0; b < nb && b < rl->ha->nb; b++) {
+    rl->ha->obs[b] = bins[b];
+    rl->ha->n += bins[b]; rl->ha->Nc += bins[b]; rl->ha->No += bins[b];
+    if (bins[b]) { if (b < rl->ha->imin) rl->ha->imin = b; if (b > rl->ha->imax) rl->ha->imax = b; }
+  }
+  if ((status = cov_WriteNullHistogram((char *) path, rl, dropin_err, FALSE)) != eslOK) goto DONE;
+  if ((status = cov_ReadNullHistogram((char *) path, &back, dropin_err, FALSE)) != eslOK) goto DONE;
+  out_meta[0] = back->ha->bmin; out_meta[1] = back->ha->bmax; out_meta[2] = back->ha->w; out_meta[3] = back->ha->xmin; out_meta[4] = back->ha->xmax;
+  out_imeta[0] = back->ha->nb; out_imeta[1] = back->ha->imin; out_imeta[2] = back->ha->imax;
+  *out_n = back->ha->n;
+  for (b = 0; b < back->ha->nb && b < out_cap; b++) out_bins[b] = back->ha->obs[b];
+ DONE:
+  if (back) cov_FreeRankList(back);
+  cov_FreeRankList(rl);
+  return status;
+}

@@ -705,3 +705,89 @@ esl_histogram_Add(ESL_HISTOGRAM *h, double x)
   if (x < h->xmin) h->xmin = x;
   return eslOK;
 }
+
+/* ------------------------------------------------------------------ esl_fileparser (the subset R-scape's readers use)
+ * Lines of whitespace-delimited tokens; everything from the comment character to the end of a line is skipped, and so are
+ * lines without a token.  esl_fileparser_NextLine moves to the next line that holds a token (eslEOF at the end of the file),
+ * esl_fileparser_GetTokenOnLine hands out its tokens one by one (eslEOL when the line is used up).  The token points into the
+ * parser's line buffer and stays valid until the next NextLine. */
+struct esl_fileparser_s { FILE *fp; char *buf; size_t cap; char *pos; char comment; };
+
+int
+esl_fileparser_Open(const char *filename, const char *envvar, ESL_FILEPARSER **ret_efp)
+{
+  ESL_FILEPARSER *efp;
+  (void) envvar;
+  *ret_efp = NULL;
+  if ((efp = calloc(1, sizeof(*efp))) == NULL) return eslEMEM;
+  if ((efp->fp = fopen(filename, "r")) == NULL) { free(efp); return eslENOTFOUND; }
+  *ret_efp = efp;
+  return eslOK;
+}
+
+int
+esl_fileparser_SetCommentChar(ESL_FILEPARSER *efp, char c)
+{
+  efp->comment = c;
+  return eslOK;
+}
+
+static int
+fileparser_readline(ESL_FILEPARSER *efp)
+{
+  size_t n = 0;
+  int    c;
+  while ((c = fgetc(efp->fp)) != EOF) {
+    if (n + 2 > efp->cap) {
+      size_t cap = efp->cap ? 2 * efp->cap : 256;
+      char  *p = realloc(efp->buf, cap);
+      if (p == NULL) return eslEMEM;
+      efp->buf = p; efp->cap = cap;
+    }
+    if (c == '\n') break;
+    efp->buf[n++] = (char) c;
+  }
+  if (c == EOF && n == 0) return eslEOF;
+  if (efp->buf == NULL) { if ((efp->buf = malloc(256)) == NULL) return eslEMEM; efp->cap = 256; }
+  efp->buf[n] = 0;
+  if (efp->comment) { char *h = strchr(efp->buf, efp->comment); if (h) *h = 0; }
+  efp->pos = efp->buf;
+  return eslOK;
+}
+
+int
+esl_fileparser_NextLine(ESL_FILEPARSER *efp)
+{
+  int status;
+  while ((status = fileparser_readline(efp)) == eslOK) {
+    char *p = efp->pos;
+    while (*p == ' ' || *p == '\t' || *p == '\r') p++;
+    if (*p) { efp->pos = p; return eslOK; }          /* a line with at least one token */
+  }
+  return status;
+}
+
+int
+esl_fileparser_GetTokenOnLine(ESL_FILEPARSER *efp, char **opt_tok, int *opt_toklen)
+{
+  char *p = efp->pos, *t;
+  if (p == NULL) return eslEOL;
+  while (*p == ' ' || *p == '\t' || *p == '\r') p++;
+  if (*p == 0) { efp->pos = p; return eslEOL; }
+  t = p;
+  while (*p && *p != ' ' && *p != '\t' && *p != '\r') p++;
+  if (opt_toklen) *opt_toklen = (int) (p - t);
+  if (*p) { *p = 0; p++; }
+  efp->pos = p;
+  if (opt_tok) *opt_tok = t;
+  return eslOK;
+}
+
+void
+esl_fileparser_Close(ESL_FILEPARSER *efp)
+{
+  if (efp == NULL) return;
+  if (efp->fp) fclose(efp->fp);
+  free(efp->buf);
+  free(efp);
+}
