@@ -199,7 +199,7 @@ slots_for(int nseq, int alen, int nnull)
   double bytes = 24.0 * alen * (double) nseq + 16.0 * 8.0 * alen * (double) alen + 3.0 * 8.0 * alen * (double) alen + (double) nseq * alen;
   int    r = (int) ceil(4.0 * 148.0 / tiles);
   int    rmem = (int) (24e9 / bytes);
-  if (r < 2) r = 2;                     /* two slot groups: statistics of one chunk overlap the contraction of the next */
+  if (r < 4) r = 4;                     /* four slot groups: the statistics chain of a chunk has three contractions to finish in */
   if (r > rmem) r = rmem;
   if (r > nnull && nnull >= 2) r = nnull;
   if (r > 64) r = 64;
@@ -227,7 +227,7 @@ null_worker_run(void *arg)
   rsb_ctx  *ctx = NULL;
   uint8_t  *stage = NULL;
   size_t    N = (size_t) mi->nseq, L = (size_t) mi->alen;
-  int       nmine = wk->r1 - wk->r0, slots, r0, r, s, imax;
+  int       nmine = wk->r1 - wk->r0, slots, batch, r0, r, s, imax;
   double    hi = -eslINFINITY;
 
   wk->status = eslFAIL; wk->err[0] = 0; wk->bins = NULL; wk->nb = 0; wk->n_added = 0;
@@ -240,9 +240,14 @@ null_worker_run(void *arg)
       rsb_set_weights(ctx, wk->nulls[0]->wgt) != 0 ||                              /* nulls carry the input's weights (:1668) */
       (data->msa2pdb && rsb_set_pair_exclusion(ctx, data->msa2pdb, RSB_DATA_MIND(data)) != 0))   /* covariation.c:421-427 */
     { snprintf(wk->err, eslERRBUFSIZE, "%s", rsb_error(ctx)); goto DONE; }
-  if ((stage = malloc((size_t) slots * N * L)) == NULL) { snprintf(wk->err, eslERRBUFSIZE, "allocation failed"); goto DONE; }
-  for (r0 = wk->r0; r0 < wk->r1; r0 += slots) {
-    int n = ESL_MIN(slots, wk->r1 - r0);
+  /* nulls handed to one rsb_null_hist call: the pipeline over the slot groups fills and drains once per call, so a call carries up
+   * to 32 of them (at most 1 GB of staging), not just one per slot */
+  batch = ESL_MIN(nmine, 32);
+  while (batch > slots && (double) batch * (double) N * (double) L > 1e9) batch /= 2;
+  if (batch < slots) batch = ESL_MIN(slots, ESL_MAX(nmine, 1));
+  if ((stage = malloc((size_t) batch * N * L)) == NULL) { snprintf(wk->err, eslERRBUFSIZE, "allocation failed"); goto DONE; }
+  for (r0 = wk->r0; r0 < wk->r1; r0 += batch) {
+    int n = ESL_MIN(batch, wk->r1 - r0);
     for (r = 0; r < n; r++)
       for (s = 0; s < (int) N; s++) memcpy(stage + ((size_t) r * N + (size_t) s) * L, wk->nulls[r0 + r]->ax[s] + 1, L);
     if (rsb_null_hist(ctx, stage, n, (int64_t) L, (int64_t) (N * L), 0, wk->base, wk->cls, wk->corr, wk->ap,
