@@ -1205,11 +1205,11 @@ int rsb_null_width(rsb_ctx *ctx, const uint8_t *null0, int64_t row_stride, int o
   return 0;
 }
 
-// The null loop, software-pipelined over two groups of replicate slots and three streams:
-//   copy stream : alignments of chunk c+1 -> slots (host buffers only), then pack into operand planes   (HBM)
-//   main stream : tcgen05 gram of chunk c                    (tensor pipe)
-//   aux stream  : marginals, statistic, correction, histogram of chunk c-1   (FP64 / HBM)
-// so the FP64 statistics of one chunk hide under the tensor-core contraction of the next.  Events order the
+// The null loop, software-pipelined over up to four groups of replicate slots (chunk c lives in group c mod G):
+//   copy stream      : alignments of chunk c+1 -> slots (host buffers only), then pack into operand planes   (HBM)
+//   main stream      : tcgen05 gram of chunk c                    (tensor pipe)
+//   aux stream c%G   : marginals, statistic, correction, histogram of chunk c   (latency-bound small kernels beside the contractions)
+// so the statistics chain of one chunk hides under the tensor-core contractions of the next G - 1.  Events order the
 // reuse of each slot group; the caller's stream (main) waits for everything before the call returns.
 // src_dev: device-resident nulls [nrep][N][L] read in place (no copy), else host/strided input that is uploaded.
 static int null_hist_pipelined(rsb_ctx *ctx, const uint8_t *nulls, int nrep, int64_t row_stride, int64_t rep_stride, int on_device,
